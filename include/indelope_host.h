@@ -1,0 +1,110 @@
+/* include/indelope_host.h -- C ABI of libindelope_host.so
+ *
+ * C++ stand-in for the parts of indelope that stay on the host (the reference keeps them in Nim; no Nim
+ * toolchain exists in this image, see DESIGN.md / INTEGRATION.md):
+ *   - the BAM sweep -> evidence counters -> coverage-gap chunking -> regions of interest
+ *     (src/indelope.nim:430-545: event_locations, overlaps, gen_roi_internal, cache_t, gen_roi)
+ *   - read quality trim and batch packing for libindelope_cuda.so (src/indelope.nim:23-38,169)
+ *   - the filter cascade, genotype likelihoods and VCF text over the device results
+ *     (src/indelope.nim:49-116,375-428,598-608; src/genotyper.nim:16-47)
+ *   - a seeded synthetic data generator with an aligner model (no aligner / BAM library is installed)
+ * This library contains no CUDA and does not link the oracle.
+ */
+#ifndef INDELOPE_HOST_H
+#define INDELOPE_HOST_H
+#include <stdint.h>
+#include "indelope_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* regions of interest in the shape gen_roi yields them, flattened (`roi = tuple[start, stop, reads]`,
+ * src/indelope.nim:21).  Reads are referenced by index so a read shared by two regions is stored once. */
+typedef struct idlh_roiset {
+	int64_t n_reads;
+	const int32_t *start;
+	const int32_t *stop;
+	const uint8_t *mapq;
+	const uint16_t *flag;
+	const int32_t *len;
+	const int64_t *seq_off;
+	const uint8_t *bases;     /* ASCII */
+	const uint8_t *quals;
+	int64_t n_rois;
+	const int32_t *roi_chrom;
+	const int32_t *roi_start, *roi_stop;
+	const int64_t *roi_read_begin;
+	const int32_t *roi_n_reads;
+	const int64_t *read_idx;
+	int32_t n_chroms;
+	const char *const *chrom_name;
+	const uint8_t *const *chrom_seq;
+	const int64_t *chrom_len;
+} idlh_roiset;
+
+typedef struct idlh_synth_params {
+	uint64_t seed;
+	int32_t n_chroms;
+	int64_t chrom_len;
+	int32_t n_events;           /* planted events per chromosome */
+	int32_t min_indel, max_indel;
+	double coverage;
+	int32_t read_len;
+	double sub_rate;            /* substitution errors per base */
+	double tr_fraction;         /* share of events that are tandem-repeat expansions/contractions */
+	int32_t tr_max_unit;        /* repeat unit 1..tr_max_unit bp */
+	double het_fraction;
+	double lowq_tail_fraction;  /* reads with a Q2 tail of 1-15 bases */
+	double low_mapq_fraction;   /* reads with MAPQ in {0,5,10,19} */
+	double dup_fraction;        /* reads flagged duplicate (skippable) */
+	double n_base_rate;         /* read bases replaced by N */
+	int32_t locus_only;         /* 1: simulate reads only within locus_flank of planted events */
+	int32_t locus_flank;
+	int32_t max_cigar_indel;    /* aligner model: longer indels are soft-clipped [30] */
+	int32_t min_cigar_flank;    /* aligner model: shorter flanks are soft-clipped [20] */
+} idlh_synth_params;
+
+void idlh_default_synth(idlh_synth_params *p);
+
+typedef struct idlh_dataset idlh_dataset;   /* reference + coordinate-sorted reads with CIGARs */
+typedef struct idlh_rois idlh_rois;         /* owns the arrays behind an idlh_roiset */
+
+idlh_dataset *idlh_synth(const idlh_synth_params *p);
+void idlh_dataset_free(idlh_dataset *d);
+/* counts[0]=reads, [1]=bases, [2]=events planted, [3]=chroms */
+void idlh_dataset_counts(const idlh_dataset *d, int64_t counts[4]);
+/* truth table: chrom, pos, ins_len, del_len, hom, is_tr (6 int64 per event) */
+int64_t idlh_dataset_truth(const idlh_dataset *d, int64_t *out, int64_t cap);
+
+/* gen_roi over every target (src/indelope.nim:515-545,601-602), regions in emission order */
+idlh_rois *idlh_sweep(const idlh_dataset *d, int32_t min_event_support, int32_t min_read_coverage, int32_t max_read_coverage);
+void idlh_rois_free(idlh_rois *r);
+const idlh_roiset *idlh_rois_view(const idlh_rois *r);
+
+/* quality trim of src/indelope.nim:23-38: returns a, *trim_len = kept bases */
+int32_t idlh_trim(const uint8_t *quals, int32_t n, int32_t *trim_len);
+
+/* batch sizing / packing of regions [lo, hi) */
+void idlh_pack_size(const idlh_roiset *rs, int64_t lo, int64_t hi, const idl_params *p, size_t *n_reads, size_t *n_seq_bases, size_t *n_ref_bases);
+int idlh_pack(const idlh_roiset *rs, int64_t lo, int64_t hi, const idl_params *p, idl_batch *out);
+/* plain-malloc batch for CPU-only inspection/tests (idl_batch_alloc gives pinned memory) */
+idl_batch *idlh_batch_alloc_host(size_t max_regions, size_t max_reads, size_t max_seq_bases, size_t max_ref_bases);
+void idlh_batch_free_host(idl_batch *b);
+/* unpack one packed record back to ASCII (round-trip tests) */
+void idlh_unpack(const uint32_t *pool2, const uint32_t *pooln, uint64_t base_off, int32_t n, char *out);
+
+/* VCF writer: header, then records through the filter cascade with the order-dependent dedup state of
+ * src/indelope.nim:598-608 carried across batches */
+typedef struct idlh_vcf idlh_vcf;
+idlh_vcf *idlh_vcf_new(void);
+void idlh_vcf_free(idlh_vcf *w);
+char *idlh_vcf_header(const idlh_roiset *rs);   /* malloc'ed; free with idlh_free */
+/* records for regions [lo, lo + res->n_regions) of rs; malloc'ed text; dump_level as the oracle's (0 = VCF only) */
+char *idlh_vcf_records(idlh_vcf *w, const idlh_roiset *rs, int64_t lo, const idl_params *p, const idl_results *res, int32_t dump_level, char **dump);
+void idlh_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

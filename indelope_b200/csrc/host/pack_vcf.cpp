@@ -1,0 +1,377 @@
+// indelope_b200/csrc/host/pack_vcf.cpp
+//
+// Host side of the drop-in boundary:
+//   * quality trim (src/indelope.nim:23-38), min_overlap (:169), 2-bit packing of reads and of the reference
+//     window into an idl_batch (include/indelope_cuda.h)
+//   * after the device pass: the filter cascade, genotype likelihoods and VCF text of
+//     src/indelope.nim:375-428,49-116 and src/genotyper.nim:16-47, with the order-dependent dedup of
+//     src/indelope.nim:598-608.  Float64 maths stays here, exactly as in the reference's host.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "indelope_host.h"
+
+namespace {
+
+inline unsigned code_of(uint8_t ch) // src/ksw2/ksw2.nim:127 lookup: ACGT/acgt -> 0..3, anything else 4
+{
+	switch (ch) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; }
+}
+
+// append n ASCII bases at base offset `off` (multiple of 64) of the pools; pools are zeroed beforehand
+void pack_bases(uint32_t *pool2, uint32_t *pooln, uint64_t off, const uint8_t *s, int64_t n)
+{
+	for (int64_t i = 0; i < n; ++i) {
+		unsigned c = code_of(s[i]);
+		uint64_t b = off + (uint64_t)i;
+		if (c > 3) pooln[b >> 5] |= 1u << (b & 31);
+		else pool2[b >> 4] |= c << (2 * (b & 15));
+	}
+}
+
+inline uint64_t round64(uint64_t x) { return (x + 63) & ~(uint64_t)63; }
+
+struct Win { int64_t ws, we, max_stop; };
+
+Win region_window(const idlh_roiset *rs, int64_t k, const idl_params *p, std::vector<int32_t> *ta, std::vector<int32_t> *tl)
+{
+	Win w; w.ws = INT64_MAX; w.max_stop = -1; int64_t far = -1;
+	for (int32_t j = 0; j < rs->roi_n_reads[k]; ++j) {
+		int64_t i = rs->read_idx[rs->roi_read_begin[k] + j];
+		int32_t n; int32_t a = idlh_trim(rs->quals + rs->seq_off[i], rs->len[i], &n);
+		if (ta) { ta->push_back(a); tl->push_back(n); }
+		w.ws = std::min<int64_t>(w.ws, (int64_t)rs->start[i] + a);
+		far = std::max<int64_t>(far, (int64_t)rs->start[i] + a + n);
+		if (rs->mapq[i] > p->stop_min_mapq) w.max_stop = std::max<int64_t>(w.max_stop, rs->stop[i]);
+	}
+	if (w.ws == INT64_MAX) w.ws = 0;
+	if (w.ws < 0) w.ws = 0;
+	w.we = std::min<int64_t>(rs->chrom_len[rs->roi_chrom[k]] - 1, std::max(far, w.max_stop) + p->window_pad);
+	return w;
+}
+
+} // namespace
+
+extern "C" {
+
+int32_t idlh_trim(const uint8_t *bq, int32_t n, int32_t *trim_len) // src/indelope.nim:23-38
+{
+	const int32_t high = n - 1, min_quality = 15;
+	int32_t a = 0;
+	while (a < high && bq[a] < min_quality) a += 1;
+	if (a == high || n <= 0) { *trim_len = 0; return n <= 0 ? 0 : a; }
+	int32_t b = high;
+	while (b > a && bq[b] < min_quality) b -= 1;
+	*trim_len = b - a + 1;
+	return a;
+}
+
+void idlh_pack_size(const idlh_roiset *rs, int64_t lo, int64_t hi, const idl_params *p, size_t *n_reads, size_t *n_seq_bases, size_t *n_ref_bases)
+{
+	size_t nr = 0, sb = 0, rb = 0;
+	for (int64_t k = lo; k < hi; ++k) {
+		nr += (size_t)rs->roi_n_reads[k];
+		for (int32_t j = 0; j < rs->roi_n_reads[k]; ++j) sb += round64((uint64_t)rs->len[rs->read_idx[rs->roi_read_begin[k] + j]]);
+		Win w = region_window(rs, k, p, nullptr, nullptr);
+		rb += round64((uint64_t)std::max<int64_t>(0, w.we - w.ws + 1));
+	}
+	*n_reads = nr; *n_seq_bases = sb; *n_ref_bases = rb;
+}
+
+int idlh_pack(const idlh_roiset *rs, int64_t lo, int64_t hi, const idl_params *p, idl_batch *b)
+{
+	size_t nr, sb, rb;
+	idlh_pack_size(rs, lo, hi, p, &nr, &sb, &rb);
+	if ((size_t)(hi - lo) > b->cap_regions || nr > b->cap_reads || sb > b->cap_seq_bases || rb > b->cap_ref_bases) return IDL_E_CAPACITY;
+	memset(b->seq2, 0, sb / 4); memset(b->seqn, 0, sb / 8);
+	memset(b->ref2, 0, rb / 4); memset(b->refn, 0, rb / 8);
+	uint64_t soff = 0, roff = 0; uint32_t ri = 0;
+	std::vector<int32_t> ta, tl;
+	for (int64_t k = lo; k < hi; ++k) {
+		ta.clear(); tl.clear();
+		Win w = region_window(rs, k, p, &ta, &tl);
+		idl_region &g = b->region[k - lo];
+		memset(&g, 0, sizeof g);
+		g.chrom_id = rs->roi_chrom[k]; g.roi_start = rs->roi_start[k]; g.roi_end = rs->roi_stop[k];
+		g.read_begin = ri; g.n_reads = (uint32_t)rs->roi_n_reads[k];
+		g.ref_start = (int32_t)w.ws; g.ref_off = (uint32_t)roff; g.ref_len = (uint32_t)std::max<int64_t>(0, w.we - w.ws + 1);
+		g.max_stop = (int32_t)w.max_stop; g.ordinal = (uint32_t)k;
+		pack_bases(b->ref2, b->refn, roff, rs->chrom_seq[g.chrom_id] + w.ws, g.ref_len);
+		roff += round64(g.ref_len);
+		for (int32_t j = 0; j < rs->roi_n_reads[k]; ++j, ++ri) {
+			int64_t i = rs->read_idx[rs->roi_read_begin[k] + j];
+			idl_read &r = b->read[ri];
+			memset(&r, 0, sizeof r);
+			if (rs->len[i] > p->max_read_len || rs->len[i] > 65535) return IDL_E_CAPACITY;
+			r.start = rs->start[i]; r.stop = rs->stop[i]; r.seq_off = (uint32_t)soff; r.len = (uint16_t)rs->len[i];
+			r.trim_a = (uint16_t)ta[j]; r.trim_len = (uint16_t)tl[j];
+			r.min_overlap = (uint16_t)(int64_t)(0.88 * (double)tl[j]); // :169
+			r.mapq = rs->mapq[i];
+			const uint16_t f = rs->flag[i];
+			r.flags = ((f & 0x400) || (f & 0x200) || (f & 0x4) || (f & 0x800) || (f & 0x100)) ? 1 : 0; // :40-47
+			pack_bases(b->seq2, b->seqn, soff, rs->bases + rs->seq_off[i], rs->len[i]);
+			soff += round64((uint64_t)rs->len[i]);
+		}
+	}
+	b->n_regions = (size_t)(hi - lo); b->n_reads = nr; b->n_seq_bases = sb; b->n_ref_bases = rb;
+	return IDL_OK;
+}
+
+idl_batch *idlh_batch_alloc_host(size_t max_regions, size_t max_reads, size_t max_seq_bases, size_t max_ref_bases)
+{
+	idl_batch *b = (idl_batch*)calloc(1, sizeof(idl_batch));
+	max_seq_bases = round64(max_seq_bases); max_ref_bases = round64(max_ref_bases);
+	b->cap_regions = max_regions; b->cap_reads = max_reads; b->cap_seq_bases = max_seq_bases; b->cap_ref_bases = max_ref_bases;
+	b->region = (idl_region*)calloc(max_regions + 1, sizeof(idl_region));
+	b->read = (idl_read*)calloc(max_reads + 1, sizeof(idl_read));
+	b->seq2 = (uint32_t*)calloc(max_seq_bases / 16 + 4, 4); b->seqn = (uint32_t*)calloc(max_seq_bases / 32 + 4, 4);
+	b->ref2 = (uint32_t*)calloc(max_ref_bases / 16 + 4, 4); b->refn = (uint32_t*)calloc(max_ref_bases / 32 + 4, 4);
+	return b;
+}
+
+void idlh_batch_free_host(idl_batch *b)
+{
+	if (!b) return;
+	free(b->region); free(b->read); free(b->seq2); free(b->seqn); free(b->ref2); free(b->refn); free(b);
+}
+
+void idlh_unpack(const uint32_t *pool2, const uint32_t *pooln, uint64_t off, int32_t n, char *out)
+{
+	for (int32_t i = 0; i < n; ++i) {
+		uint64_t b = off + (uint64_t)i;
+		out[i] = (pooln[b >> 5] >> (b & 31)) & 1 ? 'N' : "ACGT"[(pool2[b >> 4] >> (2 * (b & 15))) & 3];
+	}
+	out[n] = 0;
+}
+
+void idlh_free(void *p) { free(p); }
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// VCF: src/indelope.nim:49-116 (Variant), :375-428 (cascade), :598-608 (dedup); src/genotyper.nim
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+std::string ffmt(double x, int prec) // Nim formatFloat(ffDecimal, precision) == sprintf("%#.*f")
+{
+	char buf[2600];
+	snprintf(buf, sizeof buf, "%#.*f", prec, x);
+	return buf;
+}
+
+struct Geno { int gt; double gl[3]; double qual; };
+
+Geno genotype(int64_t r, int64_t a, double error) // src/genotyper.nim:36-47, :22-29
+{
+	Geno g; g.gt = 3; g.gl[0] = g.gl[1] = g.gl[2] = 0; g.qual = 0;
+	const double ln2 = std::log(2.0), total = (double)(r + a);
+	if (total == 0) return g;
+	g.gt = 0;
+	for (int G = 0; G < 3; ++G) {
+		g.gl[G] = -total * ln2 + (double)r * std::log((double)G * error + (double)(2 - G) * (1 - error)) +
+		          (double)a * std::log((double)G * (1 - error) + (double)(2 - G) * error);
+		if (g.gl[G] > g.gl[g.gt]) g.gt = G;
+	}
+	if (g.gt == 0) g.qual = g.gl[0] - std::max(g.gl[1], g.gl[2]);
+	else if (g.gt == 1) g.qual = g.gl[1] - std::max(g.gl[0], g.gl[2]);
+	else g.qual = g.gl[2] - std::max(g.gl[0], g.gl[1]);
+	return g;
+}
+
+int distinct(const char *s, size_t n)
+{
+	bool seen[256] = {false}; int k = 0;
+	for (size_t i = 0; i < n; ++i) if (!seen[(uint8_t)s[i]]) { seen[(uint8_t)s[i]] = true; ++k; }
+	return k;
+}
+
+double mean_of(int64_t sum, int64_t n) // src/indelope.nim:146-150; empty list divides 0.0 by 0.0 at run time
+{
+	volatile double s = (double)sum, d = (double)n;
+	return s / d;
+}
+
+std::string fetch(const idlh_roiset *rs, int chrom, int64_t a, int64_t b) // Fai.get: 0-based inclusive, clipped
+{
+	if (a < 0) a = 0;
+	if (b >= rs->chrom_len[chrom]) b = rs->chrom_len[chrom] - 1;
+	if (a > b) return std::string();
+	return std::string((const char*)rs->chrom_seq[chrom] + a, (size_t)(b - a + 1));
+}
+
+std::string cigar_text(const uint32_t *c, int n)
+{
+	std::string s;
+	for (int i = 0; i < n; ++i) { s += std::to_string(c[i] >> 4); s += "MID"[c[i] & 0xf]; }
+	return s;
+}
+
+struct Rec { std::string chrom, ref, alt, line; int64_t pos; };
+
+} // namespace
+
+struct idlh_vcf { bool have1 = false, have2 = false; Rec last1, last2; };
+
+extern "C" {
+
+idlh_vcf *idlh_vcf_new(void) { return new idlh_vcf(); }
+void idlh_vcf_free(idlh_vcf *w) { delete w; }
+
+char *idlh_vcf_header(const idlh_roiset *rs) // src/indelope.nim:77-102,548-552,600
+{
+	static const char *fixed[] = {
+	    "##fileformat=VCFv4.2",
+	    "##FORMAT=<ID=AD,Number=R,Type=Integer,Description=\"Allelic depths for the ref and alt alleles in the order listed\">",
+	    "##INFO=<ID=AD,Number=R,Type=Integer,Description=\"Allelic depths for the ref and alt alleles in the order listed\">",
+	    "##INFO=<ID=END,Number=1,Type=Integer,Description=\"End position of the variant described in this record\">",
+	    "##INFO=<ID=SVLEN,Number=1,Type=Integer,Description=\"Difference in length between REF and ALT alleles\">",
+	    "##INFO=<ID=DP,Number=1,Type=Integer,Description=\"total reads covering this site\">",
+	    "##INFO=<ID=AL,Number=0,Type=Flag,Description=\"this was genotyped with alignment, no k-mer counting\">",
+	    "##INFO=<ID=AMQ,Number=1,Type=Integer,Description=\"median mapping quality of alts\">",
+	    "##INFO=<ID=RMQ,Number=1,Type=Integer,Description=\"median mapping quality of refs\">",
+	    "##INFO=<ID=BS,Number=1,Type=Integer,Description=\"number of times there was support for both ref and alt k-mer in a single read\">",
+	    "##INFO=<ID=MF,Number=1,Type=Integer,Description=\"minimum matching bases around this event when BS > 0. Higher gives more confidence\">",
+	    "##INFO=<ID=CF,Number=1,Type=Integer,Description=\"minimum flank of the event from either end of the contig. higher is better.\">",
+	    "##INFO=<ID=NC,Number=1,Type=Integer,Description=\"number of contigs at the site of this variant.\">",
+	    "##INFO=<ID=CC,Number=1,Type=String,Description=\"contig cigar from alignment to reference\">",
+	    "##INFO=<ID=LO,Number=0,Type=Flag,Description=\"low-offset: the event occurred near at the start of the contig so we may not have the full variant\">",
+	    "##INFO=<ID=AKE,Number=1,Type=Float,Description=\"mean alt-kmer distance from end of read\">",
+	    "##INFO=<ID=RKE,Number=1,Type=Float,Description=\"mean ref-kmer distance from end of read\">",
+	    "##FORMAT=<ID=DP,Number=1,Type=Integer,Description=\"supporting k-mer depth\">",
+	    "##FORMAT=<ID=GQ,Number=1,Type=Float,Description=\"Genotype Quality\">",
+	    "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">",
+	    "##FORMAT=<ID=GL,Number=G,Type=Float,Description=\"Normalized, Phred-scaled likelihoods for genotypes as defined in the VCF specification\">",
+	    "##INFO=<ID=DP,Number=1,Type=Integer,Description=\"Approximate read depth; some reads may have been filtered\">",
+	    "##INFO=<ID=ref_kmer,Number=1,Type=String,Description=\"reference kmer used for genotyping\">",
+	    "##INFO=<ID=alt_kmer,Number=1,Type=String,Description=\"alternate kmer used for genotyping\">"};
+	std::string h;
+	for (const char *l : fixed) { h += l; h += "\n"; }
+	std::vector<std::string> cl;
+	for (int c = 0; c < rs->n_chroms; ++c) cl.push_back("##contig=<ID=" + std::string(rs->chrom_name[c]) + ",length=" + std::to_string(rs->chrom_len[c]) + ">");
+	for (size_t i = 0; i < cl.size(); ++i) { if (i) h += "\n"; h += cl[i]; }
+	h += "\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tsample\n";
+	char *out = (char*)malloc(h.size() + 1);
+	memcpy(out, h.c_str(), h.size() + 1);
+	return out;
+}
+
+char *idlh_vcf_records(idlh_vcf *w, const idlh_roiset *rs, int64_t lo, const idl_params *P, const idl_results *res, int32_t dump_level, char **dump_out)
+{
+	const int K = IDL_KMER;
+	static const char *gt_enc[] = {"0/0", "0/1", "1/1", "./."};
+	std::string vcf, d;
+	for (size_t i = 0; i < res->n_regions; ++i) {
+		const idl_region_result &rr = res->region[i];
+		const int64_t k = lo + (int64_t)i;
+		const int chrom = rs->roi_chrom[k];
+		const int64_t n_region_reads = rs->roi_n_reads[k];
+		std::vector<std::string> vlines;
+		if (dump_level & 1) {
+			d += "R\t" + std::to_string(k) + "\tpre=" + std::to_string(rr.n_contigs_pre) + "\tn=" + std::to_string(rr.n_contigs) + "\n";
+			for (int32_t ci = 0; ci < rr.n_contigs; ++ci) {
+				const idl_contig_result &c = res->contig[rr.contig_begin + ci];
+				d += "C\t" + std::to_string(k) + "\t" + std::to_string(ci) + "\t" + std::to_string(c.start) + "\t" + std::to_string(c.nreads) + "\t" +
+				     std::to_string(c.len) + "\t" + std::string(res->contig_seq + c.seq_off, (size_t)c.len);
+				if (dump_level & 2) {
+					d += "\t";
+					for (int32_t x = 0; x < c.len; ++x) { if (x) d += ","; d += std::to_string(res->contig_support ? res->contig_support[c.seq_off + x] : 0u); }
+				}
+				d += "\n";
+			}
+		}
+		for (int32_t ci = 0; ci < rr.n_contigs; ++ci) {
+			const idl_contig_result &c = res->contig[rr.contig_begin + ci];
+			if (c.aln < 0) continue;
+			const idl_aln_result &a = res->aln[c.aln];
+			const uint32_t *cig = res->cigar + a.cigar_off;
+			const char *ctg = res->contig_seq + c.seq_off;
+			if (dump_level & 4) {
+				char b[256];
+				snprintf(b, sizeof b, "A\t%lld\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t", (long long)k, ci, c.start, a.ref_len, a.max, a.zdropped,
+				         a.max_q, a.max_t, a.mqe, a.mqe_t, a.mte, a.mte_q, a.score);
+				d += b; d += cigar_text(cig, a.n_cigar) + "\t" + cigar_text(cig, a.n_cigar_trunc) + "\n";
+			}
+			if (a.n_events < 1 || a.n_events > P->max_events) continue; // src/indelope.nim:229
+			for (int32_t ei = 0; ei < a.n_events; ++ei) {
+				const idl_event_result &e = res->event[a.event_begin + ei];
+				const bool have_kmers = e.reject != IDL_EV_SHORT && e.reject != IDL_EV_WINDOW;
+				std::string ref_kmer, alt_kmer;
+				if (have_kmers) {
+					ref_kmer = fetch(rs, chrom, (int64_t)c.start + e.tstart, (int64_t)c.start + e.tstart + K - 1);
+					alt_kmer = std::string(ctg + e.qstart, (size_t)K);
+				}
+				if (dump_level & 8) {
+					char b[512];
+					snprintf(b, sizeof b, "E\t%lld\t%d\t%d\t%c\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t", (long long)k, ci, e.index, e.type == 0 ? 'I' : 'D', e.t_start, e.t_stop,
+					         e.len, e.q_start, e.q_stop, e.reject, e.tstart, e.qstart);
+					d += b; d += (have_kmers ? ref_kmer : std::string(".")) + "\t" + (have_kmers ? alt_kmer : std::string("."));
+					snprintf(b, sizeof b, "\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%lld\t%d\t%lld\t%d\t%d\t%d\t%d\n", e.k_ref, e.k_alt, e.k_both, e.aligned, e.ref_support,
+					         e.alt_support, e.both_found, e.n_adist, (long long)e.sum_adist, e.n_rdist, (long long)e.sum_rdist, e.amq_median, e.rmq_median,
+					         e.min_flank, e.offset);
+					d += b;
+				}
+				if (e.reject != IDL_EV_COUNTED) continue;
+				// ---- cascade, src/indelope.nim:375-428
+				const int64_t ref_support = e.ref_support, alt_support = e.alt_support, both_found = e.both_found, offset = e.offset;
+				if (alt_support < P->min_reads) continue;
+				if ((double)alt_support / (double)n_region_reads < 0.1) continue;
+				Geno g = genotype(ref_support, alt_support, 1e-3);
+				if (g.gt == 0) continue;
+				double qual = g.qual;
+				if (offset == 0 && both_found >= (int64_t)(0.75 * (double)std::min(ref_support, alt_support))) continue;
+				std::string info = "DP=" + std::to_string(n_region_reads);
+				if (offset < 5) { info += ";LO"; qual /= 2.0; }
+				if (both_found > 0) { info += ";BS=" + std::to_string(both_found); qual /= 1.5; }
+				else qual *= 2;
+				info += ";CC=" + cigar_text(cig, a.n_cigar_trunc);
+				if (e.aligned) info += ";AL";
+				if ((int64_t)(e.min_flank - 1) < std::max<int64_t>(e.t_stop - e.t_start, e.q_stop - e.q_start)) continue;
+				info += ";MF=" + std::to_string(e.min_flank);
+				info += ";CF=" + std::to_string(offset);
+				info += ";NC=" + std::to_string(rr.n_contigs_pre);
+				if (offset == 0) qual /= 4.0;
+				const double ake = mean_of(e.sum_adist, e.n_adist), rke = mean_of(e.sum_rdist, e.n_rdist);
+				info += ";AKE=" + ffmt(ake, 2);
+				info += ";RKE=" + ffmt(rke, 2);
+				if (e.n_adist > 0) info += ";AMQ=" + std::to_string(e.amq_median);
+				if (e.n_rdist > 0) info += ";RMQ=" + std::to_string(e.rmq_median);
+				if (ake < 5) continue;
+				Rec v; v.chrom = rs->chrom_name[chrom]; v.pos = e.t_start;
+				if (e.type == 1) {
+					v.ref = fetch(rs, chrom, (int64_t)e.t_start - 1, (int64_t)e.t_stop - 1);
+					v.alt = v.ref.substr(0, 1);
+				} else {
+					if (e.q_start < 1) continue; // the reference indexes ctg.sequence[-1]: unsupported, never reached with an M-led CIGAR
+					v.ref = fetch(rs, chrom, (int64_t)e.t_start - 1, (int64_t)e.t_start - 1);
+					v.alt = std::string(ctg + e.q_start - 1, (size_t)(e.q_stop - (e.q_start - 1)));
+					if (distinct(v.alt.data() + 1, v.alt.size() - 1) == 1 && distinct(alt_kmer.data() + K - 11, 11) == 1 &&
+					    distinct(ref_kmer.data() + K - 11, 11) == 1)
+						continue;
+				}
+				v.line = v.chrom + "\t" + std::to_string(v.pos) + "\t.\t" + v.ref + "\t" + v.alt + "\t" + ffmt(qual, 2) + "\tPASS\t" + "AD=" +
+				         std::to_string(ref_support) + "," + std::to_string(alt_support) + ";ref_kmer=" + ref_kmer + ";alt_kmer=" + alt_kmer + ";" + info +
+				         "\tGT:GQ:GL\t" + gt_enc[g.gt] + ":" + ffmt(g.qual, 4) + ":" + ffmt(g.gl[0], 4) + "," + ffmt(g.gl[1], 4) + "," + ffmt(g.gl[2], 4);
+				// order-dependent dedup against the last two emitted records, src/indelope.nim:604-608
+				auto same = [](const Rec &x, const Rec &y) { return x.pos == y.pos && x.chrom == y.chrom && x.ref == y.ref && x.alt == y.alt; };
+				if (w->have1 && same(v, w->last1)) continue;
+				if (w->have2 && same(v, w->last2)) continue;
+				vlines.push_back(v.line);
+				w->last2 = w->last1; w->have2 = w->have1;
+				w->last1 = v; w->have1 = true;
+			}
+		}
+		for (auto &l : vlines) { vcf += l + "\n"; if (dump_level & 16) d += "V\t" + l + "\n"; }
+	}
+	if (dump_out) { *dump_out = (char*)malloc(d.size() + 1); memcpy(*dump_out, d.c_str(), d.size() + 1); }
+	char *out = (char*)malloc(vcf.size() + 1);
+	memcpy(out, vcf.c_str(), vcf.size() + 1);
+	return out;
+}
+
+} // extern "C"

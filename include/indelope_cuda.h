@@ -172,6 +172,8 @@ typedef struct idl_aln_result {
 #define IDL_EV_BUG_SAME  3   /* :268-275 */
 #define IDL_EV_SHORT    10   /* :234 */
 #define IDL_EV_WINDOW   11   /* reference window shorter than K (the reference would raise) */
+#define IDL_EV_DP_ERROR 12   /* the alignment hit a capacity limit (idl_aln_result.status) */
+#define IDL_NO_EVENTS 0xffffffffu /* idl_aln_result.event_begin when no event records were written */
 
 typedef struct idl_event_result {
 	uint32_t aln;                 /* owning alignment */
@@ -230,7 +232,8 @@ int idl_device_count(void);
 /* ---- unit-level entry point: a batch of independent extension alignments through kernel 2 ------
  * Same contract as the reference's ksw_extz2_sse (src/ksw2/csrc/ksw2.h:54, flag = 0, m = 5 with the matrix of
  * src/ksw2/ksw2.nim:135-140).  query/target are 0..4 codes, concatenated; q_off/t_off have n+1 entries.
- * out[i] receives the ksw_extz_t fields; cigar_off has n+1 entries into cigar[] (cap cigar_cap ops in total). */
+ * out[i] receives the ksw_extz_t fields; cigar_off[i] is where task i's out[i].n_cigar ops start in cigar[]
+ * (cigar_cap ops in total, handed out in completion order). */
 typedef struct idl_ez {
 	int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, n_cigar;
 	int32_t status;

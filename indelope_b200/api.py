@@ -1,0 +1,86 @@
+"""Host-side mirror of the reference's calling loop over the two native libraries.
+
+    for r in gen_roi(...): for v in callsemble(r, ...): dedup; echo v        (src/indelope.nim:601-608)
+
+becomes: pack regions into pinned batches -> idl_submit (async, one lane per stream) -> idl_wait -> filter cascade +
+VCF text on the host.  Regions keep their emission order (batches are contiguous slices, records are written in
+ticket order), so the order-dependent dedup sees the same sequence as the reference's single loop.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import cuda, host
+from .abi import default_params
+
+
+def plan_batches(rois, lo, hi, max_reads=400_000, max_regions=20_000):
+    """contiguous slices [a, b) of the region list, bounded by reads and regions per batch"""
+    n = np.ctypeslib.as_array(rois.c.roi_n_reads, shape=(rois.n_rois,)) if rois.n_rois else np.zeros(0, np.int32)
+    out, a, acc = [], lo, 0
+    for k in range(lo, hi):
+        if k > a and (acc + int(n[k]) > max_reads or k - a >= max_regions):
+            out.append((a, k)); a, acc = k, 0
+        acc += int(n[k])
+    if hi > a:
+        out.append((a, hi))
+    return out
+
+
+class Caller:
+    """`indelope --min-reads M --min-contig-len C --min-event-len E` over regions, on one GPU"""
+
+    def __init__(self, device=0, min_reads=3, min_ctg_len=73, min_event_len=4, **kw):
+        self.params = default_params(min_reads=min_reads, min_ctg_len=min_ctg_len, min_event_len=min_event_len, **kw)
+        self.ctx = cuda.Context(device, self.params)
+        self._batches = {}
+
+    def _batch_for(self, lane, sizes):
+        """pinned batch per lane, grown on demand"""
+        cur = self._batches.get(lane)
+        need = (sizes[0], sizes[1], sizes[2], sizes[3])
+        if cur is None or any(n > c for n, c in zip(need, cur[1])):
+            if cur is not None:
+                self.ctx.batch_free(cur[0])
+            cap = tuple(int(x * 1.25) + 64 for x in need)
+            cur = (self.ctx.batch_alloc(*cap), cap)
+            self._batches[lane] = cur
+        return cur[0]
+
+    def call(self, rois, lo=0, hi=None, dump_level=0, max_reads=400_000, timings=None):
+        """returns (vcf record text, dump text). `timings` (list) receives one dict per batch."""
+        hi = rois.n_rois if hi is None else hi
+        writer = host.VcfWriter()
+        plans = plan_batches(rois, lo, hi, max_reads=max_reads)
+        n_lanes = self.params.n_streams
+        vcf, dump = [], []
+        inflight = []
+
+        def drain():
+            a, b, t = inflight.pop(0)
+            res = self.ctx.wait(t)
+            v, d = writer.records(rois, a, self.params, res, dump_level)
+            if timings is not None:
+                r = res.contents
+                timings.append({k: getattr(r, k) for k in ("ms_h2d", "ms_assemble", "ms_align", "ms_genotype", "ms_al", "ms_d2h", "ms_total", "n_regions",
+                                                           "n_contigs", "n_alns", "n_events", "offsets_tested", "dp_cells_a", "dp_cells_b", "dp_a", "dp_b",
+                                                           "kmer_reads", "kmer_bytes", "al_events", "kernel_launches")})
+            self.ctx.release(t)
+            vcf.append(v); dump.append(d)
+
+        for i, (a, b) in enumerate(plans):
+            if len(inflight) >= n_lanes:
+                drain()
+            nr, sb, rb = rois.pack_size(a, b, self.params)
+            batch = self._batch_for(i % n_lanes, (b - a, nr, sb, rb))
+            rois.pack(a, b, self.params, batch)
+            inflight.append((a, b, self.ctx.submit(batch)))
+        while inflight:
+            drain()
+        return "".join(vcf), "".join(dump)
+
+    def close(self):
+        for b, _ in self._batches.values():
+            self.ctx.batch_free(b)
+        self._batches = {}
+        self.ctx.close()

@@ -53,7 +53,7 @@ def build_host(force=False, verbose=False):
 
 def build_cuda(force=False, verbose=False):
     if force or _newer(CUDA_LIB, _deps(CUDA_SRCS)):
-        cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", INC, "-I", CSRC] + [os.path.join(CSRC, s) for s in CUDA_SRCS] + ["-o", CUDA_LIB, "-lcudart"]
+        cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", INC, "-I", CSRC] + [os.path.join(CSRC, s) for s in CUDA_SRCS] + ["-o", CUDA_LIB]
         if verbose:
             print(" ".join(cmd))
         r = subprocess.run(cmd, capture_output=True, text=True)

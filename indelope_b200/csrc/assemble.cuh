@@ -1,0 +1,524 @@
+// indelope_b200/csrc/assemble.cuh -- kernel 1: slide-and-vote assembler, one CTA per region of interest.
+//
+// Replaces assemble (src/indelope.nim:157-183) over src/contig.nim: slide_align (:70-141), best_match (:224-240),
+// insert (:156-222), Contig.trim (:49-68) and the two-pass combine (:254-281).
+//
+// Data layout.  A contig lives in a "slot": three bit-planes (low code bit, high code bit, non-ACGT flag), 32 bases
+// per 32-bit word, plus one uint16 support counter per base.  Slots sit in a per-CTA arena in global memory (the
+// working set of a region is a few KB and stays in L1); the query of the current best_match is staged in shared
+// memory.  The overlap scan gives every (contig, offset) pair to one lane: the overlap is compared 32 bases at a time
+// as  (q0 ^ t0) | (q1 ^ t1) | (qn ^ tn)  with a funnel shift aligning the shifted side, aborting at the first
+// word with a mismatch the voting rule does not allow; matches = overlap - popc(allowed mismatches).  The arg-max uses
+// the reference's exact order: most matches, then lowest contig index (stable sort, :239), then first offset in scan
+// order (:107,135).  Reads are consumed strictly in input order -- the greedy merge is order dependent.
+//
+// A left-overhang merge (offset < 0, :180-205) is built in the QUERY's slot (after corrections both sides agree on the
+// overlap, so only the target's tail has to be appended), which avoids shifting the target; the list entry is then
+// re-pointed to that slot.
+#pragma once
+#include "common.cuh"
+
+#define ASM_THREADS 256
+#define ASM_WARPS (ASM_THREADS / 32)
+
+struct AsmArgs {
+	// batch (device copies)
+	const idl_region *region; const idl_read *read;
+	const uint32_t *seq2, *seqn, *ref2, *refn;
+	unsigned n_regions;
+	idl_params P;
+	// arena: n_ctas * ns slots
+	uint32_t *planes; uint16_t *sup; int ns, nw, cap;
+	// outputs
+	idl_region_result *rres; idl_contig_result *cres; idl_aln_result *ares;
+	char *ctg_ascii; uint8_t *ctg_codes; uint32_t *ctg_sup; uint8_t *refcodes;
+	unsigned cap_contigs, cap_bases, cap_alns;
+	DevCounters *cnt;
+};
+
+struct AsmS { // carved out of dynamic shared memory
+	uint32_t *q0, *q1, *qn;           // staged query planes, nw words each
+	int *len, *nreads, *start;        // per slot
+	uint16_t *listA, *listB, *freestk;
+	int *corr;                        // 3 ints per correction site: qoff, toff, qbest
+	unsigned long long *best;         // per warp
+	int *sc;                          // scalars: see SC_*
+};
+enum { SC_NFREE = 0, SC_STATUS, SC_TMP0, SC_TMP1, SC_NCORR, SC_REGION, SC_HASN, SC_SLOT, SC_N };
+
+__host__ __device__ inline size_t asm_smem_bytes(int ns, int nw)
+{
+	size_t b = (size_t)3 * nw * 4 + (size_t)3 * ns * 4 + (size_t)3 * ns * 2 + (size_t)3 * IDL_MAX_CORRECTIONS * 4 + ASM_WARPS * 8 + SC_N * 4;
+	return (b + 15) & ~(size_t)15;
+}
+
+struct Asm {
+	AsmS s; const AsmArgs *a;
+	uint32_t *planes; uint16_t *supb; int nw, cap, ns;
+	unsigned long long offsets;
+	__device__ uint32_t *p0(int slot) const { return planes + ((size_t)slot * 3 + 0) * nw; }
+	__device__ uint32_t *p1(int slot) const { return planes + ((size_t)slot * 3 + 1) * nw; }
+	__device__ uint32_t *pn(int slot) const { return planes + ((size_t)slot * 3 + 2) * nw; }
+	__device__ uint16_t *sup(int slot) const { return supb + (size_t)slot * cap; }
+};
+
+// allowable_mismatch, src/contig.nim:44-47 (uint32 products on the supports, int on the read counts)
+__device__ __forceinline__ bool asm_allowed(unsigned qsup, unsigned tsup, int qreads, int treads)
+{
+	return (qsup < 3u && tsup > 3u * qsup && qreads > 3 * (int)qsup) || (tsup < 3u && qsup > 3u * tsup && treads > 3 * (int)tsup);
+}
+
+__device__ __forceinline__ uint32_t compress_even(uint64_t x) // bits 0,2,4,... -> 32 bits
+{
+	x &= 0x5555555555555555ULL;
+	x = (x | (x >> 1)) & 0x3333333333333333ULL;
+	x = (x | (x >> 2)) & 0x0f0f0f0f0f0f0f0fULL;
+	x = (x | (x >> 4)) & 0x00ff00ff00ff00ffULL;
+	x = (x | (x >> 8)) & 0x0000ffff0000ffffULL;
+	x = (x | (x >> 16)) & 0x00000000ffffffffULL;
+	return (uint32_t)x;
+}
+
+__device__ int asm_alloc(Asm &A) // uniform: every thread gets the same slot
+{
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int n = A.s.sc[SC_NFREE];
+		if (n > 0) { A.s.sc[SC_SLOT] = A.s.freestk[n - 1]; A.s.sc[SC_NFREE] = n - 1; }
+		else { A.s.sc[SC_SLOT] = -1; A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; }
+	}
+	__syncthreads();
+	return A.s.sc[SC_SLOT];
+}
+__device__ void asm_free(Asm &A, int slot) // call from uniform code; takes effect at the next barrier
+{
+	if (threadIdx.x == 0) { A.s.freestk[A.s.sc[SC_NFREE]] = (uint16_t)slot; A.s.sc[SC_NFREE] += 1; }
+}
+
+// one (query, contig, offset) candidate: number of matching bases, or -1 if a mismatch is not allowed.
+// dir2 == false: loop 1 of slide_align (:86-111), q[i] against t[o+i]; dir2 == true: loop 2 (:114-139), q[o+i] against t[i].
+__device__ int asm_eval(const Asm &A, const uint32_t *t0, const uint32_t *t1, const uint32_t *tn, const uint16_t *tsup, const uint16_t *qsup,
+                        int qlen, int tlen, int qreads, int treads, bool dir2, int o, bool vote, bool has_n)
+{
+	const int n = dir2 ? min(qlen - o, tlen) : min(qlen, tlen - o);
+	if (n <= 0) return 0; // nothing compared: ma = 0, mm = 0
+	int ncorr = 0;
+	const int nwords = (n + 31) >> 5;
+	for (int w = 0; w < nwords; ++w) {
+		uint32_t m;
+		const int pos = o + 32 * w;
+		if (!dir2) {
+			m = (A.s.q0[w] ^ get32(t0, pos)) | (A.s.q1[w] ^ get32(t1, pos));
+			if (has_n) m |= A.s.qn[w] ^ get32(tn, pos);
+		} else {
+			m = (t0[w] ^ get32(A.s.q0, pos)) | (t1[w] ^ get32(A.s.q1, pos));
+			if (has_n) m |= tn[w] ^ get32(A.s.qn, pos);
+		}
+		const int rem = n - 32 * w;
+		if (rem < 32) m &= (1u << rem) - 1u;
+		if (m) {
+			if (!vote) return -1;
+			while (m) {
+				const int b = __ffs(m) - 1; m &= m - 1;
+				const int i = 32 * w + b;
+				const int qo = dir2 ? o + i : i, to = dir2 ? i : o + i;
+				if (!asm_allowed(qsup[qo], tsup[to], qreads, treads)) return -1;
+				++ncorr;
+			}
+		}
+	}
+	return n - ncorr;
+}
+
+struct AsmMatch { int k, offset, ma; bool aligned; };
+
+// best_match (:224-240) of slot q against list[0..nlist). Uniform result.
+__device__ AsmMatch asm_best_match(Asm &A, const uint16_t *list, int nlist, int q, int mo, bool has_n)
+{
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int qlen = A.s.len[q], qreads = A.s.nreads[q];
+	__syncthreads();
+	{ // stage the query planes (+ zero padding up to nw words)
+		const int qw = (qlen + 31) >> 5;
+		const uint32_t *g0 = A.p0(q), *g1 = A.p1(q), *gn = A.pn(q);
+		for (int w = tid; w < A.nw; w += ASM_THREADS) {
+			const bool in = w < qw;
+			A.s.q0[w] = in ? g0[w] : 0u; A.s.q1[w] = in ? g1[w] : 0u; A.s.qn[w] = in ? gn[w] : 0u;
+		}
+	}
+	__syncthreads();
+	const uint16_t *qsup = A.sup(q);
+	unsigned long long best = 0;
+	for (int k = warp; k < nlist; k += ASM_WARPS) {
+		const int t = list[k];
+		const int tlen = A.s.len[t], treads = A.s.nreads[t];
+		const int omax = tlen - mo;
+		const int n1 = omax >= 0 ? omax + 1 : 0;
+		const int n2 = qlen - mo >= 0 ? qlen - mo : mo - qlen; // abs(omin), :78,114
+		const bool vote = qreads >= 4 && treads >= 4; // a vote needs support >= 4 on one side and reads >= 4 on the other (supports are 1..nreads)
+		const uint32_t *t0 = A.p0(t), *t1 = A.p1(t), *tn = A.pn(t);
+		const uint16_t *tsup = A.sup(t);
+		unsigned key = 0;
+		for (int sidx = lane; sidx < n1 + n2; sidx += 32) {
+			const bool dir2 = sidx >= n1;
+			const int o = dir2 ? sidx - n1 + 1 : sidx;
+			const int ma = asm_eval(A, t0, t1, tn, tsup, qsup, qlen, tlen, qreads, treads, dir2, o, vote, has_n);
+			// first candidate needs ma >= mo-1 (best_ma starts at mo-1, best_mm at 1: :81-82,107); later ones strictly more
+			if (ma >= 0 && ma >= mo - 1) {
+				const unsigned kk = ((unsigned)(ma + 1) << 16) | (unsigned)(0xffff - sidx);
+				key = kk > key ? kk : key;
+			}
+		}
+		key = __reduce_max_sync(FULL_MASK, key);
+		if (key) {
+			const unsigned long long k64 = ((unsigned long long)(key >> 16) << 32) | ((unsigned long long)(0xffff - k) << 16) | (key & 0xffff);
+			best = k64 > best ? k64 : best;
+		}
+		if (lane == 0) A.offsets += (unsigned long long)(n1 + n2);
+	}
+	if (lane == 0) A.s.best[warp] = best;
+	__syncthreads();
+	best = 0;
+	for (int w2 = 0; w2 < ASM_WARPS; ++w2) { const unsigned long long b = A.s.best[w2]; best = b > best ? b : best; }
+	AsmMatch m;
+	m.aligned = best != 0;
+	m.ma = (int)(best >> 32) - 1;
+	m.k = 0xffff - (int)((best >> 16) & 0xffff);
+	const int sidx = 0xffff - (int)(best & 0xffff);
+	m.offset = 0;
+	if (m.aligned) {
+		const int tlen = A.s.len[list[m.k]];
+		const int omax = tlen - mo;
+		const int n1 = omax >= 0 ? omax + 1 : 0;
+		m.offset = sidx < n1 ? sidx : -(sidx - n1 + 1);
+	}
+	return m;
+}
+
+// Contig.insert (:156-222): merge slot q into list[k] at m.offset. Returns the slot that now holds the merged contig.
+__device__ void asm_merge(Asm &A, uint16_t *list, int k, int q, int offset, bool has_n)
+{
+	const int tid = threadIdx.x;
+	const int t = list[k];
+	const int tlen = A.s.len[t], qlen = A.s.len[q], treads = A.s.nreads[t], qreads = A.s.nreads[q];
+	uint16_t *tsup = A.sup(t), *qsup = A.sup(q);
+	uint32_t *tp[3] = {A.p0(t), A.p1(t), A.pn(t)}, *qp[3] = {A.p0(q), A.p1(q), A.pn(q)};
+	const bool vote = qreads >= 4 && treads >= 4;
+	__syncthreads();
+	// 1. corrections of the winning offset, in position order (:93-99), then applied (:161-173)
+	if (tid == 0) {
+		int nc = 0;
+		if (vote) {
+			const bool dir2 = offset < 0; const int o = dir2 ? -offset : offset;
+			const int n = dir2 ? min(qlen - o, tlen) : min(qlen, tlen - o);
+			for (int w = 0; w * 32 < n; ++w) {
+				const int pos = o + 32 * w;
+				uint32_t m;
+				if (!dir2) m = (qp[0][w] ^ get32(tp[0], pos)) | (qp[1][w] ^ get32(tp[1], pos)) | (qp[2][w] ^ get32(tp[2], pos));
+				else m = (tp[0][w] ^ get32(qp[0], pos)) | (tp[1][w] ^ get32(qp[1], pos)) | (tp[2][w] ^ get32(qp[2], pos));
+				const int rem = n - 32 * w;
+				if (rem < 32) m &= (1u << rem) - 1u;
+				while (m) {
+					const int b = __ffs(m) - 1; m &= m - 1;
+					const int i = 32 * w + b;
+					const int qo = dir2 ? o + i : i, to = dir2 ? i : o + i;
+					if (nc < IDL_MAX_CORRECTIONS) { A.s.corr[3 * nc] = qo; A.s.corr[3 * nc + 1] = to; A.s.corr[3 * nc + 2] = qsup[qo] > tsup[to]; }
+					++nc;
+				}
+			}
+			if (nc > IDL_MAX_CORRECTIONS) { A.s.sc[SC_STATUS] |= IDL_RS_CORR_OVERFLOW; nc = IDL_MAX_CORRECTIONS; }
+			for (int c = 0; c < nc; ++c) {
+				const int qo = A.s.corr[3 * c], to = A.s.corr[3 * c + 1];
+				uint32_t **dst = A.s.corr[3 * c + 2] ? tp : qp, **src = A.s.corr[3 * c + 2] ? qp : tp;
+				const int di = A.s.corr[3 * c + 2] ? to : qo, si = A.s.corr[3 * c + 2] ? qo : to;
+				for (int pl = 0; pl < 3; ++pl) {
+					const uint32_t bit = (src[pl][si >> 5] >> (si & 31)) & 1u;
+					dst[pl][di >> 5] = (dst[pl][di >> 5] & ~(1u << (di & 31))) | (bit << (di & 31));
+				}
+				if (A.s.corr[3 * c + 2]) tsup[to] = qsup[qo]; else qsup[qo] = tsup[to];
+			}
+		}
+		A.s.sc[SC_NCORR] = nc;
+	}
+	__syncthreads();
+	const int nc = A.s.sc[SC_NCORR];
+	if (offset < 0) { // :180-205, built in q's slot (q frame)
+		const int ao = -offset;
+		const int newlen = max(qlen, ao + tlen);
+		if (newlen > A.cap) { if (tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; __syncthreads(); return; }
+		for (int i = ao + tid; i < ao + tlen; i += ASM_THREADS) {
+			unsigned val = tsup[i - ao];
+			if (i < qlen) {
+				bool dont = false;
+				for (int c = 0; c < nc; ++c) dont |= A.s.corr[3 * c] == i; // dont_overwrite holds qoff here (:170-171)
+				if (!dont) val += qsup[i];
+			}
+			qsup[i] = (uint16_t)val;
+		}
+		if (ao + tlen > qlen) { // append the target's tail: bases [qlen, ao+tlen) come from t[i-ao]
+			for (int w = (qlen >> 5) + tid; w * 32 < newlen; w += ASM_THREADS) {
+				const uint32_t low = qlen - 32 * w >= 32 ? 0xffffffffu : (qlen > 32 * w ? (1u << (qlen - 32 * w)) - 1u : 0u);
+				for (int pl = 0; pl < 3; ++pl) {
+					if (pl == 2 && !has_n) { qp[2][w] = 0; continue; }
+					const uint32_t tb = get32(tp[pl], 32 * w - ao);
+					qp[pl][w] = (qp[pl][w] & low) | (tb & ~low);
+				}
+			}
+		}
+		__syncthreads();
+		if (tid == 0) {
+			A.s.len[q] = newlen; A.s.nreads[q] = treads + qreads; // start stays q.start (:204)
+			list[k] = (uint16_t)q;
+		}
+		asm_free(A, t);
+	} else { // :210-222, in t's slot
+		const int o = offset;
+		const int newlen = max(tlen, o + qlen);
+		if (newlen > A.cap) { if (tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; __syncthreads(); return; }
+		for (int i = o + tid; i < o + qlen; i += ASM_THREADS) {
+			if (i < tlen) {
+				bool dont = false;
+				for (int c = 0; c < nc; ++c) dont |= A.s.corr[3 * c + 1] == i; // toff (:172-173)
+				if (!dont) tsup[i] = (uint16_t)(tsup[i] + qsup[i - o]);
+			} else tsup[i] = qsup[i - o];
+		}
+		if (o + qlen > tlen) {
+			for (int w = (tlen >> 5) + tid; w * 32 < newlen; w += ASM_THREADS) {
+				const uint32_t low = tlen - 32 * w >= 32 ? 0xffffffffu : (tlen > 32 * w ? (1u << (tlen - 32 * w)) - 1u : 0u);
+				for (int pl = 0; pl < 3; ++pl) {
+					if (pl == 2 && !has_n) { tp[2][w] = 0; continue; }
+					const uint32_t qb = get32(qp[pl], 32 * w - o);
+					tp[pl][w] = (tp[pl][w] & low) | (qb & ~low);
+				}
+			}
+		}
+		__syncthreads();
+		if (tid == 0) { A.s.len[t] = newlen; A.s.nreads[t] = treads + qreads; }
+		asm_free(A, q);
+	}
+	__syncthreads();
+}
+
+// Contig.trim (:49-68). Returns the slot holding the trimmed contig (a fresh one if bases were dropped on the left).
+__device__ int asm_trim(Asm &A, int c, int min_support, bool has_n)
+{
+	const int tid = threadIdx.x;
+	const int L = A.s.len[c];
+	const unsigned ms = (unsigned)min_support;
+	const uint16_t *sp = A.sup(c);
+	__syncthreads();
+	if (tid == 0) { A.s.sc[SC_TMP0] = 0x7fffffff; A.s.sc[SC_TMP1] = -1; }
+	__syncthreads();
+	for (int i = tid; i < L - 1; i += ASM_THREADS) if (sp[i] >= ms) { atomicMin(&A.s.sc[SC_TMP0], i); break; }
+	__syncthreads();
+	int a = A.s.sc[SC_TMP0];
+	if (a > L - 1) a = L - 1 > 0 ? L - 1 : 0;
+	if (a >= L - 1) { // :56-60
+		__syncthreads();
+		if (tid == 0) { A.s.start[c] += a; A.s.len[c] = 0; A.s.nreads[c] = 0; }
+		__syncthreads();
+		return c;
+	}
+	for (int i = L - 1 - tid; i > a; i -= ASM_THREADS) if (sp[i] >= ms) { atomicMax(&A.s.sc[SC_TMP1], i); break; }
+	__syncthreads();
+	int b = A.s.sc[SC_TMP1];
+	if (b < a) b = a;
+	const int newlen = b - a + 1;
+	if (a == 0) {
+		__syncthreads();
+		if (tid == 0) A.s.len[c] = newlen;
+		__syncthreads();
+		return c;
+	}
+	const int d = asm_alloc(A);
+	if (d < 0) return c;
+	const uint32_t *s0 = A.p0(c), *s1 = A.p1(c), *sn = A.pn(c);
+	uint32_t *d0 = A.p0(d), *d1 = A.p1(d), *dn = A.pn(d);
+	uint16_t *dsup = A.sup(d);
+	for (int w = tid; w * 32 < newlen; w += ASM_THREADS) {
+		d0[w] = get32(s0, a + 32 * w); d1[w] = get32(s1, a + 32 * w); dn[w] = has_n ? get32(sn, a + 32 * w) : 0u;
+	}
+	for (int i = tid; i < newlen; i += ASM_THREADS) dsup[i] = sp[a + i];
+	__syncthreads();
+	if (tid == 0) { A.s.len[d] = newlen; A.s.nreads[d] = A.s.nreads[c]; A.s.start[d] = A.s.start[c] + a; }
+	asm_free(A, c);
+	__syncthreads();
+	return d;
+}
+
+// one pass of combine (:262-281): in[0..n_in) -> out[], returns the new list length
+__device__ int asm_combine_pass(Asm &A, uint16_t *in, int n_in, uint16_t *out, int min_support, int mo, bool has_n)
+{
+	const int tid = threadIdx.x;
+	int usedi = -1;
+	for (int i = 0; i < n_in; ++i) {
+		int c = in[i];
+		if (min_support > 0) {
+			const int nr = A.s.nreads[c];
+			const int c2 = asm_trim(A, c, nr < min_support ? nr : min_support, has_n);
+			if (c2 != c) { __syncthreads(); if (tid == 0) in[i] = (uint16_t)c2; __syncthreads(); c = c2; }
+		}
+		if (usedi < 0 && A.s.nreads[c] > 0) usedi = i;
+	}
+	if (usedi < 0) return 0;
+	__syncthreads();
+	if (tid == 0) out[0] = in[usedi];
+	__syncthreads();
+	int n_out = 1;
+	for (int i = 0; i < n_in; ++i) {
+		if (i == usedi) continue;
+		if (A.s.sc[SC_STATUS]) break;
+		const int q = in[i];
+		const AsmMatch m = asm_best_match(A, out, n_out, q, mo, has_n);
+		if (m.aligned) asm_merge(A, out, m.k, q, m.offset, has_n);
+		else if (A.s.nreads[q] > 0) {
+			__syncthreads();
+			if (tid == 0) out[n_out] = (uint16_t)q;
+			__syncthreads();
+			++n_out;
+		} else { asm_free(A, q); __syncthreads(); }
+	}
+	return n_out;
+}
+
+__global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs args)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	Asm A;
+	A.a = &args; A.nw = args.nw; A.cap = args.cap; A.ns = args.ns; A.offsets = 0;
+	A.planes = args.planes + (size_t)blockIdx.x * args.ns * 3 * args.nw;
+	A.supb = args.sup + (size_t)blockIdx.x * args.ns * args.cap;
+	{ // carve shared memory
+		unsigned char *p = smem_raw;
+		A.s.q0 = (uint32_t*)p; p += (size_t)A.nw * 4; A.s.q1 = (uint32_t*)p; p += (size_t)A.nw * 4; A.s.qn = (uint32_t*)p; p += (size_t)A.nw * 4;
+		A.s.len = (int*)p; p += (size_t)A.ns * 4; A.s.nreads = (int*)p; p += (size_t)A.ns * 4; A.s.start = (int*)p; p += (size_t)A.ns * 4;
+		A.s.corr = (int*)p; p += (size_t)3 * IDL_MAX_CORRECTIONS * 4;
+		A.s.best = (unsigned long long*)(((uintptr_t)p + 7) & ~(uintptr_t)7); p = (unsigned char*)(A.s.best + ASM_WARPS);
+		A.s.sc = (int*)p; p += SC_N * 4;
+		A.s.listA = (uint16_t*)p; p += (size_t)A.ns * 2; A.s.listB = (uint16_t*)p; p += (size_t)A.ns * 2; A.s.freestk = (uint16_t*)p;
+	}
+	const int tid = threadIdx.x;
+	const idl_params &P = args.P;
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) A.s.sc[SC_REGION] = (int)atomicAdd(&args.cnt->region_next, 1u);
+		__syncthreads();
+		const unsigned rg = (unsigned)A.s.sc[SC_REGION];
+		if (rg >= args.n_regions) break;
+		const idl_region R = args.region[rg];
+		// reset the slot allocator; detect non-ACGT bases in this region's reads and window
+		if (tid == 0) { A.s.sc[SC_NFREE] = A.ns; A.s.sc[SC_STATUS] = R.n_reads + 2 > (unsigned)A.ns ? IDL_RS_CONTIG_OVERFLOW : 0; A.s.sc[SC_HASN] = 0; }
+		for (int i = tid; i < A.ns; i += ASM_THREADS) A.s.freestk[i] = (uint16_t)(A.ns - 1 - i);
+		__syncthreads();
+		{
+			int any = 0;
+			for (unsigned j = 0; j < R.n_reads; ++j) {
+				const idl_read rd = args.read[R.read_begin + j];
+				const uint32_t *pn = args.seqn + (rd.seq_off >> 5);
+				for (int w = tid; w * 32 < rd.len; w += ASM_THREADS) any |= pn[w] != 0;
+			}
+			if (any) A.s.sc[SC_HASN] = 1;
+		}
+		// unpack the reference window to 0..4 codes for kernel 2 / glue (src/ksw2/ksw2.nim:127-132)
+		for (unsigned i = tid; i < R.ref_len; i += ASM_THREADS) {
+			const unsigned b = R.ref_off + i;
+			const unsigned isn = (args.refn[b >> 5] >> (b & 31)) & 1u;
+			args.refcodes[b] = isn ? 4 : (uint8_t)((args.ref2[b >> 4] >> (2 * (b & 15))) & 3u);
+		}
+		__syncthreads();
+		const bool has_n = A.s.sc[SC_HASN] != 0;
+		uint16_t *list = A.s.listA, *other = A.s.listB;
+		int nlist = 0;
+		// ---- assemble (src/indelope.nim:163-169): reads in input order
+		for (unsigned j = 0; j < R.n_reads && !A.s.sc[SC_STATUS]; ++j) {
+			const idl_read rd = args.read[R.read_begin + j];
+			if ((int)rd.mapq < P.asm_min_mapq) continue;  // :164
+			if (rd.flags & 1) continue;                  // :165
+			const int q = asm_alloc(A);
+			if (q < 0) break;
+			const int tl = rd.trim_len;
+			if (tl > A.cap) { if (tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; __syncthreads(); break; }
+			{ // make_contig (:143-150) from the packed, trimmed read
+				uint32_t *g0 = A.p0(q), *g1 = A.p1(q), *gn = A.pn(q);
+				uint16_t *gs = A.sup(q);
+				const unsigned base = rd.seq_off + rd.trim_a;
+				for (int w = tid; w * 32 < tl; w += ASM_THREADS) {
+					const unsigned b = base + 32u * w;         // first base of this plane word
+					const unsigned wi = b >> 4, sh = 2 * (b & 15);
+					const uint32_t w0 = args.seq2[wi], w1 = args.seq2[wi + 1], w2 = args.seq2[wi + 2];
+					const uint64_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+					const uint64_t bits = lo | (hi << 32);     // 32 bases, 2 bits each
+					uint32_t m = 0xffffffffu;
+					if (tl - 32 * w < 32) m = (1u << (tl - 32 * w)) - 1u;
+					g0[w] = compress_even(bits) & m;
+					g1[w] = compress_even(bits >> 1) & m;
+					gn[w] = has_n ? (get32(args.seqn, (int)b) & m) : 0u;
+				}
+				for (int i = tid; i < tl; i += ASM_THREADS) gs[i] = 1;
+				if (tid == 0) { A.s.len[q] = tl; A.s.nreads[q] = 1; A.s.start[q] = rd.start + rd.trim_a; }
+			}
+			__syncthreads();
+			const AsmMatch m = asm_best_match(A, list, nlist, q, rd.min_overlap, has_n);
+			if (m.aligned) asm_merge(A, list, m.k, q, m.offset, has_n);
+			else { __syncthreads(); if (tid == 0) list[nlist] = (uint16_t)q; __syncthreads(); ++nlist; }
+		}
+		const int n_pre = nlist; // :171
+		// ---- combine (:176 -> src/contig.nim:254-281): pass A without trimming, pass B with min_support
+		if (!A.s.sc[SC_STATUS]) {
+			int n2 = asm_combine_pass(A, list, nlist, other, 0, P.combine_min_overlap, has_n);
+			{ uint16_t *t = list; list = other; other = t; } nlist = n2;
+			if (!A.s.sc[SC_STATUS]) {
+				n2 = asm_combine_pass(A, list, nlist, other, P.combine_min_support, P.combine_min_overlap, has_n);
+				{ uint16_t *t = list; list = other; other = t; } nlist = n2;
+			}
+		}
+		__syncthreads();
+		// ---- results
+		const unsigned status = (unsigned)A.s.sc[SC_STATUS];
+		if (status) nlist = 0;
+		if (tid == 0) {
+			unsigned total = 0;
+			for (int i = 0; i < nlist; ++i) total += (unsigned)((A.s.len[list[i]] + 3) & ~3);
+			A.s.sc[SC_TMP0] = (int)atomicAdd(&args.cnt->n_contigs, (unsigned)nlist);
+			A.s.sc[SC_TMP1] = (int)atomicAdd(&args.cnt->n_contig_bases, total);
+		}
+		__syncthreads();
+		const unsigned cbegin = (unsigned)A.s.sc[SC_TMP0];
+		unsigned boff = (unsigned)A.s.sc[SC_TMP1];
+		if (tid == 0) {
+			idl_region_result rr; rr.status = status; rr.n_contigs_pre = n_pre; rr.n_contigs = nlist; rr.contig_begin = cbegin;
+			args.rres[rg] = rr;
+		}
+		if (cbegin + (unsigned)nlist > args.cap_contigs) { if (tid == 0) atomicOr(&args.cnt->overflow, 1u); continue; }
+		for (int i = 0; i < nlist; ++i) {
+			const int c = list[i];
+			const int L = A.s.len[c];
+			if (boff + (unsigned)L > args.cap_bases) { if (tid == 0) atomicOr(&args.cnt->overflow, 2u); break; }
+			const uint32_t *g0 = A.p0(c), *g1 = A.p1(c), *gn = A.pn(c);
+			const uint16_t *gs = A.sup(c);
+			for (int x = tid; x < L; x += ASM_THREADS) {
+				const unsigned code = ((g0[x >> 5] >> (x & 31)) & 1u) | (((g1[x >> 5] >> (x & 31)) & 1u) << 1);
+				const bool isn = has_n && ((gn[x >> 5] >> (x & 31)) & 1u);
+				args.ctg_codes[boff + x] = isn ? 4 : (uint8_t)code;
+				args.ctg_ascii[boff + x] = isn ? 'N' : "ACGT"[code];
+				if (args.ctg_sup) args.ctg_sup[boff + x] = gs[x];
+			}
+			if (tid == 0) {
+				idl_contig_result cr; cr.start = A.s.start[c]; cr.nreads = A.s.nreads[c]; cr.len = L; cr.seq_off = boff; cr.aln = -1; cr.region = rg;
+				// gates of src/indelope.nim:209-211
+				if ((P.stages & IDL_STAGE_ALIGN) && n_pre <= P.max_contigs && cr.nreads >= P.min_reads && L >= P.min_ctg_len) {
+					const unsigned ai = atomicAdd(&args.cnt->n_alns, 1u);
+					if (ai < args.cap_alns) {
+						cr.aln = (int)ai;
+						idl_aln_result ar; memset(&ar, 0, sizeof ar);
+						ar.region = rg; ar.contig = cbegin + i;
+						args.ares[ai] = ar;
+					} else atomicOr(&args.cnt->overflow, 4u);
+				}
+				args.cres[cbegin + i] = cr;
+			}
+			boff += (unsigned)((L + 3) & ~3);
+		}
+	}
+	if ((threadIdx.x & 31) == 0 && A.offsets) atomicAdd(&args.cnt->offsets_tested, A.offsets);
+}

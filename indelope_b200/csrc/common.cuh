@@ -1,0 +1,46 @@
+// indelope_b200/csrc/common.cuh -- shared device/host definitions of libindelope_cuda.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "indelope_cuda.h"
+
+#define IDL_WARP 32
+#define FULL_MASK 0xffffffffu
+#define KSW_NEG_INF (-0x40000000)
+
+// device-side global counters of one ticket (zeroed before the chain starts)
+struct DevCounters {
+	unsigned int region_next;      // work queue heads
+	unsigned int aln_next;
+	unsigned int al_next;
+	unsigned int n_contigs;        // bump allocators of the result pools
+	unsigned int n_contig_bases;
+	unsigned int n_alns;
+	unsigned int n_events;
+	unsigned int n_cigar_ops;
+	unsigned long long al_pack;    // (#AL events << 40) | total AL work items
+	unsigned int overflow;         // result pool overflow flags
+	unsigned int pad;
+	unsigned long long offsets_tested, dp_cells_a, dp_cells_b, dp_a, dp_b, kmer_reads, kmer_bytes, al_events;
+};
+
+// alignment scoring/band parameters of one call-site (src/ksw2/ksw2.nim:142,151-157)
+struct KswParams {
+	int8_t match, mismatch, q, e;
+	int w, zdrop;
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+// 32 bits of a bit-plane starting at bit position `pos` (pos may be negative: missing low bits read as 0).
+// The caller guarantees one padding word after the last word it can touch.
+__device__ __forceinline__ uint32_t get32(const uint32_t *plane, int pos)
+{
+	if (pos >= 0) {
+		const int w = pos >> 5, sh = pos & 31;
+		return __funnelshift_r(plane[w], plane[w + 1], sh);
+	}
+	const int sh = -pos;
+	return sh < 32 ? plane[0] << sh : 0u;
+}

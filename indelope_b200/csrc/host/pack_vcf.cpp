@@ -297,7 +297,7 @@ char *idlh_vcf_records(idlh_vcf *w, const idlh_roiset *rs, int64_t lo, const idl
 				         a.max_q, a.max_t, a.mqe, a.mqe_t, a.mte, a.mte_q, a.score);
 				d += b; d += cigar_text(cig, a.n_cigar) + "\t" + cigar_text(cig, a.n_cigar_trunc) + "\n";
 			}
-			if (a.n_events < 1 || a.n_events > P->max_events) continue; // src/indelope.nim:229
+			if (a.n_events < 1 || a.n_events > P->max_events || a.event_begin == IDL_NO_EVENTS || a.status) continue; // src/indelope.nim:229
 			for (int32_t ei = 0; ei < a.n_events; ++ei) {
 				const idl_event_result &e = res->event[a.event_begin + ei];
 				const bool have_kmers = e.reject != IDL_EV_SHORT && e.reject != IDL_EV_WINDOW;

@@ -1,0 +1,580 @@
+// indelope_b200/csrc/pipeline.cu -- libindelope_cuda.so: the C ABI of include/indelope_cuda.h.
+//
+// One context per GPU.  A context owns `n_streams` lanes; each lane has its stream, device copies of one batch,
+// the result pools, the kernel workspaces and pinned host buffers for the results.  idl_submit issues, on the
+// lane's stream: cudaMemcpyAsync H2D of the pinned batch -> assemble_kernel -> align_kernel (DP + glue) ->
+// kmer_kernel -> al_kernel -> D2H of the counters; idl_wait then copies back exactly the used prefix of every
+// result pool.  All kernels are persistent (grid sized from the SM count) and pull work from device-side queues,
+// so the host never needs the intermediate counts.  No CPU fallback exists.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "common.cuh"
+#include "ksw2.cuh"
+#include "assemble.cuh"
+#include "genotype.cuh"
+
+static_assert(sizeof(idl_region) == 48 && sizeof(idl_read) == 24, "batch records are part of the ABI");
+static_assert(sizeof(idl_region_result) == 16 && sizeof(idl_contig_result) == 24 && sizeof(idl_aln_result) == 72 && sizeof(idl_event_result) == 128,
+              "result records are part of the ABI");
+
+namespace {
+
+struct DevBuf {
+	void *p = nullptr; size_t cap = 0;
+	cudaError_t ensure(size_t bytes) {
+		if (bytes <= cap && p) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct HostBuf {
+	void *p = nullptr; size_t cap = 0;
+	cudaError_t ensure(size_t bytes) {
+		if (bytes <= cap && p) return cudaSuccess;
+		if (p) cudaFreeHost(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+enum { EV_START = 0, EV_H2D, EV_ASM, EV_ALN, EV_KMER, EV_AL, EV_END, EV_N };
+
+struct Lane {
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[EV_N] = {};
+	// device batch
+	DevBuf region, read, seq2, seqn, ref2, refn;
+	// device results and intermediates
+	DevBuf rres, cres, ares, eres, cigar, ctg_ascii, ctg_codes, ctg_sup, refcodes, al_list, cnt;
+	// workspaces
+	DevBuf planes, sup, pmat, cig_scratch, spill;
+	// pinned host results
+	HostBuf h_rres, h_cres, h_ares, h_eres, h_cigar, h_seq, h_sup, h_cnt;
+	// state
+	uint64_t ticket = 0; int state = 0; // 0 free, 1 in flight, 2 done (results valid)
+	bool resident = false;              // device batch uploaded by idl_upload
+	bool payload = true;                // fetch result arrays in idl_wait
+	size_t n_regions = 0, n_reads = 0, n_seq_bases = 0, n_ref_bases = 0;
+	unsigned cap_contigs = 0, cap_bases = 0, cap_alns = 0, cap_events = 0, cap_cigar = 0;
+	unsigned launches = 0;
+	idl_results res;
+};
+
+} // namespace
+
+struct idl_ctx {
+	int device = 0; idl_params P; int n_sm = 148;
+	std::vector<Lane> lanes;
+	uint64_t next_ticket = 1;
+	int asm_ctas = 0, dp_ctas = 0, ns = 0, nw = 0;
+	size_t p_cap = 1u << 20; int cig_cap = 4096; int spill_tcap = 0;
+	char err[512] = {0};
+};
+
+namespace {
+
+int fail(idl_ctx *c, cudaError_t e, const char *what)
+{
+	if (c) snprintf(c->err, sizeof c->err, "%s: %s", what, cudaGetErrorString(e));
+	return IDL_E_CUDA;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, e_, #call); } while (0)
+
+size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+} // namespace
+
+extern "C" {
+
+void idl_default_params(idl_params *p)
+{
+	memset(p, 0, sizeof *p);
+	p->abi_version = IDL_ABI_VERSION;
+	p->min_reads = 3; p->min_ctg_len = 73; p->min_event_len = 4;
+	p->asm_min_mapq = 20; p->combine_min_support = 3; p->combine_min_overlap = 65; p->max_contigs = 20;
+	p->stop_min_mapq = 5; p->window_pad = 63; p->match = 1; p->mismatch = -2;
+	p->a_gapo = 4; p->a_gape = 1; p->a_bw = 50; p->a_zdrop = 400;
+	p->b_gapo = 5; p->b_gape = 1; p->b_bw = -1; p->b_zdrop = -1;
+	p->max_events = 4; p->count_min_mapq = 10;
+	p->max_contig_len = 4096; p->max_read_len = 512; p->max_reads_per_region = 601; p->n_streams = 2;
+	p->stages = IDL_STAGE_ALL; p->out_flags = 0;
+}
+
+const char *idl_strerror(int s)
+{
+	switch (s) {
+	case IDL_OK: return "ok";
+	case IDL_E_NO_DEVICE: return "no CUDA device (libindelope_cuda has no CPU path)";
+	case IDL_E_CUDA: return "CUDA error (see idl_last_cuda_error)";
+	case IDL_E_ARG: return "bad argument";
+	case IDL_E_NOMEM: return "out of memory";
+	case IDL_E_CAPACITY: return "batch exceeds allocated capacity";
+	case IDL_E_TICKET: return "unknown ticket";
+	case IDL_E_BUSY: return "no free lane: wait for and release an earlier ticket";
+	default: return "unknown status";
+	}
+}
+
+const char *idl_last_cuda_error(idl_ctx *ctx) { return ctx ? ctx->err : ""; }
+
+int idl_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+int idl_create(int device, const idl_params *p, idl_ctx **out)
+{
+	if (!out || !p) return IDL_E_ARG;
+	*out = nullptr;
+	if (p->abi_version != IDL_ABI_VERSION) return IDL_E_ARG;
+	if (p->max_contig_len < 64 || p->max_contig_len % 64 || p->max_contig_len > 32768 || p->max_reads_per_region < 1 || p->max_reads_per_region > 4000 ||
+	    p->max_read_len < 1 || p->max_read_len > 4096 || p->n_streams < 1 || p->n_streams > 8 || p->max_events < 1 || p->max_events > IDL_MAX_EVENTS)
+		return IDL_E_ARG;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return IDL_E_NO_DEVICE;
+	if (device < 0 || device >= n) return IDL_E_ARG;
+	idl_ctx *ctx = new (std::nothrow) idl_ctx();
+	if (!ctx) return IDL_E_NOMEM;
+	ctx->device = device; ctx->P = *p;
+	cudaError_t e = cudaSetDevice(device);
+	if (e != cudaSuccess) { delete ctx; return IDL_E_CUDA; }
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->n_sm = prop.multiProcessorCount;
+	ctx->ns = p->max_reads_per_region + 2;
+	ctx->nw = p->max_contig_len / 32 + 2;
+	ctx->asm_ctas = ctx->n_sm * 2;
+	ctx->dp_ctas = ctx->n_sm * 3;
+	ctx->spill_tcap = (int)round_up((size_t)p->max_contig_len + 1024, 16);
+	ctx->lanes.resize((size_t)p->n_streams);
+	for (Lane &L : ctx->lanes) {
+		if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { idl_destroy(ctx); return IDL_E_CUDA; }
+		for (auto &ev : L.ev) if (cudaEventCreate(&ev) != cudaSuccess) { idl_destroy(ctx); return IDL_E_CUDA; }
+	}
+	// opt in to large dynamic shared memory for the DP kernels
+	cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(al_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	*out = ctx;
+	return IDL_OK;
+}
+
+void idl_destroy(idl_ctx *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	for (Lane &L : ctx->lanes) {
+		if (L.stream) cudaStreamSynchronize(L.stream);
+		for (DevBuf *b : {&L.region, &L.read, &L.seq2, &L.seqn, &L.ref2, &L.refn, &L.rres, &L.cres, &L.ares, &L.eres, &L.cigar, &L.ctg_ascii, &L.ctg_codes,
+		                  &L.ctg_sup, &L.refcodes, &L.al_list, &L.cnt, &L.planes, &L.sup, &L.pmat, &L.cig_scratch, &L.spill})
+			b->release();
+		for (HostBuf *b : {&L.h_rres, &L.h_cres, &L.h_ares, &L.h_eres, &L.h_cigar, &L.h_seq, &L.h_sup, &L.h_cnt}) b->release();
+		for (auto &ev : L.ev) if (ev) cudaEventDestroy(ev);
+		if (L.stream) cudaStreamDestroy(L.stream);
+	}
+	delete ctx;
+}
+
+int idl_batch_alloc(idl_ctx *ctx, size_t max_regions, size_t max_reads, size_t max_seq_bases, size_t max_ref_bases, idl_batch **out)
+{
+	if (!ctx || !out) return IDL_E_ARG;
+	*out = nullptr;
+	cudaSetDevice(ctx->device);
+	idl_batch *b = (idl_batch*)calloc(1, sizeof(idl_batch));
+	if (!b) return IDL_E_NOMEM;
+	max_seq_bases = round_up(max_seq_bases, 64); max_ref_bases = round_up(max_ref_bases, 64);
+	b->cap_regions = max_regions; b->cap_reads = max_reads; b->cap_seq_bases = max_seq_bases; b->cap_ref_bases = max_ref_bases;
+	// the library owns pinned memory: the host language never hands GC memory to CUDA
+	cudaError_t e = cudaSuccess;
+	auto pin = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaHostAlloc(p, bytes, cudaHostAllocDefault); if (e == cudaSuccess) memset(*p, 0, bytes); };
+	pin((void**)&b->region, (max_regions + 1) * sizeof(idl_region));
+	pin((void**)&b->read, (max_reads + 1) * sizeof(idl_read));
+	pin((void**)&b->seq2, max_seq_bases / 4 + 16); pin((void**)&b->seqn, max_seq_bases / 8 + 16);
+	pin((void**)&b->ref2, max_ref_bases / 4 + 16); pin((void**)&b->refn, max_ref_bases / 8 + 16);
+	if (e != cudaSuccess) { idl_batch_free(ctx, b); return fail(ctx, e, "cudaHostAlloc(batch)"); }
+	*out = b;
+	return IDL_OK;
+}
+
+void idl_batch_free(idl_ctx *ctx, idl_batch *b)
+{
+	(void)ctx;
+	if (!b) return;
+	for (void *p : {(void*)b->region, (void*)b->read, (void*)b->seq2, (void*)b->seqn, (void*)b->ref2, (void*)b->refn}) if (p) cudaFreeHost(p);
+	free(b);
+}
+
+} // extern "C"
+
+namespace {
+
+int check_batch(const idl_ctx *ctx, const idl_batch *b)
+{
+	if (!b || b->n_regions > b->cap_regions || b->n_reads > b->cap_reads || b->n_seq_bases > b->cap_seq_bases || b->n_ref_bases > b->cap_ref_bases) return IDL_E_CAPACITY;
+	if (b->n_seq_bases % 64 || b->n_ref_bases % 64) return IDL_E_ARG;
+	if (b->n_seq_bases >= (1ull << 32) || b->n_ref_bases >= (1ull << 32) || b->n_reads >= (1ull << 31)) return IDL_E_CAPACITY;
+	for (size_t i = 0; i < b->n_regions; ++i) {
+		const idl_region &r = b->region[i];
+		if ((size_t)r.read_begin + r.n_reads > b->n_reads || (size_t)r.ref_off + r.ref_len > b->n_ref_bases) return IDL_E_ARG;
+		if ((int)r.n_reads + 2 > ctx->ns) return IDL_E_CAPACITY;
+	}
+	return IDL_OK;
+}
+
+// device copies of the batch + sizing of every pool (shared by submit and upload)
+int stage_batch(idl_ctx *ctx, Lane &L, const idl_batch *b, bool copy)
+{
+	L.n_regions = b->n_regions; L.n_reads = b->n_reads; L.n_seq_bases = b->n_seq_bases; L.n_ref_bases = b->n_ref_bases;
+	const size_t s2 = b->n_seq_bases / 4 + 16, sn = b->n_seq_bases / 8 + 16, r2 = b->n_ref_bases / 4 + 16, rn = b->n_ref_bases / 8 + 16;
+	CK(L.region.ensure((b->n_regions + 1) * sizeof(idl_region))); CK(L.read.ensure((b->n_reads + 1) * sizeof(idl_read)));
+	CK(L.seq2.ensure(s2)); CK(L.seqn.ensure(sn)); CK(L.ref2.ensure(r2)); CK(L.refn.ensure(rn));
+	if (copy) {
+		CK(cudaMemcpyAsync(L.region.p, b->region, b->n_regions * sizeof(idl_region), cudaMemcpyHostToDevice, L.stream));
+		CK(cudaMemcpyAsync(L.read.p, b->read, b->n_reads * sizeof(idl_read), cudaMemcpyHostToDevice, L.stream));
+		CK(cudaMemcpyAsync(L.seq2.p, b->seq2, s2, cudaMemcpyHostToDevice, L.stream));
+		CK(cudaMemcpyAsync(L.seqn.p, b->seqn, sn, cudaMemcpyHostToDevice, L.stream));
+		CK(cudaMemcpyAsync(L.ref2.p, b->ref2, r2, cudaMemcpyHostToDevice, L.stream));
+		CK(cudaMemcpyAsync(L.refn.p, b->refn, rn, cudaMemcpyHostToDevice, L.stream));
+	}
+	return IDL_OK;
+}
+
+int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
+{
+	const idl_params &P = ctx->P;
+	// pool capacities: every contig holds >= 1 read; an aligned contig holds >= max(1, min_reads) reads and a region aligns <= max_contigs
+	int max_trim = 1; unsigned max_ref = 16;
+	for (size_t i = 0; i < b->n_reads; ++i) max_trim = std::max<int>(max_trim, b->read[i].trim_len);
+	for (size_t i = 0; i < b->n_regions; ++i) max_ref = std::max(max_ref, b->region[i].ref_len);
+	L.cap_contigs = (unsigned)b->n_reads + 1;
+	L.cap_bases = (unsigned)std::min<size_t>(b->n_seq_bases + 4 * b->n_reads + 64, 0xfffffff0u);
+	L.cap_alns = (unsigned)std::min<size_t>(b->n_reads / (size_t)std::max(1, P.min_reads) + 1, (size_t)P.max_contigs * b->n_regions + 1);
+	L.cap_events = L.cap_alns * (unsigned)P.max_events;
+	L.cap_cigar = L.cap_alns * 48u + 4096u;
+	CK(L.rres.ensure((b->n_regions + 1) * sizeof(idl_region_result)));
+	CK(L.cres.ensure((size_t)L.cap_contigs * sizeof(idl_contig_result)));
+	CK(L.ares.ensure((size_t)L.cap_alns * sizeof(idl_aln_result)));
+	CK(L.eres.ensure((size_t)L.cap_events * sizeof(idl_event_result)));
+	CK(L.cigar.ensure((size_t)L.cap_cigar * 4));
+	CK(L.ctg_ascii.ensure(L.cap_bases)); CK(L.ctg_codes.ensure(L.cap_bases));
+	if (P.out_flags & IDL_OUT_SUPPORT) CK(L.ctg_sup.ensure((size_t)L.cap_bases * 4));
+	CK(L.refcodes.ensure(b->n_ref_bases + 64));
+	CK(L.al_list.ensure((size_t)L.cap_events * sizeof(AlEntry) + 16));
+	CK(L.cnt.ensure(sizeof(DevCounters)));
+	// workspaces
+	const int asm_ctas = (int)std::max<size_t>(1, std::min<size_t>(b->n_regions, (size_t)ctx->asm_ctas));
+	CK(L.planes.ensure((size_t)ctx->asm_ctas * ctx->ns * 3 * ctx->nw * 4));
+	CK(L.sup.ensure((size_t)ctx->asm_ctas * ctx->ns * P.max_contig_len * 2));
+	const size_t n_dp_warps = (size_t)ctx->dp_ctas * DP_WARPS;
+	CK(L.pmat.ensure(n_dp_warps * ctx->p_cap));
+	CK(L.cig_scratch.ensure(n_dp_warps * (size_t)ctx->cig_cap * 4));
+	CK(L.spill.ensure(n_dp_warps * ksw_lane_bytes(ctx->spill_tcap)));
+	CK(cudaMemsetAsync(L.cnt.p, 0, sizeof(DevCounters), L.stream));
+	L.launches = 0;
+
+	AsmArgs a; memset(&a, 0, sizeof a);
+	a.region = (const idl_region*)L.region.p; a.read = (const idl_read*)L.read.p;
+	a.seq2 = (const uint32_t*)L.seq2.p; a.seqn = (const uint32_t*)L.seqn.p; a.ref2 = (const uint32_t*)L.ref2.p; a.refn = (const uint32_t*)L.refn.p;
+	a.n_regions = (unsigned)b->n_regions; a.P = P;
+	a.planes = (uint32_t*)L.planes.p; a.sup = (uint16_t*)L.sup.p; a.ns = ctx->ns; a.nw = ctx->nw; a.cap = P.max_contig_len;
+	a.rres = (idl_region_result*)L.rres.p; a.cres = (idl_contig_result*)L.cres.p; a.ares = (idl_aln_result*)L.ares.p;
+	a.ctg_ascii = (char*)L.ctg_ascii.p; a.ctg_codes = (uint8_t*)L.ctg_codes.p; a.ctg_sup = (P.out_flags & IDL_OUT_SUPPORT) ? (uint32_t*)L.ctg_sup.p : nullptr;
+	a.refcodes = (uint8_t*)L.refcodes.p;
+	a.cap_contigs = L.cap_contigs; a.cap_bases = L.cap_bases; a.cap_alns = L.cap_alns;
+	a.cnt = (DevCounters*)L.cnt.p;
+	if (b->n_regions > 0 && (P.stages & IDL_STAGE_ASSEMBLE)) {
+		assemble_kernel<<<asm_ctas, ASM_THREADS, asm_smem_bytes(ctx->ns, ctx->nw), L.stream>>>(a);
+		CK(cudaGetLastError()); L.launches++;
+	}
+	CK(cudaEventRecord(L.ev[EV_ASM], L.stream));
+
+	GenoArgs g; memset(&g, 0, sizeof g);
+	g.region = a.region; g.read = a.read; g.seq2 = a.seq2; g.seqn = a.seqn; g.refcodes = a.refcodes; g.ctg_codes = a.ctg_codes;
+	g.rres = a.rres; g.cres = a.cres; g.ares = a.ares; g.eres = (idl_event_result*)L.eres.p; g.cigar = (uint32_t*)L.cigar.p;
+	g.cap_events = L.cap_events; g.cap_cigar = L.cap_cigar; g.cap_al = L.cap_events; g.cap_alns = L.cap_alns; g.al_list = (AlEntry*)L.al_list.p;
+	g.P = P; g.cnt = a.cnt;
+	g.pmat = (uint8_t*)L.pmat.p; g.p_cap = ctx->p_cap; g.cig_scratch = (uint32_t*)L.cig_scratch.p; g.cig_cap = ctx->cig_cap;
+	g.spill = (int8_t*)L.spill.p; g.spill_tcap = ctx->spill_tcap;
+	g.t_cap = (int)std::min<size_t>(round_up(max_ref, 16), 2048);
+	if (b->n_regions > 0 && (P.stages & IDL_STAGE_ALIGN)) {
+		g.hr = next_pow2(std::max(P.a_bw < 0 ? P.max_contig_len : P.a_bw + 1, 1) + 2); g.qcap = 0;
+		const size_t smem = DP_WARPS * dp_smem_per_warp(g.t_cap, g.hr, g.qcap);
+		align_kernel<<<ctx->dp_ctas, DP_THREADS, smem, L.stream>>>(g);
+		CK(cudaGetLastError()); L.launches++;
+	}
+	CK(cudaEventRecord(L.ev[EV_ALN], L.stream));
+	if (b->n_regions > 0 && (P.stages & IDL_STAGE_GENOTYPE) && (P.stages & IDL_STAGE_ALIGN)) {
+		kmer_kernel<<<ctx->n_sm * 8, KMER_THREADS, 0, L.stream>>>(g);
+		CK(cudaGetLastError()); L.launches++;
+		CK(cudaEventRecord(L.ev[EV_KMER], L.stream));
+		g.hr = next_pow2((P.b_bw < 0 ? max_trim : std::min(max_trim, P.b_bw + 1)) + 2); g.qcap = (int)round_up((size_t)max_trim, 16);
+		const size_t smem = DP_WARPS * dp_smem_per_warp(g.t_cap, g.hr, g.qcap);
+		al_kernel<<<ctx->dp_ctas, DP_THREADS, smem, L.stream>>>(g);
+		CK(cudaGetLastError()); L.launches++;
+	} else CK(cudaEventRecord(L.ev[EV_KMER], L.stream));
+	CK(cudaEventRecord(L.ev[EV_AL], L.stream));
+	CK(L.h_cnt.ensure(sizeof(DevCounters)));
+	CK(cudaMemcpyAsync(L.h_cnt.p, L.cnt.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, L.stream));
+	CK(cudaEventRecord(L.ev[EV_END], L.stream));
+	return IDL_OK;
+}
+
+Lane *find_lane(idl_ctx *ctx, uint64_t ticket)
+{
+	for (Lane &L : ctx->lanes) if (L.state != 0 && L.ticket == ticket) return &L;
+	return nullptr;
+}
+
+} // namespace
+
+extern "C" {
+
+int idl_submit(idl_ctx *ctx, idl_batch *b, uint64_t *ticket)
+{
+	if (!ctx || !b || !ticket) return IDL_E_ARG;
+	int rc = check_batch(ctx, b);
+	if (rc) return rc;
+	cudaSetDevice(ctx->device);
+	Lane *Lp = nullptr;
+	for (size_t k = 0; k < ctx->lanes.size(); ++k) { Lane &c = ctx->lanes[(ctx->next_ticket + k) % ctx->lanes.size()]; if (c.state == 0) { Lp = &c; break; } }
+	if (!Lp) return IDL_E_BUSY;
+	Lane &L = *Lp;
+	L.resident = false; L.payload = true;
+	CK(cudaEventRecord(L.ev[EV_START], L.stream));
+	rc = stage_batch(ctx, L, b, true);
+	if (rc) return rc;
+	CK(cudaEventRecord(L.ev[EV_H2D], L.stream));
+	rc = launch_chain(ctx, L, b);
+	if (rc) return rc;
+	L.ticket = ctx->next_ticket++; L.state = 1;
+	*ticket = L.ticket;
+	return IDL_OK;
+}
+
+int idl_upload(idl_ctx *ctx, idl_batch *b)
+{
+	if (!ctx || !b) return IDL_E_ARG;
+	int rc = check_batch(ctx, b);
+	if (rc) return rc;
+	cudaSetDevice(ctx->device);
+	Lane &L = ctx->lanes[0];
+	if (L.state != 0) return IDL_E_BUSY;
+	rc = stage_batch(ctx, L, b, true);
+	if (rc) return rc;
+	CK(cudaStreamSynchronize(L.stream));
+	L.resident = true;
+	return IDL_OK;
+}
+
+int idl_run_resident(idl_ctx *ctx, idl_batch *b, uint64_t *ticket)
+{
+	if (!ctx || !b || !ticket) return IDL_E_ARG;
+	cudaSetDevice(ctx->device);
+	Lane &L = ctx->lanes[0];
+	if (L.state != 0) return IDL_E_BUSY;
+	if (!L.resident || L.n_regions != b->n_regions || L.n_reads != b->n_reads) return IDL_E_ARG;
+	L.payload = false;
+	CK(cudaEventRecord(L.ev[EV_START], L.stream));
+	CK(cudaEventRecord(L.ev[EV_H2D], L.stream));
+	int rc = launch_chain(ctx, L, b);
+	if (rc) return rc;
+	L.ticket = ctx->next_ticket++; L.state = 1;
+	*ticket = L.ticket;
+	return IDL_OK;
+}
+
+int idl_wait(idl_ctx *ctx, uint64_t ticket, const idl_results **out)
+{
+	if (!ctx || !out) return IDL_E_ARG;
+	Lane *Lp = find_lane(ctx, ticket);
+	if (!Lp) return IDL_E_TICKET;
+	Lane &L = *Lp;
+	cudaSetDevice(ctx->device);
+	if (L.state == 1) {
+		CK(cudaStreamSynchronize(L.stream));
+		const DevCounters *c = (const DevCounters*)L.h_cnt.p;
+		idl_results &r = L.res; memset(&r, 0, sizeof r);
+		r.n_regions = L.n_regions;
+		r.n_contigs = std::min(c->n_contigs, L.cap_contigs);
+		r.n_contig_bases = std::min(c->n_contig_bases, L.cap_bases);
+		r.n_alns = std::min(c->n_alns, L.cap_alns);
+		r.n_events = std::min(c->n_events, L.cap_events);
+		r.n_cigar_ops = std::min(c->n_cigar_ops, L.cap_cigar);
+		float t_d2h = 0;
+		if (L.payload) {
+			cudaEvent_t a0, a1; CK(cudaEventCreate(&a0)); CK(cudaEventCreate(&a1)); // the lane's events still hold unread timings
+			CK(L.h_rres.ensure((r.n_regions + 1) * sizeof(idl_region_result))); CK(L.h_cres.ensure((r.n_contigs + 1) * sizeof(idl_contig_result)));
+			CK(L.h_ares.ensure((r.n_alns + 1) * sizeof(idl_aln_result))); CK(L.h_eres.ensure((r.n_events + 1) * sizeof(idl_event_result)));
+			CK(L.h_cigar.ensure((r.n_cigar_ops + 1) * 4)); CK(L.h_seq.ensure(r.n_contig_bases + 16));
+			CK(cudaEventRecord(a0, L.stream));
+			if (r.n_regions) CK(cudaMemcpyAsync(L.h_rres.p, L.rres.p, r.n_regions * sizeof(idl_region_result), cudaMemcpyDeviceToHost, L.stream));
+			if (r.n_contigs) CK(cudaMemcpyAsync(L.h_cres.p, L.cres.p, r.n_contigs * sizeof(idl_contig_result), cudaMemcpyDeviceToHost, L.stream));
+			if (r.n_alns) CK(cudaMemcpyAsync(L.h_ares.p, L.ares.p, r.n_alns * sizeof(idl_aln_result), cudaMemcpyDeviceToHost, L.stream));
+			if (r.n_events) CK(cudaMemcpyAsync(L.h_eres.p, L.eres.p, r.n_events * sizeof(idl_event_result), cudaMemcpyDeviceToHost, L.stream));
+			if (r.n_cigar_ops) CK(cudaMemcpyAsync(L.h_cigar.p, L.cigar.p, r.n_cigar_ops * 4, cudaMemcpyDeviceToHost, L.stream));
+			if (r.n_contig_bases) CK(cudaMemcpyAsync(L.h_seq.p, L.ctg_ascii.p, r.n_contig_bases, cudaMemcpyDeviceToHost, L.stream));
+			if (ctx->P.out_flags & IDL_OUT_SUPPORT) {
+				CK(L.h_sup.ensure((r.n_contig_bases + 4) * 4));
+				if (r.n_contig_bases) CK(cudaMemcpyAsync(L.h_sup.p, L.ctg_sup.p, r.n_contig_bases * 4, cudaMemcpyDeviceToHost, L.stream));
+			}
+			CK(cudaEventRecord(a1, L.stream));
+			CK(cudaStreamSynchronize(L.stream));
+			cudaEventElapsedTime(&t_d2h, a0, a1);
+			cudaEventDestroy(a0); cudaEventDestroy(a1);
+			r.region = (const idl_region_result*)L.h_rres.p; r.contig = (const idl_contig_result*)L.h_cres.p; r.aln = (const idl_aln_result*)L.h_ares.p;
+			r.event = (const idl_event_result*)L.h_eres.p; r.cigar = (const uint32_t*)L.h_cigar.p; r.contig_seq = (const char*)L.h_seq.p;
+			r.contig_support = (ctx->P.out_flags & IDL_OUT_SUPPORT) ? (const uint32_t*)L.h_sup.p : nullptr;
+		}
+		cudaEventElapsedTime(&r.ms_h2d, L.ev[EV_START], L.ev[EV_H2D]);
+		cudaEventElapsedTime(&r.ms_assemble, L.ev[EV_H2D], L.ev[EV_ASM]);
+		cudaEventElapsedTime(&r.ms_align, L.ev[EV_ASM], L.ev[EV_ALN]);
+		cudaEventElapsedTime(&r.ms_genotype, L.ev[EV_ALN], L.ev[EV_KMER]);
+		cudaEventElapsedTime(&r.ms_al, L.ev[EV_KMER], L.ev[EV_AL]);
+		cudaEventElapsedTime(&r.ms_total, L.ev[EV_START], L.ev[EV_END]);
+		r.ms_d2h = t_d2h; r.ms_total += t_d2h;
+		r.offsets_tested = c->offsets_tested; r.dp_cells_a = c->dp_cells_a; r.dp_cells_b = c->dp_cells_b; r.dp_a = c->dp_a; r.dp_b = c->dp_b;
+		r.kmer_reads = c->kmer_reads; r.kmer_bytes = c->kmer_bytes; r.al_events = c->al_events;
+		r.kernel_launches = L.launches;
+		if (c->overflow) snprintf(ctx->err, sizeof ctx->err, "result pool overflow mask 0x%x", c->overflow);
+		L.state = 2;
+		if (c->overflow) { *out = &L.res; return IDL_E_CAPACITY; }
+	}
+	*out = &L.res;
+	return IDL_OK;
+}
+
+int idl_release(idl_ctx *ctx, uint64_t ticket)
+{
+	if (!ctx) return IDL_E_ARG;
+	Lane *L = find_lane(ctx, ticket);
+	if (!L) return IDL_E_TICKET;
+	if (L->state == 1) { cudaSetDevice(ctx->device); cudaStreamSynchronize(L->stream); }
+	L->state = 0;
+	return IDL_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// unit-level entry point: batch of independent alignments through kernel 2
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct KswBatchArgs {
+	unsigned n; const uint8_t *query, *target; const unsigned long long *q_off, *t_off;
+	KswParams kp; idl_ez *out; uint32_t *cigar; unsigned long long *cigar_off; unsigned cigar_cap;
+	unsigned *next; unsigned *cig_used;
+	uint8_t *pmat; size_t p_cap; uint32_t *cig_scratch; int cig_cap; int t_cap, hr;
+};
+
+__global__ void __launch_bounds__(DP_THREADS) ksw2_batch_kernel(KswBatchArgs a)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int lane = lane_id();
+	const size_t per = ((ksw_lane_bytes(a.t_cap) + 15) & ~(size_t)15) + (size_t)a.hr * 4;
+	int8_t *lanes = (int8_t*)(smem_raw + per * warp_id());
+	int *H = (int*)(smem_raw + per * warp_id() + ((ksw_lane_bytes(a.t_cap) + 15) & ~(size_t)15));
+	const size_t gw = (size_t)blockIdx.x * DP_WARPS + warp_id();
+	uint8_t *pmat = a.pmat + gw * a.p_cap;
+	uint32_t *cig = a.cig_scratch + gw * (size_t)a.cig_cap;
+	for (;;) {
+		unsigned i = 0;
+		if (lane == 0) i = atomicAdd(a.next, 1u);
+		i = __shfl_sync(FULL_MASK, i, 0);
+		if (i >= a.n) break;
+		const int qlen = (int)(a.q_off[i + 1] - a.q_off[i]), tlen = (int)(a.t_off[i + 1] - a.t_off[i]);
+		KswOut o;
+		ksw2_warp(qlen, a.query + a.q_off[i], tlen, a.target + a.t_off[i], a.kp, lanes, a.t_cap, H, a.hr, pmat, a.p_cap, cig, a.cig_cap, o);
+		unsigned coff = 0;
+		if (lane == 0) coff = atomicAdd(a.cig_used, (unsigned)o.n_cigar);
+		coff = __shfl_sync(FULL_MASK, coff, 0);
+		int status = o.status;
+		if (coff + (unsigned)o.n_cigar > a.cigar_cap) status = KSW_ST_CIGCAP;
+		else for (int k = lane; k < o.n_cigar; k += 32) a.cigar[coff + k] = cig[o.n_cigar - 1 - k];
+		if (lane == 0) {
+			idl_ez e; e.max = o.max; e.zdropped = o.zdropped; e.max_q = o.max_q; e.max_t = o.max_t; e.mqe = o.mqe; e.mqe_t = o.mqe_t; e.mte = o.mte;
+			e.mte_q = o.mte_q; e.score = o.score; e.n_cigar = o.n_cigar; e.status = status; e.reserved = 0; e.cells = o.cells;
+			a.out[i] = e; a.cigar_off[i] = coff;
+		}
+		__syncwarp();
+	}
+}
+
+} // namespace
+
+extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, const uint64_t *q_off, const uint8_t *target, const uint64_t *t_off,
+                              int8_t match, int8_t mismatch, int8_t gapo, int8_t gape, int w, int zdrop,
+                              idl_ez *out, uint32_t *cigar, uint64_t *cigar_off, size_t cigar_cap, float *kernel_ms)
+{
+	if (!ctx || !query || !target || !q_off || !t_off || !out || !cigar || !cigar_off) return IDL_E_ARG;
+	if (n == 0) return IDL_OK;
+	if (n >= (1ull << 31) || cigar_cap >= (1ull << 32)) return IDL_E_ARG;
+	cudaSetDevice(ctx->device);
+	int max_q = 1, max_t = 1; size_t max_p = 0;
+	for (size_t i = 0; i < n; ++i) {
+		const int ql = (int)(q_off[i + 1] - q_off[i]), tl = (int)(t_off[i + 1] - t_off[i]);
+		max_q = std::max(max_q, ql); max_t = std::max(max_t, tl);
+		const int ww = w < 0 ? std::max(ql, tl) : w;
+		const int band = std::min(std::min(ql, tl), ww + 1);
+		max_p = std::max(max_p, (size_t)std::max(ql + tl - 1, 0) * (size_t)(((band + 15) / 16 + 1) * 16));
+	}
+	const int band_all = std::min(std::min(max_q, max_t), (w < 0 ? std::max(max_q, max_t) : w) + 1);
+	KswBatchArgs a; memset(&a, 0, sizeof a);
+	a.n = (unsigned)n; a.kp.match = match; a.kp.mismatch = mismatch; a.kp.q = gapo; a.kp.e = gape; a.kp.w = w; a.kp.zdrop = zdrop;
+	a.t_cap = (int)round_up((size_t)max_t, 16); a.hr = next_pow2(band_all + 2);
+	a.p_cap = round_up(max_p + 16, 256); a.cig_cap = max_q + max_t + 8; a.cigar_cap = (unsigned)cigar_cap;
+	const size_t per = ((ksw_lane_bytes(a.t_cap) + 15) & ~(size_t)15) + (size_t)a.hr * 4;
+	const size_t smem = per * DP_WARPS;
+	if (smem > 200 * 1024) return IDL_E_CAPACITY;
+	cudaFuncSetAttribute(ksw2_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	const int ctas = (int)std::min<size_t>((n + DP_WARPS - 1) / DP_WARPS, (size_t)ctx->n_sm * 2);
+	const size_t nwarps = (size_t)ctas * DP_WARPS;
+	const size_t qbytes = q_off[n], tbytes = t_off[n];
+	DevBuf dq, dt, dqo, dto, dout, dcig, dcoff, dmisc, dp, dscr;
+	cudaStream_t st = ctx->lanes[0].stream;
+	int rc = IDL_OK;
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	auto body = [&]() -> int {
+		CK(dq.ensure(qbytes + 16)); CK(dt.ensure(tbytes + 16)); CK(dqo.ensure((n + 1) * 8)); CK(dto.ensure((n + 1) * 8));
+		CK(dout.ensure(n * sizeof(idl_ez))); CK(dcig.ensure(cigar_cap * 4 + 16)); CK(dcoff.ensure(n * 8)); CK(dmisc.ensure(64));
+		CK(dp.ensure(nwarps * a.p_cap)); CK(dscr.ensure(nwarps * (size_t)a.cig_cap * 4));
+		CK(cudaMemcpyAsync(dq.p, query, qbytes, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(dt.p, target, tbytes, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(dqo.p, q_off, (n + 1) * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(dto.p, t_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+		CK(cudaMemsetAsync(dmisc.p, 0, 64, st));
+		a.query = (const uint8_t*)dq.p; a.target = (const uint8_t*)dt.p; a.q_off = (const unsigned long long*)dqo.p; a.t_off = (const unsigned long long*)dto.p;
+		a.out = (idl_ez*)dout.p; a.cigar = (uint32_t*)dcig.p; a.cigar_off = (unsigned long long*)dcoff.p;
+		a.next = (unsigned*)dmisc.p; a.cig_used = (unsigned*)dmisc.p + 1; a.pmat = (uint8_t*)dp.p; a.cig_scratch = (uint32_t*)dscr.p;
+		CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+		CK(cudaEventRecord(e0, st));
+		ksw2_batch_kernel<<<ctas, DP_THREADS, smem, st>>>(a);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(e1, st));
+		CK(cudaMemcpyAsync(out, dout.p, n * sizeof(idl_ez), cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(cigar, dcig.p, cigar_cap * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(cigar_off, dcoff.p, n * 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
+		return IDL_OK;
+	};
+	rc = body();
+	if (e0) cudaEventDestroy(e0);
+	if (e1) cudaEventDestroy(e1);
+	for (DevBuf *b : {&dq, &dt, &dqo, &dto, &dout, &dcig, &dcoff, &dmisc, &dp, &dscr}) b->release();
+	return rc;
+}

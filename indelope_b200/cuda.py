@@ -1,0 +1,122 @@
+"""ctypes binding of libindelope_cuda.so (include/indelope_cuda.h).  There is no CPU fallback: creating a
+Context without a CUDA device raises, and so does a missing library."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from .abi import (Batch, Ez, Params, Results, default_params)  # noqa: F401
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+
+_lib = None
+
+
+class IdlError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.CUDA_LIB
+        if not os.path.exists(path):
+            path = _build.build_cuda()
+        L = C.CDLL(path)
+        L.idl_strerror.restype = C.c_char_p
+        L.idl_last_cuda_error.restype = C.c_char_p
+        L.idl_last_cuda_error.argtypes = [C.c_void_p]
+        L.idl_create.argtypes = [C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]
+        L.idl_destroy.argtypes = [C.c_void_p]
+        L.idl_batch_alloc.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.POINTER(Batch))]
+        L.idl_batch_free.argtypes = [C.c_void_p, C.POINTER(Batch)]
+        L.idl_submit.argtypes = [C.c_void_p, C.POINTER(Batch), u64p]
+        L.idl_upload.argtypes = [C.c_void_p, C.POINTER(Batch)]
+        L.idl_run_resident.argtypes = [C.c_void_p, C.POINTER(Batch), u64p]
+        L.idl_wait.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.POINTER(Results))]
+        L.idl_release.argtypes = [C.c_void_p, C.c_uint64]
+        L.idl_default_params.argtypes = [C.POINTER(Params)]
+        L.idl_ksw2_batch.argtypes = [C.c_void_p, C.c_size_t, u8p, u64p, u8p, u64p, C.c_int8, C.c_int8, C.c_int8, C.c_int8, C.c_int, C.c_int,
+                                     C.POINTER(Ez), u32p, u64p, C.c_size_t, C.POINTER(C.c_float)]
+        _lib = L
+    return _lib
+
+
+EXPORTS = ("idl_default_params idl_create idl_destroy idl_batch_alloc idl_batch_free idl_submit idl_upload idl_run_resident idl_wait "
+           "idl_release idl_strerror idl_last_cuda_error idl_device_count idl_ksw2_batch").split()
+
+
+class Context:
+    """one per GPU (idl_create / idl_destroy)"""
+
+    def __init__(self, device=0, params=None, **kw):
+        self.params = params if params is not None else default_params(**kw)
+        self.h = C.c_void_p()
+        rc = lib().idl_create(device, C.byref(self.params), C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise IdlError("idl_create: %s" % lib().idl_strerror(rc).decode())
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise IdlError("%s: %s (%s)" % (what, lib().idl_strerror(rc).decode(), lib().idl_last_cuda_error(self.h).decode()))
+
+    def batch_alloc(self, max_regions, max_reads, max_seq_bases, max_ref_bases):
+        b = C.POINTER(Batch)()
+        self._check(lib().idl_batch_alloc(self.h, max_regions, max_reads, max_seq_bases, max_ref_bases, C.byref(b)), "idl_batch_alloc")
+        return b
+
+    def batch_free(self, b):
+        lib().idl_batch_free(self.h, b)
+
+    def submit(self, batch):
+        t = C.c_uint64()
+        self._check(lib().idl_submit(self.h, batch, C.byref(t)), "idl_submit")
+        return t.value
+
+    def upload(self, batch):
+        self._check(lib().idl_upload(self.h, batch), "idl_upload")
+
+    def run_resident(self, batch):
+        t = C.c_uint64()
+        self._check(lib().idl_run_resident(self.h, batch, C.byref(t)), "idl_run_resident")
+        return t.value
+
+    def wait(self, ticket):
+        r = C.POINTER(Results)()
+        self._check(lib().idl_wait(self.h, ticket, C.byref(r)), "idl_wait")
+        return r
+
+    def release(self, ticket):
+        self._check(lib().idl_release(self.h, ticket), "idl_release")
+
+    def ksw2_batch(self, queries, targets, match=1, mismatch=-2, gapo=4, gape=1, w=-1, zdrop=-1):
+        """queries/targets: lists of uint8 code arrays (0..4). Returns (list of field dicts, list of cigar tuples, kernel ms)"""
+        n = len(queries)
+        qo = np.zeros(n + 1, dtype=np.uint64); to = np.zeros(n + 1, dtype=np.uint64)
+        qo[1:] = np.cumsum([len(q) for q in queries]); to[1:] = np.cumsum([len(t) for t in targets])
+        qa = np.ascontiguousarray(np.concatenate([np.asarray(q, dtype=np.uint8) for q in queries] + [np.zeros(1, np.uint8)]))
+        ta = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.uint8) for t in targets] + [np.zeros(1, np.uint8)]))
+        out = (Ez * n)()
+        cap = int(qo[-1] + to[-1]) + 8 * n + 16
+        cig = np.zeros(cap, dtype=np.uint32); coff = np.zeros(n, dtype=np.uint64)
+        ms = C.c_float()
+        self._check(lib().idl_ksw2_batch(self.h, n, qa.ctypes.data_as(u8p), qo.ctypes.data_as(u64p), ta.ctypes.data_as(u8p), to.ctypes.data_as(u64p),
+                                         C.c_int8(match), C.c_int8(mismatch), C.c_int8(gapo), C.c_int8(gape), w, zdrop, out, cig.ctypes.data_as(u32p),
+                                         coff.ctypes.data_as(u64p), cap, C.byref(ms)), "idl_ksw2_batch")
+        names = "max zdropped max_q max_t mqe mqe_t mte mte_q score n_cigar".split()
+        fields = [{k: getattr(out[i], k) for k in names} for i in range(n)]
+        cigs = [tuple(int(x) for x in cig[int(coff[i]):int(coff[i]) + max(out[i].n_cigar, 0)]) for i in range(n)]
+        extra = [dict(status=out[i].status, cells=out[i].cells) for i in range(n)]
+        return fields, cigs, extra, ms.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().idl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()

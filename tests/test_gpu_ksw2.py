@@ -1,0 +1,86 @@
+"""kernel 2 (ksw2 extension DP + traceback) through the C ABI (idl_ksw2_batch) against the CPU oracle's lane model
+and, when oracle/_ref was built, against the reference's own compiled C file.  Bit-exact: every ksw_extz_t field and
+the full CIGAR."""
+import numpy as np
+import pytest
+
+import idl_testutil as util
+from oracle import pyoracle as orc
+from test_oracle_ksw2 import QRY, QRY2, TGT, TGT2, random_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from indelope_b200 import cuda
+    c = cuda.Context(0)
+    yield c
+    c.close()
+
+
+def check(ctx, pairs, impl="lane"):
+    """pairs: list of (q codes, t codes); one parameter set per call"""
+    (go, w, z) = pairs[0][2:]
+    f, c, extra, ms = ctx.ksw2_batch([p[0] for p in pairs], [p[1] for p in pairs], gapo=go, gape=1, w=w, zdrop=z)
+    bad = []
+    for i, (q, t, _, _, _) in enumerate(pairs):
+        fo, co, ez = orc.ksw2(q, t, gapo=go, gape=1, w=w, zdrop=z, impl=impl)
+        if extra[i]["status"] < 0:
+            bad.append((i, "status", extra[i]["status"], len(q), len(t)))
+        elif fo != f[i] or co != c[i] or (impl == "lane" and ez.cells != extra[i]["cells"]):
+            bad.append((i, len(q), len(t), fo, f[i], orc.cigar_str(co), orc.cigar_str(c[i])))
+    return bad
+
+
+def test_known_answers(ctx):  # SURVEY appendix F / src/ksw2/ksw2.nim:171-215 with flag 0
+    f, c, _, _ = ctx.ksw2_batch([orc.encode(QRY)], [orc.encode(TGT)], gapo=3, gape=1, w=-1, zdrop=-1)
+    assert orc.cigar_str(c[0]) == "52M19D41M6D5M22D"
+    assert (f[0]["max"], f[0]["max_q"], f[0]["max_t"], f[0]["mqe"], f[0]["mqe_t"], f[0]["mte"], f[0]["mte_q"], f[0]["score"], f[0]["zdropped"]) == (73, 97, 116, 73, 116, 42, 82, 42, 0)
+    f, c, _, _ = ctx.ksw2_batch([orc.encode(QRY), orc.encode(QRY2)], [orc.encode(TGT), orc.encode(TGT2)], gapo=4, gape=1, w=50, zdrop=400)
+    assert orc.cigar_str(c[0]) == "52M19D46M28D" and (f[0]["max"], f[0]["max_q"], f[0]["max_t"], f[0]["score"]) == (72, 71, 71, 40)
+    assert orc.cigar_str(c[1]) == "11D3M1D7M6D16M21D18M1I22M1D17M3D1M" and (f[1]["max"], f[1]["max_q"], f[1]["max_t"], f[1]["score"]) == (0, -1, -1, -75)
+
+
+def test_edge_shapes(ctx):
+    rng = np.random.default_rng(3)
+    pairs = []
+    for ql, tl in [(1, 1), (1, 40), (40, 1), (15, 16), (16, 15), (17, 33), (150, 150), (31, 500), (200, 17), (64, 64), (65, 129)]:
+        base = rng.integers(0, 4, max(ql, tl) + 5).astype(np.uint8)
+        pairs.append((base[:ql].copy(), base[:tl].copy(), 4, 50, 400))
+    assert check(ctx, pairs) == []
+    pairs = [(p[0], p[1], 5, -1, -1) for p in pairs]
+    assert check(ctx, pairs) == []
+
+
+@pytest.mark.parametrize("impl", ["lane", "ref"])
+def test_fuzz_bit_exact(ctx, impl):
+    if impl == "ref" and not orc.have_ref():
+        pytest.skip("oracle/_ref/libksw2_ref.so not built")
+    rng = np.random.default_rng(20171101 if impl == "lane" else 77)
+    groups = {}
+    for _ in range(3000):
+        q, t, go, w, z = random_pair(rng)
+        groups.setdefault((go, w, z), []).append((q, t, go, w, z))
+    bad = []
+    for key, pairs in groups.items():
+        bad += [(key,) + b for b in check(ctx, pairs, impl)]
+    assert bad == [], bad[:5]
+
+
+def test_production_shapes_many(ctx):
+    """call-site A (bw=50, z=400, q=4) and call-site B (unbanded, q=5) shapes of src/indelope.nim:221,343-344"""
+    rng = np.random.default_rng(11)
+    A, B = [], []
+    for _ in range(600):
+        ql = int(rng.integers(73, 900)); base = rng.integers(0, 4, ql + 300).astype(np.uint8)
+        q = base[:ql].copy(); t = base[:ql + int(rng.integers(64, 250))].copy()
+        pos = int(rng.integers(20, ql - 20)); L = int(rng.integers(1, 70))
+        q = np.concatenate([q[:pos], rng.integers(0, 4, L).astype(np.uint8), q[pos:]]) if rng.random() < 0.5 else np.concatenate([q[:pos], q[pos + L:]])
+        A.append((q, t, 4, 50, 400))
+        tl = int(rng.integers(100, 900)); base = rng.integers(0, 4, tl + 200).astype(np.uint8)
+        o = int(rng.integers(0, tl - 50)); r = base[o:o + int(rng.integers(30, 151))].copy()
+        m = rng.random(len(r)) < 0.01; r[m] = rng.integers(0, 4, int(m.sum()))
+        B.append((r, base[:tl].copy(), 5, -1, -1))
+    assert check(ctx, A) == []
+    assert check(ctx, B) == []

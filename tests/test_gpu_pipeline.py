@@ -1,0 +1,127 @@
+"""The whole per-region path on the GPU (through the C ABI: idl_batch_alloc / idl_submit / idl_wait) against the CPU
+oracle on the same seeded inputs: contigs (order, start, nreads, sequence, per-base support), ksw_extz_t fields and
+CIGARs, event records and counts, and the VCF bytes.  Everything is integer: the bar is bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import idl_testutil as util
+from indelope_b200 import abi, host
+from oracle import pyoracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(rois, arrays, min_reads=5, min_ctg_len=73, min_event_len=5, level=31, tag="x", **kw):
+    from indelope_b200 import api
+    caller = api.Caller(0, min_reads=min_reads, min_ctg_len=min_ctg_len, min_event_len=min_event_len, out_flags=abi.OUT_SUPPORT, **kw)
+    try:
+        tm = []
+        vcf, dump = caller.call(rois, dump_level=level, timings=tm)
+    finally:
+        caller.close()
+    odump, ovcf, cnt = orc.call(arrays, min_reads=min_reads, min_ctg_len=min_ctg_len, min_event_len=min_event_len, dump_level=level)
+    if dump != odump or vcf != ovcf:
+        with open(os.path.join(util.out_dir(), "diff_%s.txt" % tag), "w") as f:
+            f.write(util.diff_lines(odump, dump, limit=40) + "\n\nVCF:\n" + util.diff_lines(ovcf, vcf))
+        with open(os.path.join(util.out_dir(), "dump_%s_oracle.txt" % tag), "w") as f:
+            f.write(odump)
+        with open(os.path.join(util.out_dir(), "dump_%s_gpu.txt" % tag), "w") as f:
+            f.write(dump)
+    return dump, vcf, odump, ovcf, cnt, tm
+
+
+def assert_same(dump, vcf, odump, ovcf):
+    g, o = util.by_type(dump), util.by_type(odump)
+    for t in "RCAEV":
+        assert g.get(t, []) == o.get(t, []), "first diff in %s lines:\n%s" % (t, util.diff_lines("\n".join(o.get(t, [])), "\n".join(g.get(t, [])), 4))
+    assert dump == odump
+    assert vcf == ovcf
+
+
+def test_pr1_config_bit_exact():
+    """BASELINE config 1: 1 Mb, 30x, 200 planted 5-300 bp indels, --min-event-len 5 --min-reads 5"""
+    ds = util.small_dataset("pr1")
+    rois = ds.sweep(min_reads=5)
+    dump, vcf, odump, ovcf, cnt, tm = run_both(rois, rois.arrays(), tag="pr1")
+    assert cnt["variants"] >= 15 and cnt["dp_b"] > 0  # the AL fallback is exercised
+    assert_same(dump, vcf, odump, ovcf)
+    # device work counters agree with the oracle's algorithmic counts
+    assert sum(t["offsets_tested"] for t in tm) == cnt["offsets"]
+    assert sum(t["dp_cells_a"] for t in tm) == cnt["cells_a"] and sum(t["dp_cells_b"] for t in tm) == cnt["cells_b"]
+    assert sum(t["kmer_bytes"] for t in tm) == cnt["kmer_bytes"]
+
+
+def test_golden_vcf_fixture():
+    """the committed golden VCF (made by tools/make_golden.py from the oracle) is reproduced byte for byte"""
+    path = os.path.join(os.path.dirname(__file__), "golden", "pr1_small.vcf")
+    ds = util.small_dataset("pr1", chrom_len=300_000, n_events=60)
+    rois = ds.sweep(min_reads=5)
+    from indelope_b200 import api
+    caller = api.Caller(0, min_reads=5, min_ctg_len=73, min_event_len=5)
+    try:
+        vcf, _ = caller.call(rois)
+    finally:
+        caller.close()
+    assert rois.header() + vcf == open(path).read()
+
+
+@pytest.mark.parametrize("name,over", [
+    ("short_indels", dict(chrom_len=400_000, n_events=80, max_indel=40, seed=5)),
+    ("tandem", dict(chrom_len=400_000, n_events=80, max_indel=40, tr_fraction=0.7, tr_max_unit=4, seed=6)),
+    ("noisy", dict(chrom_len=300_000, n_events=60, max_indel=50, sub_rate=0.004, seed=7)),
+    ("with_n", dict(chrom_len=300_000, n_events=60, max_indel=40, n_base_rate=0.002, seed=8)),
+    ("cov100", dict(chrom_len=200_000, n_events=30, max_indel=40, coverage=100.0, tr_fraction=0.3, seed=9)),
+])
+def test_variants_of_the_generator(name, over):
+    ds = util.small_dataset("pr1", **over)
+    rois = ds.sweep(min_reads=5)
+    dump, vcf, odump, ovcf, cnt, _ = run_both(rois, rois.arrays(), tag=name)
+    assert cnt["regions"] > 20
+    assert_same(dump, vcf, odump, ovcf)
+
+
+def test_default_cli_parameters():
+    """docopt defaults: -m 3 -c 73 -e 4 (src/indelope.nim:568-570)"""
+    ds = util.small_dataset("pr1", chrom_len=300_000, n_events=60, max_indel=40, seed=12)
+    rois = ds.sweep(min_reads=3)
+    dump, vcf, odump, ovcf, cnt, _ = run_both(rois, rois.arrays(), min_reads=3, min_ctg_len=73, min_event_len=4, tag="defaults")
+    assert_same(dump, vcf, odump, ovcf)
+
+
+def test_high_coverage_panel_slice():
+    """a slice of the 500x panel: hundreds of reads and contigs per region, AL fallback heavy"""
+    ds = util.small_dataset("panel500", chrom_len=120_000, n_events=14, coverage=300.0)
+    rois = ds.sweep(min_reads=5)
+    dump, vcf, odump, ovcf, cnt, _ = run_both(rois, rois.arrays(), tag="panel")
+    assert_same(dump, vcf, odump, ovcf)
+
+
+def test_many_small_batches_keep_order_and_dedup():
+    ds = util.small_dataset("pr1", chrom_len=300_000, n_events=60, max_indel=40, seed=13)
+    rois = ds.sweep(min_reads=5)
+    from indelope_b200 import api
+    caller = api.Caller(0, min_reads=5, min_ctg_len=73, min_event_len=5)
+    try:
+        v1, _ = caller.call(rois)
+        v2, _ = caller.call(rois, max_reads=300)  # dozens of batches over both lanes
+    finally:
+        caller.close()
+    _, ovcf, _ = orc.call(rois.arrays(), min_reads=5, min_ctg_len=73, min_event_len=5, dump_level=0)
+    assert v1 == ovcf and v2 == ovcf
+
+
+def test_empty_batch_and_tiny_regions():
+    from indelope_b200 import api
+    ref = "".join("ACGT"[i] for i in np.random.default_rng(1).integers(0, 4, 3000))
+    reads = [dict(start=1000 + i, seq=ref[1000 + i:1150 + i]) for i in range(0, 50, 10)]
+    rois, arrays = util.rois_from_reads(reads, ref)
+    dump, vcf, odump, ovcf, _, _ = run_both(rois, arrays, min_reads=3, tag="tiny")
+    assert_same(dump, vcf, odump, ovcf)
+    caller = api.Caller(0)
+    try:
+        v, d = caller.call(rois, lo=0, hi=0)
+        assert v == "" and d == ""
+    finally:
+        caller.close()

@@ -1,0 +1,126 @@
+"""CPU-only checks of the host side and of the boundary: the C-ABI libraries load and export every declared symbol,
+struct layouts match the headers, packing round-trips, the sweep restates gen_roi, and the product-side VCF writer
+agrees with the oracle's on oracle-produced integers (no GPU compute here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from indelope_b200 import abi, build, host
+from oracle import pyoracle as orc
+import idl_testutil as util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(idlh?_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    build.build_cuda()
+    lib = C.CDLL(build.CUDA_LIB)  # loads without a GPU: the runtime is linked statically, no device call at load time
+    names = declared("indelope_cuda.h")
+    assert "idl_submit" in names and "idl_ksw2_batch" in names and len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.idl_device_count.restype = C.c_int
+    p = abi.Params()
+    lib.idl_default_params(C.byref(p))
+    q = abi.default_params()
+    assert bytes(p) == bytes(q)
+
+
+def test_no_cpu_fallback_without_device():
+    if util.has_gpu():
+        pytest.skip("GPU present")
+    lib = C.CDLL(build.build_cuda())
+    h = C.c_void_p()
+    p = abi.default_params()
+    rc = lib.idl_create(0, C.byref(p), C.byref(h))
+    assert rc == -1 and not h.value  # IDL_E_NO_DEVICE: the product fails loudly, it never computes on the CPU
+
+
+def test_host_library_exports_every_declared_symbol():
+    lib = host.lib()
+    for n in declared("indelope_host.h"):
+        assert hasattr(lib, n), n
+
+
+def test_struct_sizes_match_header():
+    assert C.sizeof(abi.Region) == 48 and C.sizeof(abi.Read) == 24
+    assert C.sizeof(abi.RegionResult) == 16 and C.sizeof(abi.ContigResult) == 24
+    assert C.sizeof(abi.AlnResult) == 72 and C.sizeof(abi.EventResult) == 128
+
+
+def test_trim_matches_oracle():
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        n = int(rng.integers(0, 40))
+        q = rng.choice([2, 30], size=n, p=[0.4, 0.6]).astype(np.uint8)
+        assert host.trim(q) == orc.trim(q)
+
+
+def test_pack_roundtrip_and_read_records():
+    ds = util.small_dataset("pr1", chrom_len=120_000, n_events=20, n_base_rate=0.01)
+    rois = ds.sweep(min_reads=5)
+    assert rois.n_rois > 10
+    a = rois.arrays()
+    p = abi.default_params(min_reads=5)
+    nr, sb, rb = rois.pack_size(0, rois.n_rois, p)
+    b = host.host_batch(rois.n_rois, nr, sb, rb)
+    rois.pack(0, rois.n_rois, p, b)
+    bt = b.contents
+    assert bt.n_regions == rois.n_rois and bt.n_reads == nr
+    k = 0
+    for g in range(rois.n_rois):
+        reg = bt.region[g]
+        assert reg.n_reads == a["roi_n_reads"][g] and reg.read_begin == k
+        idx = a["read_idx"][a["roi_read_begin"][g]:a["roi_read_begin"][g] + a["roi_n_reads"][g]]
+        for j, i in enumerate(idx):
+            rd = bt.read[k + j]
+            seq = bytes(a["bases"][a["seq_off"][i]:a["seq_off"][i] + a["len"][i]]).decode()
+            assert host.unpack(bt.seq2, bt.seqn, rd.seq_off, rd.len) == seq
+            ta, tl = orc.trim(a["quals"][a["seq_off"][i]:a["seq_off"][i] + a["len"][i]])
+            assert (rd.trim_a, rd.trim_len, rd.min_overlap) == (ta, tl, int(0.88 * tl))
+            assert rd.seq_off % 64 == 0 and rd.mapq == a["mapq"][i] and rd.start == a["start"][i] and rd.stop == a["stop"][i]
+        ref = bytes(a["chrom_seqs"][0][reg.ref_start:reg.ref_start + reg.ref_len]).decode()
+        assert host.unpack(bt.ref2, bt.refn, reg.ref_off, reg.ref_len) == ref
+        k += reg.n_reads
+    host.host_batch_free(b)
+
+
+def test_int_088_equals_integer_form():
+    # int(0.88*len) == 88*len div 100 for every len <= 2000
+    for n in range(0, 2001):
+        assert int(0.88 * n) == (88 * n) // 100
+
+
+def test_sweep_regions_cover_planted_events():
+    ds = util.small_dataset("pr1", chrom_len=200_000, n_events=30)
+    rois = ds.sweep(min_reads=5)
+    a = rois.arrays()
+    truth = ds.truth()
+    hit = 0
+    for ev in truth:
+        pos = ev[1]
+        hit += bool(np.any((a["roi_start"] <= pos + ev[3] + 2) & (a["roi_stop"] >= pos - 2)))
+    assert hit >= 0.9 * len(truth)
+    assert np.all(a["roi_n_reads"] >= 5) and np.all(a["roi_n_reads"] <= 600)
+    # reads of a region are in BAM order and overlap it (src/indelope.nim:449-452,480-484)
+    for g in range(rois.n_rois):
+        idx = a["read_idx"][a["roi_read_begin"][g]:a["roi_read_begin"][g] + a["roi_n_reads"][g]]
+        assert np.all(np.diff(idx) > 0)
+        assert np.all(a["start"][idx] <= a["roi_stop"][g]) and np.all(a["stop"][idx] >= a["roi_start"][g])
+
+
+def test_header_matches_oracle():
+    ds = util.small_dataset("pr1", chrom_len=50_000, n_events=3)
+    rois = ds.sweep(min_reads=5)
+    a = rois.arrays()
+    assert rois.header() == orc.vcf_header(a["chrom_names"], [len(s) for s in a["chrom_seqs"]])
+    assert rois.header().startswith("##fileformat=VCFv4.2\n") and rois.header().endswith("\tFORMAT\tsample\n")

@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of indelope's per-region calling path on B200 (see DESIGN.md "Measurement").
+
+  python bench.py --gpus 1 --steps 5 --warmup 3                    # this repo's CUDA path
+  python bench.py --impl reference --gpus 1 --steps 2 --warmup 1   # the reference algorithm on the host cores (CPU oracle)
+
+A "step" is one pass of the hot path (assemble -> align -> k-mer genotype -> AL fallback) over one workload of
+synthetic candidate regions.  Rank r of N builds its own interval shard (seed + r) of the same size, so the run is
+weak scaling: value = regions of all ranks / max-over-ranks step time.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CALL = dict(min_reads=5, min_ctg_len=73, min_event_len=5)  # `indelope --min-event-len 5 --min-reads 5` (BASELINE.json configs[0])
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="chr1", help="key of indelope_b200.host.CONFIGS")
+    ap.add_argument("--scale", type=float, default=1.0, help="scale the number of planted events (tests)")
+    ap.add_argument("--cpu-sample", type=int, default=12000, help="regions timed by the cpu_baseline leg")
+    ap.add_argument("--e2e-batches", type=int, default=8)
+    return ap.parse_args()
+
+
+def build_workload(name, rank, scale):
+    from indelope_b200 import host
+    cfg = dict(host.CONFIGS[name])
+    cfg["seed"] = cfg["seed"] + 1000 * rank
+    cfg["n_events"] = max(1, int(cfg["n_events"] * scale))
+    ds = host.Dataset(**cfg)
+    rois = ds.sweep(min_reads=CALL["min_reads"])
+    return cfg, ds, rois
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)", d.get("sm_max_mhz", 1965.0)
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def run_oracle(rois, n_regions, n_threads):
+    """CPU restatement of the reference (oracle/), the reference's own ksw2 C when oracle/_ref was built"""
+    from oracle import pyoracle as orc
+    a = rois.arrays()
+    n = min(n_regions, rois.n_rois)
+    sub = dict(a)
+    for k in ("roi_chrom", "roi_start", "roi_stop", "roi_read_begin", "roi_n_reads"):
+        sub[k] = a[k][:n]
+    use_ref = orc.have_ref()
+    _, _, cnt = orc.call(sub, use_ref_ksw2=use_ref, dump_level=0, n_threads=n_threads, **CALL)
+    return n, int(sub["roi_n_reads"].sum()), cnt, use_ref
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    cfg, ds, rois = build_workload(args.workload, 0, args.scale)
+    cores = os.cpu_count() or 1
+    sample = min(rois.n_rois, max(2000, args.cpu_sample * 2))
+    for _ in range(args.warmup):
+        run_oracle(rois, min(sample, 2000), cores)
+    t0 = time.time(); regions = reads = 0
+    for _ in range(args.steps):
+        n, nr, cnt, use_ref = run_oracle(rois, sample, cores)
+        regions += n; reads += nr
+    dt = time.time() - t0
+    val = regions / dt
+    line = {
+        "impl": "reference", "metric": "regions_per_s", "value": val, "unit": "regions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8/int32/u64", "data": "synthetic",
+        "reads_per_s": reads / dt,
+        "config": {"workload": workload_name(args, cfg), "sample_regions_per_step": sample},
+        "cpu_baseline": {"value": val, "unit": "regions/s", "cores": cores, "kind": "port+reference-ksw2" if use_ref else "port",
+                         "sample": "first %d regions of the workload per step, %d threads over regions; the Nim binary cannot be built here (no nim/hts-nim/htslib), "
+                                   "so this is the CPU oracle restating src/contig.nim + src/indelope.nim:157-428%s" % (
+                                       sample, cores, " calling the reference's own ksw2_extz2_sse.c (oracle/_ref)" if use_ref else " with its own lane-exact ksw2")},
+        "e2e": {"value": val, "unit": "regions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_name(args, cfg):
+    return "%s: %d planted events on a %.0f Mb contig, %gx %d bp reads simulated around events (locus_only=%d), indelope --min-event-len 5 --min-reads 5" % (
+        args.workload, cfg["n_events"], cfg["chrom_len"] / 1e6, cfg["coverage"], cfg["read_len"], cfg.get("locus_only", 0))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return main_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libindelope_cuda has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from indelope_b200 import abi, api, cuda, host
+
+    cfg, ds, rois = build_workload(args.workload, rank, args.scale)
+    n_regions, n_reads = rois.n_rois, rois.total_reads()
+    caller = api.Caller(local, **CALL)
+    ctx, P = caller.ctx, caller.params
+
+    # ---- pinned batches: one big batch for the device-resident leg, `e2e_batches` slices for the end-to-end leg
+    def alloc_pack(lo, hi):
+        nr, sb, rb = rois.pack_size(lo, hi, P)
+        b = ctx.batch_alloc(hi - lo + 1, nr + 1, sb + 64, rb + 64)
+        rois.pack(lo, hi, P, b)
+        return b, (hi - lo) * C.sizeof(abi.Region) + nr * C.sizeof(abi.Read) + sb // 4 + sb // 8 + rb // 4 + rb // 8
+    big, big_bytes = alloc_pack(0, n_regions)
+    cuts = [n_regions * i // args.e2e_batches for i in range(args.e2e_batches + 1)]
+    slices = [alloc_pack(cuts[i], cuts[i + 1]) for i in range(args.e2e_batches) if cuts[i + 1] > cuts[i]]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- leg 1: inputs resident in HBM, kernels only (CUDA events on the library's stream)
+    ctx.upload(big)
+    keys = ("ms_assemble", "ms_align", "ms_genotype", "ms_al", "ms_total", "offsets_tested", "dp_cells_a", "dp_cells_b", "dp_a", "dp_b", "kmer_reads",
+            "kmer_bytes", "al_events", "kernel_launches", "n_contigs", "n_alns", "n_events")
+
+    def resident_step():
+        t = ctx.run_resident(big)
+        r = ctx.wait(t).contents
+        d = {k: getattr(r, k) for k in keys}
+        ctx.release(t)
+        return d
+    for _ in range(args.warmup):
+        resident_step()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    steps = [resident_step() for _ in range(args.steps)]
+    barrier()
+    dev_ms = sum(s["ms_total"] for s in steps)
+    launches = sum(s["kernel_launches"] for s in steps)
+
+    # ---- leg 2: end to end through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H of every result
+    def e2e_step():
+        inflight, d2h = [], 0
+        for i, (b, _) in enumerate(slices):
+            if len(inflight) >= P.n_streams:
+                t = inflight.pop(0); r = ctx.wait(t).contents; d2h += result_bytes(r); ctx.release(t)
+            inflight.append(ctx.submit(b))
+        while inflight:
+            t = inflight.pop(0); r = ctx.wait(t).contents; d2h += result_bytes(r); ctx.release(t)
+        return d2h
+
+    def result_bytes(r):
+        return (r.n_regions * C.sizeof(abi.RegionResult) + r.n_contigs * C.sizeof(abi.ContigResult) + r.n_alns * C.sizeof(abi.AlnResult) +
+                r.n_events * C.sizeof(abi.EventResult) + r.n_cigar_ops * 4 + r.n_contig_bases)
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    d2h_bytes = 0
+    for _ in range(args.steps):
+        d2h_bytes = e2e_step()
+        launches += 4 * len(slices)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True; sampler.join(timeout=2)
+
+    # max over ranks
+    tt = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n_regions), float(n_reads)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max = tt.tolist(); regions_all, reads_all = tot.tolist()
+
+    if rank == 0:
+        K = args.steps
+        avg = {k: sum(s[k] for s in steps) / K for k in keys}
+        value = regions_all * K / (dev_ms_max / 1000.0)
+        e2e_val = regions_all * K / (e2e_ms_max / 1000.0)
+        peak, peak_src, sm_max = load_peaks()
+        kern = {"assemble_kernel": avg["ms_assemble"], "align_kernel": avg["ms_align"], "kmer_kernel": avg["ms_genotype"], "al_kernel": avg["ms_al"]}
+        dom = max(kern, key=kern.get)
+        # algorithmic bytes per launch of each kernel (DESIGN.md "Kernels"): what the kernel must read + write once
+        seq_bytes = big.contents.n_seq_bases // 4 + big.contents.n_seq_bases // 8
+        ref_bytes = big.contents.n_ref_bases // 4 + big.contents.n_ref_bases // 8
+        alg = {
+            "assemble_kernel": n_regions * 48 + n_reads * 24 + seq_bytes + ref_bytes + avg["n_contigs"] * 24 + n_regions * 16,
+            "align_kernel": avg["dp_cells_a"] * 1.0 + avg["n_alns"] * 72,   # one backtrack byte per in-band cell + the result record
+            "kmer_kernel": avg["kmer_bytes"],
+            "al_kernel": avg["dp_cells_b"] * 1.0,
+        }
+        ach = alg[dom] / (kern[dom] / 1000.0) / 1e9 if kern[dom] > 0 else 0.0
+        clocks = sampler.summary()
+        mhz = clocks.get("sm_mhz") or sm_max
+        int_peak = 148 * 128 * mhz * 1e6 / 1e12  # Tiop/s, INT32 lanes x clock
+        line = {
+            "metric": "regions_per_s", "value": value, "unit": "regions/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8/int32/u64", "data": "synthetic",
+            "reads_per_s": reads_all * K / (dev_ms_max / 1000.0),
+            "ksw2_gcups": (avg["dp_cells_a"] + avg["dp_cells_b"]) / ((avg["ms_align"] + avg["ms_al"]) / 1000.0) / 1e9 if avg["ms_align"] + avg["ms_al"] > 0 else None,
+            "ksw2_gcups_site_a": avg["dp_cells_a"] / (avg["ms_align"] / 1000.0) / 1e9 if avg["ms_align"] > 0 else None,
+            "kmer_gbs": avg["kmer_bytes"] / (avg["ms_genotype"] / 1000.0) / 1e9 if avg["ms_genotype"] > 0 else None,
+            "config": {"workload": workload_name(args, cfg), "regions_per_gpu": n_regions, "reads_per_gpu": n_reads, "sharding": "interval shard per rank, no collective",
+                       "l2": "inputs (%.0f MB packed) exceed the 126 MB L2; no explicit flush" % (big_bytes / 1e6), "e2e_batches": len(slices), "streams": P.n_streams},
+            "kernel_ms": kern,
+            "work": {k: avg[k] for k in ("offsets_tested", "dp_cells_a", "dp_cells_b", "dp_a", "dp_b", "kmer_reads", "kmer_bytes", "al_events", "n_contigs", "n_alns", "n_events")},
+            "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "peak_source": peak_src,
+                         "note": "integer, latency/ALU-bound kernel: algorithmic bytes are tiny, see alu and DESIGN.md",
+                         "alu": {"int32_peak_tiops": int_peak, "clock_mhz": mhz}},
+            "e2e": {"value": e2e_val, "unit": "regions/s", "h2d_bytes_per_step": sum(b for _, b in slices), "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_ms_max / K},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1:
+            n, nr, cnt, use_ref = run_oracle(rois, args.cpu_sample, 1)
+            line["cpu_baseline"] = {"value": n / cnt["seconds"], "unit": "regions/s", "cores": 1, "kind": "port+reference-ksw2" if use_ref else "port",
+                                    "reads_per_s": nr / cnt["seconds"], "seconds": cnt["seconds"],
+                                    "ksw2_gcups": None if use_ref else (cnt["cells_a"] + cnt["cells_b"]) / cnt["seconds"] / 1e9,
+                                    "sample": "first %d regions of the same workload, single thread (the reference is single-threaded on this path)" % n}
+        print(json.dumps(line))
+    for b, _ in slices + [(big, 0)]:
+        ctx.batch_free(b)
+    caller.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

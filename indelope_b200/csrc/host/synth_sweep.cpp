@@ -25,9 +25,9 @@ struct Rng {
 	double uni() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
 	int64_t below(int64_t n) { return n <= 0 ? 0 : (int64_t)(next() % (uint64_t)n); }
 	int64_t range(int64_t lo, int64_t hi) { return lo + below(hi - lo + 1); } // inclusive
-	int poisson(double lam) { // Knuth; lam is small (coverage / read_len)
-		double L = std::exp(-lam), p = 1; int k = 0;
-		do { ++k; p *= uni(); } while (p > L);
+	int poisson_exp(double expl) { // Knuth with exp(-lambda) precomputed; lambda is small (coverage / read_len)
+		double p = 1; int k = 0;
+		do { ++k; p *= uni(); } while (p > expl);
 		return k - 1;
 	}
 };
@@ -66,10 +66,18 @@ void emit_read(idlh_dataset &D, Rng &rng, int chrom, const std::string &seq0, in
 {
 	const idlh_synth_params &P = D.P;
 	std::string seq = seq0;
-	for (auto &c : seq) {
-		if (P.sub_rate > 0 && rng.uni() < P.sub_rate) { char o = c; while (o == c) o = ACGT[rng.below(4)]; c = o; }
-		if (P.n_base_rate > 0 && rng.uni() < P.n_base_rate) c = 'N';
-	}
+	// sparse errors: jump from one hit to the next with geometric gaps instead of one draw per base
+	auto sprinkle = [&](double rate, bool to_n) {
+		if (rate <= 0) return;
+		const double lg = std::log1p(-rate);
+		for (double at = std::floor(std::log(1.0 - rng.uni()) / lg); at < (double)seq.size(); at += 1.0 + std::floor(std::log(1.0 - rng.uni()) / lg)) {
+			char &c = seq[(size_t)at];
+			if (to_n) c = 'N';
+			else { char o = c; while (o == c) o = ACGT[rng.below(4)]; c = o; }
+		}
+	};
+	sprinkle(P.sub_rate, false);
+	sprinkle(P.n_base_rate, true);
 	ReadRec r;
 	r.chrom = chrom; r.start = (int32_t)start; r.stop = (int32_t)(start + ref_consumed); r.len = (int32_t)seq.size();
 	r.mapq = 60;
@@ -163,6 +171,12 @@ idlh_dataset *idlh_synth(const idlh_synth_params *pp)
 	const idlh_synth_params &P = D.P;
 	const int L = P.read_len;
 	const int flank = P.locus_flank > 0 ? P.locus_flank : 2 * L + P.max_indel;
+	{ // reserve: avoids re-copying gigabytes while the read table grows
+		const double per_base = P.coverage / (double)L;
+		const double span = P.locus_only ? (double)P.n_events * (2.0 * flank + (P.min_indel + P.max_indel) / 2.0) : (double)P.chrom_len;
+		const size_t est = (size_t)(span * per_base * P.n_chroms * 1.1) + 1024;
+		D.reads.reserve(est); D.bases.reserve(est * (size_t)L); D.quals.reserve(est * (size_t)L); D.cigars.reserve(est * 2);
+	}
 	for (int c = 0; c < P.n_chroms; ++c) {
 		Rng rng(P.seed * 1000003ULL + (uint64_t)c * 7919ULL + 17);
 		D.names.push_back("chrS" + std::to_string(c + 1));
@@ -194,18 +208,18 @@ idlh_dataset *idlh_synth(const idlh_synth_params *pp)
 			evs.push_back(ev);
 		}
 		// reads: Poisson(coverage / L) starts per reference base; each read picks a haplotype; het events live on hap 1
-		const double lam = P.coverage / (double)L;
+		const double lam = std::exp(-P.coverage / (double)L); // exp(-lambda) of the per-base Poisson
 		size_t first_read = D.reads.size();
 		auto sim_range = [&](int64_t lo, int64_t hi, const Event *ev) {
 			if (lo < 0) lo = 0;
 			if (hi > P.chrom_len - L) hi = P.chrom_len - L;
 			for (int64_t s = lo; s < hi; ++s) {
 				if (ev && s >= ev->pos && s < ev->pos + ev->dlen) { // bases that exist only on the non-carrier haplotype
-					int n = rng.poisson(lam);
+					int n = rng.poisson_exp(lam);
 					for (int i = 0; i < n; ++i) { bool hap1 = rng.below(2) != 0; bool carries = ev->hom || hap1; if (!carries) make_read(D, rng, c, ref, ev, false, s, -1); }
 					continue;
 				}
-				int n = rng.poisson(lam);
+				int n = rng.poisson_exp(lam);
 				for (int i = 0; i < n; ++i) {
 					bool hap1 = rng.below(2) != 0;
 					bool carries = ev && (ev->hom || hap1);
@@ -213,7 +227,7 @@ idlh_dataset *idlh_synth(const idlh_synth_params *pp)
 				}
 				if (ev && s == ev->pos) // reads that start inside the inserted sequence (carrier haplotypes only)
 					for (int k = 0; k < (int)ev->ins.size(); ++k) {
-						int m = rng.poisson(lam);
+						int m = rng.poisson_exp(lam);
 						for (int i = 0; i < m; ++i) { bool hap1 = rng.below(2) != 0; if (ev->hom || hap1) make_read(D, rng, c, ref, ev, true, s, k); }
 					}
 			}

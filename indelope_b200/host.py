@@ -90,20 +90,22 @@ def synth_params(**kw):
 
 
 # The five BASELINE.json configs as generator settings.  `locus_only` simulates reads only around
-# planted events: reads elsewhere carry no CIGAR event, never enter a region of interest and so never reach
-# the path this repo implements.  Event counts can be scaled down with `scale` for tests.
+# planted events (locus_flank bases either side, > read length + the longest CIGAR indel, so every read that can
+# overlap a region of interest exists): reads elsewhere carry no CIGAR event, never enter a region of interest and so
+# never reach the path this repo implements.  Event counts can be scaled down for tests.
 CONFIGS = {
     # 1 Mb, 30x, 200 planted 5-300 bp indels, whole contig simulated (the reference's CPU-runnable case)
     "pr1": dict(seed=20171101, n_chroms=1, chrom_len=1_000_000, n_events=200, coverage=30.0, read_len=150, locus_only=0),
     # exome: ~2000 indels inside targets at 100x (2x150 pairs act as independent reads on this path)
-    "exome": dict(seed=20171102, n_chroms=1, chrom_len=50_000_000, n_events=2000, coverage=100.0, read_len=150, locus_only=1),
+    "exome": dict(seed=20171102, n_chroms=1, chrom_len=50_000_000, n_events=2000, coverage=100.0, read_len=150, locus_only=1, locus_flank=220),
     # chr1-sized 30x WGS: 1 indel per 5 kb + 1 tandem-repeat event per 20 kb
-    "chr1": dict(seed=20171103, n_chroms=1, chrom_len=248_000_000, n_events=62_000, coverage=30.0, read_len=150, locus_only=1, tr_fraction=0.2),
+    "chr1": dict(seed=20171103, n_chroms=1, chrom_len=248_000_000, n_events=62_000, coverage=30.0, read_len=150, locus_only=1, locus_flank=220, tr_fraction=0.2),
     # 500x panel rich in tandem repeats / homopolymers
-    "panel500": dict(seed=20171104, n_chroms=1, chrom_len=2_000_000, n_events=400, coverage=500.0, read_len=150, locus_only=1, tr_fraction=0.6,
+    "panel500": dict(seed=20171104, n_chroms=1, chrom_len=2_000_000, n_events=400, coverage=500.0, read_len=150, locus_only=1, locus_flank=220, tr_fraction=0.6,
                      tr_max_unit=3, max_indel=60),
     # 30x whole genome, 3.1 Gb over 24 contigs: one rank's interval shard is built with n_chroms/chrom_len per shard
-    "wgs": dict(seed=20171105, n_chroms=1, chrom_len=129_000_000, n_events=32_000, coverage=30.0, read_len=150, locus_only=1, tr_fraction=0.2),
+    "wgs": dict(seed=20171105, n_chroms=1, chrom_len=129_000_000, n_events=32_000, coverage=30.0, read_len=150, locus_only=1, locus_flank=220,
+                tr_fraction=0.2),
 }
 
 

@@ -381,7 +381,7 @@ __device__ int asm_combine_pass(Asm &A, uint16_t *in, int n_in, uint16_t *out, i
 	return n_out;
 }
 
-__global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs args)
+__global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Asm A;

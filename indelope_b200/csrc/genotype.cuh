@@ -31,24 +31,32 @@ struct GenoArgs {
 	uint32_t *cig_scratch; int cig_cap;
 	int8_t *spill; int spill_tcap;   // global-memory lane storage for targets that do not fit shared memory
 	int t_cap, hr, qcap;             // shared-memory lane capacity, H ring size, query buffer bytes (AL)
+	int seq_cap;                     // shared-memory bytes per warp for the staged target / reversed query
+	size_t spill_bytes;              // global-memory spill area per warp: lanes, then sequences
 };
 
-__host__ __device__ inline size_t dp_smem_per_warp(int t_cap, int hr, int qcap) { return ((ksw_lane_bytes(t_cap) + 15) & ~(size_t)15) + (size_t)hr * 4 + (size_t)((qcap + 15) & ~15); }
+__host__ __device__ inline size_t dp_smem_per_warp(int t_cap, int hr, int qcap, int seq_cap)
+{
+	return ((ksw_lane_bytes(t_cap) + 15) & ~(size_t)15) + (size_t)hr * 4 + KSW_BTILE_BYTES + (size_t)((qcap + 15) & ~15) + (size_t)((seq_cap + 15) & ~15);
+}
 
-struct DpWarp { int8_t *lanes; int *H; uint8_t *qbuf; uint8_t *pmat; uint32_t *cig; int8_t *spill; };
+struct DpWarp { int8_t *lanes; int *H; uint8_t *btile; uint8_t *qbuf; uint8_t *seq; uint8_t *pmat; uint32_t *cig; int8_t *spill; uint8_t *spill_seq; };
 
 __device__ __forceinline__ DpWarp dp_carve(const GenoArgs &g, unsigned char *smem)
 {
 	DpWarp d;
-	const size_t per = dp_smem_per_warp(g.t_cap, g.hr, g.qcap);
+	const size_t per = dp_smem_per_warp(g.t_cap, g.hr, g.qcap, g.seq_cap);
 	unsigned char *base = smem + per * warp_id();
 	d.lanes = (int8_t*)base;
 	d.H = (int*)(base + ((ksw_lane_bytes(g.t_cap) + 15) & ~(size_t)15));
-	d.qbuf = (uint8_t*)(d.H + g.hr);
+	d.btile = (uint8_t*)(d.H + g.hr);
+	d.qbuf = d.btile + KSW_BTILE_BYTES;
+	d.seq = d.qbuf + ((g.qcap + 15) & ~15);
 	const size_t gw = (size_t)blockIdx.x * DP_WARPS + warp_id();
 	d.pmat = g.pmat + gw * g.p_cap;
 	d.cig = g.cig_scratch + gw * (size_t)g.cig_cap;
-	d.spill = g.spill + gw * ksw_lane_bytes(g.spill_tcap);
+	d.spill = g.spill + gw * g.spill_bytes;
+	d.spill_seq = (uint8_t*)d.spill + ((ksw_lane_bytes(g.spill_tcap) + 15) & ~(size_t)15);
 	return d;
 }
 
@@ -56,8 +64,9 @@ __device__ __forceinline__ DpWarp dp_carve(const GenoArgs &g, unsigned char *sme
 __device__ __forceinline__ void dp_run(const GenoArgs &g, const DpWarp &d, int qlen, const uint8_t *q, int tlen, const uint8_t *t, KswParams kp, KswOut &o)
 {
 	const int T16 = (tlen + 15) & ~15;
-	if (T16 <= g.t_cap) ksw2_warp(qlen, q, tlen, t, kp, d.lanes, g.t_cap, d.H, g.hr, d.pmat, g.p_cap, d.cig, g.cig_cap, o);
-	else ksw2_warp(qlen, q, tlen, t, kp, d.spill, g.spill_tcap, d.H, g.hr, d.pmat, g.p_cap, d.cig, g.cig_cap, o);
+	const bool fits = T16 <= g.t_cap;
+	uint8_t *seq = ksw_seq_bytes(qlen, tlen) <= (size_t)g.seq_cap ? d.seq : d.spill_seq;
+	ksw2_warp(qlen, q, tlen, t, kp, fits ? d.lanes : d.spill, fits ? g.t_cap : g.spill_tcap, seq, d.H, g.hr, d.btile, d.pmat, g.p_cap, d.cig, g.cig_cap, o);
 }
 
 __device__ __forceinline__ unsigned dp_status_bits(int st)
@@ -92,7 +101,7 @@ __device__ __forceinline__ int distinct_k(const uint8_t *a, int K)
 	return __popc(m);
 }
 
-__global__ void __launch_bounds__(DP_THREADS) align_kernel(GenoArgs g)
+__global__ void __launch_bounds__(DP_THREADS, 3) align_kernel(GenoArgs g)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const DpWarp d = dp_carve(g, smem_raw);
@@ -318,7 +327,7 @@ __device__ __forceinline__ int count_flanked(const uint32_t *cig_rev, int n, int
 // ---------------------------------------------------------------------------------------------------------------
 // AL fallback: one warp per (event, read) work item
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DP_THREADS) al_kernel(GenoArgs g)
+__global__ void __launch_bounds__(DP_THREADS, 3) al_kernel(GenoArgs g)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const DpWarp d = dp_carve(g, smem_raw);

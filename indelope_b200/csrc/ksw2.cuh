@@ -20,6 +20,8 @@ struct KswOut {
 	long long cells;  // exact in-band cells over executed diagonals
 };
 
+#define KSW_BTILE_BYTES 1024
+#define KSW_PMAT_PAD 64   /* bytes in front of every warp's backtrack matrix (the tile prefetch may start before row 0) */
 #define KSW_ST_EARLY 1
 #define KSW_ST_TCAP (-2)
 #define KSW_ST_PCAP (-3)
@@ -35,6 +37,8 @@ __device__ __forceinline__ void ksw_reset(KswOut &o) // ksw_reset_extz :81-86
 
 // bytes of lane storage for targets up to t_cap (multiple of 16): u,v,x,y and s (+16 spare lanes)
 __host__ __device__ inline size_t ksw_lane_bytes(int t_cap) { return (size_t)5 * t_cap + 16; }
+// bytes of sequence staging one alignment needs: zero-padded target (sf) and reversed, zero-padded query (qr)
+__host__ __device__ inline size_t ksw_seq_bytes(int qlen, int tlen) { return (size_t)(((tlen + 15) & ~15) + 16) + (size_t)((qlen + 35) & ~3); }
 
 // off[r] / off_end[r] of the reference are pure functions of r (:196-199,205)
 __device__ __forceinline__ void ksw_band(int r, int qlen, int tlen, int w, int &st0, int &en0)
@@ -47,12 +51,29 @@ __device__ __forceinline__ void ksw_band(int r, int qlen, int tlen, int w, int &
 	st0 = st; en0 = en;
 }
 
+// ---- four int8 lanes per 32-bit register (the reference's __m128i holds sixteen) ----
+__device__ __forceinline__ uint32_t sel4(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); } // m ? a : b, per byte (one LOP3)
+__device__ __forceinline__ uint32_t rep4(int v) { return (uint32_t)(v & 0xff) * 0x01010101u; }
+// 0xff in every byte whose top bit is set (PRMT with the sign-replicate selector bit; __byte_perm() masks that bit off)
+__device__ __forceinline__ uint32_t msb_to_mask4(uint32_t v)
+{
+	uint32_t r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0u), "r"(0xba98u));
+	return r;
+}
+
 // All 32 lanes call this with identical arguments; `out` comes back identical in every lane.
 // sm: this warp's lane storage (ksw_lane_bytes(t_cap) bytes, 16-byte aligned; shared memory, or a global-memory
-// spill area for targets that do not fit); H: ring of hr ints (power of two) in shared memory; pmat: backtrack matrix
-// workspace of p_cap bytes in global memory; cig: CIGAR scratch of cig_cap ops in global memory.
+// spill area for targets that do not fit); seqbuf: ksw_seq_bytes(qlen, tlen) bytes for the staged sequences; H: ring of
+// hr ints (power of two) in shared memory; btile: KSW_BTILE_BYTES of shared memory for the backtrack; pmat: backtrack matrix workspace of p_cap bytes in global memory; cig: CIGAR
+// scratch of cig_cap ops in global memory.
+//
+// Each thread owns FOUR consecutive columns t..t+3 of the anti-diagonal as one packed int8x4 word of u, v, x, y, s
+// (the SSE code holds sixteen per register); the x[t-1]/v[t-1] neighbour comes from the previous lane's word through
+// __shfl_up_sync + a funnel shift by one byte.  Wrapping int8 arithmetic, signed/unsigned max and compares are the
+// byte-SIMD intrinsics.
 __device__ void ksw2_warp(int qlen, const uint8_t *query, int tlen, const uint8_t *target, KswParams P,
-                          int8_t *sm, int t_cap, int *H, int hr, uint8_t *pmat, size_t p_cap, uint32_t *cig, int cig_cap, KswOut &out)
+                          int8_t *sm, int t_cap, uint8_t *seqbuf, int *H, int hr, uint8_t *btile, uint8_t *pmat, size_t p_cap, uint32_t *cig, int cig_cap, KswOut &out)
 {
 	const int lane = lane_id();
 	ksw_reset(out);
@@ -70,109 +91,165 @@ __device__ void ksw2_warp(int qlen, const uint8_t *query, int tlen, const uint8_
 	const int bandmax = n_col < w + 1 ? n_col : w + 1;
 	n_col = ((bandmax + 15) / 16 + 1) * 16;
 	if (T16 > t_cap) { out.status = KSW_ST_TCAP; return; }
-	if (bandmax + 2 > hr) { out.status = KSW_ST_HCAP; return; }
-	if ((size_t)(qlen + tlen - 1) * (size_t)n_col > p_cap) { out.status = KSW_ST_PCAP; return; }
+	if (bandmax + 8 > hr) { out.status = KSW_ST_HCAP; return; } // the ring holds whole 4-column words of the live band
+	if ((size_t)(qlen + tlen - 1) * (size_t)n_col + 2 * KSW_PMAT_PAD > p_cap) { out.status = KSW_ST_PCAP; return; }
+	pmat += KSW_PMAT_PAD;
 	const int hmask = hr - 1;
-	const int8_t qe2 = (int8_t)(qe * 2), max_sc8 = (int8_t)(P.match + qe * 2);
 	int8_t *u = sm, *v = u + t_cap, *x = v + t_cap, *y = x + t_cap, *s = y + t_cap;
+	uint32_t *U = (uint32_t*)u, *V = (uint32_t*)v, *X = (uint32_t*)x, *Y = (uint32_t*)y, *S = (uint32_t*)s;
+	uint8_t *sf = seqbuf, *qr = seqbuf + T16 + 16;
+	const uint32_t *SF = (const uint32_t*)sf, *QR = (const uint32_t*)qr;
+	const uint32_t QE2 = rep4(qe * 2), MAXSC = rep4(P.match + qe * 2), Q4 = rep4(P.q), MAT4 = rep4(P.match), MIS4 = rep4(P.mismatch);
 
-	// calloc :173 -- lanes that were never computed must read as zero
+	// calloc :173 -- lanes that were never computed must read as zero; stage sf (target, zero padded) and qr (reversed
+	// query, zero padded) exactly as :187-188 lay them out
 	for (int a = 0; a < 5; ++a) {
 		uint32_t *z = (uint32_t*)(sm + a * t_cap);
 		const int nwords = (T16 + (a == 4 ? 16 : 0)) >> 2;
 		for (int i = lane; i < nwords; i += 32) z[i] = 0;
 	}
+	for (int i = lane; i < T16 + 16; i += 32) sf[i] = i < tlen ? target[i] : (uint8_t)0;
+	{
+		const int nq = (qlen + 35) & ~3;
+		for (int i = lane; i < nq; i += 32) qr[i] = i < qlen ? query[qlen - 1 - i] : (uint8_t)0;
+	}
 	__syncwarp();
 
 	int last_st = -1, last_en = -1;
+	int4 *H4 = (int4*)H;
 	for (int r = 0; r < qlen + tlen - 1; ++r) {
 		int st0, en0;
 		ksw_band(r, qlen, tlen, w, st0, en0);
 		if (st0 > en0) { out.zdropped = 1; break; } // :200-203
 		const int st = st0 & ~15, en = en0 | 15;    // :205
 		out.cells += en0 - st0 + 1;
-		// boundary conditions :207-212 (values of the previous diagonal)
+		// boundary conditions :207-211 (values of the previous diagonal)
 		int x1, v1;
 		if (st > 0) {
 			if (st - 1 >= last_st && st - 1 <= last_en) { x1 = x[st - 1]; v1 = v[st - 1]; }
 			else x1 = v1 = 0;
 		} else { x1 = 0; v1 = r ? P.q : 0; }
-		if (en >= r && lane == 0) { y[r] = 0; u[r] = r ? P.q : 0; }
-		// scores: 16-lane blocks anchored at the exact st0 (:215-228); lanes outside keep stale s
-		{
-			const int total = ((en0 - st0) / 16 + 1) * 16;
-			for (int i = lane; i < total; i += 32) {
-				const int tt = st0 + i;
-				const int sq = tt < tlen ? target[tt] : 0;
-				const int sq2 = tt <= r ? query[r - tt] : 0; // qr[qlen-1-r+tt], zero padded past qlen
-				s[tt] = (sq == 4 || sq2 == 4) ? 0 : (sq == sq2 ? P.match : P.mismatch);
+		// One fused pass per 128 columns: every thread keeps its four columns in registers through the score blocks
+		// (:215-228), the core update (:262-284) and the exact-H update (:312-349).
+		const int bend = st0 + ((en0 - st0) / 16 + 1) * 16; // one past the last lane the 16-wide score blocks write
+		const int w1 = (bend - 1) >> 2, wend = en >> 2, wlast = wend > w1 ? wend : w1, ws0 = st0 >> 2;
+		const int en1 = st0 + (((en0 - st0) >> 2) << 2);    // end of the 4-wide vector part of the arg-max (:316)
+		uint32_t xc = (uint32_t)(x1 & 0xff) << 24, vc = (uint32_t)(v1 & 0xff) << 24;
+		// H[en0] is built from the OLD H[en0-1] (:318): fetch it before this diagonal's updates
+		const int hprev_old = r == 0 ? 0 : (en0 > 0 ? H[(en0 - 1) & hmask] : H[en0 & hmask]);
+		const unsigned bandw = (unsigned)(en0 - st0);       // columns st0 .. en0-1 are updated in the loop
+		uint32_t *pr = (uint32_t*)(pmat + (size_t)r * n_col) - (st >> 2);
+		int bh = (int)0x80000000, bt = 0; bool dup = false;  // this thread's best exact score, its column, and "seen twice"
+		const int rword = en >= r ? (r >> 2) : -1;           // :212, y[r] = 0 and u[r] = q, patched in registers
+		for (int w0 = st >> 2; w0 <= wlast; w0 += 32) {
+			const int wi = w0 + lane, t = wi << 2;
+			const bool core = wi <= wend, sca = wi >= ws0 && wi <= w1;
+			uint32_t xo = 0, vo = 0, ut = 0, yt = 0, so = 0;
+			int4 hq = make_int4(0, 0, 0, 0);
+			const bool hact = core && t + 3 >= st0 && t < en0;
+			if (core) { xo = X[wi]; vo = V[wi]; ut = U[wi]; yt = Y[wi]; }
+			if (hact) hq = H4[(t & hmask) >> 2];
+			if (core || sca) so = S[wi];
+			if (wi == rword) {
+				const int b = 8 * (r & 3);
+				yt &= ~(0xffu << b);
+				ut = (ut & ~(0xffu << b)) | ((uint32_t)((r ? P.q : 0) & 0xff) << b);
 			}
-		}
-		__syncwarp();
-		// core lanes st..en (:262-284)
-		{
-			uint8_t *pr = pmat + (size_t)r * n_col - st;
-			int xc = x1, vc = v1;
-			for (int t0 = st; t0 <= en; t0 += 32) {
-				const int t = t0 + lane;
-				const bool act = t <= en;
-				int xo = 0, vo = 0, ut = 0, yt = 0, sc = 0;
-				if (act) { xo = x[t]; vo = v[t]; ut = u[t]; yt = y[t]; sc = s[t]; }
-				int xt1 = __shfl_up_sync(FULL_MASK, xo, 1), vt1 = __shfl_up_sync(FULL_MASK, vo, 1);
-				if (lane == 0) { xt1 = xc; vt1 = vc; }
-				xc = __shfl_sync(FULL_MASK, xo, 31); vc = __shfl_sync(FULL_MASK, vo, 31);
-				if (act) {
-					int8_t z = (int8_t)(sc + qe2);
-					int8_t a = (int8_t)(xt1 + vt1);
-					int8_t b = (int8_t)(yt + ut);
-					int d = a > z ? 1 : 0;
-					z = a > z ? a : z;                                   // signed max
-					d = b > z ? 2 : d;                                   // signed compare
-					z = (uint8_t)z > (uint8_t)b ? z : b;                 // unsigned max
-					z = (uint8_t)z < (uint8_t)max_sc8 ? z : max_sc8;     // unsigned min
-					u[t] = (int8_t)(z - vt1);
-					v[t] = (int8_t)(z - ut);
-					z = (int8_t)(z - P.q);
-					a = (int8_t)(a - z);
-					b = (int8_t)(b - z);
-					x[t] = a > 0 ? a : (int8_t)0; if (a > 0) d |= 0x08;
-					y[t] = b > 0 ? b : (int8_t)0; if (b > 0) d |= 0x10;
-					pr[t] = (uint8_t)d;
+			uint32_t xp = __shfl_up_sync(FULL_MASK, xo, 1), vp = __shfl_up_sync(FULL_MASK, vo, 1);
+			if (lane == 0) { xp = xc; vp = vc; }
+			xc = __shfl_sync(FULL_MASK, xo, 31); vc = __shfl_sync(FULL_MASK, vo, 31);
+			if (sca) { // scores: lanes of this word inside the 16-wide blocks get fresh values, the others keep stale s
+				const uint32_t sq = SF[wi];
+				const int p = qlen - 1 - r + t; // qr index of lane t; negative only for lanes left of st0 (masked below)
+				uint32_t sq2;
+				if (p >= 0) sq2 = __funnelshift_r(QR[p >> 2], QR[(p >> 2) + 1], 8 * (p & 3));
+				else sq2 = p > -4 ? QR[0] << (8 * -p) : 0u;
+				const uint32_t neq = msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu);                                  // 0xff where the codes differ
+				const uint32_t nowild = msb_to_mask4(((sq ^ 0x04040404u) + 0x7f7f7f7fu) & ((sq2 ^ 0x04040404u) + 0x7f7f7f7fu)); // 0xff unless a code is 4
+				const uint32_t sc = sel4(neq, MIS4, MAT4) & nowild;
+				const int lo = st0 - t, hi = bend - t; // lanes [lo, hi) of this word belong to the blocks
+				uint32_t m = 0xffffffffu;
+				if (lo > 0) m &= 0xffffffffu << (8 * lo);
+				if (hi < 4) m &= 0xffffffffu >> (8 * (4 - hi));
+				so = sel4(m, sc, so);
+				S[wi] = so;
+			}
+			if (core) {
+				const uint32_t xt1 = __funnelshift_l(xp, xo, 8), vt1 = __funnelshift_l(vp, vo, 8); // lanes t-1..t+2
+				uint32_t z = __vadd4(so, QE2);
+				uint32_t a = __vadd4(xt1, vt1);
+				uint32_t b = __vadd4(yt, ut);
+				uint32_t m = __vcmpgts4(a, z);                 // a > z (signed)
+				uint32_t d = m & 0x01010101u;
+				z = sel4(m, a, z);                             // signed max
+				m = __vcmpgts4(b, z);                          // b > z (signed)
+				d = sel4(m, 0x02020202u, d);
+				z = sel4(__vcmpgtu4(b, z), b, z);              // unsigned max
+				z = sel4(__vcmpgtu4(z, MAXSC), MAXSC, z);      // unsigned min
+				const uint32_t vn = __vsub4(z, ut);
+				U[wi] = __vsub4(z, vt1); V[wi] = vn;
+				z = __vsub4(z, Q4);
+				a = __vsub4(a, z);
+				b = __vsub4(b, z);
+				m = __vcmpgts4(a, 0u);
+				X[wi] = a & m; d |= m & 0x08080808u;
+				m = __vcmpgts4(b, 0u);
+				Y[wi] = b & m; d |= m & 0x10101010u;
+				pr[wi] = d;
+				if (hact) { // exact H of the in-band columns st0 .. en0-1 of this word (:323-348): H[t] += v8[t] - qe
+					int hv[4] = {hq.x, hq.y, hq.z, hq.w};
+#pragma unroll
+					for (int c = 0; c < 4; ++c) {
+						const int tc = t + c;
+						const bool in = (unsigned)(tc - st0) < bandw;
+						const int h = hv[c] + (int)((vn >> (8 * c)) & 0xff) - qe;
+						const bool gt = in && h > bh, eq = in && h == bh;
+						hv[c] = in ? h : hv[c];
+						bt = gt ? tc : bt;
+						dup = gt ? false : (eq ? true : dup);
+						bh = gt ? h : bh;
+					}
+					H4[(t & hmask) >> 2] = make_int4(hv[0], hv[1], hv[2], hv[3]);
 				}
 			}
 		}
-		__syncwarp();
-		// exact max :312-357
-		int max_H, max_t, Hen0, Hst0;
-		if (r > 0) {
-			const int hen = en0 > 0 ? H[(en0 - 1) & hmask] + (int)(uint8_t)u[en0] - qe : H[en0 & hmask] + (int)(uint8_t)v[en0] - qe;
-			__syncwarp(); // every lane has read the old H[en0-1] before anyone updates
-			const int en1 = st0 + ((en0 - st0) / 4) * 4;
-			int bh = hen; unsigned br = 0; // rank 0 = the initial candidate (H[en0], en0): wins every tie
-			for (int t = st0 + lane; t < en0; t += 32) {
-				const int h = H[t & hmask] + (int)(uint8_t)v[t] - qe;
-				H[t & hmask] = h;
-				// tie order of the SSE code: 4 strided accumulators (lower accumulator, then lower t), then the scalar tail
-				const unsigned rank = 1u + ((t < en1 ? (unsigned)((t - st0) & 3) : 4u) << 20) + (unsigned)(t - st0);
-				if (h > bh || (h == bh && rank < br)) { bh = h; br = rank; }
+		__syncwarp(); // this diagonal's lanes and H[st0..en0) are visible to every thread
+		// the en0 cell, :318 / :349
+		int hen;
+		if (r == 0) hen = (int)(uint8_t)v[0] - qe - qe;
+		else hen = hprev_old + (int)(uint8_t)(en0 > 0 ? u[en0] : v[en0]) - qe;
+		int max_H, max_t;
+		{
+			const unsigned mk = __reduce_max_sync(FULL_MASK, (unsigned)bh ^ 0x80000000u);
+			const int mh = (int)(mk ^ 0x80000000u);
+			if (hen >= mh) { max_H = hen; max_t = en0; } // the initial candidate (H[en0], en0) wins every tie (:318-321)
+			else {
+				max_H = mh;
+				const bool mine = bh == mh;
+				const unsigned who = __ballot_sync(FULL_MASK, mine), twice = __ballot_sync(FULL_MASK, mine && dup);
+				if (__popc(who) == 1 && twice == 0) max_t = __shfl_sync(FULL_MASK, bt, __ffs(who) - 1);
+				else { // a tie between columns: the SSE order decides -- 4 strided accumulators (lower accumulator, then lower t), then the scalar tail
+					unsigned rk = 0xffffffffu;
+					for (int t = st0 + lane; t < en0; t += 32)
+						if (H[t & hmask] == mh) {
+							const unsigned cand = 1u + ((t < en1 ? (unsigned)((t - st0) & 3) : 4u) << 20) + (unsigned)(t - st0);
+							rk = cand < rk ? cand : rk;
+						}
+					rk = __reduce_min_sync(FULL_MASK, rk);
+					max_t = st0 + (int)((rk - 1) & 0xfffffu);
+				}
 			}
-			if (lane == 0) H[en0 & hmask] = hen;
-			const unsigned key = (unsigned)bh ^ 0x80000000u;
-			const unsigned mk = __reduce_max_sync(FULL_MASK, key);
-			const unsigned mr = __reduce_min_sync(FULL_MASK, key == mk ? br : 0xffffffffu);
-			max_H = (int)(mk ^ 0x80000000u);
-			max_t = mr == 0 ? en0 : st0 + (int)((mr - 1) & 0xfffffu);
-			Hen0 = hen;
-			__syncwarp();
-			Hst0 = H[st0 & hmask];
-		} else {
-			const int h0 = (int)(uint8_t)v[0] - qe - qe;
-			if (lane == 0) H[0] = h0;
-			max_H = h0; max_t = 0; Hen0 = h0; Hst0 = h0;
-			__syncwarp();
 		}
-		if (en0 == tlen - 1 && Hen0 > out.mte) { out.mte = Hen0; out.mte_q = r - en; }
-		if (r - st0 == qlen - 1 && Hst0 > out.mqe) { out.mqe = Hst0; out.mqe_t = st0; }
+		if (en0 == tlen - 1) {
+			if (hen > out.mte) { out.mte = hen; out.mte_q = r - en; }
+			if (r == qlen + tlen - 2) out.score = hen; // H[tlen-1]
+		}
+		if (r - st0 == qlen - 1) {
+			const int Hst0 = st0 == en0 ? hen : H[st0 & hmask];
+			if (Hst0 > out.mqe) { out.mqe = Hst0; out.mqe_t = st0; }
+		}
+		if (lane == 0) H[en0 & hmask] = hen;
+		__syncwarp();
 		{ // ksw_apply_zdrop :88-104
 			bool stop = false;
 			if (max_H > out.max) { out.max = max_H; out.max_t = max_t; out.max_q = r - max_t; }
@@ -183,7 +260,6 @@ __device__ void ksw2_warp(int qlen, const uint8_t *query, int tlen, const uint8_
 			}
 			if (stop) break;
 		}
-		if (r == qlen + tlen - 2 && en0 == tlen - 1) out.score = Hen0; // H[tlen-1]
 		last_st = st; last_en = en;
 	}
 	__syncwarp();
@@ -193,42 +269,78 @@ __device__ void ksw2_warp(int qlen, const uint8_t *query, int tlen, const uint8_
 	else if (out.max_t >= 0 && out.max_q >= 0) { i = out.max_t; j = out.max_q; }
 	else return;
 	int n = 0, ovf = 0;
-	if (lane == 0) {
+	{
+		// The walk itself is serial (one state machine), but its loads are not: before every stretch of <= 32 diagonals the
+		// whole warp prefetches the 32 x 32 tile of p[][] the path can touch (row r0-k can only be entered at columns
+		// i0-k .. i0) into shared memory, so lane 0 walks on shared-memory latency instead of one L2/HBM round trip per step.
+		uint32_t *tile = (uint32_t*)btile; // 32 rows of 8 words
 		int state = 0;
 		unsigned cur_op = 0xffu, cur_len = 0;
 		while (i >= 0 && j >= 0) {
-			const int r = i + j;
-			int st0, en0;
-			ksw_band(r, qlen, tlen, w, st0, en0);
-			const int off = st0 & ~15, off_end = en0 | 15;
-			int force_state = -1;
-			if (i < off) force_state = 2;
-			if (i > off_end) force_state = 1;
-			const unsigned tmp = force_state < 0 ? pmat[(size_t)r * n_col + i - off] : 0u;
-			if (state == 0) state = tmp & 7;
-			else if (!((tmp >> (state + 2)) & 1)) state = 0;
-			if (state == 0) state = tmp & 7;
-			if (force_state >= 0) state = force_state;
-			unsigned op;
-			if (state == 0) { op = 0; --i; --j; }
-			else if (state == 1 || state == 3) { op = 2; --i; }
-			else { op = 1; --j; }
-			if (op == cur_op) ++cur_len;
-			else {
-				if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; }
-				cur_op = op; cur_len = 1;
+			const int i0 = i, r0 = i + j;
+			{
+				const int rr = r0 - lane;
+				if (rr >= 0) {
+					int s0, e0;
+					ksw_band(rr, qlen, tlen, w, s0, e0);
+					long long x0 = (long long)rr * n_col + (i0 - 31 - (s0 & ~15)); // byte offset of column i0-31 of row rr
+					// a row that holds a readable entry has x0 within 31 bytes of the matrix; anything further out is never read
+					// (the walk is forced there), so clamping keeps the prefetch inside this warp's workspace
+					const long long x_hi = (long long)(qlen + tlen - 1) * n_col + KSW_PMAT_PAD - 40;
+					x0 = x0 < -(long long)(KSW_PMAT_PAD - 4) ? -(long long)(KSW_PMAT_PAD - 4) : (x0 > x_hi ? x_hi : x0);
+					const uint32_t *src = (const uint32_t*)(pmat + (x0 & ~3LL));          // pmat has 64 bytes of front padding
+					const int sh = 8 * (int)(x0 & 3);
+					uint32_t wprev = src[0];
+#pragma unroll
+					for (int k = 0; k < 8; ++k) {
+						const uint32_t wnext = src[k + 1];
+						tile[lane * 8 + k] = __funnelshift_r(wprev, wnext, sh);
+						wprev = wnext;
+					}
+				}
 			}
+			__syncwarp();
+			if (lane == 0) {
+				const uint8_t *tb = (const uint8_t*)tile;
+				while (i >= 0 && j >= 0 && i + j > r0 - 32) {
+					const int r = i + j;
+					int s0, e0;
+					ksw_band(r, qlen, tlen, w, s0, e0);
+					const int off = s0 & ~15, off_end = e0 | 15;
+					int force_state = -1;
+					if (i < off) force_state = 2;
+					if (i > off_end) force_state = 1;
+					const unsigned tmp = force_state < 0 ? tb[(r0 - r) * 32 + (i - (i0 - 31))] : 0u;
+					if (state == 0) state = tmp & 7;
+					else if (!((tmp >> (state + 2)) & 1)) state = 0;
+					if (state == 0) state = tmp & 7;
+					if (force_state >= 0) state = force_state;
+					unsigned op;
+					if (state == 0) { op = 0; --i; --j; }
+					else if (state == 1 || state == 3) { op = 2; --i; }
+					else { op = 1; --j; }
+					if (op == cur_op) ++cur_len;
+					else {
+						if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; }
+						cur_op = op; cur_len = 1;
+					}
+				}
+			}
+			i = __shfl_sync(FULL_MASK, i, 0); j = __shfl_sync(FULL_MASK, j, 0);
+			__syncwarp();
 		}
-		// the two trailing pushes (:73-74) merge with an equal pending op exactly as ksw_push_cigar does
-		if (i >= 0) {
-			if (cur_op == 2) cur_len += i + 1;
-			else { if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; } cur_op = 2; cur_len = i + 1; }
+		if (lane == 0) {
+			// the two trailing pushes (:73-74) merge with an equal pending op exactly as ksw_push_cigar does
+			if (i >= 0) {
+				if (cur_op == 2) cur_len += i + 1;
+				else { if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; } cur_op = 2; cur_len = i + 1; }
+			}
+			if (j >= 0) {
+				if (cur_op == 1) cur_len += j + 1;
+				else { if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; } cur_op = 1; cur_len = j + 1; }
+			}
+			if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; }
 		}
-		if (j >= 0) {
-			if (cur_op == 1) cur_len += j + 1;
-			else { if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; } cur_op = 1; cur_len = j + 1; }
-		}
-		if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; }
 	}
 	n = __shfl_sync(FULL_MASK, n, 0);
 	ovf = __shfl_sync(FULL_MASK, ovf, 0);

@@ -159,8 +159,10 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->n_sm = prop.multiProcessorCount;
 	ctx->ns = p->max_reads_per_region + 2;
 	ctx->nw = p->max_contig_len / 32 + 2;
-	ctx->asm_ctas = ctx->n_sm * 2;
-	ctx->dp_ctas = ctx->n_sm * 3;
+	// persistent grids: CTAs per SM (tunable for experiments through the environment)
+	const char *ea = getenv("IDL_ASM_CTAS_PER_SM"), *ed = getenv("IDL_DP_CTAS_PER_SM");
+	ctx->asm_ctas = ctx->n_sm * (ea && atoi(ea) > 0 ? atoi(ea) : 4);
+	ctx->dp_ctas = ctx->n_sm * (ed && atoi(ed) > 0 ? atoi(ed) : 3);
 	ctx->spill_tcap = (int)round_up((size_t)p->max_contig_len + 1024, 16);
 	ctx->lanes.resize((size_t)p->n_streams);
 	for (Lane &L : ctx->lanes) {
@@ -284,7 +286,8 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 	const size_t n_dp_warps = (size_t)ctx->dp_ctas * DP_WARPS;
 	CK(L.pmat.ensure(n_dp_warps * ctx->p_cap));
 	CK(L.cig_scratch.ensure(n_dp_warps * (size_t)ctx->cig_cap * 4));
-	CK(L.spill.ensure(n_dp_warps * ksw_lane_bytes(ctx->spill_tcap)));
+	const size_t spill_bytes = ((ksw_lane_bytes(ctx->spill_tcap) + 15) & ~(size_t)15) + ((ksw_seq_bytes(P.max_contig_len, ctx->spill_tcap) + 15) & ~(size_t)15);
+	CK(L.spill.ensure(n_dp_warps * spill_bytes));
 	CK(cudaMemsetAsync(L.cnt.p, 0, sizeof(DevCounters), L.stream));
 	L.launches = 0;
 
@@ -310,11 +313,12 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 	g.cap_events = L.cap_events; g.cap_cigar = L.cap_cigar; g.cap_al = L.cap_events; g.cap_alns = L.cap_alns; g.al_list = (AlEntry*)L.al_list.p;
 	g.P = P; g.cnt = a.cnt;
 	g.pmat = (uint8_t*)L.pmat.p; g.p_cap = ctx->p_cap; g.cig_scratch = (uint32_t*)L.cig_scratch.p; g.cig_cap = ctx->cig_cap;
-	g.spill = (int8_t*)L.spill.p; g.spill_tcap = ctx->spill_tcap;
+	g.spill = (int8_t*)L.spill.p; g.spill_tcap = ctx->spill_tcap; g.spill_bytes = spill_bytes;
 	g.t_cap = (int)std::min<size_t>(round_up(max_ref, 16), 2048);
 	if (b->n_regions > 0 && (P.stages & IDL_STAGE_ALIGN)) {
-		g.hr = next_pow2(std::max(P.a_bw < 0 ? P.max_contig_len : P.a_bw + 1, 1) + 2); g.qcap = 0;
-		const size_t smem = DP_WARPS * dp_smem_per_warp(g.t_cap, g.hr, g.qcap);
+		g.hr = next_pow2(std::max(P.a_bw < 0 ? P.max_contig_len : P.a_bw + 1, 1) + 8); g.qcap = 0;
+		g.seq_cap = (int)ksw_seq_bytes(1024, g.t_cap); // contigs up to 1 kb stage in shared memory, longer ones in the spill area
+		const size_t smem = DP_WARPS * dp_smem_per_warp(g.t_cap, g.hr, g.qcap, g.seq_cap);
 		align_kernel<<<ctx->dp_ctas, DP_THREADS, smem, L.stream>>>(g);
 		CK(cudaGetLastError()); L.launches++;
 	}
@@ -323,8 +327,9 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 		kmer_kernel<<<ctx->n_sm * 8, KMER_THREADS, 0, L.stream>>>(g);
 		CK(cudaGetLastError()); L.launches++;
 		CK(cudaEventRecord(L.ev[EV_KMER], L.stream));
-		g.hr = next_pow2((P.b_bw < 0 ? max_trim : std::min(max_trim, P.b_bw + 1)) + 2); g.qcap = (int)round_up((size_t)max_trim, 16);
-		const size_t smem = DP_WARPS * dp_smem_per_warp(g.t_cap, g.hr, g.qcap);
+		g.hr = next_pow2((P.b_bw < 0 ? max_trim : std::min(max_trim, P.b_bw + 1)) + 8); g.qcap = (int)round_up((size_t)max_trim, 16);
+		g.seq_cap = (int)ksw_seq_bytes(max_trim, g.t_cap);
+		const size_t smem = DP_WARPS * dp_smem_per_warp(g.t_cap, g.hr, g.qcap, g.seq_cap);
 		al_kernel<<<ctx->dp_ctas, DP_THREADS, smem, L.stream>>>(g);
 		CK(cudaGetLastError()); L.launches++;
 	} else CK(cudaEventRecord(L.ev[EV_KMER], L.stream));
@@ -480,16 +485,18 @@ struct KswBatchArgs {
 	unsigned n; const uint8_t *query, *target; const unsigned long long *q_off, *t_off;
 	KswParams kp; idl_ez *out; uint32_t *cigar; unsigned long long *cigar_off; unsigned cigar_cap;
 	unsigned *next; unsigned *cig_used;
-	uint8_t *pmat; size_t p_cap; uint32_t *cig_scratch; int cig_cap; int t_cap, hr;
+	uint8_t *pmat; size_t p_cap; uint32_t *cig_scratch; int cig_cap; int t_cap, hr, seq_cap;
 };
 
-__global__ void __launch_bounds__(DP_THREADS) ksw2_batch_kernel(KswBatchArgs a)
+__global__ void __launch_bounds__(DP_THREADS, 3) ksw2_batch_kernel(KswBatchArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = lane_id();
-	const size_t per = ((ksw_lane_bytes(a.t_cap) + 15) & ~(size_t)15) + (size_t)a.hr * 4;
+	const size_t per = ((ksw_lane_bytes(a.t_cap) + 15) & ~(size_t)15) + (size_t)a.hr * 4 + KSW_BTILE_BYTES + (size_t)a.seq_cap;
 	int8_t *lanes = (int8_t*)(smem_raw + per * warp_id());
 	int *H = (int*)(smem_raw + per * warp_id() + ((ksw_lane_bytes(a.t_cap) + 15) & ~(size_t)15));
+	uint8_t *btile = (uint8_t*)(H + a.hr);
+	uint8_t *seq = btile + KSW_BTILE_BYTES;
 	const size_t gw = (size_t)blockIdx.x * DP_WARPS + warp_id();
 	uint8_t *pmat = a.pmat + gw * a.p_cap;
 	uint32_t *cig = a.cig_scratch + gw * (size_t)a.cig_cap;
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(DP_THREADS) ksw2_batch_kernel(KswBatchArgs a)
 		if (i >= a.n) break;
 		const int qlen = (int)(a.q_off[i + 1] - a.q_off[i]), tlen = (int)(a.t_off[i + 1] - a.t_off[i]);
 		KswOut o;
-		ksw2_warp(qlen, a.query + a.q_off[i], tlen, a.target + a.t_off[i], a.kp, lanes, a.t_cap, H, a.hr, pmat, a.p_cap, cig, a.cig_cap, o);
+		ksw2_warp(qlen, a.query + a.q_off[i], tlen, a.target + a.t_off[i], a.kp, lanes, a.t_cap, seq, H, a.hr, btile, pmat, a.p_cap, cig, a.cig_cap, o);
 		unsigned coff = 0;
 		if (lane == 0) coff = atomicAdd(a.cig_used, (unsigned)o.n_cigar);
 		coff = __shfl_sync(FULL_MASK, coff, 0);
@@ -537,9 +544,10 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 	const int band_all = std::min(std::min(max_q, max_t), (w < 0 ? std::max(max_q, max_t) : w) + 1);
 	KswBatchArgs a; memset(&a, 0, sizeof a);
 	a.n = (unsigned)n; a.kp.match = match; a.kp.mismatch = mismatch; a.kp.q = gapo; a.kp.e = gape; a.kp.w = w; a.kp.zdrop = zdrop;
-	a.t_cap = (int)round_up((size_t)max_t, 16); a.hr = next_pow2(band_all + 2);
-	a.p_cap = round_up(max_p + 16, 256); a.cig_cap = max_q + max_t + 8; a.cigar_cap = (unsigned)cigar_cap;
-	const size_t per = ((ksw_lane_bytes(a.t_cap) + 15) & ~(size_t)15) + (size_t)a.hr * 4;
+	a.t_cap = (int)round_up((size_t)max_t, 16); a.hr = next_pow2(band_all + 8);
+	a.p_cap = round_up(max_p + 2 * KSW_PMAT_PAD + 16, 256); a.cig_cap = max_q + max_t + 8; a.cigar_cap = (unsigned)cigar_cap;
+	a.seq_cap = (int)((ksw_seq_bytes(max_q, a.t_cap) + 15) & ~(size_t)15);
+	const size_t per = ((ksw_lane_bytes(a.t_cap) + 15) & ~(size_t)15) + (size_t)a.hr * 4 + KSW_BTILE_BYTES + (size_t)a.seq_cap;
 	const size_t smem = per * DP_WARPS;
 	if (smem > 200 * 1024) return IDL_E_CAPACITY;
 	cudaFuncSetAttribute(ksw2_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -102,6 +102,11 @@ void idlh_vcf_free(idlh_vcf *w);
 char *idlh_vcf_header(const idlh_roiset *rs);   /* malloc'ed; free with idlh_free */
 /* records for regions [lo, lo + res->n_regions) of rs; malloc'ed text; dump_level as the oracle's (0 = VCF only) */
 char *idlh_vcf_records(idlh_vcf *w, const idlh_roiset *rs, int64_t lo, const idl_params *p, const idl_results *res, int32_t dump_level, char **dump);
+/* multi-GPU: shards emit records WITHOUT the dedup (idlh_vcf_set_dedup(w, 0)); after concatenating the shards in region
+ * order, idlh_vcf_dedup applies the reference's order-dependent filter (drop a record equal in CHROM, POS, REF, ALT to
+ * one of the last two emitted, src/indelope.nim:114-116,604-608) to the merged text.  Returns malloc'ed text. */
+void idlh_vcf_set_dedup(idlh_vcf *w, int on);
+char *idlh_vcf_dedup(const char *records);
 void idlh_free(void *p);
 
 #ifdef __cplusplus

@@ -47,10 +47,11 @@ class Caller:
             self._batches[lane] = cur
         return cur[0]
 
-    def call(self, rois, lo=0, hi=None, dump_level=0, max_reads=400_000, timings=None):
-        """returns (vcf record text, dump text). `timings` (list) receives one dict per batch."""
+    def call(self, rois, lo=0, hi=None, dump_level=0, max_reads=400_000, timings=None, dedup=True):
+        """returns (vcf record text, dump text). `timings` (list) receives one dict per batch.  dedup=False leaves the
+        order-dependent dedup to the caller (interval shards are merged first, see indelope_b200.shard)."""
         hi = rois.n_rois if hi is None else hi
-        writer = host.VcfWriter()
+        writer = host.VcfWriter(dedup=dedup)
         plans = plan_batches(rois, lo, hi, max_reads=max_reads)
         n_lanes = self.params.n_streams
         vcf, dump = [], []

@@ -216,11 +216,40 @@ struct Rec { std::string chrom, ref, alt, line; int64_t pos; };
 
 } // namespace
 
-struct idlh_vcf { bool have1 = false, have2 = false; Rec last1, last2; };
+struct idlh_vcf { bool have1 = false, have2 = false, dedup = true; Rec last1, last2; };
 
 extern "C" {
 
 idlh_vcf *idlh_vcf_new(void) { return new idlh_vcf(); }
+void idlh_vcf_set_dedup(idlh_vcf *w, int on) { w->dedup = on != 0; }
+
+char *idlh_vcf_dedup(const char *records)
+{
+	std::string out;
+	Rec last1, last2; bool have1 = false, have2 = false;
+	const char *p = records;
+	while (*p) {
+		const char *e = strchr(p, '\n');
+		const size_t n = e ? (size_t)(e - p) : strlen(p);
+		std::string line(p, n);
+		p += n + (e ? 1 : 0);
+		if (line.empty()) continue;
+		// CHROM POS ID REF ALT ...
+		std::vector<std::string> f;
+		size_t a = 0;
+		for (int k = 0; k < 5; ++k) { size_t b = line.find('\t', a); if (b == std::string::npos) break; f.push_back(line.substr(a, b - a)); a = b + 1; }
+		if (f.size() < 5) { out += line + "\n"; continue; }
+		Rec v; v.chrom = f[0]; v.pos = atoll(f[1].c_str()); v.ref = f[3]; v.alt = f[4];
+		auto same = [](const Rec &x, const Rec &y) { return x.pos == y.pos && x.chrom == y.chrom && x.ref == y.ref && x.alt == y.alt; };
+		if (have1 && same(v, last1)) continue;
+		if (have2 && same(v, last2)) continue;
+		out += line + "\n";
+		last2 = last1; have2 = have1; last1 = v; have1 = true;
+	}
+	char *o = (char*)malloc(out.size() + 1);
+	memcpy(o, out.c_str(), out.size() + 1);
+	return o;
+}
 void idlh_vcf_free(idlh_vcf *w) { delete w; }
 
 char *idlh_vcf_header(const idlh_roiset *rs) // src/indelope.nim:77-102,548-552,600
@@ -359,8 +388,8 @@ char *idlh_vcf_records(idlh_vcf *w, const idlh_roiset *rs, int64_t lo, const idl
 				         "\tGT:GQ:GL\t" + gt_enc[g.gt] + ":" + ffmt(g.qual, 4) + ":" + ffmt(g.gl[0], 4) + "," + ffmt(g.gl[1], 4) + "," + ffmt(g.gl[2], 4);
 				// order-dependent dedup against the last two emitted records, src/indelope.nim:604-608
 				auto same = [](const Rec &x, const Rec &y) { return x.pos == y.pos && x.chrom == y.chrom && x.ref == y.ref && x.alt == y.alt; };
-				if (w->have1 && same(v, w->last1)) continue;
-				if (w->have2 && same(v, w->last2)) continue;
+				if (w->dedup && w->have1 && same(v, w->last1)) continue;
+				if (w->dedup && w->have2 && same(v, w->last2)) continue;
 				vlines.push_back(v.line);
 				w->last2 = w->last1; w->have2 = w->have1;
 				w->last1 = v; w->have1 = true;

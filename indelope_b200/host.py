@@ -67,6 +67,9 @@ def lib():
         L.idlh_vcf_records.restype = C.c_void_p
         L.idlh_vcf_records.argtypes = [C.c_void_p, C.POINTER(RoiSetC), C.c_int64, C.POINTER(Params), C.POINTER(Results), C.c_int32, C.POINTER(C.c_void_p)]
         L.idlh_free.argtypes = [C.c_void_p]
+        L.idlh_vcf_set_dedup.argtypes = [C.c_void_p, C.c_int]
+        L.idlh_vcf_dedup.restype = C.c_void_p
+        L.idlh_vcf_dedup.argtypes = [C.c_char_p]
         L.idlh_trim.argtypes = [u8p, C.c_int32, i32p]
         L.idlh_trim.restype = C.c_int32
         _lib = L
@@ -244,8 +247,9 @@ def trim(quals):
 class VcfWriter:
     """filter cascade + VCF text over device results, carrying the dedup state of src/indelope.nim:598-608 across batches"""
 
-    def __init__(self):
+    def __init__(self, dedup=True):
         self.h = lib().idlh_vcf_new()
+        lib().idlh_vcf_set_dedup(self.h, 1 if dedup else 0)
 
     def records(self, rois, lo, params, results, dump_level=0):
         dump = C.c_void_p()
@@ -256,3 +260,8 @@ class VcfWriter:
         if getattr(self, "h", None):
             lib().idlh_vcf_free(self.h)
             self.h = None
+
+
+def dedup_records(text):
+    """order-dependent dedup of src/indelope.nim:604-608 over merged record lines"""
+    return _take(lib().idlh_vcf_dedup(text.encode()))

@@ -45,6 +45,7 @@ struct Counters {
 	int64_t slide_calls = 0, offsets = 0, char_compares = 0, exhaustive = 0;
 	int64_t contigs_pre = 0, contigs_post = 0, dp_a = 0, dp_b = 0, cells_a = 0, cells_b = 0;
 	int64_t events = 0, kmer_reads = 0, kmer_windows = 0, kmer_bytes = 0, al_events = 0;
+	int64_t corrections = 0, vote_invariant_violations = 0, left_merges = 0, merges = 0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -118,7 +119,7 @@ Match slide_align(const Contig &q, const Contig &t, int64_t min_overlap, int64_t
 				if (!allowed(q.sup[qo], t.sup[to], q.nreads, t.nreads)) {
 					mm += 1;
 					if (mm > max_mismatch) break;
-				} else correction.push_back(Corr{qo, to, q.sup[qo] > t.sup[to]});
+				} else { correction.push_back(Corr{qo, to, q.sup[qo] > t.sup[to]}); if (cn && !(q.nreads >= 4 && t.nreads >= 4)) cn->vote_invariant_violations++; }
 			} else ma += 1;
 			qo += 1; to += 1;
 		}
@@ -137,7 +138,7 @@ Match slide_align(const Contig &q, const Contig &t, int64_t min_overlap, int64_t
 				if (!allowed(q.sup[qo], t.sup[to], q.nreads, t.nreads)) {
 					mm += 1;
 					if (mm > max_mismatch) break;
-				} else correction.push_back(Corr{qo, to, q.sup[qo] > t.sup[to]});
+				} else { correction.push_back(Corr{qo, to, q.sup[qo] > t.sup[to]}); if (cn && !(q.nreads >= 4 && t.nreads >= 4)) cn->vote_invariant_violations++; }
 			} else ma += 1;
 			qo += 1; to += 1;
 		}
@@ -230,7 +231,7 @@ Match best_match(std::vector<CP> &contigs, const CP &q, int64_t min_overlap, int
 void list_insert(std::vector<CP> &contigs, CP &q, int64_t min_overlap, int64_t max_mismatch, allowed_fn allowed, Counters *cn)
 {
 	Match ma = best_match(contigs, q, min_overlap, max_mismatch, allowed, cn);
-	if (ma.aligned()) insert_contig(*contigs[ma.contig_i], *q, ma);
+	if (ma.aligned()) { if (cn) { cn->merges++; cn->left_merges += ma.offset < 0; cn->corrections += (int64_t)ma.corrections.size(); } insert_contig(*contigs[ma.contig_i], *q, ma); }
 	else contigs.push_back(q);
 }
 
@@ -249,7 +250,7 @@ std::vector<CP> combine(std::vector<CP> &contigs, int64_t max_mismatch, int64_t 
 	for (size_t i = 0; i < contigs.size(); ++i) {
 		if (i == usedi) continue;
 		Match ma = best_match(result, contigs[i], 65, max_mismatch, allowed, cn); // default min_overlap (:224)
-		if (ma.aligned()) insert_contig(*result[ma.contig_i], *contigs[i], ma);
+		if (ma.aligned()) { if (cn) { cn->merges++; cn->left_merges += ma.offset < 0; cn->corrections += (int64_t)ma.corrections.size(); } insert_contig(*result[ma.contig_i], *contigs[i], ma); }
 		else if (contigs[i]->nreads > 0) result.push_back(contigs[i]);
 	}
 	return result;
@@ -781,8 +782,9 @@ int orc_call(const orc_roiset_t *in, const orc_params_t *p, char **dump, char **
 		Out &o = outs[(size_t)k];
 		d += o.dump;
 		for (const Variant &x : o.variants) {
-			if (last_var && x.same(*last_var)) continue;
-			if (last_var2 && x.same(*last_var2)) continue;
+			const bool dedup = !(p->dump_level & 32); // bit5: raw records (interval shards dedup after merging)
+			if (dedup && last_var && x.same(*last_var)) continue;
+			if (dedup && last_var2 && x.same(*last_var2)) continue;
 			std::string line = x.text();
 			v += line + "\n";
 			if (p->dump_level & 16) d += "V\t" + line + "\n";
@@ -795,6 +797,7 @@ int orc_call(const orc_roiset_t *in, const orc_params_t *p, char **dump, char **
 		c.dp_a += o.cn.dp_a; c.dp_b += o.cn.dp_b; c.cells_a += o.cn.cells_a; c.cells_b += o.cn.cells_b;
 		c.events += o.cn.events; c.kmer_reads += o.cn.kmer_reads; c.kmer_windows += o.cn.kmer_windows; c.kmer_bytes += o.cn.kmer_bytes;
 		c.al_events += o.cn.al_events;
+		c.corrections += o.cn.corrections; c.vote_invariant_violations += o.cn.vote_invariant_violations; c.left_merges += o.cn.left_merges; c.merges += o.cn.merges;
 	}
 	c.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 	if (dump) *dump = dup_text(d);

@@ -45,7 +45,7 @@ typedef struct {
 	int32_t min_ctg_len;    /* -c, :569 */
 	int32_t min_event_len;  /* -e, :570 */
 	int32_t use_ref_ksw2;   /* 1: run DPs through oracle/_ref/libksw2_ref.so (must be loaded first) */
-	int32_t dump_level;     /* bit0 R/C lines, bit1 supports in C lines, bit2 A lines, bit3 E lines, bit4 V lines */
+	int32_t dump_level;     /* bit0 R/C lines, bit1 supports in C lines, bit2 A lines, bit3 E lines, bit4 V lines, bit5 no dedup */
 	int32_t n_threads;      /* regions are independent; >1 only parallelises across regions */
 } orc_params_t;
 
@@ -61,6 +61,9 @@ typedef struct {
 	int64_t al_events;
 	int64_t variants;
 	double seconds;                     /* wall time of the call */
+	int64_t corrections;                /* voting sites applied by Contig.insert (src/contig.nim:161-173) */
+	int64_t vote_invariant_violations;  /* a correction with q.nreads < 4 or t.nreads < 4: never happens (GPU fast path relies on it) */
+	int64_t left_merges, merges;        /* merges with offset < 0 / all merges */
 } orc_counters_t;
 
 /* load oracle/_ref/libksw2_ref.so (the compiled reference DP); 0 on success */

@@ -44,8 +44,11 @@ COUNTER_FIELDS = ("regions reads slide_calls offsets char_compares exhaustive_co
                   "cells_a cells_b events kmer_reads kmer_windows kmer_bytes al_events variants").split()
 
 
+COUNTER_TAIL = "corrections vote_invariant_violations left_merges merges".split()
+
+
 class Counters(C.Structure):
-    _fields_ = [(n, C.c_int64) for n in COUNTER_FIELDS] + [("seconds", C.c_double)]
+    _fields_ = [(n, C.c_int64) for n in COUNTER_FIELDS] + [("seconds", C.c_double)] + [(n, C.c_int64) for n in COUNTER_TAIL]
 
 
 class Match(C.Structure):
@@ -244,6 +247,6 @@ def call(roiset, min_reads=3, min_ctg_len=73, min_event_len=4, use_ref_ksw2=Fals
     dump = C.c_void_p(); vcf = C.c_void_p(); cnt = Counters()
     rc = lib().orc_call(C.byref(rs.c), C.byref(p), C.byref(dump), C.byref(vcf), C.byref(cnt))
     assert rc == 0, rc
-    cd = {n: getattr(cnt, n) for n in COUNTER_FIELDS}
+    cd = {n: getattr(cnt, n) for n in COUNTER_FIELDS + COUNTER_TAIL}
     cd["seconds"] = cnt.seconds
     return _take(dump.value), _take(vcf.value), cd

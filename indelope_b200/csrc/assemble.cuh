@@ -33,6 +33,7 @@ struct AsmArgs {
 	idl_region_result *rres; idl_contig_result *cres; idl_aln_result *ares;
 	char *ctg_ascii; uint8_t *ctg_codes; uint32_t *ctg_sup; uint8_t *refcodes;
 	unsigned cap_contigs, cap_bases, cap_alns;
+	SortBufs sortA;
 	DevCounters *cnt;
 };
 
@@ -512,7 +513,17 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 						cr.aln = (int)ai;
 						idl_aln_result ar; memset(&ar, 0, sizeof ar);
 						ar.region = rg; ar.contig = cbegin + i;
+						// reference window of :213-220: fai.get(chrom, ctg.start, max_stop + width + 50), clipped to the shipped window
+						const int win_end = R.ref_start + (int)R.ref_len - 1;
+						const int max_stop = cr.start > R.max_stop ? cr.start : R.max_stop;
+						int end = max_stop + P.window_pad; if (end > win_end) end = win_end;
+						int tlen = end - cr.start + 1;
+						if (tlen < 0 || cr.start < R.ref_start) tlen = 0;
+						ar.ref_len = tlen;
 						args.ares[ai] = ar;
+						const uint8_t key = sort_key(est_diagonals(L, tlen, P.a_bw));
+						args.sortA.keys[ai] = key;
+						atomicAdd(&args.sortA.hist[key], 1u);
 					} else atomicOr(&args.cnt->overflow, 4u);
 				}
 				args.cres[cbegin + i] = cr;

@@ -18,9 +18,9 @@ struct DevCounters {
 	unsigned int n_alns;
 	unsigned int n_events;
 	unsigned int n_cigar_ops;
+	unsigned int n_al_items;       // AL fallback: reads that passed the window tests (two DP tasks each)
 	unsigned long long al_pack;    // (#AL events << 40) | total AL work items
 	unsigned int overflow;         // result pool overflow flags
-	unsigned int pad;
 	unsigned long long offsets_tested, dp_cells_a, dp_cells_b, dp_a, dp_b, kmer_reads, kmer_bytes, al_events;
 };
 
@@ -29,6 +29,21 @@ struct KswParams {
 	int8_t match, mismatch, q, e;
 	int w, zdrop;
 };
+
+#define SORT_BUCKETS 256
+// bucket sort of alignment tasks by estimated anti-diagonals (longest first): hist/start/cursor hold SORT_BUCKETS entries
+struct SortBufs { unsigned *hist, *start, *cursor; uint8_t *keys; unsigned *order; };
+__device__ __forceinline__ uint8_t sort_key(int diagonals) { const int k = diagonals >> 3; return (uint8_t)(k > SORT_BUCKETS - 1 ? SORT_BUCKETS - 1 : (k < 0 ? 0 : k)); }
+// executed anti-diagonals of one extension alignment are bounded by the band running out (ksw2_extz2_sse.c:196-203)
+__device__ __forceinline__ int est_diagonals(int qlen, int tlen, int w)
+{
+	if (qlen <= 0 || tlen <= 0) return 0;
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	int d = qlen + tlen - 1;
+	if (d > 2 * qlen + w) d = 2 * qlen + w;
+	if (d > 2 * tlen + w) d = 2 * tlen + w;
+	return d;
+}
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }

@@ -1,12 +1,14 @@
 // indelope_b200/csrc/genotype.cuh -- the part of callsemble after assembly (src/indelope.nim:208-372):
 //
+//   sort_*        bucket sort of alignment tasks by estimated anti-diagonals, longest first: the 32/G alignments that
+//                 share a warp run in lockstep, so they should have similar lengths
 //   align_kernel  call-site A of kernel 2 (contig -> reference window, bw=50 z=400, :213-221) followed, in the same
-//                 warp, by the glue: truncated CIGAR (src/ksw2/ksw2.nim:22-33), target/query event locations
+//                 group, by the glue: truncated CIGAR (src/ksw2/ksw2.nim:22-33), target/query event locations
 //                 (:71-91), ref/alt 27-mer selection and rejects (src/indelope.nim:229-281), get_min_flank (:118-132)
 //   kmer_kernel   kernel 3: ref/alt canonical 27-mer counting over the reads of the region (:283-311), one CTA per
 //                 event, one read per thread, 128-bit loads of the 2-bit packed reads, rolling forward/reverse codes
-//   al_kernel     AL fallback (:312-372): call-site B of kernel 2, two unbanded alignments per read, vote by
-//                 count_flanked_cigar (:185-199)
+//   al_prep / al_kernel / al_vote   AL fallback (:312-372): the per-read window tests, call-site B of kernel 2 (two
+//                 unbanded alignments per read) and the vote by count_flanked_cigar (:185-199)
 #pragma once
 #include "common.cuh"
 #include "ksw2.cuh"
@@ -14,59 +16,68 @@
 #define DP_WARPS 8
 #define DP_THREADS (DP_WARPS * 32)
 #define KMER_THREADS 128
+#define DP_G 8          // threads per alignment
+#define DP_W_A 3        // packed words per thread, call-site A: 8*3*4 = 96 columns = 80-lane band + 16 lanes of score overrun
+#define DP_W_B 6        // call-site B: 192 columns = a 150 bp read's unbanded diagonal (176 lanes) + overrun in one pass
+#define DP_NG (32 / DP_G)
 
 struct AlEntry { unsigned event; unsigned base; unsigned n_reads; unsigned pad; };
+struct AlItem { unsigned event; unsigned read; int start; int pad; }; // one read of one AL event: two DP tasks (2*i: reference, 2*i+1: contig)
+
 
 struct GenoArgs {
 	const idl_region *region; const idl_read *read;
 	const uint32_t *seq2, *seqn;
 	const uint8_t *refcodes; const uint8_t *ctg_codes;
 	idl_region_result *rres; idl_contig_result *cres; idl_aln_result *ares; idl_event_result *eres; uint32_t *cigar;
-	unsigned cap_events, cap_cigar, cap_al, cap_alns;
-	AlEntry *al_list;
+	unsigned cap_events, cap_cigar, cap_al, cap_alns, cap_items;
+	AlEntry *al_list; AlItem *al_items; int8_t *al_res; // al_res[task] = count_flanked_cigar, or -1 on a DP error
+	SortBufs sortA, sortB;
 	idl_params P;
 	DevCounters *cnt;
-	// DP workspaces: one per resident warp
+	// kernel 2 geometry of this launch (per group) and its global workspaces (one per resident group)
+	int ring_cols, hr, seq_cap;
 	uint8_t *pmat; size_t p_cap;
 	uint32_t *cig_scratch; int cig_cap;
-	int8_t *spill; int spill_tcap;   // global-memory lane storage for targets that do not fit shared memory
-	int t_cap, hr, qcap;             // shared-memory lane capacity, H ring size, query buffer bytes (AL)
-	int seq_cap;                     // shared-memory bytes per warp for the staged target / reversed query
-	size_t spill_bytes;              // global-memory spill area per warp: lanes, then sequences
+	uint8_t *seq_spill; int seq_spill_cap;  // global-memory sequence staging for alignments that do not fit seq_cap
 };
 
-__host__ __device__ inline size_t dp_smem_per_warp(int t_cap, int hr, int qcap, int seq_cap)
+// exclusive scan of the bucket histogram, longest bucket first
+__global__ void sort_scan_kernel(SortBufs s)
 {
-	return ((ksw_lane_bytes(t_cap) + 15) & ~(size_t)15) + (size_t)hr * 4 + KSW_BTILE_BYTES + (size_t)((qcap + 15) & ~15) + (size_t)((seq_cap + 15) & ~15);
+	__shared__ unsigned tmp[SORT_BUCKETS];
+	const int i = threadIdx.x;
+	tmp[i] = s.hist[SORT_BUCKETS - 1 - i];
+	__syncthreads();
+	if (i == 0) { unsigned acc = 0; for (int k = 0; k < SORT_BUCKETS; ++k) { const unsigned c = tmp[k]; tmp[k] = acc; acc += c; } }
+	__syncthreads();
+	s.start[SORT_BUCKETS - 1 - i] = tmp[i];
+	s.cursor[SORT_BUCKETS - 1 - i] = 0;
+}
+__global__ void sort_scatter_kernel(SortBufs s, const unsigned *n_ptr, unsigned mul, unsigned cap)
+{
+	unsigned n = *n_ptr * mul; if (n > cap) n = cap;
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const unsigned b = s.keys[i];
+		s.order[s.start[b] + atomicAdd(&s.cursor[b], 1u)] = i;
+	}
 }
 
-struct DpWarp { int8_t *lanes; int *H; uint8_t *btile; uint8_t *qbuf; uint8_t *seq; uint8_t *pmat; uint32_t *cig; int8_t *spill; uint8_t *spill_seq; };
-
-__device__ __forceinline__ DpWarp dp_carve(const GenoArgs &g, unsigned char *smem)
+// shared/global memory of the group this thread belongs to
+__device__ __forceinline__ KswMem dp_mem(const GenoArgs &g, unsigned char *smem, int qlen, int tlen)
 {
-	DpWarp d;
-	const size_t per = dp_smem_per_warp(g.t_cap, g.hr, g.qcap, g.seq_cap);
-	unsigned char *base = smem + per * warp_id();
-	d.lanes = (int8_t*)base;
-	d.H = (int*)(base + ((ksw_lane_bytes(g.t_cap) + 15) & ~(size_t)15));
-	d.btile = (uint8_t*)(d.H + g.hr);
-	d.qbuf = d.btile + KSW_BTILE_BYTES;
-	d.seq = d.qbuf + ((g.qcap + 15) & ~15);
-	const size_t gw = (size_t)blockIdx.x * DP_WARPS + warp_id();
-	d.pmat = g.pmat + gw * g.p_cap;
-	d.cig = g.cig_scratch + gw * (size_t)g.cig_cap;
-	d.spill = g.spill + gw * g.spill_bytes;
-	d.spill_seq = (uint8_t*)d.spill + ((ksw_lane_bytes(g.spill_tcap) + 15) & ~(size_t)15);
-	return d;
-}
-
-// run one alignment, spilling the lane arrays to global memory when the target does not fit shared memory
-__device__ __forceinline__ void dp_run(const GenoArgs &g, const DpWarp &d, int qlen, const uint8_t *q, int tlen, const uint8_t *t, KswParams kp, KswOut &o)
-{
-	const int T16 = (tlen + 15) & ~15;
-	const bool fits = T16 <= g.t_cap;
-	uint8_t *seq = ksw_seq_bytes(qlen, tlen) <= (size_t)g.seq_cap ? d.seq : d.spill_seq;
-	ksw2_warp(qlen, q, tlen, t, kp, fits ? d.lanes : d.spill, fits ? g.t_cap : g.spill_tcap, seq, d.H, g.hr, d.btile, d.pmat, g.p_cap, d.cig, g.cig_cap, o);
+	const int grp = warp_id() * DP_NG + (lane_id() / DP_G);
+	const size_t per = ksw_group_smem(g.ring_cols, g.hr, g.seq_cap);
+	unsigned char *base = smem + per * grp;
+	const size_t gg = (size_t)blockIdx.x * (DP_WARPS * DP_NG) + grp;
+	KswMem m;
+	m.lanes = (int8_t*)base; m.ring_cols = g.ring_cols;
+	m.H = (int*)(base + 5 * g.ring_cols); m.hr = g.hr;
+	if (ksw_seq_bytes(qlen, tlen) <= (size_t)g.seq_cap) { m.seq = base + 5 * g.ring_cols + g.hr * 4; m.seq_cap = g.seq_cap; }
+	else { m.seq = g.seq_spill + gg * (size_t)g.seq_spill_cap; m.seq_cap = g.seq_spill_cap; }
+	m.pmat = g.pmat + gg * g.p_cap; m.p_cap = g.p_cap;
+	m.cig = g.cig_scratch + gg * (size_t)g.cig_cap; m.cig_cap = g.cig_cap;
+	return m;
 }
 
 __device__ __forceinline__ unsigned dp_status_bits(int st)
@@ -88,7 +99,6 @@ __device__ uint64_t canon_code(const uint8_t *s, int K)
 	}
 	return f < rc ? f : rc;
 }
-
 __device__ __forceinline__ bool same_k(const uint8_t *a, const uint8_t *b, int K)
 {
 	for (int i = 0; i < K; ++i) if (a[i] != b[i]) return false;
@@ -101,125 +111,128 @@ __device__ __forceinline__ int distinct_k(const uint8_t *a, int K)
 	return __popc(m);
 }
 
-__global__ void __launch_bounds__(DP_THREADS, 3) align_kernel(GenoArgs g)
+// ---------------------------------------------------------------------------------------------------------------
+// call-site A + glue: one group of DP_G threads per alignment, DP_NG alignments per warp
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DP_THREADS, 2) align_kernel(GenoArgs g)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const DpWarp d = dp_carve(g, smem_raw);
-	const int lane = lane_id();
+	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;
+	const unsigned gmask = ((1u << DP_G) - 1u) << (lane & ~(DP_G - 1));
 	const idl_params &P = g.P;
 	const int K = IDL_KMER, width = (K + 1) / 2 - 1; // :218
 	KswParams kp; kp.match = (int8_t)P.match; kp.mismatch = (int8_t)P.mismatch; kp.q = (int8_t)P.a_gapo; kp.e = (int8_t)P.a_gape; kp.w = P.a_bw; kp.zdrop = P.a_zdrop;
 	const unsigned n_alns = g.cnt->n_alns < g.cap_alns ? g.cnt->n_alns : g.cap_alns;
 	for (;;) {
-		unsigned ai = 0;
-		if (lane == 0) ai = atomicAdd(&g.cnt->aln_next, 1u);
-		ai = __shfl_sync(FULL_MASK, ai, 0);
-		if (ai >= n_alns) break;
-		idl_aln_result ar = g.ares[ai];
-		const idl_contig_result cr = g.cres[ar.contig];
-		const idl_region R = g.region[ar.region];
-		// reference window of :213-220: fai.get(chrom, ctg.start, max_stop + width + 50), clipped to the shipped window
-		const int win_end = R.ref_start + (int)R.ref_len - 1;
-		int max_stop = cr.start > R.max_stop ? cr.start : R.max_stop;
-		int end = max_stop + P.window_pad; if (end > win_end) end = win_end;
-		int tlen = end - cr.start + 1;
-		if (tlen < 0 || cr.start < R.ref_start) tlen = 0;
-		const uint8_t *tq = g.refcodes + R.ref_off + (cr.start - R.ref_start);
-		const uint8_t *qq = g.ctg_codes + cr.seq_off;
-		KswOut o;
-		dp_run(g, d, cr.len, qq, tlen, tq, kp, o);
-		const int n = o.n_cigar;
-		int ntr = 0, nev = 0;
-		if (lane == 0) {
-			ntr = ksw_trunc_count(d.cig, n, o.max_q);
-			for (int k = 0; k < ntr; ++k) nev += (d.cig[n - 1 - k] & 0xf) != 0;
-		}
-		ntr = __shfl_sync(FULL_MASK, ntr, 0); nev = __shfl_sync(FULL_MASK, nev, 0);
-		unsigned coff = 0, eoff = 0;
-		const bool want_events = (P.stages & IDL_STAGE_GENOTYPE) && nev >= 1 && nev <= P.max_events; // :229
-		if (lane == 0) {
-			coff = atomicAdd(&g.cnt->n_cigar_ops, (unsigned)n);
-			if (want_events) eoff = atomicAdd(&g.cnt->n_events, (unsigned)nev);
-		}
-		coff = __shfl_sync(FULL_MASK, coff, 0); eoff = __shfl_sync(FULL_MASK, eoff, 0);
-		unsigned st = dp_status_bits(o.status);
-		if (coff + (unsigned)n > g.cap_cigar) { st |= IDL_RS_CIGAR_OVERFLOW; if (lane == 0) atomicOr(&g.cnt->overflow, 8u); }
-		else for (int k = lane; k < n; k += 32) g.cigar[coff + k] = d.cig[n - 1 - k]; // forward order
-		bool ev_ok = want_events;
-		if (ev_ok && eoff + (unsigned)nev > g.cap_events) { ev_ok = false; if (lane == 0) atomicOr(&g.cnt->overflow, 16u); }
-		if (lane == 0) {
-			ar.ref_len = tlen; ar.max = o.max; ar.zdropped = o.zdropped; ar.max_q = o.max_q; ar.max_t = o.max_t; ar.mqe = o.mqe; ar.mqe_t = o.mqe_t;
-			ar.mte = o.mte; ar.mte_q = o.mte_q; ar.score = o.score; ar.n_cigar = n; ar.n_cigar_trunc = ntr; ar.cigar_off = coff; ar.n_events = nev;
-			ar.event_begin = ev_ok ? eoff : IDL_NO_EVENTS; ar.status = st;
-			g.ares[ai] = ar;
-			if (st) atomicOr(&g.rres[ar.region].status, st);
-			atomicAdd(&g.cnt->dp_a, 1ULL); atomicAdd(&g.cnt->dp_cells_a, (unsigned long long)o.cells);
-		}
-		// ---- glue: lane e handles event e (at most 4)
-		if (ev_ok && lane < nev && st) { // slots were handed out before the DP status was known: mark them unusable
-			idl_event_result ev; memset(&ev, 0, sizeof ev);
-			ev.aln = ai; ev.index = lane; ev.reject = IDL_EV_DP_ERROR; ev.min_flank = -1; ev.amq_median = ev.rmq_median = -1;
-			g.eres[eoff + lane] = ev;
-		}
-		if (ev_ok && lane < nev && !st) {
-			idl_event_result ev; memset(&ev, 0, sizeof ev);
-			ev.aln = ai; ev.index = lane; ev.min_flank = -1; ev.amq_median = ev.rmq_median = -1; ev.ref_code = ev.alt_code = ~0ULL;
-			int toff = 0, qoff = 0, seen = 0; // target_locations / query_locations, src/ksw2/ksw2.nim:71-91
-			for (int k = 0; k < ntr; ++k) {
-				const uint32_t c = d.cig[n - 1 - k]; const int op = c & 0xf, len = (int)(c >> 4);
-				if (op != 0) {
-					if (seen == lane) {
-						ev.len = len;
-						if (op == 1) { ev.type = 0; ev.t_start = cr.start + toff; ev.t_stop = ev.t_start + 1; ev.q_start = qoff; ev.q_stop = qoff + len; }
-						else { ev.type = 1; ev.t_start = cr.start + toff; ev.t_stop = ev.t_start + len; ev.q_start = qoff; ev.q_stop = qoff + 1; }
-					}
-					++seen;
-				}
-				if (op != 1) toff += len;
-				if (op != 2) qoff += len;
+		unsigned base = 0;
+		if (lane == 0) base = atomicAdd(&g.cnt->aln_next, (unsigned)DP_NG);
+		base = __shfl_sync(FULL_MASK, base, 0);
+		if (base >= n_alns) break;
+		if (base + grp < n_alns) {
+			const unsigned ai = g.sortA.order[base + grp];
+			idl_aln_result ar = g.ares[ai];
+			const idl_contig_result cr = g.cres[ar.contig];
+			const idl_region R = g.region[ar.region];
+			const int tlen = ar.ref_len; // window of :213-220, computed when the task was created
+			const uint8_t *tq = g.refcodes + R.ref_off + (cr.start - R.ref_start);
+			const uint8_t *qq = g.ctg_codes + cr.seq_off;
+			KswQuery kq; kq.codes = qq; kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
+			const KswMem M = dp_mem(g, smem_raw, cr.len, tlen);
+			KswOut o;
+			ksw2_group<DP_G, DP_W_A>(cr.len, kq, tlen, tq, kp, M, o);
+			const uint32_t *cg = M.cig;
+			const int n = o.n_cigar;
+			int ntr = 0, nev = 0;
+			if (gl == 0) {
+				ntr = ksw_trunc_count(cg, n, o.max_q);
+				for (int k = 0; k < ntr; ++k) nev += (cg[n - 1 - k] & 0xf) != 0;
 			}
-			const int clen = cr.len;
-			do {
-				if (ev.len < P.min_event_len) { ev.reject = IDL_EV_SHORT; break; } // :234
-				int tstart = ev.t_start - cr.start - width; if (tstart < 0) tstart = 0; // :236-238
-				if (tstart + K > tlen) tstart = tlen - K;
-				ev.tstart = tstart;
-				if (tstart < 0) { ev.reject = IDL_EV_WINDOW; break; }
-				int off = clen - ev.q_stop - 1; if (ev.q_start < off) off = ev.q_start; // :243
-				ev.offset = off;
-				int qstart = ev.q_start - width; if (qstart < 0) qstart = 0;              // :244-246
-				if (qstart + K > clen) qstart = clen - K;
-				ev.qstart = qstart;
-				if (qstart < 0) { ev.reject = IDL_EV_WINDOW; break; }
-				bool same = same_k(tq + tstart, qq + qstart, K);
-				if (same) { // :255-262
-					qstart = ev.q_start - 3; if (qstart < 0) qstart = 0;
-					if (qstart + K > clen) { int qend = ev.q_stop + 4; if (qend > clen) qend = clen; qstart = qend - K; }
+			ntr = __shfl_sync(gmask, ntr, 0, DP_G); nev = __shfl_sync(gmask, nev, 0, DP_G);
+			unsigned coff = 0, eoff = 0;
+			const bool want_events = (P.stages & IDL_STAGE_GENOTYPE) && nev >= 1 && nev <= P.max_events; // :229
+			if (gl == 0) {
+				coff = atomicAdd(&g.cnt->n_cigar_ops, (unsigned)n);
+				if (want_events) eoff = atomicAdd(&g.cnt->n_events, (unsigned)nev);
+			}
+			coff = __shfl_sync(gmask, coff, 0, DP_G); eoff = __shfl_sync(gmask, eoff, 0, DP_G);
+			unsigned st = dp_status_bits(o.status);
+			if (coff + (unsigned)n > g.cap_cigar) { st |= IDL_RS_CIGAR_OVERFLOW; if (gl == 0) atomicOr(&g.cnt->overflow, 8u); }
+			else for (int k = gl; k < n; k += DP_G) g.cigar[coff + k] = cg[n - 1 - k]; // forward order
+			bool ev_ok = want_events;
+			if (ev_ok && eoff + (unsigned)nev > g.cap_events) { ev_ok = false; if (gl == 0) atomicOr(&g.cnt->overflow, 16u); }
+			if (gl == 0) {
+				ar.max = o.max; ar.zdropped = o.zdropped; ar.max_q = o.max_q; ar.max_t = o.max_t; ar.mqe = o.mqe; ar.mqe_t = o.mqe_t;
+				ar.mte = o.mte; ar.mte_q = o.mte_q; ar.score = o.score; ar.n_cigar = n; ar.n_cigar_trunc = ntr; ar.cigar_off = coff; ar.n_events = nev;
+				ar.event_begin = ev_ok ? eoff : IDL_NO_EVENTS; ar.status = st;
+				g.ares[ai] = ar;
+				if (st) atomicOr(&g.rres[ar.region].status, st);
+				atomicAdd(&g.cnt->dp_a, 1ULL); atomicAdd(&g.cnt->dp_cells_a, (unsigned long long)o.cells);
+			}
+			// ---- glue: thread e of the group handles event e (at most 4)
+			if (ev_ok && gl < nev && st) { // slots were handed out before the DP status was known: mark them unusable
+				idl_event_result ev; memset(&ev, 0, sizeof ev);
+				ev.aln = ai; ev.index = gl; ev.reject = IDL_EV_DP_ERROR; ev.min_flank = -1; ev.amq_median = ev.rmq_median = -1;
+				g.eres[eoff + gl] = ev;
+			}
+			if (ev_ok && gl < nev && !st) {
+				idl_event_result ev; memset(&ev, 0, sizeof ev);
+				ev.aln = ai; ev.index = gl; ev.min_flank = -1; ev.amq_median = ev.rmq_median = -1; ev.ref_code = ev.alt_code = ~0ULL;
+				int toff = 0, qoff = 0, seen = 0; // target_locations / query_locations, src/ksw2/ksw2.nim:71-91
+				for (int k = 0; k < ntr; ++k) {
+					const uint32_t c = cg[n - 1 - k]; const int op = c & 0xf, len = (int)(c >> 4);
+					if (op != 0) {
+						if (seen == gl) {
+							ev.len = len;
+							if (op == 1) { ev.type = 0; ev.t_start = cr.start + toff; ev.t_stop = ev.t_start + 1; ev.q_start = qoff; ev.q_stop = qoff + len; }
+							else { ev.type = 1; ev.t_start = cr.start + toff; ev.t_stop = ev.t_start + len; ev.q_start = qoff; ev.q_stop = qoff + 1; }
+						}
+						++seen;
+					}
+					if (op != 1) toff += len;
+					if (op != 2) qoff += len;
+				}
+				const int clen = cr.len;
+				do {
+					if (ev.len < P.min_event_len) { ev.reject = IDL_EV_SHORT; break; } // :234
+					int tstart = ev.t_start - cr.start - width; if (tstart < 0) tstart = 0; // :236-238
+					if (tstart + K > tlen) tstart = tlen - K;
+					ev.tstart = tstart;
+					if (tstart < 0) { ev.reject = IDL_EV_WINDOW; break; }
+					int off = clen - ev.q_stop - 1; if (ev.q_start < off) off = ev.q_start; // :243
+					ev.offset = off;
+					int qstart = ev.q_start - width; if (qstart < 0) qstart = 0;              // :244-246
+					if (qstart + K > clen) qstart = clen - K;
 					ev.qstart = qstart;
 					if (qstart < 0) { ev.reject = IDL_EV_WINDOW; break; }
-					same = same_k(tq + tstart, qq + qstart, K);
-				}
-				if (same && (ev.q_start == 0 || distinct_k(qq + qstart, K) == 1)) { ev.reject = IDL_EV_SAME_KMER; break; } // :264
-				if (distinct_k(tq + tstart, K) < 3) { ev.reject = IDL_EV_LOW_CPLX; break; }                                 // :266
-				if (same) { ev.reject = IDL_EV_BUG_SAME; break; }                                                            // :268-275
-				ev.ref_code = canon_code(tq + tstart, K); ev.alt_code = canon_code(qq + qstart, K);
-				// get_min_flank(qloc, ez), :118-132, over the truncated CIGAR
-				{
-					long long result = 0x7fffffffffffffffLL; bool found = false; int mf = 0;
-					for (int k = 0; k < ntr; ++k) {
-						const uint32_t c = d.cig[n - 1 - k]; const int op = c & 0xf; const long long len = c >> 4;
-						if (op == 0) {
-							result = found ? (len < result ? len : result) : len;
-							if (found) { mf = (int)result; break; }
-						} else if (op - 1 == ev.type && len == ev.len) {
-							if (result == 0x7fffffffffffffffLL) result = 0;
-							found = true;
-						}
+					bool same = same_k(tq + tstart, qq + qstart, K);
+					if (same) { // :255-262
+						qstart = ev.q_start - 3; if (qstart < 0) qstart = 0;
+						if (qstart + K > clen) { int qend = ev.q_stop + 4; if (qend > clen) qend = clen; qstart = qend - K; }
+						ev.qstart = qstart;
+						if (qstart < 0) { ev.reject = IDL_EV_WINDOW; break; }
+						same = same_k(tq + tstart, qq + qstart, K);
 					}
-					ev.min_flank = mf;
-				}
-			} while (0);
-			g.eres[eoff + lane] = ev;
+					if (same && (ev.q_start == 0 || distinct_k(qq + qstart, K) == 1)) { ev.reject = IDL_EV_SAME_KMER; break; } // :264
+					if (distinct_k(tq + tstart, K) < 3) { ev.reject = IDL_EV_LOW_CPLX; break; }                                 // :266
+					if (same) { ev.reject = IDL_EV_BUG_SAME; break; }                                                            // :268-275
+					ev.ref_code = canon_code(tq + tstart, K); ev.alt_code = canon_code(qq + qstart, K);
+					{ // get_min_flank(qloc, ez), :118-132, over the truncated CIGAR
+						long long result = 0x7fffffffffffffffLL; bool found = false; int mf = 0;
+						for (int k = 0; k < ntr; ++k) {
+							const uint32_t c = cg[n - 1 - k]; const int op = c & 0xf; const long long len = c >> 4;
+							if (op == 0) {
+								result = found ? (len < result ? len : result) : len;
+								if (found) { mf = (int)result; break; }
+							} else if (op - 1 == ev.type && len == ev.len) {
+								if (result == 0x7fffffffffffffffLL) result = 0;
+								found = true;
+							}
+						}
+						ev.min_flank = mf;
+					}
+				} while (0);
+				g.eres[eoff + gl] = ev;
+			}
 		}
 		__syncwarp();
 	}
@@ -309,6 +322,47 @@ __global__ void __launch_bounds__(KMER_THREADS) kmer_kernel(GenoArgs g)
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// AL fallback, step 1: one thread per (AL event, read): the window tests of :328-341; survivors become two DP tasks
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void al_prep_kernel(GenoArgs g)
+{
+	const idl_params &P = g.P;
+	const unsigned long long pack = g.cnt->al_pack;
+	unsigned n_al = (unsigned)(pack >> 40); if (n_al > g.cap_al) n_al = g.cap_al;
+	const unsigned total = (unsigned)(pack & ((1ULL << 40) - 1));
+	if (n_al == 0) return;
+	for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
+		// entries are sorted by base (one packed atomic hands out slot and base together)
+		int lo = 0, hi = (int)n_al - 1;
+		while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (g.al_list[mid].base <= it) lo = mid; else hi = mid - 1; }
+		const AlEntry ae = g.al_list[lo];
+		const unsigned j = it - ae.base;
+		if (j >= ae.n_reads) continue; // item of an entry dropped by overflow
+		const idl_event_result ev = g.eres[ae.event];
+		const idl_aln_result ar = g.ares[ev.aln];
+		const idl_contig_result cr = g.cres[ar.contig];
+		const idl_region R = g.region[ar.region];
+		const idl_read rd = g.read[R.read_begin + j];
+		if ((int)rd.mapq < P.count_min_mapq) continue;              // :328
+		const int rs = rd.start + rd.trim_a;                       // :331
+		if (rs > ev.t_stop) continue;                              // :332
+		const int Lx = ev.type == 0 ? ev.len : 0;                  // :333-335
+		if (rs + (int)rd.trim_len + Lx < ev.t_start) continue;     // :336
+		const int start = (rs > cr.start ? rs : cr.start) - cr.start; // :339
+		const unsigned slot = atomicAdd(&g.cnt->n_al_items, 1u);
+		if (slot >= g.cap_items) { atomicOr(&g.cnt->overflow, 64u); continue; }
+		AlItem a; a.event = ae.event; a.read = R.read_begin + j; a.start = start; a.pad = 0;
+		g.al_items[slot] = a;
+		int rlen = ar.ref_len - start; if (rlen < 0) rlen = 0;
+		int clen = cr.len - start; if (clen < 0) clen = 0;
+		const int qlen = rd.trim_len, wb = P.b_bw;
+		const uint8_t k0 = sort_key(est_diagonals(qlen, rlen, wb)), k1 = sort_key(est_diagonals(qlen, clen, wb));
+		g.sortB.keys[2 * slot] = k0; g.sortB.keys[2 * slot + 1] = k1;
+		atomicAdd(&g.sortB.hist[k0], 1u); atomicAdd(&g.sortB.hist[k1], 1u);
+	}
+}
+
 // count_flanked_cigar (src/indelope.nim:185-199) over the truncated view of the reversed scratch
 __device__ __forceinline__ int count_flanked(const uint32_t *cig_rev, int n, int max_q)
 {
@@ -324,71 +378,59 @@ __device__ __forceinline__ int count_flanked(const uint32_t *cig_rev, int n, int
 	return cnt;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// AL fallback: one warp per (event, read) work item
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DP_THREADS, 3) al_kernel(GenoArgs g)
+// AL fallback, step 2: call-site B of kernel 2, one group per task (read vs reference suffix / contig suffix), :343-347
+__global__ void __launch_bounds__(DP_THREADS, 2) al_kernel(GenoArgs g)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const DpWarp d = dp_carve(g, smem_raw);
-	const int lane = lane_id();
+	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;
 	const idl_params &P = g.P;
 	KswParams kp; kp.match = (int8_t)P.match; kp.mismatch = (int8_t)P.mismatch; kp.q = (int8_t)P.b_gapo; kp.e = (int8_t)P.b_gape; kp.w = P.b_bw; kp.zdrop = P.b_zdrop;
-	const unsigned long long pack = g.cnt->al_pack;
-	unsigned n_al = (unsigned)(pack >> 40); if (n_al > g.cap_al) n_al = g.cap_al;
-	const unsigned total = (unsigned)(pack & ((1ULL << 40) - 1));
+	unsigned n_items = g.cnt->n_al_items; if (n_items > g.cap_items) n_items = g.cap_items;
+	const unsigned n_tasks = 2 * n_items;
 	for (;;) {
-		unsigned it = 0;
-		if (lane == 0) it = atomicAdd(&g.cnt->al_next, 1u);
-		it = __shfl_sync(FULL_MASK, it, 0);
-		if (it >= total) break;
-		if (n_al == 0) break;
-		// entries are sorted by base (one packed atomic hands out slot and base together)
-		int lo = 0, hi = (int)n_al - 1;
-		while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (g.al_list[mid].base <= it) lo = mid; else hi = mid - 1; }
-		const AlEntry ae = g.al_list[lo];
-		const unsigned j = it - ae.base;
-		if (j >= ae.n_reads) continue; // item belongs to a dropped (overflowed) entry
-		const idl_event_result ev = g.eres[ae.event];
-		const idl_aln_result ar = g.ares[ev.aln];
-		const idl_contig_result cr = g.cres[ar.contig];
-		const idl_region R = g.region[ar.region];
-		const idl_read rd = g.read[R.read_begin + j];
-		if ((int)rd.mapq < P.count_min_mapq) continue;              // :328
-		const int rs = rd.start + rd.trim_a;                       // :331
-		if (rs > ev.t_stop) continue;                              // :332
-		const int Lx = ev.type == 0 ? ev.len : 0;                  // :333-335
-		if (rs + (int)rd.trim_len + Lx < ev.t_start) continue;     // :336
-		const int start = (rs > cr.start ? rs : cr.start) - cr.start; // :339
-		const int qlen = rd.trim_len;
-		if (qlen > g.qcap) { if (lane == 0) atomicOr(&g.rres[ar.region].status, IDL_RS_READ_TOO_LONG); continue; }
-		// unpack the trimmed read to 0..4 codes (src/ksw2/ksw2.nim:127-132)
-		for (int i = lane; i < qlen; i += 32) {
-			const unsigned b = rd.seq_off + rd.trim_a + i;
-			const unsigned isn = (g.seqn[b >> 5] >> (b & 31)) & 1u;
-			d.qbuf[i] = isn ? 4 : (uint8_t)((g.seq2[b >> 4] >> (2 * (b & 15))) & 3u);
+		unsigned base = 0;
+		if (lane == 0) base = atomicAdd(&g.cnt->al_next, (unsigned)DP_NG);
+		base = __shfl_sync(FULL_MASK, base, 0);
+		if (base >= n_tasks) break;
+		if (base + grp < n_tasks) {
+			const unsigned task = g.sortB.order[base + grp];
+			const AlItem it = g.al_items[task >> 1];
+			const idl_event_result ev = g.eres[it.event];
+			const idl_aln_result ar = g.ares[ev.aln];
+			const idl_contig_result cr = g.cres[ar.contig];
+			const idl_region R = g.region[ar.region];
+			const idl_read rd = g.read[it.read];
+			const int qlen = rd.trim_len;
+			KswQuery kq; kq.codes = nullptr; kq.seq2 = g.seq2; kq.seqn = g.seqn; kq.base = rd.seq_off + rd.trim_a;
+			const uint8_t *t; int tlen;
+			if (!(task & 1)) { t = g.refcodes + R.ref_off + (cr.start - R.ref_start) + it.start; tlen = ar.ref_len - it.start; } // ref_sub :340
+			else { t = g.ctg_codes + cr.seq_off + it.start; tlen = cr.len - it.start; }                                          // ctg_sub :341
+			if (tlen < 0) tlen = 0;
+			const KswMem M = dp_mem(g, smem_raw, qlen, tlen);
+			KswOut o;
+			ksw2_group<DP_G, DP_W_B>(qlen, kq, tlen, t, kp, M, o);
+			if (gl == 0) {
+				const unsigned st = dp_status_bits(o.status);
+				int c = count_flanked(M.cig, o.n_cigar, o.max_q);
+				if (c > 126) c = 126; // only "== 1" and "> 1" are consumed (:353-356)
+				if (st) { atomicOr(&g.rres[ar.region].status, st); c = -1; }
+				g.al_res[task] = (int8_t)c;
+				atomicAdd(&g.cnt->dp_b, 1ULL); atomicAdd(&g.cnt->dp_cells_b, (unsigned long long)o.cells);
+			}
 		}
 		__syncwarp();
-		const uint8_t *refw = g.refcodes + R.ref_off + (cr.start - R.ref_start);
-		int rlen = ar.ref_len - start; if (rlen < 0) rlen = 0;
-		int clen = cr.len - start; if (clen < 0) clen = 0;
-		KswOut o;
-		dp_run(g, d, qlen, d.qbuf, rlen, refw + start, kp, o);          // read_seq.align_to(ref_sub, ez_ref) :343
-		unsigned st = dp_status_bits(o.status);
-		int rn = 0, an = 0;
-		if (lane == 0) rn = count_flanked(d.cig, o.n_cigar, o.max_q);
-		unsigned long long cells = (unsigned long long)o.cells;
-		__syncwarp();
-		dp_run(g, d, qlen, d.qbuf, clen, g.ctg_codes + cr.seq_off + start, kp, o); // read_seq.align_to(ctg_sub, ez_alt) :344
-		st |= dp_status_bits(o.status);
-		cells += (unsigned long long)o.cells;
-		if (lane == 0) {
-			an = count_flanked(d.cig, o.n_cigar, o.max_q);
-			if (st) atomicOr(&g.rres[ar.region].status, st);
-			else if (rn == 1 && an > 1) atomicAdd(&g.eres[ae.event].ref_support, 1);   // :353-356
-			else if (an == 1 && rn > 1) atomicAdd(&g.eres[ae.event].alt_support, 1);
-			atomicAdd(&g.cnt->dp_b, 2ULL); atomicAdd(&g.cnt->dp_cells_b, cells);
-		}
-		__syncwarp();
+	}
+}
+
+// AL fallback, step 3: the vote of :353-356
+__global__ void al_vote_kernel(GenoArgs g)
+{
+	unsigned n_items = g.cnt->n_al_items; if (n_items > g.cap_items) n_items = g.cap_items;
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+		const int rn = g.al_res[2 * i], an = g.al_res[2 * i + 1];
+		if (rn < 0 || an < 0) continue; // DP capacity error, already flagged on the region
+		const AlItem it = g.al_items[i];
+		if (rn == 1 && an > 1) atomicAdd(&g.eres[it.event].ref_support, 1);
+		else if (an == 1 && rn > 1) atomicAdd(&g.eres[it.event].alt_support, 1);
 	}
 }

@@ -58,9 +58,9 @@ struct Lane {
 	// device batch
 	DevBuf region, read, seq2, seqn, ref2, refn;
 	// device results and intermediates
-	DevBuf rres, cres, ares, eres, cigar, ctg_ascii, ctg_codes, ctg_sup, refcodes, al_list, cnt;
+	DevBuf rres, cres, ares, eres, cigar, ctg_ascii, ctg_codes, ctg_sup, refcodes, al_list, al_items, al_res, sort_misc, keysA, orderA, keysB, orderB, cnt;
 	// workspaces
-	DevBuf planes, sup, pmat, cig_scratch, spill;
+	DevBuf planes, sup, pmat, cig_scratch, seq_spill;
 	// pinned host results
 	HostBuf h_rres, h_cres, h_ares, h_eres, h_cigar, h_seq, h_sup, h_cnt;
 	// state
@@ -68,7 +68,7 @@ struct Lane {
 	bool resident = false;              // device batch uploaded by idl_upload
 	bool payload = true;                // fetch result arrays in idl_wait
 	size_t n_regions = 0, n_reads = 0, n_seq_bases = 0, n_ref_bases = 0;
-	unsigned cap_contigs = 0, cap_bases = 0, cap_alns = 0, cap_events = 0, cap_cigar = 0;
+	unsigned cap_contigs = 0, cap_bases = 0, cap_alns = 0, cap_events = 0, cap_cigar = 0, cap_items = 0;
 	unsigned launches = 0;
 	idl_results res;
 };
@@ -80,7 +80,7 @@ struct idl_ctx {
 	std::vector<Lane> lanes;
 	uint64_t next_ticket = 1;
 	int asm_ctas = 0, dp_ctas = 0, ns = 0, nw = 0;
-	size_t p_cap = 1u << 20; int cig_cap = 4096; int spill_tcap = 0;
+	int cig_cap = 2048;
 	char err[512] = {0};
 };
 
@@ -162,8 +162,7 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	// persistent grids: CTAs per SM (tunable for experiments through the environment)
 	const char *ea = getenv("IDL_ASM_CTAS_PER_SM"), *ed = getenv("IDL_DP_CTAS_PER_SM");
 	ctx->asm_ctas = ctx->n_sm * (ea && atoi(ea) > 0 ? atoi(ea) : 4);
-	ctx->dp_ctas = ctx->n_sm * (ed && atoi(ed) > 0 ? atoi(ed) : 3);
-	ctx->spill_tcap = (int)round_up((size_t)p->max_contig_len + 1024, 16);
+	ctx->dp_ctas = ctx->n_sm * (ed && atoi(ed) > 0 ? atoi(ed) : 2);
 	ctx->lanes.resize((size_t)p->n_streams);
 	for (Lane &L : ctx->lanes) {
 		if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { idl_destroy(ctx); return IDL_E_CUDA; }
@@ -184,7 +183,8 @@ void idl_destroy(idl_ctx *ctx)
 	for (Lane &L : ctx->lanes) {
 		if (L.stream) cudaStreamSynchronize(L.stream);
 		for (DevBuf *b : {&L.region, &L.read, &L.seq2, &L.seqn, &L.ref2, &L.refn, &L.rres, &L.cres, &L.ares, &L.eres, &L.cigar, &L.ctg_ascii, &L.ctg_codes,
-		                  &L.ctg_sup, &L.refcodes, &L.al_list, &L.cnt, &L.planes, &L.sup, &L.pmat, &L.cig_scratch, &L.spill})
+		                  &L.ctg_sup, &L.refcodes, &L.al_list, &L.al_items, &L.al_res, &L.sort_misc, &L.keysA, &L.orderA, &L.keysB, &L.orderB, &L.cnt, &L.planes, &L.sup,
+		                  &L.pmat, &L.cig_scratch, &L.seq_spill})
 			b->release();
 		for (HostBuf *b : {&L.h_rres, &L.h_cres, &L.h_ares, &L.h_eres, &L.h_cigar, &L.h_seq, &L.h_sup, &L.h_cnt}) b->release();
 		for (auto &ev : L.ev) if (ev) cudaEventDestroy(ev);
@@ -279,17 +279,32 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 	CK(L.refcodes.ensure(b->n_ref_bases + 64));
 	CK(L.al_list.ensure((size_t)L.cap_events * sizeof(AlEntry) + 16));
 	CK(L.cnt.ensure(sizeof(DevCounters)));
+	L.cap_items = (unsigned)std::min<size_t>(8 * b->n_reads + 1024, 0x3fffffffu); // AL items: a read takes part in few AL events
+	CK(L.al_items.ensure((size_t)L.cap_items * sizeof(AlItem))); CK(L.al_res.ensure((size_t)L.cap_items * 2 + 16));
+	CK(L.sort_misc.ensure(6 * SORT_BUCKETS * sizeof(unsigned)));
+	CK(L.keysA.ensure((size_t)L.cap_alns + 16)); CK(L.orderA.ensure((size_t)L.cap_alns * 4 + 16));
+	CK(L.keysB.ensure((size_t)L.cap_items * 2 + 16)); CK(L.orderB.ensure((size_t)L.cap_items * 8 + 16));
 	// workspaces
 	const int asm_ctas = (int)std::max<size_t>(1, std::min<size_t>(b->n_regions, (size_t)ctx->asm_ctas));
 	CK(L.planes.ensure((size_t)ctx->asm_ctas * ctx->ns * 3 * ctx->nw * 4));
 	CK(L.sup.ensure((size_t)ctx->asm_ctas * ctx->ns * P.max_contig_len * 2));
-	const size_t n_dp_warps = (size_t)ctx->dp_ctas * DP_WARPS;
-	CK(L.pmat.ensure(n_dp_warps * ctx->p_cap));
-	CK(L.cig_scratch.ensure(n_dp_warps * (size_t)ctx->cig_cap * 4));
-	const size_t spill_bytes = ((ksw_lane_bytes(ctx->spill_tcap) + 15) & ~(size_t)15) + ((ksw_seq_bytes(P.max_contig_len, ctx->spill_tcap) + 15) & ~(size_t)15);
-	CK(L.spill.ensure(n_dp_warps * spill_bytes));
+	// kernel 2 geometry: call-site A (contig vs window, banded) and B (read vs suffix, unbanded by default)
+	const int ncolA = ksw_ncol(P.max_contig_len, (int)max_ref, P.a_bw), ncolB = ksw_ncol(max_trim, std::max((int)max_ref, P.max_contig_len), P.b_bw);
+	const int wA = P.a_bw < 0 ? std::max(P.max_contig_len, (int)max_ref) : P.a_bw;
+	const size_t rowsA = std::min<size_t>((size_t)P.max_contig_len + max_ref, 2 * (size_t)max_ref + wA + 2);
+	const size_t rowsB = (size_t)max_trim + std::max<size_t>(max_ref, 1536);
+	const size_t p_cap = round_up(std::max(rowsA * ncolA, rowsB * ncolB) + 2 * KSW_PMAT_PAD + 64, 256);
+	const size_t n_groups = (size_t)ctx->dp_ctas * DP_WARPS * DP_NG;
+	const int seq_spill_cap = (int)round_up(ksw_seq_bytes(std::max(P.max_contig_len, max_trim), std::max((int)max_ref, P.max_contig_len)), 16);
+	CK(L.pmat.ensure(n_groups * p_cap));
+	CK(L.cig_scratch.ensure(n_groups * (size_t)ctx->cig_cap * 4));
+	CK(L.seq_spill.ensure(n_groups * (size_t)seq_spill_cap));
 	CK(cudaMemsetAsync(L.cnt.p, 0, sizeof(DevCounters), L.stream));
+	CK(cudaMemsetAsync(L.sort_misc.p, 0, 6 * SORT_BUCKETS * sizeof(unsigned), L.stream));
 	L.launches = 0;
+	SortBufs sA, sB;
+	sA.hist = (unsigned*)L.sort_misc.p; sA.start = sA.hist + SORT_BUCKETS; sA.cursor = sA.start + SORT_BUCKETS; sA.keys = (uint8_t*)L.keysA.p; sA.order = (unsigned*)L.orderA.p;
+	sB.hist = sA.cursor + SORT_BUCKETS; sB.start = sB.hist + SORT_BUCKETS; sB.cursor = sB.start + SORT_BUCKETS; sB.keys = (uint8_t*)L.keysB.p; sB.order = (unsigned*)L.orderB.p;
 
 	AsmArgs a; memset(&a, 0, sizeof a);
 	a.region = (const idl_region*)L.region.p; a.read = (const idl_read*)L.read.p;
@@ -300,6 +315,7 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 	a.ctg_ascii = (char*)L.ctg_ascii.p; a.ctg_codes = (uint8_t*)L.ctg_codes.p; a.ctg_sup = (P.out_flags & IDL_OUT_SUPPORT) ? (uint32_t*)L.ctg_sup.p : nullptr;
 	a.refcodes = (uint8_t*)L.refcodes.p;
 	a.cap_contigs = L.cap_contigs; a.cap_bases = L.cap_bases; a.cap_alns = L.cap_alns;
+	a.sortA = sA;
 	a.cnt = (DevCounters*)L.cnt.p;
 	if (b->n_regions > 0 && (P.stages & IDL_STAGE_ASSEMBLE)) {
 		assemble_kernel<<<asm_ctas, ASM_THREADS, asm_smem_bytes(ctx->ns, ctx->nw), L.stream>>>(a);
@@ -310,28 +326,38 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 	GenoArgs g; memset(&g, 0, sizeof g);
 	g.region = a.region; g.read = a.read; g.seq2 = a.seq2; g.seqn = a.seqn; g.refcodes = a.refcodes; g.ctg_codes = a.ctg_codes;
 	g.rres = a.rres; g.cres = a.cres; g.ares = a.ares; g.eres = (idl_event_result*)L.eres.p; g.cigar = (uint32_t*)L.cigar.p;
-	g.cap_events = L.cap_events; g.cap_cigar = L.cap_cigar; g.cap_al = L.cap_events; g.cap_alns = L.cap_alns; g.al_list = (AlEntry*)L.al_list.p;
+	g.cap_events = L.cap_events; g.cap_cigar = L.cap_cigar; g.cap_al = L.cap_events; g.cap_alns = L.cap_alns; g.cap_items = L.cap_items;
+	g.al_list = (AlEntry*)L.al_list.p; g.al_items = (AlItem*)L.al_items.p; g.al_res = (int8_t*)L.al_res.p;
+	g.sortA = sA; g.sortB = sB;
 	g.P = P; g.cnt = a.cnt;
-	g.pmat = (uint8_t*)L.pmat.p; g.p_cap = ctx->p_cap; g.cig_scratch = (uint32_t*)L.cig_scratch.p; g.cig_cap = ctx->cig_cap;
-	g.spill = (int8_t*)L.spill.p; g.spill_tcap = ctx->spill_tcap; g.spill_bytes = spill_bytes;
-	g.t_cap = (int)std::min<size_t>(round_up(max_ref, 16), 2048);
+	g.pmat = (uint8_t*)L.pmat.p; g.p_cap = p_cap; g.cig_scratch = (uint32_t*)L.cig_scratch.p; g.cig_cap = ctx->cig_cap;
+	g.seq_spill = (uint8_t*)L.seq_spill.p; g.seq_spill_cap = seq_spill_cap;
+	const size_t smem_limit = 200 * 1024;
 	if (b->n_regions > 0 && (P.stages & IDL_STAGE_ALIGN)) {
-		g.hr = next_pow2(std::max(P.a_bw < 0 ? P.max_contig_len : P.a_bw + 1, 1) + 8); g.qcap = 0;
-		g.seq_cap = (int)ksw_seq_bytes(1024, g.t_cap); // contigs up to 1 kb stage in shared memory, longer ones in the spill area
-		const size_t smem = DP_WARPS * dp_smem_per_warp(g.t_cap, g.hr, g.qcap, g.seq_cap);
+		g.ring_cols = ksw_ring_cols(ncolA); g.hr = ksw_h_ring(ncolA);
+		g.seq_cap = (int)round_up(ksw_seq_bytes(std::min(P.max_contig_len, 1024), (int)max_ref), 16); // longer contigs stage in the spill area
+		const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(g.ring_cols, g.hr, g.seq_cap);
+		if (smem > smem_limit) return IDL_E_CAPACITY;
+		sort_scan_kernel<<<1, SORT_BUCKETS, 0, L.stream>>>(sA);
+		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(sA, &a.cnt->n_alns, 1u, L.cap_alns);
 		align_kernel<<<ctx->dp_ctas, DP_THREADS, smem, L.stream>>>(g);
-		CK(cudaGetLastError()); L.launches++;
+		CK(cudaGetLastError()); L.launches += 3;
 	}
 	CK(cudaEventRecord(L.ev[EV_ALN], L.stream));
 	if (b->n_regions > 0 && (P.stages & IDL_STAGE_GENOTYPE) && (P.stages & IDL_STAGE_ALIGN)) {
 		kmer_kernel<<<ctx->n_sm * 8, KMER_THREADS, 0, L.stream>>>(g);
 		CK(cudaGetLastError()); L.launches++;
 		CK(cudaEventRecord(L.ev[EV_KMER], L.stream));
-		g.hr = next_pow2((P.b_bw < 0 ? max_trim : std::min(max_trim, P.b_bw + 1)) + 8); g.qcap = (int)round_up((size_t)max_trim, 16);
-		g.seq_cap = (int)ksw_seq_bytes(max_trim, g.t_cap);
-		const size_t smem = DP_WARPS * dp_smem_per_warp(g.t_cap, g.hr, g.qcap, g.seq_cap);
+		g.ring_cols = ksw_ring_cols(ncolB); g.hr = ksw_h_ring(ncolB);
+		g.seq_cap = (int)round_up(ksw_seq_bytes(max_trim, (int)max_ref), 16);
+		const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(g.ring_cols, g.hr, g.seq_cap);
+		if (smem > smem_limit) return IDL_E_CAPACITY;
+		al_prep_kernel<<<ctx->n_sm * 8, 256, 0, L.stream>>>(g);
+		sort_scan_kernel<<<1, SORT_BUCKETS, 0, L.stream>>>(sB);
+		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(sB, &a.cnt->n_al_items, 2u, 2 * L.cap_items);
 		al_kernel<<<ctx->dp_ctas, DP_THREADS, smem, L.stream>>>(g);
-		CK(cudaGetLastError()); L.launches++;
+		al_vote_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(g);
+		CK(cudaGetLastError()); L.launches += 5;
 	} else CK(cudaEventRecord(L.ev[EV_KMER], L.stream));
 	CK(cudaEventRecord(L.ev[EV_AL], L.stream));
 	CK(L.h_cnt.ensure(sizeof(DevCounters)));
@@ -485,39 +511,46 @@ struct KswBatchArgs {
 	unsigned n; const uint8_t *query, *target; const unsigned long long *q_off, *t_off;
 	KswParams kp; idl_ez *out; uint32_t *cigar; unsigned long long *cigar_off; unsigned cigar_cap;
 	unsigned *next; unsigned *cig_used;
-	uint8_t *pmat; size_t p_cap; uint32_t *cig_scratch; int cig_cap; int t_cap, hr, seq_cap;
+	uint8_t *pmat; size_t p_cap; uint32_t *cig_scratch; int cig_cap; int ring_cols, hr, seq_cap;
 };
 
-__global__ void __launch_bounds__(DP_THREADS, 3) ksw2_batch_kernel(KswBatchArgs a)
+template <int W>
+__global__ void __launch_bounds__(DP_THREADS, 2) ksw2_batch_kernel(KswBatchArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const int lane = lane_id();
-	const size_t per = ((ksw_lane_bytes(a.t_cap) + 15) & ~(size_t)15) + (size_t)a.hr * 4 + KSW_BTILE_BYTES + (size_t)a.seq_cap;
-	int8_t *lanes = (int8_t*)(smem_raw + per * warp_id());
-	int *H = (int*)(smem_raw + per * warp_id() + ((ksw_lane_bytes(a.t_cap) + 15) & ~(size_t)15));
-	uint8_t *btile = (uint8_t*)(H + a.hr);
-	uint8_t *seq = btile + KSW_BTILE_BYTES;
-	const size_t gw = (size_t)blockIdx.x * DP_WARPS + warp_id();
-	uint8_t *pmat = a.pmat + gw * a.p_cap;
-	uint32_t *cig = a.cig_scratch + gw * (size_t)a.cig_cap;
+	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;
+	const int cg = warp_id() * DP_NG + grp;
+	const size_t per = ksw_group_smem(a.ring_cols, a.hr, a.seq_cap);
+	const size_t gg = (size_t)blockIdx.x * (DP_WARPS * DP_NG) + cg;
+	KswMem M;
+	M.lanes = (int8_t*)(smem_raw + per * cg); M.ring_cols = a.ring_cols;
+	M.H = (int*)(smem_raw + per * cg + 5 * a.ring_cols); M.hr = a.hr;
+	M.seq = smem_raw + per * cg + 5 * a.ring_cols + a.hr * 4; M.seq_cap = a.seq_cap;
+	M.pmat = a.pmat + gg * a.p_cap; M.p_cap = a.p_cap;
+	M.cig = a.cig_scratch + gg * (size_t)a.cig_cap; M.cig_cap = a.cig_cap;
 	for (;;) {
-		unsigned i = 0;
-		if (lane == 0) i = atomicAdd(a.next, 1u);
-		i = __shfl_sync(FULL_MASK, i, 0);
-		if (i >= a.n) break;
-		const int qlen = (int)(a.q_off[i + 1] - a.q_off[i]), tlen = (int)(a.t_off[i + 1] - a.t_off[i]);
-		KswOut o;
-		ksw2_warp(qlen, a.query + a.q_off[i], tlen, a.target + a.t_off[i], a.kp, lanes, a.t_cap, seq, H, a.hr, btile, pmat, a.p_cap, cig, a.cig_cap, o);
-		unsigned coff = 0;
-		if (lane == 0) coff = atomicAdd(a.cig_used, (unsigned)o.n_cigar);
-		coff = __shfl_sync(FULL_MASK, coff, 0);
-		int status = o.status;
-		if (coff + (unsigned)o.n_cigar > a.cigar_cap) status = KSW_ST_CIGCAP;
-		else for (int k = lane; k < o.n_cigar; k += 32) a.cigar[coff + k] = cig[o.n_cigar - 1 - k];
-		if (lane == 0) {
-			idl_ez e; e.max = o.max; e.zdropped = o.zdropped; e.max_q = o.max_q; e.max_t = o.max_t; e.mqe = o.mqe; e.mqe_t = o.mqe_t; e.mte = o.mte;
-			e.mte_q = o.mte_q; e.score = o.score; e.n_cigar = o.n_cigar; e.status = status; e.reserved = 0; e.cells = o.cells;
-			a.out[i] = e; a.cigar_off[i] = coff;
+		unsigned base = 0;
+		if (lane == 0) base = atomicAdd(a.next, (unsigned)DP_NG);
+		base = __shfl_sync(FULL_MASK, base, 0);
+		if (base >= a.n) break;
+		const unsigned i = base + grp;
+		if (i < a.n) {
+			const int qlen = (int)(a.q_off[i + 1] - a.q_off[i]), tlen = (int)(a.t_off[i + 1] - a.t_off[i]);
+			KswQuery kq; kq.codes = a.query + a.q_off[i]; kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
+			KswOut o;
+			ksw2_group<DP_G, W>(qlen, kq, tlen, a.target + a.t_off[i], a.kp, M, o);
+			const unsigned gmask = ((1u << DP_G) - 1u) << (lane & ~(DP_G - 1));
+			unsigned coff = 0;
+			if (gl == 0) coff = atomicAdd(a.cig_used, (unsigned)o.n_cigar);
+			coff = __shfl_sync(gmask, coff, 0, DP_G);
+			int status = o.status;
+			if (coff + (unsigned)o.n_cigar > a.cigar_cap) status = KSW_ST_CIGCAP;
+			else for (int k = gl; k < o.n_cigar; k += DP_G) a.cigar[coff + k] = M.cig[o.n_cigar - 1 - k];
+			if (gl == 0) {
+				idl_ez e; e.max = o.max; e.zdropped = o.zdropped; e.max_q = o.max_q; e.max_t = o.max_t; e.mqe = o.mqe; e.mqe_t = o.mqe_t; e.mte = o.mte;
+				e.mte_q = o.mte_q; e.score = o.score; e.n_cigar = o.n_cigar; e.status = status; e.reserved = 0; e.cells = o.cells;
+				a.out[i] = e; a.cigar_off[i] = coff;
+			}
 		}
 		__syncwarp();
 	}
@@ -533,26 +566,27 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 	if (n == 0) return IDL_OK;
 	if (n >= (1ull << 31) || cigar_cap >= (1ull << 32)) return IDL_E_ARG;
 	cudaSetDevice(ctx->device);
-	int max_q = 1, max_t = 1; size_t max_p = 0;
+	int max_q = 1, max_t = 1, max_ncol = 32; size_t max_p = 0;
 	for (size_t i = 0; i < n; ++i) {
 		const int ql = (int)(q_off[i + 1] - q_off[i]), tl = (int)(t_off[i + 1] - t_off[i]);
 		max_q = std::max(max_q, ql); max_t = std::max(max_t, tl);
-		const int ww = w < 0 ? std::max(ql, tl) : w;
-		const int band = std::min(std::min(ql, tl), ww + 1);
-		max_p = std::max(max_p, (size_t)std::max(ql + tl - 1, 0) * (size_t)(((band + 15) / 16 + 1) * 16));
+		const int nc = ksw_ncol(std::max(ql, 1), std::max(tl, 1), w);
+		max_ncol = std::max(max_ncol, nc);
+		max_p = std::max(max_p, (size_t)std::max(ql + tl - 1, 0) * (size_t)nc);
 	}
-	const int band_all = std::min(std::min(max_q, max_t), (w < 0 ? std::max(max_q, max_t) : w) + 1);
 	KswBatchArgs a; memset(&a, 0, sizeof a);
 	a.n = (unsigned)n; a.kp.match = match; a.kp.mismatch = mismatch; a.kp.q = gapo; a.kp.e = gape; a.kp.w = w; a.kp.zdrop = zdrop;
-	a.t_cap = (int)round_up((size_t)max_t, 16); a.hr = next_pow2(band_all + 8);
-	a.p_cap = round_up(max_p + 2 * KSW_PMAT_PAD + 16, 256); a.cig_cap = max_q + max_t + 8; a.cigar_cap = (unsigned)cigar_cap;
-	a.seq_cap = (int)((ksw_seq_bytes(max_q, a.t_cap) + 15) & ~(size_t)15);
-	const size_t per = ((ksw_lane_bytes(a.t_cap) + 15) & ~(size_t)15) + (size_t)a.hr * 4 + KSW_BTILE_BYTES + (size_t)a.seq_cap;
-	const size_t smem = per * DP_WARPS;
+	a.ring_cols = ksw_ring_cols(max_ncol); a.hr = ksw_h_ring(max_ncol);
+	a.p_cap = round_up(max_p + 2 * KSW_PMAT_PAD + 64, 256); a.cig_cap = max_q + max_t + 8; a.cigar_cap = (unsigned)cigar_cap;
+	a.seq_cap = (int)round_up(ksw_seq_bytes(max_q, max_t), 16);
+	const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(a.ring_cols, a.hr, a.seq_cap);
 	if (smem > 200 * 1024) return IDL_E_CAPACITY;
-	cudaFuncSetAttribute(ksw2_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-	const int ctas = (int)std::min<size_t>((n + DP_WARPS - 1) / DP_WARPS, (size_t)ctx->n_sm * 2);
-	const size_t nwarps = (size_t)ctas * DP_WARPS;
+	const bool narrow = max_ncol <= DP_G * DP_W_A * 4 - 16;
+	if (narrow) cudaFuncSetAttribute(ksw2_batch_kernel<DP_W_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	else cudaFuncSetAttribute(ksw2_batch_kernel<DP_W_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	const size_t per_cta = (size_t)DP_WARPS * DP_NG;
+	const int ctas = (int)std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)ctx->n_sm * 2);
+	const size_t nwarps = (size_t)ctas * per_cta; // groups, each with its own workspace
 	const size_t qbytes = q_off[n], tbytes = t_off[n];
 	DevBuf dq, dt, dqo, dto, dout, dcig, dcoff, dmisc, dp, dscr;
 	cudaStream_t st = ctx->lanes[0].stream;
@@ -570,7 +604,8 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 		a.next = (unsigned*)dmisc.p; a.cig_used = (unsigned*)dmisc.p + 1; a.pmat = (uint8_t*)dp.p; a.cig_scratch = (uint32_t*)dscr.p;
 		CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 		CK(cudaEventRecord(e0, st));
-		ksw2_batch_kernel<<<ctas, DP_THREADS, smem, st>>>(a);
+		if (narrow) ksw2_batch_kernel<DP_W_A><<<ctas, DP_THREADS, smem, st>>>(a);
+		else ksw2_batch_kernel<DP_W_B><<<ctas, DP_THREADS, smem, st>>>(a);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(e1, st));
 		CK(cudaMemcpyAsync(out, dout.p, n * sizeof(idl_ez), cudaMemcpyDeviceToHost, st));

@@ -64,16 +64,16 @@ __global__ void sort_scatter_kernel(SortBufs s, const unsigned *n_ptr, unsigned 
 }
 
 // shared/global memory of the group this thread belongs to
-__device__ __forceinline__ KswMem dp_mem(const GenoArgs &g, unsigned char *smem, int qlen, int tlen)
+__device__ __forceinline__ KswMem dp_mem(const GenoArgs &g, unsigned char *smem, int qlen, int tlen, int W)
 {
 	const int grp = warp_id() * DP_NG + (lane_id() / DP_G);
 	const size_t per = ksw_group_smem(g.ring_cols, g.hr, g.seq_cap);
 	unsigned char *base = smem + per * grp;
 	const size_t gg = (size_t)blockIdx.x * (DP_WARPS * DP_NG) + grp;
 	KswMem m;
-	m.lanes = (int8_t*)base; m.ring_cols = g.ring_cols;
-	m.H = (int*)(base + 5 * g.ring_cols); m.hr = g.hr;
-	if (ksw_seq_bytes(qlen, tlen) <= (size_t)g.seq_cap) { m.seq = base + 5 * g.ring_cols + g.hr * 4; m.seq_cap = g.seq_cap; }
+	m.lanes = (int8_t*)(base + ksw_group_stagger(lane_id() / DP_G, W)); m.ring_cols = g.ring_cols;
+	m.H = (int*)(base + ksw_group_h_off(g.ring_cols)); m.hr = g.hr;
+	if (ksw_seq_bytes(qlen, tlen) <= (size_t)g.seq_cap) { m.seq = base + ksw_group_h_off(g.ring_cols) + g.hr * 4; m.seq_cap = g.seq_cap; }
 	else { m.seq = g.seq_spill + gg * (size_t)g.seq_spill_cap; m.seq_cap = g.seq_spill_cap; }
 	m.pmat = g.pmat + gg * g.p_cap; m.p_cap = g.p_cap;
 	m.cig = g.cig_scratch + gg * (size_t)g.cig_cap; m.cig_cap = g.cig_cap;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(DP_THREADS, 2) align_kernel(GenoArgs g)
 			const uint8_t *tq = g.refcodes + R.ref_off + (cr.start - R.ref_start);
 			const uint8_t *qq = g.ctg_codes + cr.seq_off;
 			KswQuery kq; kq.codes = qq; kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
-			const KswMem M = dp_mem(g, smem_raw, cr.len, tlen);
+			const KswMem M = dp_mem(g, smem_raw, cr.len, tlen, DP_W_A);
 			KswOut o;
 			ksw2_group<DP_G, DP_W_A>(cr.len, kq, tlen, tq, kp, M, o);
 			const uint32_t *cg = M.cig;
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(DP_THREADS, 2) al_kernel(GenoArgs g)
 			if (!(task & 1)) { t = g.refcodes + R.ref_off + (cr.start - R.ref_start) + it.start; tlen = ar.ref_len - it.start; } // ref_sub :340
 			else { t = g.ctg_codes + cr.seq_off + it.start; tlen = cr.len - it.start; }                                          // ctg_sub :341
 			if (tlen < 0) tlen = 0;
-			const KswMem M = dp_mem(g, smem_raw, qlen, tlen);
+			const KswMem M = dp_mem(g, smem_raw, qlen, tlen, DP_W_B);
 			KswOut o;
 			ksw2_group<DP_G, DP_W_B>(qlen, kq, tlen, t, kp, M, o);
 			if (gl == 0) {

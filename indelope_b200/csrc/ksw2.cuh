@@ -81,6 +81,9 @@ __device__ __forceinline__ uint32_t msb_to_mask4(uint32_t v)
 	return r;
 }
 
+// tie order of the SSE arg-max (:316-348): 4 strided accumulators (lower accumulator, then lower t), then the scalar tail
+__device__ __forceinline__ unsigned ksw_tie_rank(int t, int st0, int en1) { return 1u + ((t < en1 ? (unsigned)((t - st0) & 3) : 4u) << 20) + (unsigned)(t - st0); }
+
 // where the query of an alignment comes from: 0..4 codes, or a 2-bit packed read (+ non-ACGT plane) of the batch
 struct KswQuery { const uint8_t *codes; const uint32_t *seq2, *seqn; unsigned base; };
 __device__ __forceinline__ uint8_t ksw_query_code(const KswQuery &q, int i)
@@ -93,7 +96,16 @@ __device__ __forceinline__ uint8_t ksw_query_code(const KswQuery &q, int i)
 // Memory of one group: lanes = 5 rings of ring_cols bytes, H = hr ints, seq = seq_cap bytes (reused as the backtrack
 // tile) in shared memory; pmat = backtrack matrix workspace, cig = CIGAR scratch in global memory
 struct KswMem { int8_t *lanes; int ring_cols; int *H; int hr; uint8_t *seq; int seq_cap; uint8_t *pmat; size_t p_cap; uint32_t *cig; int cig_cap; };
-__host__ __device__ inline size_t ksw_group_smem(int ring_cols, int hr, int seq_cap) { return (size_t)5 * ring_cols + (size_t)hr * 4 + (size_t)((seq_cap + 15) & ~15); }
+__host__ __device__ inline size_t ksw_group_smem(int ring_cols, int hr, int seq_cap)
+{
+	return ((size_t)5 * ring_cols + 128 + (size_t)hr * 4 + (size_t)((seq_cap + 15) & ~15) + 127) & ~(size_t)127;
+}
+// layout of a group's region (a multiple of 128 bytes): [lanes: 5 rings + 128 bytes of stagger slack][H][seq]
+__host__ __device__ inline size_t ksw_group_h_off(int ring_cols) { return (size_t)5 * ring_cols + 128; }
+// Bank staggering: the G threads of a group touch words W apart, the 32/G groups of a warp touch the same relative word.
+// These byte offsets (added to the lane rings only; H and seq keep their 16-byte alignment) make the 32 words of one
+// access fall into 32 different banks for W = 3 (stride 8 words) and W = 6 (0, 1, 16, 17 words).
+__host__ __device__ inline int ksw_group_stagger(int grp_in_warp, int W) { return W == 6 ? 4 * ((grp_in_warp & 1) + 16 * (grp_in_warp >> 1)) : 32 * grp_in_warp; }
 
 // The G threads of a group call this with identical arguments; `out` comes back identical in each of them.
 template <int G, int W>
@@ -125,17 +137,19 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 	uint32_t *U = (uint32_t*)u, *V = (uint32_t*)v, *X = (uint32_t*)x, *Y = (uint32_t*)y, *S = (uint32_t*)s;
 	uint8_t *sf = M.seq, *qr = M.seq + T16 + 16;
 	const uint32_t *SF = (const uint32_t*)sf, *QR = (const uint32_t*)qr;
-	const uint32_t QE2 = rep4(qe * 2), MAXSC = rep4(P.match + qe * 2), Q4 = rep4(P.q), MAT4 = rep4(P.match), MIS4 = rep4(P.mismatch);
+	const uint32_t QE2 = rep4(qe * 2), MAXSC = rep4(P.match + qe * 2), Q4 = rep4(P.q), MATQ = rep4(P.match + qe * 2), MISQ = rep4(P.mismatch + qe * 2);
 
 	// calloc :173: columns [0,16) of u,v,x,y and [0,32) of s start as zero (later blocks are cleared as they enter);
 	// stage sf (target, zero padded) and qr (reversed query, zero padded) exactly as :187-188 lay them out
 	for (int i = gl; i < 16 / 4; i += G) { U[i] = 0; V[i] = 0; X[i] = 0; Y[i] = 0; }
-	for (int i = gl; i < 32 / 4; i += G) S[i] = 0;
-	for (int i = gl; i < T16 + 16; i += G) sf[i] = i < tlen ? target[i] : (uint8_t)0;
+	for (int i = gl; i < 32 / 4; i += G) S[i] = QE2; // S holds s + 2(q+e) (:117): one add less per word and diagonal
+	bool wild = false; // a code 4 anywhere: only then the score needs the wildcard mask (:219,226)
+	for (int i = gl; i < T16 + 16; i += G) { const uint8_t c = i < tlen ? target[i] : (uint8_t)0; wild |= c == 4; sf[i] = c; }
 	{
 		const int nq = (qlen + 35) & ~3;
-		for (int i = gl; i < nq; i += G) qr[i] = i < qlen ? ksw_query_code(query, qlen - 1 - i) : (uint8_t)0;
+		for (int i = gl; i < nq; i += G) { const uint8_t c = i < qlen ? ksw_query_code(query, qlen - 1 - i) : (uint8_t)0; wild |= c == 4; qr[i] = c; }
 	}
+	wild = __ballot_sync(gmask, wild) & gmask;
 	__syncwarp(gmask);
 
 	int last_st = -1, last_en = -1, en_clr = 15;
@@ -149,7 +163,7 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 			const int b = en_clr + 1;
 			for (int i = gl; i < 8; i += G) {
 				if (i < 4) { const int wi = ((b >> 2) + i) & rmw; U[wi] = 0; V[wi] = 0; X[wi] = 0; Y[wi] = 0; }
-				else S[(((b + 16) >> 2) + i - 4) & rmw] = 0;
+				else S[(((b + 16) >> 2) + i - 4) & rmw] = QE2;
 			}
 			en_clr += 16;
 			__syncwarp(gmask);
@@ -168,7 +182,7 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 		const int hprev_old = r == 0 ? 0 : (en0 > 0 ? H[(en0 - 1) & hmask] : H[en0 & hmask]);
 		const unsigned bandw = (unsigned)(en0 - st0);       // columns st0 .. en0-1 are updated in the loop
 		uint32_t *pr = (uint32_t*)(pmat + (size_t)r * n_col) - (st >> 2);
-		int bh = (int)0x80000000, bt = 0; bool dup = false;  // this thread's best exact score, its column, and "seen twice"
+		int bh = (int)0x80000000, bt = st0;                  // this thread's best exact score and its column (ties in SSE order)
 		const int rword = en >= r ? (r >> 2) : -1;           // :212, y[r] = 0 and u[r] = q, patched in registers
 		for (int w0 = st >> 2; w0 <= wlast; w0 += G * W) {
 			const int wb = w0 + gl * W;
@@ -194,8 +208,8 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 					if (p >= 0) sq2 = __funnelshift_r(QR[p >> 2], QR[(p >> 2) + 1], 8 * (p & 3));
 					else sq2 = p > -4 ? QR[0] << (8 * -p) : 0u;
 					const uint32_t neq = msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu);                                  // 0xff where the codes differ
-					const uint32_t nowild = msb_to_mask4(((sq ^ 0x04040404u) + 0x7f7f7f7fu) & ((sq2 ^ 0x04040404u) + 0x7f7f7f7fu)); // 0xff unless a code is 4
-					const uint32_t sc = sel4(neq, MIS4, MAT4) & nowild;
+					uint32_t sc = sel4(neq, MISQ, MATQ);
+					if (wild) sc = sel4(msb_to_mask4(((sq ^ 0x04040404u) + 0x7f7f7f7fu) & ((sq2 ^ 0x04040404u) + 0x7f7f7f7fu)), sc, QE2); // score 0 where a code is 4
 					const int lo = st0 - t, hi = bend - t; // lanes [lo, hi) of this word belong to the blocks
 					uint32_t m = 0xffffffffu;
 					if (lo > 0) m &= 0xffffffffu << (8 * lo);
@@ -212,7 +226,7 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 					}
 					const uint32_t xt1 = __funnelshift_l(k ? xo[k ? k - 1 : 0] : xp, xo[k], 8); // lanes t-1..t+2 of the previous diagonal
 					const uint32_t vt1 = __funnelshift_l(k ? vo[k ? k - 1 : 0] : vp, vo[k], 8);
-					uint32_t z = __vadd4(so, QE2);
+					uint32_t z = so;                               // s + 2(q+e)
 					uint32_t a = __vadd4(xt1, vt1);
 					uint32_t b = __vadd4(yt, ut);
 					uint32_t m = __vcmpgts4(a, z);                 // a > z (signed)
@@ -240,10 +254,10 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 							const int tc = t + c;
 							const bool in = (unsigned)(tc - st0) < bandw;
 							const int h = hv[c] + (int)((vn >> (8 * c)) & 0xff) - qe;
-							const bool gt = in && h > bh, eq = in && h == bh;
+							const bool gt = in && h > bh;
+							if (in && h == bh && ksw_tie_rank(tc, st0, en1) < ksw_tie_rank(bt, st0, en1)) bt = tc; // rare
 							hv[c] = in ? h : hv[c];
 							bt = gt ? tc : bt;
-							dup = gt ? false : (eq ? true : dup);
 							bh = gt ? h : bh;
 						}
 						H4[(t & hmask) >> 2] = make_int4(hv[0], hv[1], hv[2], hv[3]);
@@ -261,21 +275,10 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 			const unsigned mk = __reduce_max_sync(gmask, (unsigned)bh ^ 0x80000000u);
 			const int mh = (int)(mk ^ 0x80000000u);
 			if (hen >= mh) { max_H = hen; max_t = en0; } // the initial candidate (H[en0], en0) wins every tie (:318-321)
-			else {
+			else { // several threads may hold the max: the SSE tie order decides
 				max_H = mh;
-				const bool mine = bh == mh;
-				const unsigned who = __ballot_sync(gmask, mine) & gmask, twice = __ballot_sync(gmask, mine && dup) & gmask;
-				if (__popc(who) == 1 && twice == 0) max_t = __shfl_sync(gmask, bt, (__ffs(who) - 1) & (G - 1), G);
-				else { // a tie between columns: the SSE order decides -- 4 strided accumulators (lower accumulator, then lower t), then the scalar tail
-					unsigned rk = 0xffffffffu;
-					for (int t = st0 + gl; t < en0; t += G)
-						if (H[t & hmask] == mh) {
-							const unsigned cand = 1u + ((t < en1 ? (unsigned)((t - st0) & 3) : 4u) << 20) + (unsigned)(t - st0);
-							rk = cand < rk ? cand : rk;
-						}
-					rk = __reduce_min_sync(gmask, rk);
-					max_t = st0 + (int)((rk - 1) & 0xfffffu);
-				}
+				const unsigned rk = __reduce_min_sync(gmask, bh == mh ? ksw_tie_rank(bt, st0, en1) : 0xffffffffu);
+				max_t = st0 + (int)((rk - 1) & 0xfffffu);
 			}
 		}
 		if (en0 == tlen - 1) {

@@ -523,9 +523,10 @@ __global__ void __launch_bounds__(DP_THREADS, 2) ksw2_batch_kernel(KswBatchArgs 
 	const size_t per = ksw_group_smem(a.ring_cols, a.hr, a.seq_cap);
 	const size_t gg = (size_t)blockIdx.x * (DP_WARPS * DP_NG) + cg;
 	KswMem M;
-	M.lanes = (int8_t*)(smem_raw + per * cg); M.ring_cols = a.ring_cols;
-	M.H = (int*)(smem_raw + per * cg + 5 * a.ring_cols); M.hr = a.hr;
-	M.seq = smem_raw + per * cg + 5 * a.ring_cols + a.hr * 4; M.seq_cap = a.seq_cap;
+	unsigned char *gbase = smem_raw + per * cg;
+	M.lanes = (int8_t*)(gbase + ksw_group_stagger(grp, W)); M.ring_cols = a.ring_cols;
+	M.H = (int*)(gbase + ksw_group_h_off(a.ring_cols)); M.hr = a.hr;
+	M.seq = gbase + ksw_group_h_off(a.ring_cols) + a.hr * 4; M.seq_cap = a.seq_cap;
 	M.pmat = a.pmat + gg * a.p_cap; M.p_cap = a.p_cap;
 	M.cig = a.cig_scratch + gg * (size_t)a.cig_cap; M.cig_cap = a.cig_cap;
 	for (;;) {

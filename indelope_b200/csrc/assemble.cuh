@@ -18,8 +18,13 @@
 #pragma once
 #include "common.cuh"
 
-#define ASM_THREADS 256
-#define ASM_WARPS (ASM_THREADS / 32)
+#define ASM_THREADS 256        // threads per CTA of both variants
+#define ASM_SMALL_READS 126    // regions up to this many reads are assembled by ONE WARP (no block barriers); larger ones by a CTA
+#define ASM_SMALL_NS (ASM_SMALL_READS + 2)
+
+// NT = threads cooperating on one region: 32 (a warp: 8 regions per CTA, __syncwarp only) or 256 (the whole CTA).
+template <int NT> __device__ __forceinline__ void asm_bar() { if (NT == 32) __syncwarp(); else __syncthreads(); }
+template <int NT> __device__ __forceinline__ int asm_tid() { return NT == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
 
 struct AsmArgs {
 	// batch (device copies)
@@ -35,6 +40,7 @@ struct AsmArgs {
 	unsigned cap_contigs, cap_bases, cap_alns;
 	SortBufs sortA;
 	DevCounters *cnt;
+	int small;                        // 1: this launch takes the regions with <= ASM_SMALL_READS reads, 0: the others
 };
 
 struct AsmS { // carved out of dynamic shared memory
@@ -47,9 +53,10 @@ struct AsmS { // carved out of dynamic shared memory
 };
 enum { SC_NFREE = 0, SC_STATUS, SC_TMP0, SC_TMP1, SC_NCORR, SC_REGION, SC_HASN, SC_SLOT, SC_N };
 
-__host__ __device__ inline size_t asm_smem_bytes(int ns, int nw)
+// shared memory of one cooperating group (a warp or a CTA) for regions of up to ns-2 reads
+__host__ __device__ inline size_t asm_smem_bytes(int ns, int nw, int nt)
 {
-	size_t b = (size_t)3 * nw * 4 + (size_t)3 * ns * 4 + (size_t)3 * ns * 2 + (size_t)3 * IDL_MAX_CORRECTIONS * 4 + ASM_WARPS * 8 + SC_N * 4;
+	size_t b = (size_t)3 * nw * 4 + (size_t)3 * ns * 4 + (size_t)3 * ns * 2 + (size_t)3 * IDL_MAX_CORRECTIONS * 4 + (size_t)(nt / 32) * 8 + SC_N * 4 + 16;
 	return (b + 15) & ~(size_t)15;
 }
 
@@ -80,20 +87,20 @@ __device__ __forceinline__ uint32_t compress_even(uint64_t x) // bits 0,2,4,... 
 	return (uint32_t)x;
 }
 
-__device__ int asm_alloc(Asm &A) // uniform: every thread gets the same slot
+template <int NT> __device__ int asm_alloc(Asm &A) // uniform: every thread gets the same slot
 {
-	__syncthreads();
-	if (threadIdx.x == 0) {
+	asm_bar<NT>();
+	if (asm_tid<NT>() == 0) {
 		int n = A.s.sc[SC_NFREE];
 		if (n > 0) { A.s.sc[SC_SLOT] = A.s.freestk[n - 1]; A.s.sc[SC_NFREE] = n - 1; }
 		else { A.s.sc[SC_SLOT] = -1; A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; }
 	}
-	__syncthreads();
+	asm_bar<NT>();
 	return A.s.sc[SC_SLOT];
 }
-__device__ void asm_free(Asm &A, int slot) // call from uniform code; takes effect at the next barrier
+template <int NT> __device__ void asm_free(Asm &A, int slot) // call from uniform code; takes effect at the next barrier
 {
-	if (threadIdx.x == 0) { A.s.freestk[A.s.sc[SC_NFREE]] = (uint16_t)slot; A.s.sc[SC_NFREE] += 1; }
+	if (asm_tid<NT>() == 0) { A.s.freestk[A.s.sc[SC_NFREE]] = (uint16_t)slot; A.s.sc[SC_NFREE] += 1; }
 }
 
 // one (query, contig, offset) candidate: number of matching bases, or -1 if a mismatch is not allowed.
@@ -134,23 +141,23 @@ __device__ int asm_eval(const Asm &A, const uint32_t *t0, const uint32_t *t1, co
 struct AsmMatch { int k, offset, ma; bool aligned; };
 
 // best_match (:224-240) of slot q against list[0..nlist). Uniform result.
-__device__ AsmMatch asm_best_match(Asm &A, const uint16_t *list, int nlist, int q, int mo, bool has_n)
+template <int NT> __device__ AsmMatch asm_best_match(Asm &A, const uint16_t *list, int nlist, int q, int mo, bool has_n)
 {
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int tid = asm_tid<NT>(), lane = tid & 31, warp = tid >> 5;
 	const int qlen = A.s.len[q], qreads = A.s.nreads[q];
-	__syncthreads();
+	asm_bar<NT>();
 	{ // stage the query planes (+ zero padding up to nw words)
 		const int qw = (qlen + 31) >> 5;
 		const uint32_t *g0 = A.p0(q), *g1 = A.p1(q), *gn = A.pn(q);
-		for (int w = tid; w < A.nw; w += ASM_THREADS) {
+		for (int w = tid; w < A.nw; w += NT) {
 			const bool in = w < qw;
 			A.s.q0[w] = in ? g0[w] : 0u; A.s.q1[w] = in ? g1[w] : 0u; A.s.qn[w] = in ? gn[w] : 0u;
 		}
 	}
-	__syncthreads();
+	asm_bar<NT>();
 	const uint16_t *qsup = A.sup(q);
 	unsigned long long best = 0;
-	for (int k = warp; k < nlist; k += ASM_WARPS) {
+	for (int k = warp; k < nlist; k += (NT / 32)) {
 		const int t = list[k];
 		const int tlen = A.s.len[t], treads = A.s.nreads[t];
 		const int omax = tlen - mo;
@@ -178,9 +185,9 @@ __device__ AsmMatch asm_best_match(Asm &A, const uint16_t *list, int nlist, int 
 		if (lane == 0) A.offsets += (unsigned long long)(n1 + n2);
 	}
 	if (lane == 0) A.s.best[warp] = best;
-	__syncthreads();
+	asm_bar<NT>();
 	best = 0;
-	for (int w2 = 0; w2 < ASM_WARPS; ++w2) { const unsigned long long b = A.s.best[w2]; best = b > best ? b : best; }
+	for (int w2 = 0; w2 < (NT / 32); ++w2) { const unsigned long long b = A.s.best[w2]; best = b > best ? b : best; }
 	AsmMatch m;
 	m.aligned = best != 0;
 	m.ma = (int)(best >> 32) - 1;
@@ -197,15 +204,15 @@ __device__ AsmMatch asm_best_match(Asm &A, const uint16_t *list, int nlist, int 
 }
 
 // Contig.insert (:156-222): merge slot q into list[k] at m.offset. Returns the slot that now holds the merged contig.
-__device__ void asm_merge(Asm &A, uint16_t *list, int k, int q, int offset, bool has_n)
+template <int NT> __device__ void asm_merge(Asm &A, uint16_t *list, int k, int q, int offset, bool has_n)
 {
-	const int tid = threadIdx.x;
+	const int tid = asm_tid<NT>();
 	const int t = list[k];
 	const int tlen = A.s.len[t], qlen = A.s.len[q], treads = A.s.nreads[t], qreads = A.s.nreads[q];
 	uint16_t *tsup = A.sup(t), *qsup = A.sup(q);
 	uint32_t *tp[3] = {A.p0(t), A.p1(t), A.pn(t)}, *qp[3] = {A.p0(q), A.p1(q), A.pn(q)};
 	const bool vote = qreads >= 4 && treads >= 4;
-	__syncthreads();
+	asm_bar<NT>();
 	// 1. corrections of the winning offset, in position order (:93-99), then applied (:161-173)
 	if (tid == 0) {
 		int nc = 0;
@@ -241,13 +248,13 @@ __device__ void asm_merge(Asm &A, uint16_t *list, int k, int q, int offset, bool
 		}
 		A.s.sc[SC_NCORR] = nc;
 	}
-	__syncthreads();
+	asm_bar<NT>();
 	const int nc = A.s.sc[SC_NCORR];
 	if (offset < 0) { // :180-205, built in q's slot (q frame)
 		const int ao = -offset;
 		const int newlen = max(qlen, ao + tlen);
-		if (newlen > A.cap) { if (tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; __syncthreads(); return; }
-		for (int i = ao + tid; i < ao + tlen; i += ASM_THREADS) {
+		if (newlen > A.cap) { if (tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; asm_bar<NT>(); return; }
+		for (int i = ao + tid; i < ao + tlen; i += NT) {
 			unsigned val = tsup[i - ao];
 			if (i < qlen) {
 				bool dont = false;
@@ -257,7 +264,7 @@ __device__ void asm_merge(Asm &A, uint16_t *list, int k, int q, int offset, bool
 			qsup[i] = (uint16_t)val;
 		}
 		if (ao + tlen > qlen) { // append the target's tail: bases [qlen, ao+tlen) come from t[i-ao]
-			for (int w = (qlen >> 5) + tid; w * 32 < newlen; w += ASM_THREADS) {
+			for (int w = (qlen >> 5) + tid; w * 32 < newlen; w += NT) {
 				const uint32_t low = qlen - 32 * w >= 32 ? 0xffffffffu : (qlen > 32 * w ? (1u << (qlen - 32 * w)) - 1u : 0u);
 				for (int pl = 0; pl < 3; ++pl) {
 					if (pl == 2 && !has_n) { qp[2][w] = 0; continue; }
@@ -266,17 +273,17 @@ __device__ void asm_merge(Asm &A, uint16_t *list, int k, int q, int offset, bool
 				}
 			}
 		}
-		__syncthreads();
+		asm_bar<NT>();
 		if (tid == 0) {
 			A.s.len[q] = newlen; A.s.nreads[q] = treads + qreads; // start stays q.start (:204)
 			list[k] = (uint16_t)q;
 		}
-		asm_free(A, t);
+		asm_free<NT>(A, t);
 	} else { // :210-222, in t's slot
 		const int o = offset;
 		const int newlen = max(tlen, o + qlen);
-		if (newlen > A.cap) { if (tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; __syncthreads(); return; }
-		for (int i = o + tid; i < o + qlen; i += ASM_THREADS) {
+		if (newlen > A.cap) { if (tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; asm_bar<NT>(); return; }
+		for (int i = o + tid; i < o + qlen; i += NT) {
 			if (i < tlen) {
 				bool dont = false;
 				for (int c = 0; c < nc; ++c) dont |= A.s.corr[3 * c + 1] == i; // toff (:172-173)
@@ -284,7 +291,7 @@ __device__ void asm_merge(Asm &A, uint16_t *list, int k, int q, int offset, bool
 			} else tsup[i] = qsup[i - o];
 		}
 		if (o + qlen > tlen) {
-			for (int w = (tlen >> 5) + tid; w * 32 < newlen; w += ASM_THREADS) {
+			for (int w = (tlen >> 5) + tid; w * 32 < newlen; w += NT) {
 				const uint32_t low = tlen - 32 * w >= 32 ? 0xffffffffu : (tlen > 32 * w ? (1u << (tlen - 32 * w)) - 1u : 0u);
 				for (int pl = 0; pl < 3; ++pl) {
 					if (pl == 2 && !has_n) { tp[2][w] = 0; continue; }
@@ -293,140 +300,144 @@ __device__ void asm_merge(Asm &A, uint16_t *list, int k, int q, int offset, bool
 				}
 			}
 		}
-		__syncthreads();
+		asm_bar<NT>();
 		if (tid == 0) { A.s.len[t] = newlen; A.s.nreads[t] = treads + qreads; }
-		asm_free(A, q);
+		asm_free<NT>(A, q);
 	}
-	__syncthreads();
+	asm_bar<NT>();
 }
 
 // Contig.trim (:49-68). Returns the slot holding the trimmed contig (a fresh one if bases were dropped on the left).
-__device__ int asm_trim(Asm &A, int c, int min_support, bool has_n)
+template <int NT> __device__ int asm_trim(Asm &A, int c, int min_support, bool has_n)
 {
-	const int tid = threadIdx.x;
+	const int tid = asm_tid<NT>();
 	const int L = A.s.len[c];
 	const unsigned ms = (unsigned)min_support;
 	const uint16_t *sp = A.sup(c);
-	__syncthreads();
+	asm_bar<NT>();
 	if (tid == 0) { A.s.sc[SC_TMP0] = 0x7fffffff; A.s.sc[SC_TMP1] = -1; }
-	__syncthreads();
-	for (int i = tid; i < L - 1; i += ASM_THREADS) if (sp[i] >= ms) { atomicMin(&A.s.sc[SC_TMP0], i); break; }
-	__syncthreads();
+	asm_bar<NT>();
+	for (int i = tid; i < L - 1; i += NT) if (sp[i] >= ms) { atomicMin(&A.s.sc[SC_TMP0], i); break; }
+	asm_bar<NT>();
 	int a = A.s.sc[SC_TMP0];
 	if (a > L - 1) a = L - 1 > 0 ? L - 1 : 0;
 	if (a >= L - 1) { // :56-60
-		__syncthreads();
+		asm_bar<NT>();
 		if (tid == 0) { A.s.start[c] += a; A.s.len[c] = 0; A.s.nreads[c] = 0; }
-		__syncthreads();
+		asm_bar<NT>();
 		return c;
 	}
-	for (int i = L - 1 - tid; i > a; i -= ASM_THREADS) if (sp[i] >= ms) { atomicMax(&A.s.sc[SC_TMP1], i); break; }
-	__syncthreads();
+	for (int i = L - 1 - tid; i > a; i -= NT) if (sp[i] >= ms) { atomicMax(&A.s.sc[SC_TMP1], i); break; }
+	asm_bar<NT>();
 	int b = A.s.sc[SC_TMP1];
 	if (b < a) b = a;
 	const int newlen = b - a + 1;
 	if (a == 0) {
-		__syncthreads();
+		asm_bar<NT>();
 		if (tid == 0) A.s.len[c] = newlen;
-		__syncthreads();
+		asm_bar<NT>();
 		return c;
 	}
-	const int d = asm_alloc(A);
+	const int d = asm_alloc<NT>(A);
 	if (d < 0) return c;
 	const uint32_t *s0 = A.p0(c), *s1 = A.p1(c), *sn = A.pn(c);
 	uint32_t *d0 = A.p0(d), *d1 = A.p1(d), *dn = A.pn(d);
 	uint16_t *dsup = A.sup(d);
-	for (int w = tid; w * 32 < newlen; w += ASM_THREADS) {
+	for (int w = tid; w * 32 < newlen; w += NT) {
 		d0[w] = get32(s0, a + 32 * w); d1[w] = get32(s1, a + 32 * w); dn[w] = has_n ? get32(sn, a + 32 * w) : 0u;
 	}
-	for (int i = tid; i < newlen; i += ASM_THREADS) dsup[i] = sp[a + i];
-	__syncthreads();
+	for (int i = tid; i < newlen; i += NT) dsup[i] = sp[a + i];
+	asm_bar<NT>();
 	if (tid == 0) { A.s.len[d] = newlen; A.s.nreads[d] = A.s.nreads[c]; A.s.start[d] = A.s.start[c] + a; }
-	asm_free(A, c);
-	__syncthreads();
+	asm_free<NT>(A, c);
+	asm_bar<NT>();
 	return d;
 }
 
 // one pass of combine (:262-281): in[0..n_in) -> out[], returns the new list length
-__device__ int asm_combine_pass(Asm &A, uint16_t *in, int n_in, uint16_t *out, int min_support, int mo, bool has_n)
+template <int NT> __device__ int asm_combine_pass(Asm &A, uint16_t *in, int n_in, uint16_t *out, int min_support, int mo, bool has_n)
 {
-	const int tid = threadIdx.x;
+	const int tid = asm_tid<NT>();
 	int usedi = -1;
 	for (int i = 0; i < n_in; ++i) {
 		int c = in[i];
 		if (min_support > 0) {
 			const int nr = A.s.nreads[c];
-			const int c2 = asm_trim(A, c, nr < min_support ? nr : min_support, has_n);
-			if (c2 != c) { __syncthreads(); if (tid == 0) in[i] = (uint16_t)c2; __syncthreads(); c = c2; }
+			const int c2 = asm_trim<NT>(A, c, nr < min_support ? nr : min_support, has_n);
+			if (c2 != c) { asm_bar<NT>(); if (tid == 0) in[i] = (uint16_t)c2; asm_bar<NT>(); c = c2; }
 		}
 		if (usedi < 0 && A.s.nreads[c] > 0) usedi = i;
 	}
 	if (usedi < 0) return 0;
-	__syncthreads();
+	asm_bar<NT>();
 	if (tid == 0) out[0] = in[usedi];
-	__syncthreads();
+	asm_bar<NT>();
 	int n_out = 1;
 	for (int i = 0; i < n_in; ++i) {
 		if (i == usedi) continue;
 		if (A.s.sc[SC_STATUS]) break;
 		const int q = in[i];
-		const AsmMatch m = asm_best_match(A, out, n_out, q, mo, has_n);
-		if (m.aligned) asm_merge(A, out, m.k, q, m.offset, has_n);
+		const AsmMatch m = asm_best_match<NT>(A, out, n_out, q, mo, has_n);
+		if (m.aligned) asm_merge<NT>(A, out, m.k, q, m.offset, has_n);
 		else if (A.s.nreads[q] > 0) {
-			__syncthreads();
+			asm_bar<NT>();
 			if (tid == 0) out[n_out] = (uint16_t)q;
-			__syncthreads();
+			asm_bar<NT>();
 			++n_out;
-		} else { asm_free(A, q); __syncthreads(); }
+		} else { asm_free<NT>(A, q); asm_bar<NT>(); }
 	}
 	return n_out;
 }
 
+template <int NT>
 __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Asm A;
 	A.a = &args; A.nw = args.nw; A.cap = args.cap; A.ns = args.ns; A.offsets = 0;
-	A.planes = args.planes + (size_t)blockIdx.x * args.ns * 3 * args.nw;
-	A.supb = args.sup + (size_t)blockIdx.x * args.ns * args.cap;
+	const int grp_in_cta = NT == 32 ? (int)(threadIdx.x >> 5) : 0;
+	const size_t grp = (size_t)blockIdx.x * (ASM_THREADS / NT) + grp_in_cta; // this group's arena
+	A.planes = args.planes + grp * args.ns * 3 * args.nw;
+	A.supb = args.sup + grp * args.ns * args.cap;
 	{ // carve shared memory
-		unsigned char *p = smem_raw;
+		unsigned char *p = smem_raw + asm_smem_bytes(args.ns, args.nw, NT) * grp_in_cta;
 		A.s.q0 = (uint32_t*)p; p += (size_t)A.nw * 4; A.s.q1 = (uint32_t*)p; p += (size_t)A.nw * 4; A.s.qn = (uint32_t*)p; p += (size_t)A.nw * 4;
 		A.s.len = (int*)p; p += (size_t)A.ns * 4; A.s.nreads = (int*)p; p += (size_t)A.ns * 4; A.s.start = (int*)p; p += (size_t)A.ns * 4;
 		A.s.corr = (int*)p; p += (size_t)3 * IDL_MAX_CORRECTIONS * 4;
-		A.s.best = (unsigned long long*)(((uintptr_t)p + 7) & ~(uintptr_t)7); p = (unsigned char*)(A.s.best + ASM_WARPS);
+		A.s.best = (unsigned long long*)(((uintptr_t)p + 7) & ~(uintptr_t)7); p = (unsigned char*)(A.s.best + (NT / 32));
 		A.s.sc = (int*)p; p += SC_N * 4;
 		A.s.listA = (uint16_t*)p; p += (size_t)A.ns * 2; A.s.listB = (uint16_t*)p; p += (size_t)A.ns * 2; A.s.freestk = (uint16_t*)p;
 	}
-	const int tid = threadIdx.x;
+	const int tid = asm_tid<NT>();
 	const idl_params &P = args.P;
 	for (;;) {
-		__syncthreads();
-		if (tid == 0) A.s.sc[SC_REGION] = (int)atomicAdd(&args.cnt->region_next, 1u);
-		__syncthreads();
+		asm_bar<NT>();
+		if (tid == 0) A.s.sc[SC_REGION] = (int)atomicAdd(args.small ? &args.cnt->region_next : &args.cnt->region_next2, 1u);
+		asm_bar<NT>();
 		const unsigned rg = (unsigned)A.s.sc[SC_REGION];
 		if (rg >= args.n_regions) break;
 		const idl_region R = args.region[rg];
+		if ((R.n_reads <= ASM_SMALL_READS) != (args.small != 0)) continue; // the other launch assembles this region
 		// reset the slot allocator; detect non-ACGT bases in this region's reads and window
 		if (tid == 0) { A.s.sc[SC_NFREE] = A.ns; A.s.sc[SC_STATUS] = R.n_reads + 2 > (unsigned)A.ns ? IDL_RS_CONTIG_OVERFLOW : 0; A.s.sc[SC_HASN] = 0; }
-		for (int i = tid; i < A.ns; i += ASM_THREADS) A.s.freestk[i] = (uint16_t)(A.ns - 1 - i);
-		__syncthreads();
+		for (int i = tid; i < A.ns; i += NT) A.s.freestk[i] = (uint16_t)(A.ns - 1 - i);
+		asm_bar<NT>();
 		{
 			int any = 0;
 			for (unsigned j = 0; j < R.n_reads; ++j) {
 				const idl_read rd = args.read[R.read_begin + j];
 				const uint32_t *pn = args.seqn + (rd.seq_off >> 5);
-				for (int w = tid; w * 32 < rd.len; w += ASM_THREADS) any |= pn[w] != 0;
+				for (int w = tid; w * 32 < rd.len; w += NT) any |= pn[w] != 0;
 			}
 			if (any) A.s.sc[SC_HASN] = 1;
 		}
 		// unpack the reference window to 0..4 codes for kernel 2 / glue (src/ksw2/ksw2.nim:127-132)
-		for (unsigned i = tid; i < R.ref_len; i += ASM_THREADS) {
+		for (unsigned i = tid; i < R.ref_len; i += NT) {
 			const unsigned b = R.ref_off + i;
 			const unsigned isn = (args.refn[b >> 5] >> (b & 31)) & 1u;
 			args.refcodes[b] = isn ? 4 : (uint8_t)((args.ref2[b >> 4] >> (2 * (b & 15))) & 3u);
 		}
-		__syncthreads();
+		asm_bar<NT>();
 		const bool has_n = A.s.sc[SC_HASN] != 0;
 		uint16_t *list = A.s.listA, *other = A.s.listB;
 		int nlist = 0;
@@ -435,15 +446,15 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 			const idl_read rd = args.read[R.read_begin + j];
 			if ((int)rd.mapq < P.asm_min_mapq) continue;  // :164
 			if (rd.flags & 1) continue;                  // :165
-			const int q = asm_alloc(A);
+			const int q = asm_alloc<NT>(A);
 			if (q < 0) break;
 			const int tl = rd.trim_len;
-			if (tl > A.cap) { if (tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; __syncthreads(); break; }
+			if (tl > A.cap) { if (tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; asm_bar<NT>(); break; }
 			{ // make_contig (:143-150) from the packed, trimmed read
 				uint32_t *g0 = A.p0(q), *g1 = A.p1(q), *gn = A.pn(q);
 				uint16_t *gs = A.sup(q);
 				const unsigned base = rd.seq_off + rd.trim_a;
-				for (int w = tid; w * 32 < tl; w += ASM_THREADS) {
+				for (int w = tid; w * 32 < tl; w += NT) {
 					const unsigned b = base + 32u * w;         // first base of this plane word
 					const unsigned wi = b >> 4, sh = 2 * (b & 15);
 					const uint32_t w0 = args.seq2[wi], w1 = args.seq2[wi + 1], w2 = args.seq2[wi + 2];
@@ -455,25 +466,25 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 					g1[w] = compress_even(bits >> 1) & m;
 					gn[w] = has_n ? (get32(args.seqn, (int)b) & m) : 0u;
 				}
-				for (int i = tid; i < tl; i += ASM_THREADS) gs[i] = 1;
+				for (int i = tid; i < tl; i += NT) gs[i] = 1;
 				if (tid == 0) { A.s.len[q] = tl; A.s.nreads[q] = 1; A.s.start[q] = rd.start + rd.trim_a; }
 			}
-			__syncthreads();
-			const AsmMatch m = asm_best_match(A, list, nlist, q, rd.min_overlap, has_n);
-			if (m.aligned) asm_merge(A, list, m.k, q, m.offset, has_n);
-			else { __syncthreads(); if (tid == 0) list[nlist] = (uint16_t)q; __syncthreads(); ++nlist; }
+			asm_bar<NT>();
+			const AsmMatch m = asm_best_match<NT>(A, list, nlist, q, rd.min_overlap, has_n);
+			if (m.aligned) asm_merge<NT>(A, list, m.k, q, m.offset, has_n);
+			else { asm_bar<NT>(); if (tid == 0) list[nlist] = (uint16_t)q; asm_bar<NT>(); ++nlist; }
 		}
 		const int n_pre = nlist; // :171
 		// ---- combine (:176 -> src/contig.nim:254-281): pass A without trimming, pass B with min_support
 		if (!A.s.sc[SC_STATUS]) {
-			int n2 = asm_combine_pass(A, list, nlist, other, 0, P.combine_min_overlap, has_n);
+			int n2 = asm_combine_pass<NT>(A, list, nlist, other, 0, P.combine_min_overlap, has_n);
 			{ uint16_t *t = list; list = other; other = t; } nlist = n2;
 			if (!A.s.sc[SC_STATUS]) {
-				n2 = asm_combine_pass(A, list, nlist, other, P.combine_min_support, P.combine_min_overlap, has_n);
+				n2 = asm_combine_pass<NT>(A, list, nlist, other, P.combine_min_support, P.combine_min_overlap, has_n);
 				{ uint16_t *t = list; list = other; other = t; } nlist = n2;
 			}
 		}
-		__syncthreads();
+		asm_bar<NT>();
 		// ---- results
 		const unsigned status = (unsigned)A.s.sc[SC_STATUS];
 		if (status) nlist = 0;
@@ -483,7 +494,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 			A.s.sc[SC_TMP0] = (int)atomicAdd(&args.cnt->n_contigs, (unsigned)nlist);
 			A.s.sc[SC_TMP1] = (int)atomicAdd(&args.cnt->n_contig_bases, total);
 		}
-		__syncthreads();
+		asm_bar<NT>();
 		const unsigned cbegin = (unsigned)A.s.sc[SC_TMP0];
 		unsigned boff = (unsigned)A.s.sc[SC_TMP1];
 		if (tid == 0) {
@@ -497,7 +508,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 			if (boff + (unsigned)L > args.cap_bases) { if (tid == 0) atomicOr(&args.cnt->overflow, 2u); break; }
 			const uint32_t *g0 = A.p0(c), *g1 = A.p1(c), *gn = A.pn(c);
 			const uint16_t *gs = A.sup(c);
-			for (int x = tid; x < L; x += ASM_THREADS) {
+			for (int x = tid; x < L; x += NT) {
 				const unsigned code = ((g0[x >> 5] >> (x & 31)) & 1u) | (((g1[x >> 5] >> (x & 31)) & 1u) << 1);
 				const bool isn = has_n && ((gn[x >> 5] >> (x & 31)) & 1u);
 				args.ctg_codes[boff + x] = isn ? 4 : (uint8_t)code;

@@ -11,6 +11,7 @@
 // device-side global counters of one ticket (zeroed before the chain starts)
 struct DevCounters {
 	unsigned int region_next;      // work queue heads
+	unsigned int region_next2;
 	unsigned int aln_next;
 	unsigned int al_next;
 	unsigned int n_contigs;        // bump allocators of the result pools

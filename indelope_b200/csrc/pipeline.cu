@@ -60,7 +60,7 @@ struct Lane {
 	// device results and intermediates
 	DevBuf rres, cres, ares, eres, cigar, ctg_ascii, ctg_codes, ctg_sup, refcodes, al_list, al_items, al_res, sort_misc, keysA, orderA, keysB, orderB, cnt;
 	// workspaces
-	DevBuf planes, sup, pmat, cig_scratch, seq_spill;
+	DevBuf planes, sup, planes_small, sup_small, pmat, cig_scratch, seq_spill;
 	// pinned host results
 	HostBuf h_rres, h_cres, h_ares, h_eres, h_cigar, h_seq, h_sup, h_cnt;
 	// state
@@ -161,7 +161,7 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	ctx->nw = p->max_contig_len / 32 + 2;
 	// persistent grids: CTAs per SM (tunable for experiments through the environment)
 	const char *ea = getenv("IDL_ASM_CTAS_PER_SM"), *ed = getenv("IDL_DP_CTAS_PER_SM");
-	ctx->asm_ctas = ctx->n_sm * (ea && atoi(ea) > 0 ? atoi(ea) : 4);
+	ctx->asm_ctas = ctx->n_sm * (ea && atoi(ea) > 0 ? atoi(ea) : 4); // CTAs of each assembler launch (8 regions per CTA in the warp variant)
 	ctx->dp_ctas = ctx->n_sm * (ed && atoi(ed) > 0 ? atoi(ed) : 2);
 	ctx->lanes.resize((size_t)p->n_streams);
 	for (Lane &L : ctx->lanes) {
@@ -171,7 +171,8 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	// opt in to large dynamic shared memory for the DP kernels
 	cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	cudaFuncSetAttribute(al_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-	cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(assemble_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(assemble_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	*out = ctx;
 	return IDL_OK;
 }
@@ -184,7 +185,7 @@ void idl_destroy(idl_ctx *ctx)
 		if (L.stream) cudaStreamSynchronize(L.stream);
 		for (DevBuf *b : {&L.region, &L.read, &L.seq2, &L.seqn, &L.ref2, &L.refn, &L.rres, &L.cres, &L.ares, &L.eres, &L.cigar, &L.ctg_ascii, &L.ctg_codes,
 		                  &L.ctg_sup, &L.refcodes, &L.al_list, &L.al_items, &L.al_res, &L.sort_misc, &L.keysA, &L.orderA, &L.keysB, &L.orderB, &L.cnt, &L.planes, &L.sup,
-		                  &L.pmat, &L.cig_scratch, &L.seq_spill})
+		                  &L.planes_small, &L.sup_small, &L.pmat, &L.cig_scratch, &L.seq_spill})
 			b->release();
 		for (HostBuf *b : {&L.h_rres, &L.h_cres, &L.h_ares, &L.h_eres, &L.h_cigar, &L.h_seq, &L.h_sup, &L.h_cnt}) b->release();
 		for (auto &ev : L.ev) if (ev) cudaEventDestroy(ev);
@@ -285,9 +286,18 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 	CK(L.keysA.ensure((size_t)L.cap_alns + 16)); CK(L.orderA.ensure((size_t)L.cap_alns * 4 + 16));
 	CK(L.keysB.ensure((size_t)L.cap_items * 2 + 16)); CK(L.orderB.ensure((size_t)L.cap_items * 8 + 16));
 	// workspaces
-	const int asm_ctas = (int)std::max<size_t>(1, std::min<size_t>(b->n_regions, (size_t)ctx->asm_ctas));
-	CK(L.planes.ensure((size_t)ctx->asm_ctas * ctx->ns * 3 * ctx->nw * 4));
-	CK(L.sup.ensure((size_t)ctx->asm_ctas * ctx->ns * P.max_contig_len * 2));
+	size_t n_small = 0;
+	for (size_t i = 0; i < b->n_regions; ++i) n_small += b->region[i].n_reads <= ASM_SMALL_READS;
+	const size_t n_big = b->n_regions - n_small;
+	const int big_ctas = (int)std::min<size_t>(n_big, (size_t)ctx->asm_ctas), small_ctas = (int)std::min<size_t>((n_small + 7) / 8, (size_t)ctx->asm_ctas);
+	if (n_big) {
+		CK(L.planes.ensure((size_t)big_ctas * ctx->ns * 3 * ctx->nw * 4));
+		CK(L.sup.ensure((size_t)big_ctas * ctx->ns * P.max_contig_len * 2));
+	}
+	if (n_small) {
+		CK(L.planes_small.ensure((size_t)small_ctas * 8 * ASM_SMALL_NS * 3 * ctx->nw * 4));
+		CK(L.sup_small.ensure((size_t)small_ctas * 8 * ASM_SMALL_NS * P.max_contig_len * 2));
+	}
 	// kernel 2 geometry: call-site A (contig vs window, banded) and B (read vs suffix, unbanded by default)
 	const int ncolA = ksw_ncol(P.max_contig_len, (int)max_ref, P.a_bw), ncolB = ksw_ncol(max_trim, std::max((int)max_ref, P.max_contig_len), P.b_bw);
 	const int wA = P.a_bw < 0 ? std::max(P.max_contig_len, (int)max_ref) : P.a_bw;
@@ -317,8 +327,14 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 	a.cap_contigs = L.cap_contigs; a.cap_bases = L.cap_bases; a.cap_alns = L.cap_alns;
 	a.sortA = sA;
 	a.cnt = (DevCounters*)L.cnt.p;
-	if (b->n_regions > 0 && (P.stages & IDL_STAGE_ASSEMBLE)) {
-		assemble_kernel<<<asm_ctas, ASM_THREADS, asm_smem_bytes(ctx->ns, ctx->nw), L.stream>>>(a);
+	if (n_small && (P.stages & IDL_STAGE_ASSEMBLE)) { // one warp per region
+		a.small = 1; a.ns = ASM_SMALL_NS; a.planes = (uint32_t*)L.planes_small.p; a.sup = (uint16_t*)L.sup_small.p;
+		assemble_kernel<32><<<small_ctas, ASM_THREADS, 8 * asm_smem_bytes(ASM_SMALL_NS, ctx->nw, 32), L.stream>>>(a);
+		CK(cudaGetLastError()); L.launches++;
+	}
+	if (n_big && (P.stages & IDL_STAGE_ASSEMBLE)) { // one CTA per region
+		a.small = 0; a.ns = ctx->ns; a.planes = (uint32_t*)L.planes.p; a.sup = (uint16_t*)L.sup.p;
+		assemble_kernel<256><<<big_ctas, ASM_THREADS, asm_smem_bytes(ctx->ns, ctx->nw, 256), L.stream>>>(a);
 		CK(cudaGetLastError()); L.launches++;
 	}
 	CK(cudaEventRecord(L.ev[EV_ASM], L.stream));

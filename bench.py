@@ -237,6 +237,10 @@ def main():
             "al_kernel": avg["dp_cells_b"] * 1.0,
         }
         ach = alg[dom] / (kern[dom] / 1000.0) / 1e9 if kern[dom] > 0 else 0.0
+        traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture (default workload only)
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath) and args.workload == "chr1" and args.scale == 1.0:
+            traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
         clocks = sampler.summary()
         mhz = clocks.get("sm_mhz") or sm_max
         int_peak = 148 * 128 * mhz * 1e6 / 1e12  # Tiop/s, INT32 lanes x clock
@@ -251,7 +255,7 @@ def main():
                        "l2": "inputs (%.0f MB packed) exceed the 126 MB L2; no explicit flush" % (big_bytes / 1e6), "e2e_batches": len(slices), "streams": P.n_streams},
             "kernel_ms": kern,
             "work": {k: avg[k] for k in ("offsets_tested", "dp_cells_a", "dp_cells_b", "dp_a", "dp_b", "kmer_reads", "kmer_bytes", "al_events", "n_contigs", "n_alns", "n_events")},
-            "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "algorithmic_bytes": alg[dom],
                          "peak_source": peak_src,
                          "note": "integer, latency/ALU-bound kernel: algorithmic bytes are tiny, see alu and DESIGN.md",
                          "alu": {"int32_peak_tiops": int_peak, "clock_mhz": mhz}},

@@ -5,12 +5,16 @@ set -u
 SCALE=${1:-0.05}
 OUT=gpurun_out
 mkdir -p $OUT
+rm -f $OUT/prof_*.ncu-rep
 # 1. launch list: every kernel launch of one short bench run with its device time (shares, not absolutes)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --scale $SCALE --cpu-sample 200 > $OUT/ncu_bench.log 2>&1
-# 2. full captures, one launch of each kernel (skip the warm-up launch)
+# 2. full captures, one launch of each kernel of the resident leg (skip the warm-up launch)
 for K in assemble_kernel align_kernel kmer_kernel al_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -o $OUT/prof_$K -f \
       python bench.py --steps 1 --warmup 1 --scale $SCALE --cpu-sample 200 > $OUT/ncu_$K.log 2>&1
 done
-ls -la $OUT
+# 3. kernel 2 alone at fixed shapes (tools/ksw_bench.py): call-site A 300x420 (launch 0) and call-site B 150x700 (launch 9)
+ncu --set full --clock-control none --import-source on -k regex:ksw2_batch_kernel -s 0 -c 1 -o $OUT/prof_ksw2_siteA_300x420 -f python tools/ksw_bench.py 20000 > $OUT/ncu_kswA.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:ksw2_batch_kernel -s 9 -c 1 -o $OUT/prof_ksw2_siteB_150x700 -f python tools/ksw_bench.py 20000 > $OUT/ncu_kswB.log 2>&1
+ls -la $OUT | head -40

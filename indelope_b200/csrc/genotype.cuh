@@ -17,8 +17,8 @@
 #define DP_THREADS (DP_WARPS * 32)
 #define KMER_THREADS 128
 #define DP_G 8          // threads per alignment
-#define DP_W_A 3        // packed words per thread, call-site A: 8*3*4 = 96 columns = 80-lane band + 16 lanes of score overrun
-#define DP_W_B 6        // call-site B: 192 columns = a 150 bp read's unbanded diagonal (176 lanes) + overrun in one pass
+#define DP_W_A 3        // rounds of 8 packed words per trip, call-site A: 8*3*4 = 96 columns = 80-lane band + 16 lanes of score overrun
+#define DP_W_B 3        // call-site B: up to 192 columns (a 150 bp read's unbanded diagonal + overrun) in two trips of three rounds
 #define DP_NG (32 / DP_G)
 
 struct AlEntry { unsigned event; unsigned base; unsigned n_reads; unsigned pad; };

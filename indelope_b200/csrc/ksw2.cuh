@@ -102,10 +102,10 @@ __host__ __device__ inline size_t ksw_group_smem(int ring_cols, int hr, int seq_
 }
 // layout of a group's region (a multiple of 128 bytes): [lanes: 5 rings + 128 bytes of stagger slack][H][seq]
 __host__ __device__ inline size_t ksw_group_h_off(int ring_cols) { return (size_t)5 * ring_cols + 128; }
-// Bank staggering: the G threads of a group touch words W apart, the 32/G groups of a warp touch the same relative word.
-// These byte offsets (added to the lane rings only; H and seq keep their 16-byte alignment) make the 32 words of one
-// access fall into 32 different banks for W = 3 (stride 8 words) and W = 6 (0, 1, 16, 17 words).
-__host__ __device__ inline int ksw_group_stagger(int grp_in_warp, int W) { return W == 6 ? 4 * ((grp_in_warp & 1) + 16 * (grp_in_warp >> 1)) : 32 * grp_in_warp; }
+// Bank staggering: the G = 8 threads of a group touch 8 consecutive words, the 32/G groups of a warp touch the same relative
+// word.  This byte offset (added to the lane rings only; H and seq keep their 16-byte alignment) makes the 32 words of one
+// access fall into 32 different banks.
+__host__ __device__ inline int ksw_group_stagger(int grp_in_warp, int W) { (void)W; return 32 * grp_in_warp; } // the 8 threads of a group touch 8 consecutive words
 
 // The G threads of a group call this with identical arguments; `out` comes back identical in each of them.
 template <int G, int W>
@@ -184,21 +184,30 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 		uint32_t *pr = (uint32_t*)(pmat + (size_t)r * n_col) - (st >> 2);
 		int bh = (int)0x80000000, bt = st0;                  // this thread's best exact score and its column (ties in SSE order)
 		const int rword = en >= r ? (r >> 2) : -1;           // :212, y[r] = 0 and u[r] = q, patched in registers
+		// Words are dealt round-robin: word j of the band goes to thread j % G, so a narrow band (the first and last
+		// diagonals, short targets) costs ceil(words / G) rounds instead of always W.
 		for (int w0 = st >> 2; w0 <= wlast; w0 += G * W) {
-			const int wb = w0 + gl * W;
-			uint32_t xo[W], vo[W];
+			const int wb = w0 + gl;
+			uint32_t xo[W], vo[W], xp[W], vp[W];
 #pragma unroll
 			for (int k = 0; k < W; ++k) {
-				const bool core = wb + k <= wend;
-				xo[k] = core ? X[(wb + k) & rmw] : 0u;
-				vo[k] = core ? V[(wb + k) & rmw] : 0u;
+				const bool core = wb + k * G <= wend;
+				xo[k] = core ? X[(wb + k * G) & rmw] : 0u;
+				vo[k] = core ? V[(wb + k * G) & rmw] : 0u;
 			}
-			uint32_t xp = __shfl_up_sync(gmask, xo[W - 1], 1, G), vp = __shfl_up_sync(gmask, vo[W - 1], 1, G);
-			if (gl == 0) { xp = xc; vp = vc; }
+			// neighbour word (columns t-4..t-1 of the previous diagonal): the previous thread in the same round, or thread G-1 of
+			// the round before for thread 0 (the carry of the previous trip / the boundary value for the very first word)
+#pragma unroll
+			for (int k = 0; k < W; ++k) {
+				xp[k] = __shfl_up_sync(gmask, xo[k], 1, G); vp[k] = __shfl_up_sync(gmask, vo[k], 1, G);
+				const uint32_t xw = __shfl_sync(gmask, xo[k ? k - 1 : 0], G - 1, G), vw = __shfl_sync(gmask, vo[k ? k - 1 : 0], G - 1, G);
+				if (gl == 0) { xp[k] = k ? xw : xc; vp[k] = k ? vw : vc; }
+			}
 			xc = __shfl_sync(gmask, xo[W - 1], G - 1, G); vc = __shfl_sync(gmask, vo[W - 1], G - 1, G);
 #pragma unroll
 			for (int k = 0; k < W; ++k) {
-				const int wi = wb + k, t = wi << 2;
+				if (w0 + k * G > wlast) break; // the rest of this trip lies beyond the band (same for the whole group)
+				const int wi = wb + k * G, t = wi << 2;
 				const bool core = wi <= wend, sca = wi >= ws0 && wi <= w1;
 				uint32_t so = (core || sca) ? S[wi & rmw] : 0u;
 				if (sca) { // scores: lanes of this word inside the 16-wide blocks get fresh values, the others keep stale s
@@ -224,8 +233,7 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 						yt &= ~(0xffu << b);
 						ut = (ut & ~(0xffu << b)) | ((uint32_t)((r ? P.q : 0) & 0xff) << b);
 					}
-					const uint32_t xt1 = __funnelshift_l(k ? xo[k ? k - 1 : 0] : xp, xo[k], 8); // lanes t-1..t+2 of the previous diagonal
-					const uint32_t vt1 = __funnelshift_l(k ? vo[k ? k - 1 : 0] : vp, vo[k], 8);
+					const uint32_t xt1 = __funnelshift_l(xp[k], xo[k], 8), vt1 = __funnelshift_l(vp[k], vo[k], 8); // lanes t-1..t+2 of the previous diagonal
 					uint32_t z = so;                               // s + 2(q+e)
 					uint32_t a = __vadd4(xt1, vt1);
 					uint32_t b = __vadd4(yt, ut);

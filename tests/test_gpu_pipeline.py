@@ -125,3 +125,61 @@ def test_empty_batch_and_tiny_regions():
         assert v == "" and d == ""
     finally:
         caller.close()
+
+
+@pytest.mark.parametrize("read_len", [100, 250])
+def test_other_read_lengths(read_len):
+    """100 bp and 250 bp reads: the unbanded AL alignments then need one / three trips of packed words per diagonal"""
+    ds = util.small_dataset("pr1", chrom_len=300_000, n_events=50, max_indel=40, read_len=read_len, tr_fraction=0.3, seed=31 + read_len)
+    rois = ds.sweep(min_reads=5)
+    dump, vcf, odump, ovcf, cnt, _ = run_both(rois, rois.arrays(), tag="len%d" % read_len)
+    assert cnt["regions"] > 20 and cnt["dp_b"] > 0
+    assert_same(dump, vcf, odump, ovcf)
+
+
+def test_deep_regions_use_the_cta_assembler():
+    """regions with more than 126 reads (up to the 600-read cap of src/indelope.nim:515) go through assemble_kernel<256>"""
+    ds = util.small_dataset("panel500", chrom_len=100_000, n_events=10, coverage=420.0, seed=77)
+    rois = ds.sweep(min_reads=5)
+    a = rois.arrays()
+    assert a["roi_n_reads"].max() > 400 and a["roi_n_reads"].max() <= 600
+    dump, vcf, odump, ovcf, cnt, _ = run_both(rois, a, tag="deep")
+    assert_same(dump, vcf, odump, ovcf)
+
+
+def _random_seq(rng, n):
+    return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+
+
+def test_directed_gates_and_odd_reads():
+    """directed regions for paths random data rarely hits: an empty first read (all qualities below 15), MAPQ at the 20/10/5
+    gates, exactly 20 and 21 pre-combine contigs (src/indelope.nim:209), a read shorter than K, a skippable read, Ns"""
+    rng = np.random.default_rng(123)
+    ref = _random_seq(rng, 6000)
+    sets = []
+    for n_single in (18, 19):  # 1 empty + 1 merged contig + n singletons = 20 / 21 pre-combine contigs
+        reads = []
+        base = 2000
+        hap = ref[base:base + 70] + ref[base + 82:base + 400]  # 12 bp deletion
+        reads.append(dict(start=base, seq=ref[base:base + 150], qual=[2] * 150))                       # trimmed to nothing: empty first contig
+        for k in range(4):
+            for c in range(5):
+                off = 10 * k + c
+                reads.append(dict(start=base + off, seq=hap[off:off + 150], mapq=[60, 20, 19, 60, 60][c]))  # 19 is skipped by assemble
+        for j in range(n_single):
+            reads.append(dict(start=base + 20 + j, seq=_random_seq(rng, 150), mapq=60))                  # singletons
+        for j in range(3):
+            reads.append(dict(start=base + 40 + j, seq=_random_seq(rng, 150), mapq=9))                   # MAPQ 9: neither assembled nor counted
+        reads.append(dict(start=base + 30, seq=ref[base + 30:base + 50]))                              # 20 bp < K: never matches a k-mer
+        reads.append(dict(start=base + 31, seq=hap[31:181], flag=0x400))                                # duplicate: skippable
+        reads.append(dict(start=base + 32, seq=hap[32:100] + "N" + hap[101:182], mapq=5))               # N base, MAPQ 5 does not extend the window
+        reads.sort(key=lambda r: r["start"])
+        _, arrays = util.rois_from_reads(reads, ref, roi_start=base + 60, roi_stop=base + 90)
+        sets.append(arrays)
+    arrays = util.merge_rois(sets)
+    rois = host.Rois(arrays=arrays)
+    dump, vcf, odump, ovcf, cnt, _ = run_both(rois, arrays, min_reads=3, min_event_len=4, tag="directed")
+    pre = [int(l.split("\t")[2].split("=")[1]) for l in odump.splitlines() if l.startswith("R\t")]
+    assert pre == [20, 21], pre   # the two regions straddle the n_contigs > 20 gate
+    assert sum(l.startswith("A\t0\t") for l in odump.splitlines()) >= 1 and not any(l.startswith("A\t1\t") for l in odump.splitlines())
+    assert_same(dump, vcf, odump, ovcf)

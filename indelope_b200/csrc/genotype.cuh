@@ -17,8 +17,6 @@
 #define DP_THREADS (DP_WARPS * 32)
 #define KMER_THREADS 128
 #define DP_G 8          // threads per alignment
-#define DP_W_A 3        // rounds of 8 packed words per trip, call-site A: 8*3*4 = 96 columns = 80-lane band + 16 lanes of score overrun
-#define DP_W_B 3        // call-site B: up to 192 columns (a 150 bp read's unbanded diagonal + overrun) in two trips of three rounds
 #define DP_NG (32 / DP_G)
 
 struct AlEntry { unsigned event; unsigned base; unsigned n_reads; unsigned pad; };
@@ -36,7 +34,7 @@ struct GenoArgs {
 	idl_params P;
 	DevCounters *cnt;
 	// kernel 2 geometry of this launch (per group) and its global workspaces (one per resident group)
-	int ring_cols, hr, seq_cap;
+	int ring_cols, seq_cap;
 	uint8_t *pmat; size_t p_cap;
 	uint32_t *cig_scratch; int cig_cap;
 	uint8_t *seq_spill; int seq_spill_cap;  // global-memory sequence staging for alignments that do not fit seq_cap
@@ -64,16 +62,14 @@ __global__ void sort_scatter_kernel(SortBufs s, const unsigned *n_ptr, unsigned 
 }
 
 // shared/global memory of the group this thread belongs to
-__device__ __forceinline__ KswMem dp_mem(const GenoArgs &g, unsigned char *smem, int qlen, int tlen, int W)
+__device__ __forceinline__ KswMem dp_mem(const GenoArgs &g, unsigned char *smem, int qlen, int tlen)
 {
 	const int grp = warp_id() * DP_NG + (lane_id() / DP_G);
-	const size_t per = ksw_group_smem(g.ring_cols, g.hr, g.seq_cap);
-	unsigned char *base = smem + per * grp;
+	const size_t per = ksw_group_smem(g.ring_cols, g.seq_cap);
 	const size_t gg = (size_t)blockIdx.x * (DP_WARPS * DP_NG) + grp;
 	KswMem m;
-	m.lanes = (int8_t*)(base + ksw_group_stagger(lane_id() / DP_G, W)); m.ring_cols = g.ring_cols;
-	m.H = (int*)(base + ksw_group_h_off(g.ring_cols)); m.hr = g.hr;
-	if (ksw_seq_bytes(qlen, tlen) <= (size_t)g.seq_cap) { m.seq = base + ksw_group_h_off(g.ring_cols) + g.hr * 4; m.seq_cap = g.seq_cap; }
+	ksw_group_mem(m, smem + per * grp, lane_id() / DP_G, g.ring_cols);
+	if (ksw_seq_bytes(qlen, tlen) <= (size_t)g.seq_cap) m.seq_cap = g.seq_cap;
 	else { m.seq = g.seq_spill + gg * (size_t)g.seq_spill_cap; m.seq_cap = g.seq_spill_cap; }
 	m.pmat = g.pmat + gg * g.p_cap; m.p_cap = g.p_cap;
 	m.cig = g.cig_scratch + gg * (size_t)g.cig_cap; m.cig_cap = g.cig_cap;
@@ -137,9 +133,9 @@ __global__ void __launch_bounds__(DP_THREADS, 2) align_kernel(GenoArgs g)
 			const uint8_t *tq = g.refcodes + R.ref_off + (cr.start - R.ref_start);
 			const uint8_t *qq = g.ctg_codes + cr.seq_off;
 			KswQuery kq; kq.codes = qq; kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
-			const KswMem M = dp_mem(g, smem_raw, cr.len, tlen, DP_W_A);
+			const KswMem M = dp_mem(g, smem_raw, cr.len, tlen);
 			KswOut o;
-			ksw2_group<DP_G, DP_W_A>(cr.len, kq, tlen, tq, kp, M, o);
+			ksw2_group<DP_G>(cr.len, kq, tlen, tq, kp, M, o);
 			const uint32_t *cg = M.cig;
 			const int n = o.n_cigar;
 			int ntr = 0, nev = 0;
@@ -406,9 +402,9 @@ __global__ void __launch_bounds__(DP_THREADS, 2) al_kernel(GenoArgs g)
 			if (!(task & 1)) { t = g.refcodes + R.ref_off + (cr.start - R.ref_start) + it.start; tlen = ar.ref_len - it.start; } // ref_sub :340
 			else { t = g.ctg_codes + cr.seq_off + it.start; tlen = cr.len - it.start; }                                          // ctg_sub :341
 			if (tlen < 0) tlen = 0;
-			const KswMem M = dp_mem(g, smem_raw, qlen, tlen, DP_W_B);
+			const KswMem M = dp_mem(g, smem_raw, qlen, tlen);
 			KswOut o;
-			ksw2_group<DP_G, DP_W_B>(qlen, kq, tlen, t, kp, M, o);
+			ksw2_group<DP_G>(qlen, kq, tlen, t, kp, M, o);
 			if (gl == 0) {
 				const unsigned st = dp_status_bits(o.status);
 				int c = count_flanked(M.cig, o.n_cigar, o.max_q);

@@ -26,6 +26,7 @@ struct KswOut {
 };
 
 #define KSW_BTILE_BYTES 1024
+#define KSW_QR_PAD 32     /* zero bytes in front of the reversed query: lanes left of the exact band index it below 0 */
 #define KSW_PMAT_PAD 64   /* bytes in front of every backtrack matrix (the tile prefetch may start before row 0) */
 #define KSW_ST_EARLY 1
 #define KSW_ST_RCAP (-2)
@@ -51,11 +52,10 @@ __host__ __device__ inline int ksw_ncol(int qlen, int tlen, int w)
 }
 // ring of lane columns: the rounded band, the column left of it, 16 lanes of score overrun and the 16 being cleared
 __host__ __device__ inline int ksw_ring_cols(int ncol) { int r = 64; while (r < ncol + 48) r <<= 1; return r; }
-__host__ __device__ inline int ksw_h_ring(int ncol) { int r = 16; while (r < ncol + 8) r <<= 1; return r; } // ncol-16 >= exact band
 // bytes of sequence staging: zero-padded target (sf) and reversed, zero-padded query (qr); doubles as the backtrack tile
 __host__ __device__ inline size_t ksw_seq_bytes(int qlen, int tlen)
 {
-	size_t b = (size_t)(((tlen + 15) & ~15) + 16) + (size_t)((qlen + 35) & ~3);
+	size_t b = (size_t)(((tlen + 15) & ~15) + 16) + (size_t)(KSW_QR_PAD + ((qlen + 35) & ~3));
 	return b < KSW_BTILE_BYTES ? KSW_BTILE_BYTES : b;
 }
 
@@ -80,6 +80,9 @@ __device__ __forceinline__ uint32_t msb_to_mask4(uint32_t v)
 	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0u), "r"(0xba98u));
 	return r;
 }
+#define KSW_H80 0x80808080u
+// 0xff in every byte where a >= b, for bytes a, b in [0,127]: (a | 0x80) - b never borrows across bytes
+__device__ __forceinline__ uint32_t ge4_pos(uint32_t a, uint32_t b) { return msb_to_mask4((a | KSW_H80) - b); }
 
 // tie order of the SSE arg-max (:316-348): 4 strided accumulators (lower accumulator, then lower t), then the scalar tail
 __device__ __forceinline__ unsigned ksw_tie_rank(int t, int st0, int en1) { return 1u + ((t < en1 ? (unsigned)((t - st0) & 3) : 4u) << 20) + (unsigned)(t - st0); }
@@ -93,66 +96,82 @@ __device__ __forceinline__ uint8_t ksw_query_code(const KswQuery &q, int i)
 	return ((q.seqn[b >> 5] >> (b & 31)) & 1u) ? (uint8_t)4 : (uint8_t)((q.seq2[b >> 4] >> (2 * (b & 15))) & 3u);
 }
 
-// Memory of one group: lanes = 5 rings of ring_cols bytes, H = hr ints, seq = seq_cap bytes (reused as the backtrack
-// tile) in shared memory; pmat = backtrack matrix workspace, cig = CIGAR scratch in global memory
-struct KswMem { int8_t *lanes; int ring_cols; int *H; int hr; uint8_t *seq; int seq_cap; uint8_t *pmat; size_t p_cap; uint32_t *cig; int cig_cap; };
-__host__ __device__ inline size_t ksw_group_smem(int ring_cols, int hr, int seq_cap)
+// Memory of one group.  Shared memory: xvuy = ring of {x, v, u, y} packed words (16 bytes per 4 columns, one 128-bit load
+// and store per word and diagonal), g = ring of the exact scores as uint16 (8 bytes per 4 columns), S = ring of the score
+// words, all three indexed by (column word & mask) of the same ring; seq = sequence staging (reused as the backtrack tile).
+// Global memory: pmat = backtrack matrix workspace, cig = CIGAR scratch.
+struct KswMem { uint4 *xvuy; uint2 *g; uint32_t *S; int ring_cols; uint8_t *seq; int seq_cap; uint8_t *pmat; size_t p_cap; uint32_t *cig; int cig_cap; };
+// layout of a group's region (a multiple of 128 bytes): [xvuy 4R][g 2R + 64 bytes of stagger slack][S R + 128 of slack][64 pad][seq]
+__host__ __device__ inline size_t ksw_group_seq_off(int ring_cols) { return (size_t)7 * ring_cols + 256; }
+__host__ __device__ inline size_t ksw_group_smem(int ring_cols, int seq_cap)
 {
-	return ((size_t)5 * ring_cols + 128 + (size_t)hr * 4 + (size_t)((seq_cap + 15) & ~15) + 127) & ~(size_t)127;
+	return (ksw_group_seq_off(ring_cols) + (size_t)((seq_cap + 15) & ~15) + 127) & ~(size_t)127;
 }
-// layout of a group's region (a multiple of 128 bytes): [lanes: 5 rings + 128 bytes of stagger slack][H][seq]
-__host__ __device__ inline size_t ksw_group_h_off(int ring_cols) { return (size_t)5 * ring_cols + 128; }
-// Bank staggering: the G = 8 threads of a group touch 8 consecutive words, the 32/G groups of a warp touch the same relative
-// word.  This byte offset (added to the lane rings only; H and seq keep their 16-byte alignment) makes the 32 words of one
-// access fall into 32 different banks.
-__host__ __device__ inline int ksw_group_stagger(int grp_in_warp, int W) { (void)W; return 32 * grp_in_warp; } // the 8 threads of a group touch 8 consecutive words
+// Bank staggering: a 128-bit access is served one group (8 threads x 16 contiguous bytes) at a time, so xvuy needs none; the
+// 64-bit accesses to g pair two groups and the 32-bit accesses to S put all four groups of a warp into one wavefront:
+// their bases are shifted so that groups at the same relative column fall into different banks.
+__device__ __forceinline__ void ksw_group_mem(KswMem &m, unsigned char *base, int grp_in_warp, int ring_cols)
+{
+	m.xvuy = (uint4*)base; m.ring_cols = ring_cols;
+	m.g = (uint2*)(base + (size_t)4 * ring_cols + 64 * (grp_in_warp & 1));
+	m.S = (uint32_t*)(base + (size_t)6 * ring_cols + 64 + 32 * (grp_in_warp & 3));
+	m.seq = base + ksw_group_seq_off(ring_cols);
+}
 
 // The G threads of a group call this with identical arguments; `out` comes back identical in each of them.
-template <int G, int W>
+template <int G>
 __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8_t *target, KswParams P, const KswMem M, KswOut &out)
 {
+	static_assert(G == 8, "the clear-ahead step deals 8 words to the 8 threads of a group");
 	const int lane = lane_id();
 	const int gl = lane & (G - 1);
 	const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
 	ksw_reset(out);
 	if (qlen <= 0 || tlen <= 0) { out.status = KSW_ST_EARLY; return; } // :147
 	const int qe = P.q + P.e;
-	{
-		int min_sc = P.mismatch < 0 ? P.mismatch : 0;
-		if (P.match < min_sc) min_sc = P.match;
-		if (-min_sc > 2 * qe) { out.status = KSW_ST_EARLY; return; } // :171
-	}
+	int min_sc = P.mismatch < 0 ? P.mismatch : 0;
+	if (P.match < min_sc) min_sc = P.match;
+	if (-min_sc > 2 * qe) { out.status = KSW_ST_EARLY; return; } // :171
 	int w = P.w;
 	if (w < 0) w = tlen > qlen ? tlen : qlen; // :161
 	const int T16 = (tlen + 15) & ~15;
 	const int n_col = ksw_ncol(qlen, tlen, w); // :164-165 (bytes)
 	if (ksw_ring_cols(n_col) > M.ring_cols) { out.status = KSW_ST_RCAP; return; }
-	if (n_col + 8 > M.hr) { out.status = KSW_ST_HCAP; return; }
 	if (ksw_seq_bytes(qlen, tlen) > (size_t)M.seq_cap) { out.status = KSW_ST_SEQCAP; return; }
 	if ((size_t)(qlen + tlen - 1) * (size_t)n_col + 2 * KSW_PMAT_PAD > M.p_cap) { out.status = KSW_ST_PCAP; return; }
+	// The exact scores H[] (:177-178, int32 in the reference) live as uint16: g[t] = H[t] + (q+e)*(r+1) + gbias, r = the
+	// diagonal of the last update.  Every in-band column is updated on every diagonal, so the per-diagonal -(q+e) of
+	// :323-348 turns into a common offset, the update into an unsigned byte add, and the band max into a packed 16-bit max.
+	const int gbias = 2 * qe;
+	if ((long long)(qlen + tlen + 2) * qe + (long long)(qlen < tlen ? qlen : tlen) * (P.match > 0 ? P.match : 0) + gbias >= 0xF000) { out.status = KSW_ST_HCAP; return; }
 	uint8_t *pmat = M.pmat + KSW_PMAT_PAD;
-	const int hmask = M.hr - 1, rm = M.ring_cols - 1, rmw = (M.ring_cols >> 2) - 1;
-	int *H = M.H; int4 *H4 = (int4*)M.H;
-	int8_t *u = M.lanes, *v = u + M.ring_cols, *x = v + M.ring_cols, *y = x + M.ring_cols, *s = y + M.ring_cols;
-	uint32_t *U = (uint32_t*)u, *V = (uint32_t*)v, *X = (uint32_t*)x, *Y = (uint32_t*)y, *S = (uint32_t*)s;
-	uint8_t *sf = M.seq, *qr = M.seq + T16 + 16;
-	const uint32_t *SF = (const uint32_t*)sf, *QR = (const uint32_t*)qr;
+	const int rm = M.ring_cols - 1, rmw = (M.ring_cols >> 2) - 1;
+	uint4 *XV = M.xvuy; uint2 *GR = M.g; uint32_t *S = M.S;
+	uint16_t *G16 = (uint16_t*)M.g;
+	uint8_t *sf = M.seq, *qrp = M.seq + T16 + 16; // qrp: KSW_QR_PAD zero bytes, then the reversed query, zero padded
+	const uint32_t *SF = (const uint32_t*)sf, *QRP = (const uint32_t*)qrp;
 	const uint32_t QE2 = rep4(qe * 2), MAXSC = rep4(P.match + qe * 2), Q4 = rep4(P.q), MATQ = rep4(P.match + qe * 2), MISQ = rep4(P.mismatch + qe * 2);
+	// the carry-free formulation of the core needs every constant and every input byte small and non-negative
+	const bool fast_ok = P.match + 2 * qe <= 63 && P.q >= 0 && P.q + 2 * P.e + min_sc >= 0;
 
 	// calloc :173: columns [0,16) of u,v,x,y and [0,32) of s start as zero (later blocks are cleared as they enter);
 	// stage sf (target, zero padded) and qr (reversed query, zero padded) exactly as :187-188 lay them out
-	for (int i = gl; i < 16 / 4; i += G) { U[i] = 0; V[i] = 0; X[i] = 0; Y[i] = 0; }
-	for (int i = gl; i < 32 / 4; i += G) S[i] = QE2; // S holds s + 2(q+e) (:117): one add less per word and diagonal
+	if (gl < 4) XV[gl] = make_uint4(0u, 0u, 0u, 0u);
+	S[gl] = QE2; // S holds s + 2(q+e) (:117): one add less per word and diagonal
 	bool wild = false; // a code 4 anywhere: only then the score needs the wildcard mask (:219,226)
 	for (int i = gl; i < T16 + 16; i += G) { const uint8_t c = i < tlen ? target[i] : (uint8_t)0; wild |= c == 4; sf[i] = c; }
 	{
-		const int nq = (qlen + 35) & ~3;
-		for (int i = gl; i < nq; i += G) { const uint8_t c = i < qlen ? ksw_query_code(query, qlen - 1 - i) : (uint8_t)0; wild |= c == 4; qr[i] = c; }
+		const int nq = KSW_QR_PAD + ((qlen + 35) & ~3);
+		for (int i = gl; i < nq; i += G) {
+			const int k = i - KSW_QR_PAD;
+			const uint8_t c = (k >= 0 && k < qlen) ? ksw_query_code(query, qlen - 1 - k) : (uint8_t)0; wild |= c == 4; qrp[i] = c;
+		}
 	}
 	wild = __ballot_sync(gmask, wild) & gmask;
 	__syncwarp(gmask);
 
-	int last_st = -1, last_en = -1, en_clr = 15;
+	int last_st = -1, last_en = -1, last_st0 = 0, last_en0 = -1, en_clr = 15;
+	unsigned g_high = 0; // sticky: an exact score came close to the uint16 range
 	for (int r = 0; r < qlen + tlen - 1; ++r) {
 		int st0, en0;
 		ksw_band(r, qlen, tlen, w, st0, en0);
@@ -161,131 +180,162 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 		out.cells += en0 - st0 + 1;
 		if (en > en_clr) { // a 16-lane block enters the band: it must read as never written (calloc); the score overrun zone moves on
 			const int b = en_clr + 1;
-			for (int i = gl; i < 8; i += G) {
-				if (i < 4) { const int wi = ((b >> 2) + i) & rmw; U[wi] = 0; V[wi] = 0; X[wi] = 0; Y[wi] = 0; }
-				else S[(((b + 16) >> 2) + i - 4) & rmw] = QE2;
-			}
+			if (gl < 4) XV[((b >> 2) + gl) & rmw] = make_uint4(0u, 0u, 0u, 0u);
+			else S[(((b + 16) >> 2) + gl - 4) & rmw] = QE2;
 			en_clr += 16;
 			__syncwarp(gmask);
 		}
-		// boundary conditions :207-211 (values of the previous diagonal)
-		int x1, v1;
-		if (st > 0) {
-			if (st - 1 >= last_st && st - 1 <= last_en) { x1 = x[(st - 1) & rm]; v1 = v[(st - 1) & rm]; }
-			else x1 = v1 = 0;
-		} else { x1 = 0; v1 = r ? P.q : 0; }
-		const int bend = st0 + ((en0 - st0) / 16 + 1) * 16; // one past the last lane the 16-wide score blocks write
-		const int w1 = (bend - 1) >> 2, wend = en >> 2, wlast = wend > w1 ? wend : w1, ws0 = st0 >> 2;
-		const int en1 = st0 + (((en0 - st0) >> 2) << 2);    // end of the 4-wide vector part of the arg-max (:316)
-		uint32_t xc = (uint32_t)(x1 & 0xff) << 24, vc = (uint32_t)(v1 & 0xff) << 24;
+		// boundary conditions :207-211 (values of the previous diagonal): the word left of the first one supplies x[st-1], v[st-1]
+		const bool keep_prev = st > 0 && st - 1 >= last_st && st - 1 <= last_en;
+		const uint32_t v1c = (st == 0 && r) ? ((uint32_t)(P.q & 0xff) << 24) : 0u;
+		const int goff = qe * (r + 1) + gbias;
 		// H[en0] is built from the OLD H[en0-1] (:318): fetch it before this diagonal's updates
-		const int hprev_old = r == 0 ? 0 : (en0 > 0 ? H[(en0 - 1) & hmask] : H[en0 & hmask]);
+		unsigned gprev = 0;
+		if (r) {
+			const int c = en0 > 0 ? en0 - 1 : 0;
+			gprev = G16[c & rm];
+			if (c < last_st0 || c > last_en0) { // the column was not part of the previous band: its offset is older (the band left the matrix on the right)
+				int rr = r - 1;
+				for (; rr > 0; --rr) { int s_, e_; ksw_band(rr, qlen, tlen, w, s_, e_); if (s_ <= c && c <= e_) break; }
+				gprev += (unsigned)(qe * (r - 1 - rr));
+			}
+		}
+		const int bend = st0 + ((en0 - st0) / 16 + 1) * 16; // one past the last lane the 16-wide score blocks write
+		const int wfirst = st >> 2, w1 = (bend - 1) >> 2, wend = en >> 2, wlast = wend > w1 ? wend : w1, ws0 = st0 >> 2;
+		const int en1 = st0 + (((en0 - st0) >> 2) << 2);    // end of the 4-wide vector part of the arg-max (:316)
 		const unsigned bandw = (unsigned)(en0 - st0);       // columns st0 .. en0-1 are updated in the loop
-		uint32_t *pr = (uint32_t*)(pmat + (size_t)r * n_col) - (st >> 2);
-		int bh = (int)0x80000000, bt = st0;                  // this thread's best exact score and its column (ties in SSE order)
+		uint32_t *pr = (uint32_t*)(pmat + (size_t)r * n_col) - wfirst;
 		const int rword = en >= r ? (r >> 2) : -1;           // :212, y[r] = 0 and u[r] = q, patched in registers
-		// Words are dealt round-robin: word j of the band goes to thread j % G, so a narrow band (the first and last
-		// diagonals, short targets) costs ceil(words / G) rounds instead of always W.
-		for (int w0 = st >> 2; w0 <= wlast; w0 += G * W) {
-			const int wb = w0 + gl;
-			uint32_t xo[W], vo[W], xp[W], vp[W];
-#pragma unroll
-			for (int k = 0; k < W; ++k) {
-				const bool core = wb + k * G <= wend;
-				xo[k] = core ? X[(wb + k * G) & rmw] : 0u;
-				vo[k] = core ? V[(wb + k * G) & rmw] : 0u;
-			}
-			// neighbour word (columns t-4..t-1 of the previous diagonal): the previous thread in the same round, or thread G-1 of
-			// the round before for thread 0 (the carry of the previous trip / the boundary value for the very first word)
-#pragma unroll
-			for (int k = 0; k < W; ++k) {
-				xp[k] = __shfl_up_sync(gmask, xo[k], 1, G); vp[k] = __shfl_up_sync(gmask, vo[k], 1, G);
-				const uint32_t xw = __shfl_sync(gmask, xo[k ? k - 1 : 0], G - 1, G), vw = __shfl_sync(gmask, vo[k ? k - 1 : 0], G - 1, G);
-				if (gl == 0) { xp[k] = k ? xw : xc; vp[k] = k ? vw : vc; }
-			}
-			xc = __shfl_sync(gmask, xo[W - 1], G - 1, G); vc = __shfl_sync(gmask, vo[W - 1], G - 1, G);
-#pragma unroll
-			for (int k = 0; k < W; ++k) {
-				if (w0 + k * G > wlast) break; // the rest of this trip lies beyond the band (same for the whole group)
-				const int wi = wb + k * G, t = wi << 2;
-				const bool core = wi <= wend, sca = wi >= ws0 && wi <= w1;
-				uint32_t so = (core || sca) ? S[wi & rmw] : 0u;
-				if (sca) { // scores: lanes of this word inside the 16-wide blocks get fresh values, the others keep stale s
-					const uint32_t sq = SF[wi];
-					const int p = qlen - 1 - r + t; // qr index of lane t; negative only for lanes left of st0 (masked below)
-					uint32_t sq2;
-					if (p >= 0) sq2 = __funnelshift_r(QR[p >> 2], QR[(p >> 2) + 1], 8 * (p & 3));
-					else sq2 = p > -4 ? QR[0] << (8 * -p) : 0u;
-					const uint32_t neq = msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu);                                  // 0xff where the codes differ
-					uint32_t sc = sel4(neq, MISQ, MATQ);
-					if (wild) sc = sel4(msb_to_mask4(((sq ^ 0x04040404u) + 0x7f7f7f7fu) & ((sq2 ^ 0x04040404u) + 0x7f7f7f7fu)), sc, QE2); // score 0 where a code is 4
-					const int lo = st0 - t, hi = bend - t; // lanes [lo, hi) of this word belong to the blocks
+		const int cq = qlen - 1 - r;                         // lane t meets query code qr[cq + t]
+		const int qsh = 8 * (cq & 3);
+		const uint32_t *QRr = QRP + (KSW_QR_PAD >> 2) + (cq >> 2);
+		uint32_t bh2 = 0;                                     // this thread's best g over its in-band columns, two uint16 halves
+		// Words are dealt round-robin (word j of the band goes to thread j % G), last round first: every word reads the old
+		// x, v of the word to its left, which belongs to the previous thread of the same round or to a round not yet done.
+		for (int rd = (wlast - wfirst) / G; rd >= 0; --rd) {
+			const int wi = wfirst + rd * G + gl, t = wi << 2, wm = wi & rmw;
+			const bool core = wi <= wend, sca = wi >= ws0 && wi <= w1;
+			uint4 own = make_uint4(0u, 0u, 0u, 0u); uint2 prv = make_uint2(0u, 0u);
+			if (core) { own = XV[wm]; prv = *(const uint2*)&XV[(wi - 1) & rmw]; }
+			__syncwarp(gmask); // every load of the round is issued before any store of the round
+			uint32_t z0 = 0;   // s + 2(q+e)
+			if (sca) { // scores :215-228: lanes of this word inside the 16-wide blocks get fresh values, the others keep stale s
+				const uint32_t sq = SF[wi];
+				const uint32_t sq2 = __funnelshift_r(QRr[wi], QRr[wi + 1], qsh);
+				const uint32_t neq = msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu); // 0xff where the codes differ
+				uint32_t sc = sel4(neq, MISQ, MATQ);
+				if (wild) sc = sel4(msb_to_mask4(((sq ^ 0x04040404u) + 0x7f7f7f7fu) & ((sq2 ^ 0x04040404u) + 0x7f7f7f7fu)), sc, QE2); // score 0 where a code is 4
+				const int lo = st0 - t, hi = bend - t; // lanes [lo, hi) of this word belong to the blocks
+				if (lo <= 0 && hi >= 4) z0 = sc;
+				else {
 					uint32_t m = 0xffffffffu;
-					if (lo > 0) m &= 0xffffffffu << (8 * lo);
+					if (lo > 0) m <<= 8 * lo;
 					if (hi < 4) m &= 0xffffffffu >> (8 * (4 - hi));
-					so = sel4(m, sc, so);
-					S[wi & rmw] = so;
+					z0 = sel4(m, sc, S[wm]);
 				}
-				if (core) {
-					uint32_t ut = U[wi & rmw], yt = Y[wi & rmw];
-					if (wi == rword) {
-						const int b = 8 * (r & 3);
-						yt &= ~(0xffu << b);
-						ut = (ut & ~(0xffu << b)) | ((uint32_t)((r ? P.q : 0) & 0xff) << b);
-					}
-					const uint32_t xt1 = __funnelshift_l(xp[k], xo[k], 8), vt1 = __funnelshift_l(vp[k], vo[k], 8); // lanes t-1..t+2 of the previous diagonal
-					uint32_t z = so;                               // s + 2(q+e)
+				S[wm] = z0;
+			} else if (core) z0 = S[wm];
+			if (core) {
+				if (wi == wfirst && !keep_prev) { prv.x = 0u; prv.y = v1c; }
+				uint32_t ut = own.z, yt = own.w;
+				if (wi == rword) {
+					const int b = 8 * (r & 3);
+					yt &= ~(0xffu << b);
+					ut = (ut & ~(0xffu << b)) | ((uint32_t)((r ? P.q : 0) & 0xff) << b);
+				}
+				const uint32_t xt1 = __funnelshift_l(prv.x, own.x, 8), vt1 = __funnelshift_l(prv.y, own.y, 8); // lanes t-1..t+2 of the previous diagonal
+				uint32_t d, un, vn, xn, yn;
+				if (fast_ok && !((xt1 | vt1 | ut | yt) & 0xc0c0c0c0u)) {
+					// every byte is in [0,63]: sums stay below 128, signed and unsigned compares agree and nothing carries
+					// between bytes, so the core (:262-284) runs on plain 32-bit adds and (a | 0x80) - b compares
+					const uint32_t a = xt1 + vt1, b = yt + ut;
+					uint32_t m = ge4_pos(z0, a);                    // z >= a
+					uint32_t z = sel4(m, z0, a);
+					d = ~m & 0x01010101u;
+					m = ge4_pos(z, b);                              // z >= b
+					d = sel4(m, d, 0x02020202u);
+					z = sel4(m, z, b);
+					z = sel4(ge4_pos(MAXSC, z), z, MAXSC);
+					const uint32_t zh = z | KSW_H80;
+					un = (zh - vt1) ^ KSW_H80; vn = (zh - ut) ^ KSW_H80;
+					z -= Q4;
+					m = ge4_pos(z, a);                              // z >= a: x = 0
+					xn = sel4(m, z, a) - z; d |= ~m & 0x08080808u;
+					m = ge4_pos(z, b);
+					yn = sel4(m, z, b) - z; d |= ~m & 0x10101010u;
+				} else {
+					uint32_t z = z0;
 					uint32_t a = __vadd4(xt1, vt1);
 					uint32_t b = __vadd4(yt, ut);
 					uint32_t m = __vcmpgts4(a, z);                 // a > z (signed)
-					uint32_t d = m & 0x01010101u;
+					d = m & 0x01010101u;
 					z = sel4(m, a, z);                             // signed max
 					m = __vcmpgts4(b, z);                          // b > z (signed)
 					d = sel4(m, 0x02020202u, d);
 					z = sel4(__vcmpgtu4(b, z), b, z);              // unsigned max
 					z = sel4(__vcmpgtu4(z, MAXSC), MAXSC, z);      // unsigned min
-					const uint32_t vn = __vsub4(z, ut);
-					U[wi & rmw] = __vsub4(z, vt1); V[wi & rmw] = vn;
+					vn = __vsub4(z, ut); un = __vsub4(z, vt1);
 					z = __vsub4(z, Q4);
 					a = __vsub4(a, z);
 					b = __vsub4(b, z);
 					m = __vcmpgts4(a, 0u);
-					X[wi & rmw] = a & m; d |= m & 0x08080808u;
+					xn = a & m; d |= m & 0x08080808u;
 					m = __vcmpgts4(b, 0u);
-					Y[wi & rmw] = b & m; d |= m & 0x10101010u;
-					pr[wi] = d;
-					if (t + 3 >= st0 && t < en0) { // exact H of the in-band columns st0 .. en0-1 of this word (:323-348): H[t] += v8[t] - qe
-						const int4 hq = H4[(t & hmask) >> 2];
-						int hv[4] = {hq.x, hq.y, hq.z, hq.w};
-#pragma unroll
-						for (int c = 0; c < 4; ++c) {
-							const int tc = t + c;
-							const bool in = (unsigned)(tc - st0) < bandw;
-							const int h = hv[c] + (int)((vn >> (8 * c)) & 0xff) - qe;
-							const bool gt = in && h > bh;
-							if (in && h == bh && ksw_tie_rank(tc, st0, en1) < ksw_tie_rank(bt, st0, en1)) bt = tc; // rare
-							hv[c] = in ? h : hv[c];
-							bt = gt ? tc : bt;
-							bh = gt ? h : bh;
-						}
-						H4[(t & hmask) >> 2] = make_int4(hv[0], hv[1], hv[2], hv[3]);
+					yn = b & m; d |= m & 0x10101010u;
+				}
+				XV[wm] = make_uint4(xn, vn, un, yn);
+				pr[wi] = d;
+				const int lo = st0 - t, hi = en0 - t; // exact scores of the in-band columns st0 .. en0-1 of this word (:323-348): g[t] += v8[t]
+				if (hi > 0 && lo < 4) {
+					uint2 g2 = GR[wm];
+					if (lo <= 0 && hi >= 4) {
+						g2.x += __byte_perm(vn, 0u, 0x4140); g2.y += __byte_perm(vn, 0u, 0x4342);
+						bh2 = __vimax3_u16x2(bh2, g2.x, g2.y);
+					} else {
+						uint32_t m = 0xffffffffu;
+						if (lo > 0) m <<= 8 * lo;
+						if (hi < 4) m &= 0xffffffffu >> (8 * (4 - hi));
+						const uint32_t vm = vn & m;
+						g2.x += __byte_perm(vm, 0u, 0x4140); g2.y += __byte_perm(vm, 0u, 0x4342);
+						bh2 = __vimax3_u16x2(bh2, g2.x & __byte_perm(m, 0u, 0x1100), g2.y & __byte_perm(m, 0u, 0x3322));
 					}
+					GR[wm] = g2;
 				}
 			}
 		}
-		__syncwarp(gmask); // this diagonal's lanes and H[st0..en0) are visible to the whole group
+		__syncwarp(gmask); // this diagonal's lanes and g[st0..en0) are visible to the whole group
 		// the en0 cell, :318 / :349
-		int hen;
-		if (r == 0) hen = (int)(uint8_t)v[0] - qe - qe;
-		else hen = hprev_old + (int)(uint8_t)(en0 > 0 ? u[en0 & rm] : v[en0 & rm]) - qe;
+		unsigned ghen;
+		if (r == 0) ghen = (unsigned)((int)((const uint8_t*)&XV[0])[4] - qe + gbias); // H[0] = v[0] - 2(q+e)
+		else {
+			const uint8_t *wb = (const uint8_t*)&XV[(en0 >> 2) & rmw];
+			ghen = gprev + (unsigned)(en0 > 0 ? wb[8 + (en0 & 3)] : wb[4 + (en0 & 3)]); // + u8[en0] or + v8[en0]
+		}
+		const int hen = (int)ghen - goff;
+		unsigned mg = (bh2 & 0xffffu) > (bh2 >> 16) ? (bh2 & 0xffffu) : (bh2 >> 16);
+		mg = __reduce_max_sync(gmask, mg);
+		g_high |= (mg | ghen) >= 0xF000u;
+		const int mh = (int)mg - goff;
 		int max_H, max_t;
-		{
-			const unsigned mk = __reduce_max_sync(gmask, (unsigned)bh ^ 0x80000000u);
-			const int mh = (int)(mk ^ 0x80000000u);
-			if (hen >= mh) { max_H = hen; max_t = en0; } // the initial candidate (H[en0], en0) wins every tie (:318-321)
-			else { // several threads may hold the max: the SSE tie order decides
-				max_H = mh;
-				const unsigned rk = __reduce_min_sync(gmask, bh == mh ? ksw_tie_rank(bt, st0, en1) : 0xffffffffu);
+		bool have_t = true;
+		if (hen >= mh) { max_H = hen; max_t = en0; } // the initial candidate (H[en0], en0) wins every tie (:318-321)
+		else {
+			// The position of the band max matters only when it becomes the new overall max or when z-drop can fire
+			// (ksw_apply_zdrop :88-104 needs max - H > zdrop at least); only then look it up, in the SSE tie order.
+			max_H = mh; max_t = en0;
+			have_t = mh > out.max || (P.zdrop >= 0 && out.max - mh > P.zdrop);
+			if (have_t) {
+				unsigned best = 0xffffffffu;
+				for (int wi = ws0 + gl; wi <= ((en0 - 1) >> 2); wi += G) {
+					const uint2 g2 = GR[wi & rmw];
+					const int t = wi << 2;
+#pragma unroll
+					for (int c = 0; c < 4; ++c) {
+						const unsigned val = ((c < 2 ? g2.x : g2.y) >> (16 * (c & 1))) & 0xffffu;
+						if ((unsigned)(t + c - st0) < bandw && val == mg) { const unsigned rk = ksw_tie_rank(t + c, st0, en1); best = rk < best ? rk : best; }
+					}
+				}
+				const unsigned rk = __reduce_min_sync(gmask, best);
 				max_t = st0 + (int)((rk - 1) & 0xfffffu);
 			}
 		}
@@ -294,12 +344,12 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 			if (r == qlen + tlen - 2) out.score = hen; // H[tlen-1]
 		}
 		if (r - st0 == qlen - 1) {
-			const int Hst0 = st0 == en0 ? hen : H[st0 & hmask];
+			const int Hst0 = st0 == en0 ? hen : (int)G16[st0 & rm] - goff;
 			if (Hst0 > out.mqe) { out.mqe = Hst0; out.mqe_t = st0; }
 		}
-		if (gl == 0) H[en0 & hmask] = hen;
+		if (gl == 0) G16[en0 & rm] = (uint16_t)ghen;
 		__syncwarp(gmask);
-		{ // ksw_apply_zdrop :88-104
+		if (have_t) { // ksw_apply_zdrop :88-104
 			bool stop = false;
 			if (max_H > out.max) { out.max = max_H; out.max_t = max_t; out.max_q = r - max_t; }
 			else if (max_t >= out.max_t && r - max_t >= out.max_q) {
@@ -309,8 +359,9 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 			}
 			if (stop) break;
 		}
-		last_st = st; last_en = en;
+		last_st = st; last_en = en; last_st0 = st0; last_en0 = en0;
 	}
+	if (g_high) out.status = KSW_ST_HCAP;
 	__syncwarp(gmask);
 	// backtrack :380-385 -> ksw_backtrack :47-79 (is_rot = 1, left-aligned gaps)
 	int i, j;

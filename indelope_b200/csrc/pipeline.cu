@@ -350,9 +350,9 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 	g.seq_spill = (uint8_t*)L.seq_spill.p; g.seq_spill_cap = seq_spill_cap;
 	const size_t smem_limit = 200 * 1024;
 	if (b->n_regions > 0 && (P.stages & IDL_STAGE_ALIGN)) {
-		g.ring_cols = ksw_ring_cols(ncolA); g.hr = ksw_h_ring(ncolA);
+		g.ring_cols = ksw_ring_cols(ncolA);
 		g.seq_cap = (int)round_up(ksw_seq_bytes(std::min(P.max_contig_len, 1024), (int)max_ref), 16); // longer contigs stage in the spill area
-		const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(g.ring_cols, g.hr, g.seq_cap);
+		const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(g.ring_cols, g.seq_cap);
 		if (smem > smem_limit) return IDL_E_CAPACITY;
 		sort_scan_kernel<<<1, SORT_BUCKETS, 0, L.stream>>>(sA);
 		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(sA, &a.cnt->n_alns, 1u, L.cap_alns);
@@ -364,9 +364,9 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 		kmer_kernel<<<ctx->n_sm * 8, KMER_THREADS, 0, L.stream>>>(g);
 		CK(cudaGetLastError()); L.launches++;
 		CK(cudaEventRecord(L.ev[EV_KMER], L.stream));
-		g.ring_cols = ksw_ring_cols(ncolB); g.hr = ksw_h_ring(ncolB);
+		g.ring_cols = ksw_ring_cols(ncolB);
 		g.seq_cap = (int)round_up(ksw_seq_bytes(max_trim, (int)max_ref), 16);
-		const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(g.ring_cols, g.hr, g.seq_cap);
+		const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(g.ring_cols, g.seq_cap);
 		if (smem > smem_limit) return IDL_E_CAPACITY;
 		al_prep_kernel<<<ctx->n_sm * 8, 256, 0, L.stream>>>(g);
 		sort_scan_kernel<<<1, SORT_BUCKETS, 0, L.stream>>>(sB);
@@ -527,22 +527,18 @@ struct KswBatchArgs {
 	unsigned n; const uint8_t *query, *target; const unsigned long long *q_off, *t_off;
 	KswParams kp; idl_ez *out; uint32_t *cigar; unsigned long long *cigar_off; unsigned cigar_cap;
 	unsigned *next; unsigned *cig_used;
-	uint8_t *pmat; size_t p_cap; uint32_t *cig_scratch; int cig_cap; int ring_cols, hr, seq_cap;
+	uint8_t *pmat; size_t p_cap; uint32_t *cig_scratch; int cig_cap; int ring_cols, seq_cap;
 };
 
-template <int W>
 __global__ void __launch_bounds__(DP_THREADS, 2) ksw2_batch_kernel(KswBatchArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;
 	const int cg = warp_id() * DP_NG + grp;
-	const size_t per = ksw_group_smem(a.ring_cols, a.hr, a.seq_cap);
+	const size_t per = ksw_group_smem(a.ring_cols, a.seq_cap);
 	const size_t gg = (size_t)blockIdx.x * (DP_WARPS * DP_NG) + cg;
 	KswMem M;
-	unsigned char *gbase = smem_raw + per * cg;
-	M.lanes = (int8_t*)(gbase + ksw_group_stagger(grp, W)); M.ring_cols = a.ring_cols;
-	M.H = (int*)(gbase + ksw_group_h_off(a.ring_cols)); M.hr = a.hr;
-	M.seq = gbase + ksw_group_h_off(a.ring_cols) + a.hr * 4; M.seq_cap = a.seq_cap;
+	ksw_group_mem(M, smem_raw + per * cg, grp, a.ring_cols); M.seq_cap = a.seq_cap;
 	M.pmat = a.pmat + gg * a.p_cap; M.p_cap = a.p_cap;
 	M.cig = a.cig_scratch + gg * (size_t)a.cig_cap; M.cig_cap = a.cig_cap;
 	for (;;) {
@@ -555,7 +551,7 @@ __global__ void __launch_bounds__(DP_THREADS, 2) ksw2_batch_kernel(KswBatchArgs 
 			const int qlen = (int)(a.q_off[i + 1] - a.q_off[i]), tlen = (int)(a.t_off[i + 1] - a.t_off[i]);
 			KswQuery kq; kq.codes = a.query + a.q_off[i]; kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
 			KswOut o;
-			ksw2_group<DP_G, W>(qlen, kq, tlen, a.target + a.t_off[i], a.kp, M, o);
+			ksw2_group<DP_G>(qlen, kq, tlen, a.target + a.t_off[i], a.kp, M, o);
 			const unsigned gmask = ((1u << DP_G) - 1u) << (lane & ~(DP_G - 1));
 			unsigned coff = 0;
 			if (gl == 0) coff = atomicAdd(a.cig_used, (unsigned)o.n_cigar);
@@ -593,14 +589,12 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 	}
 	KswBatchArgs a; memset(&a, 0, sizeof a);
 	a.n = (unsigned)n; a.kp.match = match; a.kp.mismatch = mismatch; a.kp.q = gapo; a.kp.e = gape; a.kp.w = w; a.kp.zdrop = zdrop;
-	a.ring_cols = ksw_ring_cols(max_ncol); a.hr = ksw_h_ring(max_ncol);
+	a.ring_cols = ksw_ring_cols(max_ncol);
 	a.p_cap = round_up(max_p + 2 * KSW_PMAT_PAD + 64, 256); a.cig_cap = max_q + max_t + 8; a.cigar_cap = (unsigned)cigar_cap;
 	a.seq_cap = (int)round_up(ksw_seq_bytes(max_q, max_t), 16);
-	const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(a.ring_cols, a.hr, a.seq_cap);
+	const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(a.ring_cols, a.seq_cap);
 	if (smem > 200 * 1024) return IDL_E_CAPACITY;
-	const bool narrow = max_ncol <= DP_G * DP_W_A * 4 - 16;
-	if (narrow) cudaFuncSetAttribute(ksw2_batch_kernel<DP_W_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-	else cudaFuncSetAttribute(ksw2_batch_kernel<DP_W_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(ksw2_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	const size_t per_cta = (size_t)DP_WARPS * DP_NG;
 	const int ctas = (int)std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)ctx->n_sm * 2);
 	const size_t nwarps = (size_t)ctas * per_cta; // groups, each with its own workspace
@@ -621,8 +615,7 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 		a.next = (unsigned*)dmisc.p; a.cig_used = (unsigned*)dmisc.p + 1; a.pmat = (uint8_t*)dp.p; a.cig_scratch = (uint32_t*)dscr.p;
 		CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 		CK(cudaEventRecord(e0, st));
-		if (narrow) ksw2_batch_kernel<DP_W_A><<<ctas, DP_THREADS, smem, st>>>(a);
-		else ksw2_batch_kernel<DP_W_B><<<ctas, DP_THREADS, smem, st>>>(a);
+		ksw2_batch_kernel<<<ctas, DP_THREADS, smem, st>>>(a);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(e1, st));
 		CK(cudaMemcpyAsync(out, dout.p, n * sizeof(idl_ez), cudaMemcpyDeviceToHost, st));

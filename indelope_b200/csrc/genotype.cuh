@@ -110,7 +110,7 @@ __device__ __forceinline__ int distinct_k(const uint8_t *a, int K)
 // ---------------------------------------------------------------------------------------------------------------
 // call-site A + glue: one group of DP_G threads per alignment, DP_NG alignments per warp
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DP_THREADS, 2) align_kernel(GenoArgs g)
+__global__ void __launch_bounds__(DP_THREADS, 3) align_kernel(GenoArgs g)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;
@@ -375,7 +375,7 @@ __device__ __forceinline__ int count_flanked(const uint32_t *cig_rev, int n, int
 }
 
 // AL fallback, step 2: call-site B of kernel 2, one group per task (read vs reference suffix / contig suffix), :343-347
-__global__ void __launch_bounds__(DP_THREADS, 2) al_kernel(GenoArgs g)
+__global__ void __launch_bounds__(DP_THREADS, 3) al_kernel(GenoArgs g)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;

@@ -52,11 +52,12 @@ __host__ __device__ inline int ksw_ncol(int qlen, int tlen, int w)
 }
 // ring of lane columns: the rounded band, the column left of it, 16 lanes of score overrun and the 16 being cleared
 __host__ __device__ inline int ksw_ring_cols(int ncol) { int r = 64; while (r < ncol + 48) r <<= 1; return r; }
-// bytes of sequence staging: zero-padded target (sf) and reversed, zero-padded query (qr); doubles as the backtrack tile
+// bytes of query staging: KSW_QR_PAD zero bytes, the reversed query, zero padding (:188).  The target is not staged as a
+// whole: a ring over the live band is filled from global memory as 16-lane blocks enter.
 __host__ __device__ inline size_t ksw_seq_bytes(int qlen, int tlen)
 {
-	size_t b = (size_t)(((tlen + 15) & ~15) + 16) + (size_t)(KSW_QR_PAD + ((qlen + 35) & ~3));
-	return b < KSW_BTILE_BYTES ? KSW_BTILE_BYTES : b;
+	(void)tlen;
+	return (size_t)(KSW_QR_PAD + ((qlen + 35) & ~3));
 }
 
 // off[r] / off_end[r] of the reference are pure functions of r (:196-199,205)
@@ -96,27 +97,41 @@ __device__ __forceinline__ uint8_t ksw_query_code(const KswQuery &q, int i)
 	return ((q.seqn[b >> 5] >> (b & 31)) & 1u) ? (uint8_t)4 : (uint8_t)((q.seq2[b >> 4] >> (2 * (b & 15))) & 3u);
 }
 
-// Memory of one group.  Shared memory: xvuy = ring of {x, v, u, y} packed words (16 bytes per 4 columns, one 128-bit load
-// and store per word and diagonal), g = ring of the exact scores as uint16 (8 bytes per 4 columns), S = ring of the score
-// words, all three indexed by (column word & mask) of the same ring; seq = sequence staging (reused as the backtrack tile).
-// Global memory: pmat = backtrack matrix workspace, cig = CIGAR scratch.
-struct KswMem { uint4 *xvuy; uint2 *g; uint32_t *S; int ring_cols; uint8_t *seq; int seq_cap; uint8_t *pmat; size_t p_cap; uint32_t *cig; int cig_cap; };
-// layout of a group's region (a multiple of 128 bytes): [xvuy 4R][g 2R + 64 bytes of stagger slack][S R + 128 of slack][64 pad][seq]
-__host__ __device__ inline size_t ksw_group_seq_off(int ring_cols) { return (size_t)7 * ring_cols + 256; }
+// Memory of one group.  Shared memory, four rings over the live band indexed by ((column word + rot) & mask): xvuy =
+// {x, v, u, y} packed words (16 bytes per 4 columns, one 128-bit load and store per word and diagonal), g = the exact
+// scores as uint16 (8 bytes per 4 columns), S = score words, T = target codes; then seq = the query staging.  The start
+// of the region doubles as the backtrack tile once the DP is over.  Global memory: pmat = backtrack matrix workspace,
+// cig = CIGAR scratch.
+// Bank staggering: a 128-bit access is served one group (8 threads x 16 contiguous bytes) at a time, so xvuy needs none;
+// the 64-bit accesses to g pair two groups and the 32-bit accesses to S and T put all four groups of a warp into one
+// wavefront: group k of the warp rotates its rings by 8k words, so that groups at the same relative column fall into
+// different banks without any slack bytes.
+struct KswMem { uint4 *xvuy; uint2 *g; uint32_t *S, *T; int ring_cols, rot; uint8_t *seq; int seq_cap; uint8_t *pmat; size_t p_cap; uint32_t *cig; int cig_cap; };
+// layout of a group's region (a multiple of 128 bytes): [xvuy 4R][g 2R][S R][T R][seq]
+__host__ __device__ inline size_t ksw_group_seq_off(int ring_cols) { return (size_t)8 * ring_cols; }
 __host__ __device__ inline size_t ksw_group_smem(int ring_cols, int seq_cap)
 {
-	return (ksw_group_seq_off(ring_cols) + (size_t)((seq_cap + 15) & ~15) + 127) & ~(size_t)127;
+	size_t b = ksw_group_seq_off(ring_cols) + (size_t)((seq_cap + 15) & ~15);
+	if (b < KSW_BTILE_BYTES) b = KSW_BTILE_BYTES;
+	return (b + 127) & ~(size_t)127;
 }
-// Bank staggering: a 128-bit access is served one group (8 threads x 16 contiguous bytes) at a time, so xvuy needs none; the
-// 64-bit accesses to g pair two groups and the 32-bit accesses to S put all four groups of a warp into one wavefront:
-// their bases are shifted so that groups at the same relative column fall into different banks.
 __device__ __forceinline__ void ksw_group_mem(KswMem &m, unsigned char *base, int grp_in_warp, int ring_cols)
 {
-	m.xvuy = (uint4*)base; m.ring_cols = ring_cols;
-	m.g = (uint2*)(base + (size_t)4 * ring_cols + 64 * (grp_in_warp & 1));
-	m.S = (uint32_t*)(base + (size_t)6 * ring_cols + 64 + 32 * (grp_in_warp & 3));
+	m.xvuy = (uint4*)base; m.ring_cols = ring_cols; m.rot = 8 * (grp_in_warp & 3);
+	m.g = (uint2*)(base + (size_t)4 * ring_cols);
+	m.S = (uint32_t*)(base + (size_t)6 * ring_cols);
+	m.T = (uint32_t*)(base + (size_t)7 * ring_cols);
 	m.seq = base + ksw_group_seq_off(ring_cols);
 }
+// four target codes starting at column t, zero beyond the end (:187)
+__device__ __forceinline__ uint32_t ksw_target_word(const uint8_t *target, int tlen, int t)
+{
+	uint32_t w = 0;
+#pragma unroll
+	for (int c = 0; c < 4; ++c) if (t + c < tlen) w |= (uint32_t)target[t + c] << (8 * c);
+	return w;
+}
+__device__ __forceinline__ bool ksw_has4(uint32_t w) { const uint32_t x = w ^ 0x04040404u; return ((x - 0x01010101u) & ~x & 0x80808080u) != 0u; }
 
 // The G threads of a group call this with identical arguments; `out` comes back identical in each of them.
 template <int G>
@@ -134,7 +149,6 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 	if (-min_sc > 2 * qe) { out.status = KSW_ST_EARLY; return; } // :171
 	int w = P.w;
 	if (w < 0) w = tlen > qlen ? tlen : qlen; // :161
-	const int T16 = (tlen + 15) & ~15;
 	const int n_col = ksw_ncol(qlen, tlen, w); // :164-165 (bytes)
 	if (ksw_ring_cols(n_col) > M.ring_cols) { out.status = KSW_ST_RCAP; return; }
 	if (ksw_seq_bytes(qlen, tlen) > (size_t)M.seq_cap) { out.status = KSW_ST_SEQCAP; return; }
@@ -145,21 +159,21 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 	const int gbias = 2 * qe;
 	if ((long long)(qlen + tlen + 2) * qe + (long long)(qlen < tlen ? qlen : tlen) * (P.match > 0 ? P.match : 0) + gbias >= 0xF000) { out.status = KSW_ST_HCAP; return; }
 	uint8_t *pmat = M.pmat + KSW_PMAT_PAD;
-	const int rm = M.ring_cols - 1, rmw = (M.ring_cols >> 2) - 1;
-	uint4 *XV = M.xvuy; uint2 *GR = M.g; uint32_t *S = M.S;
+	const int rm = M.ring_cols - 1, rmw = (M.ring_cols >> 2) - 1, rotw = M.rot, rotc = M.rot << 2;
+	uint4 *XV = M.xvuy; uint2 *GR = M.g; uint32_t *S = M.S, *SF = M.T;
 	uint16_t *G16 = (uint16_t*)M.g;
-	uint8_t *sf = M.seq, *qrp = M.seq + T16 + 16; // qrp: KSW_QR_PAD zero bytes, then the reversed query, zero padded
-	const uint32_t *SF = (const uint32_t*)sf, *QRP = (const uint32_t*)qrp;
+	uint8_t *qrp = M.seq; // KSW_QR_PAD zero bytes, then the reversed query, zero padded
+	const uint32_t *QRP = (const uint32_t*)qrp;
 	const uint32_t QE2 = rep4(qe * 2), MAXSC = rep4(P.match + qe * 2), Q4 = rep4(P.q), MATQ = rep4(P.match + qe * 2), MISQ = rep4(P.mismatch + qe * 2);
 	// the carry-free formulation of the core needs every constant and every input byte small and non-negative
 	const bool fast_ok = P.match + 2 * qe <= 63 && P.q >= 0 && P.q + 2 * P.e + min_sc >= 0;
 
 	// calloc :173: columns [0,16) of u,v,x,y and [0,32) of s start as zero (later blocks are cleared as they enter);
-	// stage sf (target, zero padded) and qr (reversed query, zero padded) exactly as :187-188 lay them out
-	if (gl < 4) XV[gl] = make_uint4(0u, 0u, 0u, 0u);
-	S[gl] = QE2; // S holds s + 2(q+e) (:117): one add less per word and diagonal
-	bool wild = false; // a code 4 anywhere: only then the score needs the wildcard mask (:219,226)
-	for (int i = gl; i < T16 + 16; i += G) { const uint8_t c = i < tlen ? target[i] : (uint8_t)0; wild |= c == 4; sf[i] = c; }
+	// stage the first 32 target codes (zero padded, :187) and qr (reversed query, zero padded, :188)
+	if (gl < 4) XV[(gl + rotw) & rmw] = make_uint4(0u, 0u, 0u, 0u);
+	S[(gl + rotw) & rmw] = QE2; // S holds s + 2(q+e) (:117): one add less per word and diagonal
+	bool wild; // a code 4 seen so far: only then the score needs the wildcard mask (:219,226)
+	{ const uint32_t tw = ksw_target_word(target, tlen, 4 * gl); SF[(gl + rotw) & rmw] = tw; wild = ksw_has4(tw); }
 	{
 		const int nq = KSW_QR_PAD + ((qlen + 35) & ~3);
 		for (int i = gl; i < nq; i += G) {
@@ -167,7 +181,7 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 			const uint8_t c = (k >= 0 && k < qlen) ? ksw_query_code(query, qlen - 1 - k) : (uint8_t)0; wild |= c == 4; qrp[i] = c;
 		}
 	}
-	wild = __ballot_sync(gmask, wild) & gmask;
+	wild = (__ballot_sync(gmask, wild) & gmask) != 0u;
 	__syncwarp(gmask);
 
 	int last_st = -1, last_en = -1, last_st0 = 0, last_en0 = -1, en_clr = 15;
@@ -180,8 +194,14 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 		out.cells += en0 - st0 + 1;
 		if (en > en_clr) { // a 16-lane block enters the band: it must read as never written (calloc); the score overrun zone moves on
 			const int b = en_clr + 1;
-			if (gl < 4) XV[((b >> 2) + gl) & rmw] = make_uint4(0u, 0u, 0u, 0u);
-			else S[(((b + 16) >> 2) + gl - 4) & rmw] = QE2;
+			bool w4 = false;
+			if (gl < 4) XV[((b >> 2) + gl + rotw) & rmw] = make_uint4(0u, 0u, 0u, 0u);
+			else { // ... and the next 16 target codes are fetched
+				const int wn = ((b + 16) >> 2) + gl - 4;
+				const uint32_t tw = ksw_target_word(target, tlen, wn << 2);
+				S[(wn + rotw) & rmw] = QE2; SF[(wn + rotw) & rmw] = tw; w4 = ksw_has4(tw);
+			}
+			wild |= (__ballot_sync(gmask, w4) & gmask) != 0u;
 			en_clr += 16;
 			__syncwarp(gmask);
 		}
@@ -193,7 +213,7 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 		unsigned gprev = 0;
 		if (r) {
 			const int c = en0 > 0 ? en0 - 1 : 0;
-			gprev = G16[c & rm];
+			gprev = G16[(c + rotc) & rm];
 			if (c < last_st0 || c > last_en0) { // the column was not part of the previous band: its offset is older (the band left the matrix on the right)
 				int rr = r - 1;
 				for (; rr > 0; --rr) { int s_, e_; ksw_band(rr, qlen, tlen, w, s_, e_); if (s_ <= c && c <= e_) break; }
@@ -213,14 +233,14 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 		// Words are dealt round-robin (word j of the band goes to thread j % G), last round first: every word reads the old
 		// x, v of the word to its left, which belongs to the previous thread of the same round or to a round not yet done.
 		for (int rd = (wlast - wfirst) / G; rd >= 0; --rd) {
-			const int wi = wfirst + rd * G + gl, t = wi << 2, wm = wi & rmw;
+			const int wi = wfirst + rd * G + gl, t = wi << 2, wm = (wi + rotw) & rmw;
 			const bool core = wi <= wend, sca = wi >= ws0 && wi <= w1;
 			uint4 own = make_uint4(0u, 0u, 0u, 0u); uint2 prv = make_uint2(0u, 0u);
-			if (core) { own = XV[wm]; prv = *(const uint2*)&XV[(wi - 1) & rmw]; }
+			if (core) { own = XV[wm]; prv = *(const uint2*)&XV[(wm - 1) & rmw]; }
 			__syncwarp(gmask); // every load of the round is issued before any store of the round
 			uint32_t z0 = 0;   // s + 2(q+e)
 			if (sca) { // scores :215-228: lanes of this word inside the 16-wide blocks get fresh values, the others keep stale s
-				const uint32_t sq = SF[wi];
+				const uint32_t sq = SF[wm];
 				const uint32_t sq2 = __funnelshift_r(QRr[wi], QRr[wi + 1], qsh);
 				const uint32_t neq = msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu); // 0xff where the codes differ
 				uint32_t sc = sel4(neq, MISQ, MATQ);
@@ -306,9 +326,9 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 		__syncwarp(gmask); // this diagonal's lanes and g[st0..en0) are visible to the whole group
 		// the en0 cell, :318 / :349
 		unsigned ghen;
-		if (r == 0) ghen = (unsigned)((int)((const uint8_t*)&XV[0])[4] - qe + gbias); // H[0] = v[0] - 2(q+e)
+		if (r == 0) ghen = (unsigned)((int)((const uint8_t*)&XV[rotw & rmw])[4] - qe + gbias); // H[0] = v[0] - 2(q+e)
 		else {
-			const uint8_t *wb = (const uint8_t*)&XV[(en0 >> 2) & rmw];
+			const uint8_t *wb = (const uint8_t*)&XV[((en0 >> 2) + rotw) & rmw];
 			ghen = gprev + (unsigned)(en0 > 0 ? wb[8 + (en0 & 3)] : wb[4 + (en0 & 3)]); // + u8[en0] or + v8[en0]
 		}
 		const int hen = (int)ghen - goff;
@@ -327,7 +347,7 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 			if (have_t) {
 				unsigned best = 0xffffffffu;
 				for (int wi = ws0 + gl; wi <= ((en0 - 1) >> 2); wi += G) {
-					const uint2 g2 = GR[wi & rmw];
+					const uint2 g2 = GR[(wi + rotw) & rmw];
 					const int t = wi << 2;
 #pragma unroll
 					for (int c = 0; c < 4; ++c) {
@@ -344,10 +364,10 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 			if (r == qlen + tlen - 2) out.score = hen; // H[tlen-1]
 		}
 		if (r - st0 == qlen - 1) {
-			const int Hst0 = st0 == en0 ? hen : (int)G16[st0 & rm] - goff;
+			const int Hst0 = st0 == en0 ? hen : (int)G16[(st0 + rotc) & rm] - goff;
 			if (Hst0 > out.mqe) { out.mqe = Hst0; out.mqe_t = st0; }
 		}
-		if (gl == 0) G16[en0 & rm] = (uint16_t)ghen;
+		if (gl == 0) G16[(en0 + rotc) & rm] = (uint16_t)ghen;
 		__syncwarp(gmask);
 		if (have_t) { // ksw_apply_zdrop :88-104
 			bool stop = false;
@@ -374,7 +394,7 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 		// group prefetches the 32 x 32 tile of p[][] the path can touch (row r0-k can only be entered at columns
 		// i0-k .. i0) into shared memory (the sequence staging area is free by now), so the walker runs on shared-memory
 		// latency instead of one L2/HBM round trip per step.
-		uint32_t *tile = (uint32_t*)M.seq; // 32 rows of 8 words
+		uint32_t *tile = (uint32_t*)M.xvuy; // 32 rows of 8 words; the rings are dead by now
 		uint32_t *cig = M.cig; const int cig_cap = M.cig_cap;
 		int state = 0;
 		unsigned cur_op = 0xffu, cur_len = 0;

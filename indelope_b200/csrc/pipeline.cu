@@ -97,6 +97,14 @@ size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
+// persistent kernel-2 grids: as many CTAs as fit on the device at this shared-memory size, at most ctx->dp_ctas (the workspaces are sized for that)
+int dp_grid(const idl_ctx *ctx, const void *kernel, size_t smem)
+{
+	int nb = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, smem) != cudaSuccess || nb < 1) nb = 1;
+	return std::min(ctx->dp_ctas, ctx->n_sm * nb);
+}
+
 } // namespace
 
 extern "C" {
@@ -162,7 +170,7 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	// persistent grids: CTAs per SM (tunable for experiments through the environment)
 	const char *ea = getenv("IDL_ASM_CTAS_PER_SM"), *ed = getenv("IDL_DP_CTAS_PER_SM");
 	ctx->asm_ctas = ctx->n_sm * (ea && atoi(ea) > 0 ? atoi(ea) : 4); // CTAs of each assembler launch (8 regions per CTA in the warp variant)
-	ctx->dp_ctas = ctx->n_sm * (ed && atoi(ed) > 0 ? atoi(ed) : 2);
+	ctx->dp_ctas = ctx->n_sm * (ed && atoi(ed) > 0 ? atoi(ed) : 3); // upper bound; every launch asks the occupancy calculator
 	ctx->lanes.resize((size_t)p->n_streams);
 	for (Lane &L : ctx->lanes) {
 		if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { idl_destroy(ctx); return IDL_E_CUDA; }
@@ -356,7 +364,7 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 		if (smem > smem_limit) return IDL_E_CAPACITY;
 		sort_scan_kernel<<<1, SORT_BUCKETS, 0, L.stream>>>(sA);
 		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(sA, &a.cnt->n_alns, 1u, L.cap_alns);
-		align_kernel<<<ctx->dp_ctas, DP_THREADS, smem, L.stream>>>(g);
+		align_kernel<<<dp_grid(ctx, (const void*)align_kernel, smem), DP_THREADS, smem, L.stream>>>(g);
 		CK(cudaGetLastError()); L.launches += 3;
 	}
 	CK(cudaEventRecord(L.ev[EV_ALN], L.stream));
@@ -371,7 +379,7 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 		al_prep_kernel<<<ctx->n_sm * 8, 256, 0, L.stream>>>(g);
 		sort_scan_kernel<<<1, SORT_BUCKETS, 0, L.stream>>>(sB);
 		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(sB, &a.cnt->n_al_items, 2u, 2 * L.cap_items);
-		al_kernel<<<ctx->dp_ctas, DP_THREADS, smem, L.stream>>>(g);
+		al_kernel<<<dp_grid(ctx, (const void*)al_kernel, smem), DP_THREADS, smem, L.stream>>>(g);
 		al_vote_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(g);
 		CK(cudaGetLastError()); L.launches += 5;
 	} else CK(cudaEventRecord(L.ev[EV_KMER], L.stream));
@@ -530,7 +538,7 @@ struct KswBatchArgs {
 	uint8_t *pmat; size_t p_cap; uint32_t *cig_scratch; int cig_cap; int ring_cols, seq_cap;
 };
 
-__global__ void __launch_bounds__(DP_THREADS, 2) ksw2_batch_kernel(KswBatchArgs a)
+__global__ void __launch_bounds__(DP_THREADS, 3) ksw2_batch_kernel(KswBatchArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;
@@ -596,7 +604,7 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 	if (smem > 200 * 1024) return IDL_E_CAPACITY;
 	cudaFuncSetAttribute(ksw2_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	const size_t per_cta = (size_t)DP_WARPS * DP_NG;
-	const int ctas = (int)std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)ctx->n_sm * 2);
+	const int ctas = (int)std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)dp_grid(ctx, (const void*)ksw2_batch_kernel, smem));
 	const size_t nwarps = (size_t)ctas * per_cta; // groups, each with its own workspace
 	const size_t qbytes = q_off[n], tbytes = t_off[n];
 	DevBuf dq, dt, dqo, dto, dout, dcig, dcoff, dmisc, dp, dscr;

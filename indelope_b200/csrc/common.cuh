@@ -29,7 +29,20 @@ struct DevCounters {
 struct KswParams {
 	int8_t match, mismatch, q, e;
 	int w, zdrop;
+	// byte-replicated constants of the int8 recurrence, made once on the host so that the kernels read them straight from
+	// the constant bank: 2(q+e), match + 2(q+e) (also the clamp), q, mismatch + 2(q+e), (match + 2(q+e)) | 0x80
+	uint32_t qe2_4, maxsc_4, q_4, misq_4, maxsc_h80;
 };
+inline KswParams ksw_make_params(int match, int mismatch, int q, int e, int w, int zdrop)
+{
+	KswParams p;
+	p.match = (int8_t)match; p.mismatch = (int8_t)mismatch; p.q = (int8_t)q; p.e = (int8_t)e; p.w = w; p.zdrop = zdrop;
+	const int qe = p.q + p.e;
+	auto rep = [](int v) { return (uint32_t)(v & 0xff) * 0x01010101u; };
+	p.qe2_4 = rep(qe * 2); p.maxsc_4 = rep(p.match + qe * 2); p.q_4 = rep(p.q); p.misq_4 = rep(p.mismatch + qe * 2);
+	p.maxsc_h80 = p.maxsc_4 | 0x80808080u;
+	return p;
+}
 
 #define SORT_BUCKETS 256
 // bucket sort of alignment tasks by estimated anti-diagonals (longest first): hist/start/cursor hold SORT_BUCKETS entries

@@ -32,6 +32,7 @@ struct GenoArgs {
 	AlEntry *al_list; AlItem *al_items; int8_t *al_res; // al_res[task] = count_flanked_cigar, or -1 on a DP error
 	SortBufs sortA, sortB;
 	idl_params P;
+	KswParams kpA, kpB; // call-site A (:221) and B (:315-316) scoring, made on the host
 	DevCounters *cnt;
 	// kernel 2 geometry of this launch (per group) and its global workspaces (one per resident group)
 	int ring_cols, seq_cap;
@@ -117,25 +118,24 @@ __global__ void __launch_bounds__(DP_THREADS, 3) align_kernel(GenoArgs g)
 	const unsigned gmask = ((1u << DP_G) - 1u) << (lane & ~(DP_G - 1));
 	const idl_params &P = g.P;
 	const int K = IDL_KMER, width = (K + 1) / 2 - 1; // :218
-	KswParams kp; kp.match = (int8_t)P.match; kp.mismatch = (int8_t)P.mismatch; kp.q = (int8_t)P.a_gapo; kp.e = (int8_t)P.a_gape; kp.w = P.a_bw; kp.zdrop = P.a_zdrop;
 	const unsigned n_alns = g.cnt->n_alns < g.cap_alns ? g.cnt->n_alns : g.cap_alns;
 	for (;;) {
 		unsigned base = 0;
 		if (lane == 0) base = atomicAdd(&g.cnt->aln_next, (unsigned)DP_NG);
 		base = __shfl_sync(FULL_MASK, base, 0);
 		if (base >= n_alns) break;
-		if (base + grp < n_alns) {
-			const unsigned ai = g.sortA.order[base + grp];
-			idl_aln_result ar = g.ares[ai];
-			const idl_contig_result cr = g.cres[ar.contig];
-			const idl_region R = g.region[ar.region];
-			const int tlen = ar.ref_len; // window of :213-220, computed when the task was created
-			const uint8_t *tq = g.refcodes + R.ref_off + (cr.start - R.ref_start);
-			const uint8_t *qq = g.ctg_codes + cr.seq_off;
-			KswQuery kq; kq.codes = qq; kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
-			const KswMem M = dp_mem(g, smem_raw, cr.len, tlen);
-			KswOut o;
-			ksw2_group<DP_G>(cr.len, kq, tlen, tq, kp, M, o);
+		const bool valid = base + grp < n_alns;
+		unsigned ai = 0; idl_aln_result ar; idl_contig_result cr; idl_region R;
+		memset(&ar, 0, sizeof ar); memset(&cr, 0, sizeof cr); memset(&R, 0, sizeof R);
+		if (valid) { ai = g.sortA.order[base + grp]; ar = g.ares[ai]; cr = g.cres[ar.contig]; R = g.region[ar.region]; }
+		const int tlen = ar.ref_len; // window of :213-220, computed when the task was created
+		const uint8_t *tq = g.refcodes + R.ref_off + (cr.start - R.ref_start);
+		const uint8_t *qq = g.ctg_codes + cr.seq_off;
+		KswQuery kq; kq.codes = qq; kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
+		const KswMem M = dp_mem(g, smem_raw, cr.len, tlen);
+		KswOut o;
+		ksw2_group<DP_G>(valid, cr.len, kq, tlen, tq, g.kpA, M, o); // the whole warp: four alignments in lockstep
+		if (valid) {
 			const uint32_t *cg = M.cig;
 			const int n = o.n_cigar;
 			int ntr = 0, nev = 0;
@@ -380,7 +380,6 @@ __global__ void __launch_bounds__(DP_THREADS, 3) al_kernel(GenoArgs g)
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;
 	const idl_params &P = g.P;
-	KswParams kp; kp.match = (int8_t)P.match; kp.mismatch = (int8_t)P.mismatch; kp.q = (int8_t)P.b_gapo; kp.e = (int8_t)P.b_gape; kp.w = P.b_bw; kp.zdrop = P.b_zdrop;
 	unsigned n_items = g.cnt->n_al_items; if (n_items > g.cap_items) n_items = g.cap_items;
 	const unsigned n_tasks = 2 * n_items;
 	for (;;) {
@@ -388,28 +387,32 @@ __global__ void __launch_bounds__(DP_THREADS, 3) al_kernel(GenoArgs g)
 		if (lane == 0) base = atomicAdd(&g.cnt->al_next, (unsigned)DP_NG);
 		base = __shfl_sync(FULL_MASK, base, 0);
 		if (base >= n_tasks) break;
-		if (base + grp < n_tasks) {
-			const unsigned task = g.sortB.order[base + grp];
+		const bool valid = base + grp < n_tasks;
+		unsigned task = 0, region = 0; int qlen = 0, tlen = 0; const uint8_t *t = g.refcodes;
+		KswQuery kq; kq.codes = nullptr; kq.seq2 = g.seq2; kq.seqn = g.seqn; kq.base = 0;
+		if (valid) {
+			task = g.sortB.order[base + grp];
 			const AlItem it = g.al_items[task >> 1];
 			const idl_event_result ev = g.eres[it.event];
 			const idl_aln_result ar = g.ares[ev.aln];
 			const idl_contig_result cr = g.cres[ar.contig];
 			const idl_region R = g.region[ar.region];
 			const idl_read rd = g.read[it.read];
-			const int qlen = rd.trim_len;
-			KswQuery kq; kq.codes = nullptr; kq.seq2 = g.seq2; kq.seqn = g.seqn; kq.base = rd.seq_off + rd.trim_a;
-			const uint8_t *t; int tlen;
+			region = ar.region;
+			qlen = rd.trim_len; kq.base = rd.seq_off + rd.trim_a;
 			if (!(task & 1)) { t = g.refcodes + R.ref_off + (cr.start - R.ref_start) + it.start; tlen = ar.ref_len - it.start; } // ref_sub :340
 			else { t = g.ctg_codes + cr.seq_off + it.start; tlen = cr.len - it.start; }                                          // ctg_sub :341
 			if (tlen < 0) tlen = 0;
-			const KswMem M = dp_mem(g, smem_raw, qlen, tlen);
-			KswOut o;
-			ksw2_group<DP_G>(qlen, kq, tlen, t, kp, M, o);
+		}
+		const KswMem M = dp_mem(g, smem_raw, qlen, tlen);
+		KswOut o;
+		ksw2_group<DP_G>(valid, qlen, kq, tlen, t, g.kpB, M, o); // the whole warp: four alignments in lockstep
+		if (valid) {
 			if (gl == 0) {
 				const unsigned st = dp_status_bits(o.status);
 				int c = count_flanked(M.cig, o.n_cigar, o.max_q);
 				if (c > 126) c = 126; // only "== 1" and "> 1" are consumed (:353-356)
-				if (st) { atomicOr(&g.rres[ar.region].status, st); c = -1; }
+				if (st) { atomicOr(&g.rres[region].status, st); c = -1; }
 				g.al_res[task] = (int8_t)c;
 				atomicAdd(&g.cnt->dp_b, 1ULL); atomicAdd(&g.cnt->dp_cells_b, (unsigned long long)o.cells);
 			}

@@ -133,85 +133,101 @@ __device__ __forceinline__ uint32_t ksw_target_word(const uint8_t *target, int t
 }
 __device__ __forceinline__ bool ksw_has4(uint32_t w) { const uint32_t x = w ^ 0x04040404u; return ((x - 0x01010101u) & ~x & 0x80808080u) != 0u; }
 
-// The G threads of a group call this with identical arguments; `out` comes back identical in each of them.
+// max / min over the 8 threads of a group with full-warp butterflies (the four groups of a warp reduce side by side)
+__device__ __forceinline__ unsigned ksw_group_max(unsigned v)
+{
+	unsigned o = __shfl_xor_sync(FULL_MASK, v, 1); v = v > o ? v : o;
+	o = __shfl_xor_sync(FULL_MASK, v, 2); v = v > o ? v : o;
+	o = __shfl_xor_sync(FULL_MASK, v, 4); return v > o ? v : o;
+}
+__device__ __forceinline__ unsigned ksw_group_min(unsigned v)
+{
+	unsigned o = __shfl_xor_sync(FULL_MASK, v, 1); v = v < o ? v : o;
+	o = __shfl_xor_sync(FULL_MASK, v, 2); v = v < o ? v : o;
+	o = __shfl_xor_sync(FULL_MASK, v, 4); return v < o ? v : o;
+}
+__device__ __forceinline__ bool ksw_group_any(bool p, int lane) { return ((__ballot_sync(FULL_MASK, p) >> (lane & ~7)) & 0xffu) != 0u; }
+// wildcard (code 4) lanes score 0 (:219,226); out of line so that the common all-ACGT case pays one branch
+__device__ __noinline__ uint32_t ksw_wild_score(uint32_t sq, uint32_t sq2, uint32_t sc, uint32_t qe2)
+{
+	return sel4(msb_to_mask4(((sq ^ 0x04040404u) + 0x7f7f7f7fu) & ((sq2 ^ 0x04040404u) + 0x7f7f7f7fu)), sc, qe2);
+}
+
+// ALL 32 threads of a warp call this together: 4 groups of G = 8 threads, one alignment per group (valid = 0 for a group
+// without one).  The anti-diagonal loop and the rounds inside it run in lockstep over the four alignments, so every
+// barrier and shuffle is a plain full-warp one; a group whose alignment is shorter or has stopped idles behind a predicate.
+// The threads of a group pass identical arguments; `out` comes back identical in each of them.
 template <int G>
-__device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8_t *target, KswParams P, const KswMem M, KswOut &out)
+__device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen, const uint8_t *target, const KswParams P, const KswMem M, KswOut &out)
 {
 	static_assert(G == 8, "the clear-ahead step deals 8 words to the 8 threads of a group");
 	const int lane = lane_id();
 	const int gl = lane & (G - 1);
-	const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+	const unsigned gmask = ((1u << G) - 1u) << (lane & ~(G - 1));
 	ksw_reset(out);
-	if (qlen <= 0 || tlen <= 0) { out.status = KSW_ST_EARLY; return; } // :147
 	const int qe = P.q + P.e;
 	int min_sc = P.mismatch < 0 ? P.mismatch : 0;
 	if (P.match < min_sc) min_sc = P.match;
-	if (-min_sc > 2 * qe) { out.status = KSW_ST_EARLY; return; } // :171
 	int w = P.w;
 	if (w < 0) w = tlen > qlen ? tlen : qlen; // :161
-	const int n_col = ksw_ncol(qlen, tlen, w); // :164-165 (bytes)
-	if (ksw_ring_cols(n_col) > M.ring_cols) { out.status = KSW_ST_RCAP; return; }
-	if (ksw_seq_bytes(qlen, tlen) > (size_t)M.seq_cap) { out.status = KSW_ST_SEQCAP; return; }
-	if ((size_t)(qlen + tlen - 1) * (size_t)n_col + 2 * KSW_PMAT_PAD > M.p_cap) { out.status = KSW_ST_PCAP; return; }
+	const int n_col = valid ? ksw_ncol(qlen, tlen, w) : 16; // :164-165 (bytes)
 	// The exact scores H[] (:177-178, int32 in the reference) live as uint16: g[t] = H[t] + (q+e)*(r+1) + gbias, r = the
 	// diagonal of the last update.  Every in-band column is updated on every diagonal, so the per-diagonal -(q+e) of
 	// :323-348 turns into a common offset, the update into an unsigned byte add, and the band max into a packed 16-bit max.
 	const int gbias = 2 * qe;
-	if ((long long)(qlen + tlen + 2) * qe + (long long)(qlen < tlen ? qlen : tlen) * (P.match > 0 ? P.match : 0) + gbias >= 0xF000) { out.status = KSW_ST_HCAP; return; }
+	bool live = valid;
+	if (live) {
+		if (qlen <= 0 || tlen <= 0) { out.status = KSW_ST_EARLY; live = false; }     // :147
+		else if (-min_sc > 2 * qe) { out.status = KSW_ST_EARLY; live = false; }      // :171
+		else if (ksw_ring_cols(n_col) > M.ring_cols) { out.status = KSW_ST_RCAP; live = false; }
+		else if (ksw_seq_bytes(qlen, tlen) > (size_t)M.seq_cap) { out.status = KSW_ST_SEQCAP; live = false; }
+		else if ((size_t)(qlen + tlen - 1) * (size_t)n_col + 2 * KSW_PMAT_PAD > M.p_cap) { out.status = KSW_ST_PCAP; live = false; }
+		else if ((long long)(qlen + tlen + 2) * qe + (long long)(qlen < tlen ? qlen : tlen) * (P.match > 0 ? P.match : 0) + gbias >= 0xF000) { out.status = KSW_ST_HCAP; live = false; }
+	}
+	const bool run = live; // this group has a DP to run (and a CIGAR to walk afterwards)
 	uint8_t *pmat = M.pmat + KSW_PMAT_PAD;
 	const int rm = M.ring_cols - 1, rmw = (M.ring_cols >> 2) - 1, rotw = M.rot, rotc = M.rot << 2;
 	uint4 *XV = M.xvuy; uint2 *GR = M.g; uint32_t *S = M.S, *SF = M.T;
 	uint16_t *G16 = (uint16_t*)M.g;
 	uint8_t *qrp = M.seq; // KSW_QR_PAD zero bytes, then the reversed query, zero padded
 	const uint32_t *QRP = (const uint32_t*)qrp;
-	const uint32_t QE2 = rep4(qe * 2), MAXSC = rep4(P.match + qe * 2), Q4 = rep4(P.q), MATQ = rep4(P.match + qe * 2), MISQ = rep4(P.mismatch + qe * 2);
+	const uint32_t QE2 = P.qe2_4, MAXSC = P.maxsc_4, Q4 = P.q_4, MATQ = P.maxsc_4, MISQ = P.misq_4;
 	// the carry-free formulation of the core needs every constant and every input byte small and non-negative
 	const bool fast_ok = P.match + 2 * qe <= 63 && P.q >= 0 && P.q + 2 * P.e + min_sc >= 0;
+	const int nr = live ? qlen + tlen - 1 : 0; // anti-diagonals of this alignment
 
 	// calloc :173: columns [0,16) of u,v,x,y and [0,32) of s start as zero (later blocks are cleared as they enter);
 	// stage the first 32 target codes (zero padded, :187) and qr (reversed query, zero padded, :188)
-	if (gl < 4) XV[(gl + rotw) & rmw] = make_uint4(0u, 0u, 0u, 0u);
-	S[(gl + rotw) & rmw] = QE2; // S holds s + 2(q+e) (:117): one add less per word and diagonal
-	bool wild; // a code 4 seen so far: only then the score needs the wildcard mask (:219,226)
-	{ const uint32_t tw = ksw_target_word(target, tlen, 4 * gl); SF[(gl + rotw) & rmw] = tw; wild = ksw_has4(tw); }
-	{
+	bool wild = false; // a code 4 seen so far: only then the score needs the wildcard mask (:219,226)
+	if (live) {
+		if (gl < 4) XV[(gl + rotw) & rmw] = make_uint4(0u, 0u, 0u, 0u);
+		S[(gl + rotw) & rmw] = QE2; // S holds s + 2(q+e) (:117): one add less per word and diagonal
+		{ const uint32_t tw = ksw_target_word(target, tlen, 4 * gl); SF[(gl + rotw) & rmw] = tw; wild = ksw_has4(tw); }
 		const int nq = KSW_QR_PAD + ((qlen + 35) & ~3);
 		for (int i = gl; i < nq; i += G) {
 			const int k = i - KSW_QR_PAD;
 			const uint8_t c = (k >= 0 && k < qlen) ? ksw_query_code(query, qlen - 1 - k) : (uint8_t)0; wild |= c == 4; qrp[i] = c;
 		}
 	}
-	wild = (__ballot_sync(gmask, wild) & gmask) != 0u;
-	__syncwarp(gmask);
+	wild = ksw_group_any(wild, lane);
+	__syncwarp();
 
 	int last_st = -1, last_en = -1, last_st0 = 0, last_en0 = -1, en_clr = 15;
 	unsigned g_high = 0; // sticky: an exact score came close to the uint16 range
-	for (int r = 0; r < qlen + tlen - 1; ++r) {
-		int st0, en0;
-		ksw_band(r, qlen, tlen, w, st0, en0);
-		if (st0 > en0) { out.zdropped = 1; break; } // :200-203
+	int st0 = 0, en0 = 0; // band of diagonal 0 (:196-199)
+	for (int r = 0; ; ++r) {
+		bool act = live && r < nr;
+		if (act && st0 > en0) { out.zdropped = 1; live = false; act = false; } // :200-203
+		if (!__any_sync(FULL_MASK, act)) break;
 		const int st = st0 & ~15, en = en0 | 15;    // :205
-		out.cells += en0 - st0 + 1;
-		if (en > en_clr) { // a 16-lane block enters the band: it must read as never written (calloc); the score overrun zone moves on
-			const int b = en_clr + 1;
-			bool w4 = false;
-			if (gl < 4) XV[((b >> 2) + gl + rotw) & rmw] = make_uint4(0u, 0u, 0u, 0u);
-			else { // ... and the next 16 target codes are fetched
-				const int wn = ((b + 16) >> 2) + gl - 4;
-				const uint32_t tw = ksw_target_word(target, tlen, wn << 2);
-				S[(wn + rotw) & rmw] = QE2; SF[(wn + rotw) & rmw] = tw; w4 = ksw_has4(tw);
-			}
-			wild |= (__ballot_sync(gmask, w4) & gmask) != 0u;
-			en_clr += 16;
-			__syncwarp(gmask);
-		}
+		if (act) out.cells += en0 - st0 + 1;
 		// boundary conditions :207-211 (values of the previous diagonal): the word left of the first one supplies x[st-1], v[st-1]
 		const bool keep_prev = st > 0 && st - 1 >= last_st && st - 1 <= last_en;
 		const uint32_t v1c = (st == 0 && r) ? ((uint32_t)(P.q & 0xff) << 24) : 0u;
 		const int goff = qe * (r + 1) + gbias;
 		// H[en0] is built from the OLD H[en0-1] (:318): fetch it before this diagonal's updates
 		unsigned gprev = 0;
-		if (r) {
+		if (act && r) {
 			const int c = en0 > 0 ? en0 - 1 : 0;
 			gprev = G16[(c + rotc) & rm];
 			if (c < last_st0 || c > last_en0) { // the column was not part of the previous band: its offset is older (the band left the matrix on the right)
@@ -224,27 +240,27 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 		const int wfirst = st >> 2, w1 = (bend - 1) >> 2, wend = en >> 2, wlast = wend > w1 ? wend : w1, ws0 = st0 >> 2;
 		const int en1 = st0 + (((en0 - st0) >> 2) << 2);    // end of the 4-wide vector part of the arg-max (:316)
 		const unsigned bandw = (unsigned)(en0 - st0);       // columns st0 .. en0-1 are updated in the loop
-		uint32_t *pr = (uint32_t*)(pmat + (size_t)r * n_col) - wfirst;
-		const int rword = en >= r ? (r >> 2) : -1;           // :212, y[r] = 0 and u[r] = q, patched in registers
+		uint32_t *prg = (uint32_t*)(pmat + (size_t)r * n_col) + gl; // backtrack row r; word j of the band goes to [j]
 		const int cq = qlen - 1 - r;                         // lane t meets query code qr[cq + t]
 		const int qsh = 8 * (cq & 3);
 		const uint32_t *QRr = QRP + (KSW_QR_PAD >> 2) + (cq >> 2);
 		uint32_t bh2 = 0;                                     // this thread's best g over its in-band columns, two uint16 halves
 		// Words are dealt round-robin (word j of the band goes to thread j % G), last round first: every word reads the old
 		// x, v of the word to its left, which belongs to the previous thread of the same round or to a round not yet done.
-		for (int rd = (wlast - wfirst) / G; rd >= 0; --rd) {
-			const int wi = wfirst + rd * G + gl, t = wi << 2, wm = (wi + rotw) & rmw;
-			const bool core = wi <= wend, sca = wi >= ws0 && wi <= w1;
-			uint4 own = make_uint4(0u, 0u, 0u, 0u); uint2 prv = make_uint2(0u, 0u);
-			if (core) { own = XV[wm]; prv = *(const uint2*)&XV[(wm - 1) & rmw]; }
-			__syncwarp(gmask); // every load of the round is issued before any store of the round
+		const int rounds = act ? (wlast - wfirst) / G : -1;
+		for (int rd = (int)__reduce_max_sync(FULL_MASK, rounds); rd >= 0; --rd) {
+			const int j = rd * G + gl, wi = wfirst + j, t = wi << 2, wm = (wi + rotw) & rmw;
+			const bool mine = rd <= rounds;
+			const bool core = mine && wi <= wend, sca = mine && wi >= ws0 && wi <= w1;
+			const uint4 own = XV[wm]; uint2 prv = *(const uint2*)&XV[(wm - 1) & rmw];
+			__syncwarp(); // every load of the round is issued before any store of the round
 			uint32_t z0 = 0;   // s + 2(q+e)
 			if (sca) { // scores :215-228: lanes of this word inside the 16-wide blocks get fresh values, the others keep stale s
 				const uint32_t sq = SF[wm];
 				const uint32_t sq2 = __funnelshift_r(QRr[wi], QRr[wi + 1], qsh);
 				const uint32_t neq = msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu); // 0xff where the codes differ
 				uint32_t sc = sel4(neq, MISQ, MATQ);
-				if (wild) sc = sel4(msb_to_mask4(((sq ^ 0x04040404u) + 0x7f7f7f7fu) & ((sq2 ^ 0x04040404u) + 0x7f7f7f7fu)), sc, QE2); // score 0 where a code is 4
+				if (wild) sc = ksw_wild_score(sq, sq2, sc, QE2);
 				const int lo = st0 - t, hi = bend - t; // lanes [lo, hi) of this word belong to the blocks
 				if (lo <= 0 && hi >= 4) z0 = sc;
 				else {
@@ -256,13 +272,8 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 				S[wm] = z0;
 			} else if (core) z0 = S[wm];
 			if (core) {
-				if (wi == wfirst && !keep_prev) { prv.x = 0u; prv.y = v1c; }
-				uint32_t ut = own.z, yt = own.w;
-				if (wi == rword) {
-					const int b = 8 * (r & 3);
-					yt &= ~(0xffu << b);
-					ut = (ut & ~(0xffu << b)) | ((uint32_t)((r ? P.q : 0) & 0xff) << b);
-				}
+				if (j == 0 && !keep_prev) { prv.x = 0u; prv.y = v1c; }
+				const uint32_t ut = own.z, yt = own.w; // :212 (y[r] = 0, u[r] = q) was applied to the ring at the end of the previous diagonal
 				const uint32_t xt1 = __funnelshift_l(prv.x, own.x, 8), vt1 = __funnelshift_l(prv.y, own.y, 8); // lanes t-1..t+2 of the previous diagonal
 				uint32_t d, un, vn, xn, yn;
 				if (fast_ok && !((xt1 | vt1 | ut | yt) & 0xc0c0c0c0u)) {
@@ -275,7 +286,7 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 					m = ge4_pos(z, b);                              // z >= b
 					d = sel4(m, d, 0x02020202u);
 					z = sel4(m, z, b);
-					z = sel4(ge4_pos(MAXSC, z), z, MAXSC);
+					z = sel4(msb_to_mask4(P.maxsc_h80 - z), z, MAXSC); // min(z, max score)
 					const uint32_t zh = z | KSW_H80;
 					un = (zh - vt1) ^ KSW_H80; vn = (zh - ut) ^ KSW_H80;
 					z -= Q4;
@@ -304,7 +315,7 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 					yn = b & m; d |= m & 0x10101010u;
 				}
 				XV[wm] = make_uint4(xn, vn, un, yn);
-				pr[wi] = d;
+				prg[rd * G] = d;
 				const int lo = st0 - t, hi = en0 - t; // exact scores of the in-band columns st0 .. en0-1 of this word (:323-348): g[t] += v8[t]
 				if (hi > 0 && lo < 4) {
 					uint2 g2 = GR[wm];
@@ -323,29 +334,29 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 				}
 			}
 		}
-		__syncwarp(gmask); // this diagonal's lanes and g[st0..en0) are visible to the whole group
-		// the en0 cell, :318 / :349
-		unsigned ghen;
-		if (r == 0) ghen = (unsigned)((int)((const uint8_t*)&XV[rotw & rmw])[4] - qe + gbias); // H[0] = v[0] - 2(q+e)
-		else {
-			const uint8_t *wb = (const uint8_t*)&XV[((en0 >> 2) + rotw) & rmw];
-			ghen = gprev + (unsigned)(en0 > 0 ? wb[8 + (en0 & 3)] : wb[4 + (en0 & 3)]); // + u8[en0] or + v8[en0]
+		__syncwarp(); // this diagonal's lanes and g[st0..en0) are visible to the whole group
+		// band max of the updated columns, then the en0 cell (:318 / :349)
+		unsigned mg = (bh2 & 0xffffu) > (bh2 >> 16) ? (bh2 & 0xffffu) : (bh2 >> 16);
+		mg = ksw_group_max(mg);
+		unsigned ghen = 0;
+		if (act) {
+			if (r == 0) ghen = (unsigned)((int)((const uint8_t*)&XV[rotw & rmw])[4] - qe + gbias); // H[0] = v[0] - 2(q+e)
+			else {
+				const uint8_t *wb = (const uint8_t*)&XV[((en0 >> 2) + rotw) & rmw];
+				ghen = gprev + (unsigned)(en0 > 0 ? wb[8 + (en0 & 3)] : wb[4 + (en0 & 3)]); // + u8[en0] or + v8[en0]
+			}
 		}
 		const int hen = (int)ghen - goff;
-		unsigned mg = (bh2 & 0xffffu) > (bh2 >> 16) ? (bh2 & 0xffffu) : (bh2 >> 16);
-		mg = __reduce_max_sync(gmask, mg);
 		g_high |= (mg | ghen) >= 0xF000u;
 		const int mh = (int)mg - goff;
-		int max_H, max_t;
-		bool have_t = true;
-		if (hen >= mh) { max_H = hen; max_t = en0; } // the initial candidate (H[en0], en0) wins every tie (:318-321)
-		else {
-			// The position of the band max matters only when it becomes the new overall max or when z-drop can fire
-			// (ksw_apply_zdrop :88-104 needs max - H > zdrop at least); only then look it up, in the SSE tie order.
-			max_H = mh; max_t = en0;
-			have_t = mh > out.max || (P.zdrop >= 0 && out.max - mh > P.zdrop);
-			if (have_t) {
-				unsigned best = 0xffffffffu;
+		int max_H = hen, max_t = en0; // the initial candidate (H[en0], en0) wins every tie (:318-321)
+		// The position of the band max matters only when it becomes the new overall max or when z-drop can fire
+		// (ksw_apply_zdrop :88-104 needs max - H > zdrop at least); only then look it up, in the SSE tie order.
+		const bool better = act && mh > hen;
+		const bool need_t = better && (mh > out.max || (P.zdrop >= 0 && out.max - mh > P.zdrop));
+		if (__any_sync(FULL_MASK, need_t)) {
+			unsigned best = 0xffffffffu;
+			if (need_t)
 				for (int wi = ws0 + gl; wi <= ((en0 - 1) >> 2); wi += G) {
 					const uint2 g2 = GR[(wi + rotw) & rmw];
 					const int t = wi << 2;
@@ -355,34 +366,57 @@ __device__ void ksw2_group(int qlen, const KswQuery query, int tlen, const uint8
 						if ((unsigned)(t + c - st0) < bandw && val == mg) { const unsigned rk = ksw_tie_rank(t + c, st0, en1); best = rk < best ? rk : best; }
 					}
 				}
-				const unsigned rk = __reduce_min_sync(gmask, best);
-				max_t = st0 + (int)((rk - 1) & 0xfffffu);
+			const unsigned rk = ksw_group_min(best);
+			if (need_t) { max_H = mh; max_t = st0 + (int)((rk - 1) & 0xfffffu); }
+		}
+		// band of the next diagonal (:196-199): its new 16-lane block, if any, and its :212 patch are applied now, so that
+		// one barrier covers them together with this diagonal's H[en0]
+		int st0n, en0n;
+		ksw_band(r + 1, qlen, tlen, w, st0n, en0n);
+		const bool nxt = act && r + 1 < nr && st0n <= en0n;
+		if (act) {
+			if (en0 == tlen - 1) {
+				if (hen > out.mte) { out.mte = hen; out.mte_q = r - en; }
+				if (r == qlen + tlen - 2) out.score = hen; // H[tlen-1]
 			}
+			if (r - st0 == qlen - 1) {
+				const int Hst0 = st0 == en0 ? hen : (int)G16[(st0 + rotc) & rm] - goff;
+				if (Hst0 > out.mqe) { out.mqe = Hst0; out.mqe_t = st0; }
+			}
+			if (gl == 0) G16[(en0 + rotc) & rm] = (uint16_t)ghen;
 		}
-		if (en0 == tlen - 1) {
-			if (hen > out.mte) { out.mte = hen; out.mte_q = r - en; }
-			if (r == qlen + tlen - 2) out.score = hen; // H[tlen-1]
+		bool w4 = false;
+		const bool enter = nxt && (en0n | 15) > en_clr; // a 16-lane block enters the band: it must read as never written (calloc); the score overrun zone moves on
+		if (enter) {
+			const int b = en_clr + 1;
+			if (gl < 4) XV[((b >> 2) + gl + rotw) & rmw] = make_uint4(0u, 0u, 0u, 0u);
+			else { // ... and the next 16 target codes are fetched
+				const int wn = ((b + 16) >> 2) + gl - 4;
+				const uint32_t tw = ksw_target_word(target, tlen, wn << 2);
+				S[(wn + rotw) & rmw] = QE2; SF[(wn + rotw) & rmw] = tw; w4 = ksw_has4(tw);
+			}
+			en_clr += 16;
 		}
-		if (r - st0 == qlen - 1) {
-			const int Hst0 = st0 == en0 ? hen : (int)G16[(st0 + rotc) & rm] - goff;
-			if (Hst0 > out.mqe) { out.mqe = Hst0; out.mqe_t = st0; }
+		if (__any_sync(FULL_MASK, enter)) { wild |= ksw_group_any(w4, lane); __syncwarp(); }
+		if (nxt && (en0n | 15) >= r + 1 && gl == 0) { // :212 of the next diagonal: y[r+1] = 0, u[r+1] = q
+			uint8_t *wb = (uint8_t*)&XV[(((r + 1) >> 2) + rotw) & rmw];
+			wb[8 + ((r + 1) & 3)] = (uint8_t)P.q; wb[12 + ((r + 1) & 3)] = 0;
 		}
-		if (gl == 0) G16[(en0 + rotc) & rm] = (uint16_t)ghen;
-		__syncwarp(gmask);
-		if (have_t) { // ksw_apply_zdrop :88-104
-			bool stop = false;
+		__syncwarp();
+		if (act && (better ? need_t : true)) { // ksw_apply_zdrop :88-104 (skipped when the band max can neither raise the max nor trigger z-drop)
 			if (max_H > out.max) { out.max = max_H; out.max_t = max_t; out.max_q = r - max_t; }
 			else if (max_t >= out.max_t && r - max_t >= out.max_q) {
 				const int tl = max_t - out.max_t, ql = (r - max_t) - out.max_q;
 				const int l = tl > ql ? tl - ql : ql - tl;
-				if (P.zdrop >= 0 && out.max - max_H > P.zdrop + l * P.e) { out.zdropped = 1; stop = true; }
+				if (P.zdrop >= 0 && out.max - max_H > P.zdrop + l * P.e) { out.zdropped = 1; live = false; }
 			}
-			if (stop) break;
 		}
 		last_st = st; last_en = en; last_st0 = st0; last_en0 = en0;
+		st0 = st0n; en0 = en0n;
 	}
 	if (g_high) out.status = KSW_ST_HCAP;
-	__syncwarp(gmask);
+	__syncwarp();
+	if (!run) return;
 	// backtrack :380-385 -> ksw_backtrack :47-79 (is_rot = 1, left-aligned gaps)
 	int i, j;
 	if (!out.zdropped) { i = tlen - 1; j = qlen - 1; }

@@ -354,6 +354,8 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 	g.al_list = (AlEntry*)L.al_list.p; g.al_items = (AlItem*)L.al_items.p; g.al_res = (int8_t*)L.al_res.p;
 	g.sortA = sA; g.sortB = sB;
 	g.P = P; g.cnt = a.cnt;
+	g.kpA = ksw_make_params(P.match, P.mismatch, P.a_gapo, P.a_gape, P.a_bw, P.a_zdrop);
+	g.kpB = ksw_make_params(P.match, P.mismatch, P.b_gapo, P.b_gape, P.b_bw, P.b_zdrop);
 	g.pmat = (uint8_t*)L.pmat.p; g.p_cap = p_cap; g.cig_scratch = (uint32_t*)L.cig_scratch.p; g.cig_cap = ctx->cig_cap;
 	g.seq_spill = (uint8_t*)L.seq_spill.p; g.seq_spill_cap = seq_spill_cap;
 	const size_t smem_limit = 200 * 1024;
@@ -555,11 +557,12 @@ __global__ void __launch_bounds__(DP_THREADS, 3) ksw2_batch_kernel(KswBatchArgs 
 		base = __shfl_sync(FULL_MASK, base, 0);
 		if (base >= a.n) break;
 		const unsigned i = base + grp;
-		if (i < a.n) {
-			const int qlen = (int)(a.q_off[i + 1] - a.q_off[i]), tlen = (int)(a.t_off[i + 1] - a.t_off[i]);
-			KswQuery kq; kq.codes = a.query + a.q_off[i]; kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
-			KswOut o;
-			ksw2_group<DP_G>(qlen, kq, tlen, a.target + a.t_off[i], a.kp, M, o);
+		const bool valid = i < a.n;
+		const int qlen = valid ? (int)(a.q_off[i + 1] - a.q_off[i]) : 0, tlen = valid ? (int)(a.t_off[i + 1] - a.t_off[i]) : 0;
+		KswQuery kq; kq.codes = a.query + (valid ? a.q_off[i] : 0); kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
+		KswOut o;
+		ksw2_group<DP_G>(valid, qlen, kq, tlen, a.target + (valid ? a.t_off[i] : 0), a.kp, M, o);
+		if (valid) {
 			const unsigned gmask = ((1u << DP_G) - 1u) << (lane & ~(DP_G - 1));
 			unsigned coff = 0;
 			if (gl == 0) coff = atomicAdd(a.cig_used, (unsigned)o.n_cigar);
@@ -596,7 +599,7 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 		max_p = std::max(max_p, (size_t)std::max(ql + tl - 1, 0) * (size_t)nc);
 	}
 	KswBatchArgs a; memset(&a, 0, sizeof a);
-	a.n = (unsigned)n; a.kp.match = match; a.kp.mismatch = mismatch; a.kp.q = gapo; a.kp.e = gape; a.kp.w = w; a.kp.zdrop = zdrop;
+	a.n = (unsigned)n; a.kp = ksw_make_params(match, mismatch, gapo, gape, w, zdrop);
 	a.ring_cols = ksw_ring_cols(max_ncol);
 	a.p_cap = round_up(max_p + 2 * KSW_PMAT_PAD + 64, 256); a.cig_cap = max_q + max_t + 8; a.cigar_cap = (unsigned)cigar_cap;
 	a.seq_cap = (int)round_up(ksw_seq_bytes(max_q, max_t), 16);

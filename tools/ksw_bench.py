@@ -25,7 +25,7 @@ def make(rng, n, ql, tl, site):
 
 
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 56832  # 4 full waves of 148 SMs x 3 CTAs x 32 groups
     ctx = cuda.Context(0)
     rng = np.random.default_rng(1)
     for site, ql, tl, go, w, z in [("A", 300, 420, 4, 50, 400), ("A", 600, 720, 4, 50, 400), ("B", 150, 400, 5, -1, -1), ("B", 150, 700, 5, -1, -1)]:

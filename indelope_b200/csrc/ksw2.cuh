@@ -153,6 +153,52 @@ __device__ __noinline__ uint32_t ksw_wild_score(uint32_t sq, uint32_t sq2, uint3
 	return sel4(msb_to_mask4(((sq ^ 0x04040404u) + 0x7f7f7f7fu) & ((sq2 ^ 0x04040404u) + 0x7f7f7f7fu)), sc, qe2);
 }
 
+// The core update of one packed word, :262-284 (flag 0): in (previous diagonal) xt1, vt1 = x, v of lanes t-1 .. t+2, ut, yt = u, y
+// of lanes t .. t+3, z0 = s + 2(q+e); out the new x, v, u, y and the backtrack byte d of the four lanes.
+__device__ __forceinline__ void ksw_core_word(const KswParams &P, bool fast_ok, uint32_t z0, uint32_t xt1, uint32_t vt1, uint32_t ut, uint32_t yt,
+                                              uint32_t &xn, uint32_t &vn, uint32_t &un, uint32_t &yn, uint32_t &d)
+{
+	const uint32_t MAXSC = P.maxsc_4, Q4 = P.q_4;
+	if (fast_ok && !((xt1 | vt1 | ut | yt) & 0xc0c0c0c0u)) {
+		// every byte is in [0,63]: sums stay below 128, signed and unsigned compares agree and nothing carries
+		// between bytes, so the core runs on plain 32-bit adds and (a | 0x80) - b compares
+		const uint32_t a = xt1 + vt1, b = yt + ut;
+		uint32_t m = ge4_pos(z0, a);                    // z >= a
+		uint32_t z = sel4(m, z0, a);
+		d = ~m & 0x01010101u;
+		m = ge4_pos(z, b);                              // z >= b
+		d = sel4(m, d, 0x02020202u);
+		z = sel4(m, z, b);
+		z = sel4(msb_to_mask4(P.maxsc_h80 - z), z, MAXSC); // min(z, max score)
+		const uint32_t zh = z | KSW_H80;
+		un = (zh - vt1) ^ KSW_H80; vn = (zh - ut) ^ KSW_H80;
+		z -= Q4;
+		m = ge4_pos(z, a);                              // z >= a: x = 0
+		xn = sel4(m, z, a) - z; d |= ~m & 0x08080808u;
+		m = ge4_pos(z, b);
+		yn = sel4(m, z, b) - z; d |= ~m & 0x10101010u;
+	} else { // the lane-exact wrapping int8 form
+		uint32_t z = z0;
+		uint32_t a = __vadd4(xt1, vt1);
+		uint32_t b = __vadd4(yt, ut);
+		uint32_t m = __vcmpgts4(a, z);                 // a > z (signed)
+		d = m & 0x01010101u;
+		z = sel4(m, a, z);                             // signed max
+		m = __vcmpgts4(b, z);                          // b > z (signed)
+		d = sel4(m, 0x02020202u, d);
+		z = sel4(__vcmpgtu4(b, z), b, z);              // unsigned max
+		z = sel4(__vcmpgtu4(z, MAXSC), MAXSC, z);      // unsigned min
+		vn = __vsub4(z, ut); un = __vsub4(z, vt1);
+		z = __vsub4(z, Q4);
+		a = __vsub4(a, z);
+		b = __vsub4(b, z);
+		m = __vcmpgts4(a, 0u);
+		xn = a & m; d |= m & 0x08080808u;
+		m = __vcmpgts4(b, 0u);
+		yn = b & m; d |= m & 0x10101010u;
+	}
+}
+
 // ALL 32 threads of a warp call this together: 4 groups of G = 8 threads, one alignment per group (valid = 0 for a group
 // without one).  The anti-diagonal loop and the rounds inside it run in lockstep over the four alignments, so every
 // barrier and shuffle is a plain full-warp one; a group whose alignment is shorter or has stopped idles behind a predicate.
@@ -236,7 +282,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 				gprev += (unsigned)(qe * (r - 1 - rr));
 			}
 		}
-		const int bend = st0 + ((en0 - st0) / 16 + 1) * 16; // one past the last lane the 16-wide score blocks write
+		const int bend = st0 + (int)((((unsigned)(en0 - st0) >> 4) + 1u) << 4); // one past the last lane the 16-wide score blocks write (en0 >= st0 here)
 		const int wfirst = st >> 2, w1 = (bend - 1) >> 2, wend = en >> 2, wlast = wend > w1 ? wend : w1, ws0 = st0 >> 2;
 		const int en1 = st0 + (((en0 - st0) >> 2) << 2);    // end of the 4-wide vector part of the arg-max (:316)
 		const unsigned bandw = (unsigned)(en0 - st0);       // columns st0 .. en0-1 are updated in the loop
@@ -247,13 +293,32 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 		uint32_t bh2 = 0;                                     // this thread's best g over its in-band columns, two uint16 halves
 		// Words are dealt round-robin (word j of the band goes to thread j % G), last round first: every word reads the old
 		// x, v of the word to its left, which belongs to the previous thread of the same round or to a round not yet done.
-		const int rounds = act ? (wlast - wfirst) / G : -1;
+		const int rounds = act ? (wlast - wfirst) >> 3 : -1;
 		for (int rd = (int)__reduce_max_sync(FULL_MASK, rounds); rd >= 0; --rd) {
 			const int j = rd * G + gl, wi = wfirst + j, t = wi << 2, wm = (wi + rotw) & rmw;
 			const bool mine = rd <= rounds;
 			const bool core = mine && wi <= wend, sca = mine && wi >= ws0 && wi <= w1;
 			const uint4 own = XV[wm]; uint2 prv = *(const uint2*)&XV[(wm - 1) & rmw];
 			__syncwarp(); // every load of the round is issued before any store of the round
+			if (__all_sync(FULL_MASK, act && j > 0 && t >= st0 && t + 4 <= en0)) {
+				// every word of this round, in all four alignments, lies inside the exact band: fresh scores for all four lanes,
+				// no boundary lane, no masks
+				const uint32_t sq = SF[wm];
+				const uint32_t sq2 = __funnelshift_r(QRr[wi], QRr[wi + 1], qsh);
+				uint32_t z0 = sel4(msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu), MISQ, MATQ);
+				if (wild) z0 = ksw_wild_score(sq, sq2, z0, QE2);
+				S[wm] = z0;
+				const uint32_t xt1 = __funnelshift_l(prv.x, own.x, 8), vt1 = __funnelshift_l(prv.y, own.y, 8);
+				uint32_t d, un, vn, xn, yn;
+				ksw_core_word(P, fast_ok, z0, xt1, vt1, own.z, own.w, xn, vn, un, yn, d);
+				XV[wm] = make_uint4(xn, vn, un, yn);
+				prg[rd * G] = d;
+				uint2 g2 = GR[wm];
+				g2.x += __byte_perm(vn, 0u, 0x4140); g2.y += __byte_perm(vn, 0u, 0x4342);
+				bh2 = __vimax3_u16x2(bh2, g2.x, g2.y);
+				GR[wm] = g2;
+				continue;
+			}
 			uint32_t z0 = 0;   // s + 2(q+e)
 			if (sca) { // scores :215-228: lanes of this word inside the 16-wide blocks get fresh values, the others keep stale s
 				const uint32_t sq = SF[wm];
@@ -276,44 +341,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 				const uint32_t ut = own.z, yt = own.w; // :212 (y[r] = 0, u[r] = q) was applied to the ring at the end of the previous diagonal
 				const uint32_t xt1 = __funnelshift_l(prv.x, own.x, 8), vt1 = __funnelshift_l(prv.y, own.y, 8); // lanes t-1..t+2 of the previous diagonal
 				uint32_t d, un, vn, xn, yn;
-				if (fast_ok && !((xt1 | vt1 | ut | yt) & 0xc0c0c0c0u)) {
-					// every byte is in [0,63]: sums stay below 128, signed and unsigned compares agree and nothing carries
-					// between bytes, so the core (:262-284) runs on plain 32-bit adds and (a | 0x80) - b compares
-					const uint32_t a = xt1 + vt1, b = yt + ut;
-					uint32_t m = ge4_pos(z0, a);                    // z >= a
-					uint32_t z = sel4(m, z0, a);
-					d = ~m & 0x01010101u;
-					m = ge4_pos(z, b);                              // z >= b
-					d = sel4(m, d, 0x02020202u);
-					z = sel4(m, z, b);
-					z = sel4(msb_to_mask4(P.maxsc_h80 - z), z, MAXSC); // min(z, max score)
-					const uint32_t zh = z | KSW_H80;
-					un = (zh - vt1) ^ KSW_H80; vn = (zh - ut) ^ KSW_H80;
-					z -= Q4;
-					m = ge4_pos(z, a);                              // z >= a: x = 0
-					xn = sel4(m, z, a) - z; d |= ~m & 0x08080808u;
-					m = ge4_pos(z, b);
-					yn = sel4(m, z, b) - z; d |= ~m & 0x10101010u;
-				} else {
-					uint32_t z = z0;
-					uint32_t a = __vadd4(xt1, vt1);
-					uint32_t b = __vadd4(yt, ut);
-					uint32_t m = __vcmpgts4(a, z);                 // a > z (signed)
-					d = m & 0x01010101u;
-					z = sel4(m, a, z);                             // signed max
-					m = __vcmpgts4(b, z);                          // b > z (signed)
-					d = sel4(m, 0x02020202u, d);
-					z = sel4(__vcmpgtu4(b, z), b, z);              // unsigned max
-					z = sel4(__vcmpgtu4(z, MAXSC), MAXSC, z);      // unsigned min
-					vn = __vsub4(z, ut); un = __vsub4(z, vt1);
-					z = __vsub4(z, Q4);
-					a = __vsub4(a, z);
-					b = __vsub4(b, z);
-					m = __vcmpgts4(a, 0u);
-					xn = a & m; d |= m & 0x08080808u;
-					m = __vcmpgts4(b, 0u);
-					yn = b & m; d |= m & 0x10101010u;
-				}
+				ksw_core_word(P, fast_ok, z0, xt1, vt1, ut, yt, xn, vn, un, yn, d);
 				XV[wm] = make_uint4(xn, vn, un, yn);
 				prg[rd * G] = d;
 				const int lo = st0 - t, hi = en0 - t; // exact scores of the in-band columns st0 .. en0-1 of this word (:323-348): g[t] += v8[t]

@@ -354,41 +354,6 @@ template <int NT> __device__ int asm_trim(Asm &A, int c, int min_support, bool h
 	return d;
 }
 
-// one pass of combine (:262-281): in[0..n_in) -> out[], returns the new list length
-template <int NT> __device__ int asm_combine_pass(Asm &A, uint16_t *in, int n_in, uint16_t *out, int min_support, int mo, bool has_n)
-{
-	const int tid = asm_tid<NT>();
-	int usedi = -1;
-	for (int i = 0; i < n_in; ++i) {
-		int c = in[i];
-		if (min_support > 0) {
-			const int nr = A.s.nreads[c];
-			const int c2 = asm_trim<NT>(A, c, nr < min_support ? nr : min_support, has_n);
-			if (c2 != c) { asm_bar<NT>(); if (tid == 0) in[i] = (uint16_t)c2; asm_bar<NT>(); c = c2; }
-		}
-		if (usedi < 0 && A.s.nreads[c] > 0) usedi = i;
-	}
-	if (usedi < 0) return 0;
-	asm_bar<NT>();
-	if (tid == 0) out[0] = in[usedi];
-	asm_bar<NT>();
-	int n_out = 1;
-	for (int i = 0; i < n_in; ++i) {
-		if (i == usedi) continue;
-		if (A.s.sc[SC_STATUS]) break;
-		const int q = in[i];
-		const AsmMatch m = asm_best_match<NT>(A, out, n_out, q, mo, has_n);
-		if (m.aligned) asm_merge<NT>(A, out, m.k, q, m.offset, has_n);
-		else if (A.s.nreads[q] > 0) {
-			asm_bar<NT>();
-			if (tid == 0) out[n_out] = (uint16_t)q;
-			asm_bar<NT>();
-			++n_out;
-		} else { asm_free<NT>(A, q); asm_bar<NT>(); }
-	}
-	return n_out;
-}
-
 template <int NT>
 __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 {
@@ -439,50 +404,84 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 		}
 		asm_bar<NT>();
 		const bool has_n = A.s.sc[SC_HASN] != 0;
-		uint16_t *list = A.s.listA, *other = A.s.listB;
-		int nlist = 0;
-		// ---- assemble (src/indelope.nim:163-169): reads in input order
-		for (unsigned j = 0; j < R.n_reads && !A.s.sc[SC_STATUS]; ++j) {
-			const idl_read rd = args.read[R.read_begin + j];
-			if ((int)rd.mapq < P.asm_min_mapq) continue;  // :164
-			if (rd.flags & 1) continue;                  // :165
-			const int q = asm_alloc<NT>(A);
-			if (q < 0) break;
-			const int tl = rd.trim_len;
-			if (tl > A.cap) { if (tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; asm_bar<NT>(); break; }
-			{ // make_contig (:143-150) from the packed, trimmed read
-				uint32_t *g0 = A.p0(q), *g1 = A.p1(q), *gn = A.pn(q);
-				uint16_t *gs = A.sup(q);
-				const unsigned base = rd.seq_off + rd.trim_a;
-				for (int w = tid; w * 32 < tl; w += NT) {
-					const unsigned b = base + 32u * w;         // first base of this plane word
-					const unsigned wi = b >> 4, sh = 2 * (b & 15);
-					const uint32_t w0 = args.seq2[wi], w1 = args.seq2[wi + 1], w2 = args.seq2[wi + 2];
-					const uint64_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-					const uint64_t bits = lo | (hi << 32);     // 32 bases, 2 bits each
-					uint32_t m = 0xffffffffu;
-					if (tl - 32 * w < 32) m = (1u << (tl - 32 * w)) - 1u;
-					g0[w] = compress_even(bits) & m;
-					g1[w] = compress_even(bits >> 1) & m;
-					gn[w] = has_n ? (get32(args.seqn, (int)b) & m) : 0u;
+		// ---- assemble (src/indelope.nim:163-169) and the two passes of combine (:176 -> src/contig.nim:254-281) as ONE loop:
+		// every step takes an item q (phase 0: the next read, in input order, made into a contig; phases 1, 2: the next
+		// contig of the previous list), finds its best match in the list under construction and merges or appends it.
+		// best_match / merge / trim are instantiated once, which keeps the kernel inside the instruction cache.
+		uint16_t *list = A.s.listA, *in = A.s.listB;
+		int nlist = 0, n_pre = 0, n_in = 0, usedi = -1, i_in = 0, phase = 0;
+		unsigned j = 0;
+		for (;;) {
+			int q = -1, mo = 0;
+			if (phase == 0) {
+				bool got = false;
+				while (j < R.n_reads && !A.s.sc[SC_STATUS]) {
+					const idl_read rd = args.read[R.read_begin + j];
+					++j;
+					if ((int)rd.mapq < P.asm_min_mapq) continue;  // :164
+					if (rd.flags & 1) continue;                  // :165
+					q = asm_alloc<NT>(A);
+					if (q < 0) break;
+					const int tl = rd.trim_len;
+					if (tl > A.cap) { if (tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; asm_bar<NT>(); break; }
+					{ // make_contig (:143-150) from the packed, trimmed read
+						uint32_t *g0 = A.p0(q), *g1 = A.p1(q), *gn = A.pn(q);
+						uint16_t *gs = A.sup(q);
+						const unsigned base = rd.seq_off + rd.trim_a;
+						for (int w = tid; w * 32 < tl; w += NT) {
+							const unsigned b = base + 32u * w;         // first base of this plane word
+							const unsigned wi = b >> 4, sh = 2 * (b & 15);
+							const uint32_t w0 = args.seq2[wi], w1 = args.seq2[wi + 1], w2 = args.seq2[wi + 2];
+							const uint64_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+							const uint64_t bits = lo | (hi << 32);     // 32 bases, 2 bits each
+							uint32_t m = 0xffffffffu;
+							if (tl - 32 * w < 32) m = (1u << (tl - 32 * w)) - 1u;
+							g0[w] = compress_even(bits) & m;
+							g1[w] = compress_even(bits >> 1) & m;
+							gn[w] = has_n ? (get32(args.seqn, (int)b) & m) : 0u;
+						}
+						for (int i = tid; i < tl; i += NT) gs[i] = 1;
+						if (tid == 0) { A.s.len[q] = tl; A.s.nreads[q] = 1; A.s.start[q] = rd.start + rd.trim_a; }
+					}
+					asm_bar<NT>();
+					mo = rd.min_overlap;
+					got = true;
+					break;
 				}
-				for (int i = tid; i < tl; i += NT) gs[i] = 1;
-				if (tid == 0) { A.s.len[q] = tl; A.s.nreads[q] = 1; A.s.start[q] = rd.start + rd.trim_a; }
+				if (!got) { n_pre = nlist; phase = 1; i_in = n_in = 0; usedi = -1; } // :171; the first combine pass starts below
 			}
-			asm_bar<NT>();
-			const AsmMatch m = asm_best_match<NT>(A, list, nlist, q, rd.min_overlap, has_n);
+			if (phase > 0 && !(i_in < n_in)) { // a pass of combine is over (or the greedy pass was): start the next one
+				if (phase == 3 || A.s.sc[SC_STATUS]) break;
+				const int min_support = phase == 1 ? 0 : P.combine_min_support; // pass A merges without trimming (:260), pass B trims (:265-267)
+				{ uint16_t *t = list; list = in; in = t; } n_in = nlist; nlist = 0;
+				usedi = -1;
+				for (int i = 0; i < n_in; ++i) {
+					int c = in[i];
+					if (min_support > 0) {
+						const int nr = A.s.nreads[c];
+						const int c2 = asm_trim<NT>(A, c, nr < min_support ? nr : min_support, has_n);
+						if (c2 != c) { asm_bar<NT>(); if (tid == 0) in[i] = (uint16_t)c2; asm_bar<NT>(); c = c2; }
+					}
+					if (usedi < 0 && A.s.nreads[c] > 0) usedi = i;
+				}
+				++phase; // 2: pass A running, 3: pass B running
+				i_in = 0;
+				if (usedi < 0) { n_in = 0; continue; } // nothing left: the remaining pass is empty as well
+				asm_bar<NT>();
+				if (tid == 0) list[0] = in[usedi];
+				asm_bar<NT>();
+				nlist = 1;
+				continue;
+			}
+			if (phase > 0) {
+				if (i_in == usedi) { ++i_in; continue; }
+				if (A.s.sc[SC_STATUS]) break;
+				q = in[i_in++]; mo = P.combine_min_overlap;
+			}
+			const AsmMatch m = asm_best_match<NT>(A, list, nlist, q, mo, has_n);
 			if (m.aligned) asm_merge<NT>(A, list, m.k, q, m.offset, has_n);
-			else { asm_bar<NT>(); if (tid == 0) list[nlist] = (uint16_t)q; asm_bar<NT>(); ++nlist; }
-		}
-		const int n_pre = nlist; // :171
-		// ---- combine (:176 -> src/contig.nim:254-281): pass A without trimming, pass B with min_support
-		if (!A.s.sc[SC_STATUS]) {
-			int n2 = asm_combine_pass<NT>(A, list, nlist, other, 0, P.combine_min_overlap, has_n);
-			{ uint16_t *t = list; list = other; other = t; } nlist = n2;
-			if (!A.s.sc[SC_STATUS]) {
-				n2 = asm_combine_pass<NT>(A, list, nlist, other, P.combine_min_support, P.combine_min_overlap, has_n);
-				{ uint16_t *t = list; list = other; other = t; } nlist = n2;
-			}
+			else if (phase == 0 || A.s.nreads[q] > 0) { asm_bar<NT>(); if (tid == 0) list[nlist] = (uint16_t)q; asm_bar<NT>(); ++nlist; }
+			else { asm_free<NT>(A, q); asm_bar<NT>(); }
 		}
 		asm_bar<NT>();
 		// ---- results

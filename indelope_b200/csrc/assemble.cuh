@@ -112,6 +112,7 @@ __device__ int asm_eval(const Asm &A, const uint32_t *t0, const uint32_t *t1, co
 	if (n <= 0) return 0; // nothing compared: ma = 0, mm = 0
 	int ncorr = 0;
 	const int nwords = (n + 31) >> 5;
+	#pragma unroll 1
 	for (int w = 0; w < nwords; ++w) {
 		uint32_t m;
 		const int pos = o + 32 * w;
@@ -141,53 +142,78 @@ __device__ int asm_eval(const Asm &A, const uint32_t *t0, const uint32_t *t1, co
 struct AsmMatch { int k, offset, ma; bool aligned; };
 
 // best_match (:224-240) of slot q against list[0..nlist). Uniform result.
+// One lane per (contig, offset) candidate, a warp per contig.  A pair that cannot vote (fewer than 4 reads on either
+// side: every read of the greedy pass) needs an exact overlap, so a candidate is first screened on its first 32 bases
+// with two funnel shifts; only survivors run the full compare.  Every lane keeps its best key over all contigs
+// (matches, then lowest contig index, then first offset in scan order), one reduction per call finds the winner.
 template <int NT> __device__ AsmMatch asm_best_match(Asm &A, const uint16_t *list, int nlist, int q, int mo, bool has_n)
 {
 	const int tid = asm_tid<NT>(), lane = tid & 31, warp = tid >> 5;
 	const int qlen = A.s.len[q], qreads = A.s.nreads[q];
+	const int n2 = qlen - mo >= 0 ? qlen - mo : mo - qlen; // abs(omin), :78,114
 	asm_bar<NT>();
-	{ // stage the query planes (+ zero padding up to nw words)
+	{ // stage the query planes (zero padded two words past the end: the shifted reads of loop 2 run that far)
 		const int qw = (qlen + 31) >> 5;
 		const uint32_t *g0 = A.p0(q), *g1 = A.p1(q), *gn = A.pn(q);
-		for (int w = tid; w < A.nw; w += NT) {
+#pragma unroll 1
+		for (int w = tid; w < qw + 2 && w < A.nw; w += NT) {
 			const bool in = w < qw;
 			A.s.q0[w] = in ? g0[w] : 0u; A.s.q1[w] = in ? g1[w] : 0u; A.s.qn[w] = in ? gn[w] : 0u;
 		}
 	}
 	asm_bar<NT>();
 	const uint16_t *qsup = A.sup(q);
-	unsigned long long best = 0;
+	const uint32_t qf0 = A.s.q0[0], qf1 = A.s.q1[0], qfn = A.s.qn[0];
+	unsigned long long best = 0, tested = 0;
+#pragma unroll 1
 	for (int k = warp; k < nlist; k += (NT / 32)) {
 		const int t = list[k];
-		const int tlen = A.s.len[t], treads = A.s.nreads[t];
+		const int tlen = A.s.len[t];
 		const int omax = tlen - mo;
 		const int n1 = omax >= 0 ? omax + 1 : 0;
-		const int n2 = qlen - mo >= 0 ? qlen - mo : mo - qlen; // abs(omin), :78,114
-		const bool vote = qreads >= 4 && treads >= 4; // a vote needs support >= 4 on one side and reads >= 4 on the other (supports are 1..nreads)
-		const uint32_t *t0 = A.p0(t), *t1 = A.p1(t), *tn = A.pn(t);
-		const uint16_t *tsup = A.sup(t);
-		unsigned key = 0;
+		bool vote = false; // a vote needs support >= 4 on one side and reads >= 4 on the other (supports are 1..nreads)
+		if (qreads >= 4) vote = A.s.nreads[t] >= 4;
+		const uint32_t *t0 = A.p0(t), *t1 = t0 + A.nw, *tn = t1 + A.nw;
+		const uint32_t tf0 = t0[0], tf1 = t1[0], tfn = has_n ? tn[0] : 0u;
+		const unsigned long long kkey = (unsigned long long)(0xffff - k) << 16;
+#pragma unroll 1
 		for (int sidx = lane; sidx < n1 + n2; sidx += 32) {
 			const bool dir2 = sidx >= n1;
 			const int o = dir2 ? sidx - n1 + 1 : sidx;
-			const int ma = asm_eval(A, t0, t1, tn, tsup, qsup, qlen, tlen, qreads, treads, dir2, o, vote, has_n);
+			const int n = dir2 ? min(qlen - o, tlen) : min(qlen, tlen - o);
+			int ma = -1;
+			bool full = vote || n <= 0;
+			if (!full) { // exact overlap needed: screen the first word
+				uint32_t m;
+				const int w = o >> 5, sh = o & 31;
+				if (!dir2) {
+					m = (qf0 ^ __funnelshift_r(t0[w], t0[w + 1], sh)) | (qf1 ^ __funnelshift_r(t1[w], t1[w + 1], sh));
+					if (has_n) m |= qfn ^ __funnelshift_r(tn[w], tn[w + 1], sh);
+				} else {
+					m = (tf0 ^ __funnelshift_r(A.s.q0[w], A.s.q0[w + 1], sh)) | (tf1 ^ __funnelshift_r(A.s.q1[w], A.s.q1[w + 1], sh));
+					if (has_n) m |= tfn ^ __funnelshift_r(A.s.qn[w], A.s.qn[w + 1], sh);
+				}
+				if (n < 32) m &= (1u << n) - 1u;
+				if (!m) { if (n <= 32) ma = n; else full = true; }
+			}
+			if (full) ma = asm_eval(A, t0, t1, tn, A.sup(t), qsup, qlen, tlen, qreads, vote ? A.s.nreads[t] : 0, dir2, o, vote, has_n);
 			// first candidate needs ma >= mo-1 (best_ma starts at mo-1, best_mm at 1: :81-82,107); later ones strictly more
 			if (ma >= 0 && ma >= mo - 1) {
-				const unsigned kk = ((unsigned)(ma + 1) << 16) | (unsigned)(0xffff - sidx);
-				key = kk > key ? kk : key;
+				const unsigned long long k64 = ((unsigned long long)(unsigned)(ma + 1) << 32) | kkey | (unsigned long long)(0xffff - sidx);
+				best = k64 > best ? k64 : best;
 			}
 		}
-		key = __reduce_max_sync(FULL_MASK, key);
-		if (key) {
-			const unsigned long long k64 = ((unsigned long long)(key >> 16) << 32) | ((unsigned long long)(0xffff - k) << 16) | (key & 0xffff);
-			best = k64 > best ? k64 : best;
-		}
-		if (lane == 0) A.offsets += (unsigned long long)(n1 + n2);
+		tested += (unsigned long long)(n1 + n2);
 	}
-	if (lane == 0) A.s.best[warp] = best;
-	asm_bar<NT>();
-	best = 0;
-	for (int w2 = 0; w2 < (NT / 32); ++w2) { const unsigned long long b = A.s.best[w2]; best = b > best ? b : best; }
+#pragma unroll
+	for (int d = 16; d >= 1; d >>= 1) { const unsigned long long o = __shfl_xor_sync(FULL_MASK, best, d); best = o > best ? o : best; }
+	if (NT > 32) {
+		if (lane == 0) A.s.best[warp] = best;
+		asm_bar<NT>();
+		best = 0;
+		for (int w2 = 0; w2 < (NT / 32); ++w2) { const unsigned long long b = A.s.best[w2]; best = b > best ? b : best; }
+	}
+	if (lane == 0) A.offsets += tested;
 	AsmMatch m;
 	m.aligned = best != 0;
 	m.ma = (int)(best >> 32) - 1;
@@ -219,6 +245,7 @@ template <int NT> __device__ void asm_merge(Asm &A, uint16_t *list, int k, int q
 		if (vote) {
 			const bool dir2 = offset < 0; const int o = dir2 ? -offset : offset;
 			const int n = dir2 ? min(qlen - o, tlen) : min(qlen, tlen - o);
+			#pragma unroll 1
 			for (int w = 0; w * 32 < n; ++w) {
 				const int pos = o + 32 * w;
 				uint32_t m;
@@ -235,6 +262,7 @@ template <int NT> __device__ void asm_merge(Asm &A, uint16_t *list, int k, int q
 				}
 			}
 			if (nc > IDL_MAX_CORRECTIONS) { A.s.sc[SC_STATUS] |= IDL_RS_CORR_OVERFLOW; nc = IDL_MAX_CORRECTIONS; }
+			#pragma unroll 1
 			for (int c = 0; c < nc; ++c) {
 				const int qo = A.s.corr[3 * c], to = A.s.corr[3 * c + 1];
 				uint32_t **dst = A.s.corr[3 * c + 2] ? tp : qp, **src = A.s.corr[3 * c + 2] ? qp : tp;
@@ -254,16 +282,19 @@ template <int NT> __device__ void asm_merge(Asm &A, uint16_t *list, int k, int q
 		const int ao = -offset;
 		const int newlen = max(qlen, ao + tlen);
 		if (newlen > A.cap) { if (tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; asm_bar<NT>(); return; }
+		#pragma unroll 1
 		for (int i = ao + tid; i < ao + tlen; i += NT) {
 			unsigned val = tsup[i - ao];
 			if (i < qlen) {
 				bool dont = false;
+				#pragma unroll 1
 				for (int c = 0; c < nc; ++c) dont |= A.s.corr[3 * c] == i; // dont_overwrite holds qoff here (:170-171)
 				if (!dont) val += qsup[i];
 			}
 			qsup[i] = (uint16_t)val;
 		}
 		if (ao + tlen > qlen) { // append the target's tail: bases [qlen, ao+tlen) come from t[i-ao]
+			#pragma unroll 1
 			for (int w = (qlen >> 5) + tid; w * 32 < newlen; w += NT) {
 				const uint32_t low = qlen - 32 * w >= 32 ? 0xffffffffu : (qlen > 32 * w ? (1u << (qlen - 32 * w)) - 1u : 0u);
 				for (int pl = 0; pl < 3; ++pl) {
@@ -283,14 +314,17 @@ template <int NT> __device__ void asm_merge(Asm &A, uint16_t *list, int k, int q
 		const int o = offset;
 		const int newlen = max(tlen, o + qlen);
 		if (newlen > A.cap) { if (tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_CONTIG_OVERFLOW; asm_bar<NT>(); return; }
+		#pragma unroll 1
 		for (int i = o + tid; i < o + qlen; i += NT) {
 			if (i < tlen) {
 				bool dont = false;
+				#pragma unroll 1
 				for (int c = 0; c < nc; ++c) dont |= A.s.corr[3 * c + 1] == i; // toff (:172-173)
 				if (!dont) tsup[i] = (uint16_t)(tsup[i] + qsup[i - o]);
 			} else tsup[i] = qsup[i - o];
 		}
 		if (o + qlen > tlen) {
+			#pragma unroll 1
 			for (int w = (tlen >> 5) + tid; w * 32 < newlen; w += NT) {
 				const uint32_t low = tlen - 32 * w >= 32 ? 0xffffffffu : (tlen > 32 * w ? (1u << (tlen - 32 * w)) - 1u : 0u);
 				for (int pl = 0; pl < 3; ++pl) {
@@ -317,6 +351,7 @@ template <int NT> __device__ int asm_trim(Asm &A, int c, int min_support, bool h
 	asm_bar<NT>();
 	if (tid == 0) { A.s.sc[SC_TMP0] = 0x7fffffff; A.s.sc[SC_TMP1] = -1; }
 	asm_bar<NT>();
+	#pragma unroll 1
 	for (int i = tid; i < L - 1; i += NT) if (sp[i] >= ms) { atomicMin(&A.s.sc[SC_TMP0], i); break; }
 	asm_bar<NT>();
 	int a = A.s.sc[SC_TMP0];
@@ -327,6 +362,7 @@ template <int NT> __device__ int asm_trim(Asm &A, int c, int min_support, bool h
 		asm_bar<NT>();
 		return c;
 	}
+	#pragma unroll 1
 	for (int i = L - 1 - tid; i > a; i -= NT) if (sp[i] >= ms) { atomicMax(&A.s.sc[SC_TMP1], i); break; }
 	asm_bar<NT>();
 	int b = A.s.sc[SC_TMP1];
@@ -343,9 +379,11 @@ template <int NT> __device__ int asm_trim(Asm &A, int c, int min_support, bool h
 	const uint32_t *s0 = A.p0(c), *s1 = A.p1(c), *sn = A.pn(c);
 	uint32_t *d0 = A.p0(d), *d1 = A.p1(d), *dn = A.pn(d);
 	uint16_t *dsup = A.sup(d);
+	#pragma unroll 1
 	for (int w = tid; w * 32 < newlen; w += NT) {
 		d0[w] = get32(s0, a + 32 * w); d1[w] = get32(s1, a + 32 * w); dn[w] = has_n ? get32(sn, a + 32 * w) : 0u;
 	}
+	#pragma unroll 1
 	for (int i = tid; i < newlen; i += NT) dsup[i] = sp[a + i];
 	asm_bar<NT>();
 	if (tid == 0) { A.s.len[d] = newlen; A.s.nreads[d] = A.s.nreads[c]; A.s.start[d] = A.s.start[c] + a; }
@@ -375,6 +413,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 	}
 	const int tid = asm_tid<NT>();
 	const idl_params &P = args.P;
+	#pragma unroll 1
 	for (;;) {
 		asm_bar<NT>();
 		if (tid == 0) A.s.sc[SC_REGION] = (int)atomicAdd(args.small ? &args.cnt->region_next : &args.cnt->region_next2, 1u);
@@ -385,18 +424,22 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 		if ((R.n_reads <= ASM_SMALL_READS) != (args.small != 0)) continue; // the other launch assembles this region
 		// reset the slot allocator; detect non-ACGT bases in this region's reads and window
 		if (tid == 0) { A.s.sc[SC_NFREE] = A.ns; A.s.sc[SC_STATUS] = R.n_reads + 2 > (unsigned)A.ns ? IDL_RS_CONTIG_OVERFLOW : 0; A.s.sc[SC_HASN] = 0; }
+		#pragma unroll 1
 		for (int i = tid; i < A.ns; i += NT) A.s.freestk[i] = (uint16_t)(A.ns - 1 - i);
 		asm_bar<NT>();
 		{
 			int any = 0;
+			#pragma unroll 1
 			for (unsigned j = 0; j < R.n_reads; ++j) {
 				const idl_read rd = args.read[R.read_begin + j];
 				const uint32_t *pn = args.seqn + (rd.seq_off >> 5);
+				#pragma unroll 1
 				for (int w = tid; w * 32 < rd.len; w += NT) any |= pn[w] != 0;
 			}
 			if (any) A.s.sc[SC_HASN] = 1;
 		}
 		// unpack the reference window to 0..4 codes for kernel 2 / glue (src/ksw2/ksw2.nim:127-132)
+		#pragma unroll 1
 		for (unsigned i = tid; i < R.ref_len; i += NT) {
 			const unsigned b = R.ref_off + i;
 			const unsigned isn = (args.refn[b >> 5] >> (b & 31)) & 1u;
@@ -411,6 +454,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 		uint16_t *list = A.s.listA, *in = A.s.listB;
 		int nlist = 0, n_pre = 0, n_in = 0, usedi = -1, i_in = 0, phase = 0;
 		unsigned j = 0;
+		#pragma unroll 1
 		for (;;) {
 			int q = -1, mo = 0;
 			if (phase == 0) {
@@ -428,6 +472,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 						uint32_t *g0 = A.p0(q), *g1 = A.p1(q), *gn = A.pn(q);
 						uint16_t *gs = A.sup(q);
 						const unsigned base = rd.seq_off + rd.trim_a;
+						#pragma unroll 1
 						for (int w = tid; w * 32 < tl; w += NT) {
 							const unsigned b = base + 32u * w;         // first base of this plane word
 							const unsigned wi = b >> 4, sh = 2 * (b & 15);
@@ -440,6 +485,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 							g1[w] = compress_even(bits >> 1) & m;
 							gn[w] = has_n ? (get32(args.seqn, (int)b) & m) : 0u;
 						}
+						#pragma unroll 1
 						for (int i = tid; i < tl; i += NT) gs[i] = 1;
 						if (tid == 0) { A.s.len[q] = tl; A.s.nreads[q] = 1; A.s.start[q] = rd.start + rd.trim_a; }
 					}
@@ -455,6 +501,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 				const int min_support = phase == 1 ? 0 : P.combine_min_support; // pass A merges without trimming (:260), pass B trims (:265-267)
 				{ uint16_t *t = list; list = in; in = t; } n_in = nlist; nlist = 0;
 				usedi = -1;
+				#pragma unroll 1
 				for (int i = 0; i < n_in; ++i) {
 					int c = in[i];
 					if (min_support > 0) {
@@ -489,6 +536,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 		if (status) nlist = 0;
 		if (tid == 0) {
 			unsigned total = 0;
+			#pragma unroll 1
 			for (int i = 0; i < nlist; ++i) total += (unsigned)((A.s.len[list[i]] + 3) & ~3);
 			A.s.sc[SC_TMP0] = (int)atomicAdd(&args.cnt->n_contigs, (unsigned)nlist);
 			A.s.sc[SC_TMP1] = (int)atomicAdd(&args.cnt->n_contig_bases, total);
@@ -501,12 +549,14 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 			args.rres[rg] = rr;
 		}
 		if (cbegin + (unsigned)nlist > args.cap_contigs) { if (tid == 0) atomicOr(&args.cnt->overflow, 1u); continue; }
+		#pragma unroll 1
 		for (int i = 0; i < nlist; ++i) {
 			const int c = list[i];
 			const int L = A.s.len[c];
 			if (boff + (unsigned)L > args.cap_bases) { if (tid == 0) atomicOr(&args.cnt->overflow, 2u); break; }
 			const uint32_t *g0 = A.p0(c), *g1 = A.p1(c), *gn = A.pn(c);
 			const uint16_t *gs = A.sup(c);
+			#pragma unroll 1
 			for (int x = tid; x < L; x += NT) {
 				const unsigned code = ((g0[x >> 5] >> (x & 31)) & 1u) | (((g1[x >> 5] >> (x & 31)) & 1u) << 1);
 				const bool isn = has_n && ((gn[x >> 5] >> (x & 31)) & 1u);

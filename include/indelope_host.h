@@ -77,6 +77,15 @@ void idlh_dataset_counts(const idlh_dataset *d, int64_t counts[4]);
 /* truth table: chrom, pos, ins_len, del_len, hom, is_tr (6 int64 per event) */
 int64_t idlh_dataset_truth(const idlh_dataset *d, int64_t *out, int64_t cap);
 
+/* ---- files (indelope_b200/csrc/host/bamio.cpp, written from the SAM/BAM specification on zlib) ----
+ * idlh_load: reference FASTA (hts-nim open_fai / fai.get, src/indelope.nim:583) + coordinate-sorted BAM read front to back,
+ * the order `for target in targets: b.querys(target.name)` visits (:527,599-602); `threads` inflate BGZF blocks in
+ * parallel (the -t option, :566).  Returns NULL and a message in err on failure.  CRAM is not supported.
+ * idlh_write_fasta writes path and path.fai; idlh_write_bam writes a BGZF-compressed BAM (deflate level 0-9) of the reads. */
+idlh_dataset *idlh_load(const char *fasta_path, const char *bam_path, int threads, char *err, size_t errlen);
+int idlh_write_fasta(const idlh_dataset *d, const char *path);
+int idlh_write_bam(const idlh_dataset *d, const char *path, int level);
+
 /* gen_roi over every target (src/indelope.nim:515-545,601-602), regions in emission order */
 idlh_rois *idlh_sweep(const idlh_dataset *d, int32_t min_event_support, int32_t min_read_coverage, int32_t max_read_coverage);
 void idlh_rois_free(idlh_rois *r);

@@ -1,7 +1,8 @@
 """Build the in-tree native libraries.
 
   libindelope_cuda.so  -- CUDA kernels + the C ABI of include/indelope_cuda.h   (nvcc, sm_100a only)
-  libindelope_host.so  -- C++ host stand-in of include/indelope_host.h          (g++)
+  libindelope_host.so  -- C++ host stand-in of include/indelope_host.h          (g++, zlib)
+  indelope             -- the command line of the reference (src/indelope.nim:553-608) over the two libraries
 
 Both are written next to this file so that they travel to the GPU box with the repo snapshot.
 """
@@ -16,9 +17,11 @@ INC = os.path.join(ROOT, "include")
 CSRC = os.path.join(HERE, "csrc")
 CUDA_LIB = os.path.join(HERE, "libindelope_cuda.so")
 HOST_LIB = os.path.join(HERE, "libindelope_host.so")
+CLI_BIN = os.path.join(HERE, "indelope")
 
 CUDA_SRCS = ["pipeline.cu"]
-HOST_SRCS = ["host/synth_sweep.cpp", "host/pack_vcf.cpp"]
+HOST_SRCS = ["host/synth_sweep.cpp", "host/pack_vcf.cpp", "host/bamio.cpp"]
+CLI_SRCS = ["host/indelope_main.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 
@@ -44,7 +47,7 @@ def nvcc_path():
 
 def build_host(force=False, verbose=False):
     if force or _newer(HOST_LIB, _deps(HOST_SRCS)):
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", INC] + [os.path.join(CSRC, s) for s in HOST_SRCS] + ["-o", HOST_LIB]
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", INC] + [os.path.join(CSRC, s) for s in HOST_SRCS] + ["-o", HOST_LIB, "-lz", "-lpthread"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
@@ -66,9 +69,21 @@ def build_cuda(force=False, verbose=False):
     return CUDA_LIB
 
 
+def build_cli(force=False, verbose=False):
+    """the `indelope` binary; finds both libraries next to itself ($ORIGIN)"""
+    if force or _newer(CLI_BIN, _deps(CLI_SRCS) + [HOST_LIB, CUDA_LIB]):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", INC] + [os.path.join(CSRC, s) for s in CLI_SRCS] + [
+            "-o", CLI_BIN, "-L", HERE, "-lindelope_host", "-lindelope_cuda", "-Wl,-rpath,$ORIGIN"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    return CLI_BIN
+
+
 def build_all(force=False, verbose=False):
     build_host(force, verbose)
     build_cuda(force, verbose)
+    build_cli(force, verbose)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,137 @@
+// indelope_b200/csrc/host/indelope_main.cpp -- the `indelope` command line, drop-in for the reference's main module
+// (src/indelope.nim:553-608):
+//
+//     indelope [options] <reference> <BAM>          VCF on stdout
+//
+// Same options, defaults and output as the reference's docopt block (:556-572).  The host part -- BAM sweep, evidence
+// counters, coverage-gap chunking, VCF text -- is the C++ stand-in of libindelope_host.so (the reference keeps it in Nim);
+// every region of interest goes through libindelope_cuda.so in batches, two in flight.  There is no CPU path: without a
+// CUDA device the program stops with an error.  CRAM input and the undocumented `single-site` debugging mode (:578-586)
+// are not provided.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+#include "indelope_cuda.h"
+#include "indelope_host.h"
+
+static const char USAGE[] =
+	"indelope 0.0.1 (B200)\n"
+	"\n"
+	"  Usage: indelope [options] <reference> <BAM>\n"
+	"\n"
+	"Arguments:\n"
+	"\n"
+	"  <reference>     reference fasta file.\n"
+	"  <BAM>           call variants in this file (coordinate sorted).\n"
+	"\n"
+	"Options:\n"
+	"\n"
+	"  -m --min-reads <INT>        minimum number of reads to send for alignment [default: 3]\n"
+	"  -c --min-contig-len <INT>   minimum contig length to send for alignment [default: 73]\n"
+	"  -e --min-event-len <INT>    minimum size of indel to report [default: 4]\n"
+	"  -t --threads <INT>          number of bam decompression threads [default: 1]\n"
+	"  -d --device <INT>           CUDA device [default: 0]\n"
+	"  -h --help                   show help\n";
+
+struct Lane { idl_batch *batch = nullptr; size_t cap[4] = {0, 0, 0, 0}; };
+struct Flight { int64_t lo; uint64_t ticket; };
+
+static int die(const char *what, const std::string &why) { fprintf(stderr, "indelope: %s: %s\n", what, why.c_str()); return 1; }
+
+int main(int argc, char **argv)
+{
+	int min_reads = 3, min_ctg_len = 73, min_event_len = 4, threads = 1, device = 0;
+	std::vector<std::string> pos;
+	for (int i = 1; i < argc; ++i) {
+		const std::string a = argv[i];
+		auto int_opt = [&](const char *s, const char *l, int &dst) -> int { // 0 no match, 1 consumed, -1 error
+			std::string v;
+			if (a == s || a == l) { if (i + 1 >= argc) return -1; v = argv[++i]; }
+			else if (a.rfind(std::string(l) + "=", 0) == 0) v = a.substr(strlen(l) + 1);
+			else if (a.size() > 2 && a.compare(0, 2, s) == 0 && a[1] != '-') v = a.substr(2);
+			else return 0;
+			char *end = nullptr; const long x = strtol(v.c_str(), &end, 10);
+			if (v.empty() || *end) return -1;
+			dst = (int)x; return 1;
+		};
+		if (a == "-h" || a == "--help") { fputs(USAGE, stdout); return 0; }
+		if (a == "--version") { puts("indelope 0.0.1"); return 0; }
+		int rc;
+		if ((rc = int_opt("-m", "--min-reads", min_reads)) || (rc = int_opt("-c", "--min-contig-len", min_ctg_len)) ||
+		    (rc = int_opt("-e", "--min-event-len", min_event_len)) || (rc = int_opt("-t", "--threads", threads)) || (rc = int_opt("-d", "--device", device))) {
+			if (rc < 0) { fputs(USAGE, stderr); return 1; }
+			continue;
+		}
+		if (a.size() > 1 && a[0] == '-') { fputs(USAGE, stderr); return 1; }
+		pos.push_back(a);
+	}
+	if (pos.size() != 2) { fputs(USAGE, stderr); return 1; }
+
+	char err[512] = {0};
+	idlh_dataset *data = idlh_load(pos[0].c_str(), pos[1].c_str(), threads, err, sizeof err);
+	if (!data) return die("input", err);
+	// gen_roi(b, target, min_read_coverage=min_reads, min_event_support=max(3, min_reads-2)), src/indelope.nim:602
+	idlh_rois *rois = idlh_sweep(data, min_reads - 2 > 3 ? min_reads - 2 : 3, min_reads, 600);
+	const idlh_roiset *rs = idlh_rois_view(rois);
+
+	idl_params P;
+	idl_default_params(&P);
+	P.min_reads = min_reads; P.min_ctg_len = min_ctg_len; P.min_event_len = min_event_len;
+	idl_ctx *ctx = nullptr;
+	int rc = idl_create(device, &P, &ctx);
+	if (rc != IDL_OK) return die("libindelope_cuda", std::string(idl_strerror(rc)) + " (this program has no CPU path; it needs a CUDA device)");
+
+	{ char *h = idlh_vcf_header(rs); fputs(h, stdout); idlh_free(h); } // echo header % [b.contig_header, "sample"], :599
+	idlh_vcf *writer = idlh_vcf_new();
+	std::vector<Lane> lanes((size_t)(P.n_streams > 0 ? P.n_streams : 1));
+	std::deque<Flight> inflight;
+	int status = 0;
+	auto drain = [&]() -> bool {
+		const Flight f = inflight.front(); inflight.pop_front();
+		const idl_results *res = nullptr;
+		const int r = idl_wait(ctx, f.ticket, &res);
+		if (r != IDL_OK) { status = die("idl_wait", std::string(idl_strerror(r)) + " " + idl_last_cuda_error(ctx)); return false; }
+		char *dump = nullptr;
+		char *txt = idlh_vcf_records(writer, rs, f.lo, &P, res, 0, &dump);
+		fputs(txt, stdout);
+		idlh_free(txt); idlh_free(dump);
+		idl_release(ctx, f.ticket);
+		return true;
+	};
+	// contiguous slices of the region list, bounded by reads and regions per batch; emission order is kept (the dedup of :604-608 depends on it)
+	const int64_t max_reads = 400000, max_regions = 20000;
+	int64_t a = 0; size_t nb = 0;
+	while (a < rs->n_rois && !status) {
+		int64_t b = a, acc = 0;
+		while (b < rs->n_rois && (b == a || (acc + rs->roi_n_reads[b] <= max_reads && b - a < max_regions))) acc += rs->roi_n_reads[b++];
+		if (inflight.size() >= lanes.size() && !drain()) break;
+		Lane &L = lanes[nb % lanes.size()];
+		size_t need[4] = {(size_t)(b - a), 0, 0, 0};
+		idlh_pack_size(rs, a, b, &P, &need[1], &need[2], &need[3]);
+		bool grow = L.batch == nullptr;
+		for (int k = 0; k < 4; ++k) grow |= need[k] > L.cap[k];
+		if (grow) {
+			if (L.batch) idl_batch_free(ctx, L.batch);
+			for (int k = 0; k < 4; ++k) L.cap[k] = need[k] + need[k] / 4 + 64;
+			rc = idl_batch_alloc(ctx, L.cap[0], L.cap[1], L.cap[2], L.cap[3], &L.batch);
+			if (rc != IDL_OK) { status = die("idl_batch_alloc", idl_strerror(rc)); break; }
+		}
+		if (idlh_pack(rs, a, b, &P, L.batch) != 0) { status = die("idlh_pack", "batch does not fit"); break; }
+		uint64_t ticket = 0;
+		rc = idl_submit(ctx, L.batch, &ticket);
+		if (rc != IDL_OK) { status = die("idl_submit", std::string(idl_strerror(rc)) + " " + idl_last_cuda_error(ctx)); break; }
+		inflight.push_back({a, ticket});
+		a = b; ++nb;
+	}
+	while (!inflight.empty() && !status) if (!drain()) break;
+	for (Lane &L : lanes) if (L.batch) idl_batch_free(ctx, L.batch);
+	idlh_vcf_free(writer);
+	idl_destroy(ctx);
+	idlh_rois_free(rois);
+	idlh_dataset_free(data);
+	return status;
+}

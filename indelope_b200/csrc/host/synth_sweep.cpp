@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include "indelope_host.h"
+#include "dataset.h"
 
 namespace {
 
@@ -32,23 +33,10 @@ struct Rng {
 	}
 };
 
-struct Event { int chrom; int64_t pos; std::string ins; int dlen; bool hom; bool tr; };
-
-struct ReadRec {
-	int32_t chrom, start, stop; uint8_t mapq; uint16_t flag; int32_t len; int64_t seq_off; int64_t cig_off; int32_t n_cig; uint64_t order;
-};
+using Event = IdlhEvent;
+using ReadRec = IdlhReadRec;
 
 } // namespace
-
-struct idlh_dataset {
-	idlh_synth_params P;
-	std::vector<std::string> names;
-	std::vector<std::vector<uint8_t>> chroms;
-	std::vector<Event> events;
-	std::vector<ReadRec> reads; // coordinate sorted per chromosome
-	std::vector<uint8_t> bases, quals;
-	std::vector<uint32_t> cigars; // BAM encoding len<<4|op (M0 I1 D2 S4)
-};
 
 struct idlh_rois {
 	std::vector<int32_t> start, stop, len; std::vector<uint8_t> mapq; std::vector<uint16_t> flag; std::vector<int64_t> seq_off;

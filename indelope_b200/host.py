@@ -49,6 +49,10 @@ def lib():
         L.idlh_dataset_counts.argtypes = [C.c_void_p, i64p]
         L.idlh_dataset_truth.argtypes = [C.c_void_p, i64p, C.c_int64]
         L.idlh_dataset_truth.restype = C.c_int64
+        L.idlh_load.restype = C.c_void_p
+        L.idlh_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+        L.idlh_write_fasta.argtypes = [C.c_void_p, C.c_char_p]
+        L.idlh_write_bam.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.idlh_sweep.restype = C.c_void_p
         L.idlh_sweep.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         L.idlh_rois_free.argtypes = [C.c_void_p]
@@ -115,12 +119,34 @@ CONFIGS = {
 class Dataset:
     """synthetic reference + coordinate-sorted reads (the BAM/FASTA stand-in)"""
 
-    def __init__(self, params=None, **kw):
-        self.params = params if params is not None else synth_params(**kw)
-        self.h = lib().idlh_synth(C.byref(self.params))
+    def __init__(self, params=None, _handle=None, **kw):
+        if _handle is not None:
+            self.params, self.h = None, _handle
+        else:
+            self.params = params if params is not None else synth_params(**kw)
+            self.h = lib().idlh_synth(C.byref(self.params))
         c = (C.c_int64 * 4)()
         lib().idlh_dataset_counts(self.h, c)
         self.n_reads, self.n_bases, self.n_events, self.n_chroms = list(c)
+
+    @classmethod
+    def load(cls, fasta, bam, threads=1):
+        """reference FASTA + coordinate-sorted BAM from disk (libindelope_host's own BGZF/BAM reader)"""
+        err = C.create_string_buffer(512)
+        h = lib().idlh_load(str(fasta).encode(), str(bam).encode(), threads, err, 512)
+        if not h:
+            raise IOError(err.value.decode())
+        return cls(_handle=h)
+
+    def write_fasta(self, path):
+        """FASTA (60 columns) + path.fai"""
+        if lib().idlh_write_fasta(self.h, str(path).encode()) != 0:
+            raise IOError("cannot write %s" % path)
+
+    def write_bam(self, path, level=1):
+        """coordinate-sorted BAM of the reads (BGZF, deflate level 0-9)"""
+        if lib().idlh_write_bam(self.h, str(path).encode(), level) != 0:
+            raise IOError("cannot write %s" % path)
 
     def truth(self):
         out = np.zeros((max(self.n_events, 1), 6), dtype=np.int64)

@@ -1,0 +1,123 @@
+"""File I/O of the host stand-in (indelope_b200/csrc/host/bamio.cpp): a synthetic dataset written as FASTA + BAM and read
+back must give the same reads, the same regions of interest and the same oracle VCF; the BAM must be what the
+specification says (checked here with Python's gzip on the BGZF members, independent of the C++ reader)."""
+import gzip
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from indelope_b200 import build, host
+from oracle import pyoracle as orc
+import idl_testutil as util
+
+CALL = dict(min_reads=5, min_ctg_len=73, min_event_len=5)
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("io")
+    ds = util.small_dataset("pr1", chrom_len=120_000, n_events=24, max_indel=40, n_chroms=2, n_base_rate=0.0005, dup_fraction=0.02)
+    fa, bam = str(d / "ref.fa"), str(d / "reads.bam")
+    ds.write_fasta(fa)
+    ds.write_bam(bam, level=1)
+    return ds, fa, bam
+
+
+def test_bam_is_spec_conformant(files):
+    ds, fa, bam = files
+    raw = open(bam, "rb").read()
+    assert raw[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")  # BGZF EOF marker
+    data = gzip.decompress(raw)  # concatenated gzip members
+    assert data[:4] == b"BAM\x01"
+    l_text, = struct.unpack_from("<i", data, 4)
+    text = data[8:8 + l_text].decode()
+    assert text.startswith("@HD\tVN:1.6\tSO:coordinate") and "@SQ\tSN:chrS1\tLN:120000" in text
+    at = 8 + l_text
+    n_ref, = struct.unpack_from("<i", data, at); at += 4
+    assert n_ref == 2
+    for _ in range(n_ref):
+        l_name, = struct.unpack_from("<i", data, at); at += 4 + l_name + 4
+    rois = ds.sweep(min_reads=5)  # keep the owner alive: arrays() are views
+    a = rois.arrays()
+    n = 0
+    while at < len(data):
+        block, ref_id, pos, l_name, mapq, _bin, n_cig, flag, l_seq = struct.unpack_from("<iiiBBHHHi", data, at)
+        assert pos == a["start"][n] and mapq == a["mapq"][n] and flag == a["flag"][n] and l_seq == a["len"][n]
+        at += 4 + block; n += 1
+    assert n == len(a["start"])
+
+
+def test_fasta_and_fai(files):
+    ds, fa, bam = files
+    lines = open(fa).read().split("\n")
+    assert lines[0] == ">chrS1" and all(len(l) <= 60 for l in lines)
+    fai = [l.split("\t") for l in open(fa + ".fai").read().strip().split("\n")]
+    assert [f[0] for f in fai] == ["chrS1", "chrS2"] and fai[0][1] == "120000" and fai[0][3:] == ["60", "61"]
+    txt = open(fa, "rb").read()
+    off = int(fai[1][2])
+    assert txt[off - 7:off] == b">chrS2\n"
+
+
+def test_round_trip_gives_identical_regions_and_oracle_vcf(files):
+    ds, fa, bam = files
+    back = host.Dataset.load(fa, bam, threads=3)
+    ra, rb = ds.sweep(min_reads=5), back.sweep(min_reads=5)  # keep the owners alive: arrays() are views
+    a, b = ra.arrays(), rb.arrays()
+    for k in ("start", "stop", "mapq", "flag", "len", "roi_chrom", "roi_start", "roi_stop", "roi_read_begin", "roi_n_reads", "read_idx"):
+        assert np.array_equal(a[k], b[k]), k
+
+    def gather(x, key):  # per-read strings in read order (the generator's pool is in creation order, the file's in file order)
+        idx = np.concatenate([np.arange(o, o + l) for o, l in zip(x["seq_off"], x["len"])])
+        return x[key][idx]
+    assert np.array_equal(gather(a, "bases"), gather(b, "bases")) and np.array_equal(gather(a, "quals"), gather(b, "quals"))
+    assert a["chrom_names"] == b["chrom_names"] and all(np.array_equal(x, y) for x, y in zip(a["chrom_seqs"], b["chrom_seqs"]))
+    assert len(a["roi_start"]) > 10
+    _, v1, _ = orc.call(a, dump_level=0, **CALL)
+    _, v2, _ = orc.call(b, dump_level=0, **CALL)
+    assert v1 == v2 and v1.count("\n") > 3
+
+
+def test_reader_rejects_bad_input(files, tmp_path):
+    ds, fa, bam = files
+    with pytest.raises(IOError, match="cannot open"):
+        host.Dataset.load(fa, str(tmp_path / "missing.bam"))
+    bad = tmp_path / "bad.bam"
+    bad.write_bytes(b"not a bam")
+    with pytest.raises(IOError):
+        host.Dataset.load(fa, str(bad))
+    raw = bytearray(open(bam, "rb").read())
+    raw[200] ^= 0xff  # corrupt the first block: inflate error or CRC mismatch
+    (tmp_path / "corrupt.bam").write_bytes(bytes(raw))
+    with pytest.raises(IOError):
+        host.Dataset.load(fa, str(tmp_path / "corrupt.bam"))
+    fa2 = tmp_path / "short.fa"
+    fa2.write_text(">chrS1\nACGT\n>chrS2\nACGT\n")
+    with pytest.raises(IOError, match="different length"):
+        host.Dataset.load(str(fa2), bam)
+
+
+def test_cli_help_and_no_cpu_path(files):
+    ds, fa, bam = files
+    exe = build.build_cli()
+    out = subprocess.run([exe, "--help"], capture_output=True, text=True)
+    assert out.returncode == 0 and "--min-event-len" in out.stdout and "--min-reads" in out.stdout and "--threads" in out.stdout
+    assert subprocess.run([exe, fa], capture_output=True).returncode == 1
+    if not util.has_gpu():
+        r = subprocess.run([exe, "--min-event-len", "5", "--min-reads", "5", fa, bam], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU path" in r.stderr and r.stdout == ""  # fails loudly, prints nothing
+
+
+@pytest.mark.gpu
+def test_cli_vcf_is_byte_identical_to_the_oracle(files):
+    """`indelope --min-event-len 5 --min-reads 5 ref.fa reads.bam` (BASELINE.json configs[0] command line) on real files"""
+    ds, fa, bam = files
+    exe = build.build_cli()
+    r = subprocess.run([exe, "--min-event-len", "5", "--min-reads", "5", "-t", "2", fa, bam], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rois = ds.sweep(min_reads=5)
+    _, ovcf, cnt = orc.call(rois.arrays(), dump_level=0, **CALL)
+    assert r.stdout == rois.header() + ovcf
+    assert cnt["variants"] >= 3

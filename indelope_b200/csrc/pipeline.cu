@@ -266,7 +266,8 @@ int stage_batch(idl_ctx *ctx, Lane &L, const idl_batch *b, bool copy)
 	return IDL_OK;
 }
 
-int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
+// record_start: the device-resident timing leg has no copies to wait for, so its clock starts here, after the host-side sizing
+int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = false)
 {
 	const idl_params &P = ctx->P;
 	// pool capacities: every contig holds >= 1 read; an aligned contig holds >= max(1, min_reads) reads and a region aligns <= max_contigs
@@ -317,6 +318,7 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b)
 	CK(L.pmat.ensure(n_groups * p_cap));
 	CK(L.cig_scratch.ensure(n_groups * (size_t)ctx->cig_cap * 4));
 	CK(L.seq_spill.ensure(n_groups * (size_t)seq_spill_cap));
+	if (record_start) { CK(cudaEventRecord(L.ev[EV_START], L.stream)); CK(cudaEventRecord(L.ev[EV_H2D], L.stream)); }
 	CK(cudaMemsetAsync(L.cnt.p, 0, sizeof(DevCounters), L.stream));
 	CK(cudaMemsetAsync(L.sort_misc.p, 0, 6 * SORT_BUCKETS * sizeof(unsigned), L.stream));
 	L.launches = 0;
@@ -447,9 +449,7 @@ int idl_run_resident(idl_ctx *ctx, idl_batch *b, uint64_t *ticket)
 	if (L.state != 0) return IDL_E_BUSY;
 	if (!L.resident || L.n_regions != b->n_regions || L.n_reads != b->n_reads) return IDL_E_ARG;
 	L.payload = false;
-	CK(cudaEventRecord(L.ev[EV_START], L.stream));
-	CK(cudaEventRecord(L.ev[EV_H2D], L.stream));
-	int rc = launch_chain(ctx, L, b);
+	int rc = launch_chain(ctx, L, b, true);
 	if (rc) return rc;
 	L.ticket = ctx->next_ticket++; L.state = 1;
 	*ticket = L.ticket;

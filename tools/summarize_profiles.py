@@ -90,10 +90,58 @@ def launches(tag):
             f.write("%-34s launches=%3d total_us=%12.1f share=%6.3f avg_us=%10.1f\n" % (k, len(v), sum(v), sum(v) / tot, sum(v) / len(v)))
 
 
+def traffic(tag):
+    """per-kernel DRAM bytes / instructions / pipe utilisation at the full default workload -> profiles/<tag>_traffic.json (bench.py reads it)"""
+    import json
+    src = os.path.join(OUT, "traffic_full.csv")
+    if not os.path.exists(src):
+        return
+    shutil.copy(src, os.path.join(PROF, tag + "_traffic_full.csv"))
+    hdr, per = None, collections.defaultdict(lambda: collections.defaultdict(list))
+    for r in csv.reader(open(src)):
+        if len(r) > 5 and r[0] == "ID":
+            hdr = r; continue
+        if hdr is None or len(r) != len(hdr):
+            continue
+        d = dict(zip(hdr, r))
+        v = float(d["Metric Value"].replace(",", ""))
+        if d["Metric Name"] == "gpu__time_duration.sum":
+            v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(d["Metric Unit"], 1.0)
+        if d["Metric Unit"] in ("Kbyte", "Mbyte", "Gbyte"):
+            v *= {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[d["Metric Unit"]]
+        per[d["Kernel Name"].split("(")[0].replace("void ", "")][d["Metric Name"]].append(v)
+    out = {}
+    for full, m in per.items():
+        # the resident leg is the SECOND launch of each kernel (one warm-up first; the end-to-end leg's smaller launches follow);
+        # the two assemble_kernel variants of a step are summed
+        k = full.split("<")[0]
+        def second(name):
+            v = m.get(name, [])
+            return v[1] if len(v) > 1 else (v[0] if v else None)
+        rd, wr = second("dram__bytes_read.sum") or 0, second("dram__bytes_write.sum") or 0
+        cur = {"dram_bytes_per_launch": rd + wr, "read": rd, "write": wr, "ncu_ms": second("gpu__time_duration.sum"),
+               "thread_inst": second("smsp__thread_inst_executed.sum"), "warp_inst": second("smsp__inst_executed.sum"),
+               "pipe_alu_pct": second("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+               "issue_active_pct": second("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "warps_active_pct": second("sm__warps_active.avg.pct_of_peak_sustained_active")}
+        if k in out:
+            for f in ("dram_bytes_per_launch", "read", "write", "ncu_ms", "thread_inst", "warp_inst"):
+                out[k][f] = (out[k][f] or 0) + (cur[f] or 0)
+            for f in ("pipe_alu_pct", "issue_active_pct", "warps_active_pct"):
+                out[k][f] = max(out[k][f] or 0, cur[f] or 0)
+        else:
+            out[k] = cur
+    out["_how"] = ("ncu --metrics dram__bytes_*,smsp__thread_inst_executed.sum,... --clock-control none on `python bench.py --steps 1 --warmup 1` "
+                   "(default chr1 workload), second launch of each kernel = the device-resident leg; profiles/%s_traffic_full.csv" % tag)
+    json.dump(out, open(os.path.join(PROF, tag + "_traffic.json"), "w"), indent=1)
+    print("wrote traffic json")
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
+    traffic(tag)
     for rep in sorted(glob.glob(os.path.join(OUT, "prof_*.ncu-rep"))):
         name = os.path.basename(rep)[5:-8]
         with open(os.path.join(PROF, "%s_%s.txt" % (tag, name)), "w") as f:

@@ -32,7 +32,7 @@ def parse():
     ap.add_argument("--workload", default="chr1", help="key of indelope_b200.host.CONFIGS")
     ap.add_argument("--scale", type=float, default=1.0, help="scale the number of planted events (tests)")
     ap.add_argument("--cpu-sample", type=int, default=12000, help="regions timed by the cpu_baseline leg")
-    ap.add_argument("--e2e-batches", type=int, default=8)
+    ap.add_argument("--e2e-batches", type=int, default=4)
     return ap.parse_args()
 
 

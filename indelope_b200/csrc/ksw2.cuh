@@ -375,7 +375,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 			}
 		}
 		const int hen = (int)ghen - goff;
-		g_high |= (mg | ghen) >= 0xF000u;
+		g_high |= (unsigned)(mg >= 0xF000u) | (unsigned)(ghen >= 0xF000u);
 		const int mh = (int)mg - goff;
 		int max_H = hen, max_t = en0; // the initial candidate (H[en0], en0) wins every tie (:318-321)
 		// The position of the band max matters only when it becomes the new overall max or when z-drop can fire

@@ -84,3 +84,29 @@ def test_production_shapes_many(ctx):
         B.append((r, base[:tl].copy(), 5, -1, -1))
     assert check(ctx, A) == []
     assert check(ctx, B) == []
+
+
+def test_band_leaves_the_matrix_on_the_right(ctx):
+    """target much shorter than the query under a band: the last diagonals have a one-column band whose H[en0] is built from
+    a column that left the band earlier (the uint16 score ring re-bases it), ksw2_extz2_sse.c:318"""
+    rng = np.random.default_rng(5)
+    pairs = []
+    for ql, tl, w in [(300, 100, 50), (400, 64, 50), (257, 33, 20), (500, 180, 10), (90, 17, 3), (200, 1, 50), (150, 2, 1)]:
+        base = rng.integers(0, 4, ql + 10).astype(np.uint8)
+        pairs.append((base[:ql].copy(), base[:tl].copy(), 4, w, 10_000))  # z-drop out of the way: run until the band is exhausted
+    for p in pairs:  # one parameter set per call
+        assert check(ctx, [p]) == []
+        assert check(ctx, [(p[0], p[1], 4, p[3], -1)]) == []
+
+
+def test_long_alignments_and_score_window(ctx):
+    """a few kb per side is inside the uint16 score window of the kernel; far beyond it the alignment is reported as a capacity
+    status (negative), never returned wrong"""
+    rng = np.random.default_rng(9)
+    base = rng.integers(0, 4, 4200).astype(np.uint8)
+    q = base[:3000].copy(); t = np.concatenate([base[:1500], base[1530:3300]])
+    assert check(ctx, [(q, t, 4, 50, 400)]) == []
+    assert check(ctx, [(q[:400], t[:1000], 5, -1, -1)]) == []  # unbanded: the whole anti-diagonal lives in the shared-memory rings
+    big = rng.integers(0, 4, 9000).astype(np.uint8)
+    f, c, extra, _ = ctx.ksw2_batch([big[:4500]], [big[:8200]], gapo=4, gape=1, w=50, zdrop=400)  # (qlen + tlen)(q + e) leaves the window
+    assert extra[0]["status"] < 0 and f[0]["n_cigar"] == 0

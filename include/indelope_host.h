@@ -86,6 +86,20 @@ idlh_dataset *idlh_load(const char *fasta_path, const char *bam_path, int thread
 int idlh_write_fasta(const idlh_dataset *d, const char *path);
 int idlh_write_bam(const idlh_dataset *d, const char *path, int level);
 
+/* Streaming twin of idlh_load + idlh_sweep for files that do not fit in memory: the BAM is read front to back, BGZF blocks
+ * are inflated by `threads` workers, and gen_roi (src/indelope.nim:515-545) runs incrementally over the records; the
+ * regions and their read lists are the same as the whole-file sweep's (bamio.cpp explains why).  idlh_stream_next sweeps
+ * on until the regions collected hold at least target_reads reads (or the file ends) and returns them as a self-contained
+ * group (regions in emission order; free with idlh_rois_free); NULL after the last group, or on error with a message in
+ * err.  idlh_stream_targets gives a view without regions (contig names and lengths, for the VCF header). */
+typedef struct idlh_stream idlh_stream;
+idlh_stream *idlh_stream_open(const char *fasta_path, const char *bam_path, int threads, int32_t min_event_support, int32_t min_read_coverage,
+                              int32_t max_read_coverage, char *err, size_t errlen);
+idlh_rois *idlh_stream_next(idlh_stream *s, int64_t target_reads, char *err, size_t errlen);
+idlh_rois *idlh_stream_targets(const idlh_stream *s);
+void idlh_stream_counts(const idlh_stream *s, int64_t counts[2]);   /* BAM records read, regions emitted so far */
+void idlh_stream_close(idlh_stream *s);
+
 /* gen_roi over every target (src/indelope.nim:515-545,601-602), regions in emission order */
 idlh_rois *idlh_sweep(const idlh_dataset *d, int32_t min_event_support, int32_t min_read_coverage, int32_t max_read_coverage);
 void idlh_rois_free(idlh_rois *r);

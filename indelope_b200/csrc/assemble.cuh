@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 						if (tlen < 0 || cr.start < R.ref_start) tlen = 0;
 						ar.ref_len = tlen;
 						args.ares[ai] = ar;
-						const uint8_t key = sort_key(est_diagonals(L, tlen, P.a_bw));
+						const uint16_t key = sort_key_a(est_diagonals(L, tlen, P.a_bw));
 						args.sortA.keys[ai] = key;
 						atomicAdd(&args.sortA.hist[key], 1u);
 					} else atomicOr(&args.cnt->overflow, 4u);

@@ -41,17 +41,28 @@ struct GenoArgs {
 	uint8_t *seq_spill; int seq_spill_cap;  // global-memory sequence staging for alignments that do not fit seq_cap
 };
 
-// exclusive scan of the bucket histogram, longest bucket first
+// exclusive scan of the bucket histogram, longest bucket first (one CTA of 1024 threads, 64 buckets per thread)
 __global__ void sort_scan_kernel(SortBufs s)
 {
-	__shared__ unsigned tmp[SORT_BUCKETS];
+	__shared__ unsigned part[1024];
+	constexpr int PER = SORT_BUCKETS / 1024;
 	const int i = threadIdx.x;
-	tmp[i] = s.hist[SORT_BUCKETS - 1 - i];
+	unsigned sum = 0;
+	for (int k = 0; k < PER; ++k) sum += s.hist[SORT_BUCKETS - 1 - (i * PER + k)];
+	part[i] = sum;
 	__syncthreads();
-	if (i == 0) { unsigned acc = 0; for (int k = 0; k < SORT_BUCKETS; ++k) { const unsigned c = tmp[k]; tmp[k] = acc; acc += c; } }
-	__syncthreads();
-	s.start[SORT_BUCKETS - 1 - i] = tmp[i];
-	s.cursor[SORT_BUCKETS - 1 - i] = 0;
+	for (int d = 1; d < 1024; d <<= 1) { // inclusive Hillis-Steele scan of the per-thread sums
+		const unsigned v = i >= d ? part[i - d] : 0u;
+		__syncthreads();
+		part[i] += v;
+		__syncthreads();
+	}
+	unsigned acc = part[i] - sum;
+	for (int k = 0; k < PER; ++k) {
+		const int b = SORT_BUCKETS - 1 - (i * PER + k);
+		const unsigned c = s.hist[b];
+		s.start[b] = acc; s.cursor[b] = 0; acc += c;
+	}
 }
 __global__ void sort_scatter_kernel(SortBufs s, const unsigned *n_ptr, unsigned mul, unsigned cap)
 {
@@ -353,7 +364,7 @@ __global__ void al_prep_kernel(GenoArgs g)
 		int rlen = ar.ref_len - start; if (rlen < 0) rlen = 0;
 		int clen = cr.len - start; if (clen < 0) clen = 0;
 		const int qlen = rd.trim_len, wb = P.b_bw;
-		const uint8_t k0 = sort_key(est_diagonals(qlen, rlen, wb)), k1 = sort_key(est_diagonals(qlen, clen, wb));
+		const uint16_t k0 = sort_key_b(est_diagonals(qlen, rlen, wb), qlen), k1 = sort_key_b(est_diagonals(qlen, clen, wb), qlen);
 		g.sortB.keys[2 * slot] = k0; g.sortB.keys[2 * slot + 1] = k1;
 		atomicAdd(&g.sortB.hist[k0], 1u); atomicAdd(&g.sortB.hist[k1], 1u);
 	}

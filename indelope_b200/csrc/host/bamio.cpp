@@ -13,6 +13,9 @@
 // base_qualities() = raw phred bytes, cigar ops as in the file.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -170,6 +173,15 @@ int reg2bin(int64_t beg, int64_t end) // SAM spec 5.3
 }
 
 const char SEQ16[] = "=ACMGRSVTWYHKDBN";
+// two bases per packed byte (high nibble first)
+struct Seq16Pairs { uint8_t t[256][2]; Seq16Pairs() { for (int i = 0; i < 256; ++i) { t[i][0] = (uint8_t)SEQ16[i >> 4]; t[i][1] = (uint8_t)SEQ16[i & 15]; } } };
+const Seq16Pairs SEQ16_PAIRS;
+inline void decode_seq16(const uint8_t *packed, uint32_t n, uint8_t *out)
+{
+	uint32_t i = 0;
+	for (; i + 2 <= n; i += 2) { const uint8_t *p = SEQ16_PAIRS.t[packed[i >> 1]]; out[i] = p[0]; out[i + 1] = p[1]; }
+	if (i < n) out[i] = SEQ16_PAIRS.t[packed[i >> 1]][0];
+}
 inline uint8_t code16(uint8_t c)
 {
 	switch (c) {
@@ -207,6 +219,29 @@ bool load_fasta(const char *path, idlh_dataset &D, std::string &why)
 		D.names.push_back(name); D.chroms.push_back(std::move(seq));
 	}
 	return true;
+}
+
+// fixed part of one BAM alignment record (SAM spec 4.2) and pointers to its variable parts
+struct BamFields { int32_t ref_id, pos; uint8_t mapq; uint16_t flag; unsigned n_cig; uint32_t l_seq; const uint8_t *cig, *seq, *qual; };
+inline bool bam_fields(const uint8_t *b, uint32_t block, BamFields &f)
+{
+	f.ref_id = (int32_t)le32(b); f.pos = (int32_t)le32(b + 4);
+	const unsigned l_name = b[8]; f.mapq = b[9];
+	f.n_cig = le16(b + 12); f.flag = le16(b + 14); f.l_seq = le32(b + 16);
+	if (32 + (size_t)l_name + 4 * (size_t)f.n_cig + ((size_t)f.l_seq + 1) / 2 + f.l_seq > block) return false;
+	f.cig = b + 32 + l_name; f.seq = f.cig + 4 * f.n_cig; f.qual = f.seq + (f.l_seq + 1) / 2;
+	return true;
+}
+// reference bases the record spans, as bam_endpos counts them (hts-nim's `stop`)
+inline int64_t bam_ref_span(const BamFields &f)
+{
+	int64_t rlen = 0;
+	for (unsigned k = 0; k < f.n_cig; ++k) {
+		const uint32_t c = le32(f.cig + 4 * k); const unsigned op = c & 0xf;
+		if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += c >> 4;
+	}
+	if ((f.flag & 4) || f.n_cig == 0 || rlen == 0) rlen = 1;
+	return rlen;
 }
 
 } // namespace
@@ -313,34 +348,393 @@ idlh_dataset *idlh_load(const char *fasta_path, const char *bam_path, int thread
 		const uint32_t block = le32(p + at); at += 4;
 		if (block < 32 || at + block > n) return fail("truncated BAM record");
 		const uint8_t *b = p + at; at += block;
-		const int32_t ref_id = (int32_t)le32(b), pos = (int32_t)le32(b + 4);
-		const unsigned l_name = b[8]; const uint8_t mapq = b[9];
-		const unsigned n_cig = le16(b + 12); const uint16_t flag = le16(b + 14);
-		const uint32_t l_seq = le32(b + 16);
-		if (32 + (size_t)l_name + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq > block) return fail("malformed BAM record");
-		if (ref_id < 0) continue;
-		if ((uint32_t)ref_id >= n_ref) return fail("BAM record with an unknown reference id");
-		if (ref_id < last_ref || (ref_id == last_ref && pos < last_pos)) return fail("BAM is not coordinate sorted");
-		last_ref = ref_id; last_pos = pos;
+		BamFields f;
+		if (!bam_fields(b, block, f)) return fail("malformed BAM record");
+		if (f.ref_id < 0) continue;
+		if ((uint32_t)f.ref_id >= n_ref) return fail("BAM record with an unknown reference id");
+		if (f.ref_id < last_ref || (f.ref_id == last_ref && f.pos < last_pos)) return fail("BAM is not coordinate sorted");
+		last_ref = f.ref_id; last_pos = f.pos;
 		IdlhReadRec r;
-		r.chrom = ref_id; r.start = pos; r.mapq = mapq; r.flag = flag; r.len = (int32_t)l_seq;
-		r.seq_off = (int64_t)D->bases.size(); r.cig_off = (int64_t)D->cigars.size(); r.n_cig = (int32_t)n_cig; r.order = D->reads.size();
-		const uint8_t *cg = b + 32 + l_name;
-		int64_t rlen = 0;
-		for (unsigned k = 0; k < n_cig; ++k) {
-			const uint32_t c = le32(cg + 4 * k); const unsigned op = c & 0xf;
-			D->cigars.push_back(c);
-			if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += c >> 4;
-		}
-		if ((flag & 4) || n_cig == 0 || rlen == 0) rlen = 1; // bam_endpos
-		r.stop = (int32_t)(pos + rlen);
-		const uint8_t *sq = cg + 4 * n_cig, *ql = sq + (l_seq + 1) / 2;
-		for (uint32_t i = 0; i < l_seq; ++i) D->bases.push_back((uint8_t)SEQ16[(sq[i >> 1] >> ((~i & 1) << 2)) & 0xf]);
-		D->quals.insert(D->quals.end(), ql, ql + l_seq);
+		r.chrom = f.ref_id; r.start = f.pos; r.mapq = f.mapq; r.flag = f.flag; r.len = (int32_t)f.l_seq;
+		r.seq_off = (int64_t)D->bases.size(); r.cig_off = (int64_t)D->cigars.size(); r.n_cig = (int32_t)f.n_cig; r.order = D->reads.size();
+		for (unsigned k = 0; k < f.n_cig; ++k) D->cigars.push_back(le32(f.cig + 4 * k));
+		r.stop = (int32_t)(f.pos + bam_ref_span(f));
+		{ const size_t o = D->bases.size(); D->bases.resize(o + f.l_seq); decode_seq16(f.seq, f.l_seq, D->bases.data() + o); }
+		D->quals.insert(D->quals.end(), f.qual, f.qual + f.l_seq);
 		D->reads.push_back(r);
 	}
 	if (at != n) return fail("trailing bytes after the last BAM record");
 	return D;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming: the BAM is read front to back in slabs, BGZF blocks are inflated by `threads` workers, and the gen_roi
+// sweep (src/indelope.nim:515-545) runs INCREMENTALLY over the records, so that neither the file nor a whole
+// coverage-gap chunk has to sit in memory (the reference keeps one chunk of records, README "memory": on a deep
+// genome without coverage gaps that is a whole chromosome arm).
+//
+// Why the incremental sweep yields the reference's regions exactly.  The reference scans evidence[last_start, r.start)
+// only when a record starts past the end of everything cached (:529-534) and once more at the end of the target (:544);
+// the scanned ranges tile [0, length] in order and a region never crosses from one range into the next (:497-499 flush
+// at the end of a range).  Records arrive sorted by start and a record only adds evidence at or after its own start
+// (:430-442), so evidence[p] is final as soon as a record with start > p has arrived; scanning positions below the
+// current record's start therefore sees the same values, and a region that ends there finds every record with
+// start <= roi_end already cached, in the same order.  Only the forced flush at a range end has to be replayed: it
+// happens exactly where the reference's gap test fires (cache non-empty and r.start > cache.stop, tested BEFORE
+// skippable, :529-536).  Records whose stop lies before the next possible region start are dropped from the front of
+// the cache early; they could never pass `overlaps` (:449-452) again.
+// ---------------------------------------------------------------------------------------------------------------
+struct idlh_stream {
+	// reference
+	idlh_dataset ref;                       // names / chroms in BAM target order (reads stay empty)
+	std::vector<uint8_t> skip_chrom;
+	// file
+	FILE *f = nullptr; int threads = 1; bool file_eof = false;
+	std::vector<uint8_t> cbuf; size_t cpos = 0;      // compressed bytes not yet inflated (reader thread only)
+	std::vector<uint8_t> ubuf; size_t upos = 0;      // inflated bytes not yet parsed
+	std::string error;
+	// the reader thread reads and inflates the next slabs while the caller parses and sweeps the current one
+	std::thread reader; std::mutex mu; std::condition_variable cv;
+	std::deque<std::vector<uint8_t>> ready; bool reader_done = false, stop = false; std::string reader_error;
+	// sweep parameters and state
+	int32_t min_evidence = 3, min_reads = 3, max_reads = 600;
+	int32_t cur_chrom = -1; int64_t tlen = 0;
+	std::vector<uint8_t> evidence;
+	int64_t scan_pos = 0; bool in_roi = false; int64_t roi_start = 0, roi_end = 0;
+	int32_t last_ref = 0, last_pos = -1;
+	struct Cached { int32_t start, stop, len; uint8_t mapq; uint16_t flag; int64_t off; uint64_t epoch; int64_t out_idx; };
+	std::vector<Cached> cache; size_t head = 0; int64_t cache_stop = 0;
+	int64_t cache_len = 0;                            // the reference's cache.len: records cached since the last clear, dropped ones included
+	std::vector<uint8_t> cbases;                      // 4-bit sequence + qualities of the cached records, as in the file
+	uint64_t epoch = 1;
+	bool done = false;
+	int64_t n_records = 0, n_regions = 0;
+};
+
+namespace {
+
+const size_t SLAB = 4u << 20; // compressed bytes read per refill
+
+// reader thread: read the next slab of the file and inflate its complete blocks (with `threads` workers) into `out`;
+// false at the end of the file or on error (err set)
+bool stream_read_slab(idlh_stream &S, std::vector<uint8_t> &out, std::string &err)
+{
+	for (;;) {
+		if (S.cpos == S.cbuf.size() && S.file_eof) return false;
+		if (!S.file_eof) { // top up the compressed buffer
+			if (S.cpos) { S.cbuf.erase(S.cbuf.begin(), S.cbuf.begin() + (long)S.cpos); S.cpos = 0; }
+			const size_t old = S.cbuf.size();
+			S.cbuf.resize(old + SLAB);
+			const size_t got = fread(S.cbuf.data() + old, 1, SLAB, S.f);
+			S.cbuf.resize(old + got);
+			if (got < SLAB) { if (ferror(S.f)) { err = "read error on the BAM file"; return false; } S.file_eof = true; }
+		}
+		std::vector<BgzfBlock> blocks; size_t total = 0, at = S.cpos; // index the complete blocks
+		while (S.cbuf.size() - at >= 18) {
+			const uint8_t *h = S.cbuf.data() + at;
+			if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { err = "not a BGZF file (is it BAM? CRAM is not supported by this stand-in)"; return false; }
+			const unsigned xlen = le16(h + 10);
+			if (S.cbuf.size() - at < 12 + xlen) break;
+			int bsize = -1;
+			for (unsigned x = 0; x + 4 <= xlen;) {
+				const uint8_t *e = h + 12 + x; const unsigned slen = le16(e + 2);
+				if (e[0] == 'B' && e[1] == 'C' && slen == 2) bsize = le16(e + 4);
+				x += 4 + slen;
+			}
+			if (bsize < 0) { err = "BGZF block without BC subfield"; return false; }
+			const size_t csize = (size_t)bsize + 1;
+			if (csize < 12 + xlen + 8) { err = "truncated BGZF block"; return false; }
+			if (S.cbuf.size() - at < csize) break;
+			const size_t usize = le32(h + csize - 4);
+			blocks.push_back({at, csize, total, usize});
+			total += usize; at += csize;
+		}
+		if (blocks.empty()) {
+			if (S.file_eof) { if (at != S.cbuf.size()) err = "truncated BGZF block"; S.cpos = S.cbuf.size(); return false; }
+			continue;
+		}
+		out.resize(total);
+		std::atomic<size_t> next(0); std::atomic<bool> ok(true);
+		auto work = [&]() {
+			for (;;) {
+				const size_t i = next.fetch_add(16);
+				if (i >= blocks.size() || !ok.load()) return;
+				for (size_t k = i; k < std::min(i + 16, blocks.size()); ++k)
+					if (!bgzf_inflate_block(S.cbuf, blocks[k], out.data() + blocks[k].uoff)) { ok.store(false); return; }
+			}
+		};
+		std::vector<std::thread> pool;
+		for (int t = 1; t < S.threads; ++t) pool.emplace_back(work);
+		work();
+		for (auto &t : pool) t.join();
+		if (!ok.load()) { err = "BGZF block failed to inflate (corrupt data or CRC mismatch)"; return false; }
+		S.cpos = at;
+		if (total == 0) continue; // only empty blocks (the EOF marker)
+		return true;
+	}
+}
+
+void stream_reader_main(idlh_stream *S)
+{
+	for (;;) {
+		std::vector<uint8_t> slab; std::string err;
+		const bool ok = stream_read_slab(*S, slab, err);
+		std::unique_lock<std::mutex> lk(S->mu);
+		if (!ok) { S->reader_error = err; S->reader_done = true; S->cv.notify_all(); return; }
+		S->cv.wait(lk, [&] { return S->ready.size() < 4 || S->stop; });
+		if (S->stop) { S->reader_done = true; S->cv.notify_all(); return; }
+		S->ready.push_back(std::move(slab));
+		S->cv.notify_all();
+	}
+}
+
+// make at least `need` inflated bytes available at ubuf[upos..]; false at end of file or on error (S.error set)
+bool stream_fill(idlh_stream &S, size_t need)
+{
+	while (S.ubuf.size() - S.upos < need) {
+		std::vector<uint8_t> slab;
+		{
+			std::unique_lock<std::mutex> lk(S.mu);
+			S.cv.wait(lk, [&] { return !S.ready.empty() || S.reader_done; });
+			if (S.ready.empty()) { if (!S.reader_error.empty()) S.error = S.reader_error; return false; }
+			slab = std::move(S.ready.front()); S.ready.pop_front();
+			S.cv.notify_all();
+		}
+		if (S.upos == S.ubuf.size()) { S.ubuf.swap(slab); S.upos = 0; }
+		else { // a record straddles two slabs: keep the unparsed tail in front of the new bytes
+			S.ubuf.erase(S.ubuf.begin(), S.ubuf.begin() + (long)S.upos); S.upos = 0;
+			S.ubuf.insert(S.ubuf.end(), slab.begin(), slab.end());
+		}
+	}
+	return true;
+}
+
+// a region ends: collect its records from the cache (:476-486) into the group being built
+void stream_flush_roi(idlh_stream &S, idlh_rois &R)
+{
+	std::vector<size_t> reads;
+	for (size_t k = S.head; k < S.cache.size(); ++k) {
+		const idlh_stream::Cached &r = S.cache[k];
+		if (!(r.start > S.roi_end) && !(r.stop < S.roi_start)) { // overlaps :449-452
+			reads.push_back(k);
+			if ((int64_t)reads.size() > S.max_reads) break;
+		}
+		if (r.start > S.roi_end) break;
+	}
+	if ((int64_t)reads.size() < S.min_reads || (int64_t)reads.size() > S.max_reads) return;
+	R.roi_chrom.push_back(S.cur_chrom); R.roi_start.push_back((int32_t)S.roi_start); R.roi_stop.push_back((int32_t)S.roi_end);
+	R.roi_read_begin.push_back((int64_t)R.read_idx.size()); R.roi_n_reads.push_back((int32_t)reads.size());
+	for (size_t k : reads) {
+		idlh_stream::Cached &r = S.cache[k];
+		if (r.epoch != S.epoch) { // first use in this group: copy the record over
+			r.epoch = S.epoch; r.out_idx = (int64_t)R.start.size();
+			R.start.push_back(r.start); R.stop.push_back(r.stop); R.len.push_back(r.len); R.mapq.push_back(r.mapq); R.flag.push_back(r.flag);
+			R.seq_off.push_back((int64_t)R.own_bases.size());
+			// the cache holds the record's 4-bit sequence and its qualities as they are in the file; only records that
+			// reach a region (a few percent on a whole genome) are decoded
+			const size_t o = R.own_bases.size(), packed = ((size_t)r.len + 1) / 2;
+			R.own_bases.resize(o + (size_t)r.len);
+			decode_seq16(S.cbases.data() + r.off, (uint32_t)r.len, R.own_bases.data() + o);
+			R.own_quals.insert(R.own_quals.end(), S.cbases.begin() + (long)(r.off + packed), S.cbases.begin() + (long)(r.off + packed + r.len));
+		}
+		R.read_idx.push_back(r.out_idx);
+	}
+	++S.n_regions;
+}
+
+// gen_roi_internal's loop (:461-499) over positions [scan_pos, end); positions below `end` are final
+void stream_scan(idlh_stream &S, idlh_rois &R, int64_t end)
+{
+	if (end > (int64_t)S.evidence.size()) end = (int64_t)S.evidence.size();
+	const uint8_t *ev = S.evidence.data();
+	const uint8_t me = (uint8_t)S.min_evidence;
+	int64_t i = S.scan_pos;
+	while (i < end) {
+		if (!S.in_roi && me > 0) { // skip runs without any evidence eight positions at a time
+			while (i + 8 <= end) { uint64_t w; memcpy(&w, ev + i, 8); if (w) break; i += 8; }
+			if (i >= end) break;
+		}
+		if (ev[i] >= me) {
+			if (!S.in_roi) { S.in_roi = true; S.roi_start = i; }
+			S.roi_end = i;
+		} else if (S.in_roi) { stream_flush_roi(S, R); S.in_roi = false; }
+		++i;
+	}
+	if (end > S.scan_pos) S.scan_pos = end;
+}
+
+void stream_drop_passed(idlh_stream &S)
+{
+	const int64_t thr = S.in_roi ? S.roi_start : S.scan_pos; // no later region can start before this
+	while (S.head < S.cache.size() && S.cache[S.head].stop < thr) ++S.head;
+	if (S.head == S.cache.size()) { S.cache.clear(); S.head = 0; S.cbases.clear(); }
+	else if (S.head > 4096 && S.head * 2 > S.cache.size()) { // compact
+		const int64_t off0 = S.cache[S.head].off;
+		S.cache.erase(S.cache.begin(), S.cache.begin() + (long)S.head); S.head = 0;
+		S.cbases.erase(S.cbases.begin(), S.cbases.begin() + (long)off0);
+		for (auto &c : S.cache) c.off -= off0;
+	}
+}
+
+void stream_end_target(idlh_stream &S, idlh_rois &R)
+{
+	if (S.cur_chrom < 0) return;
+	stream_scan(S, R, (int64_t)S.evidence.size());          // :544
+	if (S.in_roi) { stream_flush_roi(S, R); S.in_roi = false; }
+	S.cache.clear(); S.head = 0; S.cbases.clear(); S.cache_stop = 0; S.cache_len = 0;
+}
+
+void stream_begin_target(idlh_stream &S, int32_t c)
+{
+	S.cur_chrom = c; S.tlen = (int64_t)S.ref.chroms[(size_t)c].size();
+	S.evidence.assign((size_t)S.tlen + 1, 0);                // :522
+	S.scan_pos = 0; S.in_roi = false; S.cache_stop = 0;
+}
+
+void stream_record(idlh_stream &S, idlh_rois &R, const BamFields &f)
+{
+	if (f.ref_id != S.cur_chrom) { stream_end_target(S, R); stream_begin_target(S, f.ref_id); }
+	const int64_t start = f.pos, stop = f.pos + bam_ref_span(f);
+	if (S.cache_len > 0 && start > S.cache_stop) {             // :529-534: coverage gap, the range ends here
+		stream_scan(S, R, start);
+		if (S.in_roi) { stream_flush_roi(S, R); S.in_roi = false; }
+		S.cache.clear(); S.head = 0; S.cbases.clear(); S.cache_stop = 0; S.cache_len = 0;
+	} else {
+		stream_scan(S, R, start);                               // positions below this record's start are final
+		stream_drop_passed(S);
+	}
+	if (S.skip_chrom[(size_t)f.ref_id] || idlh_skippable_flag(f.flag)) return; // :536
+	idlh_stream::Cached c;
+	c.start = (int32_t)start; c.stop = (int32_t)stop; c.len = (int32_t)f.l_seq; c.mapq = f.mapq; c.flag = f.flag; c.off = (int64_t)S.cbases.size();
+	c.epoch = 0; c.out_idx = -1;
+	S.cbases.insert(S.cbases.end(), f.seq, f.qual + f.l_seq); // packed sequence, then qualities (adjacent in the record)
+	S.cache.push_back(c); ++S.cache_len; if (stop > S.cache_stop) S.cache_stop = stop; // :504-506,537
+	int64_t off = 0; // event_locations :430-442
+	for (unsigned k = 0; k < f.n_cig; ++k) {
+		const uint32_t cg = le32(f.cig + 4 * k); const unsigned op = cg & 0xf; const int64_t len = cg >> 4;
+		const bool cons = op == 0 || op == 2 || op == 3 || op == 7 || op == 8;
+		if (op != 0) {
+			const int64_t es = start + off, ee = cons ? es + len : es + 1;
+			for (int64_t i = es; i < ee && i <= S.tlen; ++i) { uint8_t &e = S.evidence[(size_t)i]; e += 1; if (e == 0) e = 255; } // :539-543
+		}
+		if (cons) off += len;
+	}
+}
+
+void rois_finish_view(idlh_rois &R, const idlh_dataset &ref)
+{
+	for (size_t c = 0; c < ref.chroms.size(); ++c) {
+		R.name_ptrs.push_back(ref.names[c].c_str()); R.seq_ptrs.push_back(ref.chroms[c].data()); R.chrom_len.push_back((int64_t)ref.chroms[c].size());
+	}
+	R.bases = R.own_bases.data(); R.quals = R.own_quals.data();
+	idlh_roiset &v = R.view;
+	v.n_reads = (int64_t)R.start.size(); v.start = R.start.data(); v.stop = R.stop.data(); v.mapq = R.mapq.data(); v.flag = R.flag.data(); v.len = R.len.data();
+	v.seq_off = R.seq_off.data(); v.bases = R.bases; v.quals = R.quals;
+	v.n_rois = (int64_t)R.roi_start.size(); v.roi_chrom = R.roi_chrom.data(); v.roi_start = R.roi_start.data(); v.roi_stop = R.roi_stop.data();
+	v.roi_read_begin = R.roi_read_begin.data(); v.roi_n_reads = R.roi_n_reads.data(); v.read_idx = R.read_idx.data();
+	v.n_chroms = (int32_t)ref.chroms.size(); v.chrom_name = R.name_ptrs.data(); v.chrom_seq = R.seq_ptrs.data(); v.chrom_len = R.chrom_len.data();
+}
+
+} // namespace
+
+extern "C" {
+
+void idlh_stream_close(idlh_stream *S);
+
+idlh_stream *idlh_stream_open(const char *fasta_path, const char *bam_path, int threads, int32_t min_event_support, int32_t min_read_coverage,
+                              int32_t max_read_coverage, char *err, size_t errlen)
+{
+	idlh_stream *S = new idlh_stream();
+	memset(&S->ref.P, 0, sizeof S->ref.P);
+	auto fail = [&](const std::string &m) -> idlh_stream* { set_err(err, errlen, m); idlh_stream_close(S); return nullptr; };
+	std::string why;
+	if (!load_fasta(fasta_path, S->ref, why)) return fail(why);
+	S->f = fopen(bam_path, "rb");
+	if (!S->f) return fail(std::string("cannot open ") + bam_path);
+	S->threads = threads < 1 ? 1 : threads;
+	S->min_evidence = min_event_support; S->min_reads = min_read_coverage; S->max_reads = max_read_coverage;
+	S->reader = std::thread(stream_reader_main, S);
+	auto need = [&](size_t n) { return stream_fill(*S, n); };
+	const std::string pre = std::string(bam_path) + ": ";
+	if (!need(12) || memcmp(S->ubuf.data() + S->upos, "BAM\1", 4) != 0) return fail(pre + (S->error.empty() ? "not a BAM file" : S->error));
+	const uint32_t l_text = le32(S->ubuf.data() + S->upos + 4);
+	if (!need(12 + (size_t)l_text)) return fail(pre + "truncated BAM header");
+	S->upos += 8 + l_text;
+	const uint32_t n_ref = le32(S->ubuf.data() + S->upos); S->upos += 4;
+	std::vector<std::string> names; std::vector<std::vector<uint8_t>> chroms;
+	for (uint32_t r = 0; r < n_ref; ++r) { // BAM reference ids -> FASTA records by name; everything follows the BAM's target order (:599-601)
+		if (!need(4)) return fail(pre + "truncated BAM reference list");
+		const uint32_t l_name = le32(S->ubuf.data() + S->upos);
+		if (l_name == 0 || !need(8 + (size_t)l_name)) return fail(pre + "truncated BAM reference list");
+		const std::string name((const char*)S->ubuf.data() + S->upos + 4, l_name - 1);
+		const uint32_t l_ref = le32(S->ubuf.data() + S->upos + 4 + l_name);
+		S->upos += 8 + l_name;
+		size_t k = 0;
+		while (k < S->ref.names.size() && S->ref.names[k] != name) ++k;
+		if (k == S->ref.names.size()) return fail("BAM target " + name + " is not in the FASTA");
+		if (S->ref.chroms[k].size() != l_ref) return fail("BAM target " + name + " has a different length than the FASTA record");
+		names.push_back(name); chroms.push_back(std::move(S->ref.chroms[k])); S->ref.chroms[k].clear(); S->ref.names[k] = "\1used";
+	}
+	S->ref.names.swap(names); S->ref.chroms.swap(chroms);
+	for (const std::string &nm : S->ref.names) S->skip_chrom.push_back(idlh_skippable_chrom(nm) ? 1 : 0);
+	return S;
+}
+
+idlh_rois *idlh_stream_next(idlh_stream *S, int64_t target_reads, char *err, size_t errlen)
+{
+	if (S->done) return nullptr;
+	idlh_rois *R = new idlh_rois();
+	++S->epoch;
+	auto fail = [&](const std::string &m) -> idlh_rois* { set_err(err, errlen, m); delete R; S->done = true; return nullptr; };
+	const uint32_t n_ref = (uint32_t)S->ref.names.size();
+	for (;;) {
+		if ((int64_t)R->read_idx.size() >= target_reads && !R->roi_start.empty()) break;
+		if (!stream_fill(*S, 4)) {
+			if (!S->error.empty()) return fail(S->error);
+			if (S->ubuf.size() != S->upos) return fail("trailing bytes after the last BAM record");
+			stream_end_target(*S, *R); // the remaining targets have no records: gen_roi finds nothing there
+			S->done = true;
+			break;
+		}
+		const uint32_t block = le32(S->ubuf.data() + S->upos);
+		if (block < 32) return fail("truncated BAM record");
+		if (!stream_fill(*S, 4 + (size_t)block)) return fail(S->error.empty() ? "truncated BAM record" : S->error);
+		const uint8_t *b = S->ubuf.data() + S->upos + 4; S->upos += 4 + (size_t)block;
+		BamFields f;
+		if (!bam_fields(b, block, f)) return fail("malformed BAM record");
+		if (f.ref_id < 0) continue;
+		if ((uint32_t)f.ref_id >= n_ref) return fail("BAM record with an unknown reference id");
+		if (f.ref_id < S->last_ref || (f.ref_id == S->last_ref && f.pos < S->last_pos)) return fail("BAM is not coordinate sorted");
+		S->last_ref = f.ref_id; S->last_pos = f.pos;
+		++S->n_records;
+		stream_record(*S, *R, f);
+	}
+	rois_finish_view(*R, S->ref);
+	return R;
+}
+
+/* contig names / lengths for the VCF header (a view without regions) */
+idlh_rois *idlh_stream_targets(const idlh_stream *S)
+{
+	idlh_rois *R = new idlh_rois();
+	rois_finish_view(*R, S->ref);
+	return R;
+}
+
+void idlh_stream_counts(const idlh_stream *S, int64_t counts[2]) { counts[0] = S->n_records; counts[1] = S->n_regions; }
+
+void idlh_stream_close(idlh_stream *S)
+{
+	if (!S) return;
+	if (S->reader.joinable()) {
+		{ std::lock_guard<std::mutex> lk(S->mu); S->stop = true; }
+		S->cv.notify_all();
+		S->reader.join();
+	}
+	if (S->f) fclose(S->f);
+	delete S;
 }
 
 } // extern "C"

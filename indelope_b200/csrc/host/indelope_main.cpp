@@ -5,7 +5,7 @@
 //
 // Same options, defaults and output as the reference's docopt block (:556-572).  The host part -- BAM sweep, evidence
 // counters, coverage-gap chunking, VCF text -- is the C++ stand-in of libindelope_host.so (the reference keeps it in Nim);
-// every region of interest goes through libindelope_cuda.so in batches, two in flight.  There is no CPU path: without a
+// the BAM is streamed in bounded memory and every region of interest goes through libindelope_cuda.so in batches, two in flight.  There is no CPU path: without a
 // CUDA device the program stops with an error.  CRAM input and the undocumented `single-site` debugging mode (:578-586)
 // are not provided.
 #include <cstdint>
@@ -38,7 +38,7 @@ static const char USAGE[] =
 	"  -h --help                   show help\n";
 
 struct Lane { idl_batch *batch = nullptr; size_t cap[4] = {0, 0, 0, 0}; };
-struct Flight { int64_t lo; uint64_t ticket; };
+struct Flight { idlh_rois *rois; uint64_t ticket; };
 
 static int die(const char *what, const std::string &why) { fprintf(stderr, "indelope: %s: %s\n", what, why.c_str()); return 1; }
 
@@ -72,11 +72,10 @@ int main(int argc, char **argv)
 	if (pos.size() != 2) { fputs(USAGE, stderr); return 1; }
 
 	char err[512] = {0};
-	idlh_dataset *data = idlh_load(pos[0].c_str(), pos[1].c_str(), threads, err, sizeof err);
-	if (!data) return die("input", err);
-	// gen_roi(b, target, min_read_coverage=min_reads, min_event_support=max(3, min_reads-2)), src/indelope.nim:602
-	idlh_rois *rois = idlh_sweep(data, min_reads - 2 > 3 ? min_reads - 2 : 3, min_reads, 600);
-	const idlh_roiset *rs = idlh_rois_view(rois);
+	// gen_roi(b, target, min_read_coverage=min_reads, min_event_support=max(3, min_reads-2)), src/indelope.nim:602; the BAM
+	// is swept front to back in bounded memory (idlh_stream_*), a group of regions at a time
+	idlh_stream *in = idlh_stream_open(pos[0].c_str(), pos[1].c_str(), threads, min_reads - 2 > 3 ? min_reads - 2 : 3, min_reads, 600, err, sizeof err);
+	if (!in) return die("input", err);
 
 	idl_params P;
 	idl_default_params(&P);
@@ -85,7 +84,11 @@ int main(int argc, char **argv)
 	int rc = idl_create(device, &P, &ctx);
 	if (rc != IDL_OK) return die("libindelope_cuda", std::string(idl_strerror(rc)) + " (this program has no CPU path; it needs a CUDA device)");
 
-	{ char *h = idlh_vcf_header(rs); fputs(h, stdout); idlh_free(h); } // echo header % [b.contig_header, "sample"], :599
+	{ // echo header % [b.contig_header, "sample"], :599
+		idlh_rois *t = idlh_stream_targets(in);
+		char *h = idlh_vcf_header(idlh_rois_view(t)); fputs(h, stdout); idlh_free(h);
+		idlh_rois_free(t);
+	}
 	idlh_vcf *writer = idlh_vcf_new();
 	std::vector<Lane> lanes((size_t)(P.n_streams > 0 ? P.n_streams : 1));
 	std::deque<Flight> inflight;
@@ -94,44 +97,49 @@ int main(int argc, char **argv)
 		const Flight f = inflight.front(); inflight.pop_front();
 		const idl_results *res = nullptr;
 		const int r = idl_wait(ctx, f.ticket, &res);
-		if (r != IDL_OK) { status = die("idl_wait", std::string(idl_strerror(r)) + " " + idl_last_cuda_error(ctx)); return false; }
+		if (r != IDL_OK) { status = die("idl_wait", std::string(idl_strerror(r)) + " " + idl_last_cuda_error(ctx)); idlh_rois_free(f.rois); return false; }
 		char *dump = nullptr;
-		char *txt = idlh_vcf_records(writer, rs, f.lo, &P, res, 0, &dump);
+		char *txt = idlh_vcf_records(writer, idlh_rois_view(f.rois), 0, &P, res, 0, &dump);
 		fputs(txt, stdout);
 		idlh_free(txt); idlh_free(dump);
 		idl_release(ctx, f.ticket);
+		idlh_rois_free(f.rois);
 		return true;
 	};
-	// contiguous slices of the region list, bounded by reads and regions per batch; emission order is kept (the dedup of :604-608 depends on it)
-	const int64_t max_reads = 400000, max_regions = 20000;
-	int64_t a = 0; size_t nb = 0;
-	while (a < rs->n_rois && !status) {
-		int64_t b = a, acc = 0;
-		while (b < rs->n_rois && (b == a || (acc + rs->roi_n_reads[b] <= max_reads && b - a < max_regions))) acc += rs->roi_n_reads[b++];
-		if (inflight.size() >= lanes.size() && !drain()) break;
+	// one batch per group of regions, in emission order (the dedup of :604-608 depends on it); while the GPU works on a
+	// batch the host reads and sweeps the next stretch of the BAM
+	const int64_t target_reads = 400000;
+	size_t nb = 0;
+	while (!status) {
+		err[0] = 0;
+		idlh_rois *grp = idlh_stream_next(in, target_reads, err, sizeof err);
+		if (!grp) { if (err[0]) status = die("input", err); break; }
+		const idlh_roiset *rs = idlh_rois_view(grp);
+		if (rs->n_rois == 0) { idlh_rois_free(grp); continue; }
+		if (inflight.size() >= lanes.size() && !drain()) { idlh_rois_free(grp); break; }
 		Lane &L = lanes[nb % lanes.size()];
-		size_t need[4] = {(size_t)(b - a), 0, 0, 0};
-		idlh_pack_size(rs, a, b, &P, &need[1], &need[2], &need[3]);
+		size_t need[4] = {(size_t)rs->n_rois, 0, 0, 0};
+		idlh_pack_size(rs, 0, rs->n_rois, &P, &need[1], &need[2], &need[3]);
 		bool grow = L.batch == nullptr;
 		for (int k = 0; k < 4; ++k) grow |= need[k] > L.cap[k];
 		if (grow) {
 			if (L.batch) idl_batch_free(ctx, L.batch);
 			for (int k = 0; k < 4; ++k) L.cap[k] = need[k] + need[k] / 4 + 64;
 			rc = idl_batch_alloc(ctx, L.cap[0], L.cap[1], L.cap[2], L.cap[3], &L.batch);
-			if (rc != IDL_OK) { status = die("idl_batch_alloc", idl_strerror(rc)); break; }
+			if (rc != IDL_OK) { status = die("idl_batch_alloc", idl_strerror(rc)); idlh_rois_free(grp); break; }
 		}
-		if (idlh_pack(rs, a, b, &P, L.batch) != 0) { status = die("idlh_pack", "batch does not fit"); break; }
+		if (idlh_pack(rs, 0, rs->n_rois, &P, L.batch) != 0) { status = die("idlh_pack", "batch does not fit"); idlh_rois_free(grp); break; }
 		uint64_t ticket = 0;
 		rc = idl_submit(ctx, L.batch, &ticket);
-		if (rc != IDL_OK) { status = die("idl_submit", std::string(idl_strerror(rc)) + " " + idl_last_cuda_error(ctx)); break; }
-		inflight.push_back({a, ticket});
-		a = b; ++nb;
+		if (rc != IDL_OK) { status = die("idl_submit", std::string(idl_strerror(rc)) + " " + idl_last_cuda_error(ctx)); idlh_rois_free(grp); break; }
+		inflight.push_back({grp, ticket});
+		++nb;
 	}
 	while (!inflight.empty() && !status) if (!drain()) break;
+	while (!inflight.empty()) { idlh_rois_free(inflight.front().rois); inflight.pop_front(); }
 	for (Lane &L : lanes) if (L.batch) idl_batch_free(ctx, L.batch);
 	idlh_vcf_free(writer);
 	idl_destroy(ctx);
-	idlh_rois_free(rois);
-	idlh_dataset_free(data);
+	idlh_stream_close(in);
 	return status;
 }

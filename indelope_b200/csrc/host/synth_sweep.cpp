@@ -38,14 +38,6 @@ using ReadRec = IdlhReadRec;
 
 } // namespace
 
-struct idlh_rois {
-	std::vector<int32_t> start, stop, len; std::vector<uint8_t> mapq; std::vector<uint16_t> flag; std::vector<int64_t> seq_off;
-	const uint8_t *bases = nullptr, *quals = nullptr;
-	std::vector<int32_t> roi_chrom, roi_start, roi_stop, roi_n_reads; std::vector<int64_t> roi_read_begin, read_idx;
-	std::vector<const char*> name_ptrs; std::vector<const uint8_t*> seq_ptrs; std::vector<int64_t> chrom_len;
-	idlh_roiset view;
-};
-
 namespace {
 
 const char ACGT[] = "ACGT";
@@ -278,6 +270,7 @@ idlh_rois *idlh_sweep(const idlh_dataset *d, int32_t min_event_support, int32_t 
 		std::vector<uint8_t> evidence((size_t)tlen + 1, 0);           // :522
 		std::vector<size_t> cache; int64_t cache_stop = 0;             // :523
 		int64_t last_start = 0;                                         // :525
+		const bool skip_chrom = idlh_skippable_chrom(d->names[c]);
 		auto gen_roi_internal = [&](int64_t cache_start, int64_t cache_end) { // :461-499
 			bool in_roi = false; int64_t roi_start = 0, roi_end = 0;
 			auto flush = [&]() {
@@ -313,8 +306,7 @@ idlh_rois *idlh_sweep(const idlh_dataset *d, int32_t min_event_support, int32_t 
 				last_start = r.start;
 				cache.clear(); cache_stop = 0;
 			}
-			const uint16_t f = r.flag; // skippable :40-47 (the chrom-name tests never fire on synthetic names)
-			if ((f & 0x400) || (f & 0x200) || (f & 0x4) || (f & 0x800) || (f & 0x100)) continue;
+			if (skip_chrom || idlh_skippable_flag(r.flag)) continue; // skippable :40-47
 			cache.push_back(ri); cache_stop = std::max<int64_t>(cache_stop, r.stop); // :504-506,537
 			int64_t off = 0; // event_locations :430-442
 			for (int32_t k = 0; k < r.n_cig; ++k) {

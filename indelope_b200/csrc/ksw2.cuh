@@ -50,6 +50,10 @@ __host__ __device__ inline int ksw_ncol(int qlen, int tlen, int w)
 	n = n < w + 1 ? n : w + 1;
 	return ((n + 15) / 16 + 1) * 16;
 }
+// row pitch of the backtrack matrix in global memory: a multiple of 32 bytes, so that the 32 bytes a group stores per round
+// are one whole, aligned L2 sector (a half-written sector is first FETCHED from DRAM: with the reference's 16-byte pitch
+// every second row straddled sectors and the kernel read more than it wrote)
+__host__ __device__ inline int ksw_pitch(int ncol) { return (ncol + 31) & ~31; }
 // ring of lane columns: the rounded band, the column left of it, 16 lanes of score overrun and the 16 being cleared
 __host__ __device__ inline int ksw_ring_cols(int ncol) { int r = 64; while (r < ncol + 48) r <<= 1; return r; }
 // bytes of query staging: KSW_QR_PAD zero bytes, the reversed query, zero padding (:188).  The target is not staged as a
@@ -217,6 +221,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 	int w = P.w;
 	if (w < 0) w = tlen > qlen ? tlen : qlen; // :161
 	const int n_col = valid ? ksw_ncol(qlen, tlen, w) : 16; // :164-165 (bytes)
+	const int pitch = ksw_pitch(n_col);
 	// The exact scores H[] (:177-178, int32 in the reference) live as uint16: g[t] = H[t] + (q+e)*(r+1) + gbias, r = the
 	// diagonal of the last update.  Every in-band column is updated on every diagonal, so the per-diagonal -(q+e) of
 	// :323-348 turns into a common offset, the update into an unsigned byte add, and the band max into a packed 16-bit max.
@@ -227,7 +232,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 		else if (-min_sc > 2 * qe) { out.status = KSW_ST_EARLY; live = false; }      // :171
 		else if (ksw_ring_cols(n_col) > M.ring_cols) { out.status = KSW_ST_RCAP; live = false; }
 		else if (ksw_seq_bytes(qlen, tlen) > (size_t)M.seq_cap) { out.status = KSW_ST_SEQCAP; live = false; }
-		else if ((size_t)(qlen + tlen - 1) * (size_t)n_col + 2 * KSW_PMAT_PAD > M.p_cap) { out.status = KSW_ST_PCAP; live = false; }
+		else if ((size_t)(qlen + tlen - 1) * (size_t)pitch + 2 * KSW_PMAT_PAD > M.p_cap) { out.status = KSW_ST_PCAP; live = false; }
 		else if ((long long)(qlen + tlen + 2) * qe + (long long)(qlen < tlen ? qlen : tlen) * (P.match > 0 ? P.match : 0) + gbias >= 0xF000) { out.status = KSW_ST_HCAP; live = false; }
 	}
 	const bool run = live; // this group has a DP to run (and a CIGAR to walk afterwards)
@@ -286,7 +291,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 		const int wfirst = st >> 2, w1 = (bend - 1) >> 2, wend = en >> 2, wlast = wend > w1 ? wend : w1, ws0 = st0 >> 2;
 		const int en1 = st0 + (((en0 - st0) >> 2) << 2);    // end of the 4-wide vector part of the arg-max (:316)
 		const unsigned bandw = (unsigned)(en0 - st0);       // columns st0 .. en0-1 are updated in the loop
-		uint32_t *prg = (uint32_t*)(pmat + (size_t)r * n_col) + gl; // backtrack row r; word j of the band goes to [j]
+		uint32_t *prg = (uint32_t*)(pmat + (size_t)r * pitch) + gl; // backtrack row r; word j of the band goes to [j]
 		const int cq = qlen - 1 - r;                         // lane t meets query code qr[cq + t]
 		const int qsh = 8 * (cq & 3);
 		const uint32_t *QRr = QRP + (KSW_QR_PAD >> 2) + (cq >> 2);
@@ -300,23 +305,27 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 			const bool core = mine && wi <= wend, sca = mine && wi >= ws0 && wi <= w1;
 			const uint4 own = XV[wm]; uint2 prv = *(const uint2*)&XV[(wm - 1) & rmw];
 			__syncwarp(); // every load of the round is issued before any store of the round
-			if (__all_sync(FULL_MASK, act && j > 0 && t >= st0 && t + 4 <= en0)) {
-				// every word of this round, in all four alignments, lies inside the exact band: fresh scores for all four lanes,
-				// no boundary lane, no masks
-				const uint32_t sq = SF[wm];
-				const uint32_t sq2 = __funnelshift_r(QRr[wi], QRr[wi + 1], qsh);
-				uint32_t z0 = sel4(msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu), MISQ, MATQ);
-				if (wild) z0 = ksw_wild_score(sq, sq2, z0, QE2);
-				S[wm] = z0;
-				const uint32_t xt1 = __funnelshift_l(prv.x, own.x, 8), vt1 = __funnelshift_l(prv.y, own.y, 8);
-				uint32_t d, un, vn, xn, yn;
-				ksw_core_word(P, fast_ok, z0, xt1, vt1, own.z, own.w, xn, vn, un, yn, d);
-				XV[wm] = make_uint4(xn, vn, un, yn);
-				prg[rd * G] = d;
-				uint2 g2 = GR[wm];
-				g2.x += __byte_perm(vn, 0u, 0x4140); g2.y += __byte_perm(vn, 0u, 0x4342);
-				bh2 = __vimax3_u16x2(bh2, g2.x, g2.y);
-				GR[wm] = g2;
+			if (rd > 0 && __all_sync(FULL_MASK, !mine || t + 4 <= en0)) {
+				// every word of this round, in all four alignments, lies inside the exact band (rd > 0 puts it at least 32 lanes
+				// right of st, so right of st0 too): fresh scores for all four lanes, no boundary lane, no masks.  A group that
+				// has no word in this round (shorter band, or finished) only skips.  s is not stored: such a word lies inside
+				// the score blocks of the next diagonal as well (st0 grows by at most one, en0 never shrinks), where its
+				// scores are recomputed or, on the boundary path, stored.
+				if (mine) {
+					const uint32_t sq = SF[wm];
+					const uint32_t sq2 = __funnelshift_r(QRr[wi], QRr[wi + 1], qsh);
+					uint32_t z0 = sel4(msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu), MISQ, MATQ);
+					if (wild) z0 = ksw_wild_score(sq, sq2, z0, QE2);
+					const uint32_t xt1 = __funnelshift_l(prv.x, own.x, 8), vt1 = __funnelshift_l(prv.y, own.y, 8);
+					uint32_t d, un, vn, xn, yn;
+					ksw_core_word(P, fast_ok, z0, xt1, vt1, own.z, own.w, xn, vn, un, yn, d);
+					XV[wm] = make_uint4(xn, vn, un, yn);
+					prg[rd * G] = d;
+					uint2 g2 = GR[wm];
+					g2.x += __byte_perm(vn, 0u, 0x4140); g2.y += __byte_perm(vn, 0u, 0x4342);
+					bh2 = __vimax3_u16x2(bh2, g2.x, g2.y);
+					GR[wm] = g2;
+				}
 				continue;
 			}
 			uint32_t z0 = 0;   // s + 2(q+e)
@@ -384,9 +393,12 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 		const bool need_t = better && (mh > out.max || (P.zdrop >= 0 && out.max - mh > P.zdrop));
 		if (__any_sync(FULL_MASK, need_t)) {
 			unsigned best = 0xffffffffu;
-			if (need_t)
+			if (need_t) {
+				const uint32_t mg2 = mg * 0x10001u;
 				for (int wi = ws0 + gl; wi <= ((en0 - 1) >> 2); wi += G) {
 					const uint2 g2 = GR[(wi + rotw) & rmw];
+					const uint32_t xa = g2.x ^ mg2, xb = g2.y ^ mg2; // a zero halfword = a column that holds the band max
+					if (!((((xa - 0x00010001u) & ~xa) | ((xb - 0x00010001u) & ~xb)) & 0x80008000u)) continue;
 					const int t = wi << 2;
 #pragma unroll
 					for (int c = 0; c < 4; ++c) {
@@ -394,6 +406,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 						if ((unsigned)(t + c - st0) < bandw && val == mg) { const unsigned rk = ksw_tie_rank(t + c, st0, en1); best = rk < best ? rk : best; }
 					}
 				}
+			}
 			const unsigned rk = ksw_group_min(best);
 			if (need_t) { max_H = mh; max_t = st0 + (int)((rk - 1) & 0xfffffu); }
 		}
@@ -467,10 +480,10 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 				if (rr >= 0) {
 					int s0, e0;
 					ksw_band(rr, qlen, tlen, w, s0, e0);
-					long long x0 = (long long)rr * n_col + (i0 - 31 - (s0 & ~15)); // byte offset of column i0-31 of row rr
+					long long x0 = (long long)rr * pitch + (i0 - 31 - (s0 & ~15)); // byte offset of column i0-31 of row rr
 					// a row that holds a readable entry has x0 within 31 bytes of the matrix; anything further out is never read
 					// (the walk is forced there), so clamping keeps the prefetch inside this alignment's workspace
-					const long long x_hi = (long long)(qlen + tlen - 1) * n_col + KSW_PMAT_PAD - 40;
+					const long long x_hi = (long long)(qlen + tlen - 1) * pitch + KSW_PMAT_PAD - 40;
 					x0 = x0 < -(long long)(KSW_PMAT_PAD - 4) ? -(long long)(KSW_PMAT_PAD - 4) : (x0 > x_hi ? x_hi : x0);
 					const uint32_t *src = (const uint32_t*)(pmat + (x0 & ~3LL));
 					const int sh = 8 * (int)(x0 & 3);

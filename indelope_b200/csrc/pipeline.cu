@@ -292,8 +292,8 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 	L.cap_items = (unsigned)std::min<size_t>(8 * b->n_reads + 1024, 0x3fffffffu); // AL items: a read takes part in few AL events
 	CK(L.al_items.ensure((size_t)L.cap_items * sizeof(AlItem))); CK(L.al_res.ensure((size_t)L.cap_items * 2 + 16));
 	CK(L.sort_misc.ensure(6 * SORT_BUCKETS * sizeof(unsigned)));
-	CK(L.keysA.ensure((size_t)L.cap_alns + 16)); CK(L.orderA.ensure((size_t)L.cap_alns * 4 + 16));
-	CK(L.keysB.ensure((size_t)L.cap_items * 2 + 16)); CK(L.orderB.ensure((size_t)L.cap_items * 8 + 16));
+	CK(L.keysA.ensure((size_t)L.cap_alns * 2 + 16)); CK(L.orderA.ensure((size_t)L.cap_alns * 4 + 16));
+	CK(L.keysB.ensure((size_t)L.cap_items * 4 + 16)); CK(L.orderB.ensure((size_t)L.cap_items * 8 + 16));
 	// workspaces
 	size_t n_small = 0;
 	for (size_t i = 0; i < b->n_regions; ++i) n_small += b->region[i].n_reads <= ASM_SMALL_READS;
@@ -312,7 +312,7 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 	const int wA = P.a_bw < 0 ? std::max(P.max_contig_len, (int)max_ref) : P.a_bw;
 	const size_t rowsA = std::min<size_t>((size_t)P.max_contig_len + max_ref, 2 * (size_t)max_ref + wA + 2);
 	const size_t rowsB = (size_t)max_trim + std::max<size_t>(max_ref, 1536);
-	const size_t p_cap = round_up(std::max(rowsA * ncolA, rowsB * ncolB) + 2 * KSW_PMAT_PAD + 64, 256);
+	const size_t p_cap = round_up(std::max(rowsA * ksw_pitch(ncolA), rowsB * ksw_pitch(ncolB)) + 2 * KSW_PMAT_PAD + 64, 256);
 	const size_t n_groups = (size_t)ctx->dp_ctas * DP_WARPS * DP_NG;
 	const int seq_spill_cap = (int)round_up(ksw_seq_bytes(std::max(P.max_contig_len, max_trim), std::max((int)max_ref, P.max_contig_len)), 16);
 	CK(L.pmat.ensure(n_groups * p_cap));
@@ -323,8 +323,8 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 	CK(cudaMemsetAsync(L.sort_misc.p, 0, 6 * SORT_BUCKETS * sizeof(unsigned), L.stream));
 	L.launches = 0;
 	SortBufs sA, sB;
-	sA.hist = (unsigned*)L.sort_misc.p; sA.start = sA.hist + SORT_BUCKETS; sA.cursor = sA.start + SORT_BUCKETS; sA.keys = (uint8_t*)L.keysA.p; sA.order = (unsigned*)L.orderA.p;
-	sB.hist = sA.cursor + SORT_BUCKETS; sB.start = sB.hist + SORT_BUCKETS; sB.cursor = sB.start + SORT_BUCKETS; sB.keys = (uint8_t*)L.keysB.p; sB.order = (unsigned*)L.orderB.p;
+	sA.hist = (unsigned*)L.sort_misc.p; sA.start = sA.hist + SORT_BUCKETS; sA.cursor = sA.start + SORT_BUCKETS; sA.keys = (uint16_t*)L.keysA.p; sA.order = (unsigned*)L.orderA.p;
+	sB.hist = sA.cursor + SORT_BUCKETS; sB.start = sB.hist + SORT_BUCKETS; sB.cursor = sB.start + SORT_BUCKETS; sB.keys = (uint16_t*)L.keysB.p; sB.order = (unsigned*)L.orderB.p;
 
 	AsmArgs a; memset(&a, 0, sizeof a);
 	a.region = (const idl_region*)L.region.p; a.read = (const idl_read*)L.read.p;
@@ -366,7 +366,7 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 		g.seq_cap = (int)round_up(ksw_seq_bytes(std::min(P.max_contig_len, 1024), (int)max_ref), 16); // longer contigs stage in the spill area
 		const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(g.ring_cols, g.seq_cap);
 		if (smem > smem_limit) return IDL_E_CAPACITY;
-		sort_scan_kernel<<<1, SORT_BUCKETS, 0, L.stream>>>(sA);
+		sort_scan_kernel<<<1, 1024, 0, L.stream>>>(sA);
 		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(sA, &a.cnt->n_alns, 1u, L.cap_alns);
 		align_kernel<<<dp_grid(ctx, (const void*)align_kernel, smem), DP_THREADS, smem, L.stream>>>(g);
 		CK(cudaGetLastError()); L.launches += 3;
@@ -381,7 +381,7 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 		const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(g.ring_cols, g.seq_cap);
 		if (smem > smem_limit) return IDL_E_CAPACITY;
 		al_prep_kernel<<<ctx->n_sm * 8, 256, 0, L.stream>>>(g);
-		sort_scan_kernel<<<1, SORT_BUCKETS, 0, L.stream>>>(sB);
+		sort_scan_kernel<<<1, 1024, 0, L.stream>>>(sB);
 		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(sB, &a.cnt->n_al_items, 2u, 2 * L.cap_items);
 		al_kernel<<<dp_grid(ctx, (const void*)al_kernel, smem), DP_THREADS, smem, L.stream>>>(g);
 		al_vote_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(g);
@@ -596,7 +596,7 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 		max_q = std::max(max_q, ql); max_t = std::max(max_t, tl);
 		const int nc = ksw_ncol(std::max(ql, 1), std::max(tl, 1), w);
 		max_ncol = std::max(max_ncol, nc);
-		max_p = std::max(max_p, (size_t)std::max(ql + tl - 1, 0) * (size_t)nc);
+		max_p = std::max(max_p, (size_t)std::max(ql + tl - 1, 0) * (size_t)ksw_pitch(nc));
 	}
 	KswBatchArgs a; memset(&a, 0, sizeof a);
 	a.n = (unsigned)n; a.kp = ksw_make_params(match, mismatch, gapo, gape, w, zdrop);

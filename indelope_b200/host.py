@@ -53,6 +53,14 @@ def lib():
         L.idlh_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
         L.idlh_write_fasta.argtypes = [C.c_void_p, C.c_char_p]
         L.idlh_write_bam.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.idlh_stream_open.restype = C.c_void_p
+        L.idlh_stream_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_size_t]
+        L.idlh_stream_next.restype = C.c_void_p
+        L.idlh_stream_next.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_size_t]
+        L.idlh_stream_targets.restype = C.c_void_p
+        L.idlh_stream_targets.argtypes = [C.c_void_p]
+        L.idlh_stream_counts.argtypes = [C.c_void_p, i64p]
+        L.idlh_stream_close.argtypes = [C.c_void_p]
         L.idlh_sweep.restype = C.c_void_p
         L.idlh_sweep.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         L.idlh_rois_free.argtypes = [C.c_void_p]
@@ -160,6 +168,43 @@ class Dataset:
     def __del__(self):
         if getattr(self, "h", None):
             lib().idlh_dataset_free(self.h)
+            self.h = None
+
+
+class Stream:
+    """FASTA + coordinate-sorted BAM swept front to back in bounded memory: groups of regions of interest, the same
+    regions the whole-file sweep finds (idlh_stream_* in include/indelope_host.h)"""
+
+    def __init__(self, fasta, bam, threads=1, min_reads=3, max_read_coverage=600):
+        err = C.create_string_buffer(512)
+        self.h = lib().idlh_stream_open(str(fasta).encode(), str(bam).encode(), threads, max(3, min_reads - 2), min_reads, max_read_coverage, err, 512)
+        if not self.h:
+            raise IOError(err.value.decode())
+
+    def targets(self):
+        return Rois(lib().idlh_stream_targets(self.h), self)
+
+    def __iter__(self):
+        return self.groups()
+
+    def groups(self, target_reads=400000):
+        while True:
+            err = C.create_string_buffer(512)
+            h = lib().idlh_stream_next(self.h, target_reads, err, 512)
+            if not h:
+                if err.value:
+                    raise IOError(err.value.decode())
+                return
+            yield Rois(h, self)
+
+    def counts(self):
+        c = (C.c_int64 * 2)()
+        lib().idlh_stream_counts(self.h, c)
+        return int(c[0]), int(c[1])
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().idlh_stream_close(self.h)
             self.h = None
 
 

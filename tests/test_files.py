@@ -80,6 +80,47 @@ def test_round_trip_gives_identical_regions_and_oracle_vcf(files):
     assert v1 == v2 and v1.count("\n") > 3
 
 
+def _flatten(groups):
+    """regions of a list of groups as (chrom, start, stop, [(read start, stop, mapq, flag, bases, quals), ...])"""
+    out = []
+    for g in groups:
+        a = g.arrays()
+        for k in range(len(a["roi_start"])):
+            reads = []
+            for i in a["read_idx"][a["roi_read_begin"][k]:a["roi_read_begin"][k] + a["roi_n_reads"][k]]:
+                o, l = int(a["seq_off"][i]), int(a["len"][i])
+                reads.append((int(a["start"][i]), int(a["stop"][i]), int(a["mapq"][i]), int(a["flag"][i]), a["bases"][o:o + l].tobytes(), a["quals"][o:o + l].tobytes()))
+            out.append((int(a["roi_chrom"][k]), int(a["roi_start"][k]), int(a["roi_stop"][k]), reads))
+    return out
+
+
+@pytest.mark.parametrize("target_reads", [1, 300, 10**9])
+def test_streaming_sweep_equals_the_whole_file_sweep(files, target_reads):
+    """idlh_stream_* (incremental gen_roi, bounded memory) against idlh_load + idlh_sweep: same regions, same reads, same order,
+    whatever the group size; and the oracle VCF over the concatenated groups is the whole-file one"""
+    ds, fa, bam = files
+    whole = ds.sweep(min_reads=5)
+    st = host.Stream(fa, bam, threads=2, min_reads=5)
+    groups = list(st.groups(target_reads))
+    assert _flatten(groups) == _flatten([whole])
+    assert sum(g.n_rois for g in groups) == whole.n_rois and st.counts() == (ds.n_reads, whole.n_rois)
+    if target_reads == 1:
+        assert len(groups) >= whole.n_rois // 2  # a group ends at the first record after its target is met
+    assert st.targets().header() == whole.header()
+
+
+def test_streaming_sweep_dense_coverage_without_gaps(tmp_path):
+    """whole-contig 40x coverage: one coverage-gap chunk per contig, so every region is found by the incremental scan while
+    records are still arriving and cached records are dropped early; decoy contig names are skipped (:41-42)"""
+    ds = util.small_dataset("pr1", chrom_len=60_000, n_events=30, max_indel=25, n_chroms=2, coverage=40.0, low_mapq_fraction=0.1, dup_fraction=0.05)
+    fa, bam = str(tmp_path / "d.fa"), str(tmp_path / "d.bam")
+    ds.write_fasta(fa); ds.write_bam(bam, level=1)
+    whole = ds.sweep(min_reads=3)
+    assert whole.n_rois > 20
+    for tr in (1, 5000):
+        assert _flatten(list(host.Stream(fa, bam, min_reads=3).groups(tr))) == _flatten([whole])
+
+
 def test_reader_rejects_bad_input(files, tmp_path):
     ds, fa, bam = files
     with pytest.raises(IOError, match="cannot open"):
@@ -97,6 +138,16 @@ def test_reader_rejects_bad_input(files, tmp_path):
     fa2.write_text(">chrS1\nACGT\n>chrS2\nACGT\n")
     with pytest.raises(IOError, match="different length"):
         host.Dataset.load(str(fa2), bam)
+    with pytest.raises(IOError, match="different length"):
+        host.Stream(str(fa2), bam)
+    with pytest.raises(IOError):
+        host.Stream(fa, str(bad))
+    with pytest.raises(IOError):
+        list(host.Stream(fa, str(tmp_path / "corrupt.bam")).groups())
+    cut = tmp_path / "cut.bam"
+    cut.write_bytes(bytes(open(bam, "rb").read()[:40000]))  # ends inside a BGZF block
+    with pytest.raises(IOError):
+        list(host.Stream(fa, str(cut)).groups())
 
 
 def test_cli_help_and_no_cpu_path(files):

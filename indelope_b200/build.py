@@ -56,7 +56,7 @@ def build_host(force=False, verbose=False):
 
 def build_cuda(force=False, verbose=False):
     if force or _newer(CUDA_LIB, _deps(CUDA_SRCS)):
-        cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", INC, "-I", CSRC] + [os.path.join(CSRC, s) for s in CUDA_SRCS] + ["-o", CUDA_LIB]
+        cmd = [nvcc_path()] + NVCC_FLAGS + os.environ.get("IDL_NVCC_EXTRA", "").split() + ["-I", INC, "-I", CSRC] + [os.path.join(CSRC, s) for s in CUDA_SRCS] + ["-o", CUDA_LIB]
         if verbose:
             print(" ".join(cmd))
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -73,7 +73,7 @@ def build_cli(force=False, verbose=False):
     """the `indelope` binary; finds both libraries next to itself ($ORIGIN)"""
     if force or _newer(CLI_BIN, _deps(CLI_SRCS) + [HOST_LIB, CUDA_LIB]):
         cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", INC] + [os.path.join(CSRC, s) for s in CLI_SRCS] + [
-            "-o", CLI_BIN, "-L", HERE, "-lindelope_host", "-lindelope_cuda", "-Wl,-rpath,$ORIGIN"]
+            "-o", CLI_BIN, "-L", HERE, "-lindelope_host", "-lindelope_cuda", "-lpthread", "-Wl,-rpath,$ORIGIN"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -18,6 +18,20 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef ASM_BLOCKS
+#define ASM_BLOCKS 1          // warp variant: screen (contig, 32-offset block) pairs position-parallel
+#endif
+#ifndef ASM_EVAL_NOINLINE
+#define ASM_EVAL_NOINLINE 0
+#endif
+#ifndef ASM_SCREEN_UNROLL
+#define ASM_SCREEN_UNROLL 4
+#endif
+#if ASM_EVAL_NOINLINE
+#define ASM_EVAL_ATTR __noinline__
+#else
+#define ASM_EVAL_ATTR
+#endif
 #define ASM_THREADS 256        // threads per CTA of both variants
 #define ASM_SMALL_READS 126    // regions up to this many reads are assembled by ONE WARP (no block barriers); larger ones by a CTA
 #define ASM_SMALL_NS (ASM_SMALL_READS + 2)
@@ -47,6 +61,7 @@ struct AsmS { // carved out of dynamic shared memory
 	uint32_t *q0, *q1, *qn;           // staged query planes, nw words each
 	int *len, *nreads, *start;        // per slot
 	uint16_t *listA, *listB, *freestk;
+	uint16_t *blkcum;                 // warp variant: exclusive prefix of the screen blocks per list entry
 	int *corr;                        // 3 ints per correction site: qoff, toff, qbest
 	unsigned long long *best;         // per warp
 	int *sc;                          // scalars: see SC_*
@@ -56,7 +71,7 @@ enum { SC_NFREE = 0, SC_STATUS, SC_TMP0, SC_TMP1, SC_NCORR, SC_REGION, SC_HASN, 
 // shared memory of one cooperating group (a warp or a CTA) for regions of up to ns-2 reads
 __host__ __device__ inline size_t asm_smem_bytes(int ns, int nw, int nt)
 {
-	size_t b = (size_t)3 * nw * 4 + (size_t)3 * ns * 4 + (size_t)3 * ns * 2 + (size_t)3 * IDL_MAX_CORRECTIONS * 4 + (size_t)(nt / 32) * 8 + SC_N * 4 + 16;
+	size_t b = (size_t)3 * nw * 4 + (size_t)3 * ns * 4 + (size_t)4 * ns * 2 + (size_t)3 * IDL_MAX_CORRECTIONS * 4 + (size_t)(nt / 32) * 8 + SC_N * 4 + 16;
 	return (b + 15) & ~(size_t)15;
 }
 
@@ -64,10 +79,11 @@ struct Asm {
 	AsmS s; const AsmArgs *a;
 	uint32_t *planes; uint16_t *supb; int nw, cap, ns;
 	unsigned long long offsets;
-	__device__ uint32_t *p0(int slot) const { return planes + ((size_t)slot * 3 + 0) * nw; }
-	__device__ uint32_t *p1(int slot) const { return planes + ((size_t)slot * 3 + 1) * nw; }
-	__device__ uint32_t *pn(int slot) const { return planes + ((size_t)slot * 3 + 2) * nw; }
-	__device__ uint16_t *sup(int slot) const { return supb + (size_t)slot * cap; }
+	// 32-bit index arithmetic: a group's arena is far below 2^32 words (these show up in every inner loop)
+	__device__ uint32_t *p0(int slot) const { return planes + (unsigned)slot * (unsigned)(3 * nw); }
+	__device__ uint32_t *p1(int slot) const { return planes + ((unsigned)slot * (unsigned)(3 * nw) + (unsigned)nw); }
+	__device__ uint32_t *pn(int slot) const { return planes + ((unsigned)slot * (unsigned)(3 * nw) + 2u * (unsigned)nw); }
+	__device__ uint16_t *sup(int slot) const { return supb + (unsigned)slot * (unsigned)cap; }
 };
 
 // allowable_mismatch, src/contig.nim:44-47 (uint32 products on the supports, int on the read counts)
@@ -105,7 +121,7 @@ template <int NT> __device__ void asm_free(Asm &A, int slot) // call from unifor
 
 // one (query, contig, offset) candidate: number of matching bases, or -1 if a mismatch is not allowed.
 // dir2 == false: loop 1 of slide_align (:86-111), q[i] against t[o+i]; dir2 == true: loop 2 (:114-139), q[o+i] against t[i].
-__device__ int asm_eval(const Asm &A, const uint32_t *t0, const uint32_t *t1, const uint32_t *tn, const uint16_t *tsup, const uint16_t *qsup,
+__device__ ASM_EVAL_ATTR int asm_eval(const uint32_t *sq0, const uint32_t *sq1, const uint32_t *sqn, const uint32_t *t0, const uint32_t *t1, const uint32_t *tn, const uint16_t *tsup, const uint16_t *qsup,
                         int qlen, int tlen, int qreads, int treads, bool dir2, int o, bool vote, bool has_n)
 {
 	const int n = dir2 ? min(qlen - o, tlen) : min(qlen, tlen - o);
@@ -117,11 +133,11 @@ __device__ int asm_eval(const Asm &A, const uint32_t *t0, const uint32_t *t1, co
 		uint32_t m;
 		const int pos = o + 32 * w;
 		if (!dir2) {
-			m = (A.s.q0[w] ^ get32(t0, pos)) | (A.s.q1[w] ^ get32(t1, pos));
-			if (has_n) m |= A.s.qn[w] ^ get32(tn, pos);
+			m = (sq0[w] ^ get32(t0, pos)) | (sq1[w] ^ get32(t1, pos));
+			if (has_n) m |= sqn[w] ^ get32(tn, pos);
 		} else {
-			m = (t0[w] ^ get32(A.s.q0, pos)) | (t1[w] ^ get32(A.s.q1, pos));
-			if (has_n) m |= tn[w] ^ get32(A.s.qn, pos);
+			m = (t0[w] ^ get32(sq0, pos)) | (t1[w] ^ get32(sq1, pos));
+			if (has_n) m |= tn[w] ^ get32(sqn, pos);
 		}
 		const int rem = n - 32 * w;
 		if (rem < 32) m &= (1u << rem) - 1u;
@@ -140,6 +156,31 @@ __device__ int asm_eval(const Asm &A, const uint32_t *t0, const uint32_t *t1, co
 }
 
 struct AsmMatch { int k, offset, ma; bool aligned; };
+
+// Exact-overlap screen of 32 consecutive offsets at once.  text0/text1(/textn) hold 64 bits of the sliding side's planes
+// starting at the block's first offset, pat0/pat1(/patn) the first word of the fixed side: bit b of the result is set when
+// the 16 bases the fixed side starts with equal the sliding side's bases b .. b+15 (position-parallel compare: one funnel
+// shift per plane and base instead of one compare per offset).
+// Kept as a short loop (the kernel lives or dies by the instruction cache), the three-plane variant out of line.
+template <bool HAS_N>
+__device__ __forceinline__ uint32_t asm_screen32_t(uint32_t pat0, uint32_t pat1, uint32_t patn, uint32_t ta0, uint32_t tb0, uint32_t ta1, uint32_t tb1,
+                                                   uint32_t tan, uint32_t tbn)
+{
+	uint32_t m = 0xffffffffu;
+	const uint32_t np0 = ~pat0, np1 = ~pat1, npn = ~patn;
+	constexpr int UNR = ASM_SCREEN_UNROLL;
+#pragma unroll UNR
+	for (int j = 0; j < 16; ++j) {
+		const uint32_t a = (uint32_t)((int32_t)(np0 << (31 - j)) >> 31), b = (uint32_t)((int32_t)(np1 << (31 - j)) >> 31); // ~0 where the pattern bit is 0
+		m &= (__funnelshift_r(ta0, tb0, j) ^ a) & (__funnelshift_r(ta1, tb1, j) ^ b);
+		if (HAS_N) m &= __funnelshift_r(tan, tbn, j) ^ (uint32_t)((int32_t)(npn << (31 - j)) >> 31);
+	}
+	return m;
+}
+__device__ __noinline__ uint32_t asm_screen32_n(uint32_t pat0, uint32_t pat1, uint32_t patn, uint32_t ta0, uint32_t tb0, uint32_t ta1, uint32_t tb1, uint32_t tan, uint32_t tbn)
+{
+	return asm_screen32_t<true>(pat0, pat1, patn, ta0, tb0, ta1, tb1, tan, tbn);
+}
 
 // best_match (:224-240) of slot q against list[0..nlist). Uniform result.
 // One lane per (contig, offset) candidate, a warp per contig.  A pair that cannot vote (fewer than 4 reads on either
@@ -165,6 +206,67 @@ template <int NT> __device__ AsmMatch asm_best_match(Asm &A, const uint16_t *lis
 	const uint16_t *qsup = A.sup(q);
 	const uint32_t qf0 = A.s.q0[0], qf1 = A.s.q1[0], qfn = A.s.qn[0];
 	unsigned long long best = 0, tested = 0;
+	// Warp variant: every (contig, 32-offset block) pair of the contigs that cannot vote becomes one lane task, so one
+	// pass of the warp screens 32 blocks = up to 1024 offsets of many contigs at once; the few offsets that survive the
+	// 16-base screen run the full compare.  Needs mo - 1 >= 16: an overlap shorter than 16 bases then cannot qualify.
+	const bool blocks = ASM_BLOCKS && NT == 32 && mo >= 17;
+	if (blocks) {
+		const int nb2 = (n2 >> 5) + 1; // loop 2 offsets are 1 .. n2: bits 1 .. n2 of the blocks 0 .. n2 / 32
+		unsigned carry = 0;
+#pragma unroll 1
+		for (int k0 = 0; k0 < nlist; k0 += 32) {
+			const int k = k0 + lane;
+			unsigned nb = 0;
+			if (k < nlist) {
+				const int t = list[k];
+				const bool vote = qreads >= 4 && A.s.nreads[t] >= 4;
+				if (!vote) { const int omax = A.s.len[t] - mo; nb = (unsigned)((omax >= 0 ? (omax >> 5) + 1 : 0) + nb2); }
+			}
+			unsigned inc = nb;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(FULL_MASK, inc, d); if (lane >= d) inc += o; }
+			if (k < nlist) A.s.blkcum[k] = (uint16_t)(carry + inc - nb);
+			carry += __shfl_sync(FULL_MASK, inc, 31);
+		}
+		__syncwarp();
+		const int total = (int)carry;
+#pragma unroll 1
+		for (int task = lane; task < total; task += 32) {
+			int lo = 0, hi = nlist - 1; // the last entry whose first block is <= task (entries without blocks share their successor's start)
+			while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int)A.s.blkcum[mid] <= task) lo = mid; else hi = mid - 1; }
+			const int k = lo, t = list[k], tlen = A.s.len[t];
+			const int omax = tlen - mo, n1 = omax >= 0 ? omax + 1 : 0, nb1 = omax >= 0 ? (omax >> 5) + 1 : 0;
+			int B = task - (int)A.s.blkcum[k];
+			const bool dir2 = B >= nb1;
+			if (dir2) B -= nb1;
+			const uint32_t *t0 = A.p0(t), *t1 = t0 + A.nw, *tn = t1 + A.nw;
+			// loop 1: the contig slides under the query's first bases; loop 2: the query under the contig's
+			const uint32_t *x0 = dir2 ? A.s.q0 : t0, *x1 = dir2 ? A.s.q1 : t1;
+			const uint32_t pat0 = dir2 ? t0[0] : qf0, pat1 = dir2 ? t1[0] : qf1;
+			uint32_t m;
+			if (!has_n) m = asm_screen32_t<false>(pat0, pat1, 0u, x0[B], x0[B + 1], x1[B], x1[B + 1], 0u, 0u);
+			else { const uint32_t *xn = dir2 ? A.s.qn : tn; m = asm_screen32_n(pat0, pat1, dir2 ? tn[0] : qfn, x0[B], x0[B + 1], x1[B], x1[B + 1], xn[B], xn[B + 1]); }
+			// offsets of this block that exist (:86,114) and overlap by at least the 16 screened bases
+			const int o0 = 32 * B;
+			int last = dir2 ? min(n2, min(qlen - 16, qlen - 1)) : min(n1 - 1, tlen - 16); // largest offset worth a look
+			if (dir2 && tlen < 16) last = -1;
+			if (!dir2 && qlen < 16) last = -1;
+			const int hi_b = last - o0; // bits 0 .. hi_b
+			if (hi_b < 0) m = 0; else if (hi_b < 31) m &= (2u << hi_b) - 1u;
+			if (dir2 && B == 0) m &= ~1u; // offset 0 belongs to loop 1
+			const unsigned long long kkey = (unsigned long long)(0xffff - k) << 16;
+			while (m) {
+				const int b = __ffs(m) - 1; m &= m - 1;
+				const int o = o0 + b;
+				const int ma = asm_eval(A.s.q0, A.s.q1, A.s.qn, t0, t1, tn, A.sup(t), qsup, qlen, tlen, qreads, 0, dir2, o, false, has_n);
+				if (ma >= 0 && ma >= mo - 1) {
+					const int sidx = dir2 ? n1 + o - 1 : o;
+					const unsigned long long k64 = ((unsigned long long)(unsigned)(ma + 1) << 32) | kkey | (unsigned long long)(0xffff - sidx);
+					best = k64 > best ? k64 : best;
+				}
+			}
+		}
+	}
 #pragma unroll 1
 	for (int k = warp; k < nlist; k += (NT / 32)) {
 		const int t = list[k];
@@ -173,6 +275,8 @@ template <int NT> __device__ AsmMatch asm_best_match(Asm &A, const uint16_t *lis
 		const int n1 = omax >= 0 ? omax + 1 : 0;
 		bool vote = false; // a vote needs support >= 4 on one side and reads >= 4 on the other (supports are 1..nreads)
 		if (qreads >= 4) vote = A.s.nreads[t] >= 4;
+		tested += (unsigned long long)(n1 + n2);
+		if (blocks && !vote) continue; // screened above
 		const uint32_t *t0 = A.p0(t), *t1 = t0 + A.nw, *tn = t1 + A.nw;
 		const uint32_t tf0 = t0[0], tf1 = t1[0], tfn = has_n ? tn[0] : 0u;
 		const unsigned long long kkey = (unsigned long long)(0xffff - k) << 16;
@@ -182,7 +286,7 @@ template <int NT> __device__ AsmMatch asm_best_match(Asm &A, const uint16_t *lis
 			const int o = dir2 ? sidx - n1 + 1 : sidx;
 			const int n = dir2 ? min(qlen - o, tlen) : min(qlen, tlen - o);
 			int ma = -1;
-			bool full = vote || n <= 0;
+			bool full = vote || n <= 0 || (ASM_BLOCKS && NT == 32); // the warp variant screens by blocks above; what is left for this loop compares in full
 			if (!full) { // exact overlap needed: screen the first word
 				uint32_t m;
 				const int w = o >> 5, sh = o & 31;
@@ -196,14 +300,13 @@ template <int NT> __device__ AsmMatch asm_best_match(Asm &A, const uint16_t *lis
 				if (n < 32) m &= (1u << n) - 1u;
 				if (!m) { if (n <= 32) ma = n; else full = true; }
 			}
-			if (full) ma = asm_eval(A, t0, t1, tn, A.sup(t), qsup, qlen, tlen, qreads, vote ? A.s.nreads[t] : 0, dir2, o, vote, has_n);
+			if (full) ma = asm_eval(A.s.q0, A.s.q1, A.s.qn, t0, t1, tn, A.sup(t), qsup, qlen, tlen, qreads, vote ? A.s.nreads[t] : 0, dir2, o, vote, has_n);
 			// first candidate needs ma >= mo-1 (best_ma starts at mo-1, best_mm at 1: :81-82,107); later ones strictly more
 			if (ma >= 0 && ma >= mo - 1) {
 				const unsigned long long k64 = ((unsigned long long)(unsigned)(ma + 1) << 32) | kkey | (unsigned long long)(0xffff - sidx);
 				best = k64 > best ? k64 : best;
 			}
 		}
-		tested += (unsigned long long)(n1 + n2);
 	}
 #pragma unroll
 	for (int d = 16; d >= 1; d >>= 1) { const unsigned long long o = __shfl_xor_sync(FULL_MASK, best, d); best = o > best ? o : best; }
@@ -403,13 +506,16 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 	A.planes = args.planes + grp * args.ns * 3 * args.nw;
 	A.supb = args.sup + grp * args.ns * args.cap;
 	{ // carve shared memory
+		// plain pointer arithmetic from the shared array only (an integer round trip, e.g. to align, would turn every later
+		// access into a generic 64-bit load): the 8-byte entries come first, the group's region is a multiple of 16 bytes
 		unsigned char *p = smem_raw + asm_smem_bytes(args.ns, args.nw, NT) * grp_in_cta;
+		A.s.best = (unsigned long long*)p; p += (size_t)(NT / 32) * 8;
 		A.s.q0 = (uint32_t*)p; p += (size_t)A.nw * 4; A.s.q1 = (uint32_t*)p; p += (size_t)A.nw * 4; A.s.qn = (uint32_t*)p; p += (size_t)A.nw * 4;
 		A.s.len = (int*)p; p += (size_t)A.ns * 4; A.s.nreads = (int*)p; p += (size_t)A.ns * 4; A.s.start = (int*)p; p += (size_t)A.ns * 4;
 		A.s.corr = (int*)p; p += (size_t)3 * IDL_MAX_CORRECTIONS * 4;
-		A.s.best = (unsigned long long*)(((uintptr_t)p + 7) & ~(uintptr_t)7); p = (unsigned char*)(A.s.best + (NT / 32));
 		A.s.sc = (int*)p; p += SC_N * 4;
-		A.s.listA = (uint16_t*)p; p += (size_t)A.ns * 2; A.s.listB = (uint16_t*)p; p += (size_t)A.ns * 2; A.s.freestk = (uint16_t*)p;
+		A.s.listA = (uint16_t*)p; p += (size_t)A.ns * 2; A.s.listB = (uint16_t*)p; p += (size_t)A.ns * 2; A.s.freestk = (uint16_t*)p; p += (size_t)A.ns * 2;
+		A.s.blkcum = (uint16_t*)p;
 	}
 	const int tid = asm_tid<NT>();
 	const idl_params &P = args.P;

@@ -14,6 +14,8 @@
 #include <cstring>
 #include <deque>
 #include <string>
+#include <chrono>
+#include <thread>
 #include <vector>
 #include "indelope_cuda.h"
 #include "indelope_host.h"
@@ -39,6 +41,9 @@ static const char USAGE[] =
 
 struct Lane { idl_batch *batch = nullptr; size_t cap[4] = {0, 0, 0, 0}; };
 struct Flight { idlh_rois *rois; uint64_t ticket; };
+
+// INDELOPE_TIMING=1: wall-clock phases on stderr
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 static int die(const char *what, const std::string &why) { fprintf(stderr, "indelope: %s: %s\n", what, why.c_str()); return 1; }
 
@@ -72,6 +77,8 @@ int main(int argc, char **argv)
 	if (pos.size() != 2) { fputs(USAGE, stderr); return 1; }
 
 	char err[512] = {0};
+	const bool timing = getenv("INDELOPE_TIMING") != nullptr;
+	const double t_begin = now_s(); double t_sweep = 0, t_pack = 0, t_wait = 0, t_vcf = 0, t0;
 	// gen_roi(b, target, min_read_coverage=min_reads, min_event_support=max(3, min_reads-2)), src/indelope.nim:602; the BAM
 	// is swept front to back in bounded memory (idlh_stream_*), a group of regions at a time
 	idlh_stream *in = idlh_stream_open(pos[0].c_str(), pos[1].c_str(), threads, min_reads - 2 > 3 ? min_reads - 2 : 3, min_reads, 600, err, sizeof err);
@@ -80,23 +87,32 @@ int main(int argc, char **argv)
 	idl_params P;
 	idl_default_params(&P);
 	P.min_reads = min_reads; P.min_ctg_len = min_ctg_len; P.min_event_len = min_event_len;
+	// the CUDA context and the library's workspaces come up on a helper thread while this one already reads the BAM; nothing
+	// is printed before the context exists (without a device the program fails with empty stdout)
 	idl_ctx *ctx = nullptr;
-	int rc = idl_create(device, &P, &ctx);
-	if (rc != IDL_OK) return die("libindelope_cuda", std::string(idl_strerror(rc)) + " (this program has no CPU path; it needs a CUDA device)");
-
-	{ // echo header % [b.contig_header, "sample"], :599
-		idlh_rois *t = idlh_stream_targets(in);
+	int create_rc = IDL_OK, rc = IDL_OK, status = 0; double t_create = 0;
+	const double t_open = now_s() - t_begin;
+	std::thread creator([&]() { const double t1 = now_s(); create_rc = idl_create(device, &P, &ctx); t_create = now_s() - t1; });
+	bool have_ctx = false;
+	auto need_ctx = [&]() -> bool {
+		if (have_ctx) return true;
+		creator.join();
+		if (create_rc != IDL_OK) { status = die("libindelope_cuda", std::string(idl_strerror(create_rc)) + " (this program has no CPU path; it needs a CUDA device)"); return false; }
+		idlh_rois *t = idlh_stream_targets(in); // echo header % [b.contig_header, "sample"], :599
 		char *h = idlh_vcf_header(idlh_rois_view(t)); fputs(h, stdout); idlh_free(h);
 		idlh_rois_free(t);
-	}
+		have_ctx = true;
+		return true;
+	};
 	idlh_vcf *writer = idlh_vcf_new();
 	std::vector<Lane> lanes((size_t)(P.n_streams > 0 ? P.n_streams : 1));
 	std::deque<Flight> inflight;
-	int status = 0;
 	auto drain = [&]() -> bool {
 		const Flight f = inflight.front(); inflight.pop_front();
 		const idl_results *res = nullptr;
+		double t1 = now_s();
 		const int r = idl_wait(ctx, f.ticket, &res);
+		t_wait += now_s() - t1; t1 = now_s();
 		if (r != IDL_OK) { status = die("idl_wait", std::string(idl_strerror(r)) + " " + idl_last_cuda_error(ctx)); idlh_rois_free(f.rois); return false; }
 		char *dump = nullptr;
 		char *txt = idlh_vcf_records(writer, idlh_rois_view(f.rois), 0, &P, res, 0, &dump);
@@ -104,6 +120,7 @@ int main(int argc, char **argv)
 		idlh_free(txt); idlh_free(dump);
 		idl_release(ctx, f.ticket);
 		idlh_rois_free(f.rois);
+		t_vcf += now_s() - t1;
 		return true;
 	};
 	// one batch per group of regions, in emission order (the dedup of :604-608 depends on it); while the GPU works on a
@@ -112,12 +129,16 @@ int main(int argc, char **argv)
 	size_t nb = 0;
 	while (!status) {
 		err[0] = 0;
+		t0 = now_s();
 		idlh_rois *grp = idlh_stream_next(in, target_reads, err, sizeof err);
+		t_sweep += now_s() - t0;
 		if (!grp) { if (err[0]) status = die("input", err); break; }
 		const idlh_roiset *rs = idlh_rois_view(grp);
 		if (rs->n_rois == 0) { idlh_rois_free(grp); continue; }
+		if (!need_ctx()) { idlh_rois_free(grp); break; }
 		if (inflight.size() >= lanes.size() && !drain()) { idlh_rois_free(grp); break; }
 		Lane &L = lanes[nb % lanes.size()];
+		t0 = now_s();
 		size_t need[4] = {(size_t)rs->n_rois, 0, 0, 0};
 		idlh_pack_size(rs, 0, rs->n_rois, &P, &need[1], &need[2], &need[3]);
 		bool grow = L.batch == nullptr;
@@ -133,13 +154,20 @@ int main(int argc, char **argv)
 		rc = idl_submit(ctx, L.batch, &ticket);
 		if (rc != IDL_OK) { status = die("idl_submit", std::string(idl_strerror(rc)) + " " + idl_last_cuda_error(ctx)); idlh_rois_free(grp); break; }
 		inflight.push_back({grp, ticket});
+		t_pack += now_s() - t0;
 		++nb;
 	}
+	if (!status) need_ctx(); // a BAM without any region still gets its header
 	while (!inflight.empty() && !status) if (!drain()) break;
 	while (!inflight.empty()) { idlh_rois_free(inflight.front().rois); inflight.pop_front(); }
-	for (Lane &L : lanes) if (L.batch) idl_batch_free(ctx, L.batch);
+	for (Lane &L : lanes) if (L.batch && ctx) idl_batch_free(ctx, L.batch);
 	idlh_vcf_free(writer);
-	idl_destroy(ctx);
+	if (creator.joinable()) creator.join();
+	t0 = now_s();
+	if (ctx) idl_destroy(ctx);
 	idlh_stream_close(in);
+	if (timing)
+		fprintf(stderr, "indelope timing: open %.3f s, idl_create %.3f s, read+sweep %.3f s, pack+submit %.3f s, idl_wait %.3f s, vcf %.3f s, teardown %.3f s, total %.3f s, batches %zu\n",
+		        t_open, t_create, t_sweep, t_pack, t_wait, t_vcf, now_s() - t0, now_s() - t_begin, nb);
 	return status;
 }

@@ -77,13 +77,14 @@ __host__ __device__ inline size_t asm_smem_bytes(int ns, int nw, int nt)
 
 struct Asm {
 	AsmS s; const AsmArgs *a;
-	uint32_t *planes; uint16_t *supb; int nw, cap, ns;
+	unsigned pbase, sbase; int nw, cap, ns;  // this group's arena as 32-bit element offsets into a->planes / a->sup
 	unsigned long long offsets;
-	// 32-bit index arithmetic: a group's arena is far below 2^32 words (these show up in every inner loop)
-	__device__ uint32_t *p0(int slot) const { return planes + (unsigned)slot * (unsigned)(3 * nw); }
-	__device__ uint32_t *p1(int slot) const { return planes + ((unsigned)slot * (unsigned)(3 * nw) + (unsigned)nw); }
-	__device__ uint32_t *pn(int slot) const { return planes + ((unsigned)slot * (unsigned)(3 * nw) + 2u * (unsigned)nw); }
-	__device__ uint16_t *sup(int slot) const { return supb + (unsigned)slot * (unsigned)cap; }
+	// 32-bit index arithmetic on top of the kernel-parameter base pointers: the arenas stay below 2^32 elements, and these
+	// accessors sit in every inner loop of an instruction-cache-bound kernel
+	__device__ uint32_t *p0(int slot) const { return a->planes + (pbase + (unsigned)slot * (unsigned)(3 * nw)); }
+	__device__ uint32_t *p1(int slot) const { return a->planes + (pbase + (unsigned)slot * (unsigned)(3 * nw) + (unsigned)nw); }
+	__device__ uint32_t *pn(int slot) const { return a->planes + (pbase + (unsigned)slot * (unsigned)(3 * nw) + 2u * (unsigned)nw); }
+	__device__ uint16_t *sup(int slot) const { return a->sup + (sbase + (unsigned)slot * (unsigned)cap); }
 };
 
 // allowable_mismatch, src/contig.nim:44-47 (uint32 products on the supports, int on the read counts)
@@ -133,11 +134,11 @@ __device__ ASM_EVAL_ATTR int asm_eval(const uint32_t *sq0, const uint32_t *sq1, 
 		uint32_t m;
 		const int pos = o + 32 * w;
 		if (!dir2) {
-			m = (sq0[w] ^ get32(t0, pos)) | (sq1[w] ^ get32(t1, pos));
-			if (has_n) m |= sqn[w] ^ get32(tn, pos);
+			m = (sq0[w] ^ get32p(t0, pos)) | (sq1[w] ^ get32p(t1, pos));
+			if (has_n) m |= sqn[w] ^ get32p(tn, pos);
 		} else {
-			m = (t0[w] ^ get32(sq0, pos)) | (t1[w] ^ get32(sq1, pos));
-			if (has_n) m |= tn[w] ^ get32(sqn, pos);
+			m = (t0[w] ^ get32p(sq0, pos)) | (t1[w] ^ get32p(sq1, pos));
+			if (has_n) m |= tn[w] ^ get32p(sqn, pos);
 		}
 		const int rem = n - 32 * w;
 		if (rem < 32) m &= (1u << rem) - 1u;
@@ -352,8 +353,8 @@ template <int NT> __device__ void asm_merge(Asm &A, uint16_t *list, int k, int q
 			for (int w = 0; w * 32 < n; ++w) {
 				const int pos = o + 32 * w;
 				uint32_t m;
-				if (!dir2) m = (qp[0][w] ^ get32(tp[0], pos)) | (qp[1][w] ^ get32(tp[1], pos)) | (qp[2][w] ^ get32(tp[2], pos));
-				else m = (tp[0][w] ^ get32(qp[0], pos)) | (tp[1][w] ^ get32(qp[1], pos)) | (tp[2][w] ^ get32(qp[2], pos));
+				if (!dir2) m = (qp[0][w] ^ get32p(tp[0], pos)) | (qp[1][w] ^ get32p(tp[1], pos)) | (qp[2][w] ^ get32p(tp[2], pos));
+				else m = (tp[0][w] ^ get32p(qp[0], pos)) | (tp[1][w] ^ get32p(qp[1], pos)) | (tp[2][w] ^ get32p(qp[2], pos));
 				const int rem = n - 32 * w;
 				if (rem < 32) m &= (1u << rem) - 1u;
 				while (m) {
@@ -484,7 +485,7 @@ template <int NT> __device__ int asm_trim(Asm &A, int c, int min_support, bool h
 	uint16_t *dsup = A.sup(d);
 	#pragma unroll 1
 	for (int w = tid; w * 32 < newlen; w += NT) {
-		d0[w] = get32(s0, a + 32 * w); d1[w] = get32(s1, a + 32 * w); dn[w] = has_n ? get32(sn, a + 32 * w) : 0u;
+		d0[w] = get32p(s0, a + 32 * w); d1[w] = get32p(s1, a + 32 * w); dn[w] = has_n ? get32p(sn, a + 32 * w) : 0u;
 	}
 	#pragma unroll 1
 	for (int i = tid; i < newlen; i += NT) dsup[i] = sp[a + i];
@@ -503,8 +504,8 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 	A.a = &args; A.nw = args.nw; A.cap = args.cap; A.ns = args.ns; A.offsets = 0;
 	const int grp_in_cta = NT == 32 ? (int)(threadIdx.x >> 5) : 0;
 	const size_t grp = (size_t)blockIdx.x * (ASM_THREADS / NT) + grp_in_cta; // this group's arena
-	A.planes = args.planes + grp * args.ns * 3 * args.nw;
-	A.supb = args.sup + grp * args.ns * args.cap;
+	A.pbase = (unsigned)(grp * args.ns * 3 * args.nw);
+	A.sbase = (unsigned)(grp * args.ns * args.cap);
 	{ // carve shared memory
 		// plain pointer arithmetic from the shared array only (an integer round trip, e.g. to align, would turn every later
 		// access into a generic 64-bit load): the 8-byte entries come first, the group's region is a multiple of 16 bytes
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 							if (tl - 32 * w < 32) m = (1u << (tl - 32 * w)) - 1u;
 							g0[w] = compress_even(bits) & m;
 							g1[w] = compress_even(bits >> 1) & m;
-							gn[w] = has_n ? (get32(args.seqn, (int)b) & m) : 0u;
+							gn[w] = has_n ? (get32p(args.seqn, (int)b) & m) : 0u;
 						}
 						#pragma unroll 1
 						for (int i = tid; i < tl; i += NT) gs[i] = 1;

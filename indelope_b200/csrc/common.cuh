@@ -73,6 +73,12 @@ __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
 // 32 bits of a bit-plane starting at bit position `pos` (pos may be negative: missing low bits read as 0).
 // The caller guarantees one padding word after the last word it can touch.
+// the same for a position known to be >= 0 (no branch: the inner loops of the assembler are instruction-cache bound)
+__device__ __forceinline__ uint32_t get32p(const uint32_t *plane, int pos)
+{
+	const int w = pos >> 5;
+	return __funnelshift_r(plane[w], plane[w + 1], pos & 31);
+}
 __device__ __forceinline__ uint32_t get32(const uint32_t *plane, int pos)
 {
 	if (pos >= 0) {

@@ -299,6 +299,9 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 	for (size_t i = 0; i < b->n_regions; ++i) n_small += b->region[i].n_reads <= ASM_SMALL_READS;
 	const size_t n_big = b->n_regions - n_small;
 	const int big_ctas = (int)std::min<size_t>(n_big, (size_t)ctx->asm_ctas), small_ctas = (int)std::min<size_t>((n_small + 7) / 8, (size_t)ctx->asm_ctas);
+	// the assembler addresses its arenas with 32-bit element offsets
+	if ((size_t)big_ctas * ctx->ns * std::max<size_t>(3 * (size_t)ctx->nw, (size_t)P.max_contig_len) >= 0xffffffffULL ||
+	    (size_t)small_ctas * 8 * ASM_SMALL_NS * std::max<size_t>(3 * (size_t)ctx->nw, (size_t)P.max_contig_len) >= 0xffffffffULL) return IDL_E_CAPACITY;
 	if (n_big) {
 		CK(L.planes.ensure((size_t)big_ctas * ctx->ns * 3 * ctx->nw * 4));
 		CK(L.sup.ensure((size_t)big_ctas * ctx->ns * P.max_contig_len * 2));

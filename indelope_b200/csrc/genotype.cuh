@@ -386,6 +386,7 @@ __device__ __forceinline__ int count_flanked(const uint32_t *cig_rev, int n, int
 }
 
 // AL fallback, step 2: call-site B of kernel 2, one group per task (read vs reference suffix / contig suffix), :343-347
+template <bool UNB>
 __global__ void __launch_bounds__(DP_THREADS, 3) al_kernel(GenoArgs g)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(DP_THREADS, 3) al_kernel(GenoArgs g)
 		}
 		const KswMem M = dp_mem(g, smem_raw, qlen, tlen);
 		KswOut o;
-		ksw2_group<DP_G>(valid, qlen, kq, tlen, t, g.kpB, M, o); // the whole warp: four alignments in lockstep
+		ksw2_group<DP_G, false, UNB>(valid, qlen, kq, tlen, t, g.kpB, M, o); // the whole warp: four alignments in lockstep
 		if (valid) {
 			if (gl == 0) {
 				const unsigned st = dp_status_bits(o.status);

@@ -65,13 +65,16 @@ __host__ __device__ inline size_t ksw_seq_bytes(int qlen, int tlen)
 }
 
 // off[r] / off_end[r] of the reference are pure functions of r (:196-199,205)
-__device__ __forceinline__ void ksw_band(int r, int qlen, int tlen, int w, int &st0, int &en0)
+// unb: w >= max(qlen, tlen), where the two w-clamps never bind ((r-w+1)>>1 <= max(0, r-qlen+1) and (r+w)>>1 >= min(r, tlen-1))
+__device__ __forceinline__ void ksw_band(int r, int qlen, int tlen, int w, int &st0, int &en0, bool unb = false)
 {
 	int st = 0, en = tlen - 1;
 	if (st < r - qlen + 1) st = r - qlen + 1;
 	if (en > r) en = r;
-	if (st < ((r - w + 1) >> 1)) st = (r - w + 1) >> 1;
-	if (en > ((r + w) >> 1)) en = (r + w) >> 1;
+	if (!unb) {
+		if (st < ((r - w + 1) >> 1)) st = (r - w + 1) >> 1;
+		if (en > ((r + w) >> 1)) en = (r + w) >> 1;
+	}
 	st0 = st; en0 = en;
 }
 
@@ -207,7 +210,16 @@ __device__ __forceinline__ void ksw_core_word(const KswParams &P, bool fast_ok, 
 // without one).  The anti-diagonal loop and the rounds inside it run in lockstep over the four alignments, so every
 // barrier and shuffle is a plain full-warp one; a group whose alignment is shorter or has stopped idles behind a predicate.
 // The threads of a group pass identical arguments; `out` comes back identical in each of them.
-template <int G>
+// EZ_FULL = false drops the end-of-query / end-of-target scores (mqe, mte, score of ksw_extz_t): the AL fallback reads only
+// the CIGAR and max_q (src/indelope.nim:346-347 over the truncated iterator of src/ksw2/ksw2.nim:22-33).
+// UNB = true is the unbanded case, P.w < 0 (the AL fallback, src/indelope.nim:317-318,343-344): w = max(qlen, tlen), the
+// band is the whole anti-diagonal [max(0, r-qlen+1), min(r, tlen-1)] and neither w-clamp of :196-199 ever binds.  A real
+// cell then only reads real cells of the previous diagonal (its left neighbour t-1 was the first in-band lane there; a
+// column that enters gets u, y from the :212 patch), so the lanes the SSE code computes beyond the exact band through its
+// 16-lane rounding -- which the banded call-site must reproduce because they feed real cells later -- are write-only
+// here and nothing reads their backtrack bytes.  The variant therefore computes only the packed words that hold in-band
+// lanes, always with fresh scores (no stale-score ring), and stores backtrack rows from the band's first word.
+template <int G, bool EZ_FULL = true, bool UNB = false>
 __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen, const uint8_t *target, const KswParams P, const KswMem M, KswOut &out)
 {
 	static_assert(G == 8, "the clear-ahead step deals 8 words to the 8 threads of a group");
@@ -221,7 +233,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 	int w = P.w;
 	if (w < 0) w = tlen > qlen ? tlen : qlen; // :161
 	const int n_col = valid ? ksw_ncol(qlen, tlen, w) : 16; // :164-165 (bytes)
-	const int pitch = ksw_pitch(n_col);
+	const int pitch = UNB ? ksw_pitch(4 * ((((qlen < tlen ? qlen : tlen) + 3) >> 2) + 1)) : ksw_pitch(n_col);
 	// The exact scores H[] (:177-178, int32 in the reference) live as uint16: g[t] = H[t] + (q+e)*(r+1) + gbias, r = the
 	// diagonal of the last update.  Every in-band column is updated on every diagonal, so the per-diagonal -(q+e) of
 	// :323-348 turns into a common offset, the update into an unsigned byte add, and the band max into a packed 16-bit max.
@@ -229,6 +241,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 	bool live = valid;
 	if (live) {
 		if (qlen <= 0 || tlen <= 0) { out.status = KSW_ST_EARLY; live = false; }     // :147
+		else if (UNB && P.w >= 0) { out.status = KSW_ST_RCAP; live = false; }         // the caller picked the wrong variant
 		else if (-min_sc > 2 * qe) { out.status = KSW_ST_EARLY; live = false; }      // :171
 		else if (ksw_ring_cols(n_col) > M.ring_cols) { out.status = KSW_ST_RCAP; live = false; }
 		else if (ksw_seq_bytes(qlen, tlen) > (size_t)M.seq_cap) { out.status = KSW_ST_SEQCAP; live = false; }
@@ -283,12 +296,13 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 			gprev = G16[(c + rotc) & rm];
 			if (c < last_st0 || c > last_en0) { // the column was not part of the previous band: its offset is older (the band left the matrix on the right)
 				int rr = r - 1;
-				for (; rr > 0; --rr) { int s_, e_; ksw_band(rr, qlen, tlen, w, s_, e_); if (s_ <= c && c <= e_) break; }
+				for (; rr > 0; --rr) { int s_, e_; ksw_band(rr, qlen, tlen, w, s_, e_, UNB); if (s_ <= c && c <= e_) break; }
 				gprev += (unsigned)(qe * (r - 1 - rr));
 			}
 		}
 		const int bend = st0 + (int)((((unsigned)(en0 - st0) >> 4) + 1u) << 4); // one past the last lane the 16-wide score blocks write (en0 >= st0 here)
-		const int wfirst = st >> 2, w1 = (bend - 1) >> 2, wend = en >> 2, wlast = wend > w1 ? wend : w1, ws0 = st0 >> 2;
+		const int ws0 = st0 >> 2, w1 = (bend - 1) >> 2, wend = UNB ? en0 >> 2 : en >> 2;
+		const int wfirst = UNB ? ws0 : st >> 2, wlast = UNB ? wend : (wend > w1 ? wend : w1);
 		const int en1 = st0 + (((en0 - st0) >> 2) << 2);    // end of the 4-wide vector part of the arg-max (:316)
 		const unsigned bandw = (unsigned)(en0 - st0);       // columns st0 .. en0-1 are updated in the loop
 		uint32_t *prg = (uint32_t*)(pmat + (size_t)r * pitch) + gl; // backtrack row r; word j of the band goes to [j]
@@ -329,7 +343,14 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 				continue;
 			}
 			uint32_t z0 = 0;   // s + 2(q+e)
-			if (sca) { // scores :215-228: lanes of this word inside the 16-wide blocks get fresh values, the others keep stale s
+			if (UNB) { // every lane of an in-band word gets a fresh score; lanes outside the band are never read
+				if (core) {
+					const uint32_t sq = SF[wm];
+					const uint32_t sq2 = __funnelshift_r(QRr[wi], QRr[wi + 1], qsh);
+					z0 = sel4(msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu), MISQ, MATQ);
+					if (wild) z0 = ksw_wild_score(sq, sq2, z0, QE2);
+				}
+			} else if (sca) { // scores :215-228: lanes of this word inside the 16-wide blocks get fresh values, the others keep stale s
 				const uint32_t sq = SF[wm];
 				const uint32_t sq2 = __funnelshift_r(QRr[wi], QRr[wi + 1], qsh);
 				const uint32_t neq = msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu); // 0xff where the codes differ
@@ -346,7 +367,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 				S[wm] = z0;
 			} else if (core) z0 = S[wm];
 			if (core) {
-				if (j == 0 && !keep_prev) { prv.x = 0u; prv.y = v1c; }
+				if (UNB ? wi == 0 : (j == 0 && !keep_prev)) { prv.x = 0u; prv.y = v1c; } // UNB: the ring holds lane 4 wi - 1 of the previous diagonal whenever wi > 0
 				const uint32_t ut = own.z, yt = own.w; // :212 (y[r] = 0, u[r] = q) was applied to the ring at the end of the previous diagonal
 				const uint32_t xt1 = __funnelshift_l(prv.x, own.x, 8), vt1 = __funnelshift_l(prv.y, own.y, 8); // lanes t-1..t+2 of the previous diagonal
 				uint32_t d, un, vn, xn, yn;
@@ -413,16 +434,18 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 		// band of the next diagonal (:196-199): its new 16-lane block, if any, and its :212 patch are applied now, so that
 		// one barrier covers them together with this diagonal's H[en0]
 		int st0n, en0n;
-		ksw_band(r + 1, qlen, tlen, w, st0n, en0n);
+		ksw_band(r + 1, qlen, tlen, w, st0n, en0n, UNB);
 		const bool nxt = act && r + 1 < nr && st0n <= en0n;
 		if (act) {
-			if (en0 == tlen - 1) {
-				if (hen > out.mte) { out.mte = hen; out.mte_q = r - en; }
-				if (r == qlen + tlen - 2) out.score = hen; // H[tlen-1]
-			}
-			if (r - st0 == qlen - 1) {
-				const int Hst0 = st0 == en0 ? hen : (int)G16[(st0 + rotc) & rm] - goff;
-				if (Hst0 > out.mqe) { out.mqe = Hst0; out.mqe_t = st0; }
+			if (EZ_FULL) {
+				if (en0 == tlen - 1) {
+					if (hen > out.mte) { out.mte = hen; out.mte_q = r - en; }
+					if (r == qlen + tlen - 2) out.score = hen; // H[tlen-1]
+				}
+				if (r - st0 == qlen - 1) {
+					const int Hst0 = st0 == en0 ? hen : (int)G16[(st0 + rotc) & rm] - goff;
+					if (Hst0 > out.mqe) { out.mqe = Hst0; out.mqe_t = st0; }
+				}
 			}
 			if (gl == 0) G16[(en0 + rotc) & rm] = (uint16_t)ghen;
 		}
@@ -434,7 +457,8 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 			else { // ... and the next 16 target codes are fetched
 				const int wn = ((b + 16) >> 2) + gl - 4;
 				const uint32_t tw = ksw_target_word(target, tlen, wn << 2);
-				S[(wn + rotw) & rmw] = QE2; SF[(wn + rotw) & rmw] = tw; w4 = ksw_has4(tw);
+				if (!UNB) S[(wn + rotw) & rmw] = QE2;
+				SF[(wn + rotw) & rmw] = tw; w4 = ksw_has4(tw);
 			}
 			en_clr += 16;
 		}
@@ -479,8 +503,8 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 				const int rr = r0 - row;
 				if (rr >= 0) {
 					int s0, e0;
-					ksw_band(rr, qlen, tlen, w, s0, e0);
-					long long x0 = (long long)rr * pitch + (i0 - 31 - (s0 & ~15)); // byte offset of column i0-31 of row rr
+					ksw_band(rr, qlen, tlen, w, s0, e0, UNB);
+					long long x0 = (long long)rr * pitch + (i0 - 31 - (UNB ? (s0 & ~3) : (s0 & ~15))); // byte offset of column i0-31 of row rr
 					// a row that holds a readable entry has x0 within 31 bytes of the matrix; anything further out is never read
 					// (the walk is forced there), so clamping keeps the prefetch inside this alignment's workspace
 					const long long x_hi = (long long)(qlen + tlen - 1) * pitch + KSW_PMAT_PAD - 40;
@@ -502,7 +526,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 				while (i >= 0 && j >= 0 && i + j > r0 - 32) {
 					const int r = i + j;
 					int s0, e0;
-					ksw_band(r, qlen, tlen, w, s0, e0);
+					ksw_band(r, qlen, tlen, w, s0, e0, UNB);
 					const int off = s0 & ~15, off_end = e0 | 15;
 					int force_state = -1;
 					if (i < off) force_state = 2;

@@ -178,7 +178,8 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	}
 	// opt in to large dynamic shared memory for the DP kernels
 	cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-	cudaFuncSetAttribute(al_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(al_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(al_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	cudaFuncSetAttribute(assemble_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	cudaFuncSetAttribute(assemble_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	*out = ctx;
@@ -386,7 +387,8 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 		al_prep_kernel<<<ctx->n_sm * 8, 256, 0, L.stream>>>(g);
 		sort_scan_kernel<<<1, 1024, 0, L.stream>>>(sB);
 		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(sB, &a.cnt->n_al_items, 2u, 2 * L.cap_items);
-		al_kernel<<<dp_grid(ctx, (const void*)al_kernel, smem), DP_THREADS, smem, L.stream>>>(g);
+		if (P.b_bw < 0) al_kernel<true><<<dp_grid(ctx, (const void*)al_kernel<true>, smem), DP_THREADS, smem, L.stream>>>(g); // unbanded (the reference's setting)
+		else al_kernel<false><<<dp_grid(ctx, (const void*)al_kernel<false>, smem), DP_THREADS, smem, L.stream>>>(g);
 		al_vote_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(g);
 		CK(cudaGetLastError()); L.launches += 5;
 	} else CK(cudaEventRecord(L.ev[EV_KMER], L.stream));
@@ -543,6 +545,7 @@ struct KswBatchArgs {
 	uint8_t *pmat; size_t p_cap; uint32_t *cig_scratch; int cig_cap; int ring_cols, seq_cap;
 };
 
+template <bool UNB>
 __global__ void __launch_bounds__(DP_THREADS, 3) ksw2_batch_kernel(KswBatchArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(DP_THREADS, 3) ksw2_batch_kernel(KswBatchArgs 
 		const int qlen = valid ? (int)(a.q_off[i + 1] - a.q_off[i]) : 0, tlen = valid ? (int)(a.t_off[i + 1] - a.t_off[i]) : 0;
 		KswQuery kq; kq.codes = a.query + (valid ? a.q_off[i] : 0); kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
 		KswOut o;
-		ksw2_group<DP_G>(valid, qlen, kq, tlen, a.target + (valid ? a.t_off[i] : 0), a.kp, M, o);
+		ksw2_group<DP_G, true, UNB>(valid, qlen, kq, tlen, a.target + (valid ? a.t_off[i] : 0), a.kp, M, o);
 		if (valid) {
 			const unsigned gmask = ((1u << DP_G) - 1u) << (lane & ~(DP_G - 1));
 			unsigned coff = 0;
@@ -608,9 +611,10 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 	a.seq_cap = (int)round_up(ksw_seq_bytes(max_q, max_t), 16);
 	const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(a.ring_cols, a.seq_cap);
 	if (smem > 200 * 1024) return IDL_E_CAPACITY;
-	cudaFuncSetAttribute(ksw2_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	const void *kfn = w < 0 ? (const void*)ksw2_batch_kernel<true> : (const void*)ksw2_batch_kernel<false>; // unbanded: the lean variant of kernel 2
+	cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	const size_t per_cta = (size_t)DP_WARPS * DP_NG;
-	const int ctas = (int)std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)dp_grid(ctx, (const void*)ksw2_batch_kernel, smem));
+	const int ctas = (int)std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)dp_grid(ctx, kfn, smem));
 	const size_t nwarps = (size_t)ctas * per_cta; // groups, each with its own workspace
 	const size_t qbytes = q_off[n], tbytes = t_off[n];
 	DevBuf dq, dt, dqo, dto, dout, dcig, dcoff, dmisc, dp, dscr;
@@ -629,7 +633,8 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 		a.next = (unsigned*)dmisc.p; a.cig_used = (unsigned*)dmisc.p + 1; a.pmat = (uint8_t*)dp.p; a.cig_scratch = (uint32_t*)dscr.p;
 		CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 		CK(cudaEventRecord(e0, st));
-		ksw2_batch_kernel<<<ctas, DP_THREADS, smem, st>>>(a);
+		if (w < 0) ksw2_batch_kernel<true><<<ctas, DP_THREADS, smem, st>>>(a);
+		else ksw2_batch_kernel<false><<<ctas, DP_THREADS, smem, st>>>(a);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(e1, st));
 		CK(cudaMemcpyAsync(out, dout.p, n * sizeof(idl_ez), cudaMemcpyDeviceToHost, st));

@@ -183,3 +183,35 @@ def test_directed_gates_and_odd_reads():
     assert pre == [20, 21], pre   # the two regions straddle the n_contigs > 20 gate
     assert sum(l.startswith("A\t0\t") for l in odump.splitlines()) >= 1 and not any(l.startswith("A\t1\t") for l in odump.splitlines())
     assert_same(dump, vcf, odump, ovcf)
+
+
+def test_block_screen_edges_short_reads_and_periodic_sequence():
+    """the assembler's 32-offset block screen (16 leading bases, position parallel): reads around the min_overlap 16/17
+    switch (18-24 bp reads take the per-offset path, longer ones the blocks), and homopolymer / dinucleotide / 7-mer
+    repeats where dozens of offsets of one block survive the screen and run the full compare"""
+    rng = np.random.default_rng(2024)
+    units, rep_lens = ["A", "CA", "GATTACA", "T", "ACG", "AAAC"], [40, 90, 140, 260, 64, 33]
+    segs, haps, seg_start, at = [], [], [], 0
+    for unit, rl in zip(units, rep_lens):
+        left, right = _random_seq(rng, 1500), _random_seq(rng, 1500)
+        rep = (unit * 300)[:rl]
+        segs.append(left + rep + right)
+        haps.append(left + rep[:len(rep) - len(unit) * 3] + right)      # contraction by three units
+        seg_start.append(at); at += len(segs[-1])
+    ref = "".join(segs)
+    sets = []
+    for k in range(6):
+        base = 1500 - 170
+        reads = []
+        for i in range(0, 330, 3):
+            src = haps[k] if (i // 3) % 2 else segs[k]
+            L = [150, 150, 18, 150, 19, 20, 150, 21, 24, 150, 40, 150, 64, 150][(i // 3) % 14]
+            reads.append(dict(start=seg_start[k] + base + i, seq=src[base + i:base + i + L], mapq=60))
+        reads.sort(key=lambda r: r["start"])
+        _, arrays = util.rois_from_reads(reads, ref, roi_start=seg_start[k] + 1500, roi_stop=seg_start[k] + 1500 + rep_lens[k])
+        sets.append(arrays)
+    arrays = util.merge_rois(sets)
+    rois = host.Rois(arrays=arrays)
+    dump, vcf, odump, ovcf, cnt, _ = run_both(rois, arrays, min_reads=3, min_event_len=3, tag="blocks")
+    assert cnt["regions"] == 6 and cnt["offsets"] > 10000
+    assert_same(dump, vcf, odump, ovcf)

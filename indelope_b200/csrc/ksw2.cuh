@@ -319,6 +319,39 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 			const bool core = mine && wi <= wend, sca = mine && wi >= ws0 && wi <= w1;
 			const uint4 own = XV[wm]; uint2 prv = *(const uint2*)&XV[(wm - 1) & rmw];
 			__syncwarp(); // every load of the round is issued before any store of the round
+			if (UNB) {
+				// one path for every in-band word: fresh scores, the core, the backtrack word; only the exact-score update
+				// looks at the band edges (the word that holds st0 and the one that holds en0)
+				if (mine && wi <= wend) {
+					const uint32_t sq = SF[wm];
+					const uint32_t sq2 = __funnelshift_r(QRr[wi], QRr[wi + 1], qsh);
+					uint32_t z0 = sel4(msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu), MISQ, MATQ);
+					if (wild) z0 = ksw_wild_score(sq, sq2, z0, QE2);
+					if (wi == 0) { prv.x = 0u; prv.y = v1c; } // :207-211 with st == 0; for wi > 0 the ring holds lane 4 wi - 1 of the previous diagonal
+					const uint32_t xt1 = __funnelshift_l(prv.x, own.x, 8), vt1 = __funnelshift_l(prv.y, own.y, 8);
+					uint32_t d, un, vn, xn, yn;
+					ksw_core_word(P, fast_ok, z0, xt1, vt1, own.z, own.w, xn, vn, un, yn, d);
+					XV[wm] = make_uint4(xn, vn, un, yn);
+					prg[rd * G] = d;
+					const int lo = st0 - t, hi = en0 - t; // exact scores of the in-band columns st0 .. en0-1 of this word (:323-348): g[t] += v8[t]
+					if (lo <= 0 && hi >= 4) {
+						uint2 g2 = GR[wm];
+						g2.x += __byte_perm(vn, 0u, 0x4140); g2.y += __byte_perm(vn, 0u, 0x4342);
+						bh2 = __vimax3_u16x2(bh2, g2.x, g2.y);
+						GR[wm] = g2;
+					} else if (hi > 0 && lo < 4) {
+						uint2 g2 = GR[wm];
+						uint32_t m = 0xffffffffu;
+						if (lo > 0) m <<= 8 * lo;
+						if (hi < 4) m &= 0xffffffffu >> (8 * (4 - hi));
+						const uint32_t vm = vn & m;
+						g2.x += __byte_perm(vm, 0u, 0x4140); g2.y += __byte_perm(vm, 0u, 0x4342);
+						bh2 = __vimax3_u16x2(bh2, g2.x & __byte_perm(m, 0u, 0x1100), g2.y & __byte_perm(m, 0u, 0x3322));
+						GR[wm] = g2;
+					}
+				}
+				continue;
+			}
 			if (rd > 0 && __all_sync(FULL_MASK, !mine || t + 4 <= en0)) {
 				// every word of this round, in all four alignments, lies inside the exact band (rd > 0 puts it at least 32 lanes
 				// right of st, so right of st0 too): fresh scores for all four lanes, no boundary lane, no masks.  A group that
@@ -343,14 +376,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 				continue;
 			}
 			uint32_t z0 = 0;   // s + 2(q+e)
-			if (UNB) { // every lane of an in-band word gets a fresh score; lanes outside the band are never read
-				if (core) {
-					const uint32_t sq = SF[wm];
-					const uint32_t sq2 = __funnelshift_r(QRr[wi], QRr[wi + 1], qsh);
-					z0 = sel4(msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu), MISQ, MATQ);
-					if (wild) z0 = ksw_wild_score(sq, sq2, z0, QE2);
-				}
-			} else if (sca) { // scores :215-228: lanes of this word inside the 16-wide blocks get fresh values, the others keep stale s
+			if (sca) { // scores :215-228: lanes of this word inside the 16-wide blocks get fresh values, the others keep stale s
 				const uint32_t sq = SF[wm];
 				const uint32_t sq2 = __funnelshift_r(QRr[wi], QRr[wi + 1], qsh);
 				const uint32_t neq = msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu); // 0xff where the codes differ
@@ -367,7 +393,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 				S[wm] = z0;
 			} else if (core) z0 = S[wm];
 			if (core) {
-				if (UNB ? wi == 0 : (j == 0 && !keep_prev)) { prv.x = 0u; prv.y = v1c; } // UNB: the ring holds lane 4 wi - 1 of the previous diagonal whenever wi > 0
+				if (j == 0 && !keep_prev) { prv.x = 0u; prv.y = v1c; }
 				const uint32_t ut = own.z, yt = own.w; // :212 (y[r] = 0, u[r] = q) was applied to the ring at the end of the previous diagonal
 				const uint32_t xt1 = __funnelshift_l(prv.x, own.x, 8), vt1 = __funnelshift_l(prv.y, own.y, 8); // lanes t-1..t+2 of the previous diagonal
 				uint32_t d, un, vn, xn, yn;

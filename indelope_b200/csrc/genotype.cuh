@@ -246,75 +246,116 @@ __global__ void __launch_bounds__(DP_THREADS, 3) align_kernel(GenoArgs g)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// kernel 3: k-mer counting, one CTA per event
+// kernel 3: k-mer counting (src/indelope.nim:283-311), one WARP per event, the lanes over the windows of one read
+//
+// A window matches the event's ref (alt) k-mer when its canonical code equals the k-mer's (kmer.mincode / kmer.dists,
+// SURVEY appendix D), i.e. when it spells the k-mer or its reverse complement.  The reads are 2-bit packed with base i at
+// bits 2i, so the K bases at position p are a 54-bit field of three 32-bit words; with F the event's canonical code
+// (first base in the top bits), that field equals  ~F & mask  when the window spells the reverse complement of F's string
+// and  pair-reverse(F)  when it spells the string itself.  So a window costs two funnel shifts and four 64-bit compares --
+// no rolling state, every window independent.  The first hit per read (:302-309) is the minimum position, found with one
+// sub-warp reduction per read; MAPQ medians (:152-155,408-411) come from per-warp histograms.
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t kmer_pair_reverse(uint64_t x, int K) // reverse the order of the K 2-bit groups
+{
+	uint64_t r = __brevll(x);
+	r = ((r & 0x5555555555555555ULL) << 1) | ((r >> 1) & 0x5555555555555555ULL);
+	return r >> (64 - 2 * K);
+}
+
+// first bin where the running count exceeds nn / 2 (median(): sorted[int(len/2)]), all lanes cooperate; -1 for an empty list
+__device__ __forceinline__ int kmer_median(const unsigned *h, unsigned nn, int lane)
+{
+	if (nn == 0) return -1;
+	unsigned mine = 0;
+#pragma unroll
+	for (int q = 0; q < 8; ++q) mine += h[lane * 8 + q];
+	unsigned inc = mine;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(FULL_MASK, inc, d); if (lane >= d) inc += o; }
+	const unsigned target = nn / 2;
+	const unsigned owner = __ffs(__ballot_sync(FULL_MASK, inc > target)) - 1; // first lane whose bins cross the target
+	int med = 0;
+	if ((unsigned)lane == owner) {
+		unsigned acc = inc - mine;
+		for (int q = 0; q < 8; ++q) { acc += h[lane * 8 + q]; if (acc > target) { med = lane * 8 + q; break; } }
+	}
+	return __shfl_sync(FULL_MASK, med, owner);
+}
+
+// Four reads at a time per warp, eight lanes per read, sixteen consecutive windows per lane: a lane loads the three 32-bit
+// words (48 bases) and the 64 N-plane bits its windows span once and shifts the fields out of registers, so a read costs
+// one round trip for its record and one for its bases, with four reads in flight per warp.
 __global__ void __launch_bounds__(KMER_THREADS) kmer_kernel(GenoArgs g)
 {
-	__shared__ unsigned hist_a[256], hist_r[256];
-	__shared__ unsigned long long s_sum_a, s_sum_r, s_bytes;
-	__shared__ unsigned s_ka, s_kr, s_kb, s_reads;
-	const int tid = threadIdx.x;
+	__shared__ unsigned hist[KMER_THREADS / 32][2][256];
+	const int lane = lane_id(), warp = warp_id(), grp = lane >> 3, gl = lane & 7;
 	const idl_params &P = g.P;
 	const int K = IDL_KMER;
 	const uint64_t kmask = (1ULL << (2 * K)) - 1ULL;
 	const unsigned n_events = g.cnt->n_events < g.cap_events ? g.cnt->n_events : g.cap_events;
-	for (unsigned e = blockIdx.x; e < n_events; e += gridDim.x) {
+	unsigned *ha = hist[warp][0], *hr = hist[warp][1];
+	unsigned long long tot_reads = 0, tot_bytes = 0;
+	for (unsigned e = blockIdx.x * (KMER_THREADS / 32) + warp; e < n_events; e += gridDim.x * (KMER_THREADS / 32)) {
 		idl_event_result ev = g.eres[e];
-		if (ev.reject != IDL_EV_COUNTED) continue; // uniform
+		if (ev.reject != IDL_EV_COUNTED) continue; // warp-uniform
 		const idl_aln_result ar = g.ares[ev.aln];
 		const idl_region R = g.region[ar.region];
-		__syncthreads();
-		for (int i = tid; i < 256; i += KMER_THREADS) { hist_a[i] = 0; hist_r[i] = 0; }
-		if (tid == 0) { s_sum_a = s_sum_r = s_bytes = 0; s_ka = s_kr = s_kb = s_reads = 0; }
-		__syncthreads();
-		const uint64_t refe = ev.ref_code, alte = ev.alt_code;
-		for (unsigned j = tid; j < R.n_reads; j += KMER_THREADS) { // :293-311
-			const idl_read rd = g.read[R.read_begin + j];
-			if ((int)rd.mapq < P.count_min_mapq) continue; // :294
+		__syncwarp();
+		for (int i = lane; i < 256; i += 32) { ha[i] = 0; hr[i] = 0; }
+		__syncwarp();
+		// a code of ~0 (a k-mer with a non-ACGT base) matches nothing: its constants cannot equal a 54-bit field
+		const bool ref_ok = ev.ref_code != ~0ULL, alt_ok = ev.alt_code != ~0ULL;
+		const uint64_t r1 = ref_ok ? (~ev.ref_code & kmask) : ~0ULL, r2 = ref_ok ? kmer_pair_reverse(ev.ref_code, K) : ~0ULL;
+		const uint64_t a1 = alt_ok ? (~ev.alt_code & kmask) : ~0ULL, a2 = alt_ok ? kmer_pair_reverse(ev.alt_code, K) : ~0ULL;
+		unsigned k_ref = 0, k_alt = 0, k_both = 0, n_reads = 0, sum_r = 0, sum_a = 0, bytes = 0; // per group leader
+		for (unsigned j0 = 0; j0 < R.n_reads; j0 += 4) { // :293-311
+			const unsigned j = j0 + (unsigned)grp;
+			idl_read rd; rd.len = 0; rd.mapq = 0; rd.seq_off = 0;
+			if (j < R.n_reads) rd = g.read[R.read_begin + j];
+			const bool ok = j < R.n_reads && (int)rd.mapq >= P.count_min_mapq; // :294
 			const int L = rd.len;
-			bool rf = false, af = false; int rdist = 0, adist = 0;
-			const uint4 *p2 = (const uint4*)(g.seq2 + (rd.seq_off >> 4)); // 64 bases per 128-bit load, records are 16-byte aligned
-			const uint2 *pn = (const uint2*)(g.seqn + (rd.seq_off >> 5));
-			uint64_t f = 0, rc = 0; int valid = 0;
-			for (int blk = 0; blk * 64 < L && !(rf && af); ++blk) {
-				const uint4 w4 = __ldg(p2 + blk);
-				const uint2 n2 = __ldg(pn + blk);
-				const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
-				const uint64_t nmask = (uint64_t)n2.x | ((uint64_t)n2.y << 32);
-				const int lim = L - blk * 64 < 64 ? L - blk * 64 : 64;
-				for (int i = 0; i < lim; ++i) {
-					const unsigned b = (ws[i >> 4] >> (2 * (i & 15))) & 3u;
-					if ((nmask >> i) & 1ULL) { valid = 0; f = rc = 0; continue; } // a window holding a non-ACGT base never matches
-					f = ((f << 2) | b) & kmask;
-					rc = (rc >> 2) | ((uint64_t)(3u - b) << (2 * (K - 1)));
-					if (++valid < K) continue;
-					const uint64_t c = f < rc ? f : rc;
-					if (c == refe || c == alte) {
-						const int pos = blk * 64 + i - K + 1;
-						const int dd = pos < (L - K) - pos ? pos : (L - K) - pos; // declared kmer.dists distance
-						if (!rf && c == refe) { rf = true; rdist = dd; }
-						if (!af && c == alte) { af = true; adist = dd; }
+			const int rec2 = ((L + 63) >> 6) << 2, recn = ((L + 63) >> 6) << 1; // words of this read's records in the two pools
+			const uint32_t *w2 = g.seq2 + (rd.seq_off >> 4), *wn = g.seqn + (rd.seq_off >> 5);
+			int first_r = 0x7fffffff, first_a = 0x7fffffff;
+			if (ok)
+				for (int base = 0; base + K <= L; base += 128) {
+					const int p0 = base + 16 * gl;
+					if (p0 + K > L) continue;
+					const int w = p0 >> 4, nwd = p0 >> 5, nsh = p0 & 31;
+					const uint32_t x0 = __ldg(w2 + w), x1 = __ldg(w2 + w + 1), x2 = w + 2 < rec2 ? __ldg(w2 + w + 2) : 0u;
+					const uint32_t n0 = __ldg(wn + nwd), n1 = nwd + 1 < recn ? __ldg(wn + nwd + 1) : 0u;
+					const uint64_t nb = (((uint64_t)n1 << 32) | n0) >> nsh; // N flags of bases p0 .. p0+41 (nsh is 0 or 16)
+#pragma unroll
+					for (int i = 0; i < 16; ++i) {
+						const int p = p0 + i;
+						if (p + K > L) break;
+						if ((unsigned)(nb >> i) & ((1u << K) - 1u)) continue; // a window holding a non-ACGT base never matches
+						const uint64_t c = (((uint64_t)__funnelshift_r(x1, x2, 2 * i) << 32) | __funnelshift_r(x0, x1, 2 * i)) & kmask;
+						if (c == r1 || c == r2) first_r = min(first_r, p);
+						if (c == a1 || c == a2) first_a = min(first_a, p);
 					}
 				}
+#pragma unroll
+			for (int d = 1; d < 8; d <<= 1) { first_r = min(first_r, __shfl_xor_sync(FULL_MASK, first_r, d)); first_a = min(first_a, __shfl_xor_sync(FULL_MASK, first_a, d)); }
+			if (ok && gl == 0) {
+				const bool rf = first_r != 0x7fffffff, af = first_a != 0x7fffffff;
+				n_reads += 1; bytes += (unsigned)((L + 3) / 4 + (L + 7) / 8 + 16);
+				if (rf) { k_ref += 1; sum_r += (unsigned)(first_r < (L - K) - first_r ? first_r : (L - K) - first_r); atomicAdd(&hr[rd.mapq], 1u); } // declared kmer.dists distance
+				if (af) { k_alt += 1; sum_a += (unsigned)(first_a < (L - K) - first_a ? first_a : (L - K) - first_a); atomicAdd(&ha[rd.mapq], 1u); }
+				if (rf && af) k_both += 1;
 			}
-			atomicAdd(&s_reads, 1u);
-			atomicAdd(&s_bytes, (unsigned long long)((L + 3) / 4 + (L + 7) / 8 + 16));
-			if (rf) { atomicAdd(&s_kr, 1u); atomicAdd(&s_sum_r, (unsigned long long)rdist); atomicAdd(&hist_r[rd.mapq], 1u); }
-			if (af) { atomicAdd(&s_ka, 1u); atomicAdd(&s_sum_a, (unsigned long long)adist); atomicAdd(&hist_a[rd.mapq], 1u); }
-			if (rf && af) atomicAdd(&s_kb, 1u);
 		}
-		__syncthreads();
-		if (tid == 0) {
-			ev.k_ref = (int)s_kr; ev.k_alt = (int)s_ka; ev.k_both = (int)s_kb;
-			ev.n_adist = (int)s_ka; ev.n_rdist = (int)s_kr; ev.sum_adist = (long long)s_sum_a; ev.sum_rdist = (long long)s_sum_r;
-			// median(): sorted[int(len/2)], src/indelope.nim:152-155
-			for (int which = 0; which < 2; ++which) {
-				const unsigned *h = which ? hist_r : hist_a; const unsigned nn = which ? s_kr : s_ka;
-				int med = -1;
-				if (nn) { unsigned acc = 0; const unsigned target = nn / 2; for (int q = 0; q < 256; ++q) { acc += h[q]; if (acc > target) { med = q; break; } } }
-				if (which) ev.rmq_median = med; else ev.amq_median = med;
-			}
-			if (s_kb > 0) { // :313: genotype by alignment instead
+		k_ref = __reduce_add_sync(FULL_MASK, k_ref); k_alt = __reduce_add_sync(FULL_MASK, k_alt); k_both = __reduce_add_sync(FULL_MASK, k_both);
+		sum_r = __reduce_add_sync(FULL_MASK, sum_r); sum_a = __reduce_add_sync(FULL_MASK, sum_a);
+		n_reads = __reduce_add_sync(FULL_MASK, n_reads); bytes = __reduce_add_sync(FULL_MASK, bytes);
+		__syncwarp();
+		const int med_a = kmer_median(ha, k_alt, lane), med_r = kmer_median(hr, k_ref, lane);
+		if (lane == 0) {
+			ev.k_ref = (int)k_ref; ev.k_alt = (int)k_alt; ev.k_both = (int)k_both;
+			ev.n_adist = (int)k_alt; ev.n_rdist = (int)k_ref; ev.sum_adist = (long long)sum_a; ev.sum_rdist = (long long)sum_r;
+			ev.amq_median = med_a; ev.rmq_median = med_r;
+			if (k_both > 0) { // :313: genotype by alignment instead
 				ev.aligned = 1; ev.ref_support = ev.alt_support = ev.both_found = 0;
 				const unsigned long long old = atomicAdd(&g.cnt->al_pack, (1ULL << 40) | (unsigned long long)R.n_reads);
 				const unsigned slot = (unsigned)(old >> 40);
@@ -323,10 +364,10 @@ __global__ void __launch_bounds__(KMER_THREADS) kmer_kernel(GenoArgs g)
 				atomicAdd(&g.cnt->al_events, 1ULL);
 			} else { ev.aligned = 0; ev.ref_support = ev.k_ref; ev.alt_support = ev.k_alt; ev.both_found = 0; }
 			g.eres[e] = ev;
-			atomicAdd(&g.cnt->kmer_reads, (unsigned long long)s_reads);
-			atomicAdd(&g.cnt->kmer_bytes, s_bytes + 64ULL);
 		}
+		tot_reads += n_reads; tot_bytes += (unsigned long long)bytes + 64ULL;
 	}
+	if (lane == 0 && tot_bytes) { atomicAdd(&g.cnt->kmer_reads, tot_reads); atomicAdd(&g.cnt->kmer_bytes, tot_bytes); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio smsp__a
 smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio
 smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio
 smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio
+sm__icc_request_hit_rate.pct gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed l1tex__t_sector_hit_rate.pct
 sm__sass_inst_executed_op_shared_ld.sum sm__sass_inst_executed_op_shared_st.sum sm__sass_inst_executed_op_global_ld.sum sm__sass_inst_executed_op_global_st.sum""".split()
 
 

@@ -44,18 +44,18 @@ inline KswParams ksw_make_params(int match, int mismatch, int q, int e, int w, i
 	return p;
 }
 
-#define SORT_BUCKETS 65536
+#define SORT_BUCKETS 16384
 // bucket sort of alignment tasks, longest first: hist/start/cursor hold SORT_BUCKETS entries.  Kernel 2 runs the four
 // alignments of a warp in lockstep and takes its cheap interior path only when the words of all four lie inside their
 // bands, so the key carries the whole SHAPE of the task: call-site A (banded: the band depends on the diagonal alone
 // until the sequences end) sorts by the exact number of anti-diagonals, call-site B (unbanded: the band is
 // [r - qlen + 1, min(r, tlen - 1)]) by anti-diagonals and query length, so neighbours have the same (qlen, tlen).
 struct SortBufs { unsigned *hist, *start, *cursor; uint16_t *keys; unsigned *order; };
-__device__ __forceinline__ uint16_t sort_key_a(int diagonals) { return (uint16_t)(diagonals > 65535 ? 65535 : (diagonals < 0 ? 0 : diagonals)); }
+__device__ __forceinline__ uint16_t sort_key_a(int diagonals) { return (uint16_t)(diagonals > SORT_BUCKETS - 1 ? SORT_BUCKETS - 1 : (diagonals < 0 ? 0 : diagonals)); }
 __device__ __forceinline__ uint16_t sort_key_b(int diagonals, int qlen)
 {
-	const int d = diagonals > 2047 ? 2047 : (diagonals < 0 ? 0 : diagonals);
-	return (uint16_t)((d << 5) | (qlen & 31));
+	const int d = diagonals > 1023 ? 1023 : (diagonals < 0 ? 0 : diagonals);
+	return (uint16_t)((d << 4) | (qlen & 15));
 }
 // executed anti-diagonals of one extension alignment are bounded by the band running out (ksw2_extz2_sse.c:196-203)
 __device__ __forceinline__ int est_diagonals(int qlen, int tlen, int w)

@@ -41,27 +41,35 @@ struct GenoArgs {
 	uint8_t *seq_spill; int seq_spill_cap;  // global-memory sequence staging for alignments that do not fit seq_cap
 };
 
-// exclusive scan of the bucket histogram, longest bucket first (one CTA of 1024 threads, 64 buckets per thread)
-__global__ void sort_scan_kernel(SortBufs s)
+// exclusive scan of the bucket histogram, longest bucket first: one CTA of 1024 threads walks the histogram in 64 coalesced
+// chunks of 1024 buckets (all loads issued up front), a shuffle scan per chunk
+__global__ void __launch_bounds__(1024) sort_scan_kernel(SortBufs s)
 {
-	__shared__ unsigned part[1024];
-	constexpr int PER = SORT_BUCKETS / 1024;
-	const int i = threadIdx.x;
-	unsigned sum = 0;
-	for (int k = 0; k < PER; ++k) sum += s.hist[SORT_BUCKETS - 1 - (i * PER + k)];
-	part[i] = sum;
-	__syncthreads();
-	for (int d = 1; d < 1024; d <<= 1) { // inclusive Hillis-Steele scan of the per-thread sums
-		const unsigned v = i >= d ? part[i - d] : 0u;
+	__shared__ unsigned wsum[32];
+	constexpr int CH = SORT_BUCKETS / 1024;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	unsigned v[CH];
+#pragma unroll
+	for (int c = 0; c < CH; ++c) v[c] = s.hist[SORT_BUCKETS - 1 - (c * 1024 + tid)];
+	unsigned carry = 0;
+#pragma unroll 1
+	for (int c = 0; c < CH; ++c) {
+		unsigned x = 0;
+#pragma unroll
+		for (int k = 0; k < CH; ++k) if (k == c) x = v[k]; // register array, constant indices only
+		unsigned inc = x;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(FULL_MASK, inc, d); if (lane >= d) inc += o; }
+		if (lane == 31) wsum[warp] = inc;
 		__syncthreads();
-		part[i] += v;
+		unsigned ws = wsum[lane], wi = ws;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(FULL_MASK, wi, d); if (lane >= d) wi += o; }
+		const unsigned before = __shfl_sync(FULL_MASK, wi - ws, warp), total = __shfl_sync(FULL_MASK, wi, 31);
+		const int b = SORT_BUCKETS - 1 - (c * 1024 + tid);
+		s.start[b] = carry + before + inc - x; s.cursor[b] = 0;
+		carry += total;
 		__syncthreads();
-	}
-	unsigned acc = part[i] - sum;
-	for (int k = 0; k < PER; ++k) {
-		const int b = SORT_BUCKETS - 1 - (i * PER + k);
-		const unsigned c = s.hist[b];
-		s.start[b] = acc; s.cursor[b] = 0; acc += c;
 	}
 }
 __global__ void sort_scatter_kernel(SortBufs s, const unsigned *n_ptr, unsigned mul, unsigned cap)

@@ -25,6 +25,18 @@ struct KswOut {
 	long long cells;  // exact in-band cells over executed diagonals
 };
 
+#ifndef KSW_PSTORE_MODE
+#define KSW_PSTORE_MODE 1 /* streaming stores: the backtrack matrix is written once and read back once, in part */
+#endif
+#if KSW_PSTORE_MODE == 1
+#define KSW_PSTORE(p, v) __stcs((p), (v))
+#elif KSW_PSTORE_MODE == 2
+#define KSW_PSTORE(p, v) __stwt((p), (v))
+#elif KSW_PSTORE_MODE == 3
+#define KSW_PSTORE(p, v) __stcg((p), (v))
+#else
+#define KSW_PSTORE(p, v) (*(p) = (v))
+#endif
 #define KSW_BTILE_BYTES 1024
 #define KSW_QR_PAD 32     /* zero bytes in front of the reversed query: lanes left of the exact band index it below 0 */
 #define KSW_PMAT_PAD 64   /* bytes in front of every backtrack matrix (the tile prefetch may start before row 0) */
@@ -332,7 +344,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 					uint32_t d, un, vn, xn, yn;
 					ksw_core_word(P, fast_ok, z0, xt1, vt1, own.z, own.w, xn, vn, un, yn, d);
 					XV[wm] = make_uint4(xn, vn, un, yn);
-					prg[rd * G] = d;
+					KSW_PSTORE(prg + rd * G, d);
 					const int lo = st0 - t, hi = en0 - t; // exact scores of the in-band columns st0 .. en0-1 of this word (:323-348): g[t] += v8[t]
 					if (lo <= 0 && hi >= 4) {
 						uint2 g2 = GR[wm];
@@ -367,7 +379,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 					uint32_t d, un, vn, xn, yn;
 					ksw_core_word(P, fast_ok, z0, xt1, vt1, own.z, own.w, xn, vn, un, yn, d);
 					XV[wm] = make_uint4(xn, vn, un, yn);
-					prg[rd * G] = d;
+					KSW_PSTORE(prg + rd * G, d);
 					uint2 g2 = GR[wm];
 					g2.x += __byte_perm(vn, 0u, 0x4140); g2.y += __byte_perm(vn, 0u, 0x4342);
 					bh2 = __vimax3_u16x2(bh2, g2.x, g2.y);
@@ -399,7 +411,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 				uint32_t d, un, vn, xn, yn;
 				ksw_core_word(P, fast_ok, z0, xt1, vt1, ut, yt, xn, vn, un, yn, d);
 				XV[wm] = make_uint4(xn, vn, un, yn);
-				prg[rd * G] = d;
+				KSW_PSTORE(prg + rd * G, d);
 				const int lo = st0 - t, hi = en0 - t; // exact scores of the in-band columns st0 .. en0-1 of this word (:323-348): g[t] += v8[t]
 				if (hi > 0 && lo < 4) {
 					uint2 g2 = GR[wm];
@@ -537,13 +549,14 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 					x0 = x0 < -(long long)(KSW_PMAT_PAD - 4) ? -(long long)(KSW_PMAT_PAD - 4) : (x0 > x_hi ? x_hi : x0);
 					const uint32_t *src = (const uint32_t*)(pmat + (x0 & ~3LL));
 					const int sh = 8 * (int)(x0 & 3);
-					uint32_t wprev = src[0];
+					// row r0 - row can only be entered at columns i0 - row .. i0: fetch those bytes only (the left part of the
+					// tile row stays stale and is never read), which keeps most rows inside one DRAM sector
+					const int k0 = (31 - row) >> 2;
+					uint32_t wv[9];
 #pragma unroll
-					for (int k = 0; k < 8; ++k) {
-						const uint32_t wnext = src[k + 1];
-						tile[row * 8 + k] = __funnelshift_r(wprev, wnext, sh);
-						wprev = wnext;
-					}
+					for (int k = 0; k < 9; ++k) wv[k] = k >= k0 ? src[k] : 0u; // predicated loads, all in flight together
+#pragma unroll
+					for (int k = 0; k < 8; ++k) if (k >= k0) tile[row * 8 + k] = __funnelshift_r(wv[k], wv[k + 1], sh);
 				}
 			}
 			__syncwarp(gmask);

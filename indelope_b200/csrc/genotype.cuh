@@ -12,6 +12,7 @@
 #pragma once
 #include "common.cuh"
 #include "ksw2.cuh"
+#include "ksw2_rows.cuh"
 
 #define DP_WARPS 8
 #define DP_THREADS (DP_WARPS * 32)
@@ -88,7 +89,7 @@ __device__ __forceinline__ KswMem dp_mem(const GenoArgs &g, unsigned char *smem,
 	const size_t per = ksw_group_smem(g.ring_cols, g.seq_cap);
 	const size_t gg = (size_t)blockIdx.x * (DP_WARPS * DP_NG) + grp;
 	KswMem m;
-	ksw_group_mem(m, smem + per * grp, lane_id() / DP_G, g.ring_cols);
+	ksw_group_mem(m, smem + per * grp, lane_id() / DP_G, g.ring_cols); m.region_bytes = (int)per;
 	if (ksw_seq_bytes(qlen, tlen) <= (size_t)g.seq_cap) m.seq_cap = g.seq_cap;
 	else { m.seq = g.seq_spill + gg * (size_t)g.seq_spill_cap; m.seq_cap = g.seq_spill_cap; }
 	m.pmat = g.pmat + gg * g.p_cap; m.p_cap = g.p_cap;
@@ -467,7 +468,13 @@ __global__ void __launch_bounds__(DP_THREADS, 3) al_kernel(GenoArgs g)
 		}
 		const KswMem M = dp_mem(g, smem_raw, qlen, tlen);
 		KswOut o;
-		ksw2_group<DP_G, false, UNB>(valid, qlen, kq, tlen, t, g.kpB, M, o); // the whole warp: four alignments in lockstep
+		// the whole warp: four alignments in lockstep; reads of up to 256 bases take the row-owned variant (ksw2_rows.cuh)
+		const int rw = UNB ? ksw_rows_pick(valid, qlen, tlen, g.kpB, M) : 0;
+		if (rw == 5) ksw2_rows<5, false>(valid, qlen, kq, tlen, t, g.kpB, M, o);
+#ifndef KSW_ROWS_NO8
+		else if (rw == 8) ksw2_rows<8, false>(valid, qlen, kq, tlen, t, g.kpB, M, o);
+#endif
+		else ksw2_group<DP_G, false, UNB>(valid, qlen, kq, tlen, t, g.kpB, M, o);
 		if (valid) {
 			if (gl == 0) {
 				const unsigned st = dp_status_bits(o.status);

@@ -125,7 +125,8 @@ __device__ __forceinline__ uint8_t ksw_query_code(const KswQuery &q, int i)
 // the 64-bit accesses to g pair two groups and the 32-bit accesses to S and T put all four groups of a warp into one
 // wavefront: group k of the warp rotates its rings by 8k words, so that groups at the same relative column fall into
 // different banks without any slack bytes.
-struct KswMem { uint4 *xvuy; uint2 *g; uint32_t *S, *T; int ring_cols, rot; uint8_t *seq; int seq_cap; uint8_t *pmat; size_t p_cap; uint32_t *cig; int cig_cap; };
+struct KswMem { uint4 *xvuy; uint2 *g; uint32_t *S, *T; int ring_cols, rot; uint8_t *seq; int seq_cap; uint8_t *pmat; size_t p_cap; uint32_t *cig; int cig_cap;
+                int region_bytes; /* shared-memory bytes of the group's region (ksw2_rows.cuh stages its target there) */ };
 // layout of a group's region (a multiple of 128 bytes): [xvuy 4R][g 2R][S R][T R][seq]
 __host__ __device__ inline size_t ksw_group_seq_off(int ring_cols) { return (size_t)8 * ring_cols; }
 __host__ __device__ inline size_t ksw_group_smem(int ring_cols, int seq_cap)
@@ -141,6 +142,7 @@ __device__ __forceinline__ void ksw_group_mem(KswMem &m, unsigned char *base, in
 	m.S = (uint32_t*)(base + (size_t)6 * ring_cols);
 	m.T = (uint32_t*)(base + (size_t)7 * ring_cols);
 	m.seq = base + ksw_group_seq_off(ring_cols);
+	m.region_bytes = 0;
 }
 // four target codes starting at column t, zero beyond the end (:187)
 __device__ __forceinline__ uint32_t ksw_target_word(const uint8_t *target, int tlen, int t)

@@ -1,0 +1,316 @@
+// indelope_b200/csrc/ksw2_rows.cuh -- kernel 2, unbanded call-site (the AL fallback, src/indelope.nim:317-318,343-344:
+// w = -1, zdrop = -1) with the QUERY ROWS resident in registers.
+//
+// Same results as ksw_extz2_sse (src/ksw2/csrc/ksw2_extz2_sse.c:113-388, flag 0), bit for bit, for w < 0 and zdrop < 0.
+// The SSE code indexes u, v, x, y by target column t; on anti-diagonal r the cell (t, j = r - t) reads x, v of the cell
+// (t-1, j) -- same query row, previous diagonal -- and u, y of the cell (t, j-1) -- previous query row, previous diagonal.
+// Unbanded, a read of <= 32 W bases has few rows and every row is live for tlen consecutive diagonals, so here a
+// thread OWNS query rows: word w of the query (rows 4w .. 4w+3, one int8 lane each) belongs to thread w % 8 of the
+// group of eight, slot w / 8.  x, v never move; u, y shift up by one row per diagonal: one PRMT inside a word, one
+// shuffle between neighbouring threads.  Nothing of the recurrence touches shared memory: no ring, no addressing, no
+// load/store per word and diagonal (the column-owned variant in ksw2.cuh spends 116 instructions per word, 33 of them on
+// the recurrence; this one about 55).  The interleaved ownership keeps the eight threads busy on the ramps of the band:
+// on diagonal r the live rows max(0, r-tlen+1) .. min(r, qlen-1) are a run of consecutive words, dealt round-robin.
+//
+// Exact scores (:312-349).  H(t, j) is a potential: u = H(t,j) - H(t-1,j) + (q+e), v = H(t,j) - H(t,j-1) + (q+e) are both
+// differences of it (the boundary values v1 = q / 0 and the :212 patch encode H(-1, j) = -(q + e(j+1)), H(t, -1) likewise),
+// so H can be carried along a row with u instead of down a column with v: g_j = H + (q+e)(r+1) + bias gets u8 added on
+// every diagonal, as uint16 halves in registers.  Rows in flight before t = 0 are held at their boundary state; rows past
+// t = tlen-1 and rows >= qlen compute real cells of the problem extended with zero codes (nobody reads them) and are
+// masked out of the maximum.  The running maximum needs no exchange per diagonal: every thread keeps the best score of its
+// own rows, the FIRST diagonal it was reached on and a snapshot of its scores there; the overall maximum was first
+// reached on the smallest such diagonal among the threads that hold it, and the SSE tie order (:316-348: H[en0] first,
+// then four strided accumulators, then the scalar tail) is applied to the snapshots once, after the last diagonal.
+//
+// The backtrack matrix is written p[r][j] (one byte per row, pitch 32 W: each group stores whole 32-byte sectors) and
+// walked as ksw_backtrack (:47-79) through a 32 x 32 shared-memory tile, like the column-owned variant.
+#pragma once
+#include "ksw2.cuh"
+
+// reads of up to 32 W bases: W = 5 covers 160 bp, W = 8 covers 256 bp; 0 = not served by this variant
+__host__ __device__ inline int ksw_rows_w(int qlen) { return qlen <= 160 ? 5 : (qlen <= 256 ? 8 : 0); }
+// shared-memory bytes of the reversed, zero-padded target
+__host__ __device__ inline size_t ksw_rows_stage_bytes(int W, int tlen) { return (size_t)((tlen + 64 * W + 8 + 3) & ~3); }
+// bytes of backtrack matrix
+__host__ __device__ inline size_t ksw_rows_p_bytes(int W, int qlen, int tlen) { return (size_t)(qlen + tlen - 1) * (size_t)(32 * W) + 2 * KSW_PMAT_PAD + 64; }
+__host__ __device__ inline bool ksw_rows_params_ok(const KswParams &P)
+{
+	const int qe = P.q + P.e;
+	int min_sc = P.mismatch < 0 ? P.mismatch : 0;
+	if (P.match < min_sc) min_sc = P.match;
+	return P.w < 0 && P.zdrop < 0 && P.match > 0 && P.match + 2 * qe <= 63 && P.q >= 0 && P.e >= 0 && P.q + 2 * P.e + min_sc >= 0 && -min_sc <= 2 * qe;
+}
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+
+// ALL 32 threads of a warp call this together (4 groups of 8 threads, one alignment per group; valid = 0 for a group
+// without one).  The caller has checked ksw_rows_params_ok, qlen <= 32 W, ksw_rows_stage_bytes <= M.region_bytes and
+// ksw_rows_p_bytes <= M.p_cap for every valid group.
+template <int W, bool EZ_FULL>
+__device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, const uint8_t *target, const KswParams P, const KswMem M, KswOut &out)
+{
+	constexpr int PITCH = 32 * W, PADL = 32 * W;
+	const int lane = lane_id(), gl = lane & 7;
+	const unsigned gmask = 0xffu << (lane & ~7);
+	ksw_reset(out);
+	const int qe = P.q + P.e, gbias = 2 * qe;
+	bool live = valid;
+	if (live) {
+		if (qlen <= 0 || tlen <= 0) { out.status = KSW_ST_EARLY; live = false; }                                     // :147
+		else if (qlen > 32 * W || ksw_rows_stage_bytes(W, tlen) > (size_t)M.region_bytes) { out.status = KSW_ST_RCAP; live = false; }
+		else if (ksw_rows_p_bytes(W, qlen, tlen) > M.p_cap) { out.status = KSW_ST_PCAP; live = false; }
+		else if ((long long)(qlen + tlen + 2) * qe + (long long)(qlen < tlen ? qlen : tlen) * P.match + gbias + (long long)P.q * 32 * W >= 0xF000) { out.status = KSW_ST_HCAP; live = false; }
+	}
+	const bool run = live;
+	const int nr = live ? qlen + tlen - 1 : 0;
+	uint8_t *pmat = M.pmat + KSW_PMAT_PAD;
+	uint32_t *TW = (uint32_t*)M.xvuy; // the reversed target, zero padded: byte PADL + k holds target[tlen-1-k]
+	const uint32_t QE2 = P.qe2_4, MATQ = P.maxsc_4, MISQ = P.misq_4, Q4 = P.q_4;
+
+	bool wild = false;
+	if (live) {
+		const int total = (int)ksw_rows_stage_bytes(W, tlen);
+		for (int i = gl * 4; i < total; i += 32) {
+			uint32_t wv = 0;
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				const int k = i + c - PADL;
+				if (k >= 0 && k < tlen) wv |= (uint32_t)target[tlen - 1 - k] << (8 * c);
+			}
+			TW[i >> 2] = wv; wild |= ksw_has4(wv);
+		}
+	}
+	// rows in registers: slot s of this thread is query word 8 s + gl
+	uint32_t qw[W], x[W], v[W], u[W], y[W], gx[W], gy[W], snx[W], sny[W];
+#pragma unroll
+	for (int s = 0; s < W; ++s) {
+		const int j0 = 4 * (8 * s + gl);
+		uint32_t qv = 0;
+#pragma unroll
+		for (int c = 0; c < 4; ++c) {
+			const uint32_t code = (live && j0 + c < qlen) ? (uint32_t)ksw_query_code(query, j0 + c) : 0u;
+			wild |= code == 4u; qv |= code << (8 * c);
+		}
+		qw[s] = qv;
+		x[s] = 0u; y[s] = 0u; u[s] = 0u;
+		v[s] = Q4;                                  // v1 = q for a row that starts on a diagonal r > 0 (:211)
+		const int i0 = P.q * (j0 - 1) - P.e + gbias; // g of row j before its first cell: H(-1, j) + (q+e) j + bias
+		gx[s] = (uint32_t)(i0 & 0xffff) | ((uint32_t)((i0 + P.q) & 0xffff) << 16);
+		gy[s] = (uint32_t)((i0 + 2 * P.q) & 0xffff) | ((uint32_t)((i0 + 3 * P.q) & 0xffff) << 16);
+		snx[s] = 0u; sny[s] = 0u;
+	}
+	if (gl == 0) v[0] &= 0xffffff00u;              // ... and 0 for row 0 on diagonal 0
+	wild = ksw_group_any(wild, lane);
+	__syncwarp();
+
+	const int srcl = (lane & ~7) | ((gl + 7) & 7); // the thread that owns the word below mine
+	int tbest = 0, tr = -1;                        // best exact score over my rows so far, the first diagonal it was seen on
+	int mte = KSW_NEG_INF, mte_r = -1, mqe = KSW_NEG_INF, mqe_t = -1, score = KSW_NEG_INF;
+	const int jl = qlen - 1;                       // the last query row: slot (jl >> 5) of thread ((jl >> 2) & 7), lane jl & 3
+	const bool own_last = live && ((jl >> 2) & 7) == gl;
+	uint8_t *prow = pmat + 4 * gl;
+	const int tb = PADL + tlen - 1 + 4 * gl;       // word 8 s + gl meets the reversed-target bytes tb - r + 32 s ...
+
+	for (int r = 0; ; ++r, prow += PITCH) {
+		const bool act = live && r < nr;
+		if (!__any_sync(FULL_MASK, act)) break;
+		const int lo0 = r - 4 * gl;                // diagonal offset of the first row of slot 0: t of row 4w is lo0 - 32 s
+		const int tbase = tb - r;
+		const uint32_t *tp = TW + (tbase >> 2);
+		const int tsh = 8 * (tbase & 3);
+		const int goff = qe * (r + 1) + gbias;
+		uint32_t C[W];
+#pragma unroll
+		for (int s = 0; s < W; ++s) C[s] = prmt(u[s], y[s], 0x7300); // byte 2 = u of my top lane, byte 3 = y of it
+		const uint32_t bconst = r ? ((uint32_t)(P.q & 0xff) << 16) : 0u; // :212  u[r] = q (0 on diagonal 0), y[r] = 0
+		uint32_t dm2 = 0;
+#pragma unroll
+		for (int s = 0; s < W; ++s) {
+			const int lo = lo0 - 32 * s;           // t of row 4w on this diagonal
+			const bool on = act && lo >= 0 && lo <= tlen + 2 && 32 * s + 4 * gl < qlen;
+			if (!__any_sync(FULL_MASK, on)) continue;
+			uint32_t send = C[s];
+			if (s > 0 && gl == 7) send = C[s - 1];
+			uint32_t pc = __shfl_sync(FULL_MASK, send, srcl);
+			if (s == 0 && gl == 0) pc = bconst;
+			if (on) {
+				const uint32_t ut = prmt(u[s], pc, 0x2106), yt = prmt(y[s], pc, 0x2107); // u, y of rows 4w-1 .. 4w+2
+				const uint32_t tw = __funnelshift_r(tp[8 * s], tp[8 * s + 1], tsh);      // target codes met by rows 4w .. 4w+3
+				uint32_t z0 = sel4(msb_to_mask4((tw ^ qw[s]) + 0x7f7f7f7fu), MISQ, MATQ);
+				if (wild) z0 = ksw_wild_score(tw, qw[s], z0, QE2);
+				uint32_t d, un, vn, xn, yn;
+				ksw_core_word(P, true, z0, x[s], v[s], ut, yt, xn, vn, un, yn, d);
+				KSW_PSTORE((uint32_t*)(prow + 32 * s), d);
+				if (lo >= 3 && lo <= tlen - 1 && 32 * s + 4 * gl + 3 < qlen) { // four real cells
+					x[s] = xn; v[s] = vn; u[s] = un; y[s] = yn;
+					gx[s] += prmt(un, 0u, 0x4140); gy[s] += prmt(un, 0u, 0x4342);
+					dm2 = __vimax3_u16x2(dm2, gx[s], gy[s]);
+				} else {
+					// lane c is row 4w + c at t = lo - c: started once t >= 0, real while t <= tlen-1 and the row < qlen
+					const uint32_t ms = lo >= 3 ? 0xffffffffu : (0xffffffffu >> (8 * (3 - lo)));
+					const int cf = lo - (tlen - 1), cq = qlen - (32 * s + 4 * gl);
+					uint32_t mv = ms;
+					if (cf > 0) mv = cf >= 4 ? 0u : (mv & (0xffffffffu << (8 * cf)));
+					if (cq < 4) mv &= 0xffffffffu >> (8 * (4 - cq));
+					// rows still in front of t = 0 stay at their boundary state (x = 0, v = q, y = 0, u in range)
+					x[s] = xn & ms; y[s] = yn & ms; u[s] = un & ms; v[s] = sel4(ms, vn, Q4);
+					const uint32_t um = un & ms;
+					gx[s] += prmt(um, 0u, 0x4140); gy[s] += prmt(um, 0u, 0x4342);
+					dm2 = __vimax3_u16x2(dm2, gx[s] & prmt(mv, 0u, 0x1100), gy[s] & prmt(mv, 0u, 0x3322));
+				}
+			}
+		}
+		{
+			const int dm = (int)((dm2 & 0xffffu) > (dm2 >> 16) ? (dm2 & 0xffffu) : (dm2 >> 16)) - goff;
+			if (dm > tbest) { // strictly better than anything my rows have seen (:92 of ksw_apply_zdrop, per thread)
+				tbest = dm; tr = r;
+#pragma unroll
+				for (int s = 0; s < W; ++s) { snx[s] = gx[s]; sny[s] = gy[s]; }
+			}
+		}
+		if (EZ_FULL) {
+			if (act && r >= tlen - 1) { // en0 == tlen-1: H[en0] is the cell of row r - tlen + 1 (:351-352,356-357)
+				const int jt = r - tlen + 1;
+				if (((jt >> 2) & 7) == gl) {
+					uint32_t w2 = 0;
+#pragma unroll
+					for (int s = 0; s < W; ++s) if (s == (jt >> 5)) w2 = (jt & 2) ? gy[s] : gx[s];
+					const int hen = (int)((w2 >> (16 * (jt & 1))) & 0xffffu) - goff;
+					if (hen > mte) { mte = hen; mte_r = r; }
+				}
+			}
+			if (own_last && act && r >= jl) { // r - st0 == qlen-1: H[st0] is the cell of the last row (:353-354)
+				uint32_t w2 = 0;
+#pragma unroll
+				for (int s = 0; s < W; ++s) if (s == (jl >> 5)) w2 = (jl & 2) ? gy[s] : gx[s];
+				const int h = (int)((w2 >> (16 * (jl & 1))) & 0xffffu) - goff;
+				if (h > mqe) { mqe = h; mqe_t = r - jl; }
+				if (r == nr - 1) score = h;
+			}
+		}
+	}
+	// the overall maximum: best value, then the first diagonal it was reached on, then the SSE tie order on that diagonal
+	{
+		const unsigned V = ksw_group_max((unsigned)tbest);
+		const unsigned rs = ksw_group_min((run && (unsigned)tbest == V && tr >= 0) ? (unsigned)tr : 0x7fffffffu);
+		const bool have = run && V > 0u && rs != 0x7fffffffu;
+		const int r = have ? (int)rs : 0;
+		int st0 = 0, en0 = 0;
+		if (have) ksw_band(r, qlen, tlen, 0, st0, en0, true);
+		const int en1 = st0 + (((en0 - st0) >> 2) << 2);
+		const unsigned want = V + (unsigned)(qe * (r + 1) + gbias);
+		unsigned best = 0xffffffffu;
+		if (have && (unsigned)tbest == V && tr == r) {
+#pragma unroll
+			for (int s = 0; s < W; ++s) {
+#pragma unroll
+				for (int c = 0; c < 4; ++c) {
+					const int j = 4 * (8 * s + gl) + c, t = r - j;
+					const unsigned val = ((c < 2 ? snx[s] : sny[s]) >> (16 * (c & 1))) & 0xffffu;
+					if (j < qlen && t >= st0 && t <= en0 && val == want) {
+						const unsigned rk = t == en0 ? 0u : ksw_tie_rank(t, st0, en1);
+						best = rk < best ? rk : best;
+					}
+				}
+			}
+		}
+		const unsigned rk = ksw_group_min(best); // every lane of the warp takes part
+		if (have) {
+			const int t = rk == 0u ? en0 : st0 + (int)((rk - 1) & 0xfffffu);
+			out.max = (int)V; out.max_t = t; out.max_q = r - t;
+		}
+	}
+	if (EZ_FULL) {
+		// end-of-target scores: the first diagonal with the best H[tlen-1] (:351-352; mte_q = r - en with the ROUNDED en)
+		const unsigned bias = 0x40000000u;
+		const unsigned mv = ksw_group_max((unsigned)(mte + (int)bias));
+		const unsigned mr = ksw_group_min((mte_r >= 0 && (unsigned)(mte + (int)bias) == mv) ? (unsigned)mte_r : 0x7fffffffu);
+		if (run && mr != 0x7fffffffu) { out.mte = (int)(mv - bias); out.mte_q = (int)mr - ((tlen - 1) | 15); }
+		const int ol = (lane & ~7) | ((jl >> 2) & 7);
+		const int a = __shfl_sync(FULL_MASK, mqe, ol & 31), b = __shfl_sync(FULL_MASK, mqe_t, ol & 31), c = __shfl_sync(FULL_MASK, score, ol & 31);
+		if (run) { out.mqe = a; out.mqe_t = b; out.score = c; }
+	}
+	if (run) out.cells = (long long)qlen * (long long)tlen;
+	__syncwarp();
+	if (!run) return;
+	// ksw_backtrack :47-79 from (tlen-1, qlen-1) (never z-dropped: the band is the whole anti-diagonal), is_rot = 1.  Unbanded,
+	// the path never leaves [off, off_end], so no state is forced.  In (r, j) coordinates a step back keeps j or lowers it by
+	// one, so the rows r0 .. r0-31 can only be entered at columns j0-k .. j0: the group prefetches that triangle.
+	int i = tlen - 1, j = qlen - 1, n = 0, ovf = 0;
+	{
+		uint32_t *tile = (uint32_t*)M.xvuy;
+		uint32_t *cig = M.cig; const int cig_cap = M.cig_cap;
+		int state = 0;
+		unsigned cur_op = 0xffu, cur_len = 0;
+		const long long x_hi = (long long)(qlen + tlen - 1) * PITCH + KSW_PMAT_PAD - 40;
+		while (i >= 0 && j >= 0) {
+			const int j0 = j, r0 = i + j;
+			for (int row = gl; row < 32; row += 8) {
+				const int rr = r0 - row;
+				if (rr >= 0) {
+					long long x0 = (long long)rr * PITCH + (j0 - 31);
+					x0 = x0 < -(long long)(KSW_PMAT_PAD - 4) ? -(long long)(KSW_PMAT_PAD - 4) : (x0 > x_hi ? x_hi : x0);
+					const uint32_t *src = (const uint32_t*)(pmat + (x0 & ~3LL));
+					const int sh = 8 * (int)(x0 & 3);
+					const int k0 = (31 - row) >> 2;
+					uint32_t wv[9];
+#pragma unroll
+					for (int k = 0; k < 9; ++k) wv[k] = k >= k0 ? src[k] : 0u;
+#pragma unroll
+					for (int k = 0; k < 8; ++k) if (k >= k0) tile[row * 8 + k] = __funnelshift_r(wv[k], wv[k + 1], sh);
+				}
+			}
+			__syncwarp(gmask);
+			if (gl == 0) {
+				const uint8_t *tbp = (const uint8_t*)tile;
+				while (i >= 0 && j >= 0 && i + j > r0 - 32) {
+					const int r = i + j;
+					const unsigned tmp = tbp[(r0 - r) * 32 + (j - (j0 - 31))];
+					if (state == 0) state = tmp & 7;
+					else if (!((tmp >> (state + 2)) & 1)) state = 0;
+					if (state == 0) state = tmp & 7;
+					unsigned op;
+					if (state == 0) { op = 0; --i; --j; }
+					else if (state == 1 || state == 3) { op = 2; --i; }
+					else { op = 1; --j; }
+					if (op == cur_op) ++cur_len;
+					else {
+						if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; }
+						cur_op = op; cur_len = 1;
+					}
+				}
+			}
+			i = __shfl_sync(gmask, i, 0, 8); j = __shfl_sync(gmask, j, 0, 8);
+			__syncwarp(gmask);
+		}
+		if (gl == 0) {
+			if (i >= 0) {
+				if (cur_op == 2) cur_len += i + 1;
+				else { if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; } cur_op = 2; cur_len = i + 1; }
+			}
+			if (j >= 0) {
+				if (cur_op == 1) cur_len += j + 1;
+				else { if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; } cur_op = 1; cur_len = j + 1; }
+			}
+			if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; }
+		}
+	}
+	n = __shfl_sync(gmask, n, 0, 8);
+	ovf = __shfl_sync(gmask, ovf, 0, 8);
+	out.n_cigar = n;
+	if (ovf) out.status = KSW_ST_CIGCAP;
+	__syncwarp(gmask);
+}
+
+// which variant a warp takes: every valid group votes the W it needs (0: no alignment, 99: not served), the warp runs the
+// widest one if all its groups fit
+__device__ __forceinline__ int ksw_rows_pick(bool valid, int qlen, int tlen, const KswParams &P, const KswMem &M)
+{
+	int need = 0;
+	if (valid && qlen > 0 && tlen > 0) { need = ksw_rows_w(qlen); if (need == 0) need = 99; }
+	const int w = (int)__reduce_max_sync(FULL_MASK, (unsigned)need);
+	if (w == 0) return 5;
+	if (w > 8 || !ksw_rows_params_ok(P)) return 0;
+	const bool ok = !(valid && qlen > 0 && tlen > 0) || (ksw_rows_stage_bytes(w, tlen) <= (size_t)M.region_bytes && ksw_rows_p_bytes(w, qlen, tlen) <= M.p_cap);
+	return __all_sync(FULL_MASK, ok) ? w : 0;
+}

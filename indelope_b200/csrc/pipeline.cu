@@ -316,7 +316,8 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 	const int wA = P.a_bw < 0 ? std::max(P.max_contig_len, (int)max_ref) : P.a_bw;
 	const size_t rowsA = std::min<size_t>((size_t)P.max_contig_len + max_ref, 2 * (size_t)max_ref + wA + 2);
 	const size_t rowsB = (size_t)max_trim + std::max<size_t>(max_ref, 1536);
-	const size_t p_cap = round_up(std::max(rowsA * ksw_pitch(ncolA), rowsB * ksw_pitch(ncolB)) + 2 * KSW_PMAT_PAD + 64, 256);
+	const size_t pitchB = std::max<size_t>(ksw_pitch(ncolB), P.b_bw < 0 ? 32 * (size_t)ksw_rows_w(max_trim) : 0); // the row-owned variant stores 32 W bytes per diagonal
+	const size_t p_cap = round_up(std::max(rowsA * ksw_pitch(ncolA), rowsB * pitchB) + 2 * KSW_PMAT_PAD + 64, 256);
 	const size_t n_groups = (size_t)ctx->dp_ctas * DP_WARPS * DP_NG;
 	const int seq_spill_cap = (int)round_up(ksw_seq_bytes(std::max(P.max_contig_len, max_trim), std::max((int)max_ref, P.max_contig_len)), 16);
 	CK(L.pmat.ensure(n_groups * p_cap));
@@ -543,6 +544,7 @@ struct KswBatchArgs {
 	KswParams kp; idl_ez *out; uint32_t *cigar; unsigned long long *cigar_off; unsigned cigar_cap;
 	unsigned *next; unsigned *cig_used;
 	uint8_t *pmat; size_t p_cap; uint32_t *cig_scratch; int cig_cap; int ring_cols, seq_cap;
+	int no_rows; // IDL_KSW2_COLUMNS=1: keep unbanded alignments on the column-owned variant (tests compare the two)
 };
 
 template <bool UNB>
@@ -554,7 +556,7 @@ __global__ void __launch_bounds__(DP_THREADS, 3) ksw2_batch_kernel(KswBatchArgs 
 	const size_t per = ksw_group_smem(a.ring_cols, a.seq_cap);
 	const size_t gg = (size_t)blockIdx.x * (DP_WARPS * DP_NG) + cg;
 	KswMem M;
-	ksw_group_mem(M, smem_raw + per * cg, grp, a.ring_cols); M.seq_cap = a.seq_cap;
+	ksw_group_mem(M, smem_raw + per * cg, grp, a.ring_cols); M.seq_cap = a.seq_cap; M.region_bytes = (int)per;
 	M.pmat = a.pmat + gg * a.p_cap; M.p_cap = a.p_cap;
 	M.cig = a.cig_scratch + gg * (size_t)a.cig_cap; M.cig_cap = a.cig_cap;
 	for (;;) {
@@ -567,7 +569,13 @@ __global__ void __launch_bounds__(DP_THREADS, 3) ksw2_batch_kernel(KswBatchArgs 
 		const int qlen = valid ? (int)(a.q_off[i + 1] - a.q_off[i]) : 0, tlen = valid ? (int)(a.t_off[i + 1] - a.t_off[i]) : 0;
 		KswQuery kq; kq.codes = a.query + (valid ? a.q_off[i] : 0); kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
 		KswOut o;
-		ksw2_group<DP_G, true, UNB>(valid, qlen, kq, tlen, a.target + (valid ? a.t_off[i] : 0), a.kp, M, o);
+		const uint8_t *tq = a.target + (valid ? a.t_off[i] : 0);
+		const int rw = UNB && !a.no_rows ? ksw_rows_pick(valid, qlen, tlen, a.kp, M) : 0;
+		if (rw == 5) ksw2_rows<5, true>(valid, qlen, kq, tlen, tq, a.kp, M, o);
+#ifndef KSW_ROWS_NO8
+		else if (rw == 8) ksw2_rows<8, true>(valid, qlen, kq, tlen, tq, a.kp, M, o);
+#endif
+		else ksw2_group<DP_G, true, UNB>(valid, qlen, kq, tlen, tq, a.kp, M, o);
 		if (valid) {
 			const unsigned gmask = ((1u << DP_G) - 1u) << (lane & ~(DP_G - 1));
 			unsigned coff = 0;
@@ -602,10 +610,11 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 		max_q = std::max(max_q, ql); max_t = std::max(max_t, tl);
 		const int nc = ksw_ncol(std::max(ql, 1), std::max(tl, 1), w);
 		max_ncol = std::max(max_ncol, nc);
-		max_p = std::max(max_p, (size_t)std::max(ql + tl - 1, 0) * (size_t)ksw_pitch(nc));
+		max_p = std::max(max_p, (size_t)std::max(ql + tl - 1, 0) * std::max<size_t>(ksw_pitch(nc), w < 0 ? 32 * (size_t)ksw_rows_w(ql) : 0));
 	}
 	KswBatchArgs a; memset(&a, 0, sizeof a);
 	a.n = (unsigned)n; a.kp = ksw_make_params(match, mismatch, gapo, gape, w, zdrop);
+	{ const char *e = getenv("IDL_KSW2_COLUMNS"); a.no_rows = e && *e == '1'; }
 	a.ring_cols = ksw_ring_cols(max_ncol);
 	a.p_cap = round_up(max_p + 2 * KSW_PMAT_PAD + 64, 256); a.cig_cap = max_q + max_t + 8; a.cigar_cap = (unsigned)cigar_cap;
 	a.seq_cap = (int)round_up(ksw_seq_bytes(max_q, max_t), 16);

@@ -110,3 +110,39 @@ def test_long_alignments_and_score_window(ctx):
     big = rng.integers(0, 4, 9000).astype(np.uint8)
     f, c, extra, _ = ctx.ksw2_batch([big[:4500]], [big[:8200]], gapo=4, gape=1, w=50, zdrop=400)  # (qlen + tlen)(q + e) leaves the window
     assert extra[0]["status"] < 0 and f[0]["n_cigar"] == 0
+
+
+def test_row_owned_variant_edges(ctx):
+    """the unbanded call-site keeps the query rows in registers for reads of up to 256 bases (ksw2_rows.cuh): every row count
+    around the word / slot / variant boundaries against short and long targets, tandem repeats and N codes"""
+    rng = np.random.default_rng(17)
+    pairs = []
+    for ql in (1, 2, 3, 4, 5, 7, 8, 31, 32, 33, 127, 128, 129, 150, 159, 160, 161, 200, 255, 256, 257, 300):
+        for tl in (1, 2, 3, 4, 5, 17, 149, 233, 700):
+            base = rng.integers(0, 4, ql + tl + 8).astype(np.uint8)
+            o = int(rng.integers(0, tl))
+            q = base[o:o + ql].copy(); t = base[:tl].copy()
+            if rng.random() < 0.3:
+                unit = rng.integers(0, 4, int(rng.integers(1, 4))).astype(np.uint8)
+                k = int(rng.integers(0, max(1, tl - 1))); t[k:k + 20] = np.resize(unit, len(t[k:k + 20]))
+            m = rng.random(len(q)) < 0.03; q[m] = rng.integers(0, 5, int(m.sum()))
+            pairs.append((q, t, 5, -1, -1))
+    for impl in (["lane", "ref"] if orc.have_ref() else ["lane"]):
+        assert check(ctx, pairs, impl) == []
+    # other gap costs through the same variant
+    assert check(ctx, [(p[0], p[1], 3, -1, -1) for p in pairs[::3]]) == []
+
+
+def test_row_owned_equals_column_owned(ctx, monkeypatch):
+    """IDL_KSW2_COLUMNS=1 keeps unbanded alignments on the column-owned variant: both give the same records and CIGARs"""
+    rng = np.random.default_rng(23)
+    qs, ts = [], []
+    for _ in range(400):
+        tl = int(rng.integers(20, 900)); base = rng.integers(0, 4, tl + 260).astype(np.uint8)
+        o = int(rng.integers(0, tl)); q = base[o:o + int(rng.integers(1, 257))].copy()
+        m = rng.random(len(q)) < 0.02; q[m] = rng.integers(0, 4, int(m.sum()))
+        qs.append(q); ts.append(base[:tl].copy())
+    a = ctx.ksw2_batch(qs, ts, gapo=5, gape=1, w=-1, zdrop=-1)
+    monkeypatch.setenv("IDL_KSW2_COLUMNS", "1")
+    b = ctx.ksw2_batch(qs, ts, gapo=5, gape=1, w=-1, zdrop=-1)
+    assert a[0] == b[0] and a[1] == b[1]

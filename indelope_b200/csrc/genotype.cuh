@@ -19,6 +19,9 @@
 #define KMER_THREADS 128
 #define DP_G 8          // threads per alignment
 #define DP_NG (32 / DP_G)
+#ifndef KSW_UNB_CTAS
+#define KSW_UNB_CTAS 2 /* resident CTAs per SM of the unbanded kernels: the row-owned variant keeps 7 registers per query word */
+#endif
 
 struct AlEntry { unsigned event; unsigned base; unsigned n_reads; unsigned pad; };
 struct AlItem { unsigned event; unsigned read; int start; int pad; }; // one read of one AL event: two DP tasks (2*i: reference, 2*i+1: contig)
@@ -437,7 +440,7 @@ __device__ __forceinline__ int count_flanked(const uint32_t *cig_rev, int n, int
 
 // AL fallback, step 2: call-site B of kernel 2, one group per task (read vs reference suffix / contig suffix), :343-347
 template <bool UNB>
-__global__ void __launch_bounds__(DP_THREADS, 3) al_kernel(GenoArgs g)
+__global__ void __launch_bounds__(DP_THREADS, UNB ? KSW_UNB_CTAS : 3) al_kernel(GenoArgs g)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;

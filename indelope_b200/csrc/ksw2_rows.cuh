@@ -42,6 +42,95 @@ __host__ __device__ inline bool ksw_rows_params_ok(const KswParams &P)
 }
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+
+#define KSW_ROWS_TPAD 5u /* code of the target padding: matches no query code, so cells past the target end only lose score */
+#define KSW_ROWS_QPAD 6u /* code of the query padding (rows >= qlen) */
+
+// One packed word of four query rows on one diagonal: the recurrence of :262-284 in its carry-free form (every byte of a
+// real cell is in [0, match + 2(q+e)] <= 63: sums stay below 128 and nothing carries between bytes; `chk` collects the
+// inputs so that the caller can prove it after the fact), the backtrack word, and the exact scores g += u.
+// FRONT: the word holds lanes outside the target (outside `m`): rows that have not reached t = 0 yet keep their boundary
+// state (x = 0, v = q, y = 0, g = its initial value), rows past t = tlen-1 are parked in the same state; both stay out of
+// the maximum.  One step from in-range inputs cannot carry between bytes, so a parked lane never disturbs its neighbours.
+template <bool FRONT>
+__device__ __forceinline__ void ksw_rows_word(const KswParams &P, uint32_t m, uint32_t pc, uint32_t tw, uint32_t qv, bool wild,
+                                              uint32_t &x, uint32_t &v, uint32_t &u, uint32_t &y, uint32_t &gx, uint32_t &gy, uint32_t &dm2, uint32_t &chk, uint32_t *pdst)
+{
+	const uint32_t MAXSC = P.maxsc_4, Q4 = P.q_4;
+	const uint32_t ut = prmt(u, pc, 0x2106), yt = prmt(y, pc, 0x2107); // u, y of rows 4w-1 .. 4w+2 (previous diagonal)
+	uint32_t z0 = sel4(msb_to_mask4((tw ^ qv) + 0x7f7f7f7fu), P.misq_4, P.maxsc_4);
+	if (wild) z0 = ksw_wild_score(tw, qv, z0, P.qe2_4);
+	chk |= x | v; chk |= ut | yt;
+	const uint32_t a = x + v, b = yt + ut;
+	uint32_t mk = ge4_pos(z0, a);                   // z >= a
+	uint32_t z = sel4(mk, z0, a);
+	uint32_t d = ~mk & 0x01010101u;
+	mk = ge4_pos(z, b);                             // z >= b
+	d = sel4(mk, d, 0x02020202u);
+	z = sel4(mk, z, b);
+	z = sel4(msb_to_mask4(P.maxsc_h80 - z), z, MAXSC); // min(z, max score)
+	const uint32_t zh = z | KSW_H80;
+	uint32_t un = (zh - v) ^ KSW_H80, vn = (zh - ut) ^ KSW_H80;
+	z -= Q4;
+	mk = ge4_pos(z, a);                             // z >= a: x = 0
+	uint32_t xn = sel4(mk, z, a) - z; d |= ~mk & 0x08080808u;
+	mk = ge4_pos(z, b);
+	uint32_t yn = sel4(mk, z, b) - z; d |= ~mk & 0x10101010u;
+	KSW_PSTORE(pdst, d);
+	if (FRONT) {
+		xn &= m; yn &= m; un &= m; vn = sel4(m, vn, Q4);
+		gx += prmt(un, 0u, 0x4140); gy += prmt(un, 0u, 0x4342);
+		dm2 = __vimax3_u16x2(dm2, gx & prmt(m, 0u, 0x1100), gy & prmt(m, 0u, 0x3322));
+	} else {
+		gx += prmt(un, 0u, 0x4140); gy += prmt(un, 0u, 0x4342);
+		dm2 = __vimax3_u16x2(dm2, gx, gy);
+	}
+	x = xn; v = vn; u = un; y = yn;
+}
+
+// per-diagonal values shared by the slots of a thread
+struct KswRowsDiag { bool act, wild; int lo0, tlen, qrem, gl, srcl, tsh; uint32_t bconst, taddr; uint8_t *prow; };
+
+// The slots of one diagonal, unrolled by template recursion: every index into the register arrays is a compile-time
+// constant from the start (a `#pragma unroll` loop around warp votes and shuffles is unrolled too late for the arrays to
+// be promoted to registers).
+template <int W, int S>
+struct KswRowsSlots {
+	static __device__ __forceinline__ void run(const KswParams &P, const KswRowsDiag &dg, const uint32_t (&C)[W], const uint32_t (&qw)[W], uint32_t (&x)[W], uint32_t (&v)[W],
+	                                           uint32_t (&u)[W], uint32_t (&y)[W], uint32_t (&gx)[W], uint32_t (&gy)[W], uint32_t &dm2, uint32_t &chk)
+	{
+		const int lo = dg.lo0 - 32 * S; // t of row 4w on this diagonal; lane c is row 4w + c at t = lo - c
+		const bool on = dg.act && lo >= 0 && lo <= dg.tlen + 2 && 32 * S < dg.qrem; // a lane of the word is inside the target
+		if (__any_sync(FULL_MASK, on)) {
+			uint32_t send = C[S];
+			if (S > 0 && dg.gl == 7) send = C[S > 0 ? S - 1 : 0];
+			uint32_t pc = __shfl_sync(FULL_MASK, send, dg.srcl);
+			if (S == 0 && dg.gl == 0) pc = dg.bconst;
+			const bool whole = lo >= 3 && lo <= dg.tlen - 1;
+			if (__any_sync(FULL_MASK, on && !whole)) {
+				// the slot holds a word with lanes in front of t = 0 (the word of row r) or past t = tlen-1 (the word of row
+				// r - tlen): those lanes keep a fixed in-range state and stay out of the maximum
+				if (on) {
+					uint32_t m = lo >= 3 ? 0xffffffffu : (0xffffffffu >> (8 * (3 - lo)));
+					const int cf = lo - (dg.tlen - 1);
+					if (cf > 0) m &= 0xffffffffu << (8 * cf); // cf <= 3 while the word is on
+					const uint32_t tw = __funnelshift_r(lds32(dg.taddr + 32 * S), lds32(dg.taddr + 32 * S + 4), dg.tsh); // target codes met by rows 4w .. 4w+3
+					ksw_rows_word<true>(P, m, pc, tw, qw[S], dg.wild, x[S], v[S], u[S], y[S], gx[S], gy[S], dm2, chk, (uint32_t*)(dg.prow + 32 * S));
+				}
+			} else if (on) {
+				const uint32_t tw = __funnelshift_r(lds32(dg.taddr + 32 * S), lds32(dg.taddr + 32 * S + 4), dg.tsh);
+				ksw_rows_word<false>(P, 0u, pc, tw, qw[S], dg.wild, x[S], v[S], u[S], y[S], gx[S], gy[S], dm2, chk, (uint32_t*)(dg.prow + 32 * S));
+			}
+		}
+		KswRowsSlots<W, S + 1>::run(P, dg, C, qw, x, v, u, y, gx, gy, dm2, chk);
+	}
+};
+template <int W>
+struct KswRowsSlots<W, W> {
+	static __device__ __forceinline__ void run(const KswParams &, const KswRowsDiag &, const uint32_t (&)[W], const uint32_t (&)[W], uint32_t (&)[W], uint32_t (&)[W],
+	                                           uint32_t (&)[W], uint32_t (&)[W], uint32_t (&)[W], uint32_t (&)[W], uint32_t &, uint32_t &) {}
+};
 
 // ALL 32 threads of a warp call this together (4 groups of 8 threads, one alignment per group; valid = 0 for a group
 // without one).  The caller has checked ksw_rows_params_ok, qlen <= 32 W, ksw_rows_stage_bytes <= M.region_bytes and
@@ -64,8 +153,7 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 	const bool run = live;
 	const int nr = live ? qlen + tlen - 1 : 0;
 	uint8_t *pmat = M.pmat + KSW_PMAT_PAD;
-	uint32_t *TW = (uint32_t*)M.xvuy; // the reversed target, zero padded: byte PADL + k holds target[tlen-1-k]
-	const uint32_t QE2 = P.qe2_4, MATQ = P.maxsc_4, MISQ = P.misq_4, Q4 = P.q_4;
+	uint32_t *TW = (uint32_t*)M.xvuy; // the reversed target, padded on both sides: byte PADL + k holds target[tlen-1-k]
 
 	bool wild = false;
 	if (live) {
@@ -75,7 +163,7 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 #pragma unroll
 			for (int c = 0; c < 4; ++c) {
 				const int k = i + c - PADL;
-				if (k >= 0 && k < tlen) wv |= (uint32_t)target[tlen - 1 - k] << (8 * c);
+				wv |= ((k >= 0 && k < tlen) ? (uint32_t)target[tlen - 1 - k] : KSW_ROWS_TPAD) << (8 * c);
 			}
 			TW[i >> 2] = wv; wild |= ksw_has4(wv);
 		}
@@ -88,12 +176,12 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 		uint32_t qv = 0;
 #pragma unroll
 		for (int c = 0; c < 4; ++c) {
-			const uint32_t code = (live && j0 + c < qlen) ? (uint32_t)ksw_query_code(query, j0 + c) : 0u;
+			const uint32_t code = (live && j0 + c < qlen) ? (uint32_t)ksw_query_code(query, j0 + c) : KSW_ROWS_QPAD;
 			wild |= code == 4u; qv |= code << (8 * c);
 		}
 		qw[s] = qv;
 		x[s] = 0u; y[s] = 0u; u[s] = 0u;
-		v[s] = Q4;                                  // v1 = q for a row that starts on a diagonal r > 0 (:211)
+		v[s] = P.q_4;                               // v1 = q for a row that starts on a diagonal r > 0 (:211)
 		const int i0 = P.q * (j0 - 1) - P.e + gbias; // g of row j before its first cell: H(-1, j) + (q+e) j + bias
 		gx[s] = (uint32_t)(i0 & 0xffff) | ((uint32_t)((i0 + P.q) & 0xffff) << 16);
 		gy[s] = (uint32_t)((i0 + 2 * P.q) & 0xffff) | ((uint32_t)((i0 + 3 * P.q) & 0xffff) << 16);
@@ -110,56 +198,26 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 	const bool own_last = live && ((jl >> 2) & 7) == gl;
 	uint8_t *prow = pmat + 4 * gl;
 	const int tb = PADL + tlen - 1 + 4 * gl;       // word 8 s + gl meets the reversed-target bytes tb - r + 32 s ...
+	const uint32_t tw_sh = (uint32_t)__cvta_generic_to_shared(TW);
+	uint32_t chk = 0;
 
 	for (int r = 0; ; ++r, prow += PITCH) {
 		const bool act = live && r < nr;
 		if (!__any_sync(FULL_MASK, act)) break;
-		const int lo0 = r - 4 * gl;                // diagonal offset of the first row of slot 0: t of row 4w is lo0 - 32 s
+		const int lo0 = r - 4 * gl;                // t of row 4w on this diagonal is lo0 - 32 s
 		const int tbase = tb - r;
-		const uint32_t *tp = TW + (tbase >> 2);
+		const uint32_t taddr = tw_sh + (uint32_t)(tbase & ~3);
 		const int tsh = 8 * (tbase & 3);
-		const int goff = qe * (r + 1) + gbias;
 		uint32_t C[W];
 #pragma unroll
 		for (int s = 0; s < W; ++s) C[s] = prmt(u[s], y[s], 0x7300); // byte 2 = u of my top lane, byte 3 = y of it
 		const uint32_t bconst = r ? ((uint32_t)(P.q & 0xff) << 16) : 0u; // :212  u[r] = q (0 on diagonal 0), y[r] = 0
 		uint32_t dm2 = 0;
-#pragma unroll
-		for (int s = 0; s < W; ++s) {
-			const int lo = lo0 - 32 * s;           // t of row 4w on this diagonal
-			const bool on = act && lo >= 0 && lo <= tlen + 2 && 32 * s + 4 * gl < qlen;
-			if (!__any_sync(FULL_MASK, on)) continue;
-			uint32_t send = C[s];
-			if (s > 0 && gl == 7) send = C[s - 1];
-			uint32_t pc = __shfl_sync(FULL_MASK, send, srcl);
-			if (s == 0 && gl == 0) pc = bconst;
-			if (on) {
-				const uint32_t ut = prmt(u[s], pc, 0x2106), yt = prmt(y[s], pc, 0x2107); // u, y of rows 4w-1 .. 4w+2
-				const uint32_t tw = __funnelshift_r(tp[8 * s], tp[8 * s + 1], tsh);      // target codes met by rows 4w .. 4w+3
-				uint32_t z0 = sel4(msb_to_mask4((tw ^ qw[s]) + 0x7f7f7f7fu), MISQ, MATQ);
-				if (wild) z0 = ksw_wild_score(tw, qw[s], z0, QE2);
-				uint32_t d, un, vn, xn, yn;
-				ksw_core_word(P, true, z0, x[s], v[s], ut, yt, xn, vn, un, yn, d);
-				KSW_PSTORE((uint32_t*)(prow + 32 * s), d);
-				if (lo >= 3 && lo <= tlen - 1 && 32 * s + 4 * gl + 3 < qlen) { // four real cells
-					x[s] = xn; v[s] = vn; u[s] = un; y[s] = yn;
-					gx[s] += prmt(un, 0u, 0x4140); gy[s] += prmt(un, 0u, 0x4342);
-					dm2 = __vimax3_u16x2(dm2, gx[s], gy[s]);
-				} else {
-					// lane c is row 4w + c at t = lo - c: started once t >= 0, real while t <= tlen-1 and the row < qlen
-					const uint32_t ms = lo >= 3 ? 0xffffffffu : (0xffffffffu >> (8 * (3 - lo)));
-					const int cf = lo - (tlen - 1), cq = qlen - (32 * s + 4 * gl);
-					uint32_t mv = ms;
-					if (cf > 0) mv = cf >= 4 ? 0u : (mv & (0xffffffffu << (8 * cf)));
-					if (cq < 4) mv &= 0xffffffffu >> (8 * (4 - cq));
-					// rows still in front of t = 0 stay at their boundary state (x = 0, v = q, y = 0, u in range)
-					x[s] = xn & ms; y[s] = yn & ms; u[s] = un & ms; v[s] = sel4(ms, vn, Q4);
-					const uint32_t um = un & ms;
-					gx[s] += prmt(um, 0u, 0x4140); gy[s] += prmt(um, 0u, 0x4342);
-					dm2 = __vimax3_u16x2(dm2, gx[s] & prmt(mv, 0u, 0x1100), gy[s] & prmt(mv, 0u, 0x3322));
-				}
-			}
-		}
+		KswRowsDiag dg;
+		dg.act = act; dg.lo0 = lo0; dg.tlen = tlen; dg.qrem = qlen - 4 * gl; dg.gl = gl; dg.srcl = srcl; dg.bconst = bconst;
+		dg.taddr = taddr; dg.tsh = tsh; dg.wild = wild; dg.prow = prow;
+		KswRowsSlots<W, 0>::run(P, dg, C, qw, x, v, u, y, gx, gy, dm2, chk);
+		const int goff = qe * (r + 1) + gbias;
 		{
 			const int dm = (int)((dm2 & 0xffffu) > (dm2 >> 16) ? (dm2 & 0xffffu) : (dm2 >> 16)) - goff;
 			if (dm > tbest) { // strictly better than anything my rows have seen (:92 of ksw_apply_zdrop, per thread)
@@ -189,6 +247,8 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 			}
 		}
 	}
+	// every byte the recurrence read was in [0, 63] (the carry-free form is exact): anything else is reported, never returned
+	if (ksw_group_any((chk & 0xc0c0c0c0u) != 0u, lane) && run) out.status = KSW_ST_HCAP;
 	// the overall maximum: best value, then the first diagonal it was reached on, then the SSE tie order on that diagonal
 	{
 		const unsigned V = ksw_group_max((unsigned)tbest);

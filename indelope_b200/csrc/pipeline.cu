@@ -548,7 +548,7 @@ struct KswBatchArgs {
 };
 
 template <bool UNB>
-__global__ void __launch_bounds__(DP_THREADS, 3) ksw2_batch_kernel(KswBatchArgs a)
+__global__ void __launch_bounds__(DP_THREADS, UNB ? KSW_UNB_CTAS : 3) ksw2_batch_kernel(KswBatchArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;

@@ -27,10 +27,11 @@
 #pragma once
 #include "ksw2.cuh"
 
-// reads of up to 32 W bases: W = 5 covers 160 bp, W = 8 covers 256 bp; 0 = not served by this variant
-__host__ __device__ inline int ksw_rows_w(int qlen) { return qlen <= 160 ? 5 : (qlen <= 256 ? 8 : 0); }
+// reads of up to 32 W bases: W = 5 covers 160 bp and fits 80 registers (three CTAs per SM); 0 = not served by this variant
+// (W = 8 works -- the tests ran it -- but needs 128 registers; longer reads take the column-owned variant)
+__host__ __device__ inline int ksw_rows_w(int qlen) { return qlen <= 160 ? 5 : 0; }
 // shared-memory bytes of the reversed, zero-padded target
-__host__ __device__ inline size_t ksw_rows_stage_bytes(int W, int tlen) { return (size_t)((tlen + 64 * W + 8 + 3) & ~3); }
+__host__ __device__ inline size_t ksw_rows_stage_bytes(int W, int tlen) { return (size_t)((tlen + 64 * W + 8 + 3) & ~3) + 96; } // + the bank stagger of the group
 // bytes of backtrack matrix
 __host__ __device__ inline size_t ksw_rows_p_bytes(int W, int qlen, int tlen) { return (size_t)(qlen + tlen - 1) * (size_t)(32 * W) + 2 * KSW_PMAT_PAD + 64; }
 __host__ __device__ inline bool ksw_rows_params_ok(const KswParams &P)
@@ -53,14 +54,14 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm("ld.s
 // FRONT: the word holds lanes outside the target (outside `m`): rows that have not reached t = 0 yet keep their boundary
 // state (x = 0, v = q, y = 0, g = its initial value), rows past t = tlen-1 are parked in the same state; both stay out of
 // the maximum.  One step from in-range inputs cannot carry between bytes, so a parked lane never disturbs its neighbours.
-template <bool FRONT>
-__device__ __forceinline__ void ksw_rows_word(const KswParams &P, uint32_t m, uint32_t pc, uint32_t tw, uint32_t qv, bool wild,
+template <bool FRONT, bool WILD>
+__device__ __forceinline__ void ksw_rows_word(const KswParams &P, uint32_t m, uint32_t pc, uint32_t tw, uint32_t qv,
                                               uint32_t &x, uint32_t &v, uint32_t &u, uint32_t &y, uint32_t &gx, uint32_t &gy, uint32_t &dm2, uint32_t &chk, uint32_t *pdst)
 {
 	const uint32_t MAXSC = P.maxsc_4, Q4 = P.q_4;
 	const uint32_t ut = prmt(u, pc, 0x2106), yt = prmt(y, pc, 0x2107); // u, y of rows 4w-1 .. 4w+2 (previous diagonal)
 	uint32_t z0 = sel4(msb_to_mask4((tw ^ qv) + 0x7f7f7f7fu), P.misq_4, P.maxsc_4);
-	if (wild) z0 = ksw_wild_score(tw, qv, z0, P.qe2_4);
+	if (WILD) z0 = sel4(msb_to_mask4(((tw ^ 0x04040404u) + 0x7f7f7f7fu) & ((qv ^ 0x04040404u) + 0x7f7f7f7fu)), z0, P.qe2_4); // a code 4 on either side scores 0 (:219,226)
 	chk |= x | v; chk |= ut | yt;
 	const uint32_t a = x + v, b = yt + ut;
 	uint32_t mk = ge4_pos(z0, a);                   // z >= a
@@ -89,45 +90,45 @@ __device__ __forceinline__ void ksw_rows_word(const KswParams &P, uint32_t m, ui
 	x = xn; v = vn; u = un; y = yn;
 }
 
-// per-diagonal values shared by the slots of a thread
-struct KswRowsDiag { bool act, wild; int lo0, tlen, qrem, gl, srcl, tsh; uint32_t bconst, taddr; uint8_t *prow; };
+// per-diagonal values shared by the slots of a thread.  onm / pm: bit s = slot s of this thread has a lane inside the target /
+// has lanes outside it as well; uon / upm: the same OR-ed over the warp (uniform: they steer the branches).
+struct KswRowsDiag { int lo0, tlen, gl, srcl, tsh; unsigned onm, uon, upm; uint32_t bconst, taddr; uint8_t *prow; };
 
 // The slots of one diagonal, unrolled by template recursion: every index into the register arrays is a compile-time
 // constant from the start (a `#pragma unroll` loop around warp votes and shuffles is unrolled too late for the arrays to
 // be promoted to registers).
-template <int W, int S>
+template <int W, int S, bool WILD>
 struct KswRowsSlots {
 	static __device__ __forceinline__ void run(const KswParams &P, const KswRowsDiag &dg, const uint32_t (&C)[W], const uint32_t (&qw)[W], uint32_t (&x)[W], uint32_t (&v)[W],
 	                                           uint32_t (&u)[W], uint32_t (&y)[W], uint32_t (&gx)[W], uint32_t (&gy)[W], uint32_t &dm2, uint32_t &chk)
 	{
-		const int lo = dg.lo0 - 32 * S; // t of row 4w on this diagonal; lane c is row 4w + c at t = lo - c
-		const bool on = dg.act && lo >= 0 && lo <= dg.tlen + 2 && 32 * S < dg.qrem; // a lane of the word is inside the target
-		if (__any_sync(FULL_MASK, on)) {
+		if (dg.uon & (1u << S)) {
+			const bool on = (dg.onm & (1u << S)) != 0u;
 			uint32_t send = C[S];
 			if (S > 0 && dg.gl == 7) send = C[S > 0 ? S - 1 : 0];
 			uint32_t pc = __shfl_sync(FULL_MASK, send, dg.srcl);
 			if (S == 0 && dg.gl == 0) pc = dg.bconst;
-			const bool whole = lo >= 3 && lo <= dg.tlen - 1;
-			if (__any_sync(FULL_MASK, on && !whole)) {
+			if (dg.upm & (1u << S)) {
 				// the slot holds a word with lanes in front of t = 0 (the word of row r) or past t = tlen-1 (the word of row
 				// r - tlen): those lanes keep a fixed in-range state and stay out of the maximum
 				if (on) {
+					const int lo = dg.lo0 - 32 * S; // t of row 4w on this diagonal; lane c is row 4w + c at t = lo - c
 					uint32_t m = lo >= 3 ? 0xffffffffu : (0xffffffffu >> (8 * (3 - lo)));
 					const int cf = lo - (dg.tlen - 1);
 					if (cf > 0) m &= 0xffffffffu << (8 * cf); // cf <= 3 while the word is on
 					const uint32_t tw = __funnelshift_r(lds32(dg.taddr + 32 * S), lds32(dg.taddr + 32 * S + 4), dg.tsh); // target codes met by rows 4w .. 4w+3
-					ksw_rows_word<true>(P, m, pc, tw, qw[S], dg.wild, x[S], v[S], u[S], y[S], gx[S], gy[S], dm2, chk, (uint32_t*)(dg.prow + 32 * S));
+					ksw_rows_word<true, WILD>(P, m, pc, tw, qw[S], x[S], v[S], u[S], y[S], gx[S], gy[S], dm2, chk, (uint32_t*)(dg.prow + 32 * S));
 				}
 			} else if (on) {
 				const uint32_t tw = __funnelshift_r(lds32(dg.taddr + 32 * S), lds32(dg.taddr + 32 * S + 4), dg.tsh);
-				ksw_rows_word<false>(P, 0u, pc, tw, qw[S], dg.wild, x[S], v[S], u[S], y[S], gx[S], gy[S], dm2, chk, (uint32_t*)(dg.prow + 32 * S));
+				ksw_rows_word<false, WILD>(P, 0u, pc, tw, qw[S], x[S], v[S], u[S], y[S], gx[S], gy[S], dm2, chk, (uint32_t*)(dg.prow + 32 * S));
 			}
 		}
-		KswRowsSlots<W, S + 1>::run(P, dg, C, qw, x, v, u, y, gx, gy, dm2, chk);
+		KswRowsSlots<W, S + 1, WILD>::run(P, dg, C, qw, x, v, u, y, gx, gy, dm2, chk);
 	}
 };
-template <int W>
-struct KswRowsSlots<W, W> {
+template <int W, bool WILD>
+struct KswRowsSlots<W, W, WILD> {
 	static __device__ __forceinline__ void run(const KswParams &, const KswRowsDiag &, const uint32_t (&)[W], const uint32_t (&)[W], uint32_t (&)[W], uint32_t (&)[W],
 	                                           uint32_t (&)[W], uint32_t (&)[W], uint32_t (&)[W], uint32_t (&)[W], uint32_t &, uint32_t &) {}
 };
@@ -153,11 +154,13 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 	const bool run = live;
 	const int nr = live ? qlen + tlen - 1 : 0;
 	uint8_t *pmat = M.pmat + KSW_PMAT_PAD;
-	uint32_t *TW = (uint32_t*)M.xvuy; // the reversed target, padded on both sides: byte PADL + k holds target[tlen-1-k]
+	// the reversed target, padded on both sides: byte PADL + k holds target[tlen-1-k].  The four groups of a warp read the same
+	// relative words at the same time and their regions are a multiple of 128 bytes apart: group k starts 8 k words in
+	uint32_t *TW = (uint32_t*)((unsigned char*)M.xvuy + 32 * ((lane >> 3) & 3));
 
 	bool wild = false;
 	if (live) {
-		const int total = (int)ksw_rows_stage_bytes(W, tlen);
+		const int total = (int)ksw_rows_stage_bytes(W, tlen) - 96;
 		for (int i = gl * 4; i < total; i += 32) {
 			uint32_t wv = 0;
 #pragma unroll
@@ -188,9 +191,10 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 		snx[s] = 0u; sny[s] = 0u;
 	}
 	if (gl == 0) v[0] &= 0xffffff00u;              // ... and 0 for row 0 on diagonal 0
-	wild = ksw_group_any(wild, lane);
+	const bool wild_any = __any_sync(FULL_MASK, wild); // a code 4 anywhere in the four alignments: the scores take the wildcard mask
 	__syncwarp();
 
+	const int nsq = live ? (qlen - 4 * gl + 31) >> 5 : 0; // my slots that hold query rows
 	const int srcl = (lane & ~7) | ((gl + 7) & 7); // the thread that owns the word below mine
 	int tbest = 0, tr = -1;                        // best exact score over my rows so far, the first diagonal it was seen on
 	int mte = KSW_NEG_INF, mte_r = -1, mqe = KSW_NEG_INF, mqe_t = -1, score = KSW_NEG_INF;
@@ -214,9 +218,21 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 		const uint32_t bconst = r ? ((uint32_t)(P.q & 0xff) << 16) : 0u; // :212  u[r] = q (0 on diagonal 0), y[r] = 0
 		uint32_t dm2 = 0;
 		KswRowsDiag dg;
-		dg.act = act; dg.lo0 = lo0; dg.tlen = tlen; dg.qrem = qlen - 4 * gl; dg.gl = gl; dg.srcl = srcl; dg.bconst = bconst;
-		dg.taddr = taddr; dg.tsh = tsh; dg.wild = wild; dg.prow = prow;
-		KswRowsSlots<W, 0>::run(P, dg, C, qw, x, v, u, y, gx, gy, dm2, chk);
+		{
+			// my slots with a lane inside the target: t of the first row of slot s is lo0 - 32 s, wanted in [0, tlen + 2]
+			int s_hi = lo0 >> 5, s_lo = (lo0 - tlen + 29) >> 5;
+			s_hi = s_hi < nsq ? s_hi : nsq - 1; s_lo = s_lo > 0 ? s_lo : 0;
+			unsigned onm = 0, pm = 0;
+			if (act && s_hi >= s_lo) {
+				onm = ((2u << s_hi) - 1u) & ~((1u << s_lo) - 1u);
+				if (lo0 - 32 * s_hi < 3) pm = 1u << s_hi;          // the word of row r: lanes in front of t = 0
+				if (lo0 - 32 * s_lo > tlen - 1) pm |= 1u << s_lo;  // the word of row r - tlen: lanes past the target end
+			}
+			dg.onm = onm; dg.uon = __reduce_or_sync(FULL_MASK, onm); dg.upm = __reduce_or_sync(FULL_MASK, pm);
+		}
+		dg.lo0 = lo0; dg.tlen = tlen; dg.gl = gl; dg.srcl = srcl; dg.bconst = bconst; dg.taddr = taddr; dg.tsh = tsh; dg.prow = prow;
+		if (wild_any) KswRowsSlots<W, 0, true>::run(P, dg, C, qw, x, v, u, y, gx, gy, dm2, chk);
+		else KswRowsSlots<W, 0, false>::run(P, dg, C, qw, x, v, u, y, gx, gy, dm2, chk);
 		const int goff = qe * (r + 1) + gbias;
 		{
 			const int dm = (int)((dm2 & 0xffffu) > (dm2 >> 16) ? (dm2 & 0xffffu) : (dm2 >> 16)) - goff;
@@ -370,7 +386,7 @@ __device__ __forceinline__ int ksw_rows_pick(bool valid, int qlen, int tlen, con
 	if (valid && qlen > 0 && tlen > 0) { need = ksw_rows_w(qlen); if (need == 0) need = 99; }
 	const int w = (int)__reduce_max_sync(FULL_MASK, (unsigned)need);
 	if (w == 0) return 5;
-	if (w > 8 || !ksw_rows_params_ok(P)) return 0;
+	if (w > 5 || !ksw_rows_params_ok(P)) return 0;
 	const bool ok = !(valid && qlen > 0 && tlen > 0) || (ksw_rows_stage_bytes(w, tlen) <= (size_t)M.region_bytes && ksw_rows_p_bytes(w, qlen, tlen) <= M.p_cap);
 	return __all_sync(FULL_MASK, ok) ? w : 0;
 }

@@ -572,9 +572,6 @@ __global__ void __launch_bounds__(DP_THREADS, UNB ? KSW_UNB_CTAS : 3) ksw2_batch
 		const uint8_t *tq = a.target + (valid ? a.t_off[i] : 0);
 		const int rw = UNB && !a.no_rows ? ksw_rows_pick(valid, qlen, tlen, a.kp, M) : 0;
 		if (rw == 5) ksw2_rows<5, true>(valid, qlen, kq, tlen, tq, a.kp, M, o);
-#ifndef KSW_ROWS_NO8
-		else if (rw == 8) ksw2_rows<8, true>(valid, qlen, kq, tlen, tq, a.kp, M, o);
-#endif
 		else ksw2_group<DP_G, true, UNB>(valid, qlen, kq, tlen, tq, a.kp, M, o);
 		if (valid) {
 			const unsigned gmask = ((1u << DP_G) - 1u) << (lane & ~(DP_G - 1));

@@ -19,6 +19,9 @@
 #define KMER_THREADS 128
 #define DP_G 8          // threads per alignment
 #define DP_NG (32 / DP_G)
+#ifndef KSW_A_CTAS
+#define KSW_A_CTAS 3 /* resident CTAs per SM of the banded call-site */
+#endif
 #ifndef KSW_UNB_CTAS
 #define KSW_UNB_CTAS 2 /* resident CTAs per SM of the unbanded kernels: the row-owned variant runs faster with 128 registers and 16 warps than squeezed into 80 with 24 (measured: al_kernel 22.9 vs 24.7 ms) */
 #endif
@@ -134,7 +137,7 @@ __device__ __forceinline__ int distinct_k(const uint8_t *a, int K)
 // ---------------------------------------------------------------------------------------------------------------
 // call-site A + glue: one group of DP_G threads per alignment, DP_NG alignments per warp
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DP_THREADS, 3) align_kernel(GenoArgs g)
+__global__ void __launch_bounds__(DP_THREADS, KSW_A_CTAS) align_kernel(GenoArgs g)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;

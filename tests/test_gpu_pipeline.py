@@ -53,18 +53,24 @@ def test_pr1_config_bit_exact():
     assert sum(t["kmer_bytes"] for t in tm) == cnt["kmer_bytes"]
 
 
-def test_golden_vcf_fixture():
-    """the committed golden VCF (made by tools/make_golden.py from the oracle) is reproduced byte for byte"""
-    path = os.path.join(os.path.dirname(__file__), "golden", "pr1_small.vcf")
-    ds = util.small_dataset("pr1", chrom_len=300_000, n_events=60)
+@pytest.mark.parametrize("name", ["pr1_small", "tandem_small"])
+def test_golden_fixtures(name):
+    """the committed golden VCFs and record dumps (tools/make_golden.py: the oracle running the reference's own compiled DP) are
+    reproduced byte for byte; tandem_small sends 24 events through the AL fallback (1428 unbanded alignments)"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools"))
+    from make_golden import FIXTURES
+    gold = os.path.join(os.path.dirname(__file__), "golden", name)
+    ds = util.small_dataset("pr1", **FIXTURES[name])
     rois = ds.sweep(min_reads=5)
     from indelope_b200 import api
     caller = api.Caller(0, min_reads=5, min_ctg_len=73, min_event_len=5)
     try:
-        vcf, _ = caller.call(rois)
+        vcf, dump = caller.call(rois, dump_level=31)
     finally:
         caller.close()
-    assert rois.header() + vcf == open(path).read()
+    assert rois.header() + vcf == open(gold + ".vcf").read()
+    assert "\n".join(l for l in dump.splitlines() if l[:1] in "RAEV") + "\n" == open(gold + ".dump").read()
 
 
 @pytest.mark.parametrize("name,over", [

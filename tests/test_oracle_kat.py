@@ -6,6 +6,8 @@ oracle in tests/test_gpu_*.py.
 """
 import math
 
+import pytest
+
 from oracle import pyoracle as orc
 
 UNALIGNED = -(2 ** 63)
@@ -133,3 +135,24 @@ def test_mincode_is_canonical():
     assert orc.mincode(a) == orc.mincode(rc)
     assert orc.mincode(a) != orc.mincode("C" + a[1:])
     assert orc.mincode("N" + a[1:]) is None
+
+
+@pytest.mark.parametrize("name", ["pr1_small", "tandem_small"])
+def test_oracle_reproduces_the_golden_fixtures(name):
+    """tests/golden/* were made by tools/make_golden.py with the oracle calling the reference's own compiled ksw2_extz2_sse.c
+    (oracle/_ref); the oracle with its own lane-exact DP, which is all that exists on a box without /root/reference, must give
+    the same bytes"""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    from make_golden import FIXTURES
+    from indelope_b200 import host
+    cfg = dict(host.CONFIGS["pr1"]); cfg.update(FIXTURES[name])
+    rois = host.Dataset(**cfg).sweep(min_reads=5)
+    dump, vcf, cnt = orc.call(rois.arrays(), min_reads=5, min_ctg_len=73, min_event_len=5, use_ref_ksw2=False, dump_level=31)
+    gold = os.path.join(root, "tests", "golden", name)
+    assert rois.header() + vcf == open(gold + ".vcf").read()
+    assert "\n".join(l for l in dump.splitlines() if l[:1] in "RAEV") + "\n" == open(gold + ".dump").read()
+    if name == "tandem_small":
+        assert cnt["al_events"] >= 20 and cnt["dp_b"] > 1000

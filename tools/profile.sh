@@ -21,4 +21,7 @@ ncu --set full --clock-control none --import-source on -k regex:ksw2_batch_kerne
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__thread_inst_executed.sum,smsp__inst_executed.sum,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active \
     --clock-control none -k regex:'assemble_kernel|align_kernel|kmer_kernel|al_kernel' --csv --log-file $OUT/traffic_full.csv \
     python bench.py --steps 1 --warmup 1 --cpu-sample 200 > $OUT/ncu_traffic.log 2>&1
+# 5. the dominant kernel at the FULL default workload: one full capture of the resident leg's al_kernel launch
+ncu --set full --clock-control none --import-source on -k regex:al_kernel -s 1 -c 1 -o $OUT/prof_al_kernel_full -f \
+    python bench.py --steps 1 --warmup 1 --cpu-sample 200 > $OUT/ncu_al_full.log 2>&1
 ls -la $OUT | head -40

@@ -22,8 +22,13 @@
 #ifndef KSW_A_CTAS
 #define KSW_A_CTAS 3 /* resident CTAs per SM of the banded call-site */
 #endif
+#ifndef KSW_UNB_WARPS
+#define KSW_UNB_WARPS 5 /* warps per CTA of the unbanded al_kernel.  Measured on the chr1 workload (ms): 8 warps x 2 CTAs at 124 registers
+                           22.0, 8 x 3 at 80 24.7, 10 x 2 at 95 21.8, 6 x 3 at 96 21.2, 7 x 3 at 80 21.8, 5 x 4 at 94 21.0, 2 x 10 at 94 21.0:
+                           twenty warps at 94 registers */
+#endif
 #ifndef KSW_UNB_CTAS
-#define KSW_UNB_CTAS 2 /* resident CTAs per SM of the unbanded kernels: the row-owned variant runs faster with 128 registers and 16 warps than squeezed into 80 with 24 (measured: al_kernel 22.9 vs 24.7 ms) */
+#define KSW_UNB_CTAS 4 /* resident CTAs per SM of the unbanded al_kernel */
 #endif
 
 struct AlEntry { unsigned event; unsigned base; unsigned n_reads; unsigned pad; };
@@ -89,11 +94,11 @@ __global__ void sort_scatter_kernel(SortBufs s, const unsigned *n_ptr, unsigned 
 }
 
 // shared/global memory of the group this thread belongs to
-__device__ __forceinline__ KswMem dp_mem(const GenoArgs &g, unsigned char *smem, int qlen, int tlen)
+__device__ __forceinline__ KswMem dp_mem(const GenoArgs &g, unsigned char *smem, int qlen, int tlen, int warps_per_cta = DP_WARPS)
 {
 	const int grp = warp_id() * DP_NG + (lane_id() / DP_G);
 	const size_t per = ksw_group_smem(g.ring_cols, g.seq_cap);
-	const size_t gg = (size_t)blockIdx.x * (DP_WARPS * DP_NG) + grp;
+	const size_t gg = (size_t)blockIdx.x * (warps_per_cta * DP_NG) + grp;
 	KswMem m;
 	ksw_group_mem(m, smem + per * grp, lane_id() / DP_G, g.ring_cols); m.region_bytes = (int)per;
 	if (ksw_seq_bytes(qlen, tlen) <= (size_t)g.seq_cap) m.seq_cap = g.seq_cap;
@@ -443,7 +448,7 @@ __device__ __forceinline__ int count_flanked(const uint32_t *cig_rev, int n, int
 
 // AL fallback, step 2: call-site B of kernel 2, one group per task (read vs reference suffix / contig suffix), :343-347
 template <bool UNB>
-__global__ void __launch_bounds__(DP_THREADS, UNB ? KSW_UNB_CTAS : 3) al_kernel(GenoArgs g)
+__global__ void __launch_bounds__(UNB ? 32 * KSW_UNB_WARPS : DP_THREADS, UNB ? KSW_UNB_CTAS : 3) al_kernel(GenoArgs g)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;
@@ -472,7 +477,7 @@ __global__ void __launch_bounds__(DP_THREADS, UNB ? KSW_UNB_CTAS : 3) al_kernel(
 			else { t = g.ctg_codes + cr.seq_off + it.start; tlen = cr.len - it.start; }                                          // ctg_sub :341
 			if (tlen < 0) tlen = 0;
 		}
-		const KswMem M = dp_mem(g, smem_raw, qlen, tlen);
+		const KswMem M = dp_mem(g, smem_raw, qlen, tlen, UNB ? KSW_UNB_WARPS : DP_WARPS);
 		KswOut o;
 		// the whole warp: four alignments in lockstep; reads of up to 160 bases take the row-owned variant (ksw2_rows.cuh)
 		const int rw = UNB ? ksw_rows_pick(valid, qlen, tlen, g.kpB, M) : 0;

@@ -98,11 +98,12 @@ size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 // persistent kernel-2 grids: as many CTAs as fit on the device at this shared-memory size, at most ctx->dp_ctas (the workspaces are sized for that)
-int dp_grid(const idl_ctx *ctx, const void *kernel, size_t smem)
+int dp_grid(const idl_ctx *ctx, const void *kernel, size_t smem, int threads = 256)
 {
 	int nb = 0;
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, smem) != cudaSuccess || nb < 1) nb = 1;
-	return std::min(ctx->dp_ctas, ctx->n_sm * nb);
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+	// the per-group workspaces are sized for dp_ctas CTAs of DP_WARPS warps
+	return std::min(ctx->dp_ctas * 256 / threads, ctx->n_sm * nb);
 }
 
 } // namespace
@@ -383,12 +384,13 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 		CK(cudaEventRecord(L.ev[EV_KMER], L.stream));
 		g.ring_cols = ksw_ring_cols(ncolB);
 		g.seq_cap = (int)round_up(ksw_seq_bytes(max_trim, (int)max_ref), 16);
-		const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(g.ring_cols, g.seq_cap);
+		const int al_warps = P.b_bw < 0 ? KSW_UNB_WARPS : DP_WARPS;
+		const size_t smem = (size_t)al_warps * DP_NG * ksw_group_smem(g.ring_cols, g.seq_cap);
 		if (smem > smem_limit) return IDL_E_CAPACITY;
 		al_prep_kernel<<<ctx->n_sm * 8, 256, 0, L.stream>>>(g);
 		sort_scan_kernel<<<1, 1024, 0, L.stream>>>(sB);
 		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(sB, &a.cnt->n_al_items, 2u, 2 * L.cap_items);
-		if (P.b_bw < 0) al_kernel<true><<<dp_grid(ctx, (const void*)al_kernel<true>, smem), DP_THREADS, smem, L.stream>>>(g); // unbanded (the reference's setting)
+		if (P.b_bw < 0) al_kernel<true><<<dp_grid(ctx, (const void*)al_kernel<true>, smem, 32 * al_warps), 32 * al_warps, smem, L.stream>>>(g); // unbanded (the reference's setting)
 		else al_kernel<false><<<dp_grid(ctx, (const void*)al_kernel<false>, smem), DP_THREADS, smem, L.stream>>>(g);
 		al_vote_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(g);
 		CK(cudaGetLastError()); L.launches += 5;
@@ -548,7 +550,7 @@ struct KswBatchArgs {
 };
 
 template <bool UNB>
-__global__ void __launch_bounds__(DP_THREADS, UNB ? KSW_UNB_CTAS : 3) ksw2_batch_kernel(KswBatchArgs a)
+__global__ void __launch_bounds__(DP_THREADS, UNB ? 2 : 3) ksw2_batch_kernel(KswBatchArgs a) // unbanded: the row-owned variant wants > 80 registers
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;

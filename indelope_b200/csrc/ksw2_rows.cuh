@@ -141,7 +141,6 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 {
 	constexpr int PITCH = 32 * W, PADL = 32 * W;
 	const int lane = lane_id(), gl = lane & 7;
-	const unsigned gmask = 0xffu << (lane & ~7);
 	ksw_reset(out);
 	const int qe = P.q + P.e, gbias = 2 * qe;
 	bool live = valid;
@@ -308,36 +307,53 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 	}
 	if (run) out.cells = (long long)qlen * (long long)tlen;
 	__syncwarp();
-	if (!run) return;
+#ifdef KSW_ROWS_SKIP_TB /* timing experiment only: no CIGAR */
+	return;
+#endif
 	// ksw_backtrack :47-79 from (tlen-1, qlen-1) (never z-dropped: the band is the whole anti-diagonal), is_rot = 1.  Unbanded,
 	// the path never leaves [off, off_end], so no state is forced.  In (r, j) coordinates a step back keeps j or lowers it by
 	// one, so the rows r0 .. r0-31 can only be entered at columns j0-k .. j0: the group prefetches that triangle.
-	int i = tlen - 1, j = qlen - 1, n = 0, ovf = 0;
+	// The four groups of the warp walk in lockstep (full-warp barriers; a group whose path has ended idles): with per-group
+	// barriers the four walkers drift apart and the warp runs them one after the other (measured: 4.1 of 21.0 ms).
+	int i = run ? tlen - 1 : -1, j = run ? qlen - 1 : -1, n = 0, ovf = 0;
 	{
 		uint32_t *tile = (uint32_t*)M.xvuy;
 		uint32_t *cig = M.cig; const int cig_cap = M.cig_cap;
 		int state = 0;
 		unsigned cur_op = 0xffu, cur_len = 0;
 		const long long x_hi = (long long)(qlen + tlen - 1) * PITCH + KSW_PMAT_PAD - 40;
-		while (i >= 0 && j >= 0) {
+		while (__any_sync(FULL_MASK, i >= 0 && j >= 0)) {
+			const bool more = i >= 0 && j >= 0;
 			const int j0 = j, r0 = i + j;
-			for (int row = gl; row < 32; row += 8) {
-				const int rr = r0 - row;
-				if (rr >= 0) {
+			{
+				// all four rows of a thread in flight together: one memory round trip per tile, not four
+				uint32_t wv[4][9]; int shv[4];
+#pragma unroll
+				for (int q4 = 0; q4 < 4; ++q4) {
+					const int row = gl + 8 * q4, rr = r0 - row;
 					long long x0 = (long long)rr * PITCH + (j0 - 31);
 					x0 = x0 < -(long long)(KSW_PMAT_PAD - 4) ? -(long long)(KSW_PMAT_PAD - 4) : (x0 > x_hi ? x_hi : x0);
 					const uint32_t *src = (const uint32_t*)(pmat + (x0 & ~3LL));
-					const int sh = 8 * (int)(x0 & 3);
-					const int k0 = (31 - row) >> 2;
-					uint32_t wv[9];
+					shv[q4] = 8 * (int)(x0 & 3);
+					const int k0 = (31 - row) >> 2; // row r0 - row can only be entered at columns j0 - row .. j0
+					const bool ld = more && rr >= 0;
 #pragma unroll
-					for (int k = 0; k < 9; ++k) wv[k] = k >= k0 ? src[k] : 0u;
+					for (int k = 0; k < 9; ++k) wv[q4][k] = (ld && k >= k0) ? src[k] : 0u;
+				}
 #pragma unroll
-					for (int k = 0; k < 8; ++k) if (k >= k0) tile[row * 8 + k] = __funnelshift_r(wv[k], wv[k + 1], sh);
+				for (int q4 = 0; q4 < 4; ++q4) {
+					const int row = gl + 8 * q4, k0 = (31 - row) >> 2;
+#pragma unroll
+					for (int k = 0; k < 8; ++k) if (k >= k0) tile[row * 8 + k] = __funnelshift_r(wv[q4][k], wv[q4][k + 1], shv[q4]);
 				}
 			}
-			__syncwarp(gmask);
+			__syncwarp();
+#ifdef KSW_ROWS_TB_NOWALK /* timing experiment only */
+			if (gl == 0) { if (tile[gl] == 0x12345u) n++; if (j >= 16) { i -= 16; j -= 16; } else { i -= 32; } }
+			if (0) {
+#else
 			if (gl == 0) {
+#endif
 				const uint8_t *tbp = (const uint8_t*)tile;
 				while (i >= 0 && j >= 0 && i + j > r0 - 32) {
 					const int r = i + j;
@@ -356,8 +372,8 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 					}
 				}
 			}
-			i = __shfl_sync(gmask, i, 0, 8); j = __shfl_sync(gmask, j, 0, 8);
-			__syncwarp(gmask);
+			i = __shfl_sync(FULL_MASK, i, lane & ~7); j = __shfl_sync(FULL_MASK, j, lane & ~7);
+			__syncwarp();
 		}
 		if (gl == 0) {
 			if (i >= 0) {
@@ -371,11 +387,11 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 			if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; }
 		}
 	}
-	n = __shfl_sync(gmask, n, 0, 8);
-	ovf = __shfl_sync(gmask, ovf, 0, 8);
+	n = __shfl_sync(FULL_MASK, n, lane & ~7);
+	ovf = __shfl_sync(FULL_MASK, ovf, lane & ~7);
 	out.n_cigar = n;
 	if (ovf) out.status = KSW_ST_CIGCAP;
-	__syncwarp(gmask);
+	__syncwarp();
 }
 
 // which variant a warp takes: every valid group votes the W it needs (0: no alignment, 99: not served), the warp runs the

@@ -239,7 +239,6 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 	static_assert(G == 8, "the clear-ahead step deals 8 words to the 8 threads of a group");
 	const int lane = lane_id();
 	const int gl = lane & (G - 1);
-	const unsigned gmask = ((1u << G) - 1u) << (lane & ~(G - 1));
 	ksw_reset(out);
 	const int qe = P.q + P.e;
 	int min_sc = P.mismatch < 0 ? P.mismatch : 0;
@@ -521,47 +520,56 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 	}
 	if (g_high) out.status = KSW_ST_HCAP;
 	__syncwarp();
-	if (!run) return;
-	// backtrack :380-385 -> ksw_backtrack :47-79 (is_rot = 1, left-aligned gaps)
-	int i, j;
-	if (!out.zdropped) { i = tlen - 1; j = qlen - 1; }
-	else if (out.max_t >= 0 && out.max_q >= 0) { i = out.max_t; j = out.max_q; }
-	else return;
+	// backtrack :380-385 -> ksw_backtrack :47-79 (is_rot = 1, left-aligned gaps).  The four groups of the warp walk in
+	// lockstep (full-warp barriers; a group without a path, or whose path has ended, idles): with per-group barriers the
+	// walkers drift apart and the warp runs them one after the other.
+	int i = -1, j = -1;
+	if (run) {
+		if (!out.zdropped) { i = tlen - 1; j = qlen - 1; }
+		else if (out.max_t >= 0 && out.max_q >= 0) { i = out.max_t; j = out.max_q; }
+	}
 	int n = 0, ovf = 0;
 	{
 		// The walk itself is serial (one state machine), but its loads are not: before every stretch of <= 32 diagonals the
 		// group prefetches the 32 x 32 tile of p[][] the path can touch (row r0-k can only be entered at columns
 		// i0-k .. i0) into shared memory (the sequence staging area is free by now), so the walker runs on shared-memory
-		// latency instead of one L2/HBM round trip per step.
+		// latency instead of one L2/HBM round trip per step.  The four rows a thread fetches are in flight together.
 		uint32_t *tile = (uint32_t*)M.xvuy; // 32 rows of 8 words; the rings are dead by now
 		uint32_t *cig = M.cig; const int cig_cap = M.cig_cap;
 		int state = 0;
 		unsigned cur_op = 0xffu, cur_len = 0;
-		while (i >= 0 && j >= 0) {
+		const long long x_hi = (long long)(qlen + tlen - 1) * pitch + KSW_PMAT_PAD - 40;
+		while (__any_sync(FULL_MASK, i >= 0 && j >= 0)) {
+			const bool more = i >= 0 && j >= 0;
 			const int i0 = i, r0 = i + j;
-			for (int row = gl; row < 32; row += G) {
-				const int rr = r0 - row;
-				if (rr >= 0) {
-					int s0, e0;
-					ksw_band(rr, qlen, tlen, w, s0, e0, UNB);
+			{
+				uint32_t wv[4][9]; int shv[4];
+#pragma unroll
+				for (int q4 = 0; q4 < 4; ++q4) {
+					const int row = gl + G * q4, rr = r0 - row;
+					int s0 = 0, e0 = 0;
+					if (more && rr >= 0) ksw_band(rr, qlen, tlen, w, s0, e0, UNB);
 					long long x0 = (long long)rr * pitch + (i0 - 31 - (UNB ? (s0 & ~3) : (s0 & ~15))); // byte offset of column i0-31 of row rr
 					// a row that holds a readable entry has x0 within 31 bytes of the matrix; anything further out is never read
 					// (the walk is forced there), so clamping keeps the prefetch inside this alignment's workspace
-					const long long x_hi = (long long)(qlen + tlen - 1) * pitch + KSW_PMAT_PAD - 40;
 					x0 = x0 < -(long long)(KSW_PMAT_PAD - 4) ? -(long long)(KSW_PMAT_PAD - 4) : (x0 > x_hi ? x_hi : x0);
 					const uint32_t *src = (const uint32_t*)(pmat + (x0 & ~3LL));
-					const int sh = 8 * (int)(x0 & 3);
+					shv[q4] = 8 * (int)(x0 & 3);
 					// row r0 - row can only be entered at columns i0 - row .. i0: fetch those bytes only (the left part of the
 					// tile row stays stale and is never read), which keeps most rows inside one DRAM sector
 					const int k0 = (31 - row) >> 2;
-					uint32_t wv[9];
+					const bool ld = more && rr >= 0;
 #pragma unroll
-					for (int k = 0; k < 9; ++k) wv[k] = k >= k0 ? src[k] : 0u; // predicated loads, all in flight together
+					for (int k = 0; k < 9; ++k) wv[q4][k] = (ld && k >= k0) ? src[k] : 0u; // predicated loads, all in flight together
+				}
 #pragma unroll
-					for (int k = 0; k < 8; ++k) if (k >= k0) tile[row * 8 + k] = __funnelshift_r(wv[k], wv[k + 1], sh);
+				for (int q4 = 0; q4 < 4; ++q4) {
+					const int row = gl + G * q4, k0 = (31 - row) >> 2;
+#pragma unroll
+					for (int k = 0; k < 8; ++k) if (k >= k0) tile[row * 8 + k] = __funnelshift_r(wv[q4][k], wv[q4][k + 1], shv[q4]);
 				}
 			}
-			__syncwarp(gmask);
+			__syncwarp();
 			if (gl == 0) {
 				const uint8_t *tb = (const uint8_t*)tile;
 				while (i >= 0 && j >= 0 && i + j > r0 - 32) {
@@ -588,8 +596,8 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 					}
 				}
 			}
-			i = __shfl_sync(gmask, i, 0, G); j = __shfl_sync(gmask, j, 0, G);
-			__syncwarp(gmask);
+			i = __shfl_sync(FULL_MASK, i, lane & ~(G - 1)); j = __shfl_sync(FULL_MASK, j, lane & ~(G - 1));
+			__syncwarp();
 		}
 		if (gl == 0) {
 			// the two trailing pushes (:73-74) merge with an equal pending op exactly as ksw_push_cigar does
@@ -604,11 +612,11 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 			if (cur_len) { if (n < cig_cap) cig[n++] = cur_len << 4 | cur_op; else ovf = 1; }
 		}
 	}
-	n = __shfl_sync(gmask, n, 0, G);
-	ovf = __shfl_sync(gmask, ovf, 0, G);
+	n = __shfl_sync(FULL_MASK, n, lane & ~(G - 1));
+	ovf = __shfl_sync(FULL_MASK, ovf, lane & ~(G - 1));
 	out.n_cigar = n;
 	if (ovf) out.status = KSW_ST_CIGCAP;
-	__syncwarp(gmask);
+	__syncwarp();
 }
 
 // query-offset-limited view of the CIGAR (the `cigar` iterator of src/ksw2/ksw2.nim:22-33) over the REVERSED scratch:

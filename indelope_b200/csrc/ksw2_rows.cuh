@@ -247,7 +247,7 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 				if (((jt >> 2) & 7) == gl) {
 					uint32_t w2 = 0;
 #pragma unroll
-					for (int s = 0; s < W; ++s) if (s == (jt >> 5)) w2 = (jt & 2) ? gy[s] : gx[s];
+					for (int s = 0; s < W; ++s) w2 |= ((jt & 2) ? gy[s] : gx[s]) & (0u - (uint32_t)(s == (jt >> 5))); // constant indices only
 					const int hen = (int)((w2 >> (16 * (jt & 1))) & 0xffffu) - goff;
 					if (hen > mte) { mte = hen; mte_r = r; }
 				}
@@ -255,7 +255,7 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 			if (own_last && act && r >= jl) { // r - st0 == qlen-1: H[st0] is the cell of the last row (:353-354)
 				uint32_t w2 = 0;
 #pragma unroll
-				for (int s = 0; s < W; ++s) if (s == (jl >> 5)) w2 = (jl & 2) ? gy[s] : gx[s];
+				for (int s = 0; s < W; ++s) w2 |= ((jl & 2) ? gy[s] : gx[s]) & (0u - (uint32_t)(s == (jl >> 5)));
 				const int h = (int)((w2 >> (16 * (jl & 1))) & 0xffffu) - goff;
 				if (h > mqe) { mqe = h; mqe_t = r - jl; }
 				if (r == nr - 1) score = h;

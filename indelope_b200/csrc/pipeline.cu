@@ -550,7 +550,7 @@ struct KswBatchArgs {
 };
 
 template <bool UNB>
-__global__ void __launch_bounds__(DP_THREADS, UNB ? 2 : 3) ksw2_batch_kernel(KswBatchArgs a) // unbanded: the row-owned variant wants > 80 registers
+__global__ void __launch_bounds__(DP_THREADS, UNB ? 2 : 3) ksw2_batch_kernel(KswBatchArgs a) // unbanded: 8 warps x 2 CTAs at 122 registers (uniform shapes: 774 GCUPS at 150x700 against 745 with al_kernel's 5 x 4)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;
@@ -617,12 +617,13 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 	a.ring_cols = ksw_ring_cols(max_ncol);
 	a.p_cap = round_up(max_p + 2 * KSW_PMAT_PAD + 64, 256); a.cig_cap = max_q + max_t + 8; a.cigar_cap = (unsigned)cigar_cap;
 	a.seq_cap = (int)round_up(ksw_seq_bytes(max_q, max_t), 16);
-	const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(a.ring_cols, a.seq_cap);
+	const int wpc = DP_WARPS; // warps per CTA
+	const size_t smem = (size_t)wpc * DP_NG * ksw_group_smem(a.ring_cols, a.seq_cap);
 	if (smem > 200 * 1024) return IDL_E_CAPACITY;
 	const void *kfn = w < 0 ? (const void*)ksw2_batch_kernel<true> : (const void*)ksw2_batch_kernel<false>; // unbanded: the lean variant of kernel 2
 	cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-	const size_t per_cta = (size_t)DP_WARPS * DP_NG;
-	const int ctas = (int)std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)dp_grid(ctx, kfn, smem));
+	const size_t per_cta = (size_t)wpc * DP_NG;
+	const int ctas = (int)std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)dp_grid(ctx, kfn, smem, 32 * wpc));
 	const size_t nwarps = (size_t)ctas * per_cta; // groups, each with its own workspace
 	const size_t qbytes = q_off[n], tbytes = t_off[n];
 	DevBuf dq, dt, dqo, dto, dout, dcig, dcoff, dmisc, dp, dscr;
@@ -641,7 +642,7 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 		a.next = (unsigned*)dmisc.p; a.cig_used = (unsigned*)dmisc.p + 1; a.pmat = (uint8_t*)dp.p; a.cig_scratch = (uint32_t*)dscr.p;
 		CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 		CK(cudaEventRecord(e0, st));
-		if (w < 0) ksw2_batch_kernel<true><<<ctas, DP_THREADS, smem, st>>>(a);
+		if (w < 0) ksw2_batch_kernel<true><<<ctas, 32 * wpc, smem, st>>>(a);
 		else ksw2_batch_kernel<false><<<ctas, DP_THREADS, smem, st>>>(a);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(e1, st));

@@ -186,28 +186,32 @@ def main():
     dev_ms = sum(s["ms_total"] for s in steps)
     launches = sum(s["kernel_launches"] for s in steps)
 
-    # ---- leg 2: end to end through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H of every result
-    def e2e_step():
-        inflight, d2h, nl = [], 0, 0
-        for i, (b, _) in enumerate(slices):
-            if len(inflight) >= P.n_streams:
-                t = inflight.pop(0); r = ctx.wait(t).contents; d2h += result_bytes(r); nl += r.kernel_launches; ctx.release(t)
-            inflight.append(ctx.submit(b))
-        while inflight:
-            t = inflight.pop(0); r = ctx.wait(t).contents; d2h += result_bytes(r); nl += r.kernel_launches; ctx.release(t)
-        return d2h, nl
-
+    # ---- leg 2: end to end through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H of every result.  The caller
+    # streams batches as the reference-facing API intends (idl_submit / idl_wait with tickets, `n_streams` batches in flight):
+    # the pipeline runs on across step boundaries and is drained once, inside the timed region, before the closing barrier.
     def result_bytes(r):
         return (r.n_regions * C.sizeof(abi.RegionResult) + r.n_contigs * C.sizeof(abi.ContigResult) + r.n_alns * C.sizeof(abi.AlnResult) +
                 r.n_events * C.sizeof(abi.EventResult) + r.n_cigar_ops * 4 + r.n_contig_bases)
-    for _ in range(args.warmup):
-        e2e_step()
+
+    def e2e_steps(k):
+        inflight, d2h, nl, dev = [], 0, 0, 0.0
+        def retire():
+            nonlocal d2h, nl, dev
+            t = inflight.pop(0); r = ctx.wait(t).contents; d2h += result_bytes(r); nl += r.kernel_launches; dev += r.ms_total; ctx.release(t)
+        for _ in range(k):
+            for b, _ in slices:
+                if len(inflight) >= P.n_streams:
+                    retire()
+                inflight.append(ctx.submit(b))
+        while inflight:
+            retire()
+        return d2h, nl, dev
+    e2e_steps(args.warmup)
     barrier()
     t0 = time.perf_counter()
-    d2h_bytes = 0
-    for _ in range(args.steps):
-        d2h_bytes, nl = e2e_step()
-        launches += nl
+    d2h_total, nl, e2e_dev_ms = e2e_steps(args.steps)
+    d2h_bytes = d2h_total // max(1, args.steps)
+    launches += nl
     barrier()
     e2e_s = time.perf_counter() - t0
     sampler.stop_flag = True; sampler.join(timeout=2)
@@ -260,7 +264,8 @@ def main():
             "ksw2_gcups_site_a": avg["dp_cells_a"] / (avg["ms_align"] / 1000.0) / 1e9 if avg["ms_align"] > 0 else None,
             "kmer_gbs": avg["kmer_bytes"] / (avg["ms_genotype"] / 1000.0) / 1e9 if avg["ms_genotype"] > 0 else None,
             "config": {"workload": workload_name(args, cfg), "regions_per_gpu": n_regions, "reads_per_gpu": n_reads, "sharding": "interval shard per rank, no collective",
-                       "l2": "inputs (%.0f MB packed) exceed the 126 MB L2; no explicit flush" % (big_bytes / 1e6), "e2e_batches": len(slices), "streams": P.n_streams},
+                       "l2": "inputs (%.0f MB packed) exceed the 126 MB L2; no explicit flush" % (big_bytes / 1e6), "e2e_batches": len(slices), "streams": P.n_streams,
+                       "e2e_pipelining": "batches streamed through idl_submit/idl_wait across step boundaries, %d in flight, drained once inside the timed region" % P.n_streams},
             "kernel_ms": kern,
             "work": {k: avg[k] for k in ("offsets_tested", "dp_cells_a", "dp_cells_b", "dp_a", "dp_b", "kmer_reads", "kmer_bytes", "al_events", "n_contigs", "n_alns", "n_events")},
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "algorithmic_bytes": alg[dom],
@@ -268,7 +273,7 @@ def main():
                          "note": "integer kernel bound by the ALU pipe, not by HBM: one backtrack byte per DP cell is all it must move; `alu` is the roof that binds (DESIGN.md)",
                          "alu": alu},
             "e2e": {"value": e2e_val, "unit": "regions/s", "h2d_bytes_per_step": sum(b for _, b in slices), "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_ms_max / K},
+                    "ms_per_step": e2e_ms_max / K, "kernel_ms_per_step": e2e_dev_ms / K},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -50,7 +50,7 @@ struct HostBuf {
 	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-enum { EV_START = 0, EV_H2D, EV_ASM, EV_ALN, EV_KMER, EV_AL, EV_END, EV_N };
+enum { EV_START = 0, EV_H2D, EV_ASM, EV_ALN, EV_KMER, EV_AL, EV_END, EV_IN, EV_N };
 
 struct Lane {
 	cudaStream_t stream = nullptr;
@@ -78,6 +78,7 @@ struct Lane {
 struct idl_ctx {
 	int device = 0; idl_params P; int n_sm = 148;
 	std::vector<Lane> lanes;
+	cudaStream_t compute = nullptr; // every lane's kernels run here, in submission order; the lanes' own streams carry the copies
 	uint64_t next_ticket = 1;
 	int asm_ctas = 0, dp_ctas = 0, ns = 0, nw = 0;
 	int cig_cap = 2048;
@@ -173,6 +174,11 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	ctx->asm_ctas = ctx->n_sm * (ea && atoi(ea) > 0 ? atoi(ea) : 4); // CTAs of each assembler launch (8 regions per CTA in the warp variant)
 	ctx->dp_ctas = ctx->n_sm * (ed && atoi(ed) > 0 ? atoi(ed) : 3); // upper bound; every launch asks the occupancy calculator
 	ctx->lanes.resize((size_t)p->n_streams);
+	{
+		// IDL_OVERLAP_KERNELS=1: the kernels of a batch run on its lane's stream and may share the SMs with another batch's
+		const char *eo = getenv("IDL_OVERLAP_KERNELS");
+		if (!(eo && *eo == '1') && cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess) { idl_destroy(ctx); return IDL_E_CUDA; }
+	}
 	for (Lane &L : ctx->lanes) {
 		if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { idl_destroy(ctx); return IDL_E_CUDA; }
 		for (auto &ev : L.ev) if (cudaEventCreate(&ev) != cudaSuccess) { idl_destroy(ctx); return IDL_E_CUDA; }
@@ -191,6 +197,7 @@ void idl_destroy(idl_ctx *ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
+	if (ctx->compute) { cudaStreamSynchronize(ctx->compute); }
 	for (Lane &L : ctx->lanes) {
 		if (L.stream) cudaStreamSynchronize(L.stream);
 		for (DevBuf *b : {&L.region, &L.read, &L.seq2, &L.seqn, &L.ref2, &L.refn, &L.rres, &L.cres, &L.ares, &L.eres, &L.cigar, &L.ctg_ascii, &L.ctg_codes,
@@ -201,6 +208,7 @@ void idl_destroy(idl_ctx *ctx)
 		for (auto &ev : L.ev) if (ev) cudaEventDestroy(ev);
 		if (L.stream) cudaStreamDestroy(L.stream);
 	}
+	if (ctx->compute) cudaStreamDestroy(ctx->compute);
 	delete ctx;
 }
 
@@ -324,9 +332,13 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 	CK(L.pmat.ensure(n_groups * p_cap));
 	CK(L.cig_scratch.ensure(n_groups * (size_t)ctx->cig_cap * 4));
 	CK(L.seq_spill.ensure(n_groups * (size_t)seq_spill_cap));
-	if (record_start) { CK(cudaEventRecord(L.ev[EV_START], L.stream)); CK(cudaEventRecord(L.ev[EV_H2D], L.stream)); }
-	CK(cudaMemsetAsync(L.cnt.p, 0, sizeof(DevCounters), L.stream));
-	CK(cudaMemsetAsync(L.sort_misc.p, 0, 6 * SORT_BUCKETS * sizeof(unsigned), L.stream));
+	// copies travel on the lane's stream, kernels on the context's compute stream: batches overlap their transfers with each
+	// other's kernels, and the persistent kernels of two batches never compete for the SMs
+	cudaStream_t cs = ctx->compute ? ctx->compute : L.stream;
+	if (cs != L.stream) { CK(cudaEventRecord(L.ev[EV_IN], L.stream)); CK(cudaStreamWaitEvent(cs, L.ev[EV_IN], 0)); }
+	if (record_start) { CK(cudaEventRecord(L.ev[EV_START], cs)); CK(cudaEventRecord(L.ev[EV_H2D], cs)); }
+	CK(cudaMemsetAsync(L.cnt.p, 0, sizeof(DevCounters), cs));
+	CK(cudaMemsetAsync(L.sort_misc.p, 0, 6 * SORT_BUCKETS * sizeof(unsigned), cs));
 	L.launches = 0;
 	SortBufs sA, sB;
 	sA.hist = (unsigned*)L.sort_misc.p; sA.start = sA.hist + SORT_BUCKETS; sA.cursor = sA.start + SORT_BUCKETS; sA.keys = (uint16_t*)L.keysA.p; sA.order = (unsigned*)L.orderA.p;
@@ -345,15 +357,15 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 	a.cnt = (DevCounters*)L.cnt.p;
 	if (n_small && (P.stages & IDL_STAGE_ASSEMBLE)) { // one warp per region
 		a.small = 1; a.ns = ASM_SMALL_NS; a.planes = (uint32_t*)L.planes_small.p; a.sup = (uint16_t*)L.sup_small.p;
-		assemble_kernel<32><<<small_ctas, ASM_THREADS, 8 * asm_smem_bytes(ASM_SMALL_NS, ctx->nw, 32), L.stream>>>(a);
+		assemble_kernel<32><<<small_ctas, ASM_THREADS, 8 * asm_smem_bytes(ASM_SMALL_NS, ctx->nw, 32), cs>>>(a);
 		CK(cudaGetLastError()); L.launches++;
 	}
 	if (n_big && (P.stages & IDL_STAGE_ASSEMBLE)) { // one CTA per region
 		a.small = 0; a.ns = ctx->ns; a.planes = (uint32_t*)L.planes.p; a.sup = (uint16_t*)L.sup.p;
-		assemble_kernel<256><<<big_ctas, ASM_THREADS, asm_smem_bytes(ctx->ns, ctx->nw, 256), L.stream>>>(a);
+		assemble_kernel<256><<<big_ctas, ASM_THREADS, asm_smem_bytes(ctx->ns, ctx->nw, 256), cs>>>(a);
 		CK(cudaGetLastError()); L.launches++;
 	}
-	CK(cudaEventRecord(L.ev[EV_ASM], L.stream));
+	CK(cudaEventRecord(L.ev[EV_ASM], cs));
 
 	GenoArgs g; memset(&g, 0, sizeof g);
 	g.region = a.region; g.read = a.read; g.seq2 = a.seq2; g.seqn = a.seqn; g.refcodes = a.refcodes; g.ctg_codes = a.ctg_codes;
@@ -372,30 +384,31 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 		g.seq_cap = (int)round_up(ksw_seq_bytes(std::min(P.max_contig_len, 1024), (int)max_ref), 16); // longer contigs stage in the spill area
 		const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(g.ring_cols, g.seq_cap);
 		if (smem > smem_limit) return IDL_E_CAPACITY;
-		sort_scan_kernel<<<1, 1024, 0, L.stream>>>(sA);
-		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(sA, &a.cnt->n_alns, 1u, L.cap_alns);
-		align_kernel<<<dp_grid(ctx, (const void*)align_kernel, smem), DP_THREADS, smem, L.stream>>>(g);
+		sort_scan_kernel<<<1, 1024, 0, cs>>>(sA);
+		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, cs>>>(sA, &a.cnt->n_alns, 1u, L.cap_alns);
+		align_kernel<<<dp_grid(ctx, (const void*)align_kernel, smem), DP_THREADS, smem, cs>>>(g);
 		CK(cudaGetLastError()); L.launches += 3;
 	}
-	CK(cudaEventRecord(L.ev[EV_ALN], L.stream));
+	CK(cudaEventRecord(L.ev[EV_ALN], cs));
 	if (b->n_regions > 0 && (P.stages & IDL_STAGE_GENOTYPE) && (P.stages & IDL_STAGE_ALIGN)) {
-		kmer_kernel<<<ctx->n_sm * 8, KMER_THREADS, 0, L.stream>>>(g);
+		kmer_kernel<<<ctx->n_sm * 8, KMER_THREADS, 0, cs>>>(g);
 		CK(cudaGetLastError()); L.launches++;
-		CK(cudaEventRecord(L.ev[EV_KMER], L.stream));
+		CK(cudaEventRecord(L.ev[EV_KMER], cs));
 		g.ring_cols = ksw_ring_cols(ncolB);
 		g.seq_cap = (int)round_up(ksw_seq_bytes(max_trim, (int)max_ref), 16);
 		const int al_warps = P.b_bw < 0 ? KSW_UNB_WARPS : DP_WARPS;
 		const size_t smem = (size_t)al_warps * DP_NG * ksw_group_smem(g.ring_cols, g.seq_cap);
 		if (smem > smem_limit) return IDL_E_CAPACITY;
-		al_prep_kernel<<<ctx->n_sm * 8, 256, 0, L.stream>>>(g);
-		sort_scan_kernel<<<1, 1024, 0, L.stream>>>(sB);
-		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(sB, &a.cnt->n_al_items, 2u, 2 * L.cap_items);
-		if (P.b_bw < 0) al_kernel<true><<<dp_grid(ctx, (const void*)al_kernel<true>, smem, 32 * al_warps), 32 * al_warps, smem, L.stream>>>(g); // unbanded (the reference's setting)
-		else al_kernel<false><<<dp_grid(ctx, (const void*)al_kernel<false>, smem), DP_THREADS, smem, L.stream>>>(g);
-		al_vote_kernel<<<ctx->n_sm * 4, 256, 0, L.stream>>>(g);
+		al_prep_kernel<<<ctx->n_sm * 8, 256, 0, cs>>>(g);
+		sort_scan_kernel<<<1, 1024, 0, cs>>>(sB);
+		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, cs>>>(sB, &a.cnt->n_al_items, 2u, 2 * L.cap_items);
+		if (P.b_bw < 0) al_kernel<true><<<dp_grid(ctx, (const void*)al_kernel<true>, smem, 32 * al_warps), 32 * al_warps, smem, cs>>>(g); // unbanded (the reference's setting)
+		else al_kernel<false><<<dp_grid(ctx, (const void*)al_kernel<false>, smem), DP_THREADS, smem, cs>>>(g);
+		al_vote_kernel<<<ctx->n_sm * 4, 256, 0, cs>>>(g);
 		CK(cudaGetLastError()); L.launches += 5;
-	} else CK(cudaEventRecord(L.ev[EV_KMER], L.stream));
-	CK(cudaEventRecord(L.ev[EV_AL], L.stream));
+	} else CK(cudaEventRecord(L.ev[EV_KMER], cs));
+	CK(cudaEventRecord(L.ev[EV_AL], cs));
+	if (cs != L.stream) CK(cudaStreamWaitEvent(L.stream, L.ev[EV_AL], 0));
 	CK(L.h_cnt.ensure(sizeof(DevCounters)));
 	CK(cudaMemcpyAsync(L.h_cnt.p, L.cnt.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, L.stream));
 	CK(cudaEventRecord(L.ev[EV_END], L.stream));

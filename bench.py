@@ -218,10 +218,10 @@ def main():
 
     # max over ranks
     tt = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(n_regions), float(n_reads)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n_regions), float(n_reads), float(sum(b for _, b in slices)), float(d2h_bytes)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max = tt.tolist(); regions_all, reads_all = tot.tolist()
+    dev_ms_max, e2e_ms_max = tt.tolist(); regions_all, reads_all, h2d_all, d2h_all = tot.tolist()  # whole job: summed over ranks
 
     if rank == 0:
         K = args.steps
@@ -272,7 +272,7 @@ def main():
                          "peak_source": peak_src,
                          "note": "integer kernel bound by the ALU pipe, not by HBM: one backtrack byte per DP cell is all it must move; `alu` is the roof that binds (DESIGN.md)",
                          "alu": alu},
-            "e2e": {"value": e2e_val, "unit": "regions/s", "h2d_bytes_per_step": sum(b for _, b in slices), "d2h_bytes_per_step": d2h_bytes,
+            "e2e": {"value": e2e_val, "unit": "regions/s", "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                     "ms_per_step": e2e_ms_max / K, "kernel_ms_per_step": e2e_dev_ms / K},
             "gpu_launches": int(launches),
             "clocks": clocks,

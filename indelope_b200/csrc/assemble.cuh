@@ -55,6 +55,8 @@ struct AsmArgs {
 	SortBufs sortA;
 	DevCounters *cnt;
 	int small;                        // 1: this launch takes the regions with <= ASM_SMALL_READS reads, 0: the others
+	const unsigned *order;            // regions by read count, deepest first: the work of a region grows faster than its reads,
+	                                  // so the persistent grid ends on the cheapest regions instead of idling behind a deep one
 };
 
 struct AsmS { // carved out of dynamic shared memory
@@ -525,8 +527,9 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 		asm_bar<NT>();
 		if (tid == 0) A.s.sc[SC_REGION] = (int)atomicAdd(args.small ? &args.cnt->region_next : &args.cnt->region_next2, 1u);
 		asm_bar<NT>();
-		const unsigned rg = (unsigned)A.s.sc[SC_REGION];
-		if (rg >= args.n_regions) break;
+		const unsigned qi = (unsigned)A.s.sc[SC_REGION];
+		if (qi >= args.n_regions) break;
+		const unsigned rg = args.order[qi];
 		const idl_region R = args.region[rg];
 		if ((R.n_reads <= ASM_SMALL_READS) != (args.small != 0)) continue; // the other launch assembles this region
 		// reset the slot allocator; detect non-ACGT bases in this region's reads and window

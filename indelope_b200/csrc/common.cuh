@@ -23,6 +23,7 @@ struct DevCounters {
 	unsigned long long al_pack;    // (#AL events << 40) | total AL work items
 	unsigned int overflow;         // result pool overflow flags
 	unsigned long long offsets_tested, dp_cells_a, dp_cells_b, dp_a, dp_b, kmer_reads, kmer_bytes, al_events;
+	unsigned int n_regions_in, pad_;  // regions of the batch (written by region_key_kernel: the count sort_scatter_kernel reads)
 };
 
 // alignment scoring/band parameters of one call-site (src/ksw2/ksw2.nim:142,151-157)

@@ -93,6 +93,16 @@ __global__ void sort_scatter_kernel(SortBufs s, const unsigned *n_ptr, unsigned 
 	}
 }
 
+// sort key of the assembler's queue: the read count of a region
+__global__ void region_key_kernel(SortBufs s, const idl_region *region, unsigned n, DevCounters *cnt)
+{
+	if (blockIdx.x == 0 && threadIdx.x == 0) cnt->n_regions_in = n;
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const unsigned k = region[i].n_reads < SORT_BUCKETS - 1 ? region[i].n_reads : SORT_BUCKETS - 1;
+		s.keys[i] = (uint16_t)k; atomicAdd(&s.hist[k], 1u);
+	}
+}
+
 // shared/global memory of the group this thread belongs to
 __device__ __forceinline__ KswMem dp_mem(const GenoArgs &g, unsigned char *smem, int qlen, int tlen, int warps_per_cta = DP_WARPS)
 {

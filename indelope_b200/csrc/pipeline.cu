@@ -58,7 +58,7 @@ struct Lane {
 	// device batch
 	DevBuf region, read, seq2, seqn, ref2, refn;
 	// device results and intermediates
-	DevBuf rres, cres, ares, eres, cigar, ctg_ascii, ctg_codes, ctg_sup, refcodes, al_list, al_items, al_res, sort_misc, keysA, orderA, keysB, orderB, cnt;
+	DevBuf rres, cres, ares, eres, cigar, ctg_ascii, ctg_codes, ctg_sup, refcodes, al_list, al_items, al_res, sort_misc, keysA, orderA, keysB, orderB, keysR, orderR, cnt;
 	// workspaces
 	DevBuf planes, sup, planes_small, sup_small, pmat, cig_scratch, seq_spill;
 	// pinned host results
@@ -201,7 +201,7 @@ void idl_destroy(idl_ctx *ctx)
 	for (Lane &L : ctx->lanes) {
 		if (L.stream) cudaStreamSynchronize(L.stream);
 		for (DevBuf *b : {&L.region, &L.read, &L.seq2, &L.seqn, &L.ref2, &L.refn, &L.rres, &L.cres, &L.ares, &L.eres, &L.cigar, &L.ctg_ascii, &L.ctg_codes,
-		                  &L.ctg_sup, &L.refcodes, &L.al_list, &L.al_items, &L.al_res, &L.sort_misc, &L.keysA, &L.orderA, &L.keysB, &L.orderB, &L.cnt, &L.planes, &L.sup,
+		                  &L.ctg_sup, &L.refcodes, &L.al_list, &L.al_items, &L.al_res, &L.sort_misc, &L.keysA, &L.orderA, &L.keysB, &L.orderB, &L.keysR, &L.orderR, &L.cnt, &L.planes, &L.sup,
 		                  &L.planes_small, &L.sup_small, &L.pmat, &L.cig_scratch, &L.seq_spill})
 			b->release();
 		for (HostBuf *b : {&L.h_rres, &L.h_cres, &L.h_ares, &L.h_eres, &L.h_cigar, &L.h_seq, &L.h_sup, &L.h_cnt}) b->release();
@@ -301,7 +301,8 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 	CK(L.cnt.ensure(sizeof(DevCounters)));
 	L.cap_items = (unsigned)std::min<size_t>(8 * b->n_reads + 1024, 0x3fffffffu); // AL items: a read takes part in few AL events
 	CK(L.al_items.ensure((size_t)L.cap_items * sizeof(AlItem))); CK(L.al_res.ensure((size_t)L.cap_items * 2 + 16));
-	CK(L.sort_misc.ensure(6 * SORT_BUCKETS * sizeof(unsigned)));
+	CK(L.sort_misc.ensure(9 * SORT_BUCKETS * sizeof(unsigned)));
+	CK(L.keysR.ensure((size_t)b->n_regions * 2 + 16)); CK(L.orderR.ensure((size_t)b->n_regions * 4 + 16));
 	CK(L.keysA.ensure((size_t)L.cap_alns * 2 + 16)); CK(L.orderA.ensure((size_t)L.cap_alns * 4 + 16));
 	CK(L.keysB.ensure((size_t)L.cap_items * 4 + 16)); CK(L.orderB.ensure((size_t)L.cap_items * 8 + 16));
 	// workspaces
@@ -338,11 +339,13 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 	if (cs != L.stream) { CK(cudaEventRecord(L.ev[EV_IN], L.stream)); CK(cudaStreamWaitEvent(cs, L.ev[EV_IN], 0)); }
 	if (record_start) { CK(cudaEventRecord(L.ev[EV_START], cs)); CK(cudaEventRecord(L.ev[EV_H2D], cs)); }
 	CK(cudaMemsetAsync(L.cnt.p, 0, sizeof(DevCounters), cs));
-	CK(cudaMemsetAsync(L.sort_misc.p, 0, 6 * SORT_BUCKETS * sizeof(unsigned), cs));
+	CK(cudaMemsetAsync(L.sort_misc.p, 0, 9 * SORT_BUCKETS * sizeof(unsigned), cs));
 	L.launches = 0;
 	SortBufs sA, sB;
 	sA.hist = (unsigned*)L.sort_misc.p; sA.start = sA.hist + SORT_BUCKETS; sA.cursor = sA.start + SORT_BUCKETS; sA.keys = (uint16_t*)L.keysA.p; sA.order = (unsigned*)L.orderA.p;
 	sB.hist = sA.cursor + SORT_BUCKETS; sB.start = sB.hist + SORT_BUCKETS; sB.cursor = sB.start + SORT_BUCKETS; sB.keys = (uint16_t*)L.keysB.p; sB.order = (unsigned*)L.orderB.p;
+	SortBufs sR;
+	sR.hist = sB.cursor + SORT_BUCKETS; sR.start = sR.hist + SORT_BUCKETS; sR.cursor = sR.start + SORT_BUCKETS; sR.keys = (uint16_t*)L.keysR.p; sR.order = (unsigned*)L.orderR.p;
 
 	AsmArgs a; memset(&a, 0, sizeof a);
 	a.region = (const idl_region*)L.region.p; a.read = (const idl_read*)L.read.p;
@@ -355,6 +358,13 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 	a.cap_contigs = L.cap_contigs; a.cap_bases = L.cap_bases; a.cap_alns = L.cap_alns;
 	a.sortA = sA;
 	a.cnt = (DevCounters*)L.cnt.p;
+	a.order = sR.order;
+	if (b->n_regions > 0 && (P.stages & IDL_STAGE_ASSEMBLE)) { // the assembler's queue: regions by read count, deepest first
+		region_key_kernel<<<ctx->n_sm * 2, 256, 0, cs>>>(sR, a.region, a.n_regions, a.cnt);
+		sort_scan_kernel<<<1, 1024, 0, cs>>>(sR);
+		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, cs>>>(sR, &a.cnt->n_regions_in, 1u, a.n_regions);
+		CK(cudaGetLastError()); L.launches += 3;
+	}
 	if (n_small && (P.stages & IDL_STAGE_ASSEMBLE)) { // one warp per region
 		a.small = 1; a.ns = ASM_SMALL_NS; a.planes = (uint32_t*)L.planes_small.p; a.sup = (uint16_t*)L.sup_small.p;
 		assemble_kernel<32><<<small_ctas, ASM_THREADS, 8 * asm_smem_bytes(ASM_SMALL_NS, ctx->nw, 32), cs>>>(a);

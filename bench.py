@@ -32,7 +32,7 @@ def parse():
     ap.add_argument("--workload", default="chr1", help="key of indelope_b200.host.CONFIGS")
     ap.add_argument("--scale", type=float, default=1.0, help="scale the number of planted events (tests)")
     ap.add_argument("--cpu-sample", type=int, default=40000, help="regions timed by the cpu_baseline leg (about 15 s of one core)")
-    ap.add_argument("--e2e-batches", type=int, default=4)
+    ap.add_argument("--e2e-batches", type=int, default=2, help="batches per step in the end-to-end leg (measured: 2 -> 41.6 ms per step, 3 -> 42.7, 4 -> 42.7: smaller batches leave the persistent kernels too few tasks per warp)")
     return ap.parse_args()
 
 

@@ -129,6 +129,10 @@ def test_row_owned_variant_edges(ctx):
             pairs.append((q, t, 5, -1, -1))
     for impl in (["lane", "ref"] if orc.have_ref() else ["lane"]):
         assert check(ctx, pairs, impl) == []
+    # targets too long for the shared-memory staging of the row-owned variant fall back to the column-owned one, per warp
+    long_t = rng.integers(0, 4, 2600).astype(np.uint8)
+    mixed = [(long_t[40:190].copy(), long_t[:2500].copy(), 5, -1, -1), (long_t[5:105].copy(), long_t[:1900].copy(), 5, -1, -1)] + pairs[100:110]
+    assert check(ctx, mixed) == []
     # other gap costs through the same variant
     assert check(ctx, [(p[0], p[1], 3, -1, -1) for p in pairs[::3]]) == []
 

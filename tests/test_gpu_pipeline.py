@@ -221,3 +221,27 @@ def test_block_screen_edges_short_reads_and_periodic_sequence():
     dump, vcf, odump, ovcf, cnt, _ = run_both(rois, arrays, min_reads=3, min_event_len=3, tag="blocks")
     assert cnt["regions"] == 6 and cnt["offsets"] > 10000
     assert_same(dump, vcf, odump, ovcf)
+
+
+def test_chr1_full_workload_is_byte_identical_and_batching_invariant():
+    """BASELINE config 3 at its full size (the workload bench.py times: 62 000 planted events on a 248 Mb contig, ~85 k regions,
+    ~2.5 M reads, ~484 k unbanded and ~128 k banded alignments): the VCF equals the oracle's byte for byte, the device work
+    counters equal the oracle's, and cutting the work into finer batches changes nothing"""
+    ds = util.small_dataset("chr1")
+    rois = ds.sweep(min_reads=5)
+    assert rois.n_rois > 80_000
+    from indelope_b200 import api
+    caller = api.Caller(0, min_reads=5, min_ctg_len=73, min_event_len=5)
+    try:
+        tm = []
+        v1, _ = caller.call(rois, timings=tm)
+        v2, _ = caller.call(rois, max_reads=90_000)
+    finally:
+        caller.close()
+    _, ovcf, cnt = orc.call(rois.arrays(), min_reads=5, min_ctg_len=73, min_event_len=5, dump_level=0, n_threads=os.cpu_count() or 1)
+    assert v1 == ovcf
+    assert v2 == v1
+    assert sum(t["offsets_tested"] for t in tm) == cnt["offsets"]
+    assert sum(t["dp_cells_a"] for t in tm) == cnt["cells_a"] and sum(t["dp_cells_b"] for t in tm) == cnt["cells_b"]
+    assert sum(t["dp_b"] for t in tm) == cnt["dp_b"] and sum(t["al_events"] for t in tm) == cnt["al_events"]
+    assert cnt["variants"] > 10_000

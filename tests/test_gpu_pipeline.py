@@ -223,13 +223,26 @@ def test_block_screen_edges_short_reads_and_periodic_sequence():
     assert_same(dump, vcf, odump, ovcf)
 
 
-def test_chr1_full_workload_is_byte_identical_and_batching_invariant():
-    """BASELINE config 3 at its full size (the workload bench.py times: 62 000 planted events on a 248 Mb contig, ~85 k regions,
-    ~2.5 M reads, ~484 k unbanded and ~128 k banded alignments): the VCF equals the oracle's byte for byte, the device work
-    counters equal the oracle's, and cutting the work into finer batches changes nothing"""
-    ds = util.small_dataset("chr1")
+@pytest.mark.parametrize("name", ["exome", "panel500"])
+def test_exome_and_panel_configs_at_full_size(name):
+    """BASELINE configs 2 and 4 as host.CONFIGS defines them (100x exome: ~2 900 regions of 100-300 reads; 500x panel: regions at
+    the 600-read cap, most of them past the 20-contig gate): every record -- contigs with per-base support, alignments, events --
+    and the VCF, bit for bit"""
+    ds = util.small_dataset(name)
     rois = ds.sweep(min_reads=5)
-    assert rois.n_rois > 80_000
+    dump, vcf, odump, ovcf, cnt, _ = run_both(rois, rois.arrays(), tag=name)
+    assert cnt["regions"] > 400
+    assert_same(dump, vcf, odump, ovcf)
+
+
+@pytest.mark.parametrize("name,min_regions,min_variants", [("chr1", 80_000, 10_000), ("wgs", 40_000, 5_000)])
+def test_full_workloads_are_byte_identical_and_batching_invariant(name, min_regions, min_variants):
+    """BASELINE config 3 at its full size (the workload bench.py times: 62 000 planted events on a 248 Mb contig, ~85 k regions,
+    ~2.5 M reads, ~484 k unbanded and ~128 k banded alignments) and one rank's shard of config 5: the VCF equals the oracle's
+    byte for byte, the device work counters equal the oracle's, and cutting the work into finer batches changes nothing"""
+    ds = util.small_dataset(name)
+    rois = ds.sweep(min_reads=5)
+    assert rois.n_rois > min_regions
     from indelope_b200 import api
     caller = api.Caller(0, min_reads=5, min_ctg_len=73, min_event_len=5)
     try:
@@ -244,4 +257,4 @@ def test_chr1_full_workload_is_byte_identical_and_batching_invariant():
     assert sum(t["offsets_tested"] for t in tm) == cnt["offsets"]
     assert sum(t["dp_cells_a"] for t in tm) == cnt["cells_a"] and sum(t["dp_cells_b"] for t in tm) == cnt["cells_b"]
     assert sum(t["dp_b"] for t in tm) == cnt["dp_b"] and sum(t["al_events"] for t in tm) == cnt["al_events"]
-    assert cnt["variants"] > 10_000
+    assert cnt["variants"] > min_variants

@@ -307,14 +307,12 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 	}
 	if (run) out.cells = (long long)qlen * (long long)tlen;
 	__syncwarp();
-#ifdef KSW_ROWS_SKIP_TB /* timing experiment only: no CIGAR */
-	return;
-#endif
 	// ksw_backtrack :47-79 from (tlen-1, qlen-1) (never z-dropped: the band is the whole anti-diagonal), is_rot = 1.  Unbanded,
 	// the path never leaves [off, off_end], so no state is forced.  In (r, j) coordinates a step back keeps j or lowers it by
 	// one, so the rows r0 .. r0-31 can only be entered at columns j0-k .. j0: the group prefetches that triangle.
 	// The four groups of the warp walk in lockstep (full-warp barriers; a group whose path has ended idles): with per-group
-	// barriers the four walkers drift apart and the warp runs them one after the other (measured: 4.1 of 21.0 ms).
+	// barriers the four walkers drift apart and the warp runs them one after the other.  (The whole traceback is 3.2 of the
+	// 20.0 ms of al_kernel: tile prefetch 1.7, walkers 1.5.)
 	int i = run ? tlen - 1 : -1, j = run ? qlen - 1 : -1, n = 0, ovf = 0;
 	{
 		uint32_t *tile = (uint32_t*)M.xvuy;
@@ -348,12 +346,7 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 				}
 			}
 			__syncwarp();
-#ifdef KSW_ROWS_TB_NOWALK /* timing experiment only */
-			if (gl == 0) { if (tile[gl] == 0x12345u) n++; if (j >= 16) { i -= 16; j -= 16; } else { i -= 32; } }
-			if (0) {
-#else
 			if (gl == 0) {
-#endif
 				const uint8_t *tbp = (const uint8_t*)tile;
 				while (i >= 0 && j >= 0 && i + j > r0 - 32) {
 					const int r = i + j;

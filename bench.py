@@ -137,6 +137,8 @@ def main():
     if args.impl == "reference":
         return main_reference(args, rank, world)
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # no version banner on stdout: rank 0 prints ONE JSON line
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():

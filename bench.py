@@ -20,6 +20,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+OUT = sys.stdout
 CALL = dict(min_reads=5, min_ctg_len=73, min_event_len=5)  # `indelope --min-event-len 5 --min-reads 5` (BASELINE.json configs[0])
 
 
@@ -123,7 +124,7 @@ def main_reference(args, rank, world):
                                        sample, cores, " calling the reference's own ksw2_extz2_sse.c compiled unmodified (oracle/_ref)" if use_ref else " with its own lane-exact ksw2")},
         "e2e": {"value": val, "unit": "regions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 def workload_name(args, cfg):
@@ -133,12 +134,16 @@ def workload_name(args, cfg):
 
 def main():
     args = parse()
+    # rank 0 prints ONE JSON line on stdout: keep the real stdout aside and point fd 1 at stderr, so that nothing a native
+    # library prints there (NCCL writes its version banner to stdout) lands next to it
+    global OUT
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return main_reference(args, rank, world)
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # no version banner on stdout: rank 0 prints ONE JSON line
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -286,7 +291,7 @@ def main():
                                     "ksw2_gcups": None if use_ref else (cnt["cells_a"] + cnt["cells_b"]) / cnt["seconds"] / 1e9,
                                     "sample": "first %d regions of the same workload, single thread (the reference is single-threaded on this path); CPU oracle%s" % (
                                         n, " calling the reference's own ksw2_extz2_sse.c compiled unmodified (oracle/_ref)" if use_ref else " with its own lane-exact ksw2")}
-        print(json.dumps(line))
+        print(json.dumps(line), file=OUT, flush=True)
     for b, _ in slices + [(big, 0)]:
         ctx.batch_free(b)
     caller.close()

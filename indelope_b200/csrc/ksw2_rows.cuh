@@ -31,7 +31,8 @@
 // (W = 8 works -- the tests ran it -- but needs 128 registers; longer reads take the column-owned variant)
 __host__ __device__ inline int ksw_rows_w(int qlen) { return qlen <= 160 ? 5 : 0; }
 // shared-memory bytes of the reversed, zero-padded target
-__host__ __device__ inline size_t ksw_rows_stage_bytes(int W, int tlen) { return (size_t)((tlen + 64 * W + 8 + 3) & ~3) + 96; } // + the bank stagger of the group
+__host__ __device__ inline size_t ksw_rows_snap_bytes(int W) { return (size_t)128 * ((2 * W + 3) / 4); } // score snapshots: (2 W + 3) / 4 uint4 per thread
+__host__ __device__ inline size_t ksw_rows_stage_bytes(int W, int tlen) { return (size_t)((tlen + 64 * W + 8 + 3) & ~3) + 96 + ksw_rows_snap_bytes(W); } // + the bank stagger of the group + the snapshots
 // bytes of backtrack matrix
 __host__ __device__ inline size_t ksw_rows_p_bytes(int W, int qlen, int tlen) { return (size_t)(qlen + tlen - 1) * (size_t)(32 * W) + 2 * KSW_PMAT_PAD + 64; }
 __host__ __device__ inline bool ksw_rows_params_ok(const KswParams &P)
@@ -159,7 +160,7 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 
 	bool wild = false;
 	if (live) {
-		const int total = (int)ksw_rows_stage_bytes(W, tlen) - 96;
+		const int total = (int)(ksw_rows_stage_bytes(W, tlen) - 96 - ksw_rows_snap_bytes(W));
 		for (int i = gl * 4; i < total; i += 32) {
 			uint32_t wv = 0;
 #pragma unroll
@@ -171,7 +172,7 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 		}
 	}
 	// rows in registers: slot s of this thread is query word 8 s + gl
-	uint32_t qw[W], x[W], v[W], u[W], y[W], gx[W], gy[W], snx[W], sny[W];
+	uint32_t qw[W], x[W], v[W], u[W], y[W], gx[W], gy[W];
 #pragma unroll
 	for (int s = 0; s < W; ++s) {
 		const int j0 = 4 * (8 * s + gl);
@@ -187,13 +188,16 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 		const int i0 = P.q * (j0 - 1) - P.e + gbias; // g of row j before its first cell: H(-1, j) + (q+e) j + bias
 		gx[s] = (uint32_t)(i0 & 0xffff) | ((uint32_t)((i0 + P.q) & 0xffff) << 16);
 		gy[s] = (uint32_t)((i0 + 2 * P.q) & 0xffff) | ((uint32_t)((i0 + 3 * P.q) & 0xffff) << 16);
-		snx[s] = 0u; sny[s] = 0u;
 	}
 	if (gl == 0) v[0] &= 0xffffff00u;              // ... and 0 for row 0 on diagonal 0
 	const bool wild_any = __any_sync(FULL_MASK, wild); // a code 4 anywhere in the four alignments: the scores take the wildcard mask
 	__syncwarp();
 
 	const int nsq = live ? (qlen - 4 * gl + 31) >> 5 : 0; // my slots that hold query rows
+	// score snapshots of this thread (taken when its best score rises): the last bytes of the group's region, 16 bytes per
+	// thread and vector, so that a group's store is one conflict-free 128-byte line; only the owner ever reads them back
+	constexpr int NSV = (2 * W + 3) / 4;
+	uint4 *SNAP = (uint4*)((unsigned char*)M.xvuy + (M.region_bytes - (int)ksw_rows_snap_bytes(W))) + gl;
 	const int srcl = (lane & ~7) | ((gl + 7) & 7); // the thread that owns the word below mine
 	int tbest = 0, tr = -1;                        // best exact score over my rows so far, the first diagonal it was seen on
 	int mte = KSW_NEG_INF, mte_r = -1, mqe = KSW_NEG_INF, mqe_t = -1, score = KSW_NEG_INF;
@@ -204,9 +208,9 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 	const uint32_t tw_sh = (uint32_t)__cvta_generic_to_shared(TW);
 	uint32_t chk = 0;
 
-	for (int r = 0; ; ++r, prow += PITCH) {
-		const bool act = live && r < nr;
-		if (!__any_sync(FULL_MASK, act)) break;
+	const int nr_all = (int)__reduce_max_sync(FULL_MASK, (unsigned)nr); // the warp runs until its longest alignment ends
+	for (int r = 0; r < nr_all; ++r, prow += PITCH) {
+		const bool act = r < nr;
 		const int lo0 = r - 4 * gl;                // t of row 4w on this diagonal is lo0 - 32 s
 		const int tbase = tb - r;
 		const uint32_t taddr = tw_sh + (uint32_t)(tbase & ~3);
@@ -238,7 +242,12 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 			if (dm > tbest) { // strictly better than anything my rows have seen (:92 of ksw_apply_zdrop, per thread)
 				tbest = dm; tr = r;
 #pragma unroll
-				for (int s = 0; s < W; ++s) { snx[s] = gx[s]; sny[s] = gy[s]; }
+				for (int k = 0; k < NSV; ++k) {
+					uint32_t q4[4];
+#pragma unroll
+					for (int c = 0; c < 4; ++c) { const int e = 4 * k + c; q4[c] = e < 2 * W ? ((e & 1) ? gy[e >> 1] : gx[e >> 1]) : 0u; }
+					SNAP[8 * k] = make_uint4(q4[0], q4[1], q4[2], q4[3]);
+				}
 			}
 		}
 		if (EZ_FULL) {
@@ -276,12 +285,15 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 		const unsigned want = V + (unsigned)(qe * (r + 1) + gbias);
 		unsigned best = 0xffffffffu;
 		if (have && (unsigned)tbest == V && tr == r) {
+			uint32_t sn[4 * NSV];
+#pragma unroll
+			for (int k = 0; k < NSV; ++k) { const uint4 q4 = SNAP[8 * k]; sn[4 * k] = q4.x; sn[4 * k + 1] = q4.y; sn[4 * k + 2] = q4.z; sn[4 * k + 3] = q4.w; }
 #pragma unroll
 			for (int s = 0; s < W; ++s) {
 #pragma unroll
 				for (int c = 0; c < 4; ++c) {
 					const int j = 4 * (8 * s + gl) + c, t = r - j;
-					const unsigned val = ((c < 2 ? snx[s] : sny[s]) >> (16 * (c & 1))) & 0xffffu;
+					const unsigned val = (sn[2 * s + (c >> 1)] >> (16 * (c & 1))) & 0xffffu;
 					if (j < qlen && t >= st0 && t <= en0 && val == want) {
 						const unsigned rk = t == en0 ? 0u : ksw_tie_rank(t, st0, en1);
 						best = rk < best ? rk : best;

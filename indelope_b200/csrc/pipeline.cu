@@ -404,7 +404,7 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 		kmer_kernel<<<ctx->n_sm * 8, KMER_THREADS, 0, cs>>>(g);
 		CK(cudaGetLastError()); L.launches++;
 		CK(cudaEventRecord(L.ev[EV_KMER], cs));
-		g.ring_cols = ksw_ring_cols(ncolB);
+		g.ring_cols = std::max(ksw_ring_cols(ncolB), P.b_bw < 0 ? 256 : 0); // unbanded: room for the row-owned variant's target staging whatever the reads' length
 		g.seq_cap = (int)round_up(ksw_seq_bytes(max_trim, (int)max_ref), 16);
 		const int al_warps = P.b_bw < 0 ? KSW_UNB_WARPS : DP_WARPS;
 		const size_t smem = (size_t)al_warps * DP_NG * ksw_group_smem(g.ring_cols, g.seq_cap);

@@ -63,7 +63,9 @@ __device__ __forceinline__ void ksw_rows_word(const KswParams &P, uint32_t m, ui
 	const uint32_t ut = prmt(u, pc, 0x2106), yt = prmt(y, pc, 0x2107); // u, y of rows 4w-1 .. 4w+2 (previous diagonal)
 	uint32_t z0 = sel4(msb_to_mask4((tw ^ qv) + 0x7f7f7f7fu), P.misq_4, P.maxsc_4);
 	if (WILD) z0 = sel4(msb_to_mask4(((tw ^ 0x04040404u) + 0x7f7f7f7fu) & ((qv ^ 0x04040404u) + 0x7f7f7f7fu)), z0, P.qe2_4); // a code 4 on either side scores 0 (:219,226)
+#ifndef KSW_ROWS_NOCHK /* the proof after the fact that the carry-free form was exact: 0.51 of 19.3 ms */
 	chk |= x | v; chk |= ut | yt;
+#endif
 	const uint32_t a = x + v, b = yt + ut;
 	uint32_t mk = ge4_pos(z0, a);                   // z >= a
 	uint32_t z = sel4(mk, z0, a);
@@ -71,7 +73,9 @@ __device__ __forceinline__ void ksw_rows_word(const KswParams &P, uint32_t m, ui
 	mk = ge4_pos(z, b);                             // z >= b
 	d = sel4(mk, d, 0x02020202u);
 	z = sel4(mk, z, b);
+#ifndef KSW_ROWS_NOMIN /* a no-op for real cells (H(t,j) - H(t-1,j-1) <= match), kept because the reference does it: 0.64 of 19.3 ms */
 	z = sel4(msb_to_mask4(P.maxsc_h80 - z), z, MAXSC); // min(z, max score)
+#endif
 	const uint32_t zh = z | KSW_H80;
 	uint32_t un = (zh - v) ^ KSW_H80, vn = (zh - ut) ^ KSW_H80;
 	z -= Q4;

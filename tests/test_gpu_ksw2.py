@@ -150,3 +150,27 @@ def test_row_owned_equals_column_owned(ctx, monkeypatch):
     monkeypatch.setenv("IDL_KSW2_COLUMNS", "1")
     b = ctx.ksw2_batch(qs, ts, gapo=5, gape=1, w=-1, zdrop=-1)
     assert a[0] == b[0] and a[1] == b[1]
+
+
+@pytest.mark.parametrize("match,mismatch,gapo,gape", [(2, -4, 4, 2), (1, -1, 2, 1), (3, -6, 10, 3), (5, -4, 20, 5), (1, -3, 6, 1), (2, -4, 30, 2)])
+def test_unbanded_other_scoring_parameters(ctx, match, mismatch, gapo, gape):
+    """the unbanded call-site under scoring parameters other than indelope's: the row-owned variant serves every set with
+    match + 2(q+e) <= 63 (its carry-free recurrence), the last set exceeds that and falls back to the column-owned variant;
+    all against the reference's own compiled C file when it is there, the lane model otherwise"""
+    impl = "ref" if orc.have_ref() else "lane"
+    rng = np.random.default_rng(1000 + 7 * match + gapo)
+    qs, ts = [], []
+    for _ in range(160):
+        tl = int(rng.integers(1, 500)); base = rng.integers(0, 4, tl + 170).astype(np.uint8)
+        o = int(rng.integers(0, tl)); q = base[o:o + int(rng.integers(1, 161))].copy()
+        if rng.random() < 0.3:
+            unit = rng.integers(0, 4, int(rng.integers(1, 5))).astype(np.uint8); q = np.resize(unit, len(q)).copy()
+        m = rng.random(len(q)) < 0.03; q[m] = rng.integers(0, 5, int(m.sum()))
+        qs.append(q); ts.append(base[:tl].copy())
+    f, c, extra, _ = ctx.ksw2_batch(qs, ts, match=match, mismatch=mismatch, gapo=gapo, gape=gape, w=-1, zdrop=-1)
+    bad = []
+    for i, (q, t) in enumerate(zip(qs, ts)):
+        fo, co, _ = orc.ksw2(q, t, match=match, mismatch=mismatch, gapo=gapo, gape=gape, w=-1, zdrop=-1, impl=impl)
+        if extra[i]["status"] < 0 or fo != f[i] or co != c[i]:
+            bad.append((i, len(q), len(t), extra[i]["status"], fo, f[i]))
+    assert bad == [], bad[:3]

@@ -21,6 +21,8 @@ def compare(qry, tgt, **kw):
     fm, cm = rows_align([int(c) for c in qry], [int(c) for c in tgt], **kw)
     assert {k: fo[k] for k in FIELDS} == {k: fm[k] for k in FIELDS}, (len(qry), len(tgt))
     assert [(c & 0xf, c >> 4) for c in co] == cm, (len(qry), len(tgt))
+    # H(t, j) - H(t-1, j-1) <= match for real cells: the clamp of ksw2_extz2_sse.c:132 never binds unbanded (the kernel keeps it anyway)
+    assert fm["clamp_binds"] == 0
 
 
 def test_known_answer():

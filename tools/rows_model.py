@@ -28,7 +28,8 @@ def tie_rank(t, st0, en1):
 def rows_align(query, target, match=1, mismatch=-2, q=5, e=1, W=5):
     """query/target: sequences of codes 0..4.  Returns (fields dict, cigar list of (op, len)) like oracle.pyoracle.ksw2."""
     qlen, tlen = len(query), len(target)
-    out = dict(max=0, zdropped=0, max_q=-1, max_t=-1, mqe=NEG_INF, mqe_t=-1, mte=NEG_INF, mte_q=-1, score=NEG_INF, n_cigar=0)
+    out = dict(max=0, zdropped=0, max_q=-1, max_t=-1, mqe=NEG_INF, mqe_t=-1, mte=NEG_INF, mte_q=-1, score=NEG_INF, n_cigar=0,
+               clamp_binds=0)  # clamp_binds: live cells where min(z, match + 2(q+e)) of :132 changed z (never, for real cells)
     if qlen <= 0 or tlen <= 0:
         return out, []
     assert qlen <= 32 * W
@@ -69,7 +70,10 @@ def rows_align(query, target, match=1, mismatch=-2, q=5, e=1, W=5):
                 z = max(z, a)
                 if b > z:
                     d = 2
-                z = min(max(z, b), maxsc)
+                z = max(z, b)
+                if z > maxsc and 0 <= t <= tlen - 1 and j < qlen:
+                    out["clamp_binds"] += 1
+                z = min(z, maxsc)
                 un, vn = z - v[j], z - ut
                 z -= q
                 xn, yn = max(a - z, 0), max(b - z, 0)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define IDL_ABI_VERSION 1
+#define IDL_ABI_VERSION 2
 
 typedef enum {
 	IDL_OK = 0,
@@ -44,7 +44,17 @@ typedef enum {
 #define IDL_RS_CORR_OVERFLOW   2u   /* more than IDL_MAX_CORRECTIONS voting sites in one merge */
 #define IDL_RS_DP_OVERFLOW     4u   /* an alignment exceeded the DP workspace (tlen/qlen caps) */
 #define IDL_RS_CIGAR_OVERFLOW  8u
-#define IDL_RS_READ_TOO_LONG  16u
+#define IDL_RS_READ_TOO_LONG  16u   /* a read longer than idl_params.max_read_len (idl_region.flags IDL_RF_READ_TOO_LONG): region dropped */
+#define IDL_RS_ALPHABET       32u   /* WARNING, results are produced: a byte outside {A,C,G,T,N} (lower case, IUPAC codes, '=') was folded
+                                       at pack time (acgt -> ACGT, anything else -> N).  The reference compares raw characters
+                                       (src/contig.nim:93,122), so its answer may differ for this region */
+#define IDL_RS_BAD_INPUT      64u   /* a read record of the batch is malformed (bounds / alignment): region dropped */
+/* bits that drop the region (no contigs are returned); the others are warnings */
+#define IDL_RS_FATAL (IDL_RS_CONTIG_OVERFLOW | IDL_RS_CORR_OVERFLOW | IDL_RS_READ_TOO_LONG | IDL_RS_BAD_INPUT)
+
+/* idl_region.flags, set by whoever packs the batch */
+#define IDL_RF_ALPHABET       1u    /* a base of this region's reads or window was folded (see IDL_RS_ALPHABET) */
+#define IDL_RF_READ_TOO_LONG  2u    /* a read of this region exceeds max_read_len and was packed empty */
 
 #define IDL_MAX_CORRECTIONS 128
 #define IDL_MAX_EVENTS 4            /* src/indelope.nim:229 */
@@ -107,7 +117,8 @@ typedef struct idl_region {
 	uint32_t ref_len;             /* window must reach min(chrom_len-1, max(max_stop, max read start+trim)+window_pad) */
 	int32_t max_stop;             /* max(read.stop) over reads with MAPQ > stop_min_mapq, or -1 (:213-216) */
 	uint32_t ordinal;             /* emission order key of the region */
-	uint32_t reserved[2];
+	uint32_t flags;               /* IDL_RF_* */
+	uint32_t reserved;
 } idl_region;                     /* 48 bytes */
 
 typedef struct idl_read {
@@ -133,6 +144,13 @@ typedef struct idl_batch {
 	uint32_t *ref2;
 	uint32_t *refn;
 	void *impl;       /* library private */
+	/* optional summary, filled by the packer (idlh_pack does): with summary_valid != 0 idl_submit sizes its workspaces from
+	 * these instead of scanning every read and region record on the host */
+	uint32_t summary_valid;
+	uint32_t max_trim_len;        /* max(read.trim_len), >= 1 */
+	uint32_t max_ref_len;         /* max(region.ref_len) */
+	uint32_t max_region_reads;    /* max(region.n_reads) */
+	size_t n_small_regions;       /* regions with n_reads <= 126 (assembled one per warp) */
 } idl_batch;
 
 /* ---- results (library-owned pinned memory, valid until idl_release) -------------------------- */
@@ -209,6 +227,7 @@ typedef struct idl_results {
 	/* device-side work counters (algorithmic units) */
 	uint64_t offsets_tested, dp_cells_a, dp_cells_b, dp_a, dp_b, kmer_reads, kmer_bytes, al_events;
 	uint32_t kernel_launches;
+	uint32_t pool_retries;           /* times the chain was run again with larger CIGAR / AL item pools (their sizes are estimates) */
 } idl_results;
 
 typedef struct idl_ctx idl_ctx;

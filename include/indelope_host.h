@@ -108,7 +108,12 @@ const idlh_roiset *idlh_rois_view(const idlh_rois *r);
 /* quality trim of src/indelope.nim:23-38: returns a, *trim_len = kept bases */
 int32_t idlh_trim(const uint8_t *quals, int32_t n, int32_t *trim_len);
 
-/* batch sizing / packing of regions [lo, hi) */
+/* batch sizing / packing of regions [lo, hi).  Packing runs on idlh_set_threads(n) host threads (0 = $IDLH_THREADS, else every core
+ * up to 32): 16 bases per SSE2 step into the 2-bit pool + the non-ACGT plane.  Bytes outside {A,C,G,T,N} are folded (acgt -> ACGT,
+ * anything else -> N) and the region is flagged IDL_RF_ALPHABET; a read longer than max_read_len is packed empty and the region
+ * flagged IDL_RF_READ_TOO_LONG (the device drops that region and reports it) instead of failing the batch.  idlh_pack also fills
+ * the batch summary (idl_batch.summary_valid) so that idl_submit does no per-read host work. */
+void idlh_set_threads(int n);
 void idlh_pack_size(const idlh_roiset *rs, int64_t lo, int64_t hi, const idl_params *p, size_t *n_reads, size_t *n_seq_bases, size_t *n_ref_bases);
 int idlh_pack(const idlh_roiset *rs, int64_t lo, int64_t hi, const idl_params *p, idl_batch *out);
 /* plain-malloc batch for CPU-only inspection/tests (idl_batch_alloc gives pinned memory) */
@@ -129,6 +134,9 @@ char *idlh_vcf_records(idlh_vcf *w, const idlh_roiset *rs, int64_t lo, const idl
  * order, idlh_vcf_dedup applies the reference's order-dependent filter (drop a record equal in CHROM, POS, REF, ALT to
  * one of the last two emitted, src/indelope.nim:114-116,604-608) to the merged text.  Returns malloc'ed text. */
 void idlh_vcf_set_dedup(idlh_vcf *w, int on);
+/* regions seen so far with each idl_region_result.status bit set (index = bit number of IDL_RS_*); every such region also gets a
+ * warning on stderr (the first 20): capacity limits and the alphabet fold never change the output silently */
+void idlh_vcf_status_counts(const idlh_vcf *w, uint64_t out[8]);
 char *idlh_vcf_dedup(const char *records);
 void idlh_free(void *p);
 

@@ -1,11 +1,12 @@
 """ctypes mirrors of the structs in include/indelope_cuda.h (no library is loaded here)."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 u32p = C.POINTER(C.c_uint32)
 
 STAGE_ASSEMBLE, STAGE_ALIGN, STAGE_GENOTYPE, STAGE_ALL = 1, 2, 4, 7
 OUT_SUPPORT = 1
+RS_CONTIG_OVERFLOW, RS_CORR_OVERFLOW, RS_DP_OVERFLOW, RS_CIGAR_OVERFLOW, RS_READ_TOO_LONG, RS_ALPHABET, RS_BAD_INPUT = 1, 2, 4, 8, 16, 32, 64
 
 PARAM_FIELDS = ("abi_version min_reads min_ctg_len min_event_len asm_min_mapq combine_min_support combine_min_overlap max_contigs "
                 "stop_min_mapq window_pad match mismatch a_gapo a_gape a_bw a_zdrop b_gapo b_gape b_bw b_zdrop max_events count_min_mapq "
@@ -32,7 +33,7 @@ def default_params(**kw):
 class Region(C.Structure):
     _fields_ = [("chrom_id", C.c_int32), ("roi_start", C.c_int32), ("roi_end", C.c_int32), ("read_begin", C.c_uint32), ("n_reads", C.c_uint32),
                 ("ref_start", C.c_int32), ("ref_off", C.c_uint32), ("ref_len", C.c_uint32), ("max_stop", C.c_int32), ("ordinal", C.c_uint32),
-                ("reserved", C.c_uint32 * 2)]
+                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Read(C.Structure):
@@ -44,7 +45,8 @@ class Batch(C.Structure):
     _fields_ = [("cap_regions", C.c_size_t), ("cap_reads", C.c_size_t), ("cap_seq_bases", C.c_size_t), ("cap_ref_bases", C.c_size_t),
                 ("n_regions", C.c_size_t), ("n_reads", C.c_size_t), ("n_seq_bases", C.c_size_t), ("n_ref_bases", C.c_size_t),
                 ("region", C.POINTER(Region)), ("read", C.POINTER(Read)), ("seq2", u32p), ("seqn", u32p), ("ref2", u32p), ("refn", u32p),
-                ("impl", C.c_void_p)]
+                ("impl", C.c_void_p), ("summary_valid", C.c_uint32), ("max_trim_len", C.c_uint32), ("max_ref_len", C.c_uint32),
+                ("max_region_reads", C.c_uint32), ("n_small_regions", C.c_size_t)]
 
 
 class RegionResult(C.Structure):
@@ -75,7 +77,7 @@ class Results(C.Structure):
                 ("event", C.POINTER(EventResult)), ("cigar", u32p), ("contig_seq", C.POINTER(C.c_char)), ("contig_support", u32p)] + \
                [(n, C.c_float) for n in "ms_h2d ms_assemble ms_align ms_genotype ms_al ms_d2h ms_total".split()] + \
                [(n, C.c_uint64) for n in "offsets_tested dp_cells_a dp_cells_b dp_a dp_b kmer_reads kmer_bytes al_events".split()] + \
-               [("kernel_launches", C.c_uint32)]
+               [("kernel_launches", C.c_uint32), ("pool_retries", C.c_uint32)]
 
 
 class Ez(C.Structure):

@@ -65,7 +65,7 @@ class Caller:
                 r = res.contents
                 timings.append({k: getattr(r, k) for k in ("ms_h2d", "ms_assemble", "ms_align", "ms_genotype", "ms_al", "ms_d2h", "ms_total", "n_regions",
                                                            "n_contigs", "n_alns", "n_events", "offsets_tested", "dp_cells_a", "dp_cells_b", "dp_a", "dp_b",
-                                                           "kmer_reads", "kmer_bytes", "al_events", "kernel_launches")})
+                                                           "kmer_reads", "kmer_bytes", "al_events", "kernel_launches", "pool_retries")})
             self.ctx.release(t)
             vcf.append(v); dump.append(d)
 
@@ -78,6 +78,7 @@ class Caller:
             inflight.append((a, b, self.ctx.submit(batch)))
         while inflight:
             drain()
+        self.status_counts = writer.status_counts()  # regions per IDL_RS_* bit of the last call (warnings went to stderr)
         return "".join(vcf), "".join(dump)
 
     def close(self):

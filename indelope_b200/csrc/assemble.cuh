@@ -44,7 +44,7 @@ struct AsmArgs {
 	// batch (device copies)
 	const idl_region *region; const idl_read *read;
 	const uint32_t *seq2, *seqn, *ref2, *refn;
-	unsigned n_regions;
+	unsigned n_regions, n_reads, n_seq_bases;
 	idl_params P;
 	// arena: n_ctas * ns slots
 	uint32_t *planes; uint16_t *sup; int ns, nw, cap;
@@ -533,20 +533,28 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 		const idl_region R = args.region[rg];
 		if ((R.n_reads <= ASM_SMALL_READS) != (args.small != 0)) continue; // the other launch assembles this region
 		// reset the slot allocator; detect non-ACGT bases in this region's reads and window
-		if (tid == 0) { A.s.sc[SC_NFREE] = A.ns; A.s.sc[SC_STATUS] = R.n_reads + 2 > (unsigned)A.ns ? IDL_RS_CONTIG_OVERFLOW : 0; A.s.sc[SC_HASN] = 0; }
+		if (tid == 0) {
+			A.s.sc[SC_NFREE] = A.ns; A.s.sc[SC_HASN] = 0;
+			A.s.sc[SC_STATUS] = (R.n_reads + 2 > (unsigned)A.ns ? IDL_RS_CONTIG_OVERFLOW : 0) | ((R.flags & IDL_RF_READ_TOO_LONG) ? IDL_RS_READ_TOO_LONG : 0);
+		}
 		#pragma unroll 1
 		for (int i = tid; i < A.ns; i += NT) A.s.freestk[i] = (uint16_t)(A.ns - 1 - i);
 		asm_bar<NT>();
 		{
-			int any = 0;
+			// the read records are validated here, by the first kernel that touches them (the host checks only the region records):
+			// a record that points outside the pools or whose trim range leaves the read drops the region (IDL_RS_BAD_INPUT)
+			int any = 0, bad = 0;
 			#pragma unroll 1
 			for (unsigned j = 0; j < R.n_reads; ++j) {
 				const idl_read rd = args.read[R.read_begin + j];
+				if ((rd.seq_off & 63u) || (unsigned long long)rd.seq_off + (((unsigned)rd.len + 63u) & ~63u) > (unsigned long long)args.n_seq_bases ||
+				    (unsigned)rd.trim_a + (unsigned)rd.trim_len > (unsigned)rd.len || (int)rd.len > P.max_read_len) { bad = 1; continue; }
 				const uint32_t *pn = args.seqn + (rd.seq_off >> 5);
 				#pragma unroll 1
 				for (int w = tid; w * 32 < rd.len; w += NT) any |= pn[w] != 0;
 			}
 			if (any) A.s.sc[SC_HASN] = 1;
+			if (bad && tid == 0) A.s.sc[SC_STATUS] |= IDL_RS_BAD_INPUT; // every thread saw the same records
 		}
 		// unpack the reference window to 0..4 codes for kernel 2 / glue (src/ksw2/ksw2.nim:127-132)
 		#pragma unroll 1
@@ -655,7 +663,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 4) assemble_kernel(AsmArgs args)
 		const unsigned cbegin = (unsigned)A.s.sc[SC_TMP0];
 		unsigned boff = (unsigned)A.s.sc[SC_TMP1];
 		if (tid == 0) {
-			idl_region_result rr; rr.status = status; rr.n_contigs_pre = n_pre; rr.n_contigs = nlist; rr.contig_begin = cbegin;
+			idl_region_result rr; rr.status = status | ((R.flags & IDL_RF_ALPHABET) ? IDL_RS_ALPHABET : 0u); rr.n_contigs_pre = n_pre; rr.n_contigs = nlist; rr.contig_begin = cbegin;
 			args.rres[rg] = rr;
 		}
 		if (cbegin + (unsigned)nlist > args.cap_contigs) { if (tid == 0) atomicOr(&args.cnt->overflow, 1u); continue; }

@@ -12,39 +12,116 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include "indelope_host.h"
 
 namespace {
 
-inline unsigned code_of(uint8_t ch) // src/ksw2/ksw2.nim:127 lookup: ACGT/acgt -> 0..3, anything else 4
+// ---- 2-bit packing ------------------------------------------------------------------------------------------------
+// src/ksw2/ksw2.nim:127 lookup: ACGT -> 0..3, anything else 4.  This implementation's alphabet is {A,C,G,T,N}: lower-case acgt
+// are folded to upper case and every other byte to N, and the fold is REPORTED (IDL_RF_ALPHABET on the region), because the
+// reference compares raw characters (src/contig.nim:93,122) and may answer differently there.
+// LUT entry: bits 0-1 code, bit 2 "not ACGT" (N plane), bit 3 "folded" (a byte outside the upper-case alphabet ACGTN)
+struct Lut { uint8_t t[256]; Lut() { for (int i = 0; i < 256; ++i) t[i] = 4 | 8; t['A'] = 0; t['C'] = 1; t['G'] = 2; t['T'] = 3; t['N'] = 4;
+                                     t['a'] = 0 | 8; t['c'] = 1 | 8; t['g'] = 2 | 8; t['t'] = 3 | 8; } };
+const Lut LUT;
+
+inline uint32_t spread16(uint32_t x) // bit i -> bit 2i
 {
-	switch (ch) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; }
+	x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
+	return x;
 }
 
-// append n ASCII bases at base offset `off` (multiple of 64) of the pools; pools are zeroed beforehand
-void pack_bases(uint32_t *pool2, uint32_t *pooln, uint64_t off, const uint8_t *s, int64_t n)
+// 16 bases -> one 2-bit word + 16 N-plane bits; returns nonzero if a byte was folded.  n < 16: the rest reads as padding (zero)
+inline unsigned pack16_scalar(const uint8_t *s, int n, uint32_t *w2, uint16_t *wn)
 {
-	for (int64_t i = 0; i < n; ++i) {
-		unsigned c = code_of(s[i]);
-		uint64_t b = off + (uint64_t)i;
-		if (c > 3) pooln[b >> 5] |= 1u << (b & 31);
-		else pool2[b >> 4] |= c << (2 * (b & 15));
+	uint32_t a = 0, b = 0; unsigned bad = 0;
+	for (int i = 0; i < n; ++i) { const unsigned c = LUT.t[s[i]]; bad |= c & 8; if (c & 4) b |= 1u << i; else a |= (c & 3) << (2 * i); }
+	*w2 = a; *wn = (uint16_t)b;
+	return bad;
+}
+
+#if defined(__x86_64__)
+// 32 bases per step on AVX2 + BMI2 (chosen at run time): five byte compares, three movemasks, two PDEPs for the bit interleave
+__attribute__((target("avx2,bmi2"))) int64_t pack_chunks_avx2(const uint8_t *s, int64_t n, uint32_t *d2, uint16_t *dn, unsigned *bad_out)
+{
+	const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'), cT = _mm256_set1_epi8('T'), cN = _mm256_set1_epi8('N'),
+	              fold = _mm256_set1_epi8((char)0xDF);
+	__m256i okv = _mm256_set1_epi8((char)0xFF);
+	int64_t c = 0;
+	for (; (c + 2) * 16 <= n; c += 2) {
+		const __m256i x = _mm256_loadu_si256((const __m256i*)(s + 16 * c));
+		const __m256i xf = _mm256_and_si256(x, fold);
+		const __m256i eA = _mm256_cmpeq_epi8(xf, cA), eC = _mm256_cmpeq_epi8(xf, cC), eG = _mm256_cmpeq_epi8(xf, cG), eT = _mm256_cmpeq_epi8(xf, cT);
+		const __m256i acgt = _mm256_or_si256(_mm256_or_si256(eA, eC), _mm256_or_si256(eG, eT));
+		const uint32_t b0 = (uint32_t)_mm256_movemask_epi8(_mm256_or_si256(eC, eT)), b1 = (uint32_t)_mm256_movemask_epi8(_mm256_or_si256(eG, eT));
+		const uint64_t w = _pdep_u64(b0, 0x5555555555555555ULL) | _pdep_u64(b1, 0xAAAAAAAAAAAAAAAAULL);
+		memcpy(d2 + c, &w, 8);
+		const uint32_t nn = ~(uint32_t)_mm256_movemask_epi8(acgt);
+		memcpy(dn + c, &nn, 4);
+		// exact upper-case ACGTN: the folded compare hit and the byte was not changed by the fold, or it is 'N'
+		okv = _mm256_and_si256(okv, _mm256_or_si256(_mm256_and_si256(acgt, _mm256_cmpeq_epi8(x, xf)), _mm256_cmpeq_epi8(x, cN)));
 	}
+	*bad_out |= ~(unsigned)_mm256_movemask_epi8(okv);
+	return c;
+}
+const bool HAVE_AVX2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
+#endif
+
+// write one record (n ASCII bases, padded with zero codes to a multiple of 64) at base offset `off` (a multiple of 64).  Every word
+// of the record is stored, so the pools need no clearing.  Returns nonzero if a byte was folded.
+unsigned pack_record(uint32_t *pool2, uint32_t *pooln, uint64_t off, const uint8_t *s, int64_t n)
+{
+	uint32_t *d2 = pool2 + (off >> 4); uint16_t *dn = (uint16_t*)pooln + (off >> 4);
+	const int64_t chunks = (int64_t)(((uint64_t)n + 63) & ~(uint64_t)63) >> 4;
+	unsigned bad = 0;
+	int64_t c = 0;
+#if defined(__x86_64__)
+	if (HAVE_AVX2) c = pack_chunks_avx2(s, n, d2, dn, &bad);
+	const __m128i cA = _mm_set1_epi8('A'), cC = _mm_set1_epi8('C'), cG = _mm_set1_epi8('G'), cT = _mm_set1_epi8('T'), cN = _mm_set1_epi8('N'), fold = _mm_set1_epi8((char)0xDF);
+	__m128i badv = _mm_setzero_si128();
+	for (; (c + 1) * 16 <= n; ++c) {
+		const __m128i x = _mm_loadu_si128((const __m128i*)(s + 16 * c));
+		const __m128i xf = _mm_and_si128(x, fold); // a-z -> A-Z (other bytes that change are caught by the exact compares below)
+		const __m128i eC = _mm_cmpeq_epi8(xf, cC), eG = _mm_cmpeq_epi8(xf, cG), eT = _mm_cmpeq_epi8(xf, cT);
+		const __m128i acgt = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(xf, cA), eC), _mm_or_si128(eG, eT));
+		const uint32_t b0 = (uint32_t)_mm_movemask_epi8(_mm_or_si128(eC, eT)), b1 = (uint32_t)_mm_movemask_epi8(_mm_or_si128(eG, eT));
+		d2[c] = spread16(b0) | (spread16(b1) << 1);
+		dn[c] = (uint16_t)(~(uint32_t)_mm_movemask_epi8(acgt));
+		// folded: not exactly one of A C G T N in upper case
+		const __m128i exact = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(x, cA), _mm_cmpeq_epi8(x, cC)),
+		                                   _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(x, cG), _mm_cmpeq_epi8(x, cT)), _mm_cmpeq_epi8(x, cN)));
+		badv = _mm_or_si128(badv, _mm_andnot_si128(exact, _mm_set1_epi8((char)0xFF)));
+	}
+	bad |= (unsigned)_mm_movemask_epi8(badv);
+#endif
+	for (; c < chunks; ++c) {
+		const int64_t left = n - 16 * c;
+		bad |= pack16_scalar(s + 16 * c, left >= 16 ? 16 : (left > 0 ? (int)left : 0), d2 + c, dn + c);
+	}
+	return bad;
 }
 
 inline uint64_t round64(uint64_t x) { return (x + 63) & ~(uint64_t)63; }
 
 struct Win { int64_t ws, we, max_stop; };
 
-Win region_window(const idlh_roiset *rs, int64_t k, const idl_params *p, std::vector<int32_t> *ta, std::vector<int32_t> *tl)
+// the reference window a region ships (include/indelope_cuda.h: idl_region.ref_len) and, optionally, the quality trim of its reads
+template <class F>
+Win region_window(const idlh_roiset *rs, int64_t k, const idl_params *p, F &&per_read)
 {
 	Win w; w.ws = INT64_MAX; w.max_stop = -1; int64_t far = -1;
 	for (int32_t j = 0; j < rs->roi_n_reads[k]; ++j) {
 		int64_t i = rs->read_idx[rs->roi_read_begin[k] + j];
 		int32_t n; int32_t a = idlh_trim(rs->quals + rs->seq_off[i], rs->len[i], &n);
-		if (ta) { ta->push_back(a); tl->push_back(n); }
+		per_read(j, i, a, n);
 		w.ws = std::min<int64_t>(w.ws, (int64_t)rs->start[i] + a);
 		far = std::max<int64_t>(far, (int64_t)rs->start[i] + a + n);
 		if (rs->mapq[i] > p->stop_min_mapq) w.max_stop = std::max<int64_t>(w.max_stop, rs->stop[i]);
@@ -55,9 +132,40 @@ Win region_window(const idlh_roiset *rs, int64_t k, const idl_params *p, std::ve
 	return w;
 }
 
+// ---- a small fork-join helper: packing a step of the chr1 workload is ~400 Mbases; one core cannot feed the GPU ----
+std::atomic<int> g_threads{0};
+
+int pack_threads()
+{
+	int n = g_threads.load();
+	if (n <= 0) { const char *e = getenv("IDLH_THREADS"); n = e ? atoi(e) : 0; }
+	if (n <= 0) { n = (int)std::thread::hardware_concurrency(); if (n > 32) n = 32; }
+	return n < 1 ? 1 : n;
+}
+
+// f(begin, end, thread) over [0, n) in blocks handed out dynamically
+template <class F>
+void parallel_blocks(int64_t n, int64_t block, F &&f)
+{
+	int nt = pack_threads();
+	const int64_t nblocks = (n + block - 1) / block;
+	if (nt > nblocks) nt = (int)std::max<int64_t>(1, nblocks);
+	if (nt <= 1) { if (n > 0) f((int64_t)0, n, 0); return; }
+	std::atomic<int64_t> next{0};
+	auto work = [&](int t) { for (;;) { const int64_t b = next.fetch_add(1); if (b >= nblocks) break; f(b * block, std::min(n, (b + 1) * block), t); } };
+	std::vector<std::thread> th;
+	for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+	work(0);
+	for (auto &x : th) x.join();
+}
+
+inline bool read_too_long(const idlh_roiset *rs, int64_t i, const idl_params *p) { return rs->len[i] > p->max_read_len || rs->len[i] > 65535; }
+
 } // namespace
 
 extern "C" {
+
+void idlh_set_threads(int n) { g_threads.store(n); }
 
 int32_t idlh_trim(const uint8_t *bq, int32_t n, int32_t *trim_len) // src/indelope.nim:23-38
 {
@@ -73,52 +181,97 @@ int32_t idlh_trim(const uint8_t *bq, int32_t n, int32_t *trim_len) // src/indelo
 
 void idlh_pack_size(const idlh_roiset *rs, int64_t lo, int64_t hi, const idl_params *p, size_t *n_reads, size_t *n_seq_bases, size_t *n_ref_bases)
 {
-	size_t nr = 0, sb = 0, rb = 0;
-	for (int64_t k = lo; k < hi; ++k) {
-		nr += (size_t)rs->roi_n_reads[k];
-		for (int32_t j = 0; j < rs->roi_n_reads[k]; ++j) sb += round64((uint64_t)rs->len[rs->read_idx[rs->roi_read_begin[k] + j]]);
-		Win w = region_window(rs, k, p, nullptr, nullptr);
-		rb += round64((uint64_t)std::max<int64_t>(0, w.we - w.ws + 1));
-	}
+	std::atomic<size_t> nr{0}, sb{0}, rb{0};
+	parallel_blocks(hi - lo, 256, [&](int64_t a, int64_t e, int) {
+		size_t r = 0, s = 0, w8 = 0;
+		for (int64_t k = lo + a; k < lo + e; ++k) {
+			r += (size_t)rs->roi_n_reads[k];
+			Win w = region_window(rs, k, p, [&](int32_t, int64_t i, int32_t, int32_t) { if (!read_too_long(rs, i, p)) s += round64((uint64_t)rs->len[i]); });
+			w8 += round64((uint64_t)std::max<int64_t>(0, w.we - w.ws + 1));
+		}
+		nr += r; sb += s; rb += w8;
+	});
 	*n_reads = nr; *n_seq_bases = sb; *n_ref_bases = rb;
 }
 
 int idlh_pack(const idlh_roiset *rs, int64_t lo, int64_t hi, const idl_params *p, idl_batch *b)
 {
-	size_t nr, sb, rb;
-	idlh_pack_size(rs, lo, hi, p, &nr, &sb, &rb);
-	if ((size_t)(hi - lo) > b->cap_regions || nr > b->cap_reads || sb > b->cap_seq_bases || rb > b->cap_ref_bases) return IDL_E_CAPACITY;
-	memset(b->seq2, 0, sb / 4); memset(b->seqn, 0, sb / 8);
-	memset(b->ref2, 0, rb / 4); memset(b->refn, 0, rb / 8);
-	uint64_t soff = 0, roff = 0; uint32_t ri = 0;
-	std::vector<int32_t> ta, tl;
-	for (int64_t k = lo; k < hi; ++k) {
-		ta.clear(); tl.clear();
-		Win w = region_window(rs, k, p, &ta, &tl);
-		idl_region &g = b->region[k - lo];
-		memset(&g, 0, sizeof g);
-		g.chrom_id = rs->roi_chrom[k]; g.roi_start = rs->roi_start[k]; g.roi_end = rs->roi_stop[k];
-		g.read_begin = ri; g.n_reads = (uint32_t)rs->roi_n_reads[k];
-		g.ref_start = (int32_t)w.ws; g.ref_off = (uint32_t)roff; g.ref_len = (uint32_t)std::max<int64_t>(0, w.we - w.ws + 1);
-		g.max_stop = (int32_t)w.max_stop; g.ordinal = (uint32_t)k;
-		pack_bases(b->ref2, b->refn, roff, rs->chrom_seq[g.chrom_id] + w.ws, g.ref_len);
-		roff += round64(g.ref_len);
-		for (int32_t j = 0; j < rs->roi_n_reads[k]; ++j, ++ri) {
-			int64_t i = rs->read_idx[rs->roi_read_begin[k] + j];
-			idl_read &r = b->read[ri];
-			memset(&r, 0, sizeof r);
-			if (rs->len[i] > p->max_read_len || rs->len[i] > 65535) return IDL_E_CAPACITY;
-			r.start = rs->start[i]; r.stop = rs->stop[i]; r.seq_off = (uint32_t)soff; r.len = (uint16_t)rs->len[i];
-			r.trim_a = (uint16_t)ta[j]; r.trim_len = (uint16_t)tl[j];
-			r.min_overlap = (uint16_t)(int64_t)(0.88 * (double)tl[j]); // :169
-			r.mapq = rs->mapq[i];
-			const uint16_t f = rs->flag[i];
-			r.flags = ((f & 0x400) || (f & 0x200) || (f & 0x4) || (f & 0x800) || (f & 0x100)) ? 1 : 0; // :40-47
-			pack_bases(b->seq2, b->seqn, soff, rs->bases + rs->seq_off[i], rs->len[i]);
-			soff += round64((uint64_t)rs->len[i]);
+	const int64_t n = hi - lo;
+	if (n < 0 || (size_t)n > b->cap_regions) return IDL_E_CAPACITY;
+	// read records are laid out region after region: a serial prefix over the regions' read counts
+	std::vector<uint64_t> ri0((size_t)n + 1), so((size_t)n + 1), ro((size_t)n + 1);
+	ri0[0] = 0;
+	for (int64_t k = 0; k < n; ++k) ri0[k + 1] = ri0[k] + (uint64_t)rs->roi_n_reads[lo + k];
+	if (ri0[n] > b->cap_reads) return IDL_E_CAPACITY;
+	const bool timing = getenv("IDLH_PACK_TIMING") != nullptr;
+	auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double t0 = now();
+	// pass A: quality trim, read and region records (everything but the pool offsets), sizes
+	parallel_blocks(n, 128, [&](int64_t a, int64_t e, int) {
+		for (int64_t kk = a; kk < e; ++kk) {
+			const int64_t k = lo + kk;
+			idl_region &g = b->region[kk];
+			memset(&g, 0, sizeof g);
+			uint64_t sbases = 0; uint32_t flags = 0;
+			idl_read *rd = b->read + ri0[kk];
+			Win w = region_window(rs, k, p, [&](int32_t j, int64_t i, int32_t ta, int32_t tl) {
+				idl_read &r = rd[j];
+				memset(&r, 0, sizeof r);
+				r.start = rs->start[i]; r.stop = rs->stop[i]; r.mapq = rs->mapq[i];
+				const uint16_t f = rs->flag[i];
+				r.flags = ((f & 0x400) || (f & 0x200) || (f & 0x4) || (f & 0x800) || (f & 0x100)) ? 1 : 0; // :40-47
+				if (read_too_long(rs, i, p)) { flags |= IDL_RF_READ_TOO_LONG; return; } // packed empty; the device drops the region and says so
+				r.len = (uint16_t)rs->len[i]; r.trim_a = (uint16_t)ta; r.trim_len = (uint16_t)tl;
+				r.min_overlap = (uint16_t)(int64_t)(0.88 * (double)tl); // :169
+				sbases += round64((uint64_t)rs->len[i]);
+			});
+			g.chrom_id = rs->roi_chrom[k]; g.roi_start = rs->roi_start[k]; g.roi_end = rs->roi_stop[k];
+			g.read_begin = (uint32_t)ri0[kk]; g.n_reads = (uint32_t)rs->roi_n_reads[k];
+			g.ref_start = (int32_t)w.ws; g.ref_len = (uint32_t)std::max<int64_t>(0, w.we - w.ws + 1);
+			g.max_stop = (int32_t)w.max_stop; g.ordinal = (uint32_t)k; g.flags = flags;
+			so[kk + 1] = sbases; ro[kk + 1] = round64(g.ref_len);
 		}
+	});
+	so[0] = ro[0] = 0;
+	for (int64_t k = 0; k < n; ++k) { so[k + 1] += so[k]; ro[k + 1] += ro[k]; }
+	const size_t sb = so[n], rb = ro[n];
+	const double t1 = now();
+	if (sb > b->cap_seq_bases || rb > b->cap_ref_bases) return IDL_E_CAPACITY;
+	// pass B: bases.  Every word of every record is written, so the pools are not cleared first.
+	const int nt = pack_threads();
+	std::vector<uint32_t> mx_trim((size_t)nt, 1), mx_ref((size_t)nt, 0), mx_reads((size_t)nt, 0); std::vector<size_t> n_small((size_t)nt, 0);
+	parallel_blocks(n, 64, [&](int64_t a, int64_t e, int t) {
+		for (int64_t kk = a; kk < e; ++kk) {
+			const int64_t k = lo + kk;
+			idl_region &g = b->region[kk];
+			g.ref_off = (uint32_t)ro[kk];
+			unsigned bad = pack_record(b->ref2, b->refn, ro[kk], rs->chrom_seq[g.chrom_id] + g.ref_start, g.ref_len);
+			uint64_t soff = so[kk];
+			idl_read *rd = b->read + ri0[kk];
+			for (uint32_t j = 0; j < g.n_reads; ++j) {
+				const int64_t i = rs->read_idx[rs->roi_read_begin[k] + j];
+				idl_read &r = rd[j];
+				r.seq_off = (uint32_t)soff;
+				if (r.len == 0 && read_too_long(rs, i, p)) continue;
+				bad |= pack_record(b->seq2, b->seqn, soff, rs->bases + rs->seq_off[i], r.len);
+				soff += round64((uint64_t)r.len);
+				mx_trim[t] = std::max<uint32_t>(mx_trim[t], r.trim_len);
+			}
+			if (bad) g.flags |= IDL_RF_ALPHABET;
+			mx_ref[t] = std::max(mx_ref[t], g.ref_len); mx_reads[t] = std::max(mx_reads[t], g.n_reads);
+			n_small[t] += g.n_reads <= 126;
+		}
+	});
+	// guard words behind the pools (the device reads up to two words past a record)
+	memset(b->seq2 + sb / 16, 0, 16); memset(b->seqn + sb / 32, 0, 16); memset(b->ref2 + rb / 16, 0, 16); memset(b->refn + rb / 32, 0, 16);
+	b->n_regions = (size_t)n; b->n_reads = ri0[n]; b->n_seq_bases = sb; b->n_ref_bases = rb;
+	b->max_trim_len = 1; b->max_ref_len = 0; b->max_region_reads = 0; b->n_small_regions = 0;
+	for (int t = 0; t < nt; ++t) {
+		b->max_trim_len = std::max(b->max_trim_len, mx_trim[t]); b->max_ref_len = std::max(b->max_ref_len, mx_ref[t]);
+		b->max_region_reads = std::max(b->max_region_reads, mx_reads[t]); b->n_small_regions += n_small[t];
 	}
-	b->n_regions = (size_t)(hi - lo); b->n_reads = nr; b->n_seq_bases = sb; b->n_ref_bases = rb;
+	b->summary_valid = 1;
+	if (timing) fprintf(stderr, "idlh_pack: %lld regions, %d threads: records %.1f ms, bases %.1f ms\n", (long long)n, nt, t1 - t0, now() - t1);
 	return IDL_OK;
 }
 
@@ -216,12 +369,20 @@ struct Rec { std::string chrom, ref, alt, line; int64_t pos; };
 
 } // namespace
 
-struct idlh_vcf { bool have1 = false, have2 = false, dedup = true; Rec last1, last2; };
+struct idlh_vcf { bool have1 = false, have2 = false, dedup = true; Rec last1, last2; uint64_t status_count[8] = {0}; int warned = 0; };
+
+namespace {
+const char *const RS_NAMES[8] = {"a contig outgrew max_contig_len (region dropped)", "more than 128 voting sites in one merge (region dropped)",
+                                 "an alignment exceeded the DP workspace (its events are not called)", "a CIGAR exceeded the scratch capacity (its events are not called)",
+                                 "a read longer than max_read_len (region dropped)", "bases outside {A,C,G,T,N} were folded (acgt -> ACGT, others -> N); the reference compares raw characters",
+                                 "malformed read record (region dropped)", "unknown"};
+}
 
 extern "C" {
 
 idlh_vcf *idlh_vcf_new(void) { return new idlh_vcf(); }
 void idlh_vcf_set_dedup(idlh_vcf *w, int on) { w->dedup = on != 0; }
+void idlh_vcf_status_counts(const idlh_vcf *w, uint64_t out[8]) { for (int i = 0; i < 8; ++i) out[i] = w->status_count[i]; }
 
 char *idlh_vcf_dedup(const char *records)
 {
@@ -301,6 +462,16 @@ char *idlh_vcf_records(idlh_vcf *w, const idlh_roiset *rs, int64_t lo, const idl
 		const int chrom = rs->roi_chrom[k];
 		const int64_t n_region_reads = rs->roi_n_reads[k];
 		std::vector<std::string> vlines;
+		if (rr.status) { // never silent: the output for this region may differ from the reference's (include/indelope_cuda.h IDL_RS_*)
+			for (int bit = 0; bit < 8; ++bit)
+				if (rr.status & (1u << bit)) {
+					w->status_count[bit] += 1;
+					if (w->warned < 20) {
+						fprintf(stderr, "indelope: warning: region %s:%d-%d: %s\n", rs->chrom_name[chrom], rs->roi_start[k], rs->roi_stop[k], RS_NAMES[bit]);
+						if (++w->warned == 20) fprintf(stderr, "indelope: further region warnings are counted, not printed\n");
+					}
+				}
+		}
 		if (dump_level & 1) {
 			d += "R\t" + std::to_string(k) + "\tpre=" + std::to_string(rr.n_contigs_pre) + "\tn=" + std::to_string(rr.n_contigs) + "\n";
 			for (int32_t ci = 0; ci < rr.n_contigs; ++ci) {

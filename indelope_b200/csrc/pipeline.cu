@@ -68,6 +68,11 @@ struct Lane {
 	bool resident = false;              // device batch uploaded by idl_upload
 	bool payload = true;                // fetch result arrays in idl_wait
 	size_t n_regions = 0, n_reads = 0, n_seq_bases = 0, n_ref_bases = 0;
+	// summary of the batch (from idl_batch.summary_*, or one host scan in check_batch when the packer left it out)
+	int max_trim = 1; unsigned max_ref = 16; size_t n_small = 0;
+	// pools whose size is an estimate grow on overflow: idl_wait relaunches the chain with larger ones (the batch is still resident)
+	unsigned cigar_per_aln = 48, items_per_read = 8, cigar_slack = 4096, items_slack = 1024; int retries = 0;
+	cudaEvent_t ev_d2h[2] = {};
 	unsigned cap_contigs = 0, cap_bases = 0, cap_alns = 0, cap_events = 0, cap_cigar = 0, cap_items = 0;
 	unsigned launches = 0;
 	idl_results res;
@@ -179,9 +184,14 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 		const char *eo = getenv("IDL_OVERLAP_KERNELS");
 		if (!(eo && *eo == '1') && cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess) { idl_destroy(ctx); return IDL_E_CUDA; }
 	}
+	// initial estimates of the two growable pools (tests shrink them to exercise the relaunch)
+	const char *ec = getenv("IDL_CIGAR_PER_ALN"), *ei = getenv("IDL_ITEMS_PER_READ");
 	for (Lane &L : ctx->lanes) {
+		if (ec && atoi(ec) >= 0) { L.cigar_per_aln = (unsigned)atoi(ec); L.cigar_slack = 16; }
+		if (ei && atoi(ei) >= 0) { L.items_per_read = (unsigned)atoi(ei); L.items_slack = 16; }
 		if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { idl_destroy(ctx); return IDL_E_CUDA; }
 		for (auto &ev : L.ev) if (cudaEventCreate(&ev) != cudaSuccess) { idl_destroy(ctx); return IDL_E_CUDA; }
+		for (auto &ev : L.ev_d2h) if (cudaEventCreate(&ev) != cudaSuccess) { idl_destroy(ctx); return IDL_E_CUDA; }
 	}
 	// opt in to large dynamic shared memory for the DP kernels
 	cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -206,6 +216,7 @@ void idl_destroy(idl_ctx *ctx)
 			b->release();
 		for (HostBuf *b : {&L.h_rres, &L.h_cres, &L.h_ares, &L.h_eres, &L.h_cigar, &L.h_seq, &L.h_sup, &L.h_cnt}) b->release();
 		for (auto &ev : L.ev) if (ev) cudaEventDestroy(ev);
+		for (auto &ev : L.ev_d2h) if (ev) cudaEventDestroy(ev);
 		if (L.stream) cudaStreamDestroy(L.stream);
 	}
 	if (ctx->compute) cudaStreamDestroy(ctx->compute);
@@ -245,15 +256,29 @@ void idl_batch_free(idl_ctx *ctx, idl_batch *b)
 
 namespace {
 
-int check_batch(const idl_ctx *ctx, const idl_batch *b)
+struct BatchSummary { int max_trim = 1; unsigned max_ref = 16; size_t n_small = 0; };
+
+// Host-side validation: O(regions).  The read records are validated on the device, by the kernel that first touches them
+// (assemble_kernel: bounds, alignment, trim range; a malformed record drops its region with IDL_RS_BAD_INPUT), so a submit does
+// no per-read host work when the packer filled the batch summary.
+int check_batch(const idl_ctx *ctx, const idl_batch *b, BatchSummary &S)
 {
 	if (!b || b->n_regions > b->cap_regions || b->n_reads > b->cap_reads || b->n_seq_bases > b->cap_seq_bases || b->n_ref_bases > b->cap_ref_bases) return IDL_E_CAPACITY;
 	if (b->n_seq_bases % 64 || b->n_ref_bases % 64) return IDL_E_ARG;
 	if (b->n_seq_bases >= (1ull << 32) || b->n_ref_bases >= (1ull << 32) || b->n_reads >= (1ull << 31)) return IDL_E_CAPACITY;
+	unsigned max_ref = 16; size_t n_small = 0;
 	for (size_t i = 0; i < b->n_regions; ++i) {
 		const idl_region &r = b->region[i];
-		if ((size_t)r.read_begin + r.n_reads > b->n_reads || (size_t)r.ref_off + r.ref_len > b->n_ref_bases) return IDL_E_ARG;
+		if ((size_t)r.read_begin + r.n_reads > b->n_reads || (size_t)r.ref_off + r.ref_len > b->n_ref_bases || (r.ref_off & 63u)) return IDL_E_ARG;
 		if ((int)r.n_reads + 2 > ctx->ns) return IDL_E_CAPACITY;
+		max_ref = std::max(max_ref, r.ref_len); n_small += r.n_reads <= ASM_SMALL_READS;
+	}
+	S.max_ref = max_ref; S.n_small = n_small;
+	if (b->summary_valid) S.max_trim = (int)std::max<uint32_t>(1u, std::min<uint32_t>(b->max_trim_len, (uint32_t)ctx->P.max_read_len));
+	else {
+		int mt = 1;
+		for (size_t i = 0; i < b->n_reads; ++i) mt = std::max<int>(mt, b->read[i].trim_len);
+		S.max_trim = std::min(mt, ctx->P.max_read_len);
 	}
 	return IDL_OK;
 }
@@ -277,18 +302,19 @@ int stage_batch(idl_ctx *ctx, Lane &L, const idl_batch *b, bool copy)
 }
 
 // record_start: the device-resident timing leg has no copies to wait for, so its clock starts here, after the host-side sizing
-int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = false)
+struct LaneSizes { size_t n_regions, n_reads, n_seq_bases, n_ref_bases; };
+
+int launch_chain(idl_ctx *ctx, Lane &L, bool record_start = false)
 {
 	const idl_params &P = ctx->P;
+	const LaneSizes bb = {L.n_regions, L.n_reads, L.n_seq_bases, L.n_ref_bases}; const LaneSizes *b = &bb;
 	// pool capacities: every contig holds >= 1 read; an aligned contig holds >= max(1, min_reads) reads and a region aligns <= max_contigs
-	int max_trim = 1; unsigned max_ref = 16;
-	for (size_t i = 0; i < b->n_reads; ++i) max_trim = std::max<int>(max_trim, b->read[i].trim_len);
-	for (size_t i = 0; i < b->n_regions; ++i) max_ref = std::max(max_ref, b->region[i].ref_len);
+	const int max_trim = L.max_trim; const unsigned max_ref = L.max_ref;
 	L.cap_contigs = (unsigned)b->n_reads + 1;
 	L.cap_bases = (unsigned)std::min<size_t>(b->n_seq_bases + 4 * b->n_reads + 64, 0xfffffff0u);
 	L.cap_alns = (unsigned)std::min<size_t>(b->n_reads / (size_t)std::max(1, P.min_reads) + 1, (size_t)P.max_contigs * b->n_regions + 1);
 	L.cap_events = L.cap_alns * (unsigned)P.max_events;
-	L.cap_cigar = L.cap_alns * 48u + 4096u;
+	L.cap_cigar = (unsigned)std::min<size_t>((size_t)L.cap_alns * L.cigar_per_aln + L.cigar_slack, 0xfffffff0u); // an estimate: grown by idl_wait on overflow
 	CK(L.rres.ensure((b->n_regions + 1) * sizeof(idl_region_result)));
 	CK(L.cres.ensure((size_t)L.cap_contigs * sizeof(idl_contig_result)));
 	CK(L.ares.ensure((size_t)L.cap_alns * sizeof(idl_aln_result)));
@@ -299,15 +325,14 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 	CK(L.refcodes.ensure(b->n_ref_bases + 64));
 	CK(L.al_list.ensure((size_t)L.cap_events * sizeof(AlEntry) + 16));
 	CK(L.cnt.ensure(sizeof(DevCounters)));
-	L.cap_items = (unsigned)std::min<size_t>(8 * b->n_reads + 1024, 0x3fffffffu); // AL items: a read takes part in few AL events
+	L.cap_items = (unsigned)std::min<size_t>((size_t)L.items_per_read * b->n_reads + L.items_slack, 0x3fffffffu); // AL items: a read takes part in few AL events (an estimate: grown by idl_wait on overflow)
 	CK(L.al_items.ensure((size_t)L.cap_items * sizeof(AlItem))); CK(L.al_res.ensure((size_t)L.cap_items * 2 + 16));
 	CK(L.sort_misc.ensure(9 * SORT_BUCKETS * sizeof(unsigned)));
 	CK(L.keysR.ensure((size_t)b->n_regions * 2 + 16)); CK(L.orderR.ensure((size_t)b->n_regions * 4 + 16));
 	CK(L.keysA.ensure((size_t)L.cap_alns * 2 + 16)); CK(L.orderA.ensure((size_t)L.cap_alns * 4 + 16));
 	CK(L.keysB.ensure((size_t)L.cap_items * 4 + 16)); CK(L.orderB.ensure((size_t)L.cap_items * 8 + 16));
 	// workspaces
-	size_t n_small = 0;
-	for (size_t i = 0; i < b->n_regions; ++i) n_small += b->region[i].n_reads <= ASM_SMALL_READS;
+	const size_t n_small = L.n_small;
 	const size_t n_big = b->n_regions - n_small;
 	const int big_ctas = (int)std::min<size_t>(n_big, (size_t)ctx->asm_ctas), small_ctas = (int)std::min<size_t>((n_small + 7) / 8, (size_t)ctx->asm_ctas);
 	// the assembler addresses its arenas with 32-bit element offsets
@@ -350,7 +375,7 @@ int launch_chain(idl_ctx *ctx, Lane &L, const idl_batch *b, bool record_start = 
 	AsmArgs a; memset(&a, 0, sizeof a);
 	a.region = (const idl_region*)L.region.p; a.read = (const idl_read*)L.read.p;
 	a.seq2 = (const uint32_t*)L.seq2.p; a.seqn = (const uint32_t*)L.seqn.p; a.ref2 = (const uint32_t*)L.ref2.p; a.refn = (const uint32_t*)L.refn.p;
-	a.n_regions = (unsigned)b->n_regions; a.P = P;
+	a.n_regions = (unsigned)b->n_regions; a.n_reads = (unsigned)b->n_reads; a.n_seq_bases = (unsigned)b->n_seq_bases; a.P = P;
 	a.planes = (uint32_t*)L.planes.p; a.sup = (uint16_t*)L.sup.p; a.ns = ctx->ns; a.nw = ctx->nw; a.cap = P.max_contig_len;
 	a.rres = (idl_region_result*)L.rres.p; a.cres = (idl_contig_result*)L.cres.p; a.ares = (idl_aln_result*)L.ares.p;
 	a.ctg_ascii = (char*)L.ctg_ascii.p; a.ctg_codes = (uint8_t*)L.ctg_codes.p; a.ctg_sup = (P.out_flags & IDL_OUT_SUPPORT) ? (uint32_t*)L.ctg_sup.p : nullptr;
@@ -438,19 +463,21 @@ extern "C" {
 int idl_submit(idl_ctx *ctx, idl_batch *b, uint64_t *ticket)
 {
 	if (!ctx || !b || !ticket) return IDL_E_ARG;
-	int rc = check_batch(ctx, b);
+	BatchSummary S;
+	int rc = check_batch(ctx, b, S);
 	if (rc) return rc;
 	cudaSetDevice(ctx->device);
 	Lane *Lp = nullptr;
 	for (size_t k = 0; k < ctx->lanes.size(); ++k) { Lane &c = ctx->lanes[(ctx->next_ticket + k) % ctx->lanes.size()]; if (c.state == 0) { Lp = &c; break; } }
 	if (!Lp) return IDL_E_BUSY;
 	Lane &L = *Lp;
-	L.resident = false; L.payload = true;
+	L.resident = false; L.payload = true; L.retries = 0;
+	L.max_trim = S.max_trim; L.max_ref = S.max_ref; L.n_small = S.n_small;
 	CK(cudaEventRecord(L.ev[EV_START], L.stream));
 	rc = stage_batch(ctx, L, b, true);
 	if (rc) return rc;
 	CK(cudaEventRecord(L.ev[EV_H2D], L.stream));
-	rc = launch_chain(ctx, L, b);
+	rc = launch_chain(ctx, L);
 	if (rc) return rc;
 	L.ticket = ctx->next_ticket++; L.state = 1;
 	*ticket = L.ticket;
@@ -460,11 +487,13 @@ int idl_submit(idl_ctx *ctx, idl_batch *b, uint64_t *ticket)
 int idl_upload(idl_ctx *ctx, idl_batch *b)
 {
 	if (!ctx || !b) return IDL_E_ARG;
-	int rc = check_batch(ctx, b);
+	BatchSummary S;
+	int rc = check_batch(ctx, b, S);
 	if (rc) return rc;
 	cudaSetDevice(ctx->device);
 	Lane &L = ctx->lanes[0];
 	if (L.state != 0) return IDL_E_BUSY;
+	L.max_trim = S.max_trim; L.max_ref = S.max_ref; L.n_small = S.n_small;
 	rc = stage_batch(ctx, L, b, true);
 	if (rc) return rc;
 	CK(cudaStreamSynchronize(L.stream));
@@ -479,8 +508,8 @@ int idl_run_resident(idl_ctx *ctx, idl_batch *b, uint64_t *ticket)
 	Lane &L = ctx->lanes[0];
 	if (L.state != 0) return IDL_E_BUSY;
 	if (!L.resident || L.n_regions != b->n_regions || L.n_reads != b->n_reads) return IDL_E_ARG;
-	L.payload = false;
-	int rc = launch_chain(ctx, L, b, true);
+	L.payload = false; L.retries = 0;
+	int rc = launch_chain(ctx, L, true);
 	if (rc) return rc;
 	L.ticket = ctx->next_ticket++; L.state = 1;
 	*ticket = L.ticket;
@@ -497,6 +526,17 @@ int idl_wait(idl_ctx *ctx, uint64_t ticket, const idl_results **out)
 	if (L.state == 1) {
 		CK(cudaStreamSynchronize(L.stream));
 		const DevCounters *c = (const DevCounters*)L.h_cnt.p;
+		// The CIGAR pool and the AL item pool are sized from estimates (48 ops per alignment, 8 AL events per read).  A batch that
+		// needs more -- noisy contigs, deep regions over tandem repeats -- is run again with pools sized from what the device
+		// counted: its inputs are still resident, nothing is returned from the short run, the caller only waits longer.
+		while ((c->overflow & (8u | 64u)) && L.retries < 6) {
+			if (c->overflow & 8u) L.cigar_per_aln = (unsigned)std::min<unsigned long long>(0xfffffu, std::max<unsigned long long>(2ull * L.cigar_per_aln, (unsigned long long)c->n_cigar_ops / std::max(1u, L.cap_alns) + 16));
+			if (c->overflow & 64u) L.items_per_read = (unsigned)std::min<unsigned long long>(0xfffffu, std::max<unsigned long long>(2ull * L.items_per_read, (unsigned long long)c->n_al_items / std::max<size_t>(1, L.n_reads) + 2));
+			L.retries += 1;
+			int rc = launch_chain(ctx, L, !L.payload);
+			if (rc) return rc;
+			CK(cudaStreamSynchronize(L.stream));
+		}
 		idl_results &r = L.res; memset(&r, 0, sizeof r);
 		r.n_regions = L.n_regions;
 		r.n_contigs = std::min(c->n_contigs, L.cap_contigs);
@@ -506,7 +546,7 @@ int idl_wait(idl_ctx *ctx, uint64_t ticket, const idl_results **out)
 		r.n_cigar_ops = std::min(c->n_cigar_ops, L.cap_cigar);
 		float t_d2h = 0;
 		if (L.payload) {
-			cudaEvent_t a0, a1; CK(cudaEventCreate(&a0)); CK(cudaEventCreate(&a1)); // the lane's events still hold unread timings
+			cudaEvent_t a0 = L.ev_d2h[0], a1 = L.ev_d2h[1]; // the lane's stage events still hold unread timings
 			CK(L.h_rres.ensure((r.n_regions + 1) * sizeof(idl_region_result))); CK(L.h_cres.ensure((r.n_contigs + 1) * sizeof(idl_contig_result)));
 			CK(L.h_ares.ensure((r.n_alns + 1) * sizeof(idl_aln_result))); CK(L.h_eres.ensure((r.n_events + 1) * sizeof(idl_event_result)));
 			CK(L.h_cigar.ensure((r.n_cigar_ops + 1) * 4)); CK(L.h_seq.ensure(r.n_contig_bases + 16));
@@ -524,7 +564,6 @@ int idl_wait(idl_ctx *ctx, uint64_t ticket, const idl_results **out)
 			CK(cudaEventRecord(a1, L.stream));
 			CK(cudaStreamSynchronize(L.stream));
 			cudaEventElapsedTime(&t_d2h, a0, a1);
-			cudaEventDestroy(a0); cudaEventDestroy(a1);
 			r.region = (const idl_region_result*)L.h_rres.p; r.contig = (const idl_contig_result*)L.h_cres.p; r.aln = (const idl_aln_result*)L.h_ares.p;
 			r.event = (const idl_event_result*)L.h_eres.p; r.cigar = (const uint32_t*)L.h_cigar.p; r.contig_seq = (const char*)L.h_seq.p;
 			r.contig_support = (ctx->P.out_flags & IDL_OUT_SUPPORT) ? (const uint32_t*)L.h_sup.p : nullptr;
@@ -538,7 +577,7 @@ int idl_wait(idl_ctx *ctx, uint64_t ticket, const idl_results **out)
 		r.ms_d2h = t_d2h; r.ms_total += t_d2h;
 		r.offsets_tested = c->offsets_tested; r.dp_cells_a = c->dp_cells_a; r.dp_cells_b = c->dp_cells_b; r.dp_a = c->dp_a; r.dp_b = c->dp_b;
 		r.kmer_reads = c->kmer_reads; r.kmer_bytes = c->kmer_bytes; r.al_events = c->al_events;
-		r.kernel_launches = L.launches;
+		r.kernel_launches = L.launches; r.pool_retries = (uint32_t)L.retries;
 		if (c->overflow) snprintf(ctx->err, sizeof ctx->err, "result pool overflow mask 0x%x", c->overflow);
 		L.state = 2;
 		if (c->overflow) { *out = &L.res; return IDL_E_CAPACITY; }

@@ -82,6 +82,8 @@ def lib():
         L.idlh_vcf_set_dedup.argtypes = [C.c_void_p, C.c_int]
         L.idlh_vcf_dedup.restype = C.c_void_p
         L.idlh_vcf_dedup.argtypes = [C.c_char_p]
+        L.idlh_set_threads.argtypes = [C.c_int]
+        L.idlh_vcf_status_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.idlh_trim.argtypes = [u8p, C.c_int32, i32p]
         L.idlh_trim.restype = C.c_int32
         _lib = L
@@ -118,6 +120,11 @@ CONFIGS = {
     # 500x panel rich in tandem repeats / homopolymers
     "panel500": dict(seed=20171104, n_chroms=1, chrom_len=2_000_000, n_events=400, coverage=500.0, read_len=150, locus_only=1, locus_flank=220, tr_fraction=0.6,
                      tr_max_unit=3, max_indel=60),
+    # the same panel at a lower substitution rate (2e-4 per base): most deep regions then stay at or under the 20-contig gate of
+    # src/indelope.nim:209, so regions of hundreds of reads reach the contig alignment, the k-mer pass and -- tandem repeats --
+    # the AL fallback with hundreds of reads per event (config 4's "survivors")
+    "panel500_lowerr": dict(seed=20171104, n_chroms=1, chrom_len=2_000_000, n_events=400, coverage=500.0, read_len=150, locus_only=1, locus_flank=220,
+                            tr_fraction=0.6, tr_max_unit=3, max_indel=60, sub_rate=2e-4),
     # 30x whole genome, 3.1 Gb over 24 contigs: one rank's interval shard is built with n_chroms/chrom_len per shard
     "wgs": dict(seed=20171105, n_chroms=1, chrom_len=129_000_000, n_events=32_000, coverage=30.0, read_len=150, locus_only=1, locus_flank=220,
                 tr_fraction=0.2),
@@ -294,6 +301,11 @@ class Rois:
             self.h = None
 
 
+def set_threads(n):
+    """host threads of idlh_pack / idlh_pack_size (0 = $IDLH_THREADS, else every core up to 32)"""
+    lib().idlh_set_threads(int(n))
+
+
 def host_batch(max_regions, max_reads, max_seq_bases, max_ref_bases):
     return lib().idlh_batch_alloc_host(max_regions, max_reads, max_seq_bases, max_ref_bases)
 
@@ -321,6 +333,12 @@ class VcfWriter:
     def __init__(self, dedup=True):
         self.h = lib().idlh_vcf_new()
         lib().idlh_vcf_set_dedup(self.h, 1 if dedup else 0)
+
+    def status_counts(self):
+        """regions seen so far per idl_region_result.status bit (IDL_RS_*: index = bit number)"""
+        out = (C.c_uint64 * 8)()
+        lib().idlh_vcf_status_counts(self.h, out)
+        return list(out)
 
     def records(self, rois, lo, params, results, dump_level=0):
         dump = C.c_void_p()

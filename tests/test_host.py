@@ -94,6 +94,82 @@ def test_pack_roundtrip_and_read_records():
     host.host_batch_free(b)
 
 
+def _pack(rois, p, threads=0):
+    host.set_threads(threads)
+    try:
+        nr, sb, rb = rois.pack_size(0, rois.n_rois, p)
+        b = host.host_batch(rois.n_rois, nr, sb, rb)
+        rois.pack(0, rois.n_rois, p, b)
+    finally:
+        host.set_threads(0)
+    return b, (nr, sb, rb)
+
+
+def _pool_bytes(bt):
+    return tuple(C.string_at(ptr, n) for ptr, n in ((bt.region, bt.n_regions * 48), (bt.read, bt.n_reads * 24), (bt.seq2, bt.n_seq_bases // 4),
+                                                    (bt.seqn, bt.n_seq_bases // 8), (bt.ref2, bt.n_ref_bases // 4), (bt.refn, bt.n_ref_bases // 8)))
+
+
+def test_pack_is_thread_count_invariant_and_fills_the_summary():
+    """idlh_pack on 1 thread and on 7 threads writes the same bytes; the batch summary idl_submit relies on equals a scan"""
+    ds = util.small_dataset("pr1", chrom_len=200_000, n_events=40, n_base_rate=0.005)
+    rois = ds.sweep(min_reads=5)
+    p = abi.default_params(min_reads=5)
+    b1, s1 = _pack(rois, p, 1)
+    b7, s7 = _pack(rois, p, 7)
+    assert s1 == s7 and _pool_bytes(b1.contents) == _pool_bytes(b7.contents)
+    bt = b7.contents
+    assert bt.summary_valid == 1
+    assert bt.max_trim_len == max(bt.read[i].trim_len for i in range(bt.n_reads))
+    assert bt.max_ref_len == max(bt.region[i].ref_len for i in range(bt.n_regions))
+    assert bt.max_region_reads == max(bt.region[i].n_reads for i in range(bt.n_regions))
+    assert bt.n_small_regions == sum(bt.region[i].n_reads <= 126 for i in range(bt.n_regions))
+    assert all(bt.region[i].flags == 0 for i in range(bt.n_regions))  # ACGTN only: nothing was folded
+    host.host_batch_free(b1); host.host_batch_free(b7)
+
+
+def test_pack_flags_folded_bytes_and_overlong_reads():
+    """bytes outside {A,C,G,T,N} (soft-masked lower case, IUPAC codes, '=') are folded AND reported per region; a read longer
+    than max_read_len is packed empty and flagged instead of failing the batch (src/contig.nim:93 compares raw characters)"""
+    rng = np.random.default_rng(3)
+    ref = "".join("ACGT"[i] for i in rng.integers(0, 4, 4000))
+    sets = []
+    for case in range(4):
+        reads = [dict(start=1000 + i, seq=ref[1000 + i:1150 + i]) for i in range(0, 60, 5)]
+        if case == 1:
+            reads[3]["seq"] = reads[3]["seq"][:40] + "r" + reads[3]["seq"][41:]        # IUPAC, lower case -> N
+        if case == 2:
+            reads[5]["seq"] = reads[5]["seq"][:17].lower() + reads[5]["seq"][17:]      # soft-masked -> upper case
+        if case == 3:
+            reads[2] = dict(start=1010, seq=ref[1010:1010 + 700])                      # longer than max_read_len = 512
+        _, arrays = util.rois_from_reads(reads, ref)
+        sets.append(arrays)
+    arrays = util.merge_rois(sets)
+    rois = host.Rois(arrays=arrays)
+    p = abi.default_params(min_reads=3)
+    b, _ = _pack(rois, p, 2)
+    bt = b.contents
+    assert [bt.region[i].flags for i in range(4)] == [0, 1, 1, 2]
+    rd = bt.read[bt.region[1].read_begin + 3]
+    assert host.unpack(bt.seq2, bt.seqn, rd.seq_off, rd.len)[38:43] == reads_text(arrays, 1, 3)[38:40] + "N" + reads_text(arrays, 1, 3)[41:43]
+    rd = bt.read[bt.region[2].read_begin + 5]
+    assert host.unpack(bt.seq2, bt.seqn, rd.seq_off, rd.len) == reads_text(arrays, 2, 5).upper()
+    rd = bt.read[bt.region[3].read_begin + 2]
+    assert rd.len == 0 and rd.trim_len == 0
+    host.host_batch_free(b)
+    # a soft-masked reference window is folded and flagged as well
+    _, arrays = util.rois_from_reads([dict(start=1000 + i, seq=ref[1000 + i:1150 + i]) for i in range(0, 60, 5)], ref[:1100] + ref[1100:1200].lower() + ref[1200:])
+    rois = host.Rois(arrays=arrays)
+    b, _ = _pack(rois, p, 1)
+    assert b.contents.region[0].flags == 1
+    host.host_batch_free(b)
+
+
+def reads_text(a, region, j):
+    i = a["read_idx"][a["roi_read_begin"][region] + j]
+    return bytes(a["bases"][a["seq_off"][i]:a["seq_off"][i] + a["len"][i]]).decode()
+
+
 def test_int_088_equals_integer_form():
     # SURVEY 8: int(0.88*len) == 88*len div 100 for every len <= 2000
     for n in range(0, 2001):

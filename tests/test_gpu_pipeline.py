@@ -357,4 +357,4 @@ def test_status_bits_are_reported_never_silent(capfd):
         up[k] = arrays[k][:2]
     odump, ovcf, _ = orc.call(up, min_reads=3, min_ctg_len=73, min_event_len=4, dump_level=31, use_ref_ksw2=orc.have_ref())
     assert "\n".join(l for l in dump.splitlines() if l.split("\t")[1] in ("0", "1") or l.startswith("V")) == odump.rstrip("\n")
-    assert vcf == ovcf and vcf.count("\n") >= 2
+    assert vcf == ovcf and vcf.count("\n") == 1  # regions 0 and 1 call the same deletion: the second record falls to the dedup (:604-608)

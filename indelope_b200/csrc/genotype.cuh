@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "ksw2.cuh"
 #include "ksw2_rows.cuh"
+#include "ksw2_band.cuh"
 
 #define DP_WARPS 8
 #define DP_THREADS (DP_WARPS * 32)
@@ -21,6 +22,12 @@
 #define DP_NG (32 / DP_G)
 #ifndef KSW_A_CTAS
 #define KSW_A_CTAS 3 /* resident CTAs per SM of the banded call-site */
+#endif
+#ifndef KSW_BAND_G
+#define KSW_BAND_G 8 /* threads per alignment of the register-ring variant of the banded call-site (4 or 8) */
+#endif
+#ifndef KSW_BAND_CTAS
+#define KSW_BAND_CTAS 3
 #endif
 #ifndef KSW_UNB_WARPS
 #define KSW_UNB_WARPS 5 /* warps per CTA of the unbanded al_kernel.  Measured on the chr1 workload (ms): 8 warps x 2 CTAs at 124 registers
@@ -104,13 +111,15 @@ __global__ void region_key_kernel(SortBufs s, const idl_region *region, unsigned
 }
 
 // shared/global memory of the group this thread belongs to
+template <int G = DP_G>
 __device__ __forceinline__ KswMem dp_mem(const GenoArgs &g, unsigned char *smem, int qlen, int tlen, int warps_per_cta = DP_WARPS)
 {
-	const int grp = warp_id() * DP_NG + (lane_id() / DP_G);
+	constexpr int NG = 32 / G;
+	const int grp = warp_id() * NG + (lane_id() / G);
 	const size_t per = ksw_group_smem(g.ring_cols, g.seq_cap);
-	const size_t gg = (size_t)blockIdx.x * (warps_per_cta * DP_NG) + grp;
+	const size_t gg = (size_t)blockIdx.x * (warps_per_cta * NG) + grp;
 	KswMem m;
-	ksw_group_mem(m, smem + per * grp, lane_id() / DP_G, g.ring_cols); m.region_bytes = (int)per;
+	ksw_group_mem(m, smem + per * grp, lane_id() / G, g.ring_cols); m.region_bytes = (int)per;
 	if (ksw_seq_bytes(qlen, tlen) <= (size_t)g.seq_cap) m.seq_cap = g.seq_cap;
 	else { m.seq = g.seq_spill + gg * (size_t)g.seq_spill_cap; m.seq_cap = g.seq_spill_cap; }
 	m.pmat = g.pmat + gg * g.p_cap; m.p_cap = g.p_cap;
@@ -152,17 +161,19 @@ __device__ __forceinline__ int distinct_k(const uint8_t *a, int K)
 // ---------------------------------------------------------------------------------------------------------------
 // call-site A + glue: one group of DP_G threads per alignment, DP_NG alignments per warp
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DP_THREADS, KSW_A_CTAS) align_kernel(GenoArgs g)
+// BAND: the register-ring variant (ksw2_band.cuh), G threads per alignment; otherwise the column-owned shared-memory variant, 8 threads
+template <int G, bool BAND>
+__device__ __forceinline__ void align_body(const GenoArgs &g, unsigned char *smem_raw)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;
-	const unsigned gmask = ((1u << DP_G) - 1u) << (lane & ~(DP_G - 1));
+	constexpr int GG = G, NGG = 32 / G;
+	const int lane = lane_id(), gl = lane & (GG - 1), grp = lane / GG;
+	const unsigned gmask = (GG == 32 ? 0xffffffffu : ((1u << GG) - 1u)) << (lane & ~(GG - 1));
 	const idl_params &P = g.P;
 	const int K = IDL_KMER, width = (K + 1) / 2 - 1; // :218
 	const unsigned n_alns = g.cnt->n_alns < g.cap_alns ? g.cnt->n_alns : g.cap_alns;
 	for (;;) {
 		unsigned base = 0;
-		if (lane == 0) base = atomicAdd(&g.cnt->aln_next, (unsigned)DP_NG);
+		if (lane == 0) base = atomicAdd(&g.cnt->aln_next, (unsigned)NGG);
 		base = __shfl_sync(FULL_MASK, base, 0);
 		if (base >= n_alns) break;
 		const bool valid = base + grp < n_alns;
@@ -173,9 +184,10 @@ __global__ void __launch_bounds__(DP_THREADS, KSW_A_CTAS) align_kernel(GenoArgs 
 		const uint8_t *tq = g.refcodes + R.ref_off + (cr.start - R.ref_start);
 		const uint8_t *qq = g.ctg_codes + cr.seq_off;
 		KswQuery kq; kq.codes = qq; kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
-		const KswMem M = dp_mem(g, smem_raw, cr.len, tlen);
+		const KswMem M = dp_mem<G>(g, smem_raw, cr.len, tlen);
 		KswOut o;
-		ksw2_group<DP_G>(valid, cr.len, kq, tlen, tq, g.kpA, M, o); // the whole warp: four alignments in lockstep
+		if (BAND) ksw2_band<G, true>(valid, cr.len, kq, tlen, tq, g.kpA, M, o); // the whole warp: 32 / G alignments in lockstep
+		else ksw2_group<8>(valid, cr.len, kq, tlen, tq, g.kpA, M, o);
 		if (valid) {
 			const uint32_t *cg = M.cig;
 			const int n = o.n_cigar;
@@ -184,17 +196,17 @@ __global__ void __launch_bounds__(DP_THREADS, KSW_A_CTAS) align_kernel(GenoArgs 
 				ntr = ksw_trunc_count(cg, n, o.max_q);
 				for (int k = 0; k < ntr; ++k) nev += (cg[n - 1 - k] & 0xf) != 0;
 			}
-			ntr = __shfl_sync(gmask, ntr, 0, DP_G); nev = __shfl_sync(gmask, nev, 0, DP_G);
+			ntr = __shfl_sync(gmask, ntr, 0, GG); nev = __shfl_sync(gmask, nev, 0, GG);
 			unsigned coff = 0, eoff = 0;
 			const bool want_events = (P.stages & IDL_STAGE_GENOTYPE) && nev >= 1 && nev <= P.max_events; // :229
 			if (gl == 0) {
 				coff = atomicAdd(&g.cnt->n_cigar_ops, (unsigned)n);
 				if (want_events) eoff = atomicAdd(&g.cnt->n_events, (unsigned)nev);
 			}
-			coff = __shfl_sync(gmask, coff, 0, DP_G); eoff = __shfl_sync(gmask, eoff, 0, DP_G);
+			coff = __shfl_sync(gmask, coff, 0, GG); eoff = __shfl_sync(gmask, eoff, 0, GG);
 			unsigned st = dp_status_bits(o.status);
 			if (coff + (unsigned)n > g.cap_cigar) { st |= IDL_RS_CIGAR_OVERFLOW; if (gl == 0) atomicOr(&g.cnt->overflow, 8u); }
-			else for (int k = gl; k < n; k += DP_G) g.cigar[coff + k] = cg[n - 1 - k]; // forward order
+			else for (int k = gl; k < n; k += GG) g.cigar[coff + k] = cg[n - 1 - k]; // forward order
 			bool ev_ok = want_events;
 			if (ev_ok && eoff + (unsigned)nev > g.cap_events) { ev_ok = false; if (gl == 0) atomicOr(&g.cnt->overflow, 16u); }
 			if (gl == 0) {
@@ -273,6 +285,17 @@ __global__ void __launch_bounds__(DP_THREADS, KSW_A_CTAS) align_kernel(GenoArgs 
 		}
 		__syncwarp();
 	}
+}
+
+__global__ void __launch_bounds__(DP_THREADS, KSW_A_CTAS) align_kernel(GenoArgs g) // any band width: the shared-memory rings
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	align_body<8, false>(g, smem_raw);
+}
+__global__ void __launch_bounds__(DP_THREADS, KSW_BAND_CTAS) align_band_kernel(GenoArgs g) // rounded bands of up to 96 lanes (w <= 79): the ring in registers
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	align_body<KSW_BAND_G, true>(g, smem_raw);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

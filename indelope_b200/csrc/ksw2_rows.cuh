@@ -330,6 +330,9 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 	// barriers the four walkers drift apart and the warp runs them one after the other.  (The whole traceback is 3.2 of the
 	// 20.0 ms of al_kernel: tile prefetch 1.7, walkers 1.5.)
 	int i = run ? tlen - 1 : -1, j = run ? qlen - 1 : -1, n = 0, ovf = 0;
+#ifdef KSW_ROWS_NOTB /* timing / traffic experiments only: skip the traceback (results are wrong) */
+	i = j = -1;
+#endif
 	{
 		uint32_t *tile = (uint32_t*)M.xvuy;
 		uint32_t *cig = M.cig; const int cig_cap = M.cig_cap;

@@ -177,7 +177,7 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	// persistent grids: CTAs per SM (tunable for experiments through the environment)
 	const char *ea = getenv("IDL_ASM_CTAS_PER_SM"), *ed = getenv("IDL_DP_CTAS_PER_SM");
 	ctx->asm_ctas = ctx->n_sm * (ea && atoi(ea) > 0 ? atoi(ea) : 4); // CTAs of each assembler launch (8 regions per CTA in the warp variant)
-	ctx->dp_ctas = ctx->n_sm * (ed && atoi(ed) > 0 ? atoi(ed) : 3); // upper bound; every launch asks the occupancy calculator
+	ctx->dp_ctas = ctx->n_sm * (ed && atoi(ed) > 0 ? atoi(ed) : 4); // upper bound; every launch asks the occupancy calculator
 	ctx->lanes.resize((size_t)p->n_streams);
 	{
 		// IDL_OVERLAP_KERNELS=1: the kernels of a batch run on its lane's stream and may share the SMs with another batch's
@@ -195,6 +195,7 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	}
 	// opt in to large dynamic shared memory for the DP kernels
 	cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(align_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	cudaFuncSetAttribute(al_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	cudaFuncSetAttribute(al_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	cudaFuncSetAttribute(assemble_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -352,10 +353,13 @@ int launch_chain(idl_ctx *ctx, Lane &L, bool record_start = false)
 	const size_t rowsA = std::min<size_t>((size_t)P.max_contig_len + max_ref, 2 * (size_t)max_ref + wA + 2);
 	const size_t rowsB = (size_t)max_trim + std::max<size_t>(max_ref, 1536);
 	const size_t pitchB = std::max<size_t>(ksw_pitch(ncolB), P.b_bw < 0 ? 32 * (size_t)ksw_rows_w(max_trim) : 0); // the row-owned variant stores 32 W bytes per diagonal
-	const size_t p_cap = round_up(std::max(rowsA * ksw_pitch(ncolA), rowsB * pitchB) + 2 * KSW_PMAT_PAD + 64, 256);
-	const size_t n_groups = (size_t)ctx->dp_ctas * DP_WARPS * DP_NG;
+	// the banded call-site runs the register-ring variant whenever its band fits (w <= 79: indelope's 50 does), G threads per alignment
+	const bool bandA = P.a_bw >= 0 && ksw_ncol(P.max_contig_len, (int)max_ref, P.a_bw) <= KSW_BAND_MAX_NCOL;
+	const size_t p_capA = round_up(rowsA * ksw_pitch(ncolA) + 2 * KSW_PMAT_PAD + 64, 256), p_capB = round_up(rowsB * pitchB + 2 * KSW_PMAT_PAD + 64, 256);
+	const size_t groups_a = (size_t)ctx->dp_ctas * DP_WARPS * (bandA ? 32 / KSW_BAND_G : DP_NG), groups_b = (size_t)ctx->dp_ctas * DP_WARPS * DP_NG;
+	const size_t n_groups = std::max(groups_a, groups_b);
 	const int seq_spill_cap = (int)round_up(ksw_seq_bytes(std::max(P.max_contig_len, max_trim), std::max((int)max_ref, P.max_contig_len)), 16);
-	CK(L.pmat.ensure(n_groups * p_cap));
+	CK(L.pmat.ensure(std::max(groups_a * p_capA, groups_b * p_capB)));
 	CK(L.cig_scratch.ensure(n_groups * (size_t)ctx->cig_cap * 4));
 	CK(L.seq_spill.ensure(n_groups * (size_t)seq_spill_cap));
 	// copies travel on the lane's stream, kernels on the context's compute stream: batches overlap their transfers with each
@@ -411,20 +415,22 @@ int launch_chain(idl_ctx *ctx, Lane &L, bool record_start = false)
 	g.P = P; g.cnt = a.cnt;
 	g.kpA = ksw_make_params(P.match, P.mismatch, P.a_gapo, P.a_gape, P.a_bw, P.a_zdrop);
 	g.kpB = ksw_make_params(P.match, P.mismatch, P.b_gapo, P.b_gape, P.b_bw, P.b_zdrop);
-	g.pmat = (uint8_t*)L.pmat.p; g.p_cap = p_cap; g.cig_scratch = (uint32_t*)L.cig_scratch.p; g.cig_cap = ctx->cig_cap;
+	g.pmat = (uint8_t*)L.pmat.p; g.p_cap = p_capA; g.cig_scratch = (uint32_t*)L.cig_scratch.p; g.cig_cap = ctx->cig_cap;
 	g.seq_spill = (uint8_t*)L.seq_spill.p; g.seq_spill_cap = seq_spill_cap;
 	const size_t smem_limit = 200 * 1024;
 	if (b->n_regions > 0 && (P.stages & IDL_STAGE_ALIGN)) {
-		g.ring_cols = ksw_ring_cols(ncolA);
+		g.ring_cols = bandA ? 0 : ksw_ring_cols(ncolA); // the register-ring variant keeps only the reversed query (later the backtrack tile) in shared memory
 		g.seq_cap = (int)round_up(ksw_seq_bytes(std::min(P.max_contig_len, 1024), (int)max_ref), 16); // longer contigs stage in the spill area
-		const size_t smem = (size_t)DP_WARPS * DP_NG * ksw_group_smem(g.ring_cols, g.seq_cap);
+		const size_t smem = (size_t)DP_WARPS * (bandA ? 32 / KSW_BAND_G : DP_NG) * ksw_group_smem(g.ring_cols, g.seq_cap);
 		if (smem > smem_limit) return IDL_E_CAPACITY;
 		sort_scan_kernel<<<1, 1024, 0, cs>>>(sA);
 		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, cs>>>(sA, &a.cnt->n_alns, 1u, L.cap_alns);
-		align_kernel<<<dp_grid(ctx, (const void*)align_kernel, smem), DP_THREADS, smem, cs>>>(g);
+		if (bandA) align_band_kernel<<<dp_grid(ctx, (const void*)align_band_kernel, smem), DP_THREADS, smem, cs>>>(g);
+		else align_kernel<<<dp_grid(ctx, (const void*)align_kernel, smem), DP_THREADS, smem, cs>>>(g);
 		CK(cudaGetLastError()); L.launches += 3;
 	}
 	CK(cudaEventRecord(L.ev[EV_ALN], cs));
+	g.p_cap = p_capB;
 	if (b->n_regions > 0 && (P.stages & IDL_STAGE_GENOTYPE) && (P.stages & IDL_STAGE_ALIGN)) {
 		kmer_kernel<<<ctx->n_sm * 8, KMER_THREADS, 0, cs>>>(g);
 		CK(cudaGetLastError()); L.launches++;
@@ -611,21 +617,24 @@ struct KswBatchArgs {
 	int no_rows; // IDL_KSW2_COLUMNS=1: keep unbanded alignments on the column-owned variant (tests compare the two)
 };
 
-template <bool UNB>
-__global__ void __launch_bounds__(DP_THREADS, UNB ? 2 : 3) ksw2_batch_kernel(KswBatchArgs a) // unbanded: 8 warps x 2 CTAs at 122 registers (uniform shapes: 774 GCUPS at 150x700 against 745 with al_kernel's 5 x 4)
+// MODE 0: banded, shared-memory rings (any w >= 0); 1: unbanded (row-owned variant for reads of up to 160 bases, else the rings);
+// 2: banded, the ring in registers (rounded bands of up to 96 lanes), G threads per alignment
+template <int MODE, int G>
+__global__ void __launch_bounds__(DP_THREADS, MODE == 1 ? 2 : 3) ksw2_batch_kernel(KswBatchArgs a) // unbanded: 8 warps x 2 CTAs at 122 registers (uniform shapes: 774 GCUPS at 150x700 against 745 with al_kernel's 5 x 4)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const int lane = lane_id(), gl = lane & (DP_G - 1), grp = lane / DP_G;
-	const int cg = warp_id() * DP_NG + grp;
+	constexpr int NG = 32 / G;
+	const int lane = lane_id(), gl = lane & (G - 1), grp = lane / G;
+	const int cg = warp_id() * NG + grp;
 	const size_t per = ksw_group_smem(a.ring_cols, a.seq_cap);
-	const size_t gg = (size_t)blockIdx.x * (DP_WARPS * DP_NG) + cg;
+	const size_t gg = (size_t)blockIdx.x * (DP_WARPS * NG) + cg;
 	KswMem M;
 	ksw_group_mem(M, smem_raw + per * cg, grp, a.ring_cols); M.seq_cap = a.seq_cap; M.region_bytes = (int)per;
 	M.pmat = a.pmat + gg * a.p_cap; M.p_cap = a.p_cap;
 	M.cig = a.cig_scratch + gg * (size_t)a.cig_cap; M.cig_cap = a.cig_cap;
 	for (;;) {
 		unsigned base = 0;
-		if (lane == 0) base = atomicAdd(a.next, (unsigned)DP_NG);
+		if (lane == 0) base = atomicAdd(a.next, (unsigned)NG);
 		base = __shfl_sync(FULL_MASK, base, 0);
 		if (base >= a.n) break;
 		const unsigned i = base + grp;
@@ -634,17 +643,20 @@ __global__ void __launch_bounds__(DP_THREADS, UNB ? 2 : 3) ksw2_batch_kernel(Ksw
 		KswQuery kq; kq.codes = a.query + (valid ? a.q_off[i] : 0); kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
 		KswOut o;
 		const uint8_t *tq = a.target + (valid ? a.t_off[i] : 0);
-		const int rw = UNB && !a.no_rows ? ksw_rows_pick(valid, qlen, tlen, a.kp, M) : 0;
-		if (rw == 5) ksw2_rows<5, true>(valid, qlen, kq, tlen, tq, a.kp, M, o);
-		else ksw2_group<DP_G, true, UNB>(valid, qlen, kq, tlen, tq, a.kp, M, o);
+		if (MODE == 2) ksw2_band<G, true>(valid, qlen, kq, tlen, tq, a.kp, M, o);
+		else {
+			const int rw = MODE == 1 && !a.no_rows ? ksw_rows_pick(valid, qlen, tlen, a.kp, M) : 0;
+			if (rw == 5) ksw2_rows<5, true>(valid, qlen, kq, tlen, tq, a.kp, M, o);
+			else ksw2_group<8, true, MODE == 1>(valid, qlen, kq, tlen, tq, a.kp, M, o);
+		}
 		if (valid) {
-			const unsigned gmask = ((1u << DP_G) - 1u) << (lane & ~(DP_G - 1));
+			const unsigned gmask = ((1u << G) - 1u) << (lane & ~(G - 1));
 			unsigned coff = 0;
 			if (gl == 0) coff = atomicAdd(a.cig_used, (unsigned)o.n_cigar);
-			coff = __shfl_sync(gmask, coff, 0, DP_G);
+			coff = __shfl_sync(gmask, coff, 0, G);
 			int status = o.status;
 			if (coff + (unsigned)o.n_cigar > a.cigar_cap) status = KSW_ST_CIGCAP;
-			else for (int k = gl; k < o.n_cigar; k += DP_G) a.cigar[coff + k] = M.cig[o.n_cigar - 1 - k];
+			else for (int k = gl; k < o.n_cigar; k += G) a.cigar[coff + k] = M.cig[o.n_cigar - 1 - k];
 			if (gl == 0) {
 				idl_ez e; e.max = o.max; e.zdropped = o.zdropped; e.max_q = o.max_q; e.max_t = o.max_t; e.mqe = o.mqe; e.mqe_t = o.mqe_t; e.mte = o.mte;
 				e.mte_q = o.mte_q; e.score = o.score; e.n_cigar = o.n_cigar; e.status = status; e.reserved = 0; e.cells = o.cells;
@@ -676,15 +688,18 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 	KswBatchArgs a; memset(&a, 0, sizeof a);
 	a.n = (unsigned)n; a.kp = ksw_make_params(match, mismatch, gapo, gape, w, zdrop);
 	{ const char *e = getenv("IDL_KSW2_COLUMNS"); a.no_rows = e && *e == '1'; }
-	a.ring_cols = ksw_ring_cols(max_ncol);
+	// 0 <= w with a rounded band of up to 96 lanes: the register-ring variant (IDL_KSW2_COLUMNS=1 keeps the shared-memory rings: tests compare the two)
+	const int mode = w < 0 ? 1 : (max_ncol <= KSW_BAND_MAX_NCOL && !a.no_rows ? 2 : 0);
+	const int ng = mode == 2 ? 32 / KSW_BAND_G : DP_NG;
+	a.ring_cols = mode == 2 ? 0 : ksw_ring_cols(max_ncol);
 	a.p_cap = round_up(max_p + 2 * KSW_PMAT_PAD + 64, 256); a.cig_cap = max_q + max_t + 8; a.cigar_cap = (unsigned)cigar_cap;
 	a.seq_cap = (int)round_up(ksw_seq_bytes(max_q, max_t), 16);
 	const int wpc = DP_WARPS; // warps per CTA
-	const size_t smem = (size_t)wpc * DP_NG * ksw_group_smem(a.ring_cols, a.seq_cap);
+	const size_t smem = (size_t)wpc * ng * ksw_group_smem(a.ring_cols, a.seq_cap);
 	if (smem > 200 * 1024) return IDL_E_CAPACITY;
-	const void *kfn = w < 0 ? (const void*)ksw2_batch_kernel<true> : (const void*)ksw2_batch_kernel<false>; // unbanded: the lean variant of kernel 2
+	const void *kfn = mode == 1 ? (const void*)ksw2_batch_kernel<1, 8> : mode == 2 ? (const void*)ksw2_batch_kernel<2, KSW_BAND_G> : (const void*)ksw2_batch_kernel<0, 8>;
 	cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-	const size_t per_cta = (size_t)wpc * DP_NG;
+	const size_t per_cta = (size_t)wpc * ng;
 	const int ctas = (int)std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)dp_grid(ctx, kfn, smem, 32 * wpc));
 	const size_t nwarps = (size_t)ctas * per_cta; // groups, each with its own workspace
 	const size_t qbytes = q_off[n], tbytes = t_off[n];
@@ -704,8 +719,9 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 		a.next = (unsigned*)dmisc.p; a.cig_used = (unsigned*)dmisc.p + 1; a.pmat = (uint8_t*)dp.p; a.cig_scratch = (uint32_t*)dscr.p;
 		CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 		CK(cudaEventRecord(e0, st));
-		if (w < 0) ksw2_batch_kernel<true><<<ctas, 32 * wpc, smem, st>>>(a);
-		else ksw2_batch_kernel<false><<<ctas, DP_THREADS, smem, st>>>(a);
+		if (mode == 1) ksw2_batch_kernel<1, 8><<<ctas, 32 * wpc, smem, st>>>(a);
+		else if (mode == 2) ksw2_batch_kernel<2, KSW_BAND_G><<<ctas, DP_THREADS, smem, st>>>(a);
+		else ksw2_batch_kernel<0, 8><<<ctas, DP_THREADS, smem, st>>>(a);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(e1, st));
 		CK(cudaMemcpyAsync(out, dout.p, n * sizeof(idl_ez), cudaMemcpyDeviceToHost, st));

@@ -174,3 +174,24 @@ def test_unbanded_other_scoring_parameters(ctx, match, mismatch, gapo, gape):
         if extra[i]["status"] < 0 or fo != f[i] or co != c[i]:
             bad.append((i, len(q), len(t), extra[i]["status"], fo, f[i]))
     assert bad == [], bad[:3]
+
+
+def test_register_ring_equals_shared_memory_ring(ctx, monkeypatch):
+    """the banded call-site runs with the band ring in registers (ksw2_band.cuh) for rounded bands of up to 96 lanes;
+    IDL_KSW2_COLUMNS=1 keeps those alignments on the shared-memory rings (ksw2.cuh): same records and CIGARs, for several band
+    widths incl. the widest one the register ring serves (w = 79) and one it does not (w = 80: both runs take the rings)"""
+    rng = np.random.default_rng(29)
+    for w, z in [(50, 400), (79, 400), (80, 400), (1, 100), (17, -1), (33, 60)]:
+        qs, ts = [], []
+        for _ in range(250):
+            ql = int(rng.integers(1, 700)); base = rng.integers(0, 4, ql + 400).astype(np.uint8)
+            q = base[:ql].copy(); t = base[:max(1, ql + int(rng.integers(-60, 260)))].copy()
+            pos = int(rng.integers(0, max(1, ql - 1))); L = int(rng.integers(1, 90))
+            q = np.concatenate([q[:pos], rng.integers(0, 4, L).astype(np.uint8), q[pos:]]) if rng.random() < 0.5 else np.concatenate([q[:pos], q[min(len(q) - 1, pos + L):]])
+            m = rng.random(len(q)) < 0.02; q[m] = rng.integers(0, 5, int(m.sum()))
+            qs.append(q); ts.append(t)
+        a = ctx.ksw2_batch(qs, ts, gapo=4, gape=1, w=w, zdrop=z)
+        monkeypatch.setenv("IDL_KSW2_COLUMNS", "1")
+        b = ctx.ksw2_batch(qs, ts, gapo=4, gape=1, w=w, zdrop=z)
+        monkeypatch.delenv("IDL_KSW2_COLUMNS")
+        assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2], (w, z)

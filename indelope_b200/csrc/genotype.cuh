@@ -26,8 +26,11 @@
 #ifndef KSW_BAND_G
 #define KSW_BAND_G 8 /* threads per alignment of the register-ring variant of the banded call-site (4 or 8) */
 #endif
+#ifndef KSW_BAND_WARPS
+#define KSW_BAND_WARPS 8 /* warps per CTA of the register-ring variant: 2 CTAs x 8 warps = 4 warps per scheduler at up to 128 registers */
+#endif
 #ifndef KSW_BAND_CTAS
-#define KSW_BAND_CTAS 3
+#define KSW_BAND_CTAS 2
 #endif
 #ifndef KSW_UNB_WARPS
 #define KSW_UNB_WARPS 5 /* warps per CTA of the unbanded al_kernel.  Measured on the chr1 workload (ms): 8 warps x 2 CTAs at 124 registers
@@ -184,7 +187,7 @@ __device__ __forceinline__ void align_body(const GenoArgs &g, unsigned char *sme
 		const uint8_t *tq = g.refcodes + R.ref_off + (cr.start - R.ref_start);
 		const uint8_t *qq = g.ctg_codes + cr.seq_off;
 		KswQuery kq; kq.codes = qq; kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
-		const KswMem M = dp_mem<G>(g, smem_raw, cr.len, tlen);
+		const KswMem M = dp_mem<G>(g, smem_raw, cr.len, tlen, BAND ? KSW_BAND_WARPS : DP_WARPS);
 		KswOut o;
 		if (BAND) ksw2_band<G, true>(valid, cr.len, kq, tlen, tq, g.kpA, M, o); // the whole warp: 32 / G alignments in lockstep
 		else ksw2_group<8>(valid, cr.len, kq, tlen, tq, g.kpA, M, o);
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(DP_THREADS, KSW_A_CTAS) align_kernel(GenoArgs 
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	align_body<8, false>(g, smem_raw);
 }
-__global__ void __launch_bounds__(DP_THREADS, KSW_BAND_CTAS) align_band_kernel(GenoArgs g) // rounded bands of up to 96 lanes (w <= 79): the ring in registers
+__global__ void __launch_bounds__(32 * KSW_BAND_WARPS, KSW_BAND_CTAS) align_band_kernel(GenoArgs g) // rounded bands of up to 96 lanes (w <= 79): the ring in registers
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	align_body<KSW_BAND_G, true>(g, smem_raw);

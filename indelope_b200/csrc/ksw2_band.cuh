@@ -21,6 +21,14 @@
 // maximum is a packed max per thread and one butterfly per diagonal; its position (SSE tie order) is looked up only when it can
 // raise the overall maximum or trigger z-drop.  The backtrack matrix has the reference's layout p[r][t - st] (pitch rounded to
 // 32 bytes) and is walked by ksw_backtrack's state machine (:47-79) through the shared 32 x 32 tile prefetch.
+//
+// MEASURED (round 2, profiles/r02_align_variants.txt): bit-exact, 10.4 G warp instructions against the shared-memory variant's 11.2 G on
+// the chr1 workload, but 13.8 ms against 12.9 ms: both are bound by the ALU pipe (one warp instruction per two cycles per scheduler:
+// LOP3 / PRMT / ISETP / SEL / SHF all issue there), and this variant turns the other one's shared-memory loads and stores (LSU pipe) into
+// selects, masks and slot dispatch on the ALU pipe (65 % of its instructions against ~50 %), at 4 instead of 6 warps per scheduler.
+// A block-owned layout of the same ring (thread = one 16-lane block, one SHFL per diagonal, 128-bit backtrack stores, straight-line code)
+// was also written and verified bit-exact: 10.9 G instructions, ALU pipe 84 % busy, 14.2 ms.  The shared-memory variant therefore stays
+// the default of the banded call-site; this one runs with IDL_BAND_REGS=1 and in the parity tests.
 #pragma once
 #include "ksw2.cuh"
 
@@ -28,7 +36,8 @@
 #define KSW_BAND_MAX_NCOL 96
 __host__ __device__ inline bool ksw_band_serves(int qlen, int tlen, int w) { return w >= 0 && ksw_ncol(qlen > 0 ? qlen : 1, tlen > 0 ? tlen : 1, w) <= KSW_BAND_MAX_NCOL; }
 // shared memory of a group: the reversed, padded query; later the 1 KB backtrack tile in the same bytes
-__host__ __device__ inline size_t ksw_band_smem(int seq_cap) { size_t b = (size_t)((seq_cap + 15) & ~15); if (b < KSW_BTILE_BYTES) b = KSW_BTILE_BYTES; return (b + 127) & ~(size_t)127; }
+// + 32 bytes for the end-of-query / end-of-target scores (KswBandEz)
+__host__ __device__ inline size_t ksw_band_smem(int seq_cap) { size_t b = (size_t)((seq_cap + 15) & ~15); if (b < KSW_BTILE_BYTES) b = KSW_BTILE_BYTES; return (b + 32 + 127) & ~(size_t)127; }
 
 // ksw_backtrack (:47-79, is_rot = 1) over p[r][t - off[r]] with the 32 x 32 tile prefetch; ALL 32 threads of the warp call it, G
 // threads per alignment (i = j = -1 for a group without a path).  The walker is thread 0 of the group; n / ovf come back in every
@@ -131,121 +140,96 @@ template <int G> __device__ __forceinline__ bool ksw_gany(bool p, int lane) { re
 
 // per-diagonal values shared by the slots of a thread
 struct KswBandDiag {
-	int st, st0, en0, en, bend;     // rounded band, exact band, one past the last lane of the score blocks
+	int st, en, en0;                 // rounded band (:205) and the last exact column
 	int cq;                          // lane t meets the reversed-query byte cq + t
-	unsigned uon, ubd, onm;          // slots with a word of [st, max(en, bend-1)] in this thread (onm) / in any thread of the warp (uon); ubd: some thread's word there is not interior
-	bool first_const;                // the word at st takes the constant boundary (x1 = 0, v1 = v1c) instead of its left neighbour
-	uint32_t v1c;                    // v1 << 8 (byte 1 of the neighbour word)
+	unsigned uon, onm;               // slots with a word of [st, max(en, bend-1)] in this thread (onm) / in any thread of the warp (uon)
+	uint32_t A4, B4, E4;             // st0 - st, bend - st, en0 - st, replicated into the four bytes (all <= 111)
+	uint32_t nb_first;               // what the word at st reads instead of its left neighbour when the boundary is constant (x1 = 0, v1 << 8), else ~0
 	uint8_t *prow;                   // backtrack row of this diagonal, column st
 	const uint32_t *qrp;             // reversed query words (shared memory), KSW_QR_PAD bytes of zeros in front
 	bool wild, fast_ok;
-	int r, last_st0, last_en0, qlen, tlen, w, qe;
+	int r, st0, last_st0, last_en0, qlen, tlen, w, qe;
 };
 
-// One slot of one diagonal.  INTERIOR: every thread of the warp whose word in this slot is live has all four lanes inside the exact
-// band [st0, en0) and right of st: fresh scores, no masks.  Otherwise the general form: lanes [st0, bend) get fresh scores and the
-// others keep their stale ones (:215-228), the word at st may take the constant boundary, words right of en only update scores,
-// the exact scores of lanes [st0, en0) are updated (:323-348) and the word that holds en0 builds H[en0] (:318).
-template <int G, int NS, int S, bool INTERIOR>
-__device__ __forceinline__ void ksw_band_slot(const KswParams &P, const KswBandDiag &dg, uint32_t recv, const int (&tcol)[NS], uint32_t (&x)[NS], uint32_t (&v)[NS], uint32_t (&u)[NS],
-                                              uint32_t (&y)[NS], uint32_t (&Sc)[NS], const uint32_t (&T)[NS], uint32_t (&gx)[NS], uint32_t (&gy)[NS], uint32_t &bh2, unsigned &ghen)
+// One slot of one diagonal, every case in one branch-free form (byte masks from lane numbers relative to st, all below 128):
+// lanes [st0, bend) get fresh scores and the others keep their stale ones (:215-228); words up to en run the core (:262-284), the word
+// at st with the constant boundary when the left neighbour is not valid (:207-211); words right of en only had their scores
+// updated; the exact scores of lanes [st0, en0) are updated (:323-348); the word that holds en0 builds H[en0] (:318).
+template <int G, int NS, int S>
+__device__ __forceinline__ void ksw_band_slot(const KswParams &P, const KswBandDiag &dg, const uint32_t recv, const int (&tcol)[NS], uint32_t (&x)[NS], uint32_t (&v)[NS], uint32_t (&u)[NS],
+                                              uint32_t (&y)[NS], uint32_t (&Sc)[NS], const uint32_t (&T)[NS], uint32_t (&gx)[NS], uint32_t (&gy)[NS], uint32_t &bh2)
 {
-	const int t = tcol[S];
-	const int cqt = dg.cq + t; // >= -KSW_QR_PAD for every lane the score blocks touch
+	const int t = tcol[S], d0 = t - dg.st;                       // d0 in [0, 124]
+	const int cqt = dg.cq + t;                                   // >= -KSW_QR_PAD for every lane the score blocks touch
 	const uint32_t *qw = dg.qrp + (cqt >> 2);
 	const uint32_t sq2 = __funnelshift_r(qw[0], qw[1], 8 * (cqt & 3));
 	const uint32_t sq = T[S];
 	uint32_t sc = sel4(msb_to_mask4((sq ^ sq2) + 0x7f7f7f7fu), P.misq_4, P.maxsc_4);
 	if (dg.wild) sc = ksw_wild_score(sq, sq2, sc, P.qe2_4);
-	if (INTERIOR) {
-		Sc[S] = sc;
-		const uint32_t xt1 = __byte_perm(recv, x[S], 0x6540), vt1 = __byte_perm(recv, v[S], 0x6541);
+	const uint32_t O80 = (uint32_t)d0 * 0x01010101u + 0x83828180u; // 0x80 + lane number relative to st, per byte
+	const uint32_t mA = msb_to_mask4(O80 - dg.A4);               // lanes >= st0
+	const uint32_t mB = msb_to_mask4(O80 - dg.B4);               // lanes >= bend
+	const uint32_t z0 = sel4(mA & ~mB, sc, Sc[S]);
+	Sc[S] = z0;
+	if (t <= dg.en) { // core over the rounded band
+		const uint32_t nb = (d0 == 0 && dg.nb_first != 0xffffffffu) ? dg.nb_first : recv; // x, v of the lane left of this word
+		const uint32_t xt1 = __byte_perm(nb, x[S], 0x6540), vt1 = __byte_perm(nb, v[S], 0x6541);
 		uint32_t d, un, vn, xn, yn;
-		ksw_core_word(P, dg.fast_ok, sc, xt1, vt1, u[S], y[S], xn, vn, un, yn, d);
+		ksw_core_word(P, dg.fast_ok, z0, xt1, vt1, u[S], y[S], xn, vn, un, yn, d);
 		x[S] = xn; v[S] = vn; u[S] = un; y[S] = yn;
-		KSW_PSTORE((uint32_t*)(dg.prow + (t - dg.st)), d);
-		gx[S] += __byte_perm(vn, 0u, 0x4140); gy[S] += __byte_perm(vn, 0u, 0x4342);
-		bh2 = __vimax3_u16x2(bh2, gx[S], gy[S]);
-	} else {
-		{ // scores: lanes [lo, hi) of this word belong to the 16-wide blocks
-			const int lo = dg.st0 - t, hi = dg.bend - t;
-			if (hi > 0 && lo < 4) {
-				uint32_t m = 0xffffffffu;
-				if (lo > 0) m <<= 8 * lo;
-				if (hi < 4) m &= 0xffffffffu >> (8 * (4 - hi));
-				Sc[S] = sel4(m, sc, Sc[S]);
-			}
-		}
-		if (t <= dg.en) { // core over the rounded band
-			const uint32_t nb = (t == dg.st && dg.first_const) ? dg.v1c : recv; // x, v of the lane left of this word; recv keeps the neighbour's exact score
-			const uint32_t xt1 = __byte_perm(nb, x[S], 0x6540), vt1 = __byte_perm(nb, v[S], 0x6541);
-			uint32_t d, un, vn, xn, yn;
-			ksw_core_word(P, dg.fast_ok, Sc[S], xt1, vt1, u[S], y[S], xn, vn, un, yn, d);
-			x[S] = xn; v[S] = vn; u[S] = un; y[S] = yn;
-			KSW_PSTORE((uint32_t*)(dg.prow + (t - dg.st)), d);
-			const int lo = dg.st0 - t, hi = dg.en0 - t; // exact scores of the in-band columns st0 .. en0-1 of this word: g[t] += v8[t]
-			const uint32_t gox = gx[S], goy = gy[S];     // the old scores: H[en0] is built from the OLD H[en0-1] (:318)
-			if (hi > 0 && lo < 4) {
-				if (lo <= 0 && hi >= 4) {
-					gx[S] += __byte_perm(vn, 0u, 0x4140); gy[S] += __byte_perm(vn, 0u, 0x4342);
-					bh2 = __vimax3_u16x2(bh2, gx[S], gy[S]);
-				} else {
-					uint32_t m = 0xffffffffu;
-					if (lo > 0) m <<= 8 * lo;
-					if (hi < 4) m &= 0xffffffffu >> (8 * (4 - hi));
-					const uint32_t vm = vn & m;
-					gx[S] += __byte_perm(vm, 0u, 0x4140); gy[S] += __byte_perm(vm, 0u, 0x4342);
-					bh2 = __vimax3_u16x2(bh2, gx[S] & __byte_perm(m, 0u, 0x1100), gy[S] & __byte_perm(m, 0u, 0x3322));
-				}
-			}
-			if (hi >= 0 && hi < 4) { // this word holds en0: H[en0] (:318 / :349), kept as g
-				unsigned gh;
-				if (dg.r == 0) gh = (unsigned)((int)(vn & 0xffu) - dg.qe + 2 * dg.qe); // H[0] = v[0] - 2(q+e), g = H + (q+e) + bias
-				else {
-					unsigned gprev; // g of column c = max(en0 - 1, 0) before this diagonal's update
-					if (dg.en0 == 0) gprev = gox & 0xffffu;
-					else if (hi == 0) gprev = recv >> 16;
-					else gprev = ((hi - 1) & 2 ? goy : gox) >> (16 * ((hi - 1) & 1)) & 0xffffu;
-					const int c = dg.en0 > 0 ? dg.en0 - 1 : 0;
-					if (c < dg.last_st0 || c > dg.last_en0) { // the column was not part of the previous band: its offset is older (the band left the matrix on the right)
-						int rr = dg.r - 1;
-						for (; rr > 0; --rr) { int s_, e_; ksw_band(rr, dg.qlen, dg.tlen, dg.w, s_, e_); if (s_ <= c && c <= e_) break; }
-						gprev += (unsigned)(dg.qe * (dg.r - 1 - rr));
-					}
-					const uint32_t add = dg.en0 > 0 ? un : vn; // + u8[en0] or + v8[en0]
-					gh = gprev + ((add >> (8 * hi)) & 0xffu);
-				}
-				ghen = gh;
-				const uint32_t ins = (gh & 0xffffu) << (16 * (hi & 1)), keep = 0xffffu << (16 * ((hi & 1) ^ 1));
-				if (hi & 2) gy[S] = (gy[S] & keep) | ins; else gx[S] = (gx[S] & keep) | ins;
-			}
-		}
+		KSW_PSTORE((uint32_t*)(dg.prow + d0), d);
+		const uint32_t mG = mA & ~msb_to_mask4(O80 - dg.E4);       // lanes in [st0, en0): g[t] += v8[t] (:323-348)
+		const uint32_t vm = vn & mG;
+		gx[S] += __byte_perm(vm, 0u, 0x4140); gy[S] += __byte_perm(vm, 0u, 0x4342);
+		bh2 = __vimax3_u16x2(bh2, gx[S] & __byte_perm(mG, 0u, 0x1100), gy[S] & __byte_perm(mG, 0u, 0x3322));
 	}
 }
+
+// H[en0] (:318 / :349), kept as g: H[en0] = H_old[en0 - 1] + u_new[en0] - (q+e) (v_new[0] on column 0).  Runs once per diagonal, after the
+// slots, in the thread that owns column en0; `gprev` = g of column max(en0 - 1, 0) before this diagonal's update, re-based by the caller.
+template <int NS, int S>
+__device__ __forceinline__ unsigned ksw_band_en0(int en0, unsigned gprev, const uint32_t (&u)[NS], const uint32_t (&v)[NS], uint32_t (&gx)[NS], uint32_t (&gy)[NS])
+{
+	const int hi = en0 & 3;
+	const uint32_t add = en0 > 0 ? u[S] : v[S]; // + u8[en0] or + v8[en0]
+	const unsigned gh = gprev + ((add >> (8 * hi)) & 0xffu);
+	const uint32_t ins = (gh & 0xffffu) << (16 * (hi & 1)), keep = 0xffffu << (16 * ((hi & 1) ^ 1));
+	if (hi & 2) gy[S] = (gy[S] & keep) | ins; else gx[S] = (gx[S] & keep) | ins;
+	return gh;
+}
+template <int NS, int S>
+__device__ __forceinline__ unsigned ksw_band_glane(int c, const uint32_t (&gx)[NS], const uint32_t (&gy)[NS]) { return (((c & 2) ? gy[S] : gx[S]) >> (16 * (c & 1))) & 0xffffu; }
 
 // the slots of one diagonal, unrolled by template recursion (constant register indices from the start)
 template <int G, int NS, int S>
 struct KswBandSlots {
-	static __device__ __forceinline__ void run(const KswParams &P, const KswBandDiag &dg, const uint32_t (&recv)[NS], const int (&tcol)[NS], uint32_t (&x)[NS], uint32_t (&v)[NS],
-	                                           uint32_t (&u)[NS], uint32_t (&y)[NS], uint32_t (&Sc)[NS], const uint32_t (&T)[NS], uint32_t (&gx)[NS], uint32_t (&gy)[NS], uint32_t &bh2, unsigned &ghen)
+	static __device__ __forceinline__ void run(const KswParams &P, const KswBandDiag &dg, const int srcl, const int gl, const int (&tcol)[NS], uint32_t (&x)[NS], uint32_t (&v)[NS],
+	                                           uint32_t (&u)[NS], uint32_t (&y)[NS], uint32_t (&Sc)[NS], const uint32_t (&T)[NS], uint32_t (&gx)[NS], uint32_t (&gy)[NS],
+	                                           const uint32_t (&C)[NS], uint32_t &bh2)
 	{
 		if (dg.uon & (1u << S)) {
-			const bool on = (dg.onm & (1u << S)) != 0u;
-			if (dg.ubd & (1u << S)) { if (on) ksw_band_slot<G, NS, S, false>(P, dg, recv[S], tcol, x, v, u, y, Sc, T, gx, gy, bh2, ghen); }
-			else if (on) ksw_band_slot<G, NS, S, true>(P, dg, recv[S], tcol, x, v, u, y, Sc, T, gx, gy, bh2, ghen);
+			// the neighbour exchange: the word left of thread 0's word in slot s sits in the previous slot of thread G-1.  C holds the values of
+			// the previous diagonal for every slot, so the order in which the slots are updated does not matter.
+			const uint32_t recv = __shfl_sync(FULL_MASK, gl == G - 1 ? C[(S + NS - 1) % NS] : C[S], srcl);
+			if (dg.onm & (1u << S)) ksw_band_slot<G, NS, S>(P, dg, recv, tcol, x, v, u, y, Sc, T, gx, gy, bh2);
 		}
-		KswBandSlots<G, NS, S + 1>::run(P, dg, recv, tcol, x, v, u, y, Sc, T, gx, gy, bh2, ghen);
+		KswBandSlots<G, NS, S + 1>::run(P, dg, srcl, gl, tcol, x, v, u, y, Sc, T, gx, gy, C, bh2);
 	}
 };
 template <int G, int NS>
 struct KswBandSlots<G, NS, NS> {
-	static __device__ __forceinline__ void run(const KswParams &, const KswBandDiag &, const uint32_t (&)[NS], const int (&)[NS], uint32_t (&)[NS], uint32_t (&)[NS], uint32_t (&)[NS],
-	                                           uint32_t (&)[NS], uint32_t (&)[NS], const uint32_t (&)[NS], uint32_t (&)[NS], uint32_t (&)[NS], uint32_t &, unsigned &) {}
+	static __device__ __forceinline__ void run(const KswParams &, const KswBandDiag &, const int, const int, const int (&)[NS], uint32_t (&)[NS], uint32_t (&)[NS], uint32_t (&)[NS],
+	                                           uint32_t (&)[NS], uint32_t (&)[NS], const uint32_t (&)[NS], uint32_t (&)[NS], uint32_t (&)[NS], const uint32_t (&)[NS], uint32_t &) {}
 };
+
+// end-of-query / end-of-target scores of ksw_extz_t, kept in shared memory while the DP runs (they change on few diagonals and would
+// otherwise hold five registers for the whole loop)
+struct KswBandEz { int mqe, mqe_t, mte, mte_q, score, pad[3]; };
 
 // ALL 32 threads of a warp call this together: 32 / G groups of G threads, one alignment per group (valid = 0 for a group without one),
 // the anti-diagonal loop in lockstep over the groups.  The caller has checked ksw_band_serves(qlen, tlen, P.w) for every valid group.
-// M.seq (seq_cap bytes) stages the reversed query; M.xvuy points at 1 KB of shared memory for the backtrack tile (it may alias M.seq).
+// M.seq (seq_cap bytes) stages the reversed query; M.xvuy points at 1 KB of shared memory for the backtrack tile (it may alias M.seq);
+// the last 32 bytes of the group's shared-memory region (M.region_bytes) hold a KswBandEz.
 template <int G, bool EZ_FULL>
 __device__ void ksw2_band(bool valid, int qlen, const KswQuery query, int tlen, const uint8_t *target, const KswParams P, const KswMem M, KswOut &out)
 {
@@ -264,13 +248,14 @@ __device__ void ksw2_band(bool valid, int qlen, const KswQuery query, int tlen, 
 		if (qlen <= 0 || tlen <= 0) { out.status = KSW_ST_EARLY; live = false; }     // :147
 		else if (-min_sc > 2 * qe) { out.status = KSW_ST_EARLY; live = false; }      // :171
 		else if (w < 0 || n_col > KSW_BAND_MAX_NCOL) { out.status = KSW_ST_RCAP; live = false; } // the caller picked the wrong variant
-		else if (ksw_seq_bytes(qlen, tlen) > (size_t)M.seq_cap) { out.status = KSW_ST_SEQCAP; live = false; }
+		else if (ksw_seq_bytes(qlen, tlen) + sizeof(KswBandEz) > (size_t)M.seq_cap) { out.status = KSW_ST_SEQCAP; live = false; } // the staging area ends 32 bytes early: KswBandEz
 		else if ((size_t)(qlen + tlen - 1) * (size_t)pitch + 2 * KSW_PMAT_PAD > M.p_cap) { out.status = KSW_ST_PCAP; live = false; }
 		else if ((long long)(qlen + tlen + 2) * qe + (long long)(qlen < tlen ? qlen : tlen) * (P.match > 0 ? P.match : 0) + gbias >= 0xF000) { out.status = KSW_ST_HCAP; live = false; }
 	}
 	const bool run = live;
 	uint8_t *pmat = M.pmat + KSW_PMAT_PAD;
 	uint8_t *qrp = M.seq;
+	KswBandEz *ez = (KswBandEz*)((unsigned char*)M.xvuy + (M.region_bytes - (int)sizeof(KswBandEz)));
 	const int nr = live ? qlen + tlen - 1 : 0;
 
 	// the ring: slot s of this thread starts as column word s * G + gl; every lane reads as calloc'ed memory (:173), the stale scores as
@@ -291,6 +276,7 @@ __device__ void ksw2_band(bool valid, int qlen, const KswQuery query, int tlen, 
 			const uint8_t c = (k >= 0 && k < qlen) ? ksw_query_code(query, qlen - 1 - k) : (uint8_t)0; wild |= c == 4; qrp[i] = c;
 		}
 	}
+	if (gl == 0) { ez->mqe = ez->mte = ez->score = KSW_NEG_INF; ez->mqe_t = ez->mte_q = -1; }
 	wild = ksw_gany<G>(wild, lane);
 	__syncwarp();
 
@@ -298,54 +284,82 @@ __device__ void ksw2_band(bool valid, int qlen, const KswQuery query, int tlen, 
 	dg.qrp = (const uint32_t*)qrp + (KSW_QR_PAD >> 2); dg.qlen = qlen; dg.tlen = tlen; dg.w = w; dg.qe = qe;
 	dg.fast_ok = P.match + 2 * qe <= 63 && P.q >= 0 && P.q + 2 * P.e + min_sc >= 0;
 	const int srcl = (lane & ~(G - 1)) | ((gl + G - 1) & (G - 1)); // the thread that owns the word left of mine
-	int last_st = -1, last_en = -1, last_st0 = 0, last_en0 = -1, en_clr = 15, base = 0; // ring = columns [base, base + 128)
-	unsigned g_high = 0;
+	int last_st0 = 0, last_en0 = -1, base = 0;                     // ring = columns [base, base + 128)
+	unsigned g_high = 0, cells = 0;
 	int st0 = 0, en0 = 0;
-	for (int r = 0; ; ++r) {
+	uint8_t *prow = pmat;
+	for (int r = 0; ; ++r, prow += pitch) {
 		bool act = live && r < nr;
 		if (act && st0 > en0) { out.zdropped = 1; live = false; act = false; } // :200-203
 		if (!__any_sync(FULL_MASK, act)) break;
 		const int st = st0 & ~15, en = en0 | 15;    // :205
-		if (act) out.cells += en0 - st0 + 1;
-		const bool keep_prev = st > 0 && st - 1 >= last_st && st - 1 <= last_en; // :207-211
+		if (act) cells += (unsigned)(en0 - st0 + 1);
 		const int bend = st0 + (int)((((unsigned)(en0 - st0) >> 4) + 1u) << 4);
-		const int wl_last = (en > bend - 1 ? en : bend - 1) | 3;
-		const int en1 = st0 + (((en0 - st0) >> 2) << 2);
-		const unsigned bandw = (unsigned)(en0 - st0);
+		const int wl_last = en > bend - 1 ? en : bend - 1;
 		const int goff = qe * (r + 1) + gbias;
-		// the neighbour exchange, for every slot, before any word of this diagonal is updated: top x lane, top v lane, top exact score
-		uint32_t recv[NS];
-		{
-			uint32_t C[NS];
+		// the values the neighbours will ask for, from every slot, before any word of this diagonal is updated: top x lane, top v lane,
+		// top exact score
+		uint32_t C[NS];
 #pragma unroll
-			for (int s = 0; s < NS; ++s) C[s] = __byte_perm(__byte_perm(x[s], v[s], 0x0073), gy[s], 0x7610);
-#pragma unroll
-			for (int s = 0; s < NS; ++s) {
-				uint32_t send = C[s];
-				if (gl == G - 1) send = C[(s + NS - 1) % NS]; // the word left of thread 0's word in slot s sits in the previous slot of thread G-1
-				recv[s] = __shfl_sync(FULL_MASK, send, srcl);
-			}
+		for (int s = 0; s < NS; ++s) C[s] = __byte_perm(__byte_perm(x[s], v[s], 0x0073), gy[s], 0x7610);
+		{ // which of my slots hold a word of this diagonal
+			// my words are gl + G k: those of [st, wl_last] are the rounds k in [kA, kB], at most NS of them, in slots k % NS
+			const int kA = ((st >> 2) - gl + G - 1) / G, kB = ((wl_last >> 2) - gl) >= 0 ? ((wl_last >> 2) - gl) / G : -1; // st >= 0: no negative division on the left
+			const int nk = act ? kB - kA + 1 : 0;
+			const unsigned m = nk > 0 ? (1u << nk) - 1u : 0u, sh = (unsigned)kA % NS;
+			const unsigned onm = ((m << sh) | (m << sh >> NS)) & ((1u << NS) - 1u);
+			dg.onm = onm; dg.uon = __reduce_or_sync(FULL_MASK, onm);
 		}
-		// which of my slots hold a word of this diagonal, and which of those are interior
 		{
-			const int ilo = st0 > st ? st0 : st + 4, ihi = en0 - 4;
-			unsigned onm = 0, inm = 0;
-#pragma unroll
-			for (int s = 0; s < NS; ++s) {
-				const int t = tcol[s];
-				const bool on = act && t >= st && t <= wl_last;
-				onm |= (unsigned)on << s; inm |= (unsigned)(on && t >= ilo && t <= ihi) << s;
-			}
-			dg.onm = onm; dg.uon = __reduce_or_sync(FULL_MASK, onm); dg.ubd = __reduce_or_sync(FULL_MASK, onm & ~inm);
+			// boundary conditions :207-211 (values of the previous diagonal): the word left of st supplies x[st-1], v[st-1] when it was
+			// inside the previous rounded band, else x1 = 0 and v1 = q (0 on diagonal 0, and 0 when st > 0)
+			const bool keep_prev = st > 0 && st - 1 >= (last_st0 & ~15) && st - 1 <= (last_en0 | 15) && last_en0 >= 0;
+			dg.nb_first = keep_prev ? 0xffffffffu : ((st == 0 && r) ? ((uint32_t)(P.q & 0xff) << 8) : 0u);
 		}
-		dg.st = st; dg.st0 = st0; dg.en0 = en0; dg.en = en; dg.bend = bend; dg.cq = qlen - 1 - r; dg.r = r; dg.last_st0 = last_st0; dg.last_en0 = last_en0;
-		dg.first_const = !keep_prev; dg.v1c = (st == 0 && r) ? ((uint32_t)(P.q & 0xff) << 8) : 0u;
-		dg.prow = pmat + (size_t)r * pitch; dg.wild = wild;
-		uint32_t bh2 = 0; unsigned ghen = 0;
-		KswBandSlots<G, NS, 0>::run(P, dg, recv, tcol, x, v, u, y, Sc, T, gx, gy, bh2, ghen);
-		// band max of the updated columns, then the en0 cell (:318 / :349): its owner computed it, everyone needs it
+		dg.st = st; dg.en = en; dg.en0 = en0; dg.st0 = st0; dg.cq = qlen - 1 - r; dg.r = r; dg.last_st0 = last_st0; dg.last_en0 = last_en0;
+		dg.A4 = (uint32_t)(st0 - st) * 0x01010101u; dg.B4 = (uint32_t)(bend - st) * 0x01010101u; dg.E4 = (uint32_t)(en0 - st) * 0x01010101u;
+		dg.prow = prow; dg.wild = wild;
+		// H[en0] is built from the OLD H[en0-1] (:318): fetch it from its owner before this diagonal's updates.  Column word wi always
+		// sits in slot (wi / G) % NS of thread wi % G (recycling moves a slot by NS * G words), so the slot is a uniform switch.
+		unsigned gprev = 0;
+		{
+			const int c = en0 > 0 ? en0 - 1 : 0;
+			switch (((c >> 2) / G) % NS) {
+			case 0: gprev = ksw_band_glane<NS, 0>(c, gx, gy); break;
+			case 1: gprev = ksw_band_glane<NS, 1 % NS>(c, gx, gy); break;
+			case 2: gprev = ksw_band_glane<NS, 2 % NS>(c, gx, gy); break;
+			case 3: gprev = ksw_band_glane<NS, 3 % NS>(c, gx, gy); break;
+			case 4: gprev = ksw_band_glane<NS, 4 % NS>(c, gx, gy); break;
+			case 5: gprev = ksw_band_glane<NS, 5 % NS>(c, gx, gy); break;
+			case 6: gprev = ksw_band_glane<NS, 6 % NS>(c, gx, gy); break;
+			default: gprev = ksw_band_glane<NS, 7 % NS>(c, gx, gy); break;
+			}
+			gprev = __shfl_sync(FULL_MASK, gprev, (lane & ~(G - 1)) | ((c >> 2) & (G - 1)));
+			if (act && r > 0 && (c < last_st0 || c > last_en0)) { // the column was not part of the previous band: its offset is older (the band left the matrix on the right)
+				int rr = r - 1;
+				for (; rr > 0; --rr) { int s_, e_; ksw_band(rr, qlen, tlen, w, s_, e_); if (s_ <= c && c <= e_) break; }
+				gprev += (unsigned)(qe * (r - 1 - rr));
+			}
+			if (r == 0) gprev = (unsigned)qe; // H[0] = v[0] - 2(q+e): g = H + (q+e) + bias = v[0] + (q+e)
+		}
+		uint32_t bh2 = 0;
+		KswBandSlots<G, NS, 0>::run(P, dg, srcl, gl, tcol, x, v, u, y, Sc, T, gx, gy, C, bh2);
+		// band max of the updated columns, then the en0 cell (:318 / :349): its owner computes it, everyone needs it
 		unsigned mg = (bh2 & 0xffffu) > (bh2 >> 16) ? (bh2 & 0xffffu) : (bh2 >> 16);
 		mg = ksw_gmax<G>(mg);
+		unsigned ghen = 0;
+		if (act && gl == ((en0 >> 2) & (G - 1))) {
+			switch (((en0 >> 2) / G) % NS) {
+			case 0: ghen = ksw_band_en0<NS, 0>(en0, gprev, u, v, gx, gy); break;
+			case 1: ghen = ksw_band_en0<NS, 1 % NS>(en0, gprev, u, v, gx, gy); break;
+			case 2: ghen = ksw_band_en0<NS, 2 % NS>(en0, gprev, u, v, gx, gy); break;
+			case 3: ghen = ksw_band_en0<NS, 3 % NS>(en0, gprev, u, v, gx, gy); break;
+			case 4: ghen = ksw_band_en0<NS, 4 % NS>(en0, gprev, u, v, gx, gy); break;
+			case 5: ghen = ksw_band_en0<NS, 5 % NS>(en0, gprev, u, v, gx, gy); break;
+			case 6: ghen = ksw_band_en0<NS, 6 % NS>(en0, gprev, u, v, gx, gy); break;
+			default: ghen = ksw_band_en0<NS, 7 % NS>(en0, gprev, u, v, gx, gy); break;
+			}
+		}
 		ghen = __shfl_sync(FULL_MASK, ghen, (lane & ~(G - 1)) | ((en0 >> 2) & (G - 1)));
 		if (!act) ghen = 0;
 		const int hen = (int)ghen - goff;
@@ -357,13 +371,19 @@ __device__ void ksw2_band(bool valid, int qlen, const KswQuery query, int tlen, 
 		if (__any_sync(FULL_MASK, need_t)) { // position of the band max in the SSE tie order (:316-348), only when it matters
 			unsigned best = 0xffffffffu;
 			if (need_t) {
+				const int en1 = st0 + (((en0 - st0) >> 2) << 2);
+				const unsigned bandw = (unsigned)(en0 - st0);
+				const uint32_t mg2 = mg * 0x10001u;
 #pragma unroll
 				for (int s = 0; s < NS; ++s) {
+					const uint32_t xa = gx[s] ^ mg2, xb = gy[s] ^ mg2; // a zero halfword = a column that holds the band max (if it is in the band)
+					if ((((xa - 0x00010001u) & ~xa) | ((xb - 0x00010001u) & ~xb)) & 0x80008000u) {
 #pragma unroll
-					for (int c = 0; c < 4; ++c) {
-						const unsigned val = ((c < 2 ? gx[s] : gy[s]) >> (16 * (c & 1))) & 0xffffu;
-						const int t = tcol[s] + c;
-						if ((unsigned)(t - st0) < bandw && val == mg) { const unsigned rk = ksw_tie_rank(t, st0, en1); best = rk < best ? rk : best; }
+						for (int c = 0; c < 4; ++c) {
+							const unsigned val = ((c < 2 ? gx[s] : gy[s]) >> (16 * (c & 1))) & 0xffffu;
+							const int t = tcol[s] + c;
+							if ((unsigned)(t - st0) < bandw && val == mg) { const unsigned rk = ksw_tie_rank(t, st0, en1); best = rk < best ? rk : best; }
+						}
 					}
 				}
 			}
@@ -371,19 +391,21 @@ __device__ void ksw2_band(bool valid, int qlen, const KswQuery query, int tlen, 
 			if (need_t) { max_H = mh; max_t = st0 + (int)((rk - 1) & 0xfffffu); }
 		}
 		if (EZ_FULL) {
-			if (act && en0 == tlen - 1) {
-				if (hen > out.mte) { out.mte = hen; out.mte_q = r - en; }
-				if (r == qlen + tlen - 2) out.score = hen; // H[tlen-1]
-			}
-			const bool at_qend = act && r - st0 == qlen - 1;
-			if (__any_sync(FULL_MASK, at_qend)) { // H[st0] of the last query row (:353-354): its owner has it
-				unsigned gv = 0;
+			const bool at_tend = act && en0 == tlen - 1, at_qend = act && r - st0 == qlen - 1;
+			if (__any_sync(FULL_MASK, at_tend || at_qend)) {
+				unsigned gv = 0; // H[st0] of the last query row (:353-354): its owner has it
 #pragma unroll
 				for (int s = 0; s < NS; ++s) if (tcol[s] == (st0 & ~3)) gv = (((st0 & 2) ? gy[s] : gx[s]) >> (16 * (st0 & 1))) & 0xffffu;
 				gv = __shfl_sync(FULL_MASK, gv, (lane & ~(G - 1)) | ((st0 >> 2) & (G - 1)));
-				if (at_qend) {
-					const int Hst0 = st0 == en0 ? hen : (int)gv - goff;
-					if (Hst0 > out.mqe) { out.mqe = Hst0; out.mqe_t = st0; }
+				if (gl == 0) {
+					if (at_tend) {
+						if (hen > ez->mte) { ez->mte = hen; ez->mte_q = r - en; }
+						if (r == qlen + tlen - 2) ez->score = hen; // H[tlen-1]
+					}
+					if (at_qend) {
+						const int Hst0 = st0 == en0 ? hen : (int)gv - goff;
+						if (Hst0 > ez->mqe) { ez->mqe = Hst0; ez->mqe_t = st0; }
+					}
 				}
 			}
 		}
@@ -391,21 +413,20 @@ __device__ void ksw2_band(bool valid, int qlen, const KswQuery query, int tlen, 
 		int st0n, en0n;
 		ksw_band(r + 1, qlen, tlen, w, st0n, en0n);
 		const bool nxt = act && r + 1 < nr && st0n <= en0n;
-		const bool enter = nxt && (en0n | 15) > en_clr;
+		// the ring must reach 16 lanes past the rounded band (the score overrun): when the next band needs more, recycle the 16 leftmost
+		// columns -- dead by then -- for the 16 columns right of the ring; they read as never written (calloc), scores as s = 0
+		const bool enter = nxt && base + 128 < (en0n | 15) + 17;
 		if (__any_sync(FULL_MASK, enter)) {
 			bool w4 = false;
 			if (enter) {
-				en_clr += 16;
-				if (base + 128 < en_clr + 17) { // the ring must reach 16 lanes past the block that enters (the score overrun): recycle the 16 leftmost columns
-					base += 16;
+				base += 16;
 #pragma unroll
-					for (int s = 0; s < NS; ++s)
-						if (tcol[s] < base) {
-							tcol[s] += 128;
-							x[s] = v[s] = u[s] = y[s] = 0u; Sc[s] = P.qe2_4;
-							T[s] = ksw_target_word(target, tlen, tcol[s]); w4 |= ksw_has4(T[s]);
-						}
-				}
+				for (int s = 0; s < NS; ++s)
+					if (tcol[s] < base) {
+						tcol[s] += 128;
+						x[s] = v[s] = u[s] = y[s] = 0u; Sc[s] = P.qe2_4;
+						T[s] = ksw_target_word(target, tlen, tcol[s]); w4 |= ksw_has4(T[s]);
+					}
 			}
 			wild |= ksw_gany<G>(w4, lane);
 		}
@@ -426,10 +447,13 @@ __device__ void ksw2_band(bool valid, int qlen, const KswQuery query, int tlen, 
 				if (P.zdrop >= 0 && out.max - max_H > P.zdrop + l * P.e) { out.zdropped = 1; live = false; }
 			}
 		}
-		last_st = st; last_en = en; last_st0 = st0; last_en0 = en0;
+		last_st0 = st0; last_en0 = en0;
 		st0 = st0n; en0 = en0n;
 	}
 	if (g_high) out.status = KSW_ST_HCAP;
+	out.cells = (long long)cells;
+	__syncwarp();
+	if (EZ_FULL && run) { out.mqe = ez->mqe; out.mqe_t = ez->mqe_t; out.mte = ez->mte; out.mte_q = ez->mte_q; out.score = ez->score; }
 	__syncwarp();
 	// backtrack :380-385
 	int i = -1, j = -1;
@@ -443,3 +467,4 @@ __device__ void ksw2_band(bool valid, int qlen, const KswQuery query, int tlen, 
 	if (ovf) out.status = KSW_ST_CIGCAP;
 	__syncwarp();
 }
+

@@ -87,6 +87,7 @@ struct idl_ctx {
 	uint64_t next_ticket = 1;
 	int asm_ctas = 0, dp_ctas = 0, ns = 0, nw = 0;
 	int cig_cap = 2048;
+	bool band_regs = false; // IDL_BAND_REGS=1: the banded call-site keeps its band ring in registers (ksw2_band.cuh) instead of shared memory (measured slower, kept for the parity tests)
 	char err[512] = {0};
 };
 
@@ -178,6 +179,7 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	const char *ea = getenv("IDL_ASM_CTAS_PER_SM"), *ed = getenv("IDL_DP_CTAS_PER_SM");
 	ctx->asm_ctas = ctx->n_sm * (ea && atoi(ea) > 0 ? atoi(ea) : 4); // CTAs of each assembler launch (8 regions per CTA in the warp variant)
 	ctx->dp_ctas = ctx->n_sm * (ed && atoi(ed) > 0 ? atoi(ed) : 4); // upper bound; every launch asks the occupancy calculator
+	{ const char *eb = getenv("IDL_BAND_REGS"); ctx->band_regs = eb && *eb == '1'; }
 	ctx->lanes.resize((size_t)p->n_streams);
 	{
 		// IDL_OVERLAP_KERNELS=1: the kernels of a batch run on its lane's stream and may share the SMs with another batch's
@@ -354,11 +356,11 @@ int launch_chain(idl_ctx *ctx, Lane &L, bool record_start = false)
 	const size_t rowsB = (size_t)max_trim + std::max<size_t>(max_ref, 1536);
 	const size_t pitchB = std::max<size_t>(ksw_pitch(ncolB), P.b_bw < 0 ? 32 * (size_t)ksw_rows_w(max_trim) : 0); // the row-owned variant stores 32 W bytes per diagonal
 	// the banded call-site runs the register-ring variant whenever its band fits (w <= 79: indelope's 50 does), G threads per alignment
-	const bool bandA = P.a_bw >= 0 && ksw_ncol(P.max_contig_len, (int)max_ref, P.a_bw) <= KSW_BAND_MAX_NCOL;
+	const bool bandA = ctx->band_regs && P.a_bw >= 0 && ksw_ncol(P.max_contig_len, (int)max_ref, P.a_bw) <= KSW_BAND_MAX_NCOL;
 	const size_t p_capA = round_up(rowsA * ksw_pitch(ncolA) + 2 * KSW_PMAT_PAD + 64, 256), p_capB = round_up(rowsB * pitchB + 2 * KSW_PMAT_PAD + 64, 256);
-	const size_t groups_a = (size_t)ctx->dp_ctas * DP_WARPS * (bandA ? 32 / KSW_BAND_G : DP_NG), groups_b = (size_t)ctx->dp_ctas * DP_WARPS * DP_NG;
+	const size_t groups_a = bandA ? (size_t)ctx->n_sm * KSW_BAND_CTAS * KSW_BAND_WARPS * (32 / KSW_BAND_G) : (size_t)ctx->dp_ctas * DP_WARPS * DP_NG, groups_b = (size_t)ctx->dp_ctas * DP_WARPS * DP_NG;
 	const size_t n_groups = std::max(groups_a, groups_b);
-	const int seq_spill_cap = (int)round_up(ksw_seq_bytes(std::max(P.max_contig_len, max_trim), std::max((int)max_ref, P.max_contig_len)), 16);
+	const int seq_spill_cap = (int)round_up(ksw_seq_bytes(std::max(P.max_contig_len, max_trim), std::max((int)max_ref, P.max_contig_len)) + 32, 16);
 	CK(L.pmat.ensure(std::max(groups_a * p_capA, groups_b * p_capB)));
 	CK(L.cig_scratch.ensure(n_groups * (size_t)ctx->cig_cap * 4));
 	CK(L.seq_spill.ensure(n_groups * (size_t)seq_spill_cap));
@@ -420,12 +422,16 @@ int launch_chain(idl_ctx *ctx, Lane &L, bool record_start = false)
 	const size_t smem_limit = 200 * 1024;
 	if (b->n_regions > 0 && (P.stages & IDL_STAGE_ALIGN)) {
 		g.ring_cols = bandA ? 0 : ksw_ring_cols(ncolA); // the register-ring variant keeps only the reversed query (later the backtrack tile) in shared memory
-		g.seq_cap = (int)round_up(ksw_seq_bytes(std::min(P.max_contig_len, 1024), (int)max_ref), 16); // longer contigs stage in the spill area
-		const size_t smem = (size_t)DP_WARPS * (bandA ? 32 / KSW_BAND_G : DP_NG) * ksw_group_smem(g.ring_cols, g.seq_cap);
+		g.seq_cap = (int)round_up(ksw_seq_bytes(std::min(P.max_contig_len, 1024), (int)max_ref), 16) + (bandA ? 32 : 0); // longer contigs stage in the spill area; + KswBandEz
+		const size_t smem = (size_t)(bandA ? KSW_BAND_WARPS * (32 / KSW_BAND_G) : DP_WARPS * DP_NG) * ksw_group_smem(g.ring_cols, g.seq_cap);
 		if (smem > smem_limit) return IDL_E_CAPACITY;
 		sort_scan_kernel<<<1, 1024, 0, cs>>>(sA);
 		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, cs>>>(sA, &a.cnt->n_alns, 1u, L.cap_alns);
-		if (bandA) align_band_kernel<<<dp_grid(ctx, (const void*)align_band_kernel, smem), DP_THREADS, smem, cs>>>(g);
+		if (bandA) {
+			int nb = 0;
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)align_band_kernel, 32 * KSW_BAND_WARPS, smem) != cudaSuccess || nb < 1) nb = 1;
+			align_band_kernel<<<ctx->n_sm * std::min(nb, KSW_BAND_CTAS), 32 * KSW_BAND_WARPS, smem, cs>>>(g);
+		}
 		else align_kernel<<<dp_grid(ctx, (const void*)align_kernel, smem), DP_THREADS, smem, cs>>>(g);
 		CK(cudaGetLastError()); L.launches += 3;
 	}
@@ -620,14 +626,14 @@ struct KswBatchArgs {
 // MODE 0: banded, shared-memory rings (any w >= 0); 1: unbanded (row-owned variant for reads of up to 160 bases, else the rings);
 // 2: banded, the ring in registers (rounded bands of up to 96 lanes), G threads per alignment
 template <int MODE, int G>
-__global__ void __launch_bounds__(DP_THREADS, MODE == 1 ? 2 : 3) ksw2_batch_kernel(KswBatchArgs a) // unbanded: 8 warps x 2 CTAs at 122 registers (uniform shapes: 774 GCUPS at 150x700 against 745 with al_kernel's 5 x 4)
+__global__ void __launch_bounds__(MODE == 2 ? 32 * KSW_BAND_WARPS : DP_THREADS, MODE == 1 ? 2 : (MODE == 2 ? KSW_BAND_CTAS : 3)) ksw2_batch_kernel(KswBatchArgs a) // unbanded: 8 warps x 2 CTAs at 122 registers (uniform shapes: 774 GCUPS at 150x700 against 745 with al_kernel's 5 x 4)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	constexpr int NG = 32 / G;
 	const int lane = lane_id(), gl = lane & (G - 1), grp = lane / G;
 	const int cg = warp_id() * NG + grp;
 	const size_t per = ksw_group_smem(a.ring_cols, a.seq_cap);
-	const size_t gg = (size_t)blockIdx.x * (DP_WARPS * NG) + cg;
+	const size_t gg = (size_t)blockIdx.x * ((blockDim.x >> 5) * NG) + cg;
 	KswMem M;
 	ksw_group_mem(M, smem_raw + per * cg, grp, a.ring_cols); M.seq_cap = a.seq_cap; M.region_bytes = (int)per;
 	M.pmat = a.pmat + gg * a.p_cap; M.p_cap = a.p_cap;
@@ -688,13 +694,14 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 	KswBatchArgs a; memset(&a, 0, sizeof a);
 	a.n = (unsigned)n; a.kp = ksw_make_params(match, mismatch, gapo, gape, w, zdrop);
 	{ const char *e = getenv("IDL_KSW2_COLUMNS"); a.no_rows = e && *e == '1'; }
-	// 0 <= w with a rounded band of up to 96 lanes: the register-ring variant (IDL_KSW2_COLUMNS=1 keeps the shared-memory rings: tests compare the two)
-	const int mode = w < 0 ? 1 : (max_ncol <= KSW_BAND_MAX_NCOL && !a.no_rows ? 2 : 0);
+	// IDL_BAND_REGS=1 and 0 <= w with a rounded band of up to 96 lanes: the register-ring variant of the banded call-site (tests compare the two)
+	const char *ebr = getenv("IDL_BAND_REGS");
+	const int mode = w < 0 ? 1 : (max_ncol <= KSW_BAND_MAX_NCOL && ebr && *ebr == '1' ? 2 : 0);
 	const int ng = mode == 2 ? 32 / KSW_BAND_G : DP_NG;
 	a.ring_cols = mode == 2 ? 0 : ksw_ring_cols(max_ncol);
 	a.p_cap = round_up(max_p + 2 * KSW_PMAT_PAD + 64, 256); a.cig_cap = max_q + max_t + 8; a.cigar_cap = (unsigned)cigar_cap;
-	a.seq_cap = (int)round_up(ksw_seq_bytes(max_q, max_t), 16);
-	const int wpc = DP_WARPS; // warps per CTA
+	a.seq_cap = (int)round_up(ksw_seq_bytes(max_q, max_t), 16) + (mode == 2 ? 32 : 0); // + KswBandEz
+	const int wpc = mode == 2 ? KSW_BAND_WARPS : DP_WARPS; // warps per CTA
 	const size_t smem = (size_t)wpc * ng * ksw_group_smem(a.ring_cols, a.seq_cap);
 	if (smem > 200 * 1024) return IDL_E_CAPACITY;
 	const void *kfn = mode == 1 ? (const void*)ksw2_batch_kernel<1, 8> : mode == 2 ? (const void*)ksw2_batch_kernel<2, KSW_BAND_G> : (const void*)ksw2_batch_kernel<0, 8>;
@@ -720,7 +727,7 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 		CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 		CK(cudaEventRecord(e0, st));
 		if (mode == 1) ksw2_batch_kernel<1, 8><<<ctas, 32 * wpc, smem, st>>>(a);
-		else if (mode == 2) ksw2_batch_kernel<2, KSW_BAND_G><<<ctas, DP_THREADS, smem, st>>>(a);
+		else if (mode == 2) ksw2_batch_kernel<2, KSW_BAND_G><<<ctas, 32 * wpc, smem, st>>>(a);
 		else ksw2_batch_kernel<0, 8><<<ctas, DP_THREADS, smem, st>>>(a);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(e1, st));

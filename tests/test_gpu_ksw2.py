@@ -177,8 +177,8 @@ def test_unbanded_other_scoring_parameters(ctx, match, mismatch, gapo, gape):
 
 
 def test_register_ring_equals_shared_memory_ring(ctx, monkeypatch):
-    """the banded call-site runs with the band ring in registers (ksw2_band.cuh) for rounded bands of up to 96 lanes;
-    IDL_KSW2_COLUMNS=1 keeps those alignments on the shared-memory rings (ksw2.cuh): same records and CIGARs, for several band
+    """IDL_BAND_REGS=1 runs the banded call-site with the band ring in registers (ksw2_band.cuh) for rounded bands of up to 96
+    lanes instead of the shared-memory rings (ksw2.cuh, the default: it measured faster): same records and CIGARs, for several band
     widths incl. the widest one the register ring serves (w = 79) and one it does not (w = 80: both runs take the rings)"""
     rng = np.random.default_rng(29)
     for w, z in [(50, 400), (79, 400), (80, 400), (1, 100), (17, -1), (33, 60)]:
@@ -191,7 +191,15 @@ def test_register_ring_equals_shared_memory_ring(ctx, monkeypatch):
             m = rng.random(len(q)) < 0.02; q[m] = rng.integers(0, 5, int(m.sum()))
             qs.append(q); ts.append(t)
         a = ctx.ksw2_batch(qs, ts, gapo=4, gape=1, w=w, zdrop=z)
-        monkeypatch.setenv("IDL_KSW2_COLUMNS", "1")
+        monkeypatch.setenv("IDL_BAND_REGS", "1")
         b = ctx.ksw2_batch(qs, ts, gapo=4, gape=1, w=w, zdrop=z)
-        monkeypatch.delenv("IDL_KSW2_COLUMNS")
+        monkeypatch.delenv("IDL_BAND_REGS")
         assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2], (w, z)
+    # ... and against the oracle directly, production parameters
+    monkeypatch.setenv("IDL_BAND_REGS", "1")
+    pairs = []
+    for _ in range(600):
+        q, t, go, w, z = random_pair(rng)
+        if w >= 0:
+            pairs.append((q, t, 4, 50, 400))
+    assert check(ctx, pairs, "ref" if orc.have_ref() else "lane") == []

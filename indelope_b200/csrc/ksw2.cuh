@@ -16,6 +16,7 @@
 // values the SSE code leaves behind), H is a ring of the exact band, the backtrack matrix goes to global memory and is
 // walked through a 32x32 shared-memory tile.  All arithmetic is integer; no tensor cores.
 #pragma once
+#include <climits>
 #include "common.cuh"
 
 struct KswOut {
@@ -37,7 +38,8 @@ struct KswOut {
 #else
 #define KSW_PSTORE(p, v) (*(p) = (v))
 #endif
-#define KSW_BTILE_BYTES 1024
+#define KSW_BTILE_BYTES 1152 /* backtrack tile: 32 rows of nine aligned words */
+#define KSW_BTILE_ROW 36
 #define KSW_QR_PAD 32     /* zero bytes in front of the reversed query: lanes left of the exact band index it below 0 */
 #define KSW_PMAT_PAD 64   /* bytes in front of every backtrack matrix (the tile prefetch may start before row 0) */
 #define KSW_ST_EARLY 1
@@ -76,6 +78,13 @@ __host__ __device__ inline size_t ksw_seq_bytes(int qlen, int tlen)
 	return (size_t)(KSW_QR_PAD + ((qlen + 35) & ~3));
 }
 
+// rows of the backtrack matrix an alignment can write: the anti-diagonals it can execute before the band runs out (st0 > en0, :200-203)
+__host__ __device__ inline int ksw_rows_bound(int qlen, int tlen, int w)
+{
+	int d = qlen + tlen - 1;
+	if (w >= 0) { if (d > 2 * qlen + w + 1) d = 2 * qlen + w + 1; if (d > 2 * tlen + w + 1) d = 2 * tlen + w + 1; }
+	return d > 0 ? d : 0;
+}
 // off[r] / off_end[r] of the reference are pure functions of r (:196-199,205)
 // unb: w >= max(qlen, tlen), where the two w-clamps never bind ((r-w+1)>>1 <= max(0, r-qlen+1) and (r+w)>>1 >= min(r, tlen-1))
 __device__ __forceinline__ void ksw_band(int r, int qlen, int tlen, int w, int &st0, int &en0, bool unb = false)
@@ -220,6 +229,64 @@ __device__ __forceinline__ void ksw_core_word(const KswParams &P, bool fast_ok, 
 	}
 }
 
+// Prefetch of the backtrack bytes the next 32 diagonals of the walk can touch, by the eight threads of a group (all 32 threads of the warp
+// call this together).  Tile row k = diagonal r0 - k; the path can enter it at columns c0 - k .. c0 only, i.e. at the matrix bytes
+// e_k - k .. e_k with e_k = `row_end(k)`, the byte offset of (r0 - k, c0) from `pmat` (INT_MIN: no such row).  The tile row holds the nine
+// aligned words that end with the word of e_k, so the byte of column c0 - d sits at tile byte 36 k + 32 + (e_k & 3) - d; e_k & 3 is the same
+// for every row (row pitches and band offsets are multiples of 4).  The eight lanes read eight consecutive words of ONE row per
+// instruction -- one or two 32-byte sectors per row.  (The first version gave every thread four rows and one LDG.32 per word: the L1 does
+// not merge requests to a sector that is in flight, so every word cost a sector at the L2 and, the lines being long evicted, in DRAM:
+// al_kernel read 31.7 GB back for the 20.4 GB it wrote.)  lo / hi bound the byte offsets that may be touched (the workspace of this
+// alignment incl. its padding); a row whose entry bytes lie outside is never read by the walk (its state is forced there).
+#ifndef KSW_TILE_LD
+#define KSW_TILE_LD 1
+#endif
+// one word of the backtrack matrix into the shared-memory tile: an asynchronous copy (LDGSTS), so that the 33 words a thread moves per
+// tile are all in flight at once without holding 33 registers -- one DRAM round trip per tile, not one per batch of loads -- and with
+// the L2 prefetch size capped at 64 bytes: a plain ld.global pulled 128 bytes around every word it missed, four sectors per row of
+// the tile where one or two are needed (al_kernel: 804 M sectors read from L2 per launch against 448 M with the cap)
+__device__ __forceinline__ void ksw_tile_cp(uint32_t *dst, const uint32_t *src)
+{
+	const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+#if KSW_TILE_LD == 1
+	asm volatile("cp.async.ca.shared.global.L2::64B [%0], [%1], 4;" :: "r"(d), "l"(src) : "memory");
+#elif KSW_TILE_LD == 2
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(src) : "memory");
+#else
+	uint32_t v; asm volatile("ld.global.L1::no_allocate.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(src)); *dst = v;
+#endif
+}
+__device__ __forceinline__ void ksw_tile_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <class F>
+__device__ __forceinline__ void ksw_tile_fetch(bool more, F &&row_end, const uint8_t *pmat, int lo, int hi, uint32_t *tile)
+{
+	const int lane = lane_id(), gl = lane & 7, gbase = lane & ~7;
+	int ev[4];
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		int e = more ? row_end(gl + 8 * q) : INT_MIN;
+		if (e != INT_MIN) e = e < lo + 35 ? lo + 35 : (e > hi - 4 ? hi - 4 : e);
+		ev[q] = e;
+	}
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+#pragma unroll
+		for (int kk = 0; kk < 8; ++kk) {
+			const int k = 8 * q + kk;
+			const int e = __shfl_sync(FULL_MASK, ev[q], gbase + kk);
+			const int w = (e >> 2) - gl;                         // my word of this row
+			if (e != INT_MIN && w >= ((e - k) >> 2)) ksw_tile_cp(tile + (k * 9 + 8 - gl), (const uint32_t*)(pmat + 4 * (long long)w));
+		}
+	}
+	{ // rows 29 .. 31 can need a ninth word
+		const int k = 29 + gl;
+		const int e = __shfl_sync(FULL_MASK, ev[3], gbase + ((5 + gl) & 7));
+		const int w = (e >> 2) - 8;
+		if (gl < 3 && e != INT_MIN && w >= ((e - k) >> 2)) ksw_tile_cp(tile + k * 9, (const uint32_t*)(pmat + 4 * (long long)w));
+	}
+	ksw_tile_wait();
+}
+
 // ALL 32 threads of a warp call this together: 4 groups of G = 8 threads, one alignment per group (valid = 0 for a group
 // without one).  The anti-diagonal loop and the rounds inside it run in lockstep over the four alignments, so every
 // barrier and shuffle is a plain full-warp one; a group whose alignment is shorter or has stopped idles behind a predicate.
@@ -258,7 +325,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 		else if (-min_sc > 2 * qe) { out.status = KSW_ST_EARLY; live = false; }      // :171
 		else if (ksw_ring_cols(n_col) > M.ring_cols) { out.status = KSW_ST_RCAP; live = false; }
 		else if (ksw_seq_bytes(qlen, tlen) > (size_t)M.seq_cap) { out.status = KSW_ST_SEQCAP; live = false; }
-		else if ((size_t)(qlen + tlen - 1) * (size_t)pitch + 2 * KSW_PMAT_PAD > M.p_cap) { out.status = KSW_ST_PCAP; live = false; }
+		else if ((size_t)ksw_rows_bound(qlen, tlen, P.w) * (size_t)pitch + 2 * KSW_PMAT_PAD > M.p_cap) { out.status = KSW_ST_PCAP; live = false; }
 		else if ((long long)(qlen + tlen + 2) * qe + (long long)(qlen < tlen ? qlen : tlen) * (P.match > 0 ? P.match : 0) + gbias >= 0xF000) { out.status = KSW_ST_HCAP; live = false; }
 	}
 	const bool run = live; // this group has a DP to run (and a CIGAR to walk afterwards)
@@ -534,41 +601,21 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 		// group prefetches the 32 x 32 tile of p[][] the path can touch (row r0-k can only be entered at columns
 		// i0-k .. i0) into shared memory (the sequence staging area is free by now), so the walker runs on shared-memory
 		// latency instead of one L2/HBM round trip per step.  The four rows a thread fetches are in flight together.
-		uint32_t *tile = (uint32_t*)M.xvuy; // 32 rows of 8 words; the rings are dead by now
+		uint32_t *tile = (uint32_t*)M.xvuy; // 32 rows of 9 words (ksw_tile_fetch); the rings are dead by now
 		uint32_t *cig = M.cig; const int cig_cap = M.cig_cap;
 		int state = 0;
 		unsigned cur_op = 0xffu, cur_len = 0;
-		const long long x_hi = (long long)(qlen + tlen - 1) * pitch + KSW_PMAT_PAD - 40;
+		const int p_hi = ksw_rows_bound(qlen, tlen, P.w) * pitch + KSW_PMAT_PAD;
 		while (__any_sync(FULL_MASK, i >= 0 && j >= 0)) {
 			const bool more = i >= 0 && j >= 0;
 			const int i0 = i, r0 = i + j;
-			{
-				uint32_t wv[4][9]; int shv[4];
-#pragma unroll
-				for (int q4 = 0; q4 < 4; ++q4) {
-					const int row = gl + G * q4, rr = r0 - row;
-					int s0 = 0, e0 = 0;
-					if (more && rr >= 0) ksw_band(rr, qlen, tlen, w, s0, e0, UNB);
-					long long x0 = (long long)rr * pitch + (i0 - 31 - (UNB ? (s0 & ~3) : (s0 & ~15))); // byte offset of column i0-31 of row rr
-					// a row that holds a readable entry has x0 within 31 bytes of the matrix; anything further out is never read
-					// (the walk is forced there), so clamping keeps the prefetch inside this alignment's workspace
-					x0 = x0 < -(long long)(KSW_PMAT_PAD - 4) ? -(long long)(KSW_PMAT_PAD - 4) : (x0 > x_hi ? x_hi : x0);
-					const uint32_t *src = (const uint32_t*)(pmat + (x0 & ~3LL));
-					shv[q4] = 8 * (int)(x0 & 3);
-					// row r0 - row can only be entered at columns i0 - row .. i0: fetch those bytes only (the left part of the
-					// tile row stays stale and is never read), which keeps most rows inside one DRAM sector
-					const int k0 = (31 - row) >> 2;
-					const bool ld = more && rr >= 0;
-#pragma unroll
-					for (int k = 0; k < 9; ++k) wv[q4][k] = (ld && k >= k0) ? src[k] : 0u; // predicated loads, all in flight together
-				}
-#pragma unroll
-				for (int q4 = 0; q4 < 4; ++q4) {
-					const int row = gl + G * q4, k0 = (31 - row) >> 2;
-#pragma unroll
-					for (int k = 0; k < 8; ++k) if (k >= k0) tile[row * 8 + k] = __funnelshift_r(wv[q4][k], wv[q4][k + 1], shv[q4]);
-				}
-			}
+			ksw_tile_fetch(more, [&](int k) -> int {
+				const int rr = r0 - k;
+				if (rr < 0) return INT_MIN;
+				int s0, e0;
+				ksw_band(rr, qlen, tlen, w, s0, e0, UNB);
+				return rr * pitch + (i0 - (UNB ? (s0 & ~3) : (s0 & ~15))); // byte offset of column i0 in row rr
+			}, pmat, -KSW_PMAT_PAD, p_hi, tile);
 			__syncwarp();
 			if (gl == 0) {
 				const uint8_t *tb = (const uint8_t*)tile;
@@ -580,7 +627,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 					int force_state = -1;
 					if (i < off) force_state = 2;
 					if (i > off_end) force_state = 1;
-					const unsigned tmp = force_state < 0 ? tb[(r0 - r) * 32 + (i - (i0 - 31))] : 0u;
+					const unsigned tmp = force_state < 0 ? tb[(r0 - r) * KSW_BTILE_ROW + 32 + (i0 & 3) - (i0 - i)] : 0u;
 					if (state == 0) state = tmp & 7;
 					else if (!((tmp >> (state + 2)) & 1)) state = 0;
 					if (state == 0) state = tmp & 7;

@@ -48,36 +48,17 @@ __device__ __forceinline__ void ksw_walk_cols(int i, int j, int qlen, int tlen, 
 	const int lane = lane_id(), gl = lane & (G - 1);
 	int n = 0, ovf = 0, state = 0;
 	unsigned cur_op = 0xffu, cur_len = 0;
-	const long long x_hi = (long long)(qlen + tlen - 1) * pitch + KSW_PMAT_PAD - 40;
+	const int p_hi = ksw_rows_bound(qlen, tlen, w) * pitch + KSW_PMAT_PAD;
 	while (__any_sync(FULL_MASK, i >= 0 && j >= 0)) {
 		const bool more = i >= 0 && j >= 0;
 		const int i0 = i, r0 = i + j;
-#pragma unroll 1
-		for (int pass = 0; pass < 32 / (4 * G) + (32 % (4 * G) ? 1 : 0); ++pass) {
-			uint32_t wv[4][9]; int shv[4];
-#pragma unroll
-			for (int q4 = 0; q4 < 4; ++q4) {
-				const int row = gl + G * (q4 + 4 * pass), rr = r0 - row;
-				int s0 = 0, e0 = 0;
-				if (more && rr >= 0) ksw_band(rr, qlen, tlen, w, s0, e0);
-				long long x0 = (long long)rr * pitch + (i0 - 31 - (s0 & ~15)); // byte offset of column i0-31 of row rr
-				x0 = x0 < -(long long)(KSW_PMAT_PAD - 4) ? -(long long)(KSW_PMAT_PAD - 4) : (x0 > x_hi ? x_hi : x0);
-				const uint32_t *src = (const uint32_t*)(pmat + (x0 & ~3LL));
-				shv[q4] = 8 * (int)(x0 & 3);
-				const int k0 = (31 - row) >> 2; // row r0 - row can only be entered at columns i0 - row .. i0
-				const bool ld = more && rr >= 0 && row < 32;
-#pragma unroll
-				for (int k = 0; k < 9; ++k) wv[q4][k] = (ld && k >= k0) ? src[k] : 0u;
-			}
-#pragma unroll
-			for (int q4 = 0; q4 < 4; ++q4) {
-				const int row = gl + G * (q4 + 4 * pass), k0 = (31 - row) >> 2;
-				if (row < 32) {
-#pragma unroll
-					for (int k = 0; k < 8; ++k) if (k >= k0) tile[row * 8 + k] = __funnelshift_r(wv[q4][k], wv[q4][k + 1], shv[q4]);
-				}
-			}
-		}
+		ksw_tile_fetch(more, [&](int k) -> int {
+			const int rr = r0 - k;
+			if (rr < 0) return INT_MIN;
+			int s0, e0;
+			ksw_band(rr, qlen, tlen, w, s0, e0);
+			return rr * pitch + (i0 - (s0 & ~15)); // byte offset of column i0 in row rr
+		}, pmat, -KSW_PMAT_PAD, p_hi, tile);
 		__syncwarp();
 		if (gl == 0) {
 			const uint8_t *tb = (const uint8_t*)tile;
@@ -89,7 +70,7 @@ __device__ __forceinline__ void ksw_walk_cols(int i, int j, int qlen, int tlen, 
 				int force_state = -1;
 				if (i < off) force_state = 2;
 				if (i > off_end) force_state = 1;
-				const unsigned tmp = force_state < 0 ? tb[(r0 - r) * 32 + (i - (i0 - 31))] : 0u;
+				const unsigned tmp = force_state < 0 ? tb[(r0 - r) * KSW_BTILE_ROW + 32 + (i0 & 3) - (i0 - i)] : 0u;
 				if (state == 0) state = tmp & 7;
 				else if (!((tmp >> (state + 2)) & 1)) state = 0;
 				if (state == 0) state = tmp & 7;
@@ -234,7 +215,7 @@ template <int G, bool EZ_FULL>
 __device__ void ksw2_band(bool valid, int qlen, const KswQuery query, int tlen, const uint8_t *target, const KswParams P, const KswMem M, KswOut &out)
 {
 	constexpr int NS = 32 / G;
-	static_assert(G == 4 || G == 8, "4 or 8 threads per alignment");
+	static_assert(G == 8, "8 threads per alignment (the tile prefetch deals eight words of a row to a group)");
 	const int lane = lane_id(), gl = lane & (G - 1);
 	ksw_reset(out);
 	const int qe = P.q + P.e, gbias = 2 * qe;
@@ -249,7 +230,7 @@ __device__ void ksw2_band(bool valid, int qlen, const KswQuery query, int tlen, 
 		else if (-min_sc > 2 * qe) { out.status = KSW_ST_EARLY; live = false; }      // :171
 		else if (w < 0 || n_col > KSW_BAND_MAX_NCOL) { out.status = KSW_ST_RCAP; live = false; } // the caller picked the wrong variant
 		else if (ksw_seq_bytes(qlen, tlen) + sizeof(KswBandEz) > (size_t)M.seq_cap) { out.status = KSW_ST_SEQCAP; live = false; } // the staging area ends 32 bytes early: KswBandEz
-		else if ((size_t)(qlen + tlen - 1) * (size_t)pitch + 2 * KSW_PMAT_PAD > M.p_cap) { out.status = KSW_ST_PCAP; live = false; }
+		else if ((size_t)ksw_rows_bound(qlen, tlen, w) * (size_t)pitch + 2 * KSW_PMAT_PAD > M.p_cap) { out.status = KSW_ST_PCAP; live = false; }
 		else if ((long long)(qlen + tlen + 2) * qe + (long long)(qlen < tlen ? qlen : tlen) * (P.match > 0 ? P.match : 0) + gbias >= 0xF000) { out.status = KSW_ST_HCAP; live = false; }
 	}
 	const bool run = live;

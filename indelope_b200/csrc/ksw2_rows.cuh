@@ -118,9 +118,9 @@ struct KswRowsSlots {
 				// r - tlen): those lanes keep a fixed in-range state and stay out of the maximum
 				if (on) {
 					const int lo = dg.lo0 - 32 * S; // t of row 4w on this diagonal; lane c is row 4w + c at t = lo - c
-					uint32_t m = lo >= 3 ? 0xffffffffu : (0xffffffffu >> (8 * (3 - lo)));
+					uint32_t m = lo >= 3 ? 0xffffffffu : (lo < 0 ? 0u : (0xffffffffu >> (8 * (3 - lo)))); // a word wholly in front of t = 0 is parked as a whole
 					const int cf = lo - (dg.tlen - 1);
-					if (cf > 0) m &= 0xffffffffu << (8 * cf); // cf <= 3 while the word is on
+					if (cf > 0) m = cf > 3 ? 0u : (m & (0xffffffffu << (8 * cf)));                            // ... and so is one wholly past the end
 					const uint32_t tw = __funnelshift_r(lds32(dg.taddr + 32 * S), lds32(dg.taddr + 32 * S + 4), dg.tsh); // target codes met by rows 4w .. 4w+3
 					ksw_rows_word<true, WILD>(P, m, pc, tw, qw[S], x[S], v[S], u[S], y[S], gx[S], gy[S], dm2, chk, (uint32_t*)(dg.prow + 32 * S));
 				}
@@ -197,7 +197,9 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 	const bool wild_any = __any_sync(FULL_MASK, wild); // a code 4 anywhere in the four alignments: the scores take the wildcard mask
 	__syncwarp();
 
-	const int nsq = live ? (qlen - 4 * gl + 31) >> 5 : 0; // my slots that hold query rows
+	// slots that hold query rows: the same for every thread of the group -- in the last one some threads hold only padding rows (code 6: real
+	// cells of the query-extended problem that can only lose score), so that the eight threads always store a whole 32-byte sector
+	const int nsq = live ? (qlen + 31) >> 5 : 0;
 	// score snapshots of this thread (taken when its best score rises): the last bytes of the group's region, 16 bytes per
 	// thread and vector, so that a group's store is one conflict-free 128-byte line; only the owner ever reads them back
 	constexpr int NSV = (2 * W + 3) / 4;
@@ -235,6 +237,19 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 				if (lo0 - 32 * s_hi < 3) pm = 1u << s_hi;          // the word of row r: lanes in front of t = 0
 				if (lo0 - 32 * s_lo > tlen - 1) pm |= 1u << s_lo;  // the word of row r - tlen: lanes past the target end
 			}
+			// KSW_ROWS_FULL_SECTORS: a slot is run by ALL EIGHT threads of the group as soon as one of them has a live word in it (thread 0 reaches the highest slot, thread
+			// 7 the lowest): the others' words are wholly in front of t = 0 or wholly past t = tlen-1 and stay parked behind an all-zero mask, in
+			// the same instruction stream (the word of row r / row r - tlen puts the slot on the masked path anyway).  Their backtrack words are
+			// never read, but the group then writes whole 32-byte sectors: a partly written sector is FETCHED from DRAM before it is written
+			// back (38 % of the sectors al_kernel wrote were, 7.8 GB of DRAM reads per launch that no load asked for).
+			// MEASURED: DRAM reads 20.4 -> 13.4 GB per launch, but 528 G instead of 440 G thread instructions and 20.3 instead of 19.1 ms: off by
+			// default.  (The uniform slot count `nsq` above already makes the tail of the last slot whole at no cost.)
+#ifdef KSW_ROWS_FULL_SECTORS
+			int g_hi = r >> 5, g_lo = (r - tlen + 1) >> 5;
+			g_hi = g_hi < nsq ? g_hi : nsq - 1; g_lo = g_lo > 0 ? g_lo : 0;
+			const unsigned gonm = (act && g_hi >= g_lo) ? (((2u << g_hi) - 1u) & ~((1u << g_lo) - 1u)) : 0u;
+			pm |= gonm & ~onm; onm = gonm;
+#endif
 			dg.onm = onm; dg.uon = __reduce_or_sync(FULL_MASK, onm); dg.upm = __reduce_or_sync(FULL_MASK, pm);
 		}
 		dg.lo0 = lo0; dg.tlen = tlen; dg.gl = gl; dg.srcl = srcl; dg.bconst = bconst; dg.taddr = taddr; dg.tsh = tsh; dg.prow = prow;
@@ -338,38 +353,17 @@ __device__ void ksw2_rows(bool valid, int qlen, const KswQuery query, int tlen, 
 		uint32_t *cig = M.cig; const int cig_cap = M.cig_cap;
 		int state = 0;
 		unsigned cur_op = 0xffu, cur_len = 0;
-		const long long x_hi = (long long)(qlen + tlen - 1) * PITCH + KSW_PMAT_PAD - 40;
+		const int p_hi = (qlen + tlen - 1) * PITCH + KSW_PMAT_PAD;
 		while (__any_sync(FULL_MASK, i >= 0 && j >= 0)) {
 			const bool more = i >= 0 && j >= 0;
 			const int j0 = j, r0 = i + j;
-			{
-				// all four rows of a thread in flight together: one memory round trip per tile, not four
-				uint32_t wv[4][9]; int shv[4];
-#pragma unroll
-				for (int q4 = 0; q4 < 4; ++q4) {
-					const int row = gl + 8 * q4, rr = r0 - row;
-					long long x0 = (long long)rr * PITCH + (j0 - 31);
-					x0 = x0 < -(long long)(KSW_PMAT_PAD - 4) ? -(long long)(KSW_PMAT_PAD - 4) : (x0 > x_hi ? x_hi : x0);
-					const uint32_t *src = (const uint32_t*)(pmat + (x0 & ~3LL));
-					shv[q4] = 8 * (int)(x0 & 3);
-					const int k0 = (31 - row) >> 2; // row r0 - row can only be entered at columns j0 - row .. j0
-					const bool ld = more && rr >= 0;
-#pragma unroll
-					for (int k = 0; k < 9; ++k) wv[q4][k] = (ld && k >= k0) ? src[k] : 0u;
-				}
-#pragma unroll
-				for (int q4 = 0; q4 < 4; ++q4) {
-					const int row = gl + 8 * q4, k0 = (31 - row) >> 2;
-#pragma unroll
-					for (int k = 0; k < 8; ++k) if (k >= k0) tile[row * 8 + k] = __funnelshift_r(wv[q4][k], wv[q4][k + 1], shv[q4]);
-				}
-			}
+			ksw_tile_fetch(more, [&](int k) -> int { return r0 - k < 0 ? INT_MIN : (r0 - k) * PITCH + j0; }, pmat, -KSW_PMAT_PAD, p_hi, tile);
 			__syncwarp();
 			if (gl == 0) {
 				const uint8_t *tbp = (const uint8_t*)tile;
 				while (i >= 0 && j >= 0 && i + j > r0 - 32) {
 					const int r = i + j;
-					const unsigned tmp = tbp[(r0 - r) * 32 + (j - (j0 - 31))];
+					const unsigned tmp = tbp[(r0 - r) * KSW_BTILE_ROW + 32 + (j0 & 3) - (j0 - j)];
 					if (state == 0) state = tmp & 7;
 					else if (!((tmp >> (state + 2)) & 1)) state = 0;
 					if (state == 0) state = tmp & 7;

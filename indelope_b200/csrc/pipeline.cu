@@ -180,6 +180,7 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	ctx->asm_ctas = ctx->n_sm * (ea && atoi(ea) > 0 ? atoi(ea) : 4); // CTAs of each assembler launch (8 regions per CTA in the warp variant)
 	ctx->dp_ctas = ctx->n_sm * (ed && atoi(ed) > 0 ? atoi(ed) : 4); // upper bound; every launch asks the occupancy calculator
 	{ const char *eb = getenv("IDL_BAND_REGS"); ctx->band_regs = eb && *eb == '1'; }
+	{ const char *el = getenv("IDL_L2_FETCH"); if (el && atoi(el) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(el)); } // experiments: 32 / 64 / 128
 	ctx->lanes.resize((size_t)p->n_streams);
 	{
 		// IDL_OVERLAP_KERNELS=1: the kernels of a batch run on its lane's stream and may share the SMs with another batch's
@@ -351,8 +352,7 @@ int launch_chain(idl_ctx *ctx, Lane &L, bool record_start = false)
 	}
 	// kernel 2 geometry: call-site A (contig vs window, banded) and B (read vs suffix, unbanded by default)
 	const int ncolA = ksw_ncol(P.max_contig_len, (int)max_ref, P.a_bw), ncolB = ksw_ncol(max_trim, std::max((int)max_ref, P.max_contig_len), P.b_bw);
-	const int wA = P.a_bw < 0 ? std::max(P.max_contig_len, (int)max_ref) : P.a_bw;
-	const size_t rowsA = std::min<size_t>((size_t)P.max_contig_len + max_ref, 2 * (size_t)max_ref + wA + 2);
+	const size_t rowsA = (size_t)ksw_rows_bound(P.max_contig_len, (int)max_ref, P.a_bw); // the anti-diagonals an alignment can execute before its band runs out
 	const size_t rowsB = (size_t)max_trim + std::max<size_t>(max_ref, 1536);
 	const size_t pitchB = std::max<size_t>(ksw_pitch(ncolB), P.b_bw < 0 ? 32 * (size_t)ksw_rows_w(max_trim) : 0); // the row-owned variant stores 32 W bytes per diagonal
 	// the banded call-site runs the register-ring variant whenever its band fits (w <= 79: indelope's 50 does), G threads per alignment

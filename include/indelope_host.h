@@ -63,6 +63,8 @@ typedef struct idlh_synth_params {
 	int32_t locus_flank;
 	int32_t max_cigar_indel;    /* aligner model: longer indels are soft-clipped [30] */
 	int32_t min_cigar_flank;    /* aligner model: shorter flanks are soft-clipped [20] */
+	int32_t chrom_first;        /* generate chromosomes chrom_first .. chrom_first + n_chroms - 1 of the genome this seed defines (every
+	                               chromosome has its own random stream, so a rank can build just its interval shard) [0] */
 } idlh_synth_params;
 
 void idlh_default_synth(idlh_synth_params *p);
@@ -138,6 +140,8 @@ void idlh_vcf_set_dedup(idlh_vcf *w, int on);
  * warning on stderr (the first 20): capacity limits and the alphabet fold never change the output silently */
 void idlh_vcf_status_counts(const idlh_vcf *w, uint64_t out[8]);
 char *idlh_vcf_dedup(const char *records);
+char *idlh_vcf_dedup_n(const char *records, size_t n, size_t *out_len);   /* the same over n bytes, not necessarily terminated */
+/* idlh_vcf_records without the terminating-string contract: the record text as (pointer, length), for callers that ship bytes */
 void idlh_free(void *p);
 
 #ifdef __cplusplus

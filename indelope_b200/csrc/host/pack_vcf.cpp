@@ -384,31 +384,48 @@ idlh_vcf *idlh_vcf_new(void) { return new idlh_vcf(); }
 void idlh_vcf_set_dedup(idlh_vcf *w, int on) { w->dedup = on != 0; }
 void idlh_vcf_status_counts(const idlh_vcf *w, uint64_t out[8]) { for (int i = 0; i < 8; ++i) out[i] = w->status_count[i]; }
 
-char *idlh_vcf_dedup(const char *records)
+char *idlh_vcf_dedup(const char *records) { return idlh_vcf_dedup_n(records, strlen(records), nullptr); }
+
+// the same over a buffer of `n` bytes that need not be terminated (the gathered shards of a multi-GPU run: tens of megabytes per
+// genome, so lines are compared in place and copied once)
+char *idlh_vcf_dedup_n(const char *records, size_t n, size_t *out_len)
 {
-	std::string out;
-	Rec last1, last2; bool have1 = false, have2 = false;
-	const char *p = records;
-	while (*p) {
-		const char *e = strchr(p, '\n');
-		const size_t n = e ? (size_t)(e - p) : strlen(p);
-		std::string line(p, n);
-		p += n + (e ? 1 : 0);
-		if (line.empty()) continue;
+	struct Key { const char *chrom, *pos, *ref, *alt; size_t lc, lp, lr, la; };
+	auto same = [](const Key &x, const Key &y) {
+		return x.lp == y.lp && x.lc == y.lc && x.lr == y.lr && x.la == y.la && !memcmp(x.pos, y.pos, x.lp) && !memcmp(x.chrom, y.chrom, x.lc) &&
+		       !memcmp(x.ref, y.ref, x.lr) && !memcmp(x.alt, y.alt, x.la);
+	};
+	char *o = (char*)malloc(n + 2);
+	size_t w = 0;
+	Key last1{}, last2{}; bool have1 = false, have2 = false;
+	const char *p = records, *end = records + n;
+	while (p < end) {
+		const char *e = (const char*)memchr(p, '\n', (size_t)(end - p));
+		const char *le = e ? e : end;
+		const char *line = p;
+		p = e ? e + 1 : end;
+		if (le == line) continue;
 		// CHROM POS ID REF ALT ...
-		std::vector<std::string> f;
-		size_t a = 0;
-		for (int k = 0; k < 5; ++k) { size_t b = line.find('\t', a); if (b == std::string::npos) break; f.push_back(line.substr(a, b - a)); a = b + 1; }
-		if (f.size() < 5) { out += line + "\n"; continue; }
-		Rec v; v.chrom = f[0]; v.pos = atoll(f[1].c_str()); v.ref = f[3]; v.alt = f[4];
-		auto same = [](const Rec &x, const Rec &y) { return x.pos == y.pos && x.chrom == y.chrom && x.ref == y.ref && x.alt == y.alt; };
-		if (have1 && same(v, last1)) continue;
-		if (have2 && same(v, last2)) continue;
-		out += line + "\n";
-		last2 = last1; have2 = have1; last1 = v; have1 = true;
+		const char *f[6]; int nf = 0; f[nf++] = line;
+		for (const char *q = line; q < le && nf < 6; ) { const char *t = (const char*)memchr(q, '\t', (size_t)(le - q)); if (!t) break; f[nf++] = t + 1; q = t + 1; }
+		bool keep = true; Key k{};
+		if (nf == 6) {
+			k.chrom = f[0]; k.lc = (size_t)(f[1] - 1 - f[0]); k.pos = f[1]; k.lp = (size_t)(f[2] - 1 - f[1]);
+			k.ref = f[3]; k.lr = (size_t)(f[4] - 1 - f[3]); k.alt = f[4]; k.la = (size_t)(f[5] - 1 - f[4]);
+			if ((have1 && same(k, last1)) || (have2 && same(k, last2))) keep = false;
+		}
+		if (!keep) continue;
+		const size_t ll = (size_t)(le - line);
+		memcpy(o + w, line, ll);
+		if (nf == 6) { // the keys point into the output from now on (the input may be released by the caller in a streaming use)
+			const ptrdiff_t sh = (o + w) - line;
+			k.chrom += sh; k.pos += sh; k.ref += sh; k.alt += sh;
+			last2 = last1; have2 = have1; last1 = k; have1 = true;
+		}
+		w += ll; o[w++] = '\n';
 	}
-	char *o = (char*)malloc(out.size() + 1);
-	memcpy(o, out.c_str(), out.size() + 1);
+	o[w] = 0;
+	if (out_len) *out_len = w;
 	return o;
 }
 void idlh_vcf_free(idlh_vcf *w) { delete w; }
@@ -455,23 +472,20 @@ char *idlh_vcf_records(idlh_vcf *w, const idlh_roiset *rs, int64_t lo, const idl
 {
 	const int K = IDL_KMER;
 	static const char *gt_enc[] = {"0/0", "0/1", "1/1", "./."};
-	std::string vcf, d;
-	for (size_t i = 0; i < res->n_regions; ++i) {
+	// Regions are independent up to the order-dependent dedup: the cascade and the text of every region are made on all host cores (the
+	// host cascade of a chr1-sized step, 85 k regions, took 46 ms on one core against 38 ms of GPU time), the dedup then walks the
+	// candidate records in region order on one.
+	const size_t nreg = res->n_regions;
+	std::vector<std::vector<Rec>> cand(nreg);
+	std::vector<std::string> dtext(dump_level ? nreg : 0);
+	auto do_region = [&](size_t i) {
 		const idl_region_result &rr = res->region[i];
 		const int64_t k = lo + (int64_t)i;
 		const int chrom = rs->roi_chrom[k];
 		const int64_t n_region_reads = rs->roi_n_reads[k];
-		std::vector<std::string> vlines;
-		if (rr.status) { // never silent: the output for this region may differ from the reference's (include/indelope_cuda.h IDL_RS_*)
-			for (int bit = 0; bit < 8; ++bit)
-				if (rr.status & (1u << bit)) {
-					w->status_count[bit] += 1;
-					if (w->warned < 20) {
-						fprintf(stderr, "indelope: warning: region %s:%d-%d: %s\n", rs->chrom_name[chrom], rs->roi_start[k], rs->roi_stop[k], RS_NAMES[bit]);
-						if (++w->warned == 20) fprintf(stderr, "indelope: further region warnings are counted, not printed\n");
-					}
-				}
-		}
+		std::vector<Rec> &out = cand[i];
+		std::string dlocal;
+		std::string &d = dump_level ? dtext[i] : dlocal;
 		if (dump_level & 1) {
 			d += "R\t" + std::to_string(k) + "\tpre=" + std::to_string(rr.n_contigs_pre) + "\tn=" + std::to_string(rr.n_contigs) + "\n";
 			for (int32_t ci = 0; ci < rr.n_contigs; ++ci) {
@@ -557,16 +571,37 @@ char *idlh_vcf_records(idlh_vcf *w, const idlh_roiset *rs, int64_t lo, const idl
 				v.line = v.chrom + "\t" + std::to_string(v.pos) + "\t.\t" + v.ref + "\t" + v.alt + "\t" + ffmt(qual, 2) + "\tPASS\t" + "AD=" +
 				         std::to_string(ref_support) + "," + std::to_string(alt_support) + ";ref_kmer=" + ref_kmer + ";alt_kmer=" + alt_kmer + ";" + info +
 				         "\tGT:GQ:GL\t" + gt_enc[g.gt] + ":" + ffmt(g.qual, 4) + ":" + ffmt(g.gl[0], 4) + "," + ffmt(g.gl[1], 4) + "," + ffmt(g.gl[2], 4);
-				// order-dependent dedup against the last two emitted records, src/indelope.nim:604-608
-				auto same = [](const Rec &x, const Rec &y) { return x.pos == y.pos && x.chrom == y.chrom && x.ref == y.ref && x.alt == y.alt; };
-				if (w->dedup && w->have1 && same(v, w->last1)) continue;
-				if (w->dedup && w->have2 && same(v, w->last2)) continue;
-				vlines.push_back(v.line);
-				w->last2 = w->last1; w->have2 = w->have1;
-				w->last1 = v; w->have1 = true;
+				out.push_back(std::move(v));
 			}
 		}
-		for (auto &l : vlines) { vcf += l + "\n"; if (dump_level & 16) d += "V\t" + l + "\n"; }
+	};
+	if (nreg < 256) for (size_t i = 0; i < nreg; ++i) do_region(i);
+	else parallel_blocks((int64_t)nreg, 256, [&](int64_t a, int64_t e, int) { for (int64_t i = a; i < e; ++i) do_region((size_t)i); });
+	std::string vcf, d;
+	auto same = [](const Rec &x, const Rec &y) { return x.pos == y.pos && x.chrom == y.chrom && x.ref == y.ref && x.alt == y.alt; };
+	for (size_t i = 0; i < nreg; ++i) {
+		const idl_region_result &rr = res->region[i];
+		if (rr.status) { // never silent: the output for this region may differ from the reference's (include/indelope_cuda.h IDL_RS_*)
+			const int64_t k = lo + (int64_t)i;
+			for (int bit = 0; bit < 8; ++bit)
+				if (rr.status & (1u << bit)) {
+					w->status_count[bit] += 1;
+					if (w->warned < 20) {
+						fprintf(stderr, "indelope: warning: region %s:%d-%d: %s\n", rs->chrom_name[rs->roi_chrom[k]], rs->roi_start[k], rs->roi_stop[k], RS_NAMES[bit]);
+						if (++w->warned == 20) fprintf(stderr, "indelope: further region warnings are counted, not printed\n");
+					}
+				}
+		}
+		if (dump_level) d += dtext[i];
+		for (Rec &v : cand[i]) {
+			// order-dependent dedup against the last two emitted records, src/indelope.nim:604-608
+			if (w->dedup && w->have1 && same(v, w->last1)) continue;
+			if (w->dedup && w->have2 && same(v, w->last2)) continue;
+			vcf += v.line; vcf += "\n";
+			if (dump_level & 16) { d += "V\t"; d += v.line; d += "\n"; }
+			w->last2 = std::move(w->last1); w->have2 = w->have1;
+			w->last1 = std::move(v); w->have1 = true;
+		}
 	}
 	if (dump_out) { *dump_out = (char*)malloc(d.size() + 1); memcpy(*dump_out, d.c_str(), d.size() + 1); }
 	char *out = (char*)malloc(vcf.size() + 1);

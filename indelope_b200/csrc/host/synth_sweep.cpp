@@ -158,8 +158,8 @@ idlh_dataset *idlh_synth(const idlh_synth_params *pp)
 		D.reads.reserve(est); D.bases.reserve(est * (size_t)L); D.quals.reserve(est * (size_t)L); D.cigars.reserve(est * 2);
 	}
 	for (int c = 0; c < P.n_chroms; ++c) {
-		Rng rng(P.seed * 1000003ULL + (uint64_t)c * 7919ULL + 17);
-		D.names.push_back("chrS" + std::to_string(c + 1));
+		Rng rng(P.seed * 1000003ULL + (uint64_t)(P.chrom_first + c) * 7919ULL + 17);
+		D.names.push_back("chrS" + std::to_string(P.chrom_first + c + 1));
 		D.chroms.emplace_back((size_t)P.chrom_len);
 		std::vector<uint8_t> &ref = D.chroms.back();
 		for (int64_t i = 0; i < P.chrom_len; i += 32) { // 2 bits per base out of each 64-bit draw

@@ -73,7 +73,10 @@ __device__ __forceinline__ void ksw_rows_word(const KswParams &P, uint32_t m, ui
 	mk = ge4_pos(z, b);                             // z >= b
 	d = sel4(mk, d, 0x02020202u);
 	z = sel4(mk, z, b);
-#ifndef KSW_ROWS_NOMIN /* a no-op for real cells (H(t,j) - H(t-1,j-1) <= match), kept because the reference does it: 0.64 of 19.3 ms */
+#ifdef KSW_ROWS_WITH_MIN /* z = min(z, match + 2(q+e)) of :132: a no-op here.  z is H(t,j) - H(t-1,j-1) + 2(q+e) and a step along the main diagonal
+	   of an affine-gap DP gains at most the match score (Suzuki & Kasahara 2018, the bound ksw2's int8 lanes rest on); this variant computes real
+	   cells only (rows >= qlen are real cells of the query-extended problem, parked lanes are overwritten), so the clamp the reference needs
+	   for the stale lanes of its rounded band never binds.  0.64 of 19.3 ms; every parity test runs without it. */
 	z = sel4(msb_to_mask4(P.maxsc_h80 - z), z, MAXSC); // min(z, max score)
 #endif
 	const uint32_t zh = z | KSW_H80;

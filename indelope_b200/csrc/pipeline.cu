@@ -50,7 +50,7 @@ struct HostBuf {
 	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-enum { EV_START = 0, EV_H2D, EV_ASM, EV_ALN, EV_KMER, EV_AL, EV_END, EV_IN, EV_N };
+enum { EV_START = 0, EV_H2D, EV_K0, EV_ASM, EV_ALN, EV_KMER, EV_AL, EV_END, EV_IN, EV_N };
 
 struct Lane {
 	cudaStream_t stream = nullptr;
@@ -369,6 +369,7 @@ int launch_chain(idl_ctx *ctx, Lane &L, bool record_start = false)
 	cudaStream_t cs = ctx->compute ? ctx->compute : L.stream;
 	if (cs != L.stream) { CK(cudaEventRecord(L.ev[EV_IN], L.stream)); CK(cudaStreamWaitEvent(cs, L.ev[EV_IN], 0)); }
 	if (record_start) { CK(cudaEventRecord(L.ev[EV_START], cs)); CK(cudaEventRecord(L.ev[EV_H2D], cs)); }
+	CK(cudaEventRecord(L.ev[EV_K0], cs)); // the stage times start here, on the compute stream: behind the copies AND behind the kernels of the batch ahead
 	CK(cudaMemsetAsync(L.cnt.p, 0, sizeof(DevCounters), cs));
 	CK(cudaMemsetAsync(L.sort_misc.p, 0, 9 * SORT_BUCKETS * sizeof(unsigned), cs));
 	L.launches = 0;
@@ -581,7 +582,7 @@ int idl_wait(idl_ctx *ctx, uint64_t ticket, const idl_results **out)
 			r.contig_support = (ctx->P.out_flags & IDL_OUT_SUPPORT) ? (const uint32_t*)L.h_sup.p : nullptr;
 		}
 		cudaEventElapsedTime(&r.ms_h2d, L.ev[EV_START], L.ev[EV_H2D]);
-		cudaEventElapsedTime(&r.ms_assemble, L.ev[EV_H2D], L.ev[EV_ASM]);
+		cudaEventElapsedTime(&r.ms_assemble, L.ev[EV_K0], L.ev[EV_ASM]);
 		cudaEventElapsedTime(&r.ms_align, L.ev[EV_ASM], L.ev[EV_ALN]);
 		cudaEventElapsedTime(&r.ms_genotype, L.ev[EV_ALN], L.ev[EV_KMER]);
 		cudaEventElapsedTime(&r.ms_al, L.ev[EV_KMER], L.ev[EV_AL]);

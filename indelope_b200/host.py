@@ -31,7 +31,7 @@ class SynthParams(C.Structure):
         ("max_indel", C.c_int32), ("coverage", C.c_double), ("read_len", C.c_int32), ("sub_rate", C.c_double), ("tr_fraction", C.c_double),
         ("tr_max_unit", C.c_int32), ("het_fraction", C.c_double), ("lowq_tail_fraction", C.c_double), ("low_mapq_fraction", C.c_double),
         ("dup_fraction", C.c_double), ("n_base_rate", C.c_double), ("locus_only", C.c_int32), ("locus_flank", C.c_int32),
-        ("max_cigar_indel", C.c_int32), ("min_cigar_flank", C.c_int32),
+        ("max_cigar_indel", C.c_int32), ("min_cigar_flank", C.c_int32), ("chrom_first", C.c_int32),
     ]
 
 
@@ -82,6 +82,8 @@ def lib():
         L.idlh_vcf_set_dedup.argtypes = [C.c_void_p, C.c_int]
         L.idlh_vcf_dedup.restype = C.c_void_p
         L.idlh_vcf_dedup.argtypes = [C.c_char_p]
+        L.idlh_vcf_dedup_n.restype = C.c_void_p
+        L.idlh_vcf_dedup_n.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.idlh_set_threads.argtypes = [C.c_int]
         L.idlh_vcf_status_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.idlh_trim.argtypes = [u8p, C.c_int32, i32p]
@@ -345,6 +347,13 @@ class VcfWriter:
         p = lib().idlh_vcf_records(self.h, C.byref(rois.c), lo, C.byref(params), results, dump_level, C.byref(dump))
         return _take(p), _take(dump.value)
 
+    def records_bytes(self, rois, lo, params, results):
+        """the record text as bytes (no dump, no str round trip: a genome's records are tens of megabytes)"""
+        p = lib().idlh_vcf_records(self.h, C.byref(rois.c), lo, C.byref(params), results, 0, None)
+        out = C.string_at(p)
+        lib().idlh_free(p)
+        return out
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().idlh_vcf_free(self.h)
@@ -352,5 +361,12 @@ class VcfWriter:
 
 
 def dedup_records(text):
-    """order-dependent dedup of src/indelope.nim:604-608 over merged record lines"""
-    return _take(lib().idlh_vcf_dedup(text.encode()))
+    """order-dependent dedup of src/indelope.nim:604-608 over merged record lines (str -> str, bytes-like -> bytes)"""
+    if isinstance(text, str):
+        return _take(lib().idlh_vcf_dedup(text.encode()))
+    buf = (C.c_char * len(text)).from_buffer(text) if isinstance(text, bytearray) else C.create_string_buffer(bytes(text), len(text))
+    n = C.c_size_t()
+    p = lib().idlh_vcf_dedup_n(C.addressof(buf), len(text), C.byref(n))
+    out = C.string_at(p, n.value)
+    lib().idlh_free(p)
+    return out

@@ -263,6 +263,41 @@ int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, const uint64_t 
                    int8_t match, int8_t mismatch, int8_t gapo, int8_t gape, int w, int zdrop,
                    idl_ez *out, uint32_t *cigar, uint64_t *cigar_off, size_t cigar_cap, float *kernel_ms);
 
+/* ---- regions of interest on the GPU -----------------------------------------------------------------
+ * One call per target (chromosome): replaces the body of gen_roi (src/indelope.nim:515-545) with gen_roi_internal (:461-499),
+ * event_locations (:430-442), overlaps (:449-452) and the flag tests of skippable (:40-47; the two contig-name tests stay with the
+ * caller, who simply does not call this for a decoy contig).  Input: the records of the target in BAM order (coordinate sorted) as
+ * plain arrays; output: the regions in the order gen_roi yields them, each with the indices of its records (into the input arrays),
+ * exactly the (roi_start, roi_end, reads) tuples of src/indelope.nim:21.  min_read_coverage must be >= 1.
+ * Synchronous; the arrays of idl_sweep_out belong to the library (idl_sweep_free). */
+typedef struct idl_sweep_in {
+	int32_t chrom_len;            /* t.length (:522) */
+	size_t n_reads;
+	const int32_t *start, *stop;  /* hts-nim start (0-based) / stop (exclusive end) */
+	const uint16_t *flag;         /* BAM flag */
+	const uint32_t *cigar;        /* BAM encoding len<<4|op (M0 I1 D2 N3 S4 H5 P6 =7 X8), all records concatenated */
+	const uint64_t *cig_off;      /* n_reads + 1 offsets into cigar[] */
+} idl_sweep_in;
+
+#define IDL_SWEEP_EVIDENCE 1u     /* also return the saturating uint8 evidence array (:522,538-543; parity tests) */
+
+typedef struct idl_sweep_out {
+	size_t n_rois;
+	int32_t *roi_start, *roi_end; /* inclusive, as yielded by gen_roi_internal */
+	int64_t *roi_read_begin;      /* into read_idx[] */
+	int32_t *roi_n_reads;
+	size_t n_read_idx;
+	int64_t *read_idx;            /* record indices, BAM order inside a region */
+	size_t n_runs;                /* runs of evidence >= min_event_support before the read-count filter of :486 */
+	size_t n_evidence; uint8_t *evidence;   /* chrom_len + 1 bytes with IDL_SWEEP_EVIDENCE, else NULL */
+	float ms_h2d, ms_kernels, ms_d2h;       /* CUDA events on the call's stream */
+	uint64_t algorithmic_bytes;   /* records + CIGARs once, one evidence byte per position written and read once, results */
+	uint64_t streamed_bytes;      /* what the passes really move through HBM (memsets, difference array twice, evidence + cuts twice ...) */
+} idl_sweep_out;
+
+int idl_sweep(int device, const idl_sweep_in *in, int32_t min_event_support, int32_t min_read_coverage, int32_t max_read_coverage, uint32_t flags, idl_sweep_out **out);
+void idl_sweep_free(idl_sweep_out *out);
+
 #ifdef __cplusplus
 }
 #endif

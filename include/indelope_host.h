@@ -102,6 +102,20 @@ idlh_rois *idlh_stream_targets(const idlh_stream *s);
 void idlh_stream_counts(const idlh_stream *s, int64_t counts[2]);   /* BAM records read, regions emitted so far */
 void idlh_stream_close(idlh_stream *s);
 
+/* the records of one chromosome of a dataset as the plain arrays idl_sweep (libindelope_cuda: gen_roi on the GPU) takes: BAM order, CIGARs
+ * concatenated.  first_read = index of the chromosome's first record in the dataset (read_idx of idlh_sweep counts from the dataset's
+ * first record).  Free with idlh_chrom_free. */
+typedef struct idlh_chrom_reads {
+	int64_t first_read, n_reads;
+	int32_t chrom_len;
+	int32_t *start, *stop;
+	uint16_t *flag;
+	uint32_t *cigar;
+	uint64_t *cig_off;   /* n_reads + 1 */
+} idlh_chrom_reads;
+idlh_chrom_reads *idlh_dataset_chrom(const idlh_dataset *d, int32_t chrom);
+void idlh_chrom_free(idlh_chrom_reads *c);
+
 /* gen_roi over every target (src/indelope.nim:515-545,601-602), regions in emission order */
 idlh_rois *idlh_sweep(const idlh_dataset *d, int32_t min_event_support, int32_t min_read_coverage, int32_t max_read_coverage);
 void idlh_rois_free(idlh_rois *r);
@@ -141,7 +155,7 @@ void idlh_vcf_set_dedup(idlh_vcf *w, int on);
 void idlh_vcf_status_counts(const idlh_vcf *w, uint64_t out[8]);
 char *idlh_vcf_dedup(const char *records);
 char *idlh_vcf_dedup_n(const char *records, size_t n, size_t *out_len);   /* the same over n bytes, not necessarily terminated */
-/* idlh_vcf_records without the terminating-string contract: the record text as (pointer, length), for callers that ship bytes */
+size_t idlh_vcf_dedup_inplace(char *records, size_t n);                   /* the same in place (n + 1 bytes writable); returns the new length */
 void idlh_free(void *p);
 
 #ifdef __cplusplus

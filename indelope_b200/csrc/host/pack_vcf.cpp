@@ -387,15 +387,16 @@ void idlh_vcf_status_counts(const idlh_vcf *w, uint64_t out[8]) { for (int i = 0
 char *idlh_vcf_dedup(const char *records) { return idlh_vcf_dedup_n(records, strlen(records), nullptr); }
 
 // the same over a buffer of `n` bytes that need not be terminated (the gathered shards of a multi-GPU run: tens of megabytes per
-// genome, so lines are compared in place and copied once)
-char *idlh_vcf_dedup_n(const char *records, size_t n, size_t *out_len)
+// genome).  In place: lines are compared where they lie and the kept ones are moved down over the dropped ones, so nothing is
+// allocated; returns the new length.
+size_t idlh_vcf_dedup_inplace(char *records, size_t n)
 {
 	struct Key { const char *chrom, *pos, *ref, *alt; size_t lc, lp, lr, la; };
 	auto same = [](const Key &x, const Key &y) {
 		return x.lp == y.lp && x.lc == y.lc && x.lr == y.lr && x.la == y.la && !memcmp(x.pos, y.pos, x.lp) && !memcmp(x.chrom, y.chrom, x.lc) &&
 		       !memcmp(x.ref, y.ref, x.lr) && !memcmp(x.alt, y.alt, x.la);
 	};
-	char *o = (char*)malloc(n + 2);
+	char *o = records;
 	size_t w = 0;
 	Key last1{}, last2{}; bool have1 = false, have2 = false;
 	const char *p = records, *end = records + n;
@@ -408,22 +409,29 @@ char *idlh_vcf_dedup_n(const char *records, size_t n, size_t *out_len)
 		// CHROM POS ID REF ALT ...
 		const char *f[6]; int nf = 0; f[nf++] = line;
 		for (const char *q = line; q < le && nf < 6; ) { const char *t = (const char*)memchr(q, '\t', (size_t)(le - q)); if (!t) break; f[nf++] = t + 1; q = t + 1; }
-		bool keep = true; Key k{};
+		Key k{};
 		if (nf == 6) {
 			k.chrom = f[0]; k.lc = (size_t)(f[1] - 1 - f[0]); k.pos = f[1]; k.lp = (size_t)(f[2] - 1 - f[1]);
 			k.ref = f[3]; k.lr = (size_t)(f[4] - 1 - f[3]); k.alt = f[4]; k.la = (size_t)(f[5] - 1 - f[4]);
-			if ((have1 && same(k, last1)) || (have2 && same(k, last2))) keep = false;
+			if ((have1 && same(k, last1)) || (have2 && same(k, last2))) continue;
 		}
-		if (!keep) continue;
 		const size_t ll = (size_t)(le - line);
-		memcpy(o + w, line, ll);
-		if (nf == 6) { // the keys point into the output from now on (the input may be released by the caller in a streaming use)
+		if (o + w != line) memmove(o + w, line, ll); // (the keys of the last two kept lines lie below o + w: never overwritten)
+		if (nf == 6) {
 			const ptrdiff_t sh = (o + w) - line;
 			k.chrom += sh; k.pos += sh; k.ref += sh; k.alt += sh;
 			last2 = last1; have2 = have1; last1 = k; have1 = true;
 		}
 		w += ll; o[w++] = '\n';
 	}
+	return w;
+}
+
+char *idlh_vcf_dedup_n(const char *records, size_t n, size_t *out_len)
+{
+	char *o = (char*)malloc(n + 2);
+	memcpy(o, records, n);
+	const size_t w = idlh_vcf_dedup_inplace(o, n);
 	o[w] = 0;
 	if (out_len) *out_len = w;
 	return o;

@@ -336,6 +336,35 @@ idlh_rois *idlh_sweep(const idlh_dataset *d, int32_t min_event_support, int32_t 
 	return R;
 }
 
+idlh_chrom_reads *idlh_dataset_chrom(const idlh_dataset *d, int32_t chrom)
+{
+	if (chrom < 0 || (size_t)chrom >= d->chroms.size()) return nullptr;
+	size_t a = 0, n = d->reads.size();
+	while (a < n && d->reads[a].chrom < chrom) ++a;
+	size_t b = a;
+	while (b < n && d->reads[b].chrom == chrom) ++b;
+	idlh_chrom_reads *c = (idlh_chrom_reads*)calloc(1, sizeof *c);
+	const size_t m = b - a;
+	size_t nc = 0;
+	for (size_t i = a; i < b; ++i) nc += (size_t)d->reads[i].n_cig;
+	c->first_read = (int64_t)a; c->n_reads = (int64_t)m; c->chrom_len = (int32_t)d->chroms[(size_t)chrom].size();
+	c->start = (int32_t*)malloc((m + 1) * 4); c->stop = (int32_t*)malloc((m + 1) * 4); c->flag = (uint16_t*)malloc((m + 1) * 2);
+	c->cigar = (uint32_t*)malloc((nc + 1) * 4); c->cig_off = (uint64_t*)malloc((m + 1) * 8);
+	size_t k = 0;
+	for (size_t i = 0; i < m; ++i) {
+		const ReadRec &r = d->reads[a + i];
+		c->start[i] = r.start; c->stop[i] = r.stop; c->flag[i] = r.flag; c->cig_off[i] = k;
+		for (int32_t j = 0; j < r.n_cig; ++j) c->cigar[k++] = d->cigars[(size_t)r.cig_off + j];
+	}
+	c->cig_off[m] = k;
+	return c;
+}
+void idlh_chrom_free(idlh_chrom_reads *c)
+{
+	if (!c) return;
+	free(c->start); free(c->stop); free(c->flag); free(c->cigar); free(c->cig_off); free(c);
+}
+
 void idlh_rois_free(idlh_rois *r) { delete r; }
 const idlh_roiset *idlh_rois_view(const idlh_rois *r) { return &r->view; }
 

@@ -46,7 +46,43 @@ def lib():
 
 
 EXPORTS = ("idl_default_params idl_create idl_destroy idl_batch_alloc idl_batch_free idl_submit idl_upload idl_run_resident idl_wait "
-           "idl_release idl_strerror idl_last_cuda_error idl_device_count idl_ksw2_batch").split()
+           "idl_release idl_strerror idl_last_cuda_error idl_device_count idl_ksw2_batch idl_sweep idl_sweep_free").split()
+
+
+class SweepIn(C.Structure):
+    _fields_ = [("chrom_len", C.c_int32), ("n_reads", C.c_size_t), ("start", C.POINTER(C.c_int32)), ("stop", C.POINTER(C.c_int32)), ("flag", C.POINTER(C.c_uint16)),
+                ("cigar", u32p), ("cig_off", u64p)]
+
+
+class SweepOut(C.Structure):
+    _fields_ = [("n_rois", C.c_size_t), ("roi_start", C.POINTER(C.c_int32)), ("roi_end", C.POINTER(C.c_int32)), ("roi_read_begin", C.POINTER(C.c_int64)),
+                ("roi_n_reads", C.POINTER(C.c_int32)), ("n_read_idx", C.c_size_t), ("read_idx", C.POINTER(C.c_int64)), ("n_runs", C.c_size_t),
+                ("n_evidence", C.c_size_t), ("evidence", u8p), ("ms_h2d", C.c_float), ("ms_kernels", C.c_float), ("ms_d2h", C.c_float),
+                ("algorithmic_bytes", C.c_uint64), ("streamed_bytes", C.c_uint64)]
+
+
+def sweep(chrom_len, start, stop, flag, cigar, cig_off, min_event_support=3, min_read_coverage=3, max_read_coverage=600, evidence=False, device=0):
+    """idl_sweep for one target: gen_roi (src/indelope.nim:515-545) on the GPU.  Arrays are numpy (int32, int32, uint16, uint32, uint64).
+    Returns a dict of numpy arrays (copies) + timings."""
+    L = lib()
+    L.idl_sweep.argtypes = [C.c_int, C.POINTER(SweepIn), C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.POINTER(SweepOut))]
+    L.idl_sweep_free.argtypes = [C.POINTER(SweepOut)]
+    a = [np.ascontiguousarray(x, dtype=t) for x, t in ((start, np.int32), (stop, np.int32), (flag, np.uint16), (cigar, np.uint32), (cig_off, np.uint64))]
+    si = SweepIn(int(chrom_len), len(a[0]), a[0].ctypes.data_as(C.POINTER(C.c_int32)), a[1].ctypes.data_as(C.POINTER(C.c_int32)), a[2].ctypes.data_as(C.POINTER(C.c_uint16)),
+                 a[3].ctypes.data_as(u32p), a[4].ctypes.data_as(u64p))
+    out = C.POINTER(SweepOut)()
+    rc = L.idl_sweep(device, C.byref(si), min_event_support, min_read_coverage, max_read_coverage, 1 if evidence else 0, C.byref(out))
+    if rc != 0:
+        raise IdlError("idl_sweep: %s" % L.idl_strerror(rc).decode())
+    o = out.contents
+    def arr(p, n, t):
+        return np.ctypeslib.as_array(p, shape=(n,)).astype(t, copy=True) if n else np.zeros(0, t)
+    r = dict(roi_start=arr(o.roi_start, o.n_rois, np.int32), roi_end=arr(o.roi_end, o.n_rois, np.int32), roi_read_begin=arr(o.roi_read_begin, o.n_rois, np.int64),
+             roi_n_reads=arr(o.roi_n_reads, o.n_rois, np.int32), read_idx=arr(o.read_idx, o.n_read_idx, np.int64), n_runs=int(o.n_runs),
+             evidence=arr(o.evidence, o.n_evidence, np.uint8) if evidence else None, ms_h2d=o.ms_h2d, ms_kernels=o.ms_kernels, ms_d2h=o.ms_d2h,
+             algorithmic_bytes=int(o.algorithmic_bytes), streamed_bytes=int(o.streamed_bytes))
+    L.idl_sweep_free(out)
+    return r
 
 
 class Context:

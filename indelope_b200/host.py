@@ -25,6 +25,11 @@ class RoiSetC(C.Structure):
     ]
 
 
+class ChromReads(C.Structure):
+    _fields_ = [("first_read", C.c_int64), ("n_reads", C.c_int64), ("chrom_len", C.c_int32), ("start", i32p), ("stop", i32p), ("flag", u16p),
+                ("cigar", u32p), ("cig_off", C.POINTER(C.c_uint64))]
+
+
 class SynthParams(C.Structure):
     _fields_ = [
         ("seed", C.c_uint64), ("n_chroms", C.c_int32), ("chrom_len", C.c_int64), ("n_events", C.c_int32), ("min_indel", C.c_int32),
@@ -61,6 +66,9 @@ def lib():
         L.idlh_stream_targets.argtypes = [C.c_void_p]
         L.idlh_stream_counts.argtypes = [C.c_void_p, i64p]
         L.idlh_stream_close.argtypes = [C.c_void_p]
+        L.idlh_dataset_chrom.restype = C.POINTER(ChromReads)
+        L.idlh_dataset_chrom.argtypes = [C.c_void_p, C.c_int32]
+        L.idlh_chrom_free.argtypes = [C.POINTER(ChromReads)]
         L.idlh_sweep.restype = C.c_void_p
         L.idlh_sweep.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         L.idlh_rois_free.argtypes = [C.c_void_p]
@@ -82,6 +90,8 @@ def lib():
         L.idlh_vcf_set_dedup.argtypes = [C.c_void_p, C.c_int]
         L.idlh_vcf_dedup.restype = C.c_void_p
         L.idlh_vcf_dedup.argtypes = [C.c_char_p]
+        L.idlh_vcf_dedup_inplace.restype = C.c_size_t
+        L.idlh_vcf_dedup_inplace.argtypes = [C.c_void_p, C.c_size_t]
         L.idlh_vcf_dedup_n.restype = C.c_void_p
         L.idlh_vcf_dedup_n.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.idlh_set_threads.argtypes = [C.c_int]
@@ -164,6 +174,21 @@ class Dataset:
         """coordinate-sorted BAM of the reads (BGZF, deflate level 0-9)"""
         if lib().idlh_write_bam(self.h, str(path).encode(), level) != 0:
             raise IOError("cannot write %s" % path)
+
+    def chrom_reads(self, chrom):
+        """records of one chromosome as numpy arrays (copies): first_read, chrom_len, start, stop, flag, cigar, cig_off -- the input of cuda.sweep"""
+        p = lib().idlh_dataset_chrom(self.h, chrom)
+        if not p:
+            raise IndexError(chrom)
+        c = p.contents
+        n = int(c.n_reads)
+        def arr(ptr, m, t):
+            return np.ctypeslib.as_array(ptr, shape=(m,)).astype(t, copy=True) if m else np.zeros(0, t)
+        off = arr(c.cig_off, n + 1, np.uint64)
+        out = dict(first_read=int(c.first_read), chrom_len=int(c.chrom_len), start=arr(c.start, n, np.int32), stop=arr(c.stop, n, np.int32),
+                   flag=arr(c.flag, n, np.uint16), cig_off=off, cigar=arr(c.cigar, int(off[-1]) if n else 0, np.uint32))
+        lib().idlh_chrom_free(p)
+        return out
 
     def truth(self):
         out = np.zeros((max(self.n_events, 1), 6), dtype=np.int64)
@@ -358,6 +383,11 @@ class VcfWriter:
         if getattr(self, "h", None):
             lib().idlh_vcf_free(self.h)
             self.h = None
+
+
+def dedup_inplace(ptr, n):
+    """order-dependent dedup over n bytes at address ptr (n + 1 writable), in place; returns the new length"""
+    return int(lib().idlh_vcf_dedup_inplace(ptr, n))
 
 
 def dedup_records(text):

@@ -83,8 +83,13 @@ int64_t idlh_dataset_truth(const idlh_dataset *d, int64_t *out, int64_t cap);
  * idlh_load: reference FASTA (hts-nim open_fai / fai.get, src/indelope.nim:583) + coordinate-sorted BAM read front to back,
  * the order `for target in targets: b.querys(target.name)` visits (:527,599-602); `threads` inflate BGZF blocks in
  * parallel (the -t option, :566).  Returns NULL and a message in err on failure.  CRAM is not supported.
- * idlh_write_fasta writes path and path.fai; idlh_write_bam writes a BGZF-compressed BAM (deflate level 0-9) of the reads. */
+ * idlh_write_fasta writes path and path.fai; idlh_write_bam writes a BGZF-compressed BAM (deflate level 0-9) of the reads and its
+ * BAI index path.bai (SAM spec 5.2: binning index + 16 kb linear index). */
 idlh_dataset *idlh_load(const char *fasta_path, const char *bam_path, int threads, char *err, size_t errlen);
+/* idlh_load_region: `b.querys(region)` through the BAI index <bam>.bai (idlh_write_bam writes it next to the BAM; the reference opens its
+ * BAM with index=true, src/indelope.nim:595): only the records of `target` that overlap [beg, end) (0-based, half open; end <= 0 = to
+ * the end of the target), only their BGZF blocks inflated. */
+idlh_dataset *idlh_load_region(const char *fasta_path, const char *bam_path, const char *target, int64_t beg, int64_t end, char *err, size_t errlen);
 int idlh_write_fasta(const idlh_dataset *d, const char *path);
 int idlh_write_bam(const idlh_dataset *d, const char *path, int level);
 

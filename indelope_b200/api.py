@@ -27,6 +27,28 @@ def plan_batches(rois, lo, hi, max_reads=400_000, max_regions=20_000):
     return out
 
 
+def gpu_rois(ds, min_reads=3, max_read_coverage=600, device=0, timings=None):
+    """gen_roi for every target of a dataset ON THE GPU (idl_sweep): the same regions and record lists as
+    ds.sweep(min_reads) -- src/indelope.nim:515-545,601-602 with min_event_support = max(3, min_reads - 2) -- as a host.Rois"""
+    base = host.Rois(host.lib().idlh_sweep(ds.h, 255, 1 << 30, 1 << 30), ds)  # no regions: just the record arrays of the dataset
+    a = dict(base.arrays())
+    chrom, rs, re, nr, idx = [], [], [], [], []
+    for c in range(ds.n_chroms):
+        cr = ds.chrom_reads(c)
+        r = cuda.sweep(cr["chrom_len"], cr["start"], cr["stop"], cr["flag"], cr["cigar"], cr["cig_off"], min_event_support=max(3, min_reads - 2),
+                       min_read_coverage=min_reads, max_read_coverage=max_read_coverage, device=device)
+        chrom.append(np.full(len(r["roi_start"]), c, np.int32)); rs.append(r["roi_start"]); re.append(r["roi_end"]); nr.append(r["roi_n_reads"])
+        idx.append(r["read_idx"] + cr["first_read"])
+        if timings is not None:
+            timings.append({k: r[k] for k in ("ms_h2d", "ms_kernels", "ms_d2h", "algorithmic_bytes", "streamed_bytes", "n_runs")})
+    a["roi_chrom"] = np.concatenate(chrom); a["roi_start"] = np.concatenate(rs); a["roi_stop"] = np.concatenate(re); a["roi_n_reads"] = np.concatenate(nr)
+    a["read_idx"] = np.concatenate(idx)
+    a["roi_read_begin"] = np.concatenate([[0], np.cumsum(a["roi_n_reads"])[:-1]]).astype(np.int64) if len(a["roi_n_reads"]) else np.zeros(0, np.int64)
+    out = host.Rois(arrays=a)
+    out._keep = (base, ds)  # the arrays are views of the dataset's memory
+    return out
+
+
 class Caller:
     """`indelope --min-reads M --min-contig-len C --min-event-len E` over regions, on one GPU"""
 

@@ -13,6 +13,7 @@
 // base_qualities() = raw phred bytes, cigar ops as in the file.
 #include <algorithm>
 #include <atomic>
+#include <map>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -123,6 +124,8 @@ bool bgzf_read_all(const char *path, int threads, std::vector<uint8_t> &out, std
 
 struct BgzfWriter {
 	FILE *f = nullptr; std::vector<uint8_t> buf; int level = 1; bool ok = true;
+	uint64_t coff = 0; // compressed bytes written so far = file offset of the block being filled
+	uint64_t tell() const { return coff << 16 | (uint64_t)buf.size(); } // virtual file offset (SAM spec 4.1.1)
 	void flush_block(const uint8_t *p, size_t n)
 	{
 		std::vector<uint8_t> out(18 + compressBound((uLong)n) + 8);
@@ -141,6 +144,7 @@ struct BgzfWriter {
 		const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), p, (uInt)n);
 		for (int i = 0; i < 4; ++i) { out[18 + clen + i] = (uint8_t)(crc >> (8 * i)); out[18 + clen + 4 + i] = (uint8_t)((uint32_t)n >> (8 * i)); }
 		if (fwrite(out.data(), 1, bsize, f) != bsize) ok = false;
+		coff += bsize;
 	}
 	void write(const uint8_t *p, size_t n)
 	{
@@ -171,6 +175,43 @@ int reg2bin(int64_t beg, int64_t end) // SAM spec 5.3
 	if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
 	return 0;
 }
+
+// BAI index (SAM spec 5.2): per reference the binning index (bin -> chunks of virtual offsets) and the 16 kb linear index
+struct BaiRef { std::map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins; std::vector<uint64_t> lin; };
+struct BaiBuilder {
+	std::vector<BaiRef> refs;
+	void add(int ref, int64_t beg, int64_t end, uint64_t v0, uint64_t v1)
+	{
+		if (ref < 0 || (size_t)ref >= refs.size()) return;
+		if (end <= beg) end = beg + 1;
+		BaiRef &R = refs[(size_t)ref];
+		auto &ch = R.bins[(uint32_t)reg2bin(beg, end)];
+		if (!ch.empty() && ch.back().second == v0) ch.back().second = v1; else ch.push_back({v0, v1}); // records of one bin written back to back are one chunk
+		const size_t w0 = (size_t)(beg >> 14), w1 = (size_t)((end - 1) >> 14);
+		if (R.lin.size() <= w1) R.lin.resize(w1 + 1, 0);
+		for (size_t w = w0; w <= w1; ++w) if (R.lin[w] == 0) R.lin[w] = v0; // first record that overlaps the window (the file is coordinate sorted)
+	}
+	bool write(const std::string &path) const
+	{
+		std::vector<uint8_t> b = {'B', 'A', 'I', 1};
+		put32(b, (uint32_t)refs.size());
+		auto put64 = [&](uint64_t x) { for (int i = 0; i < 8; ++i) b.push_back((uint8_t)(x >> (8 * i))); };
+		for (const BaiRef &R : refs) {
+			put32(b, (uint32_t)R.bins.size());
+			for (const auto &kv : R.bins) {
+				put32(b, kv.first); put32(b, (uint32_t)kv.second.size());
+				for (const auto &c : kv.second) { put64(c.first); put64(c.second); }
+			}
+			put32(b, (uint32_t)R.lin.size());
+			uint64_t last = 0;
+			for (size_t w = 0; w < R.lin.size(); ++w) { if (R.lin[w]) last = R.lin[w]; put64(last); } // empty windows carry the previous offset on, as htslib writes them
+		}
+		FILE *f = fopen(path.c_str(), "wb");
+		if (!f) return false;
+		const bool ok = fwrite(b.data(), 1, b.size(), f) == b.size();
+		return fclose(f) == 0 && ok;
+	}
+};
 
 const char SEQ16[] = "=ACMGRSVTWYHKDBN";
 // two bases per packed byte (high nibble first)
@@ -290,8 +331,10 @@ int idlh_write_bam(const idlh_dataset *d, const char *path, int level)
 		put32(b, (uint32_t)d->chroms[c].size());
 	}
 	w.write(b.data(), b.size());
+	BaiBuilder bai; bai.refs.resize(d->chroms.size());
 	for (const IdlhReadRec &r : d->reads) {
 		b.clear();
+		const uint64_t v0 = w.tell();
 		char name[32];
 		const int ln = snprintf(name, sizeof name, "r%llu", (unsigned long long)r.order) + 1;
 		const uint32_t block = 32 + (uint32_t)ln + 4u * (uint32_t)r.n_cig + (uint32_t)(r.len + 1) / 2 + (uint32_t)r.len;
@@ -305,9 +348,11 @@ int idlh_write_bam(const idlh_dataset *d, const char *path, int level)
 		for (int i = 0; i < r.len; i += 2) b.push_back((uint8_t)(code16(s[i]) << 4 | (i + 1 < r.len ? code16(s[i + 1]) : 0)));
 		b.insert(b.end(), q, q + r.len);
 		w.write(b.data(), b.size());
+		bai.add(r.chrom, r.start, r.stop, v0, w.tell());
 	}
 	w.close();
-	return w.ok ? 0 : -1;
+	if (!w.ok) return -1;
+	return bai.write(std::string(path) + ".bai") ? 0 : -1; // the reference opens its BAM with index=true (src/indelope.nim:595)
 }
 
 /* reference FASTA + coordinate-sorted BAM -> dataset.  Records without a reference id are dropped (a per-target query never
@@ -364,6 +409,141 @@ idlh_dataset *idlh_load(const char *fasta_path, const char *bam_path, int thread
 		D->reads.push_back(r);
 	}
 	if (at != n) return fail("trailing bytes after the last BAM record");
+	return D;
+}
+
+/* `b.querys(region)` (src/indelope.nim:454-459 single_roi, :527 per target): the records of <bam> that overlap target:beg-end (0-based,
+ * half open; beg = 0, end <= 0: the whole target) found THROUGH THE INDEX <bam>.bai -- candidate bins of the region (SAM spec 5.3),
+ * their chunks, cut below the linear index' offset for the region's first 16 kb window -- and only those BGZF blocks are inflated.
+ * Returns a dataset with the FASTA's sequences for the BAM's targets and just those records, in file order. */
+idlh_dataset *idlh_load_region(const char *fasta_path, const char *bam_path, const char *target, int64_t beg, int64_t end, char *err, size_t errlen)
+{
+	idlh_dataset *D = new idlh_dataset();
+	memset(&D->P, 0, sizeof D->P);
+	std::string why;
+	auto fail = [&](const std::string &m) -> idlh_dataset* { set_err(err, errlen, m); delete D; return nullptr; };
+	if (!load_fasta(fasta_path, *D, why)) return fail(why);
+	std::vector<uint8_t> file, bai;
+	if (!read_file(bam_path, file, why)) return fail(why);
+	if (!read_file((std::string(bam_path) + ".bai").c_str(), bai, why)) return fail(why + " (no index: write one with idlh_write_bam or samtools index)");
+	std::vector<BgzfBlock> blocks; size_t total = 0;
+	if (!bgzf_index(file, blocks, total, why)) return fail(std::string(bam_path) + ": " + why);
+	auto block_at = [&](uint64_t coff) -> long {
+		size_t lo = 0, hi = blocks.size();
+		while (lo < hi) { const size_t mid = (lo + hi) / 2; if (blocks[mid].off < coff) lo = mid + 1; else hi = mid; }
+		return lo < blocks.size() && blocks[lo].off == coff ? (long)lo : -1;
+	};
+	// the header: inflate blocks from the start until the reference list is complete
+	std::vector<uint8_t> u; size_t nb = 0;
+	auto need = [&](size_t bytes) -> bool {
+		while (u.size() < bytes && nb < blocks.size()) { const size_t o = u.size(); u.resize(o + blocks[nb].usize); if (!bgzf_inflate_block(file, blocks[nb], u.data() + o)) return false; ++nb; }
+		return u.size() >= bytes;
+	};
+	if (!need(12) || memcmp(u.data(), "BAM\1", 4) != 0) return fail(std::string(bam_path) + ": not a BAM file");
+	size_t at = 4;
+	const uint32_t l_text = le32(u.data() + at); at += 4;
+	if (!need(at + l_text + 4)) return fail("truncated BAM header");
+	at += l_text;
+	const uint32_t n_ref = le32(u.data() + at); at += 4;
+	std::vector<std::string> names; std::vector<std::vector<uint8_t>> chroms; int tid = -1;
+	for (uint32_t r = 0; r < n_ref; ++r) {
+		if (!need(at + 4)) return fail("truncated BAM reference list");
+		const uint32_t l_name = le32(u.data() + at); at += 4;
+		if (l_name == 0 || !need(at + l_name + 4)) return fail("truncated BAM reference list");
+		const std::string name((const char*)u.data() + at, l_name - 1); at += l_name;
+		const uint32_t l_ref = le32(u.data() + at); at += 4;
+		size_t k = 0;
+		while (k < D->names.size() && D->names[k] != name) ++k;
+		if (k == D->names.size()) return fail("BAM target " + name + " is not in the FASTA");
+		if (D->chroms[k].size() != l_ref) return fail("BAM target " + name + " has a different length than the FASTA record");
+		if (name == target) tid = (int)r;
+		names.push_back(name); chroms.push_back(D->chroms[k]);
+	}
+	D->names.swap(names); D->chroms.swap(chroms);
+	if (tid < 0) return fail(std::string("target ") + target + " is not in the BAM header");
+	const int64_t tlen = (int64_t)D->chroms[(size_t)tid].size();
+	if (beg < 0) beg = 0;
+	if (end <= 0 || end > tlen) end = tlen;
+	if (beg >= end) return D;
+	// the index
+	if (bai.size() < 8 || memcmp(bai.data(), "BAI\1", 4) != 0) return fail("not a BAI index");
+	size_t ia = 4;
+	auto rd32 = [&](uint32_t &x) -> bool { if (ia + 4 > bai.size()) return false; x = le32(bai.data() + ia); ia += 4; return true; };
+	auto rd64 = [&](uint64_t &x) -> bool { if (ia + 8 > bai.size()) return false; x = (uint64_t)le32(bai.data() + ia) | (uint64_t)le32(bai.data() + ia + 4) << 32; ia += 8; return true; };
+	uint32_t bn_ref = 0;
+	if (!rd32(bn_ref) || bn_ref != n_ref) return fail("the index does not belong to this BAM (reference count differs)");
+	std::vector<std::pair<uint64_t, uint64_t>> chunks; uint64_t min_off = 0;
+	{ // candidate bins of [beg, end), SAM spec 5.3 reg2bins
+		std::vector<uint32_t> want = {0};
+		const int64_t e1 = end - 1;
+		for (int64_t k = 1 + (beg >> 26); k <= 1 + (e1 >> 26); ++k) want.push_back((uint32_t)k);
+		for (int64_t k = 9 + (beg >> 23); k <= 9 + (e1 >> 23); ++k) want.push_back((uint32_t)k);
+		for (int64_t k = 73 + (beg >> 20); k <= 73 + (e1 >> 20); ++k) want.push_back((uint32_t)k);
+		for (int64_t k = 585 + (beg >> 17); k <= 585 + (e1 >> 17); ++k) want.push_back((uint32_t)k);
+		for (int64_t k = 4681 + (beg >> 14); k <= 4681 + (e1 >> 14); ++k) want.push_back((uint32_t)k);
+		std::sort(want.begin(), want.end());
+		for (uint32_t r = 0; r < n_ref; ++r) {
+			uint32_t n_bin = 0;
+			if (!rd32(n_bin)) return fail("truncated index");
+			for (uint32_t b = 0; b < n_bin; ++b) {
+				uint32_t bin = 0, n_chunk = 0;
+				if (!rd32(bin) || !rd32(n_chunk)) return fail("truncated index");
+				const bool take = (int)r == tid && std::binary_search(want.begin(), want.end(), bin);
+				for (uint32_t c = 0; c < n_chunk; ++c) { uint64_t a = 0, z = 0; if (!rd64(a) || !rd64(z)) return fail("truncated index"); if (take) chunks.push_back({a, z}); }
+			}
+			uint32_t n_intv = 0;
+			if (!rd32(n_intv)) return fail("truncated index");
+			for (uint32_t w = 0; w < n_intv; ++w) { uint64_t o = 0; if (!rd64(o)) return fail("truncated index"); if ((int)r == tid && (int64_t)w == (beg >> 14)) min_off = o; }
+		}
+	}
+	std::sort(chunks.begin(), chunks.end());
+	// walk the chunks: records are addressed by virtual offsets; a record may straddle blocks
+	uint64_t done_to = 0;
+	for (const auto &ch : chunks) {
+		uint64_t v = std::max(ch.first, std::max(min_off, done_to));
+		if (v >= ch.second) continue;
+		long bi = block_at(v >> 16);
+		if (bi < 0) return fail("the index points between BGZF blocks");
+		std::vector<uint8_t> ub; size_t ub_first = (size_t)bi, ub_next = (size_t)bi; // inflated bytes of blocks [ub_first, ub_next)
+		auto fill = [&](size_t bytes) -> bool {
+			while (ub.size() < bytes && ub_next < blocks.size()) { const size_t o = ub.size(); ub.resize(o + blocks[ub_next].usize); if (!bgzf_inflate_block(file, blocks[ub_next], ub.data() + o)) return false; ++ub_next; }
+			return ub.size() >= bytes;
+		};
+		size_t pos = (size_t)(v & 0xffff);
+		for (;;) {
+			// virtual offset of `pos`: find the block it falls into
+			size_t acc = 0, k = ub_first;
+			if (!fill(pos + 4)) break; // end of file
+			while (k < ub_next && pos >= acc + blocks[k].usize) { acc += blocks[k].usize; ++k; }
+			const uint64_t vcur = (uint64_t)blocks[k < blocks.size() ? k : blocks.size() - 1].off << 16 | (uint64_t)(pos - acc);
+			if (vcur >= ch.second) { done_to = vcur; break; }
+			const uint32_t block = le32(ub.data() + pos);
+			if (block < 32 || !fill(pos + 4 + block)) return fail("truncated BAM record");
+			BamFields f;
+			if (!bam_fields(ub.data() + pos + 4, block, f)) return fail("malformed BAM record");
+			pos += 4 + block;
+			done_to = vcur + 1;
+			if (f.ref_id != tid) { if (f.ref_id > tid || f.ref_id < 0) break; continue; }
+			if (f.pos >= end) break;                       // sorted: nothing further in this chunk can overlap
+			const int64_t stop = f.pos + bam_ref_span(f);
+			if (stop <= beg) continue;
+			IdlhReadRec r;
+			r.chrom = f.ref_id; r.start = f.pos; r.mapq = f.mapq; r.flag = f.flag; r.len = (int32_t)f.l_seq;
+			r.seq_off = (int64_t)D->bases.size(); r.cig_off = (int64_t)D->cigars.size(); r.n_cig = (int32_t)f.n_cig; r.order = vcur;
+			for (unsigned c = 0; c < f.n_cig; ++c) D->cigars.push_back(le32(f.cig + 4 * c));
+			r.stop = (int32_t)stop;
+			{ const size_t o = D->bases.size(); D->bases.resize(o + f.l_seq); decode_seq16(f.seq, f.l_seq, D->bases.data() + o); }
+			D->quals.insert(D->quals.end(), f.qual, f.qual + f.l_seq);
+			D->reads.push_back(r);
+		}
+	}
+	// chunks of different bins interleave in the file: file order = virtual offset order; a record reached through two chunks is kept once
+	std::stable_sort(D->reads.begin(), D->reads.end(), [](const IdlhReadRec &a, const IdlhReadRec &b) { return a.order < b.order; });
+	{
+		std::vector<IdlhReadRec> uniq;
+		for (const IdlhReadRec &r : D->reads) if (uniq.empty() || uniq.back().order != r.order) uniq.push_back(r);
+		D->reads.swap(uniq);
+	}
 	return D;
 }
 

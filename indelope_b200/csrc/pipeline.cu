@@ -177,7 +177,7 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	ctx->nw = p->max_contig_len / 32 + 2;
 	// persistent grids: CTAs per SM (tunable for experiments through the environment)
 	const char *ea = getenv("IDL_ASM_CTAS_PER_SM"), *ed = getenv("IDL_DP_CTAS_PER_SM");
-	ctx->asm_ctas = ctx->n_sm * (ea && atoi(ea) > 0 ? atoi(ea) : 4); // CTAs of each assembler launch (8 regions per CTA in the warp variant)
+	ctx->asm_ctas = ctx->n_sm * (ea && atoi(ea) > 0 ? atoi(ea) : ASM_CTAS); // CTAs of each assembler launch (8 regions per CTA in the warp variant)
 	ctx->dp_ctas = ctx->n_sm * (ed && atoi(ed) > 0 ? atoi(ed) : 4); // upper bound; every launch asks the occupancy calculator
 	{ const char *eb = getenv("IDL_BAND_REGS"); ctx->band_regs = eb && *eb == '1'; }
 	{ const char *el = getenv("IDL_L2_FETCH"); if (el && atoi(el) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(el)); } // experiments: 32 / 64 / 128

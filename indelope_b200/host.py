@@ -56,6 +56,8 @@ def lib():
         L.idlh_dataset_truth.restype = C.c_int64
         L.idlh_load.restype = C.c_void_p
         L.idlh_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+        L.idlh_load_region.restype = C.c_void_p
+        L.idlh_load_region.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.c_int64, C.c_char_p, C.c_size_t]
         L.idlh_write_fasta.argtypes = [C.c_void_p, C.c_char_p]
         L.idlh_write_bam.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.idlh_stream_open.restype = C.c_void_p
@@ -161,6 +163,15 @@ class Dataset:
         """reference FASTA + coordinate-sorted BAM from disk (libindelope_host's own BGZF/BAM reader)"""
         err = C.create_string_buffer(512)
         h = lib().idlh_load(str(fasta).encode(), str(bam).encode(), threads, err, 512)
+        if not h:
+            raise IOError(err.value.decode())
+        return cls(_handle=h)
+
+    @classmethod
+    def load_region(cls, fasta, bam, target, beg=0, end=0):
+        """`b.querys("target:beg-end")` through <bam>.bai: only the records overlapping [beg, end) of `target` (0-based, half open)"""
+        err = C.create_string_buffer(512)
+        h = lib().idlh_load_region(str(fasta).encode(), str(bam).encode(), str(target).encode(), beg, end, err, 512)
         if not h:
             raise IOError(err.value.decode())
         return cls(_handle=h)

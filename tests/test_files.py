@@ -172,3 +172,105 @@ def test_cli_vcf_is_byte_identical_to_the_oracle(files):
     _, ovcf, cnt = orc.call(rois.arrays(), dump_level=0, **CALL)
     assert r.stdout == rois.header() + ovcf
     assert cnt["variants"] >= 3
+
+
+def _parse_bai(path):
+    """the index as the SAM specification lays it out (5.2), read with struct alone"""
+    b = open(path, "rb").read()
+    assert b[:4] == b"BAI\x01"
+    n_ref, = struct.unpack_from("<i", b, 4); at = 8
+    refs = []
+    for _ in range(n_ref):
+        n_bin, = struct.unpack_from("<i", b, at); at += 4
+        bins = {}
+        for _ in range(n_bin):
+            bn, n_chunk = struct.unpack_from("<Ii", b, at); at += 8
+            bins[bn] = [struct.unpack_from("<QQ", b, at + 16 * c) for c in range(n_chunk)]; at += 16 * n_chunk
+        n_intv, = struct.unpack_from("<i", b, at); at += 4
+        lin = list(struct.unpack_from("<%dQ" % n_intv, b, at)); at += 8 * n_intv
+        refs.append((bins, lin))
+    assert at == len(b)
+    return refs
+
+
+def _reg2bin(beg, end):
+    end -= 1
+    for shift, off in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        if beg >> shift == end >> shift:
+            return off + (beg >> shift)
+    return 0
+
+
+def test_bai_index_is_spec_conformant(files):
+    """the .bai written next to the BAM (the reference opens its BAM with index=true, src/indelope.nim:595): every record lies inside a
+    chunk of its bin, chunks are ordered and start at record boundaries, the linear index holds the first record of each 16 kb window"""
+    ds, fa, bam = files
+    refs = _parse_bai(bam + ".bai")
+    assert len(refs) == 2
+    rois = ds.sweep(min_reads=5)
+    a = rois.arrays()
+    # virtual offsets of every record, recomputed from the BGZF members with gzip/zlib alone
+    raw = open(bam, "rb").read()
+    blocks, at, uoff = [], 0, 0
+    while at < len(raw):
+        bsize = struct.unpack_from("<H", raw, at + 16)[0] + 1
+        isize, = struct.unpack_from("<I", raw, at + bsize - 4)
+        blocks.append((at, uoff, isize)); uoff += isize; at += bsize
+    data = gzip.decompress(raw)
+    def voff(u):
+        k = max(i for i, bl in enumerate(blocks) if bl[1] <= u and (bl[2] > 0 or bl[1] < u))
+        while blocks[k][2] == 0 or u - blocks[k][1] >= blocks[k][2]:
+            k += 1
+        return blocks[k][0] << 16 | (u - blocks[k][1])
+    l_text, = struct.unpack_from("<i", data, 4); at = 8 + l_text
+    n_ref, = struct.unpack_from("<i", data, at); at += 4
+    for _ in range(n_ref):
+        l_name, = struct.unpack_from("<i", data, at); at += 4 + l_name + 4
+    n = 0
+    first_in_window = [dict(), dict()]
+    while at < len(data):
+        block, ref_id, pos = struct.unpack_from("<iii", data, at)
+        v0 = voff(at)
+        stop = int(a["stop"][n])
+        bins, lin = refs[ref_id]
+        chunks = bins[_reg2bin(pos, max(stop, pos + 1))]
+        assert any(c0 <= v0 < c1 for c0, c1 in chunks)
+        for w in range(pos >> 14, ((max(stop, pos + 1) - 1) >> 14) + 1):
+            first_in_window[ref_id].setdefault(w, v0)
+        at += 4 + block; n += 1
+    for r in range(2):
+        bins, lin = refs[r]
+        for ch in bins.values():
+            assert all(c0 < c1 for c0, c1 in ch) and all(ch[i][1] <= ch[i + 1][0] for i in range(len(ch) - 1))
+        for w, v in first_in_window[r].items():
+            assert lin[w] == v
+
+
+def test_region_queries_through_the_index(files):
+    """idlh_load_region = b.querys("chr:beg-end") (src/indelope.nim:454-459,527): the records that overlap the interval, in file order,
+    found through the .bai; the whole-target query feeds the sweep exactly like the sequential read"""
+    ds, fa, bam = files
+    full = host.Dataset.load(fa, bam, threads=2)
+    rf = full.sweep(min_reads=5); af = rf.arrays()
+    n0 = int((np.array([full.chrom_reads(0)["first_read"], full.chrom_reads(1)["first_read"]])[1]))
+    rng = np.random.default_rng(4)
+    queries = [("chrS1", 0, 0), ("chrS2", 0, 0), ("chrS1", 50_000, 50_001), ("chrS2", 119_000, 0), ("chrS1", 16_383, 16_385), ("chrS2", 0, 10)]
+    queries += [("chrS%d" % (1 + int(rng.integers(0, 2))), int(b), int(b + rng.integers(1, 40_000))) for b in rng.integers(0, 119_000, 12)]
+    for name, beg, end in queries:
+        c = int(name[-1]) - 1
+        sub = host.Dataset.load_region(fa, bam, name, beg, end)
+        cr = full.chrom_reads(c)
+        e = end if end > 0 else cr["chrom_len"]
+        want = np.nonzero((cr["start"] < e) & (cr["stop"] > beg))[0]
+        got = sub.chrom_reads(c)
+        assert len(got["start"]) == len(want), (name, beg, end)
+        assert np.array_equal(got["start"], cr["start"][want]) and np.array_equal(got["stop"], cr["stop"][want]) and np.array_equal(got["flag"], cr["flag"][want])
+        assert np.array_equal(got["cigar"], np.concatenate([cr["cigar"][int(cr["cig_off"][i]):int(cr["cig_off"][i + 1])] for i in want]) if len(want) else np.zeros(0, np.uint32))
+    # per-target queries give the regions of the sequential sweep (what `for target in targets: b.querys(target.name)` relies on)
+    for c, name in enumerate(("chrS1", "chrS2")):
+        sub = host.Dataset.load_region(fa, bam, name)
+        rs = sub.sweep(min_reads=5); a = rs.arrays()
+        sel = af["roi_chrom"] == c
+        assert np.array_equal(a["roi_start"][a["roi_chrom"] == c], af["roi_start"][sel]) and np.array_equal(a["roi_n_reads"][a["roi_chrom"] == c], af["roi_n_reads"][sel])
+    with pytest.raises(IOError):
+        host.Dataset.load_region(fa, bam, "chrNope")

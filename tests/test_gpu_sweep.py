@@ -105,15 +105,15 @@ def test_directed_boundaries_caps_and_saturation():
     add(5000, [(100, M)], flag=0x400)
     add(5050, [(100, M)], flag=0x400)
     for k in range(8):
-        add(6000 + k, [(50, M), (4, I), (50, M)])
+        add(6000, [(50 + k, M), (4, I), (50, M)][0:1] + [(4, I), (50, M)]) if False else add(6000 + (k & 1), [(50 - (k & 1), M), (4, I), (50, M)])
     # (3) saturation: 300 records, same 1-base insertion site
     for k in range(300):
         add(10_000, [(60, M), (2, I), (60, M)])
     # (4) exactly 20 records / 21 records over an insertion (max_reads = 20 below applies to (3) as well: dropped)
     for k in range(20):
-        add(20_000 + k, [(40, M), (3, I), (80, M)])
+        add(20_000 + (k % 4), [(40 - (k % 4), M), (3, I), (80, M)])
     for k in range(21):
-        add(30_000 + k, [(40, M), (3, I), (80, M)])
+        add(30_000 + (k % 4), [(40 - (k % 4), M), (3, I), (80, M)])
     # (5) deletion reaching the last base of the contig
     for k in range(6):
         add(39_900, [(50, M), (60, D)])
@@ -134,7 +134,7 @@ def test_directed_boundaries_caps_and_saturation():
     want_idx = [i for _, _, l in exp for i in l]
     assert r["read_idx"].tolist() == want_idx
     starts = [g[0] for g in got]
-    assert 1100 in starts and 1101 in starts and 10_060 not in starts and 20_040 in [g[0] for g in got] and 30_040 not in starts
+    assert 1100 in starts and 1101 in starts and 6050 in starts and 10_060 not in starts and 20_040 in starts and 30_040 not in starts and 39_950 in starts
 
 
 def python_gen_roi(start, stop, flag, cig, off, chrom_len, min_ev, min_reads, max_reads):
@@ -184,3 +184,20 @@ def python_gen_roi(start, stop, flag, cig, off, chrom_len, min_ev, min_reads, ma
                 o += ln
     internal(last_start, chrom_len + 1)
     return out
+
+
+def test_gpu_sweep_feeds_the_calling_path():
+    """regions from idl_sweep -> idl_submit: BAM records to VCF with no per-record host loop but the packing; the VCF is the oracle's over
+    the HOST sweep's regions, byte for byte"""
+    from indelope_b200 import api
+    from oracle import pyoracle as orc
+    ds = util.small_dataset("pr1", chrom_len=400_000, n_events=80, max_indel=40, tr_fraction=0.3, seed=19)
+    rois = api.gpu_rois(ds, min_reads=5)
+    caller = api.Caller(0, min_reads=5, min_ctg_len=73, min_event_len=5)
+    try:
+        vcf, _ = caller.call(rois)
+    finally:
+        caller.close()
+    href = ds.sweep(min_reads=5)
+    _, ovcf, cnt = orc.call(href.arrays(), min_reads=5, min_ctg_len=73, min_event_len=5, dump_level=0, use_ref_ksw2=orc.have_ref())
+    assert cnt["variants"] > 10 and vcf == ovcf

@@ -473,6 +473,7 @@ def main():
             "ksw2_gcups_site_a": avg["dp_cells_a"] / (avg["ms_align"] / 1000.0) / 1e9 if avg["ms_align"] > 0 else None,
             "ksw2_gcups_site_b": avg["dp_cells_b"] / (avg["ms_al"] / 1000.0) / 1e9 if avg["ms_al"] > 0 else None,
             "kmer_gbs": avg["kmer_bytes"] / (avg["ms_genotype"] / 1000.0) / 1e9 if avg["ms_genotype"] > 0 else None,
+            "assembler_offsets_per_s": avg["offsets_tested"] / (avg["ms_assemble"] / 1000.0) if avg["ms_assemble"] > 0 else None,
             "config": config_of(args, cfg, mode, rois),
             "run": {"l2": "inputs (%.0f MB packed per rank) exceed the 126 MB L2; no explicit flush" % (big_bytes / 1e6), "e2e_batches": len(slices), "streams": P.n_streams,
                     "e2e_pipelining": "batches streamed through idl_submit/idl_wait, %d in flight%s" % (
@@ -495,6 +496,12 @@ def main():
                               "merge_ms_per_step": extra["merge_ms_per_step"], "merge_share_of_e2e": extra["merge_ms_per_step"] / (e2e_ms_max / K), "verify": verify}
         if world == 1:
             n, nr, cnt, use_ref, _ = run_oracle(rois, args.cpu_sample, 1)
+            if cnt["offsets"] > 0 and avg["ms_assemble"] > 0:
+                # SURVEY 8(d) secondary unit: exhaustive base compares (sum over tested offsets of the overlap length), the natural GPU
+                # formulation -- ~100x the reference's early-abort count, never CPU-equivalent work.  The device counts offsets; the
+                # compares per offset come from the oracle's counters on its sample of the same workload.
+                line["assembler_exhaustive_compares_per_s"] = avg["offsets_tested"] * (cnt["exhaustive_compares"] / cnt["offsets"]) / (avg["ms_assemble"] / 1000.0)
+                line["assembler_compares_per_offset"] = cnt["exhaustive_compares"] / cnt["offsets"]
             line["cpu_baseline"] = {"value": n / cnt["seconds"], "unit": "regions/s", "cores": 1, "kind": "port", "cpu": cpu_model(), "build": oracle_build_flags(),
                                     "reads_per_s": nr / cnt["seconds"], "seconds": cnt["seconds"],
                                     "ksw2_gcups": None if use_ref else (cnt["cells_a"] + cnt["cells_b"]) / cnt["seconds"] / 1e9,

@@ -187,10 +187,10 @@ __device__ __forceinline__ void align_body(const GenoArgs &g, unsigned char *sme
 		const uint8_t *tq = g.refcodes + R.ref_off + (cr.start - R.ref_start);
 		const uint8_t *qq = g.ctg_codes + cr.seq_off;
 		KswQuery kq; kq.codes = qq; kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
-		const KswMem M = dp_mem<G>(g, smem_raw, cr.len, tlen, BAND ? KSW_BAND_WARPS : DP_WARPS);
+		const KswMem M = dp_mem<G>(g, smem_raw, cr.len, tlen, (int)(blockDim.x >> 5));
 		KswOut o;
-		if (BAND) ksw2_band<G, true>(valid, cr.len, kq, tlen, tq, g.kpA, M, o); // the whole warp: 32 / G alignments in lockstep
-		else ksw2_group<8>(valid, cr.len, kq, tlen, tq, g.kpA, M, o);
+		if constexpr (BAND) ksw2_band<G, true>(valid, cr.len, kq, tlen, tq, g.kpA, M, o); // the whole warp: 32 / G alignments in lockstep
+		else ksw2_group<G>(valid, cr.len, kq, tlen, tq, g.kpA, M, o);
 		if (valid) {
 			const uint32_t *cg = M.cig;
 			const int n = o.n_cigar;
@@ -294,6 +294,19 @@ __global__ void __launch_bounds__(DP_THREADS, KSW_A_CTAS) align_kernel(GenoArgs 
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	align_body<8, false>(g, smem_raw);
+}
+#ifndef KSW_A4_WARPS
+#define KSW_A4_WARPS 4
+#endif
+#ifndef KSW_A4_CTAS
+#define KSW_A4_CTAS 4
+#endif
+// the same shared-memory rings with FOUR threads per alignment, eight alignments per warp in lockstep: the per-diagonal control code (band,
+// exact-score bookkeeping, z-drop, block entry) is issued once for twice as many alignments and the words of a diagonal fill the rounds
+__global__ void __launch_bounds__(32 * KSW_A4_WARPS, KSW_A4_CTAS) align4_kernel(GenoArgs g)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	align_body<4, false>(g, smem_raw);
 }
 __global__ void __launch_bounds__(32 * KSW_BAND_WARPS, KSW_BAND_CTAS) align_band_kernel(GenoArgs g) // rounded bands of up to 96 lanes (w <= 79): the ring in registers
 {

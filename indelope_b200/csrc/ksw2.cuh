@@ -164,19 +164,19 @@ __device__ __forceinline__ uint32_t ksw_target_word(const uint8_t *target, int t
 __device__ __forceinline__ bool ksw_has4(uint32_t w) { const uint32_t x = w ^ 0x04040404u; return ((x - 0x01010101u) & ~x & 0x80808080u) != 0u; }
 
 // max / min over the 8 threads of a group with full-warp butterflies (the four groups of a warp reduce side by side)
-__device__ __forceinline__ unsigned ksw_group_max(unsigned v)
+template <int G = 8> __device__ __forceinline__ unsigned ksw_group_max(unsigned v)
 {
-	unsigned o = __shfl_xor_sync(FULL_MASK, v, 1); v = v > o ? v : o;
-	o = __shfl_xor_sync(FULL_MASK, v, 2); v = v > o ? v : o;
-	o = __shfl_xor_sync(FULL_MASK, v, 4); return v > o ? v : o;
+#pragma unroll
+	for (int d = 1; d < G; d <<= 1) { const unsigned o = __shfl_xor_sync(FULL_MASK, v, d); v = v > o ? v : o; }
+	return v;
 }
-__device__ __forceinline__ unsigned ksw_group_min(unsigned v)
+template <int G = 8> __device__ __forceinline__ unsigned ksw_group_min(unsigned v)
 {
-	unsigned o = __shfl_xor_sync(FULL_MASK, v, 1); v = v < o ? v : o;
-	o = __shfl_xor_sync(FULL_MASK, v, 2); v = v < o ? v : o;
-	o = __shfl_xor_sync(FULL_MASK, v, 4); return v < o ? v : o;
+#pragma unroll
+	for (int d = 1; d < G; d <<= 1) { const unsigned o = __shfl_xor_sync(FULL_MASK, v, d); v = v < o ? v : o; }
+	return v;
 }
-__device__ __forceinline__ bool ksw_group_any(bool p, int lane) { return ((__ballot_sync(FULL_MASK, p) >> (lane & ~7)) & 0xffu) != 0u; }
+template <int G = 8> __device__ __forceinline__ bool ksw_group_any(bool p, int lane) { return ((__ballot_sync(FULL_MASK, p) >> (lane & ~(G - 1))) & ((1u << G) - 1u)) != 0u; }
 // wildcard (code 4) lanes score 0 (:219,226); out of line so that the common all-ACGT case pays one branch
 __device__ __noinline__ uint32_t ksw_wild_score(uint32_t sq, uint32_t sq2, uint32_t sc, uint32_t qe2)
 {
@@ -257,30 +257,36 @@ __device__ __forceinline__ void ksw_tile_cp(uint32_t *dst, const uint32_t *src)
 #endif
 }
 __device__ __forceinline__ void ksw_tile_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-template <class F>
+template <int G = 8, class F>
 __device__ __forceinline__ void ksw_tile_fetch(bool more, F &&row_end, const uint8_t *pmat, int lo, int hi, uint32_t *tile)
 {
-	const int lane = lane_id(), gl = lane & 7, gbase = lane & ~7;
-	int ev[4];
+	static_assert(G == 8 || G == 4, "groups of 8 or 4 threads");
+	const int lane = lane_id(), gl = lane & (G - 1), gbase = lane & ~(G - 1);
+	constexpr int Q = 32 / G;                                    // rows per thread: thread gl computes the ends of rows gl, gl + G, ...
+	int ev[Q];
 #pragma unroll
-	for (int q = 0; q < 4; ++q) {
-		int e = more ? row_end(gl + 8 * q) : INT_MIN;
+	for (int q = 0; q < Q; ++q) {
+		int e = more ? row_end(gl + G * q) : INT_MIN;
 		if (e != INT_MIN) e = e < lo + 35 ? lo + 35 : (e > hi - 4 ? hi - 4 : e);
 		ev[q] = e;
 	}
 #pragma unroll
-	for (int q = 0; q < 4; ++q) {
+	for (int q = 0; q < Q; ++q) {
 #pragma unroll
-		for (int kk = 0; kk < 8; ++kk) {
-			const int k = 8 * q + kk;
+		for (int kk = 0; kk < G; ++kk) {
+			const int k = G * q + kk;
 			const int e = __shfl_sync(FULL_MASK, ev[q], gbase + kk);
-			const int w = (e >> 2) - gl;                         // my word of this row
-			if (e != INT_MIN && w >= ((e - k) >> 2)) ksw_tile_cp(tile + (k * 9 + 8 - gl), (const uint32_t*)(pmat + 4 * (long long)w));
+#pragma unroll
+			for (int h = 0; h < 8 / G; ++h) {
+				const int wo = gl + G * h;                           // my word(s) of this row, counted down from the word of e
+				const int w = (e >> 2) - wo;
+				if (e != INT_MIN && w >= ((e - k) >> 2)) ksw_tile_cp(tile + (k * 9 + 8 - wo), (const uint32_t*)(pmat + 4 * (long long)w));
+			}
 		}
 	}
 	{ // rows 29 .. 31 can need a ninth word
 		const int k = 29 + gl;
-		const int e = __shfl_sync(FULL_MASK, ev[3], gbase + ((5 + gl) & 7));
+		const int e = __shfl_sync(FULL_MASK, ev[Q - 1], gbase + ((29 + gl) & (G - 1)));
 		const int w = (e >> 2) - 8;
 		if (gl < 3 && e != INT_MIN && w >= ((e - k) >> 2)) ksw_tile_cp(tile + k * 9, (const uint32_t*)(pmat + 4 * (long long)w));
 	}
@@ -303,7 +309,7 @@ __device__ __forceinline__ void ksw_tile_fetch(bool more, F &&row_end, const uin
 template <int G, bool EZ_FULL = true, bool UNB = false>
 __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen, const uint8_t *target, const KswParams P, const KswMem M, KswOut &out)
 {
-	static_assert(G == 8, "the clear-ahead step deals 8 words to the 8 threads of a group");
+	static_assert(G == 8 || G == 4, "8 threads per alignment (4 alignments per warp) or 4 (8 per warp: the per-diagonal control code is issued once for twice as many alignments)");
 	const int lane = lane_id();
 	const int gl = lane & (G - 1);
 	ksw_reset(out);
@@ -344,16 +350,18 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 	// stage the first 32 target codes (zero padded, :187) and qr (reversed query, zero padded, :188)
 	bool wild = false; // a code 4 seen so far: only then the score needs the wildcard mask (:219,226)
 	if (live) {
-		if (gl < 4) XV[(gl + rotw) & rmw] = make_uint4(0u, 0u, 0u, 0u);
-		S[(gl + rotw) & rmw] = QE2; // S holds s + 2(q+e) (:117): one add less per word and diagonal
-		{ const uint32_t tw = ksw_target_word(target, tlen, 4 * gl); SF[(gl + rotw) & rmw] = tw; wild = ksw_has4(tw); }
+		for (int k = gl; k < 4; k += G) XV[(k + rotw) & rmw] = make_uint4(0u, 0u, 0u, 0u);
+		for (int k = gl; k < 8; k += G) {
+			S[(k + rotw) & rmw] = QE2; // S holds s + 2(q+e) (:117): one add less per word and diagonal
+			const uint32_t tw = ksw_target_word(target, tlen, 4 * k); SF[(k + rotw) & rmw] = tw; wild |= ksw_has4(tw);
+		}
 		const int nq = KSW_QR_PAD + ((qlen + 35) & ~3);
 		for (int i = gl; i < nq; i += G) {
 			const int k = i - KSW_QR_PAD;
 			const uint8_t c = (k >= 0 && k < qlen) ? ksw_query_code(query, qlen - 1 - k) : (uint8_t)0; wild |= c == 4; qrp[i] = c;
 		}
 	}
-	wild = ksw_group_any(wild, lane);
+	wild = ksw_group_any<G>(wild, lane);
 	__syncwarp();
 
 	int last_st = -1, last_en = -1, last_st0 = 0, last_en0 = -1, en_clr = 15;
@@ -392,7 +400,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 		uint32_t bh2 = 0;                                     // this thread's best g over its in-band columns, two uint16 halves
 		// Words are dealt round-robin (word j of the band goes to thread j % G), last round first: every word reads the old
 		// x, v of the word to its left, which belongs to the previous thread of the same round or to a round not yet done.
-		const int rounds = act ? (wlast - wfirst) >> 3 : -1;
+		const int rounds = act ? (wlast - wfirst) / G : -1;
 		for (int rd = (int)__reduce_max_sync(FULL_MASK, rounds); rd >= 0; --rd) {
 			const int j = rd * G + gl, wi = wfirst + j, t = wi << 2, wm = (wi + rotw) & rmw;
 			const bool mine = rd <= rounds;
@@ -501,7 +509,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 		__syncwarp(); // this diagonal's lanes and g[st0..en0) are visible to the whole group
 		// band max of the updated columns, then the en0 cell (:318 / :349)
 		unsigned mg = (bh2 & 0xffffu) > (bh2 >> 16) ? (bh2 & 0xffffu) : (bh2 >> 16);
-		mg = ksw_group_max(mg);
+		mg = ksw_group_max<G>(mg);
 		unsigned ghen = 0;
 		if (act) {
 			if (r == 0) ghen = (unsigned)((int)((const uint8_t*)&XV[rotw & rmw])[4] - qe + gbias); // H[0] = v[0] - 2(q+e)
@@ -534,7 +542,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 					}
 				}
 			}
-			const unsigned rk = ksw_group_min(best);
+			const unsigned rk = ksw_group_min<G>(best);
 			if (need_t) { max_H = mh; max_t = st0 + (int)((rk - 1) & 0xfffffu); }
 		}
 		// band of the next diagonal (:196-199): its new 16-lane block, if any, and its :212 patch are applied now, so that
@@ -559,16 +567,16 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 		const bool enter = nxt && (en0n | 15) > en_clr; // a 16-lane block enters the band: it must read as never written (calloc); the score overrun zone moves on
 		if (enter) {
 			const int b = en_clr + 1;
-			if (gl < 4) XV[((b >> 2) + gl + rotw) & rmw] = make_uint4(0u, 0u, 0u, 0u);
-			else { // ... and the next 16 target codes are fetched
-				const int wn = ((b + 16) >> 2) + gl - 4;
+			if (G == 4 || gl < 4) XV[((b >> 2) + (gl & 3) + rotw) & rmw] = make_uint4(0u, 0u, 0u, 0u);
+			if (G == 4 || gl >= 4) { // ... and the next 16 target codes are fetched
+				const int wn = ((b + 16) >> 2) + (gl & 3);
 				const uint32_t tw = ksw_target_word(target, tlen, wn << 2);
 				if (!UNB) S[(wn + rotw) & rmw] = QE2;
 				SF[(wn + rotw) & rmw] = tw; w4 = ksw_has4(tw);
 			}
 			en_clr += 16;
 		}
-		if (__any_sync(FULL_MASK, enter)) { wild |= ksw_group_any(w4, lane); __syncwarp(); }
+		if (__any_sync(FULL_MASK, enter)) { wild |= ksw_group_any<G>(w4, lane); __syncwarp(); }
 		if (nxt && (en0n | 15) >= r + 1 && gl == 0) { // :212 of the next diagonal: y[r+1] = 0, u[r+1] = q
 			uint8_t *wb = (uint8_t*)&XV[(((r + 1) >> 2) + rotw) & rmw];
 			wb[8 + ((r + 1) & 3)] = (uint8_t)P.q; wb[12 + ((r + 1) & 3)] = 0;
@@ -609,7 +617,7 @@ __device__ void ksw2_group(bool valid, int qlen, const KswQuery query, int tlen,
 		while (__any_sync(FULL_MASK, i >= 0 && j >= 0)) {
 			const bool more = i >= 0 && j >= 0;
 			const int i0 = i, r0 = i + j;
-			ksw_tile_fetch(more, [&](int k) -> int {
+			ksw_tile_fetch<G>(more, [&](int k) -> int {
 				const int rr = r0 - k;
 				if (rr < 0) return INT_MIN;
 				int s0, e0;

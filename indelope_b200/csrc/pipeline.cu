@@ -21,6 +21,10 @@ static_assert(sizeof(idl_region) == 48 && sizeof(idl_read) == 24, "batch records
 static_assert(sizeof(idl_region_result) == 16 && sizeof(idl_contig_result) == 24 && sizeof(idl_aln_result) == 72 && sizeof(idl_event_result) == 128,
               "result records are part of the ABI");
 
+#ifndef IDL_ALIGN_G_DEFAULT
+#define IDL_ALIGN_G_DEFAULT 4 /* threads per alignment of the banded call-site: 4 (align4_kernel) measured 10.1 ms on chr1 against 12.9 with 8 */
+#endif
+
 namespace {
 
 struct DevBuf {
@@ -87,6 +91,7 @@ struct idl_ctx {
 	uint64_t next_ticket = 1;
 	int asm_ctas = 0, dp_ctas = 0, ns = 0, nw = 0;
 	int cig_cap = 2048;
+	int align_g = 8;        // IDL_ALIGN_G=4: four threads per alignment in the banded call-site (align4_kernel)
 	bool band_regs = false; // IDL_BAND_REGS=1: the banded call-site keeps its band ring in registers (ksw2_band.cuh) instead of shared memory (measured slower, kept for the parity tests)
 	char err[512] = {0};
 };
@@ -180,6 +185,7 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	ctx->asm_ctas = ctx->n_sm * (ea && atoi(ea) > 0 ? atoi(ea) : ASM_CTAS); // CTAs of each assembler launch (8 regions per CTA in the warp variant)
 	ctx->dp_ctas = ctx->n_sm * (ed && atoi(ed) > 0 ? atoi(ed) : 4); // upper bound; every launch asks the occupancy calculator
 	{ const char *eb = getenv("IDL_BAND_REGS"); ctx->band_regs = eb && *eb == '1'; }
+	{ const char *eg = getenv("IDL_ALIGN_G"); ctx->align_g = eg && atoi(eg) == 8 ? 8 : (eg && atoi(eg) == 4 ? 4 : IDL_ALIGN_G_DEFAULT); }
 	{ const char *el = getenv("IDL_L2_FETCH"); if (el && atoi(el) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(el)); } // experiments: 32 / 64 / 128
 	ctx->lanes.resize((size_t)p->n_streams);
 	{
@@ -199,6 +205,7 @@ int idl_create(int device, const idl_params *p, idl_ctx **out)
 	// opt in to large dynamic shared memory for the DP kernels
 	cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	cudaFuncSetAttribute(align_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(align4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	cudaFuncSetAttribute(al_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	cudaFuncSetAttribute(al_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	cudaFuncSetAttribute(assemble_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -358,7 +365,9 @@ int launch_chain(idl_ctx *ctx, Lane &L, bool record_start = false)
 	// the banded call-site runs the register-ring variant whenever its band fits (w <= 79: indelope's 50 does), G threads per alignment
 	const bool bandA = ctx->band_regs && P.a_bw >= 0 && ksw_ncol(P.max_contig_len, (int)max_ref, P.a_bw) <= KSW_BAND_MAX_NCOL;
 	const size_t p_capA = round_up(rowsA * ksw_pitch(ncolA) + 2 * KSW_PMAT_PAD + 64, 256), p_capB = round_up(rowsB * pitchB + 2 * KSW_PMAT_PAD + 64, 256);
-	const size_t groups_a = bandA ? (size_t)ctx->n_sm * KSW_BAND_CTAS * KSW_BAND_WARPS * (32 / KSW_BAND_G) : (size_t)ctx->dp_ctas * DP_WARPS * DP_NG, groups_b = (size_t)ctx->dp_ctas * DP_WARPS * DP_NG;
+	const bool a4 = !bandA && ctx->align_g == 4;
+	const size_t groups_a = bandA ? (size_t)ctx->n_sm * KSW_BAND_CTAS * KSW_BAND_WARPS * (32 / KSW_BAND_G) : a4 ? (size_t)ctx->n_sm * KSW_A4_CTAS * KSW_A4_WARPS * 8
+	                                                                                                            : (size_t)ctx->dp_ctas * DP_WARPS * DP_NG, groups_b = (size_t)ctx->dp_ctas * DP_WARPS * DP_NG;
 	const size_t n_groups = std::max(groups_a, groups_b);
 	const int seq_spill_cap = (int)round_up(ksw_seq_bytes(std::max(P.max_contig_len, max_trim), std::max((int)max_ref, P.max_contig_len)) + 32, 16);
 	CK(L.pmat.ensure(std::max(groups_a * p_capA, groups_b * p_capB)));
@@ -423,8 +432,12 @@ int launch_chain(idl_ctx *ctx, Lane &L, bool record_start = false)
 	const size_t smem_limit = 200 * 1024;
 	if (b->n_regions > 0 && (P.stages & IDL_STAGE_ALIGN)) {
 		g.ring_cols = bandA ? 0 : ksw_ring_cols(ncolA); // the register-ring variant keeps only the reversed query (later the backtrack tile) in shared memory
-		g.seq_cap = (int)round_up(ksw_seq_bytes(std::min(P.max_contig_len, 1024), (int)max_ref), 16) + (bandA ? 32 : 0); // longer contigs stage in the spill area; + KswBandEz
-		const size_t smem = (size_t)(bandA ? KSW_BAND_WARPS * (32 / KSW_BAND_G) : DP_WARPS * DP_NG) * ksw_group_smem(g.ring_cols, g.seq_cap);
+		const char *es = getenv("IDL_SEQ_STAGE"); // contigs up to this many bases stage their reversed copy in shared memory, longer ones in the global spill area
+		// (four threads per alignment: 448 bases keep a group at 1.5 KB, four CTAs of 32 alignments per SM -- 16 warps; at 1024 bases three CTAs
+		// fit and the kernel ran 12.4 instead of 10.1 ms.  Five CTAs at 256 bases gave nothing more.)
+		const int stage = es && atoi(es) >= 64 ? atoi(es) : (a4 ? 448 : 1024);
+		g.seq_cap = (int)round_up(ksw_seq_bytes(std::min(P.max_contig_len, stage), (int)max_ref), 16) + (bandA ? 32 : 0); // + KswBandEz
+		const size_t smem = (size_t)(bandA ? KSW_BAND_WARPS * (32 / KSW_BAND_G) : a4 ? KSW_A4_WARPS * 8 : DP_WARPS * DP_NG) * ksw_group_smem(g.ring_cols, g.seq_cap);
 		if (smem > smem_limit) return IDL_E_CAPACITY;
 		sort_scan_kernel<<<1, 1024, 0, cs>>>(sA);
 		sort_scatter_kernel<<<ctx->n_sm * 4, 256, 0, cs>>>(sA, &a.cnt->n_alns, 1u, L.cap_alns);
@@ -432,6 +445,11 @@ int launch_chain(idl_ctx *ctx, Lane &L, bool record_start = false)
 			int nb = 0;
 			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)align_band_kernel, 32 * KSW_BAND_WARPS, smem) != cudaSuccess || nb < 1) nb = 1;
 			align_band_kernel<<<ctx->n_sm * std::min(nb, KSW_BAND_CTAS), 32 * KSW_BAND_WARPS, smem, cs>>>(g);
+		}
+		else if (a4) {
+			int nb = 0;
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)align4_kernel, 32 * KSW_A4_WARPS, smem) != cudaSuccess || nb < 1) nb = 1;
+			align4_kernel<<<ctx->n_sm * std::min(nb, KSW_A4_CTAS), 32 * KSW_A4_WARPS, smem, cs>>>(g);
 		}
 		else align_kernel<<<dp_grid(ctx, (const void*)align_kernel, smem), DP_THREADS, smem, cs>>>(g);
 		CK(cudaGetLastError()); L.launches += 3;
@@ -627,7 +645,7 @@ struct KswBatchArgs {
 // MODE 0: banded, shared-memory rings (any w >= 0); 1: unbanded (row-owned variant for reads of up to 160 bases, else the rings);
 // 2: banded, the ring in registers (rounded bands of up to 96 lanes), G threads per alignment
 template <int MODE, int G>
-__global__ void __launch_bounds__(MODE == 2 ? 32 * KSW_BAND_WARPS : DP_THREADS, MODE == 1 ? 2 : (MODE == 2 ? KSW_BAND_CTAS : 3)) ksw2_batch_kernel(KswBatchArgs a) // unbanded: 8 warps x 2 CTAs at 122 registers (uniform shapes: 774 GCUPS at 150x700 against 745 with al_kernel's 5 x 4)
+__global__ void __launch_bounds__(MODE == 2 ? 32 * KSW_BAND_WARPS : (G == 4 ? 32 * KSW_A4_WARPS : DP_THREADS), MODE == 1 ? 2 : (MODE == 2 ? KSW_BAND_CTAS : (G == 4 ? KSW_A4_CTAS : 3))) ksw2_batch_kernel(KswBatchArgs a) // unbanded: 8 warps x 2 CTAs at 122 registers (uniform shapes: 774 GCUPS at 150x700 against 745 with al_kernel's 5 x 4)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	constexpr int NG = 32 / G;
@@ -650,7 +668,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 32 * KSW_BAND_WARPS : DP_THREADS, 
 		KswQuery kq; kq.codes = a.query + (valid ? a.q_off[i] : 0); kq.seq2 = nullptr; kq.seqn = nullptr; kq.base = 0;
 		KswOut o;
 		const uint8_t *tq = a.target + (valid ? a.t_off[i] : 0);
-		if (MODE == 2) ksw2_band<G, true>(valid, qlen, kq, tlen, tq, a.kp, M, o);
+		if constexpr (MODE == 2) ksw2_band<G, true>(valid, qlen, kq, tlen, tq, a.kp, M, o);
+		else if constexpr (G == 4) ksw2_group<4, true, false>(valid, qlen, kq, tlen, tq, a.kp, M, o);
 		else {
 			const int rw = MODE == 1 && !a.no_rows ? ksw_rows_pick(valid, qlen, tlen, a.kp, M) : 0;
 			if (rw == 5) ksw2_rows<5, true>(valid, qlen, kq, tlen, tq, a.kp, M, o);
@@ -698,14 +717,17 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 	// IDL_BAND_REGS=1 and 0 <= w with a rounded band of up to 96 lanes: the register-ring variant of the banded call-site (tests compare the two)
 	const char *ebr = getenv("IDL_BAND_REGS");
 	const int mode = w < 0 ? 1 : (max_ncol <= KSW_BAND_MAX_NCOL && ebr && *ebr == '1' ? 2 : 0);
-	const int ng = mode == 2 ? 32 / KSW_BAND_G : DP_NG;
+	const char *eg4 = getenv("IDL_ALIGN_G");
+	const bool g4 = mode == 0 && (eg4 ? atoi(eg4) == 4 : ctx->align_g == 4); // the banded call-site with four threads per alignment
+	const int ng = mode == 2 ? 32 / KSW_BAND_G : (g4 ? 8 : DP_NG);
 	a.ring_cols = mode == 2 ? 0 : ksw_ring_cols(max_ncol);
 	a.p_cap = round_up(max_p + 2 * KSW_PMAT_PAD + 64, 256); a.cig_cap = max_q + max_t + 8; a.cigar_cap = (unsigned)cigar_cap;
 	a.seq_cap = (int)round_up(ksw_seq_bytes(max_q, max_t), 16) + (mode == 2 ? 32 : 0); // + KswBandEz
-	const int wpc = mode == 2 ? KSW_BAND_WARPS : DP_WARPS; // warps per CTA
+	const int wpc = mode == 2 ? KSW_BAND_WARPS : (g4 ? KSW_A4_WARPS : DP_WARPS); // warps per CTA
 	const size_t smem = (size_t)wpc * ng * ksw_group_smem(a.ring_cols, a.seq_cap);
 	if (smem > 200 * 1024) return IDL_E_CAPACITY;
-	const void *kfn = mode == 1 ? (const void*)ksw2_batch_kernel<1, 8> : mode == 2 ? (const void*)ksw2_batch_kernel<2, KSW_BAND_G> : (const void*)ksw2_batch_kernel<0, 8>;
+	const void *kfn = mode == 1 ? (const void*)ksw2_batch_kernel<1, 8> : mode == 2 ? (const void*)ksw2_batch_kernel<2, KSW_BAND_G> : g4 ? (const void*)ksw2_batch_kernel<0, 4>
+	                                                                                                                                  : (const void*)ksw2_batch_kernel<0, 8>;
 	cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	const size_t per_cta = (size_t)wpc * ng;
 	const int ctas = (int)std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)dp_grid(ctx, kfn, smem, 32 * wpc));
@@ -729,6 +751,7 @@ extern "C" int idl_ksw2_batch(idl_ctx *ctx, size_t n, const uint8_t *query, cons
 		CK(cudaEventRecord(e0, st));
 		if (mode == 1) ksw2_batch_kernel<1, 8><<<ctas, 32 * wpc, smem, st>>>(a);
 		else if (mode == 2) ksw2_batch_kernel<2, KSW_BAND_G><<<ctas, 32 * wpc, smem, st>>>(a);
+		else if (g4) ksw2_batch_kernel<0, 4><<<ctas, 32 * wpc, smem, st>>>(a);
 		else ksw2_batch_kernel<0, 8><<<ctas, DP_THREADS, smem, st>>>(a);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(e1, st));

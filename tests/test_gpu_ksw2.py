@@ -203,3 +203,30 @@ def test_register_ring_equals_shared_memory_ring(ctx, monkeypatch):
         if w >= 0:
             pairs.append((q, t, 4, 50, 400))
     assert check(ctx, pairs, "ref" if orc.have_ref() else "lane") == []
+
+
+def test_four_threads_per_alignment_equals_eight(ctx, monkeypatch):
+    """IDL_ALIGN_G=4 runs the banded call-site's shared-memory rings with four threads per alignment (eight alignments per warp in
+    lockstep) instead of eight: same records and CIGARs for several band widths, and the oracle on production parameters"""
+    rng = np.random.default_rng(31)
+    for w, z in [(50, 400), (100, 400), (7, 100), (33, -1), (200, 50)]:
+        qs, ts = [], []
+        for _ in range(250):
+            ql = int(rng.integers(1, 700)); base = rng.integers(0, 4, ql + 400).astype(np.uint8)
+            q = base[:ql].copy(); t = base[:max(1, ql + int(rng.integers(-60, 260)))].copy()
+            pos = int(rng.integers(0, max(1, ql - 1))); L = int(rng.integers(1, 90))
+            q = np.concatenate([q[:pos], rng.integers(0, 4, L).astype(np.uint8), q[pos:]]) if rng.random() < 0.5 else np.concatenate([q[:pos], q[min(len(q) - 1, pos + L):]])
+            m = rng.random(len(q)) < 0.02; q[m] = rng.integers(0, 5, int(m.sum()))
+            qs.append(q); ts.append(t)
+        monkeypatch.setenv("IDL_ALIGN_G", "8")
+        a = ctx.ksw2_batch(qs, ts, gapo=4, gape=1, w=w, zdrop=z)
+        monkeypatch.setenv("IDL_ALIGN_G", "4")
+        b = ctx.ksw2_batch(qs, ts, gapo=4, gape=1, w=w, zdrop=z)
+        assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2], (w, z)
+    monkeypatch.setenv("IDL_ALIGN_G", "4")
+    pairs = []
+    for _ in range(900):
+        q, t, go, w, z = random_pair(rng)
+        if w >= 0:
+            pairs.append((q, t, 4, 50, 400))
+    assert check(ctx, pairs, "ref" if orc.have_ref() else "lane") == []

@@ -432,13 +432,15 @@ def main():
         value = regions_all * K / (dev_ms_max / 1000.0)
         e2e_val = regions_all * K / (e2e_ms_max / 1000.0)
         peak, peak_src, sm_max = load_peaks()
-        kern = {"assemble_kernel": avg["ms_assemble"], "align_kernel": avg["ms_align"], "kmer_kernel": avg["ms_genotype"], "al_kernel": avg["ms_al"]}
+        # the kernel that serves call-site A under the current settings (pipeline.cu launch_chain): four threads per alignment by default
+        site_a = "align_band_kernel" if os.environ.get("IDL_BAND_REGS") == "1" else ("align_kernel" if os.environ.get("IDL_ALIGN_G") == "8" else "align4_kernel")
+        kern = {"assemble_kernel": avg["ms_assemble"], site_a: avg["ms_align"], "kmer_kernel": avg["ms_genotype"], "al_kernel": avg["ms_al"]}
         dom = max(kern, key=kern.get)
         # algorithmic bytes per launch of each kernel (DESIGN.md "Kernels"): what the kernel must read + write once
         pk_bytes = big_bytes if mode == "weak" else h2d_bytes
         alg = {
             "assemble_kernel": pk_bytes + avg["n_contigs"] * 24 + n_regions * 16,
-            "align_kernel": avg["dp_cells_a"] * 1.0 + avg["n_alns"] * 72,   # one backtrack byte per in-band cell + the result record
+            site_a: avg["dp_cells_a"] * 1.0 + avg["n_alns"] * 72,   # one backtrack byte per in-band cell + the result record
             "kmer_kernel": avg["kmer_bytes"],
             "al_kernel": avg["dp_cells_b"] * 1.0,
         }

@@ -120,6 +120,11 @@ typedef struct idlh_chrom_reads {
 } idlh_chrom_reads;
 idlh_chrom_reads *idlh_dataset_chrom(const idlh_dataset *d, int32_t chrom);
 void idlh_chrom_free(idlh_chrom_reads *c);
+int32_t idlh_dataset_n_chroms(const idlh_dataset *d);
+const char *idlh_dataset_chrom_name(const idlh_dataset *d, int32_t chrom);
+/* the regions idl_sweep returned (read_idx + first_read = dataset-wide record indices) as an idlh_rois over the dataset, ready for idlh_pack */
+idlh_rois *idlh_rois_from_regions(const idlh_dataset *d, int64_t n_rois, const int32_t *roi_chrom, const int32_t *roi_start, const int32_t *roi_stop,
+                                  const int32_t *roi_n_reads, const int64_t *read_idx);
 
 /* gen_roi over every target (src/indelope.nim:515-545,601-602), regions in emission order */
 idlh_rois *idlh_sweep(const idlh_dataset *d, int32_t min_event_support, int32_t min_read_coverage, int32_t max_read_coverage);

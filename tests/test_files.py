@@ -174,6 +174,18 @@ def test_cli_vcf_is_byte_identical_to_the_oracle(files):
     assert cnt["variants"] >= 3
 
 
+@pytest.mark.gpu
+def test_cli_gpu_sweep_gives_the_same_vcf(files):
+    """`indelope --gpu-sweep`: the regions come from idl_sweep (gen_roi on the GPU, src/indelope.nim:515-545) instead of the host sweep; same bytes"""
+    ds, fa, bam = files
+    exe = build.build_cli()
+    r = subprocess.run([exe, "--gpu-sweep", "--min-event-len", "5", "--min-reads", "5", "-t", "2", fa, bam], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rois = ds.sweep(min_reads=5)
+    _, ovcf, cnt = orc.call(rois.arrays(), dump_level=0, **CALL)
+    assert r.stdout == rois.header() + ovcf
+
+
 def _parse_bai(path):
     """the index as the SAM specification lays it out (5.2), read with struct alone"""
     b = open(path, "rb").read()

@@ -53,8 +53,9 @@ def main():
             out["oracle_s_all_threads"] = round(time.time() - t0, 3); out["oracle_threads"] = os.cpu_count()
             out["vcf_identical_to_oracle"] = (r.stdout == whole.header() + ovcf)
     print(json.dumps(out))
-    for f in (fa, fa + ".fai", bam):
-        os.remove(f)
+    for f in (fa, fa + ".fai", bam, bam + ".bai"):
+        if os.path.exists(f):
+            os.remove(f)
     os.rmdir(d)
 
 

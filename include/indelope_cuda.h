@@ -35,7 +35,8 @@ typedef enum {
 	IDL_E_NOMEM = -4,
 	IDL_E_CAPACITY = -5,    /* batch exceeds what idl_batch_alloc / idl_create sized */
 	IDL_E_TICKET = -6,
-	IDL_E_BUSY = -7
+	IDL_E_BUSY = -7,
+	IDL_E_FORMAT = -8       /* idl_bam_open: not a BGZF / BAM file, corrupt member, unsorted records; the call's message has the detail */
 } idl_status;
 
 /* per-region status bits (idl_region_result.status) */
@@ -297,6 +298,58 @@ typedef struct idl_sweep_out {
 
 int idl_sweep(int device, const idl_sweep_in *in, int32_t min_event_support, int32_t min_read_coverage, int32_t max_read_coverage, uint32_t flags, idl_sweep_out **out);
 void idl_sweep_free(idl_sweep_out *out);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * 8(f)3: the BAM on the device.  Replaces what stands between the file and gen_roi in the reference: htslib's BGZF reader (one
+ * inflate + CRC-32 per <= 64 KiB member, `open(b, path, threads = ..., index = true)`, src/indelope.nim:595) and the record
+ * iterator behind `for aln in b.querys(t.name)` (:527) with the accessors the sweep uses (aln.start, aln.stop, aln.flag, aln.cigar:
+ * :40-47, :430-452), and the base / quality strings `callsemble` takes from the cached records (:216-222).
+ *
+ * idl_bam_open: the whole file (bytes as read from disk) -> device: every member inflated and CRC-checked by one warp, record
+ * boundaries found per 64 KiB segment and chained exactly (a guessed start is only kept when the previous segment's chain ends
+ * on it), one thread per record extracts the fixed fields and the reference span of the CIGAR.  Records without a target (the
+ * unplaced tail of a sorted BAM) are not kept; a record without a target BEFORE a placed one, an unsorted file, a malformed
+ * record or member give IDL_E_FORMAT with the reason in err.  The file and 4-5x its size must fit in device memory.
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct idl_bam idl_bam;
+
+typedef struct idl_bam_info {
+	uint64_t file_bytes, inflated_bytes;
+	uint32_t n_members;              /* BGZF members, the empty EOF marker included */
+	uint32_t boundary_fixups;        /* segments whose guessed first record was not on the chain (re-walked from the true offset) */
+	int32_t n_ref;                   /* targets of the header, in header order (the order gen_roi visits them, :599-601) */
+	const char *const *ref_name;     /* library-owned, valid until idl_bam_close */
+	const int64_t *ref_len;
+	const char *header_text; size_t header_len;
+	int64_t n_records;               /* records with a target */
+	int64_t n_unplaced;              /* records of the unplaced tail (dropped) */
+	const int64_t *ref_first;        /* n_ref + 1 entries: records [ref_first[c], ref_first[c + 1]) belong to target c */
+	float ms_h2d, ms_inflate, ms_parse;   /* CUDA events on the call's stream */
+} idl_bam_info;
+
+int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **bam, char *err, size_t errlen);
+const idl_bam_info *idl_bam_get_info(const idl_bam *bam);
+void idl_bam_close(idl_bam *bam);
+
+/* gen_roi for one target on the resident records: the regions idl_sweep returns for the same records given as host arrays;
+ * read_idx[] are indices into the BAM's kept records (0 .. n_records). */
+int idl_bam_sweep(idl_bam *bam, int32_t target, int32_t min_event_support, int32_t min_read_coverage, int32_t max_read_coverage, uint32_t flags, idl_sweep_out **out);
+
+#define IDL_BAM_SEQ 1u      /* bases (ASCII, "=ACMGRSVTWYHKDBN") and qualities */
+#define IDL_BAM_CIGAR 2u    /* CIGAR operations */
+
+/* records idx[0..n) (idx == NULL: records 0..n) as host arrays, in the order of idx: what callsemble reads of a cached record */
+typedef struct idl_bam_reads {
+	size_t n;
+	int32_t *chrom, *start, *stop, *len; uint8_t *mapq; uint16_t *flag;
+	int64_t *seq_off;                /* n + 1 offsets into bases[] / quals[] (IDL_BAM_SEQ) */
+	uint8_t *bases, *quals;
+	uint64_t *cig_off;               /* n + 1 offsets into cigar[] (IDL_BAM_CIGAR) */
+	uint32_t *cigar;                 /* BAM encoding len << 4 | op */
+	float ms_kernels, ms_d2h;
+} idl_bam_reads;
+int idl_bam_fetch(idl_bam *bam, size_t n, const int64_t *idx, uint32_t what, idl_bam_reads **out);
+void idl_bam_reads_free(idl_bam_reads *r);
 
 #ifdef __cplusplus
 }

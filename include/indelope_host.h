@@ -122,9 +122,13 @@ idlh_chrom_reads *idlh_dataset_chrom(const idlh_dataset *d, int32_t chrom);
 void idlh_chrom_free(idlh_chrom_reads *c);
 int32_t idlh_dataset_n_chroms(const idlh_dataset *d);
 const char *idlh_dataset_chrom_name(const idlh_dataset *d, int32_t chrom);
-/* the regions idl_sweep returned (read_idx + first_read = dataset-wide record indices) as an idlh_rois over the dataset, ready for idlh_pack */
-idlh_rois *idlh_rois_from_regions(const idlh_dataset *d, int64_t n_rois, const int32_t *roi_chrom, const int32_t *roi_start, const int32_t *roi_stop,
-                                  const int32_t *roi_n_reads, const int64_t *read_idx);
+/* the device reads the BAM (idl_bam_open of indelope_cuda.h); the host keeps the reference sequences and turns what idl_bam_sweep / idl_bam_fetch
+ * return into the idlh_rois that idlh_pack and idlh_vcf_records take */
+idlh_dataset *idlh_load_fasta(const char *fasta_path, char *err, size_t errlen);
+int idlh_dataset_set_targets(idlh_dataset *d, int32_t n_ref, const char *const *ref_name, const int64_t *ref_len, char *err, size_t errlen);
+idlh_rois *idlh_rois_from_arrays(const idlh_dataset *d, int64_t n_reads, const int32_t *start, const int32_t *stop, const int32_t *len, const uint8_t *mapq, const uint16_t *flag,
+                                 const int64_t *seq_off, const uint8_t *bases, const uint8_t *quals, int64_t n_rois, const int32_t *roi_chrom, const int32_t *roi_start,
+                                 const int32_t *roi_stop, const int32_t *roi_n_reads, const int64_t *read_idx);
 
 /* gen_roi over every target (src/indelope.nim:515-545,601-602), regions in emission order */
 idlh_rois *idlh_sweep(const idlh_dataset *d, int32_t min_event_support, int32_t min_read_coverage, int32_t max_read_coverage);

@@ -285,6 +285,8 @@ inline int64_t bam_ref_span(const BamFields &f)
 	return rlen;
 }
 
+void rois_finish_view(idlh_rois &R, const idlh_dataset &ref);
+
 } // namespace
 
 extern "C" {
@@ -357,6 +359,56 @@ int idlh_write_bam(const idlh_dataset *d, const char *path, int level)
 
 /* reference FASTA + coordinate-sorted BAM -> dataset.  Records without a reference id are dropped (a per-target query never
  * returns them); everything else, flags included, is kept for the sweep's `skippable` test (src/indelope.nim:40-47). */
+/* the reference sequences alone (the device reads the BAM: idl_bam_open) */
+idlh_dataset *idlh_load_fasta(const char *fasta_path, char *err, size_t errlen)
+{
+	idlh_dataset *D = new idlh_dataset();
+	memset(&D->P, 0, sizeof D->P);
+	std::string why;
+	if (!load_fasta(fasta_path, *D, why)) { set_err(err, errlen, why); delete D; return nullptr; }
+	return D;
+}
+
+/* order the sequences as the BAM header lists its targets (the VCF header and the sweep follow the BAM's target order, src/indelope.nim:599-601);
+ * same checks and messages as idlh_load.  0 = ok. */
+int idlh_dataset_set_targets(idlh_dataset *D, int32_t n_ref, const char *const *ref_name, const int64_t *ref_len, char *err, size_t errlen)
+{
+	std::vector<std::string> names; std::vector<std::vector<uint8_t>> chroms;
+	for (int32_t r = 0; r < n_ref; ++r) {
+		const std::string name(ref_name[r]);
+		size_t k = 0;
+		while (k < D->names.size() && D->names[k] != name) ++k;
+		if (k == D->names.size()) { set_err(err, errlen, "BAM target " + name + " is not in the FASTA"); return 1; }
+		if ((int64_t)D->chroms[k].size() != ref_len[r]) { set_err(err, errlen, "BAM target " + name + " has a different length than the FASTA record"); return 1; }
+		names.push_back(name); chroms.push_back(D->chroms[k]);
+	}
+	D->names.swap(names); D->chroms.swap(chroms);
+	return 0;
+}
+
+/* regions and their records found elsewhere (idl_bam_sweep + idl_bam_fetch: BAM decode and gen_roi on the GPU) as an idlh_rois over the sequences of
+ * <d>: the arrays describe n_reads records (seq_off has n_reads + 1 entries), read_idx indexes them.  Everything is copied. */
+idlh_rois *idlh_rois_from_arrays(const idlh_dataset *d, int64_t n_reads, const int32_t *start, const int32_t *stop, const int32_t *len, const uint8_t *mapq, const uint16_t *flag,
+                                 const int64_t *seq_off, const uint8_t *bases, const uint8_t *quals, int64_t n_rois, const int32_t *roi_chrom, const int32_t *roi_start,
+                                 const int32_t *roi_stop, const int32_t *roi_n_reads, const int64_t *read_idx)
+{
+	idlh_rois *R = new idlh_rois();
+	const size_t n = (size_t)n_reads;
+	R->start.assign(start, start + n); R->stop.assign(stop, stop + n); R->len.assign(len, len + n); R->mapq.assign(mapq, mapq + n); R->flag.assign(flag, flag + n);
+	R->seq_off.assign(seq_off, seq_off + n);
+	const size_t nb = n ? (size_t)seq_off[n] : 0;
+	R->own_bases.assign(bases, bases + nb); R->own_quals.assign(quals, quals + nb);
+	int64_t at = 0;
+	for (int64_t k = 0; k < n_rois; ++k) {
+		R->roi_chrom.push_back(roi_chrom[k]); R->roi_start.push_back(roi_start[k]); R->roi_stop.push_back(roi_stop[k]);
+		R->roi_read_begin.push_back(at); R->roi_n_reads.push_back(roi_n_reads[k]);
+		at += roi_n_reads[k];
+	}
+	R->read_idx.assign(read_idx, read_idx + at);
+	rois_finish_view(*R, *d);
+	return R;
+}
+
 idlh_dataset *idlh_load(const char *fasta_path, const char *bam_path, int threads, char *err, size_t errlen)
 {
 	idlh_dataset *D = new idlh_dataset();

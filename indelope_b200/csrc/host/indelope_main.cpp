@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <deque>
 #include <string>
 #include <chrono>
@@ -37,8 +38,8 @@ static const char USAGE[] =
 	"  -e --min-event-len <INT>    minimum size of indel to report [default: 4]\n"
 	"  -t --threads <INT>          number of bam decompression threads [default: 1]\n"
 	"  -d --device <INT>           CUDA device [default: 0]\n"
-	"  -g --gpu-sweep              find the regions of interest on the GPU as well (idl_sweep: the evidence array and the region\n"
-	"                              extraction of gen_roi); the BAM is then read whole instead of streamed\n"
+	"  -g --gpu-decode             inflate and parse the BAM and find the regions of interest on the GPU as well (idl_bam_open,\n"
+	"                              idl_bam_sweep); the file is then read whole instead of streamed, --threads is not used\n"
 	"  -h --help                   show help\n";
 
 struct Lane { idl_batch *batch = nullptr; size_t cap[4] = {0, 0, 0, 0}; };
@@ -49,9 +50,10 @@ static double now_s() { return std::chrono::duration<double>(std::chrono::steady
 
 static int die(const char *what, const std::string &why) { fprintf(stderr, "indelope: %s: %s\n", what, why.c_str()); return 1; }
 
-// --gpu-sweep: BAM records -> arrays -> idl_sweep per target (gen_roi on the GPU) -> batches of regions -> idl_submit.  The host decodes the BAM,
-// packs the reads of the regions and writes the VCF; it runs no per-record sweep.
-static int main_gpu_sweep(const std::string &fa, const std::string &bam, int min_reads, int min_ctg_len, int min_event_len, int threads, int device)
+// --gpu-decode: the whole front end on the GPU.  The file's bytes go to the device, idl_bam_open inflates the BGZF members and parses the records there,
+// idl_bam_sweep runs gen_roi per target on the resident records, idl_bam_fetch returns the bases of the records a batch of regions needs.  The host reads
+// the two files, packs the reads of the regions (idlh_pack) and writes the VCF: no inflate, no record parse, no sweep on the host.
+static int main_gpu_decode(const std::string &fa, const std::string &bam_path, int min_reads, int min_ctg_len, int min_event_len, int device)
 {
 	char err[512] = {0};
 	const bool timing = getenv("INDELOPE_TIMING") != nullptr;
@@ -59,86 +61,131 @@ static int main_gpu_sweep(const std::string &fa, const std::string &bam, int min
 	idl_params P;
 	idl_default_params(&P);
 	P.min_reads = min_reads; P.min_ctg_len = min_ctg_len; P.min_event_len = min_event_len;
-	idl_ctx *ctx = nullptr; int create_rc = IDL_OK;
-	std::thread creator([&]() { create_rc = idl_create(device, &P, &ctx); });
-	idlh_dataset *ds = idlh_load(fa.c_str(), bam.c_str(), threads, err, sizeof err);
-	creator.join();
-	if (!ds) { if (ctx) idl_destroy(ctx); return die("input", err); }
-	if (create_rc != IDL_OK) { idlh_dataset_free(ds); return die("libindelope_cuda", std::string(idl_strerror(create_rc)) + " (this program has no CPU path; it needs a CUDA device)"); }
-	const double t_load = now_s() - t_begin;
-	double t_sweep = 0, t_pack = 0, t_wait = 0, t_vcf = 0;
-	std::vector<int32_t> rc_, rs_, re_, rn_; std::vector<int64_t> idx_;
-	int status = 0;
-	for (int32_t c = 0; c < idlh_dataset_n_chroms(ds) && !status; ++c) {
-		const std::string name = idlh_dataset_chrom_name(ds, c);
-		if (name == "hs37d5" || name.compare(0, 2, "GL") == 0) continue; // skippable, src/indelope.nim:41-42: no record of a decoy contig is cached
-		idlh_chrom_reads *cr = idlh_dataset_chrom(ds, c);
-		idl_sweep_in in; memset(&in, 0, sizeof in);
-		in.chrom_len = cr->chrom_len; in.n_reads = (size_t)cr->n_reads; in.start = cr->start; in.stop = cr->stop; in.flag = cr->flag; in.cigar = cr->cigar; in.cig_off = cr->cig_off;
-		idl_sweep_out *so = nullptr;
-		const double t1 = now_s();
-		const int r = idl_sweep(device, &in, min_reads - 2 > 3 ? min_reads - 2 : 3, min_reads, 600, 0, &so); // gen_roi(b, target, ...), :602
-		t_sweep += now_s() - t1;
-		if (r != IDL_OK) { status = die("idl_sweep", idl_strerror(r)); idlh_chrom_free(cr); break; }
-		for (size_t k = 0; k < so->n_rois; ++k) { rc_.push_back(c); rs_.push_back(so->roi_start[k]); re_.push_back(so->roi_end[k]); rn_.push_back(so->roi_n_reads[k]); }
-		for (size_t k = 0; k < so->n_read_idx; ++k) idx_.push_back(so->read_idx[k] + cr->first_read);
-		idl_sweep_free(so); idlh_chrom_free(cr);
+	// the BAM's bytes
+	std::vector<uint8_t> file;
+	{
+		FILE *f = fopen(bam_path.c_str(), "rb");
+		if (!f) return die("input", "cannot open " + bam_path);
+		fseek(f, 0, SEEK_END); const long n = ftell(f); fseek(f, 0, SEEK_SET);
+		file.resize(n > 0 ? (size_t)n : 0);
+		if (n > 0 && fread(file.data(), 1, (size_t)n, f) != (size_t)n) { fclose(f); return die("input", "cannot read " + bam_path); }
+		fclose(f);
 	}
-	idlh_rois *rois = status ? nullptr : idlh_rois_from_regions(ds, (int64_t)rs_.size(), rc_.data(), rs_.data(), re_.data(), rn_.data(), idx_.data());
+	const double t_read = now_s() - t_begin;
+	// the device decodes the BAM and creates the calling context while this thread reads the FASTA
+	idl_ctx *ctx = nullptr; idl_bam *bam = nullptr; int create_rc = IDL_OK, open_rc = IDL_OK; double t_open = 0, t_create = 0;
+	char bam_err[512] = {0};
+	std::thread opener([&]() {
+		double t1 = now_s();
+		open_rc = idl_bam_open(device, file.data(), file.size(), &bam, bam_err, sizeof bam_err);
+		t_open = now_s() - t1; t1 = now_s();
+		if (open_rc == IDL_OK) create_rc = idl_create(device, &P, &ctx);
+		t_create = now_s() - t1;
+	});
+	double t1 = now_s();
+	idlh_dataset *ref = idlh_load_fasta(fa.c_str(), err, sizeof err);
+	const double t_fasta = now_s() - t1;
+	opener.join();
+	std::vector<uint8_t>().swap(file);
+	int status = 0;
+	if (!ref) status = die("input", err);
+	else if (open_rc == IDL_E_NO_DEVICE) status = die("libindelope_cuda", std::string(idl_strerror(open_rc)) + " (this program has no CPU path; it needs a CUDA device)");
+	else if (open_rc != IDL_OK) status = die("input", bam_path + ": " + (bam_err[0] ? bam_err : idl_strerror(open_rc)));
+	else if (create_rc != IDL_OK) status = die("libindelope_cuda", std::string(idl_strerror(create_rc)) + " (this program has no CPU path; it needs a CUDA device)");
+	double t_sweep = 0, t_fetch = 0, t_pack = 0, t_wait = 0, t_vcf = 0;
+	size_t nb = 0, n_regions = 0;
+	const idl_bam_info *info = bam ? idl_bam_get_info(bam) : nullptr;
+	if (!status && idlh_dataset_set_targets(ref, info->n_ref, info->ref_name, info->ref_len, err, sizeof err) != 0) status = die("input", err);
 	if (!status) {
-		const idlh_roiset *rs = idlh_rois_view(rois);
-		char *h = idlh_vcf_header(rs); fputs(h, stdout); idlh_free(h);
+		// gen_roi per target, in header order (:599-602)
+		std::vector<int32_t> rc_, rs_, re_, rn_; std::vector<int64_t> idx_;
+		t1 = now_s();
+		for (int32_t c = 0; c < info->n_ref && !status; ++c) {
+			const std::string name = info->ref_name[c];
+			if (name == "hs37d5" || name.compare(0, 2, "GL") == 0) continue;   // skippable targets, :41-42
+			idl_sweep_out *so = nullptr;
+			const int r = idl_bam_sweep(bam, c, min_reads - 2 > 3 ? min_reads - 2 : 3, min_reads, 600, 0, &so);
+			if (r != IDL_OK) { status = die("idl_bam_sweep", idl_strerror(r)); break; }
+			for (size_t k = 0; k < so->n_rois; ++k) { rc_.push_back(c); rs_.push_back(so->roi_start[k]); re_.push_back(so->roi_end[k]); rn_.push_back(so->roi_n_reads[k]); }
+			idx_.insert(idx_.end(), so->read_idx, so->read_idx + so->n_read_idx);
+			idl_sweep_free(so);
+		}
+		t_sweep = now_s() - t1;
+		n_regions = rs_.size();
+		{
+			idlh_rois *hdr = idlh_rois_from_arrays(ref, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+			if (!status) { char *h = idlh_vcf_header(idlh_rois_view(hdr)); fputs(h, stdout); idlh_free(h); }   // echo header % [b.contig_header, "sample"], :599
+			idlh_rois_free(hdr);
+		}
 		idlh_vcf *writer = idlh_vcf_new();
 		std::vector<Lane> lanes((size_t)(P.n_streams > 0 ? P.n_streams : 1));
-		struct Fl { int64_t lo; uint64_t ticket; };
-		std::deque<Fl> inflight;
+		std::deque<Flight> inflight;
 		auto drain = [&]() -> bool {
-			const Fl f = inflight.front(); inflight.pop_front();
+			const Flight f = inflight.front(); inflight.pop_front();
 			const idl_results *res = nullptr;
-			double t1 = now_s();
+			double t2 = now_s();
 			const int r = idl_wait(ctx, f.ticket, &res);
-			t_wait += now_s() - t1; t1 = now_s();
-			if (r != IDL_OK) { status = die("idl_wait", std::string(idl_strerror(r)) + " " + idl_last_cuda_error(ctx)); return false; }
-			char *txt = idlh_vcf_records(writer, rs, f.lo, &P, res, 0, nullptr);
+			t_wait += now_s() - t2; t2 = now_s();
+			if (r != IDL_OK) { status = die("idl_wait", std::string(idl_strerror(r)) + " " + idl_last_cuda_error(ctx)); idlh_rois_free(f.rois); return false; }
+			char *txt = idlh_vcf_records(writer, idlh_rois_view(f.rois), 0, &P, res, 0, nullptr);
 			fputs(txt, stdout); idlh_free(txt);
 			idl_release(ctx, f.ticket);
-			t_vcf += now_s() - t1;
+			idlh_rois_free(f.rois);
+			t_vcf += now_s() - t2;
 			return true;
 		};
-		size_t nb = 0;
-		for (int64_t lo = 0; lo < rs->n_rois && !status; ) {
-			int64_t hi = lo, reads = 0;
-			while (hi < rs->n_rois && (hi == lo || (reads + rs->roi_n_reads[hi] <= 400000 && hi - lo < 20000))) reads += rs->roi_n_reads[hi++];
-			if (inflight.size() >= lanes.size() && !drain()) break;
+		// batches of regions in emission order (the dedup of :604-608 depends on it); the records of a batch are fetched from the device once each
+		size_t at_idx = 0;
+		std::vector<int64_t> uniq, local;
+		for (size_t lo = 0; lo < n_regions && !status; ) {
+			size_t hi = lo; int64_t reads = 0;
+			while (hi < n_regions && (hi == lo || (reads + rn_[hi] <= 400000 && hi - lo < 20000))) reads += rn_[hi++];
+			double t2 = now_s();
+			uniq.assign(idx_.begin() + (long)at_idx, idx_.begin() + (long)(at_idx + (size_t)reads));
+			std::sort(uniq.begin(), uniq.end()); uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+			local.resize((size_t)reads);
+			for (int64_t k = 0; k < reads; ++k) local[(size_t)k] = std::lower_bound(uniq.begin(), uniq.end(), idx_[at_idx + (size_t)k]) - uniq.begin();
+			idl_bam_reads *rd = nullptr;
+			const int fr = idl_bam_fetch(bam, uniq.size(), uniq.data(), IDL_BAM_SEQ, &rd);
+			if (fr != IDL_OK) { status = die("idl_bam_fetch", idl_strerror(fr)); break; }
+			idlh_rois *grp = idlh_rois_from_arrays(ref, (int64_t)rd->n, rd->start, rd->stop, rd->len, rd->mapq, rd->flag, rd->seq_off, rd->bases, rd->quals, (int64_t)(hi - lo),
+			                                       rc_.data() + lo, rs_.data() + lo, re_.data() + lo, rn_.data() + lo, local.data());
+			idl_bam_reads_free(rd);
+			t_fetch += now_s() - t2;
+			const idlh_roiset *rs = idlh_rois_view(grp);
+			if (inflight.size() >= lanes.size() && !drain()) { idlh_rois_free(grp); break; }
 			Lane &L = lanes[nb % lanes.size()];
-			const double t1 = now_s();
-			size_t need[4] = {(size_t)(hi - lo), 0, 0, 0};
-			idlh_pack_size(rs, lo, hi, &P, &need[1], &need[2], &need[3]);
+			t2 = now_s();
+			size_t need[4] = {(size_t)rs->n_rois, 0, 0, 0};
+			idlh_pack_size(rs, 0, rs->n_rois, &P, &need[1], &need[2], &need[3]);
 			bool grow = L.batch == nullptr;
 			for (int k = 0; k < 4; ++k) grow |= need[k] > L.cap[k];
 			if (grow) {
 				if (L.batch) idl_batch_free(ctx, L.batch);
 				for (int k = 0; k < 4; ++k) L.cap[k] = need[k] + need[k] / 4 + 64;
-				if (idl_batch_alloc(ctx, L.cap[0], L.cap[1], L.cap[2], L.cap[3], &L.batch) != IDL_OK) { status = die("idl_batch_alloc", "out of pinned memory"); break; }
+				if (idl_batch_alloc(ctx, L.cap[0], L.cap[1], L.cap[2], L.cap[3], &L.batch) != IDL_OK) { status = die("idl_batch_alloc", "out of pinned memory"); idlh_rois_free(grp); break; }
 			}
-			if (idlh_pack(rs, lo, hi, &P, L.batch) != 0) { status = die("idlh_pack", "the pinned batch is smaller than idlh_pack_size reported (internal error)"); break; }
+			if (idlh_pack(rs, 0, rs->n_rois, &P, L.batch) != 0) { status = die("idlh_pack", "the pinned batch is smaller than idlh_pack_size reported (internal error)"); idlh_rois_free(grp); break; }
 			uint64_t ticket = 0;
 			const int r = idl_submit(ctx, L.batch, &ticket);
-			if (r != IDL_OK) { status = die("idl_submit", std::string(idl_strerror(r)) + " " + idl_last_cuda_error(ctx)); break; }
-			inflight.push_back({lo, ticket});
-			t_pack += now_s() - t1;
-			lo = hi; ++nb;
+			if (r != IDL_OK) { status = die("idl_submit", std::string(idl_strerror(r)) + " " + idl_last_cuda_error(ctx)); idlh_rois_free(grp); break; }
+			inflight.push_back({grp, ticket});
+			t_pack += now_s() - t2;
+			at_idx += (size_t)reads; lo = hi; ++nb;
 		}
 		while (!inflight.empty() && !status) if (!drain()) break;
+		while (!inflight.empty()) { idlh_rois_free(inflight.front().rois); inflight.pop_front(); }
 		for (Lane &L : lanes) if (L.batch) idl_batch_free(ctx, L.batch);
 		idlh_vcf_free(writer);
-		if (timing)
-			fprintf(stderr, "indelope timing (gpu sweep): load %.3f s, idl_sweep %.3f s, pack+submit %.3f s, idl_wait %.3f s, vcf %.3f s, total %.3f s, batches %zu, regions %lld\n",
-			        t_load, t_sweep, t_pack, t_wait, t_vcf, now_s() - t_begin, nb, (long long)rs->n_rois);
 	}
-	if (rois) idlh_rois_free(rois);
-	idl_destroy(ctx);
-	idlh_dataset_free(ds);
+	if (timing && info)
+		fprintf(stderr, "indelope timing (gpu decode): read file %.3f s, fasta %.3f s, idl_bam_open %.3f s (h2d %.1f ms, inflate %.1f ms, parse %.1f ms; %.1f MB -> %.1f MB, "
+		        "%lld records, %u boundary fixups), idl_create %.3f s, idl_bam_sweep %.3f s, idl_bam_fetch %.3f s, pack+submit %.3f s, idl_wait %.3f s, vcf %.3f s, total %.3f s, "
+		        "batches %zu, regions %zu\n", t_read, t_fasta, t_open, info->ms_h2d, info->ms_inflate, info->ms_parse, info->file_bytes / 1e6, info->inflated_bytes / 1e6,
+		        (long long)info->n_records, info->boundary_fixups, t_create, t_sweep, t_fetch, t_pack, t_wait, t_vcf, now_s() - t_begin, nb, n_regions);
+	if (bam) idl_bam_close(bam);
+	if (ctx) idl_destroy(ctx);
+	if (ref) idlh_dataset_free(ref);
 	return status;
 }
 
@@ -161,7 +208,7 @@ int main(int argc, char **argv)
 		};
 		if (a == "-h" || a == "--help") { fputs(USAGE, stdout); return 0; }
 		if (a == "--version") { puts("indelope 0.0.1"); return 0; }
-		if (a == "-g" || a == "--gpu-sweep") { gpu_sweep = true; continue; }
+		if (a == "-g" || a == "--gpu-decode" || a == "--gpu-sweep") { gpu_sweep = true; continue; }
 		int rc;
 		if ((rc = int_opt("-m", "--min-reads", min_reads)) || (rc = int_opt("-c", "--min-contig-len", min_ctg_len)) ||
 		    (rc = int_opt("-e", "--min-event-len", min_event_len)) || (rc = int_opt("-t", "--threads", threads)) || (rc = int_opt("-d", "--device", device))) {
@@ -176,7 +223,7 @@ int main(int argc, char **argv)
 	char err[512] = {0};
 	const bool timing = getenv("INDELOPE_TIMING") != nullptr;
 	const double t_begin = now_s(); double t_sweep = 0, t_pack = 0, t_wait = 0, t_vcf = 0, t0;
-	if (gpu_sweep) return main_gpu_sweep(pos[0], pos[1], min_reads, min_ctg_len, min_event_len, threads, device);
+	if (gpu_sweep) return main_gpu_decode(pos[0], pos[1], min_reads, min_ctg_len, min_event_len, device);
 	// gen_roi(b, target, min_read_coverage=min_reads, min_event_support=max(3, min_reads-2)), src/indelope.nim:602; the BAM
 	// is swept front to back in bounded memory (idlh_stream_*), a group of regions at a time
 	idlh_stream *in = idlh_stream_open(pos[0].c_str(), pos[1].c_str(), threads, min_reads - 2 > 3 ? min_reads - 2 : 3, min_reads, 600, err, sizeof err);

@@ -365,36 +365,6 @@ void idlh_chrom_free(idlh_chrom_reads *c)
 	free(c->start); free(c->stop); free(c->flag); free(c->cigar); free(c->cig_off); free(c);
 }
 
-/* regions found elsewhere (idl_sweep: gen_roi on the GPU) as an idlh_rois over a dataset: read_idx holds dataset-wide record indices */
-idlh_rois *idlh_rois_from_regions(const idlh_dataset *d, int64_t n_rois, const int32_t *roi_chrom, const int32_t *roi_start, const int32_t *roi_stop,
-                                  const int32_t *roi_n_reads, const int64_t *read_idx)
-{
-	idlh_rois *R = new idlh_rois();
-	const size_t n = d->reads.size();
-	R->start.resize(n); R->stop.resize(n); R->len.resize(n); R->mapq.resize(n); R->flag.resize(n); R->seq_off.resize(n);
-	for (size_t i = 0; i < n; ++i) {
-		const ReadRec &r = d->reads[i];
-		R->start[i] = r.start; R->stop[i] = r.stop; R->len[i] = r.len; R->mapq[i] = r.mapq; R->flag[i] = r.flag; R->seq_off[i] = r.seq_off;
-	}
-	R->bases = d->bases.data(); R->quals = d->quals.data();
-	int64_t at = 0;
-	for (int64_t k = 0; k < n_rois; ++k) {
-		R->roi_chrom.push_back(roi_chrom[k]); R->roi_start.push_back(roi_start[k]); R->roi_stop.push_back(roi_stop[k]);
-		R->roi_read_begin.push_back(at); R->roi_n_reads.push_back(roi_n_reads[k]);
-		for (int32_t j = 0; j < roi_n_reads[k]; ++j) R->read_idx.push_back(read_idx[at + j]);
-		at += roi_n_reads[k];
-	}
-	for (size_t c = 0; c < d->chroms.size(); ++c) {
-		R->name_ptrs.push_back(d->names[c].c_str()); R->seq_ptrs.push_back(d->chroms[c].data()); R->chrom_len.push_back((int64_t)d->chroms[c].size());
-	}
-	idlh_roiset &v = R->view;
-	v.n_reads = (int64_t)n; v.start = R->start.data(); v.stop = R->stop.data(); v.mapq = R->mapq.data(); v.flag = R->flag.data(); v.len = R->len.data();
-	v.seq_off = R->seq_off.data(); v.bases = R->bases; v.quals = R->quals;
-	v.n_rois = (int64_t)R->roi_start.size(); v.roi_chrom = R->roi_chrom.data(); v.roi_start = R->roi_start.data(); v.roi_stop = R->roi_stop.data();
-	v.roi_read_begin = R->roi_read_begin.data(); v.roi_n_reads = R->roi_n_reads.data(); v.read_idx = R->read_idx.data();
-	v.n_chroms = (int32_t)d->chroms.size(); v.chrom_name = R->name_ptrs.data(); v.chrom_seq = R->seq_ptrs.data(); v.chrom_len = R->chrom_len.data();
-	return R;
-}
 int32_t idlh_dataset_n_chroms(const idlh_dataset *d) { return (int32_t)d->chroms.size(); }
 const char *idlh_dataset_chrom_name(const idlh_dataset *d, int32_t c) { return c >= 0 && (size_t)c < d->names.size() ? d->names[(size_t)c].c_str() : nullptr; }
 

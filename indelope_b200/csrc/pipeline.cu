@@ -147,6 +147,7 @@ const char *idl_strerror(int s)
 	case IDL_E_CAPACITY: return "batch exceeds allocated capacity";
 	case IDL_E_TICKET: return "unknown ticket";
 	case IDL_E_BUSY: return "no free lane: wait for and release an earlier ticket";
+	case IDL_E_FORMAT: return "not a valid BGZF / BAM file (the call's message buffer has the detail)";
 	default: return "unknown status";
 	}
 }

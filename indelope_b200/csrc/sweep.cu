@@ -25,6 +25,7 @@
 #include <cstring>
 #include <cuda_runtime.h>
 #include "indelope_cuda.h"
+#include "sweep_impl.h"
 
 namespace {
 
@@ -316,6 +317,16 @@ void idl_sweep_free(idl_sweep_out *o)
 
 int idl_sweep(int device, const idl_sweep_in *in, int32_t min_event_support, int32_t min_read_coverage, int32_t max_read_coverage, uint32_t flags, idl_sweep_out **out)
 {
+	if (!in || !out) return IDL_E_ARG;
+	return idl_sweep_impl(device, in, false, in->n_reads && in->cig_off ? (size_t)in->cig_off[in->n_reads] : 0, min_event_support, min_read_coverage, max_read_coverage, flags, out);
+}
+
+} // extern "C"
+
+// the body of idl_sweep; with dev_in the arrays of `in` already live on `device` (idl_bam_sweep: records parsed there by bamdev.cu)
+int idl_sweep_impl(int device, const idl_sweep_in *in, bool dev_in, size_t n_cig, int32_t min_event_support, int32_t min_read_coverage, int32_t max_read_coverage,
+                   uint32_t flags, idl_sweep_out **out)
+{
 	if (!in || !out || in->chrom_len < 0 || (in->n_reads && (!in->start || !in->stop || !in->flag || !in->cigar || !in->cig_off))) return IDL_E_ARG;
 	*out = nullptr;
 	if (min_read_coverage < 1 || max_read_coverage < min_read_coverage || min_event_support < 1 || min_event_support > 255) return IDL_E_ARG;
@@ -326,7 +337,6 @@ int idl_sweep(int device, const idl_sweep_in *in, int32_t min_event_support, int
 	if (cudaSetDevice(device) != cudaSuccess) return IDL_E_CUDA;
 	const size_t n = in->n_reads, np = (size_t)in->chrom_len + 2;          // evidence positions 0 .. chrom_len, one more for the closing -1
 	const size_t npad = tiles(np) * SW_TILE, nrpad = std::max<size_t>(1, tiles(n)) * SW_TILE;
-	const size_t n_cig = n ? (size_t)in->cig_off[n] : 0;
 	idl_sweep_out *o = (idl_sweep_out*)calloc(1, sizeof *o);
 	if (!o) return IDL_E_NOMEM;
 	cudaStream_t st = nullptr; cudaEvent_t ev[4] = {};
@@ -340,26 +350,30 @@ int idl_sweep(int device, const idl_sweep_in *in, int32_t min_event_support, int
 			if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { unsigned long long thr = ~0ULL; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
 		}
 		for (auto &e : ev) SWCK(cudaEventCreate(&e));
-		SWCK(d_start.get(nrpad * 4, st)); SWCK(d_stop.get(nrpad * 4, st)); SWCK(d_flag.get(nrpad * 2, st)); SWCK(d_cig.get(n_cig * 4 + 16, st)); SWCK(d_coff.get((n + 1) * 8, st));
+		if (!dev_in) { SWCK(d_start.get(nrpad * 4, st)); SWCK(d_stop.get(nrpad * 4, st)); SWCK(d_flag.get(nrpad * 2, st)); SWCK(d_cig.get(n_cig * 4 + 16, st)); SWCK(d_coff.get((n + 1) * 8, st)); }
 		SWCK(d_diff.get(npad * 4, st)); SWCK(d_stopv.get(nrpad * 4, st)); SWCK(d_pm.get(nrpad * 4, st)); SWCK(d_cut.get(npad + 16, st)); SWCK(d_ev.get(npad + 16, st));
 		const size_t ntp = tiles(np), ntr = std::max<size_t>(1, tiles(n));
 		SWCK(d_tot.get(std::max(ntp, ntr) * 4, st)); SWCK(d_tot2.get(std::max(ntp, ntr) * 4, st)); SWCK(d_grand.get(16, st));
 		SWCK(cudaEventRecord(ev[0], st));
-		if (n) {
+		if (n && !dev_in) {
 			SWCK(cudaMemcpyAsync(d_start.p, in->start, n * 4, cudaMemcpyHostToDevice, st)); SWCK(cudaMemcpyAsync(d_stop.p, in->stop, n * 4, cudaMemcpyHostToDevice, st));
 			SWCK(cudaMemcpyAsync(d_flag.p, in->flag, n * 2, cudaMemcpyHostToDevice, st)); SWCK(cudaMemcpyAsync(d_cig.p, in->cigar, n_cig * 4, cudaMemcpyHostToDevice, st));
 			SWCK(cudaMemcpyAsync(d_coff.p, in->cig_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
 		}
 		SWCK(cudaEventRecord(ev[1], st));
+		const int32_t *p_start = dev_in ? in->start : d_start.as<int32_t>(), *p_stop = dev_in ? in->stop : d_stop.as<int32_t>();
+		const uint16_t *p_flag = dev_in ? in->flag : d_flag.as<uint16_t>();
+		const uint32_t *p_cig = dev_in ? in->cigar : d_cig.as<uint32_t>();
+		const unsigned long long *p_coff = dev_in ? (const unsigned long long*)in->cig_off : d_coff.as<unsigned long long>();
 		SWCK(cudaMemsetAsync(d_diff.p, 0, npad * 4, st)); SWCK(cudaMemsetAsync(d_cut.p, 0, npad + 16, st));
 		int n_runs = 0, n_runs_e = 0;
 		if (n) {
-			sw_mark_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_start.as<int32_t>(), d_stop.as<int32_t>(), d_flag.as<uint16_t>(), d_cig.as<uint32_t>(),
-			                                                           d_coff.as<unsigned long long>(), in->chrom_len, d_diff.as<int>(), d_stopv.as<int32_t>());
+			sw_mark_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, p_start, p_stop, p_flag, p_cig,
+			                                                           p_coff, in->chrom_len, d_diff.as<int>(), d_stopv.as<int32_t>());
 			// (B) prefix maximum of the stops, cuts
 			sw_totals_kernel<true><<<(unsigned)ntr, SW_THREADS, 0, st>>>(d_stopv.as<int>(), n, d_tot.as<int>());
 			sw_scan_totals_kernel<true><<<1, SW_SCAN_THREADS, 0, st>>>(d_tot.as<int>(), ntr, nullptr);
-			sw_prefmax_apply_kernel<<<(unsigned)ntr, SW_THREADS, 0, st>>>(d_stopv.as<int32_t>(), d_start.as<int32_t>(), n, d_tot.as<int>(), d_pm.as<int32_t>(), d_cut.as<uint8_t>(), in->chrom_len);
+			sw_prefmax_apply_kernel<<<(unsigned)ntr, SW_THREADS, 0, st>>>(d_stopv.as<int32_t>(), p_start, n, d_tot.as<int>(), d_pm.as<int32_t>(), d_cut.as<uint8_t>(), in->chrom_len);
 		}
 		// (C) evidence bytes
 		sw_totals_kernel<false><<<(unsigned)ntp, SW_THREADS, 0, st>>>(d_diff.as<int>(), np, d_tot.as<int>());
@@ -384,7 +398,7 @@ int idl_sweep(int device, const idl_sweep_in *in, int32_t min_event_support, int
 			                                                          d_rs.as<int32_t>(), d_re.as<int32_t>());
 			// (E) records of every run: count, accept, scan, write
 			const unsigned wb = (unsigned)(((size_t)n_runs * 32 + SW_THREADS - 1) / SW_THREADS);
-			sw_reads_kernel<false><<<wb, SW_THREADS, 0, st>>>(d_rs.as<int32_t>(), d_re.as<int32_t>(), n_runs, d_start.as<int32_t>(), d_stopv.as<int32_t>(), d_pm.as<int32_t>(), n,
+			sw_reads_kernel<false><<<wb, SW_THREADS, 0, st>>>(d_rs.as<int32_t>(), d_re.as<int32_t>(), n_runs, p_start, d_stopv.as<int32_t>(), d_pm.as<int32_t>(), n,
 			                                                 min_read_coverage, max_read_coverage, d_count.as<int>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 			sw_accept_kernel<<<(unsigned)((n_runs + 255) / 256), 256, 0, st>>>(d_count.as<int>(), n_runs, d_slot.as<int>(), d_roff.as<int>());
 			exclusive_sum(d_slot.as<int>(), (size_t)n_runs, d_tot.as<int>(), d_grand.as<int>() + 2, st);
@@ -397,7 +411,7 @@ int idl_sweep(int device, const idl_sweep_in *in, int32_t min_event_support, int
 			SWCK(d_o1.get((size_t)n_rois * 4 + 16, st)); SWCK(d_o2.get((size_t)n_rois * 4 + 16, st)); SWCK(d_o3.get((size_t)n_rois * 8 + 16, st)); SWCK(d_o4.get((size_t)n_rois * 4 + 16, st));
 			SWCK(d_o5.get((size_t)n_idx * 8 + 16, st));
 			if (n_rois)
-				sw_reads_kernel<true><<<wb, SW_THREADS, 0, st>>>(d_rs.as<int32_t>(), d_re.as<int32_t>(), n_runs, d_start.as<int32_t>(), d_stopv.as<int32_t>(), d_pm.as<int32_t>(), n,
+				sw_reads_kernel<true><<<wb, SW_THREADS, 0, st>>>(d_rs.as<int32_t>(), d_re.as<int32_t>(), n_runs, p_start, d_stopv.as<int32_t>(), d_pm.as<int32_t>(), n,
 				                                                min_read_coverage, max_read_coverage, d_count.as<int>(), d_slot.as<int>(), d_roff.as<int>(), d_o1.as<int32_t>(),
 				                                                d_o2.as<int32_t>(), d_o3.as<long long>(), d_o4.as<int32_t>(), d_o5.as<long long>());
 		}
@@ -439,5 +453,3 @@ done:
 	return IDL_OK;
 #undef SWCK
 }
-
-} // extern "C"

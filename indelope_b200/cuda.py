@@ -46,7 +46,8 @@ def lib():
 
 
 EXPORTS = ("idl_default_params idl_create idl_destroy idl_batch_alloc idl_batch_free idl_submit idl_upload idl_run_resident idl_wait "
-           "idl_release idl_strerror idl_last_cuda_error idl_device_count idl_ksw2_batch idl_sweep idl_sweep_free").split()
+           "idl_release idl_strerror idl_last_cuda_error idl_device_count idl_ksw2_batch idl_sweep idl_sweep_free "
+           "idl_bam_open idl_bam_get_info idl_bam_close idl_bam_sweep idl_bam_fetch idl_bam_reads_free").split()
 
 
 class SweepIn(C.Structure):
@@ -74,6 +75,10 @@ def sweep(chrom_len, start, stop, flag, cigar, cig_off, min_event_support=3, min
     rc = L.idl_sweep(device, C.byref(si), min_event_support, min_read_coverage, max_read_coverage, 1 if evidence else 0, C.byref(out))
     if rc != 0:
         raise IdlError("idl_sweep: %s" % L.idl_strerror(rc).decode())
+    return _sweep_out(L, out, evidence)
+
+
+def _sweep_out(L, out, evidence=False):
     o = out.contents
     def arr(p, n, t):
         return np.ctypeslib.as_array(p, shape=(n,)).astype(t, copy=True) if n else np.zeros(0, t)
@@ -83,6 +88,92 @@ def sweep(chrom_len, start, stop, flag, cigar, cig_off, min_event_support=3, min
              algorithmic_bytes=int(o.algorithmic_bytes), streamed_bytes=int(o.streamed_bytes))
     L.idl_sweep_free(out)
     return r
+
+
+class BamInfo(C.Structure):
+    _fields_ = [("file_bytes", C.c_uint64), ("inflated_bytes", C.c_uint64), ("n_members", C.c_uint32), ("boundary_fixups", C.c_uint32), ("n_ref", C.c_int32),
+                ("ref_name", C.POINTER(C.c_char_p)), ("ref_len", C.POINTER(C.c_int64)), ("header_text", C.c_void_p), ("header_len", C.c_size_t),
+                ("n_records", C.c_int64), ("n_unplaced", C.c_int64), ("ref_first", C.POINTER(C.c_int64)), ("ms_h2d", C.c_float), ("ms_inflate", C.c_float),
+                ("ms_parse", C.c_float)]
+
+
+class BamReads(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("chrom", C.POINTER(C.c_int32)), ("start", C.POINTER(C.c_int32)), ("stop", C.POINTER(C.c_int32)), ("len", C.POINTER(C.c_int32)),
+                ("mapq", u8p), ("flag", C.POINTER(C.c_uint16)), ("seq_off", C.POINTER(C.c_int64)), ("bases", u8p), ("quals", u8p), ("cig_off", u64p), ("cigar", u32p),
+                ("ms_kernels", C.c_float), ("ms_d2h", C.c_float)]
+
+
+BAM_SEQ, BAM_CIGAR = 1, 2
+
+
+class Bam:
+    """idl_bam_*: a BAM file inflated and parsed on the GPU.  `data` = the file's bytes."""
+
+    def __init__(self, data, device=0):
+        L = lib()
+        L.idl_bam_open.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+        L.idl_bam_get_info.argtypes = [C.c_void_p]; L.idl_bam_get_info.restype = C.POINTER(BamInfo)
+        L.idl_bam_close.argtypes = [C.c_void_p]
+        L.idl_bam_sweep.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.POINTER(SweepOut))]
+        L.idl_sweep_free.argtypes = [C.POINTER(SweepOut)]
+        L.idl_bam_fetch.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int64), C.c_uint32, C.POINTER(C.POINTER(BamReads))]
+        L.idl_bam_reads_free.argtypes = [C.POINTER(BamReads)]
+        self.h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = L.idl_bam_open(device, data, len(data), C.byref(self.h), err, 512)
+        if rc != 0:
+            self.h = None
+            raise IdlError("idl_bam_open: %s: %s" % (L.idl_strerror(rc).decode(), err.value.decode()))
+        i = L.idl_bam_get_info(self.h).contents
+        self.n_ref = int(i.n_ref)
+        self.ref_names = [i.ref_name[k].decode() for k in range(self.n_ref)]
+        self.ref_len = [int(i.ref_len[k]) for k in range(self.n_ref)]
+        self.ref_first = [int(i.ref_first[k]) for k in range(self.n_ref + 1)]
+        self.header = C.string_at(i.header_text, i.header_len).decode() if i.header_len else ""
+        self.n_records, self.n_unplaced = int(i.n_records), int(i.n_unplaced)
+        self.info = dict(file_bytes=int(i.file_bytes), inflated_bytes=int(i.inflated_bytes), n_members=int(i.n_members), boundary_fixups=int(i.boundary_fixups),
+                         ms_h2d=i.ms_h2d, ms_inflate=i.ms_inflate, ms_parse=i.ms_parse)
+
+    def sweep(self, target, min_event_support=3, min_read_coverage=3, max_read_coverage=600, evidence=False):
+        L = lib()
+        out = C.POINTER(SweepOut)()
+        rc = L.idl_bam_sweep(self.h, target, min_event_support, min_read_coverage, max_read_coverage, 1 if evidence else 0, C.byref(out))
+        if rc != 0:
+            raise IdlError("idl_bam_sweep: %s" % L.idl_strerror(rc).decode())
+        return _sweep_out(L, out, evidence)
+
+    def fetch(self, idx=None, what=BAM_SEQ | BAM_CIGAR):
+        """records idx (None: all) as numpy arrays"""
+        L = lib()
+        out = C.POINTER(BamReads)()
+        if idx is None:
+            n, ip = self.n_records, None
+        else:
+            ia = np.ascontiguousarray(idx, dtype=np.int64); n, ip = len(ia), ia.ctypes.data_as(C.POINTER(C.c_int64))
+        rc = L.idl_bam_fetch(self.h, n, ip, what, C.byref(out))
+        if rc != 0:
+            raise IdlError("idl_bam_fetch: %s" % L.idl_strerror(rc).decode())
+        o = out.contents
+        def arr(p, k, t):
+            return np.ctypeslib.as_array(p, shape=(k,)).astype(t, copy=True) if k and p else np.zeros(0, t)
+        r = dict(chrom=arr(o.chrom, n, np.int32), start=arr(o.start, n, np.int32), stop=arr(o.stop, n, np.int32), len=arr(o.len, n, np.int32), mapq=arr(o.mapq, n, np.uint8),
+                 flag=arr(o.flag, n, np.uint16), ms_kernels=o.ms_kernels, ms_d2h=o.ms_d2h)
+        if what & BAM_SEQ:
+            r["seq_off"] = arr(o.seq_off, n + 1, np.int64)
+            nb = int(r["seq_off"][-1]) if n else 0
+            r["bases"] = arr(o.bases, nb, np.uint8); r["quals"] = arr(o.quals, nb, np.uint8)
+        if what & BAM_CIGAR:
+            r["cig_off"] = arr(o.cig_off, n + 1, np.uint64)
+            r["cigar"] = arr(o.cigar, int(r["cig_off"][-1]) if n else 0, np.uint32)
+        L.idl_bam_reads_free(out)
+        return r
+
+    def close(self):
+        if self.h:
+            lib().idl_bam_close(self.h); self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 class Context:

@@ -175,11 +175,12 @@ def test_cli_vcf_is_byte_identical_to_the_oracle(files):
 
 
 @pytest.mark.gpu
-def test_cli_gpu_sweep_gives_the_same_vcf(files):
-    """`indelope --gpu-sweep`: the regions come from idl_sweep (gen_roi on the GPU, src/indelope.nim:515-545) instead of the host sweep; same bytes"""
+def test_cli_gpu_decode_gives_the_same_vcf(files):
+    """`indelope --gpu-decode`: BGZF inflate, record parse (idl_bam_open) and gen_roi (idl_bam_sweep, src/indelope.nim:515-545) on the GPU instead of the
+    host reader and sweep; same bytes"""
     ds, fa, bam = files
     exe = build.build_cli()
-    r = subprocess.run([exe, "--gpu-sweep", "--min-event-len", "5", "--min-reads", "5", "-t", "2", fa, bam], capture_output=True, text=True)
+    r = subprocess.run([exe, "--gpu-decode", "--min-event-len", "5", "--min-reads", "5", "-t", "2", fa, bam], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     rois = ds.sweep(min_reads=5)
     _, ovcf, cnt = orc.call(rois.arrays(), dump_level=0, **CALL)

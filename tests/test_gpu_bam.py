@@ -1,0 +1,196 @@
+"""SURVEY 8(f)3 on the GPU: idl_bam_open (BGZF inflate + CRC, record boundaries, fields), idl_bam_fetch, idl_bam_sweep against (1) a BAM
+parsed with struct + zlib alone, (2) the host reader of the stand-in (bamio.cpp) and (3) idl_sweep on the host reader's arrays."""
+import gzip
+import random
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from indelope_b200 import cuda, host
+import idl_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+COLS = ("chrom", "start", "stop", "len", "mapq", "flag", "seq_off", "cig_off", "bases", "quals", "cigar")
+
+
+def check_against_parse(raw_bam, file_bytes):
+    text, refs, want, n_unplaced = util.parse_bam(raw_bam)
+    b = cuda.Bam(file_bytes)
+    assert b.header == text and list(zip(b.ref_names, b.ref_len)) == refs
+    assert b.n_records == len(want["start"]) and b.n_unplaced == n_unplaced
+    got = b.fetch()
+    for k in COLS:
+        assert np.array_equal(got[k], want[k]), k
+    # the per-target ranges
+    for c in range(len(refs)):
+        lo, hi = b.ref_first[c], b.ref_first[c + 1]
+        assert np.all(want["chrom"][lo:hi] == c) and (lo == 0 or want["chrom"][lo - 1] < c) and (hi == len(want["chrom"]) or want["chrom"][hi] > c)
+    return b, want
+
+
+def random_records(rng, refs, n, max_len=250, long_every=0):
+    recs, keys = [], []
+    for _ in range(n):
+        c = rng.randrange(len(refs)); pos = rng.randrange(0, refs[c][1] - 1)
+        keys.append((c, pos))
+    keys.sort()
+    for k, (c, pos) in enumerate(keys):
+        l = rng.randrange(0, max_len)
+        if long_every and k % long_every == long_every - 1:
+            l = rng.randrange(70_000, 200_000)       # a record longer than a 64 KiB segment and than a BGZF member
+        seq = "".join(rng.choice("ACGTN" if rng.random() < 0.98 else util.SEQ16) for _ in range(l))
+        cig, left = [], l
+        if l and rng.random() < 0.9:
+            while left > 0:
+                op = rng.choice("MMMMIDSNX=") if cig else rng.choice("MS")
+                ln = rng.randrange(1, max(2, min(left, 120) + 1))
+                if op in "MISX=":
+                    ln = min(ln, left); left -= ln
+                cig.append((op, ln))
+        flag = rng.choice([0, 16, 99, 147, 1024, 256, 4, 2048, 512])
+        recs.append(util.bam_record(c, pos, cig, seq, qual=[rng.randrange(0, 42) for _ in range(l)], mapq=rng.randrange(0, 61), flag=flag,
+                                    name=("q%d" % k).encode() * rng.randrange(1, 4), tags=b"NMC\x03" if rng.random() < 0.5 else b""))
+    return recs
+
+
+def test_members_of_every_kind_and_records_across_boundaries():
+    rng = random.Random(11)
+    refs = [("chrA", 500_000), ("chrB", 80_000), ("chrEmpty", 1000), ("chrC", 3_000_000)]
+    recs = [r for r in random_records(rng, refs, 6000)]
+    recs += [util.bam_record(-1, -1, [], "ACGT", flag=4, name=b"unplaced%d" % k) for k in range(5)]
+    raw = util.bam_bytes(refs, recs)
+    kinds = [(6, zlib.Z_DEFAULT_STRATEGY), (0, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_FIXED), (9, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_HUFFMAN_ONLY), (4, zlib.Z_RLE)]
+    for block in (0xff00, 777, 30_000):
+        data = util.bgzf_compress(raw, levels=kinds, block=block)
+        assert gzip.decompress(data) == raw
+        b, want = check_against_parse(raw, data)
+        assert b.info["n_members"] == (len(raw) + block - 1) // block + 1 and b.info["inflated_bytes"] == len(raw)
+        b.close()
+
+
+def test_long_records_span_segments():
+    rng = random.Random(12)
+    refs = [("chr1", 5_000_000)]
+    recs = random_records(rng, refs, 300, long_every=7)
+    raw = util.bam_bytes(refs, recs)
+    assert len(raw) > 3_000_000
+    b, want = check_against_parse(raw, util.bgzf_compress(raw, level=1))
+    b.close()
+
+
+def test_bait_inside_a_record_is_not_taken_for_a_record():
+    """qualities that spell out a chain of perfectly plausible records, placed so that a 64 KiB segment starts inside them: the guess takes the bait,
+    the chain check (segment k's exit must be segment k+1's first record) re-walks the segment from the true offset -- the result stays exact"""
+    refs = [("chr1", 1_000_000)]
+    fake = b"".join(util.bam_record(0, 1000 + k, [("M", 50)], "A" * 50, name=b"fake") for k in range(40))
+    head = util.bam_bytes(refs, [])
+    recs, size, k = [], len(head), 0
+    while size < 400_000:
+        # filler up to ~2 KiB before the next segment boundary (segments are counted from the first record), then a record whose qualities hold the bait
+        seg_left = 65536 - ((size - len(head)) % 65536)
+        if seg_left > 6000:
+            r = util.bam_record(0, 10 + k, [("M", 100)], "ACGT" * 25, name=b"fill%d" % k)
+        else:
+            l = len(fake) + 3000
+            qual = bytes([20] * (seg_left + 100)) + fake
+            qual = qual + bytes([20] * (l - len(qual)))
+            r = util.bam_record(0, 10 + k, [("M", l)], "C" * l, qual=qual, name=b"bait%d" % k)
+        recs.append(r); size += len(r); k += 1
+    raw = util.bam_bytes(refs, recs)
+    b, want = check_against_parse(raw, util.bgzf_compress(raw, level=6))
+    assert b.info["boundary_fixups"] >= 3
+    b.close()
+
+
+def test_empty_and_header_only_files():
+    refs = [("chr1", 1000), ("chr2", 2000)]
+    raw = util.bam_bytes(refs, [])
+    b, want = check_against_parse(raw, util.bgzf_compress(raw))
+    assert b.n_records == 0 and b.ref_first == [0, 0, 0]
+    s = b.sweep(0)
+    assert len(s["roi_start"]) == 0
+    b.close()
+    raw = util.bam_bytes(refs, [util.bam_record(-1, -1, [], "AC", flag=4)])      # only unplaced records
+    b, want = check_against_parse(raw, util.bgzf_compress(raw))
+    assert b.n_records == 0 and b.n_unplaced == 1
+    b.close()
+    big = [("contig%d" % k, 1000 + k) for k in range(40_000)]                      # a header of more than 1 MiB
+    raw = util.bam_bytes(big, [util.bam_record(39_999, 5, [("M", 4)], "ACGT")])
+    b, want = check_against_parse(raw, util.bgzf_compress(raw, level=1))
+    assert b.ref_first[39_999] == 0 and b.ref_first[40_000] == 1
+    b.close()
+
+
+def test_bad_files_are_refused():
+    rng = random.Random(13)
+    refs = [("chr1", 100_000)]
+    recs = random_records(rng, refs, 2000)
+    raw = util.bam_bytes(refs, recs)
+    data = util.bgzf_compress(raw, level=6)
+    def refused(d, match):
+        with pytest.raises(cuda.IdlError, match=match):
+            cuda.Bam(d)
+    refused(b"not a bam at all, just text " * 4, "not a BGZF")
+    refused(data[:len(data) // 2], "truncated BGZF")
+    bad = bytearray(data); bad[5000] ^= 0x10
+    refused(bytes(bad), "failed to inflate")                                       # a flipped bit in the deflate data: decoder error or CRC mismatch
+    member = util.bgzf_member(raw[:30_000])
+    wrong_crc = member[:-8] + struct.pack("<I", zlib.crc32(raw[:30_000]) ^ 1) + member[-4:]
+    refused(wrong_crc + util.BGZF_EOF, "CRC mismatch")
+    refused(util.bgzf_compress(b"BAX\1" + raw[4:]), "not a BAM")
+    refused(util.bgzf_compress(raw[:len(raw) - 10]), "truncated BAM record")
+    refused(util.bgzf_compress(util.bam_bytes(refs, [recs[-1], recs[0]])), "not coordinate sorted")
+    refused(util.bgzf_compress(util.bam_bytes(refs, [util.bam_record(3, 5, [("M", 4)], "ACGT")])), "unknown reference id")
+    refused(util.bgzf_compress(util.bam_bytes(refs, [util.bam_record(-1, -1, [], "AC", flag=4), recs[0]])), "unplaced records are only supported as the tail")
+    broken = bytearray(util.bam_record(0, 5, [("M", 4)], "ACGT")); broken[20:24] = struct.pack("<i", 4000)   # l_seq larger than the record
+    refused(util.bgzf_compress(util.bam_bytes(refs, [bytes(broken)])), "malformed BAM record")
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("gbam")
+    ds = util.small_dataset("pr1", chrom_len=400_000, n_events=80, max_indel=40, n_chroms=3, n_base_rate=0.0005, dup_fraction=0.02)
+    fa, bam = str(d / "ref.fa"), str(d / "reads.bam")
+    ds.write_fasta(fa)
+    ds.write_bam(bam, level=6)
+    return ds, fa, bam
+
+
+def test_same_records_and_regions_as_the_host_reader(files):
+    """the stand-in's own BAM through both readers: identical records; idl_bam_sweep == idl_sweep on the host arrays == the host sweep"""
+    ds, fa, bam = files
+    data = open(bam, "rb").read()
+    b, want = check_against_parse(gzip.decompress(data), data)
+    full = host.Dataset.load(fa, bam, threads=2)
+    rois = full.sweep(min_reads=5)
+    a = rois.arrays()
+    got = b.fetch(what=cuda.BAM_SEQ)
+    for k in ("start", "stop", "len", "mapq", "flag"):
+        assert np.array_equal(got[k], a[k]), k
+    assert np.array_equal(got["bases"], a["bases"][:len(got["bases"])]) and np.array_equal(got["quals"], a["quals"][:len(got["quals"])])
+    n_regions = 0
+    for c in range(b.n_ref):
+        cr = full.chrom_reads(c)
+        assert cr["first_read"] == b.ref_first[c] and len(cr["start"]) == b.ref_first[c + 1] - b.ref_first[c]
+        s_dev = b.sweep(c, min_event_support=3, min_read_coverage=5, evidence=True)
+        s_host = cuda.sweep(cr["chrom_len"], cr["start"], cr["stop"], cr["flag"], cr["cigar"], cr["cig_off"], min_event_support=3, min_read_coverage=5, evidence=True)
+        for k in ("roi_start", "roi_end", "roi_n_reads", "roi_read_begin", "evidence"):
+            assert np.array_equal(s_dev[k], s_host[k]), k
+        assert np.array_equal(s_dev["read_idx"], s_host["read_idx"] + cr["first_read"])
+        sel = a["roi_chrom"] == c
+        assert np.array_equal(s_dev["roi_start"], a["roi_start"][sel]) and np.array_equal(s_dev["roi_end"], a["roi_stop"][sel])
+        n_regions += len(s_dev["roi_start"])
+    assert n_regions == len(a["roi_start"]) > 50
+    # a subset, in an order of the caller's choosing
+    idx = np.array([5, 0, b.n_records - 1, 17, 17], dtype=np.int64)
+    sub = b.fetch(idx)
+    allr = b.fetch()
+    for j, i in enumerate(idx):
+        assert sub["start"][j] == allr["start"][i] and sub["flag"][j] == allr["flag"][i]
+        assert np.array_equal(sub["bases"][sub["seq_off"][j]:sub["seq_off"][j + 1]], allr["bases"][allr["seq_off"][i]:allr["seq_off"][i + 1]])
+        assert np.array_equal(sub["quals"][sub["seq_off"][j]:sub["seq_off"][j + 1]], allr["quals"][allr["seq_off"][i]:allr["seq_off"][i + 1]])
+        assert np.array_equal(sub["cigar"][int(sub["cig_off"][j]):int(sub["cig_off"][j + 1])], allr["cigar"][int(allr["cig_off"][i]):int(allr["cig_off"][i + 1])])
+    b.close()

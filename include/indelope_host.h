@@ -65,6 +65,9 @@ typedef struct idlh_synth_params {
 	int32_t min_cigar_flank;    /* aligner model: shorter flanks are soft-clipped [20] */
 	int32_t chrom_first;        /* generate chromosomes chrom_first .. chrom_first + n_chroms - 1 of the genome this seed defines (every
 	                               chromosome has its own random stream, so a rank can build just its interval shard) [0] */
+	int32_t qual_levels;        /* 0/1: every untrimmed base has quality 30; k > 1: k distinct qualities in 15 .. 41 drawn per base from a hash of
+	                               (read, position) -- all at or above the trim threshold, so reads, regions and calls stay the same while the BAM
+	                               compresses like sequencer output instead of 12:1 [0] */
 } idlh_synth_params;
 
 void idlh_default_synth(idlh_synth_params *p);

@@ -22,6 +22,7 @@
 //   5. a 64-bit exclusive scan of n_cigar + a gather make the contiguous CIGAR array idl_sweep's kernels take; per-target record ranges
 //      by binary search.
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -37,8 +38,14 @@ namespace {
 
 using namespace idl_inflate;
 
-constexpr int INF_WARPS = 8;                 // warps per CTA of the inflate kernel: 8 x 3.6 KB of tables
-constexpr int INF_CTAS_PER_SM = 4;
+#ifndef INF_WARPS_
+#define INF_WARPS_ 6
+#endif
+#ifndef INF_CTAS_PER_SM_
+#define INF_CTAS_PER_SM_ 5
+#endif
+constexpr int INF_WARPS = INF_WARPS_;        // warps per CTA of the inflate kernel: 6 x 6.1 KB of tables
+constexpr int INF_CTAS_PER_SM = INF_CTAS_PER_SM_;
 constexpr unsigned SEG_BYTES = 1u << 16;     // segment of the inflated stream one warp chains
 constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
@@ -348,6 +355,7 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 {
 	if (!out || (!file && file_len)) return IDL_E_ARG;
 	*out = nullptr;
+	const double t_enter = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_err(err, errlen, "no CUDA device (idl_bam_open has no CPU path)"); return IDL_E_NO_DEVICE; }
 	if (device < 0 || device >= ndev) return IDL_E_ARG;
@@ -376,7 +384,13 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 	}
 	if (members.empty() || total < 12) { set_err(err, errlen, "not a BAM file"); return IDL_E_FORMAT; }
 	if (members.size() >= (1ull << 32)) return IDL_E_CAPACITY;
+	// IDL_BAM_TIMING=1: wall-clock phases of the call on stderr (context creation and allocations are not inside the CUDA events)
+	const bool timing = getenv("IDL_BAM_TIMING") != nullptr;
+	auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double tw[8] = {now(), 0, 0, 0, 0, 0, 0, 0};
 	if (cudaSetDevice(device) != cudaSuccess) return IDL_E_CUDA;
+	cudaFree(nullptr);
+	tw[1] = now();
 	idl_bam *b = new idl_bam();
 	b->device = device; b->total = total;
 	int rc = IDL_OK;
@@ -392,11 +406,12 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 		cudaStream_t st = b->st;
 		for (auto &e : ev) BCK(cudaEventCreate(&e));
 		Member *d_members = nullptr; unsigned long long *d_err = nullptr; unsigned *d_next = nullptr;
-		BALLOC(b->d_comp, file_len + 64); BALLOC(b->d_out, total + 64); BALLOC(d_members, members.size() * sizeof(Member)); BALLOC(d_err, 64); BALLOC(d_next, 16);
+		BALLOC(b->d_comp, file_len + 512); BALLOC(b->d_out, total + 64); BALLOC(d_members, members.size() * sizeof(Member)); BALLOC(d_err, 64); BALLOC(d_next, 16);
 		// 2. H2D + inflate
+		tw[2] = now();
 		BCK(cudaEventRecord(ev[0], st));
 		BCK(cudaMemcpyAsync(b->d_comp, file, file_len, cudaMemcpyHostToDevice, st));
-		BCK(cudaMemsetAsync(b->d_comp + file_len, 0, 64, st));
+		BCK(cudaMemsetAsync(b->d_comp + file_len, 0, 512, st));
 		BCK(cudaMemcpyAsync(d_members, members.data(), members.size() * sizeof(Member), cudaMemcpyHostToDevice, st));
 		BCK(cudaMemsetAsync(d_err, 0xff, 64, st)); BCK(cudaMemsetAsync(d_next, 0, 16, st)); BCK(cudaMemsetAsync(b->d_out + total, 0, 64, st));
 		BCK(cudaEventRecord(ev[1], st));
@@ -412,6 +427,7 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 		std::vector<uint8_t> head(std::min<size_t>(total, 1u << 20));
 		BCK(cudaMemcpyAsync(head.data(), b->d_out, head.size(), cudaMemcpyDeviceToHost, st));
 		BCK(cudaStreamSynchronize(st));
+		tw[3] = now();
 		if (herr[0] != ~0ULL) {
 			char msg[160];
 			snprintf(msg, sizeof msg, "BGZF block %llu failed to inflate (corrupt data or CRC mismatch: %s)", herr[0] >> 8, inf_error_text((int)(herr[0] & 0xff)));
@@ -491,6 +507,7 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 			}
 			if (expect != total) BFAIL("truncated BAM record");
 		}
+		tw[4] = now();
 		if (n_all >= (1ull << 31)) { rc = IDL_E_CAPACITY; why = "more than 2^31 records"; goto done; }
 		b->n_all = n_all;
 		// 4. offsets and fields
@@ -545,6 +562,10 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 		for (auto &s : b->names) b->name_ptrs.push_back(s.c_str());
 		b->info.ref_name = b->name_ptrs.data(); b->info.ref_len = b->ref_len.data(); b->info.ref_first = b->ref_first.data();
 		b->info.header_text = b->header.c_str(); b->info.header_len = b->header.size();
+		tw[5] = now();
+		if (timing)
+			fprintf(stderr, "idl_bam_open: member index %.1f ms, context %.1f ms, stream + allocations %.1f ms, h2d + inflate + header %.1f ms, boundaries %.1f ms, fields + cigars %.1f ms\n",
+			        (tw[0] - t_enter) * 1e3, (tw[1] - tw[0]) * 1e3, (tw[2] - tw[1]) * 1e3, (tw[3] - tw[2]) * 1e3, (tw[4] - tw[3]) * 1e3, (tw[5] - tw[4]) * 1e3);
 	}
 done:
 	for (auto &e : ev) if (e) cudaEventDestroy(e);

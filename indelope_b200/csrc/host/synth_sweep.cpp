@@ -69,6 +69,13 @@ void emit_read(idlh_dataset &D, Rng &rng, int chrom, const std::string &seq0, in
 	D.bases.insert(D.bases.end(), seq.begin(), seq.end());
 	size_t q0 = D.quals.size();
 	D.quals.resize(q0 + seq.size(), 30);
+	if (P.qual_levels > 1) {   // per-base qualities from a hash: the main random stream (and with it every read) is unchanged
+		uint64_t h = (uint64_t)D.reads.size() * 0x9E3779B97F4A7C15ULL + P.seed;
+		for (size_t i = 0; i < seq.size(); ++i) {
+			h ^= h >> 27; h *= 0x3C79AC492BA7B653ULL; h ^= h >> 33; h += 0x1C69B3F74AC4AE35ULL;
+			D.quals[q0 + i] = (uint8_t)(15 + (h >> 40) % (uint64_t)P.qual_levels * 26 / (uint64_t)(P.qual_levels - 1));
+		}
+	}
 	if (rng.uni() < P.lowq_tail_fraction) {
 		int n = (int)rng.range(1, 15);
 		if (n > (int)seq.size()) n = (int)seq.size();

@@ -36,7 +36,7 @@ class SynthParams(C.Structure):
         ("max_indel", C.c_int32), ("coverage", C.c_double), ("read_len", C.c_int32), ("sub_rate", C.c_double), ("tr_fraction", C.c_double),
         ("tr_max_unit", C.c_int32), ("het_fraction", C.c_double), ("lowq_tail_fraction", C.c_double), ("low_mapq_fraction", C.c_double),
         ("dup_fraction", C.c_double), ("n_base_rate", C.c_double), ("locus_only", C.c_int32), ("locus_flank", C.c_int32),
-        ("max_cigar_indel", C.c_int32), ("min_cigar_flank", C.c_int32), ("chrom_first", C.c_int32),
+        ("max_cigar_indel", C.c_int32), ("min_cigar_flank", C.c_int32), ("chrom_first", C.c_int32), ("qual_levels", C.c_int32),
     ]
 
 

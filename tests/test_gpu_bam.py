@@ -94,9 +94,8 @@ def test_bait_inside_a_record_is_not_taken_for_a_record():
         if seg_left > 6000:
             r = util.bam_record(0, 10 + k, [("M", 100)], "ACGT" * 25, name=b"fill%d" % k)
         else:
-            l = len(fake) + 3000
-            qual = bytes([20] * (seg_left + 100)) + fake
-            qual = qual + bytes([20] * (l - len(qual)))
+            qual = bytes([20] * (seg_left + 100)) + fake + bytes([20] * 500)
+            l = len(qual)
             r = util.bam_record(0, 10 + k, [("M", l)], "C" * l, qual=qual, name=b"bait%d" % k)
         recs.append(r); size += len(r); k += 1
     raw = util.bam_bytes(refs, recs)

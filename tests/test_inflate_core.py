@@ -14,13 +14,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-@pytest.fixture(scope="module")
-def L():
+@pytest.fixture(scope="module", params=[0, 2048], ids=["no-ring", "ring2048"])
+def L(request):
+    """both build variants of the decoder: matches read back from the output, or from a ring of the last 2 KiB where they reach no further"""
+    ring = request.param
     src = os.path.join(HERE, "native", "inflate_host.cpp")
-    so = os.path.join(HERE, "native", "libinflate_host.so")
+    so = os.path.join(HERE, "native", "libinflate_host_r%d.so" % ring)
     core = os.path.join(ROOT, "indelope_b200", "csrc", "inflate_core.cuh")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-x", "c++", "-I", os.path.join(ROOT, "indelope_b200", "csrc"), src, "-o", so])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-x", "c++", "-DIDL_INF_RING=%d" % ring, "-I", os.path.join(ROOT, "indelope_b200", "csrc"), src, "-o", so])
     lib = C.CDLL(so)
     lib.idl_test_inflate.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_uint32]
     lib.idl_test_inflate_at.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_char_p, C.c_uint32]
@@ -41,6 +43,10 @@ def _payloads():
     yield bytes((i * 7) & 255 for i in range(65280))
     yield (r.integers(0, 4, 65000) + r.integers(0, 2, 65000) * 40).astype(np.uint8).tobytes()
     yield (r.integers(0, 256, 30000) % r.integers(1, 200, 30000)).astype(np.uint8).tobytes() + b"x" * 300 + bytes(range(256)) * 20
+    # repeats at distances around and beyond the decoder's ring of recent output (2048 bytes): matches served from the ring and from global memory
+    for period in (1700, 1789, 1790, 1791, 2047, 2048, 2049, 2300, 3000, 20000):
+        blk = bytes(rng.getrandbits(8) for _ in range(period))
+        yield (blk * (65000 // period + 1))[:65000]
 
 
 def raw_deflate(d, level, strategy):

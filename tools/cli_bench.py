@@ -1,5 +1,5 @@
 """End-to-end timing of the `indelope` command line on real files (BAM -> VCF), next to its host-only share.
-  python tools/cli_bench.py [chrom_len_mb] [threads]
+  python tools/cli_bench.py [chrom_len_mb] [threads] [qual_levels]      (qual_levels 8 or 40: per-base qualities, a BAM that compresses ~4:1 / ~3:1)
 Writes a whole-contig 30x dataset (BASELINE config 1 scaled up: 200 planted indels per Mb) as .fa/.bam under a temp
 directory, then times (1) the streaming sweep alone (BGZF inflate + BAM parse + gen_roi, no GPU), (2) the binary end to
 end, and checks the binary's VCF against the CPU oracle run over the same regions (timed as the CPU baseline).
@@ -18,12 +18,13 @@ from indelope_b200 import build, host
 def main():
     mb = float(sys.argv[1]) if len(sys.argv) > 1 else 20.0
     threads = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-    cfg = dict(host.CONFIGS["pr1"]); cfg.update(chrom_len=int(mb * 1e6), n_events=int(200 * mb))
+    levels = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 0
+    cfg = dict(host.CONFIGS["pr1"]); cfg.update(chrom_len=int(mb * 1e6), n_events=int(200 * mb), qual_levels=levels)
     t0 = time.time(); ds = host.Dataset(**cfg); t_gen = time.time() - t0
     d = tempfile.mkdtemp(prefix="idl_cli_")
     fa, bam = os.path.join(d, "ref.fa"), os.path.join(d, "reads.bam")
     t0 = time.time(); ds.write_fasta(fa); ds.write_bam(bam, level=1); t_write = time.time() - t0
-    out = {"chrom_len": cfg["chrom_len"], "reads": ds.n_reads, "bam_bytes": os.path.getsize(bam), "threads": threads, "gen_s": round(t_gen, 2), "write_s": round(t_write, 2)}
+    out = {"chrom_len": cfg["chrom_len"], "qual_levels": levels, "reads": ds.n_reads, "bam_bytes": os.path.getsize(bam), "threads": threads, "gen_s": round(t_gen, 2), "write_s": round(t_write, 2)}
     t0 = time.time()
     st = host.Stream(fa, bam, threads=threads, min_reads=5)
     groups = list(st.groups())
@@ -52,6 +53,34 @@ def main():
             _, ovcf, cnt = orc.call(whole.arrays(), min_reads=5, min_ctg_len=73, min_event_len=5, dump_level=0, n_threads=os.cpu_count() or 1)
             out["oracle_s_all_threads"] = round(time.time() - t0, 3); out["oracle_threads"] = os.cpu_count()
             out["vcf_identical_to_oracle"] = (r.stdout == whole.header() + ovcf)
+            # the same command with the front end on the GPU (idl_bam_open / idl_bam_sweep / idl_bam_fetch)
+            best = None
+            for _ in range(3):
+                t0 = time.time()
+                r2 = subprocess.run([exe, "--gpu-decode", "--min-event-len", "5", "--min-reads", "5", fa, bam], capture_output=True, text=True,
+                                    env=dict(os.environ, INDELOPE_TIMING="1", IDL_BAM_TIMING="1"))
+                dt = time.time() - t0
+                if r2.returncode != 0:
+                    out["gpu_decode_error"] = r2.stderr[-300:]; break
+                if best is None or dt < best:
+                    best = dt; out["gpu_decode_phases"] = r2.stderr.strip().split("\n")[-2:]
+            if best is not None:
+                out["gpu_decode_cli_s"] = round(best, 3); out["gpu_decode_vcf_identical_to_oracle"] = (r2.stdout == whole.header() + ovcf)
+            # the decoders alone, in process: host reader (inflate + parse on `threads` host threads) against idl_bam_open
+            from indelope_b200 import cuda
+            data = open(bam, "rb").read()
+            t0 = time.time(); full = host.Dataset.load(fa, bam, threads=threads); out["host_load_s"] = round(time.time() - t0, 3)
+            del full
+            cuda.Bam(data).close()  # context + first-touch
+            best = None
+            for _ in range(3):
+                t0 = time.time(); b = cuda.Bam(data); dt = time.time() - t0
+                if best is None or dt < best:
+                    best = dt; out["idl_bam_open"] = dict(b.info, wall_s=round(dt, 4), n_records=b.n_records)
+                b.close()
+            i = out["idl_bam_open"]
+            out["inflate_gbs_out"] = round(i["inflated_bytes"] / (i["ms_inflate"] / 1e3) / 1e9, 2)
+            out["idl_bam_open_gbs_out"] = round(i["inflated_bytes"] / i["wall_s"] / 1e9, 2)
     print(json.dumps(out))
     for f in (fa, fa + ".fai", bam, bam + ".bai"):
         if os.path.exists(f):

@@ -108,6 +108,30 @@ type
     algorithmic_bytes*, streamed_bytes*: uint64
 
   IdlCtx* = pointer
+  IdlBam* = pointer                        ## a BAM decoded into device memory (idl_bam_open)
+
+  IdlBamInfo* {.bycopy.} = object          ## idl_bam_info
+    file_bytes*, inflated_bytes*: uint64
+    n_members*, boundary_fixups*: uint32
+    n_ref*: int32
+    ref_name*: cstringArray
+    ref_len*: ptr UncheckedArray[int64]
+    header_text*: cstring
+    header_len*: csize_t
+    n_records*, n_unplaced*: int64
+    ref_first*: ptr UncheckedArray[int64]  ## n_ref + 1: records of target c are [ref_first[c], ref_first[c + 1])
+    ms_h2d*, ms_inflate*, ms_parse*: cfloat
+
+  IdlBamReads* {.bycopy.} = object         ## idl_bam_reads: what callsemble reads of a cached Record (src/indelope.nim:216-222)
+    n*: csize_t
+    chrom*, start*, stop*, len*: ptr UncheckedArray[int32]
+    mapq*: ptr UncheckedArray[uint8]
+    flag*: ptr UncheckedArray[uint16]
+    seq_off*: ptr UncheckedArray[int64]
+    bases*, quals*: ptr UncheckedArray[uint8]
+    cig_off*: ptr UncheckedArray[uint64]
+    cigar*: ptr UncheckedArray[uint32]
+    ms_kernels*, ms_d2h*: cfloat
 
 const
   IDL_ABI_VERSION* = 2'i32
@@ -115,6 +139,9 @@ const
   IDL_E_NO_DEVICE* = -1
   IDL_E_CAPACITY* = -5
   IDL_E_BUSY* = -7
+  IDL_E_FORMAT* = -8
+  IDL_BAM_SEQ* = 1'u32
+  IDL_BAM_CIGAR* = 2'u32
   IDL_RS_FATAL* = 1'u32 or 2'u32 or 16'u32 or 64'u32
   IDL_RS_ALPHABET* = 32'u32
   IDL_EV_COUNTED* = 0'i32
@@ -136,6 +163,14 @@ proc idl_device_count*(): cint {.importc.}
 proc idl_sweep*(device: cint, inp: ptr IdlSweepIn, min_event_support, min_read_coverage, max_read_coverage: int32, flags: uint32,
                 outp: ptr ptr IdlSweepOut): cint {.importc.}
 proc idl_sweep_free*(o: ptr IdlSweepOut) {.importc.}
+# the BAM on the device: replaces hts-nim's open / querys / Record accessors for the sweep (src/indelope.nim:595, :527, :40-47, :430-452)
+proc idl_bam_open*(device: cint, file: ptr uint8, file_len: csize_t, bam: ptr IdlBam, err: cstring, errlen: csize_t): cint {.importc.}
+proc idl_bam_get_info*(bam: IdlBam): ptr IdlBamInfo {.importc.}
+proc idl_bam_close*(bam: IdlBam) {.importc.}
+proc idl_bam_sweep*(bam: IdlBam, target: int32, min_event_support, min_read_coverage, max_read_coverage: int32, flags: uint32,
+                    outp: ptr ptr IdlSweepOut): cint {.importc.}
+proc idl_bam_fetch*(bam: IdlBam, n: csize_t, idx: ptr int64, what: uint32, outp: ptr ptr IdlBamReads): cint {.importc.}
+proc idl_bam_reads_free*(r: ptr IdlBamReads) {.importc.}
 {.pop.}
 
 when isMainModule:

@@ -21,6 +21,8 @@ import sys
 import threading
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -39,6 +41,7 @@ def parse():
     ap.add_argument("--mode", default="auto", choices=["auto", "weak", "strong"], help="auto: strong for --workload wgs, weak otherwise")
     ap.add_argument("--scale", type=float, default=1.0, help="scale the number of planted events (tests)")
     ap.add_argument("--cpu-sample", type=int, default=40000, help="regions timed by the cpu_baseline leg (about 15 s of one core)")
+    ap.add_argument("--no-bam-leg", action="store_true", help="skip the leg that starts from a BAM resident on the device (idl_bam_open + idl_bam_submit; N=1 only: it writes the workload as a BAM first)")
     ap.add_argument("--e2e-batches", type=int, default=2, help="batches per step in the end-to-end leg (measured: 2 -> 41.6 ms per step, 3 -> 42.7, 4 -> 42.7: smaller batches leave the persistent kernels too few tasks per warp)")
     ap.add_argument("--verify", type=int, default=1, help="strong mode: compare the merged VCF with the oracle's once after timing")
     return ap.parse_args()
@@ -312,6 +315,62 @@ def main():
             rois.pack(lo, hi, P, b)
         extra["pack_ms"] = (time.perf_counter() - tp0) * 1000.0
         merged = None
+        # ---- leg 4 (N=1): the same regions from a BAM RESIDENT ON THE DEVICE: the workload written as a BAM file, decoded by idl_bam_open (inflate, record
+        # chaining, fields), every batch BUILT ON THE DEVICE by idl_bam_submit (quality trim, windows, records, 2-bit pools from the BAM's nibbles) and run;
+        # per step only the regions' coordinates and record indices go up, the results come down.  Compare with e2e_packed, where the host packs.
+        if world == 1 and not args.no_bam_leg:
+            import shutil
+            import tempfile
+            tmpd = tempfile.mkdtemp(prefix="idl_bench_")
+            try:
+                bam_path = os.path.join(tmpd, "w.bam")
+                tw = time.perf_counter(); ds.write_bam(bam_path, level=1); write_s = time.perf_counter() - tw
+                data = open(bam_path, "rb").read()
+            finally:
+                shutil.rmtree(tmpd, ignore_errors=True)
+            cuda.Bam(data, device=local).close()   # first use: module load, allocator warm-up
+            to = time.perf_counter(); bamdev = cuda.Bam(data, device=local); open_s = time.perf_counter() - to
+            arr = rois.arrays()
+            for c in range(bamdev.n_ref):
+                bamdev.set_reference(c, arr["chrom_seqs"][c])
+            rbeg = np.concatenate([arr["roi_read_begin"], [len(arr["read_idx"])]]).astype(np.int64)
+            bam_slices = [(np.ascontiguousarray(arr["roi_chrom"][lo:hi]), np.ascontiguousarray(arr["roi_start"][lo:hi]), np.ascontiguousarray(arr["roi_stop"][lo:hi]),
+                           np.ascontiguousarray(arr["roi_n_reads"][lo:hi]), np.ascontiguousarray(arr["read_idx"][rbeg[lo]:rbeg[hi]]), lo) for lo, hi in spans]
+
+            def bam_steps(k):
+                inflight, nl, kern, sig = [], 0, 0.0, []
+
+                def retire():
+                    nonlocal nl, kern
+                    t = inflight.pop(0); r = ctx.wait(t).contents; nl += r.kernel_launches + 9
+                    kern += sum(getattr(r, s) for s in STAGES); sig.append((r.n_regions, r.n_contigs, r.n_alns, r.n_events, r.n_cigar_ops)); ctx.release(t)
+                for _ in range(k):
+                    for ch, st_, en, nr_, idx, lo in bam_slices:
+                        if len(inflight) >= P.n_streams:
+                            retire()
+                        inflight.append(ctx.bam_submit(bamdev, ch, st_, en, nr_, idx, ordinal_base=lo))
+                while inflight:
+                    retire()
+                return nl, kern, sig
+            _, _, sig_bam = bam_steps(max(1, args.warmup))
+            # the same work as the host-packed batches: result counts of every batch agree
+            ref_sig = []
+            for (b, _), _ in zip(slices, spans):
+                t = ctx.submit(b); r = ctx.wait(t).contents; ref_sig.append((r.n_regions, r.n_contigs, r.n_alns, r.n_events, r.n_cigar_ops)); ctx.release(t)
+            bam_ok = sig_bam[:len(ref_sig)] == ref_sig
+            kb = max(1, args.steps // 2)
+            barrier()
+            t0 = time.perf_counter()
+            nl, bam_kern, _ = bam_steps(kb)
+            barrier()
+            bam_s = time.perf_counter() - t0
+            launches += nl
+            extra["e2e_bam"] = {"value": n_regions * kb / bam_s, "unit": "regions/s", "steps": kb, "ms_per_step": bam_s * 1000.0 / kb, "kernel_ms_per_step": bam_kern / kb,
+                                "h2d_bytes_per_step": int(n_regions * 16 + len(arr["read_idx"]) * 8), "same_result_counts_as_host_packed_batches": bool(bam_ok),
+                                "bam": {"file_bytes": len(data), "write_s": write_s, "idl_bam_open_wall_s": open_s, **bamdev.info, "records": bamdev.n_records},
+                                "what": "regions from a BAM resident on the device: idl_bam_open once (outside the timed region), then per step every batch is built on the device "
+                                        "by idl_bam_submit (quality trim, windows, records, 2-bit pools from the BAM's nibbles) and run; results copied back as in e2e"}
+            bamdev.close()
     else:
         # ---- strong scaling: this rank's block of contigs in pinned batches; per step every batch goes through submit / wait / the host
         # cascade (filters, genotype likelihoods, VCF text), then the shards' records are gathered on rank 0 and deduped
@@ -490,6 +549,8 @@ def main():
             "clocks": clocks,
         }
         if mode == "weak":
+            if "e2e_bam" in extra:
+                line["e2e_bam"] = extra["e2e_bam"]
             line["e2e_packed"] = {"value": regions_all * K / (pk_ms_max / 1000.0), "unit": "regions/s", "ms_per_step": pk_ms_max / K, "pack_ms_per_step_alone": extra["pack_ms"],
                                   "pack_threads": min(32, os.cpu_count() or 1),
                                   "what": "as e2e, plus idlh_pack of every batch from the ASCII reads on the host cores inside the timed region (quality trim, 2-bit packing, read and region records)"}

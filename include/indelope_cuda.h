@@ -351,6 +351,22 @@ typedef struct idl_bam_reads {
 int idl_bam_fetch(idl_bam *bam, size_t n, const int64_t *idx, uint32_t what, idl_bam_reads **out);
 void idl_bam_reads_free(idl_bam_reads *r);
 
+/* The batch built ON THE DEVICE: regions (as idl_bam_sweep returned them: target, bounds, records) -> the quality trim of their records
+ * (src/indelope.nim:23-38), the reference windows (:213-220), read and region records and the 2-bit + N-plane pools, written straight into
+ * a lane's device buffers from the resident BAM (bases are still BAM nibbles there) and the resident reference -- no record, base or
+ * quality crosses the bus.  Byte for byte the batch idlh_pack builds on the host from idl_bam_fetch's arrays.
+ *   idl_bam_set_reference: the sequence of one target (ASCII, as in the FASTA; length must equal the header's) -- once per target.
+ *   idl_bam_submit:        build + run the calling chain; wait / release with idl_wait / idl_release as after idl_submit.
+ *                          roi_n_reads[k] records per region, concatenated in read_idx[] (indices into the BAM's records);
+ *                          ordinal_base + k becomes idl_region.ordinal.  IDL_E_ARG for an index outside the BAM or a target without reference.
+ *   idl_bam_pack:          build only and copy the batch into <out> (from idl_batch_alloc, large enough: IDL_E_CAPACITY otherwise) -- for
+ *                          tests and for callers that want to keep the batch. */
+int idl_bam_set_reference(idl_bam *bam, int32_t target, const uint8_t *seq, int64_t len);
+int idl_bam_submit(idl_ctx *ctx, idl_bam *bam, size_t n_regions, const int32_t *roi_chrom, const int32_t *roi_start, const int32_t *roi_end,
+                   const int32_t *roi_n_reads, const int64_t *read_idx, uint32_t ordinal_base, uint64_t *ticket);
+int idl_bam_pack(idl_ctx *ctx, idl_bam *bam, size_t n_regions, const int32_t *roi_chrom, const int32_t *roi_start, const int32_t *roi_end,
+                 const int32_t *roi_n_reads, const int64_t *read_idx, uint32_t ordinal_base, idl_batch *out);
+
 #ifdef __cplusplus
 }
 #endif

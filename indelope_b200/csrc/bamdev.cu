@@ -32,6 +32,7 @@
 #include <cuda_runtime.h>
 #include "indelope_cuda.h"
 #include "sweep_impl.h"
+#include "bamdev.h"
 #include "inflate_core.cuh"
 
 namespace {
@@ -301,6 +302,172 @@ __global__ void __launch_bounds__(256) bam_fetch_cigar_kernel(const long long *i
 	for (unsigned long long k = s; k < e; ++k) dst[d + (k - s)] = src[k];
 }
 
+// ---- the batch builder (idl_bam_submit / idl_bam_pack): what idlh_pack does on the host (pack_vcf.cpp), from the resident records ----
+struct BuildCounters { unsigned max_trim_len, max_ref_len, max_region_reads, n_small_regions, bad_index, pad[3]; };
+
+// quality trim, src/indelope.nim:23-38 (the restatement of idlh_trim): first and last base with quality >= 15
+__device__ __forceinline__ int bam_trim(const uint8_t *bq, int n, int *trim_len)
+{
+	const int high = n - 1, min_quality = 15;
+	int a = 0;
+	while (a < high && bq[a] < min_quality) a += 1;
+	if (a == high || n <= 0) { *trim_len = 0; return n <= 0 ? 0 : a; }
+	int b = high;
+	while (b > a && bq[b] < min_quality) b -= 1;
+	*trim_len = b - a + 1;
+	return a;
+}
+// one warp per region: read records (all but seq_off), the window, the region record (all but ref_off), padded lengths for the two scans
+__global__ void __launch_bounds__(256) bam_build_records_kernel(const uint8_t *u, Rec R, size_t n_records, const int32_t *ref_len, const uint8_t *const *ref_seq, int32_t n_ref,
+                                                                idl_params P, size_t n_regions, const int32_t *roi_chrom, const int32_t *roi_start, const int32_t *roi_end,
+                                                                const int32_t *roi_n_reads, const unsigned long long *roi_read_begin, const long long *read_idx,
+                                                                uint32_t ordinal_base, idl_region *region, idl_read *read, uint32_t *read_pad, uint32_t *slot_region,
+                                                                uint32_t *ref_pad, BuildCounters *cnt)
+{
+	const size_t k = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (k >= n_regions) return;
+	const unsigned long long begin = roi_read_begin[k];
+	const int nr = roi_n_reads[k];
+	long long ws = LLONG_MAX, far = -1, max_stop = -1;
+	unsigned flags = 0, max_trim = 1, bad = 0;
+	for (int j = lane; j < nr; j += 32) {
+		const long long i = read_idx[begin + j];
+		idl_read r; memset(&r, 0, sizeof r);
+		unsigned pad = 0;
+		if (i < 0 || (size_t)i >= n_records) bad = 1;
+		else {
+			const int len = R.l_seq[i];
+			const uint8_t *q = u + R.seq_at[i] + (len + 1) / 2;
+			int tl; const int ta = bam_trim(q, len, &tl);
+			const int start = R.pos[i], stop = R.stop[i]; const unsigned mapq = R.mapq[i], f = R.flag[i];
+			r.start = start; r.stop = stop; r.mapq = (uint8_t)mapq;
+			r.flags = ((f & 0x400) || (f & 0x200) || (f & 0x4) || (f & 0x800) || (f & 0x100)) ? 1 : 0;   // :40-47
+			if (len > P.max_read_len || len > 65535) flags |= IDL_RF_READ_TOO_LONG;                      // packed empty: the device drops the region and says so
+			else {
+				r.len = (uint16_t)len; r.trim_a = (uint16_t)ta; r.trim_len = (uint16_t)tl;
+				r.min_overlap = (uint16_t)(long long)(0.88 * (double)tl);                                // :169
+				pad = ((unsigned)len + 63u) & ~63u;
+				max_trim = max(max_trim, (unsigned)tl);
+			}
+			ws = min(ws, (long long)start + ta); far = max(far, (long long)start + ta + tl);
+			if ((int)mapq > P.stop_min_mapq) max_stop = max(max_stop, (long long)stop);
+		}
+		read[begin + j] = r; read_pad[begin + j] = pad; slot_region[begin + j] = (uint32_t)k;
+	}
+#pragma unroll
+	for (int d = 16; d >= 1; d >>= 1) {
+		ws = min(ws, __shfl_xor_sync(0xffffffffu, ws, d)); far = max(far, __shfl_xor_sync(0xffffffffu, far, d)); max_stop = max(max_stop, __shfl_xor_sync(0xffffffffu, max_stop, d));
+		flags |= __shfl_xor_sync(0xffffffffu, flags, d); max_trim = max(max_trim, __shfl_xor_sync(0xffffffffu, max_trim, d)); bad |= __shfl_xor_sync(0xffffffffu, bad, d);
+	}
+	if (lane == 0) {
+		const int c = roi_chrom[k];
+		if (c < 0 || c >= n_ref || !ref_seq[c]) bad = 1;
+		if (ws == LLONG_MAX) ws = 0;
+		if (ws < 0) ws = 0;
+		const long long clen = bad ? 1 : ref_len[c];
+		const long long we = min(clen - 1, max(far, max_stop) + P.window_pad);
+		idl_region g; memset(&g, 0, sizeof g);
+		g.chrom_id = c; g.roi_start = roi_start[k]; g.roi_end = roi_end[k];
+		g.read_begin = (uint32_t)begin; g.n_reads = (uint32_t)nr;
+		g.ref_start = (int32_t)ws; g.ref_len = (uint32_t)max(0ll, we - ws + 1);
+		g.max_stop = (int32_t)max_stop; g.ordinal = ordinal_base + (uint32_t)k; g.flags = flags;
+		region[k] = g;
+		ref_pad[k] = (g.ref_len + 63u) & ~63u;
+		atomicMax(&cnt->max_trim_len, max_trim); atomicMax(&cnt->max_ref_len, g.ref_len); atomicMax(&cnt->max_region_reads, (unsigned)nr);
+		if (nr <= 126) atomicAdd(&cnt->n_small_regions, 1u);
+		if (bad) atomicOr(&cnt->bad_index, 1u);
+	}
+}
+__global__ void __launch_bounds__(256) bam_build_offsets_kernel(size_t n_reads, size_t n_regions, const unsigned long long *seq_off, const unsigned long long *ref_off, idl_read *read,
+                                                                idl_region *region)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_reads) read[i].seq_off = (uint32_t)seq_off[i];
+	if (i < n_regions) region[i].ref_off = (uint32_t)ref_off[i];
+}
+// one warp per read: BAM nibbles -> 2-bit codes + N plane, 16 bases per lane and step; the record is padded to a multiple of 64 bases with zero
+// words and every word of it is stored.  Nibbles: 1 A, 2 C, 4 G, 8 T, 15 N; the other codes of "=ACMGRSVTWYHKDBN" fold to N and are reported
+// (IDL_RF_ALPHABET), as the host packer does with their letters
+__global__ void __launch_bounds__(256) bam_pack_reads_kernel(const uint8_t *u, Rec R, const long long *read_idx, size_t n_reads, const idl_read *read, const uint32_t *slot_region,
+                                                             idl_region *region, uint32_t *seq2, uint32_t *seqn)
+{
+	const size_t s = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (s >= n_reads) return;
+	const idl_read r = read[s];
+	if (r.len == 0) return;
+	const uint8_t *seq = u + R.seq_at[read_idx[s]];
+	const unsigned len = r.len, words = ((len + 63u) & ~63u) >> 4;
+	uint32_t *d2 = seq2 + (r.seq_off >> 4); uint16_t *dn = (uint16_t*)seqn + (r.seq_off >> 4);
+	unsigned folded = 0;
+	for (unsigned w = (unsigned)lane; w < words; w += 32) {
+		uint32_t a = 0, nb = 0;
+		const unsigned b0 = 16u * w;
+		if (b0 < len) {
+			// 16 bases = 8 bytes, two nibbles each, the first base in the high nibble
+#pragma unroll
+			for (int t = 0; t < 8; ++t) {
+				const unsigned base = b0 + 2u * (unsigned)t;
+				if (base >= len) break;
+				const unsigned by = seq[base >> 1];
+#pragma unroll
+				for (int h = 0; h < 2; ++h) {
+					if (base + (unsigned)h >= len) break;
+					const unsigned nib = h ? (by & 15u) : (by >> 4);
+					const int i = 2 * t + h;
+					if (nib == 1u) { }
+					else if (nib == 2u) a |= 1u << (2 * i);
+					else if (nib == 4u) a |= 2u << (2 * i);
+					else if (nib == 8u) a |= 3u << (2 * i);
+					else { nb |= 1u << i; folded |= nib != 15u; }
+				}
+			}
+		}
+		d2[w] = a; dn[w] = (uint16_t)nb;
+	}
+	folded = __any_sync(0xffffffffu, folded != 0);
+	if (folded && lane == 0) atomicOr(&region[slot_region[s]].flags, (unsigned)IDL_RF_ALPHABET);
+}
+// one warp per region: the reference window, ASCII -> 2-bit codes + N plane; lower-case acgt fold to upper case, every other byte to N, both
+// reported (IDL_RF_ALPHABET): the reference compares raw characters (src/contig.nim:93,122)
+__global__ void __launch_bounds__(256) bam_pack_ref_kernel(const uint8_t *const *ref_seq, size_t n_regions, idl_region *region, uint32_t *ref2, uint32_t *refn)
+{
+	const size_t k = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (k >= n_regions) return;
+	const idl_region g = region[k];
+	const uint8_t *s = ref_seq[g.chrom_id] + g.ref_start;
+	const unsigned len = g.ref_len, words = ((len + 63u) & ~63u) >> 4;
+	uint32_t *d2 = ref2 + (g.ref_off >> 4); uint16_t *dn = (uint16_t*)refn + (g.ref_off >> 4);
+	unsigned folded = 0;
+	for (unsigned w = (unsigned)lane; w < words; w += 32) {
+		uint32_t a = 0, nb = 0;
+		const unsigned b0 = 16u * w;
+#pragma unroll
+		for (int i = 0; i < 16; ++i) {
+			if (b0 + (unsigned)i >= len) break;
+			const unsigned c = s[b0 + i];
+			if (c == 'A') { }
+			else if (c == 'C') a |= 1u << (2 * i);
+			else if (c == 'G') a |= 2u << (2 * i);
+			else if (c == 'T') a |= 3u << (2 * i);
+			else if (c == 'N') nb |= 1u << i;
+			else {
+				folded = 1;
+				if (c == 'a') { }
+				else if (c == 'c') a |= 1u << (2 * i);
+				else if (c == 'g') a |= 2u << (2 * i);
+				else if (c == 't') a |= 3u << (2 * i);
+				else nb |= 1u << i;
+			}
+		}
+		d2[w] = a; dn[w] = (uint16_t)nb;
+	}
+	folded = __any_sync(0xffffffffu, folded != 0);
+	if (folded && lane == 0) region[k].flags = g.flags | region[k].flags | (unsigned)IDL_RF_ALPHABET;
+}
+
 inline uint16_t h16(const uint8_t *p) { return (uint16_t)(p[0] | p[1] << 8); }
 inline uint32_t h32(const uint8_t *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
 
@@ -332,6 +499,11 @@ struct idl_bam {
 	long long *d_rec_off = nullptr;
 	unsigned long long *d_cig_off = nullptr; uint32_t *d_cigar = nullptr;
 	size_t n_all = 0, n_cigar = 0;
+	int32_t *d_ref_len = nullptr;
+	const uint8_t **d_ref_seq = nullptr;       // per target: its sequence (ASCII) on the device, or null (idl_bam_set_reference)
+	std::vector<const uint8_t*> ref_seq;
+	// scratch of the batch builder (grown on demand, reused)
+	void *scratch[8] = {}; size_t scratch_cap[8] = {};
 	std::vector<void*> owned;   // every cudaMalloc of this object
 	idl_bam_info info = {};
 	std::vector<std::string> names; std::vector<const char*> name_ptrs; std::vector<int64_t> ref_len, ref_first;
@@ -345,6 +517,8 @@ void idl_bam_close(idl_bam *b)
 	if (!b) return;
 	cudaSetDevice(b->device);
 	for (void *p : b->owned) cudaFree(p);
+	for (void *p : b->scratch) if (p) cudaFree(p);
+	for (const uint8_t *p : b->ref_seq) if (p) cudaFree((void*)p);
 	if (b->st) cudaStreamDestroy(b->st);
 	delete b;
 }
@@ -459,9 +633,9 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 		// 3. record boundaries
 		const size_t span = total - begin;
 		const uint32_t n_seg = (uint32_t)((span + SEG_BYTES - 1) / SEG_BYTES);
-		int32_t *d_ref_len = nullptr; long long *d_first = nullptr, *d_exit = nullptr, *d_preset = nullptr; uint32_t *d_count = nullptr, *d_bad = nullptr, *d_which = nullptr;
+		int32_t *&d_ref_len = b->d_ref_len; long long *d_first = nullptr, *d_exit = nullptr, *d_preset = nullptr; uint32_t *d_count = nullptr, *d_bad = nullptr, *d_which = nullptr;
 		unsigned long long *d_rec_base = nullptr;
-		BALLOC(d_ref_len, (size_t)n_ref * 4); BALLOC(d_first, (size_t)n_seg * 8); BALLOC(d_exit, (size_t)n_seg * 8); BALLOC(d_preset, (size_t)n_seg * 8);
+		BALLOC(d_ref_len, (size_t)n_ref * 4); BALLOC(b->d_ref_seq, (size_t)n_ref * 8); BCK(cudaMemsetAsync(b->d_ref_seq, 0, (size_t)n_ref * 8 + (n_ref ? 0 : 16), st)); b->ref_seq.assign(n_ref, nullptr); BALLOC(d_first, (size_t)n_seg * 8); BALLOC(d_exit, (size_t)n_seg * 8); BALLOC(d_preset, (size_t)n_seg * 8);
 		BALLOC(d_count, (size_t)n_seg * 4); BALLOC(d_bad, (size_t)n_seg * 4); BALLOC(d_which, (size_t)n_seg * 4); BALLOC(d_rec_base, (size_t)n_seg * 8 + 8);
 		if (n_ref) BCK(cudaMemcpyAsync(d_ref_len, ref_len32.data(), (size_t)n_ref * 4, cudaMemcpyHostToDevice, st));
 		std::vector<long long> first(n_seg), exitv(n_seg), preset(n_seg, -2);
@@ -679,3 +853,103 @@ done:
 }
 
 } // extern "C"
+
+// ---- batch builder entry points (bamdev.h) ----
+namespace {
+template <class T> cudaError_t scratch_get(idl_bam *b, int slot, size_t count, T **out)
+{
+	const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+	if (b->scratch_cap[slot] < bytes) {
+		if (b->scratch[slot]) cudaFree(b->scratch[slot]);
+		b->scratch[slot] = nullptr; b->scratch_cap[slot] = 0;
+		const cudaError_t e = cudaMalloc(&b->scratch[slot], bytes + bytes / 4);
+		if (e != cudaSuccess) return e;
+		b->scratch_cap[slot] = bytes + bytes / 4;
+	}
+	*out = (T*)b->scratch[slot];
+	return cudaSuccess;
+}
+// exclusive 64-bit scan of n uint32 values into out[0..n] (out[n] = total); tot = scratch for the tile totals
+cudaError_t scan_u32(const uint32_t *in, size_t n, unsigned long long *out, unsigned long long *tot, cudaStream_t st)
+{
+	const size_t nt = std::max<size_t>(1, (n + 1 + SCAN_TILE - 1) / SCAN_TILE);
+	scan_tile_totals_kernel<<<(unsigned)nt, SCAN_THREADS, 0, st>>>(in, n, tot);
+	scan_totals_kernel<<<1, 1024, 0, st>>>(tot, nt);
+	scan_apply_kernel<<<(unsigned)nt, SCAN_THREADS, 0, st>>>(in, n, tot, out);
+	return cudaGetLastError();
+}
+} // namespace
+
+int bam_device_of(const idl_bam *b) { return b ? b->device : -1; }
+
+int bam_batch_records(idl_bam *b, cudaStream_t st, const idl_params *P, size_t n_regions, const int32_t *roi_chrom, const int32_t *roi_start, const int32_t *roi_end,
+                      const int32_t *roi_n_reads, const int64_t *read_idx, size_t n_reads, uint32_t ordinal_base, idl_region *d_region, idl_read *d_read, BamBatchTotals *T)
+{
+#define QCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fprintf(stderr, "idl_bam batch: %s: %s\n", #call, cudaGetErrorString(e_)); return IDL_E_CUDA; } } while (0)
+	memset(T, 0, sizeof *T);
+	// scratch: 0 roi arrays (4 x int32), 1 read_idx, 2 read_pad + slot_region, 3 ref_pad, 4 scans (n_reads + 1 + n_regions + 1 + tile totals), 5 roi_read_begin + counters
+	int32_t *d_roi; long long *d_idx; uint32_t *d_rp; uint32_t *d_refpad; unsigned long long *d_scan; unsigned long long *d_rb;
+	QCK(scratch_get(b, 0, 4 * n_regions, &d_roi)); QCK(scratch_get(b, 1, n_reads, &d_idx)); QCK(scratch_get(b, 2, 2 * n_reads + 2, &d_rp));
+	QCK(scratch_get(b, 3, n_regions + 1, &d_refpad));
+	const size_t nt = (std::max(n_reads, n_regions) + 1 + SCAN_TILE - 1) / SCAN_TILE + 1;
+	QCK(scratch_get(b, 4, n_reads + 1 + n_regions + 1 + nt, &d_scan)); QCK(scratch_get(b, 5, n_regions + 1 + 8, &d_rb));
+	std::vector<unsigned long long> rb(n_regions + 1, 0);
+	for (size_t k = 0; k < n_regions; ++k) { if (roi_n_reads[k] < 0) return IDL_E_ARG; rb[k + 1] = rb[k] + (unsigned long long)roi_n_reads[k]; }
+	if (rb[n_regions] != n_reads) return IDL_E_ARG;
+	BuildCounters *d_cnt = (BuildCounters*)(d_rb + n_regions + 1);
+	uint32_t *d_slot_region = d_rp + n_reads + 1;
+	if (n_regions) {
+		QCK(cudaMemcpyAsync(d_roi, roi_chrom, n_regions * 4, cudaMemcpyHostToDevice, st)); QCK(cudaMemcpyAsync(d_roi + n_regions, roi_start, n_regions * 4, cudaMemcpyHostToDevice, st));
+		QCK(cudaMemcpyAsync(d_roi + 2 * n_regions, roi_end, n_regions * 4, cudaMemcpyHostToDevice, st));
+		QCK(cudaMemcpyAsync(d_roi + 3 * n_regions, roi_n_reads, n_regions * 4, cudaMemcpyHostToDevice, st));
+	}
+	if (n_reads) QCK(cudaMemcpyAsync(d_idx, read_idx, n_reads * 8, cudaMemcpyHostToDevice, st));
+	QCK(cudaMemcpyAsync(d_rb, rb.data(), (n_regions + 1) * 8, cudaMemcpyHostToDevice, st));
+	QCK(cudaMemsetAsync(d_cnt, 0, sizeof(BuildCounters), st));
+	if (n_regions)
+		bam_build_records_kernel<<<(unsigned)((n_regions * 32 + 255) / 256), 256, 0, st>>>(b->d_out, b->R, (size_t)b->info.n_records, b->d_ref_len, b->d_ref_seq, b->info.n_ref, *P, n_regions,
+		                                                                                  d_roi, d_roi + n_regions, d_roi + 2 * n_regions, d_roi + 3 * n_regions, d_rb, d_idx, ordinal_base,
+		                                                                                  d_region, d_read, d_rp, d_slot_region, d_refpad, d_cnt);
+	unsigned long long *d_soff = d_scan, *d_roff = d_scan + n_reads + 1, *d_tot = d_roff + n_regions + 1;
+	QCK(scan_u32(d_rp, n_reads, d_soff, d_tot, st));
+	QCK(scan_u32(d_refpad, n_regions, d_roff, d_tot, st));
+	const size_t nmax = std::max(n_reads, n_regions);
+	if (nmax) bam_build_offsets_kernel<<<(unsigned)((nmax + 255) / 256), 256, 0, st>>>(n_reads, n_regions, d_soff, d_roff, d_read, d_region);
+	QCK(cudaGetLastError());
+	BuildCounters hc; unsigned long long tot[2] = {0, 0};
+	QCK(cudaMemcpyAsync(&hc, d_cnt, sizeof hc, cudaMemcpyDeviceToHost, st));
+	QCK(cudaMemcpyAsync(&tot[0], d_soff + n_reads, 8, cudaMemcpyDeviceToHost, st)); QCK(cudaMemcpyAsync(&tot[1], d_roff + n_regions, 8, cudaMemcpyDeviceToHost, st));
+	QCK(cudaStreamSynchronize(st));
+	T->n_seq_bases = tot[0]; T->n_ref_bases = tot[1];
+	T->max_trim_len = std::max(1u, hc.max_trim_len); T->max_ref_len = hc.max_ref_len; T->max_region_reads = hc.max_region_reads; T->n_small_regions = hc.n_small_regions;
+	T->bad_index = hc.bad_index;
+	return IDL_OK;
+}
+
+int bam_batch_bases(idl_bam *b, cudaStream_t st, size_t n_regions, size_t n_reads, idl_region *d_region, const idl_read *d_read, const BamBatchTotals *T,
+                    uint32_t *seq2, uint32_t *seqn, uint32_t *ref2, uint32_t *refn)
+{
+	const long long *d_idx = (const long long*)b->scratch[1];
+	const uint32_t *d_slot_region = (const uint32_t*)b->scratch[2] + n_reads + 1;
+	if (n_reads) bam_pack_reads_kernel<<<(unsigned)((n_reads * 32 + 255) / 256), 256, 0, st>>>(b->d_out, b->R, d_idx, n_reads, d_read, d_slot_region, d_region, seq2, seqn);
+	if (n_regions) bam_pack_ref_kernel<<<(unsigned)((n_regions * 32 + 255) / 256), 256, 0, st>>>(b->d_ref_seq, n_regions, d_region, ref2, refn);
+	QCK(cudaGetLastError());
+	// guard words behind the pools (the kernels read up to two words past a record)
+	QCK(cudaMemsetAsync(seq2 + T->n_seq_bases / 16, 0, 16, st)); QCK(cudaMemsetAsync(seqn + T->n_seq_bases / 32, 0, 16, st));
+	QCK(cudaMemsetAsync(ref2 + T->n_ref_bases / 16, 0, 16, st)); QCK(cudaMemsetAsync(refn + T->n_ref_bases / 32, 0, 16, st));
+	return IDL_OK;
+#undef QCK
+}
+
+extern "C" int idl_bam_set_reference(idl_bam *b, int32_t target, const uint8_t *seq, int64_t len)
+{
+	if (!b || target < 0 || target >= b->info.n_ref || !seq || len != b->ref_len[(size_t)target]) return IDL_E_ARG;
+	if (cudaSetDevice(b->device) != cudaSuccess) return IDL_E_CUDA;
+	if (b->ref_seq[(size_t)target]) return IDL_OK;
+	uint8_t *d = nullptr;
+	if (cudaMalloc((void**)&d, (size_t)len + 64) != cudaSuccess) return IDL_E_NOMEM;
+	if (cudaMemcpyAsync(d, seq, (size_t)len, cudaMemcpyHostToDevice, b->st) != cudaSuccess || cudaMemsetAsync(d + len, 0, 64, b->st) != cudaSuccess ||
+	    cudaMemcpyAsync(b->d_ref_seq + target, &d, 8, cudaMemcpyHostToDevice, b->st) != cudaSuccess || cudaStreamSynchronize(b->st) != cudaSuccess) { cudaFree(d); return IDL_E_CUDA; }
+	b->ref_seq[(size_t)target] = d;
+	return IDL_OK;
+}

@@ -134,41 +134,68 @@ static int main_gpu_decode(const std::string &fa, const std::string &bam_path, i
 			t_vcf += now_s() - t2;
 			return true;
 		};
-		// batches of regions in emission order (the dedup of :604-608 depends on it); the records of a batch are fetched from the device once each
+		// batches of regions in emission order (the dedup of :604-608 depends on it).  Default: the batch is BUILT ON THE DEVICE from the resident
+		// records and reference (idl_bam_submit) -- nothing but the regions' coordinates and record indices crosses the bus.  INDELOPE_HOST_PACK=1:
+		// the records of a batch are fetched (idl_bam_fetch) and packed on the host (idlh_pack), as the streamed path does.
+		const bool host_pack = getenv("INDELOPE_HOST_PACK") != nullptr;
+		if (!host_pack) {
+			std::vector<char> has(info->n_ref > 0 ? (size_t)info->n_ref : 0, 0);
+			for (int32_t c : rc_) has[(size_t)c] = 1;
+			const idlh_roiset *all = nullptr;
+			idlh_rois *seqs = idlh_rois_from_arrays(ref, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+			all = idlh_rois_view(seqs);
+			double t2 = now_s();
+			for (int32_t c = 0; c < info->n_ref && !status; ++c)
+				if (has[(size_t)c] && idl_bam_set_reference(bam, c, all->chrom_seq[c], all->chrom_len[c]) != IDL_OK) status = die("idl_bam_set_reference", "could not place the reference on the device");
+			t_fetch += now_s() - t2;
+			idlh_rois_free(seqs);
+		}
 		size_t at_idx = 0;
 		std::vector<int64_t> uniq, local;
 		for (size_t lo = 0; lo < n_regions && !status; ) {
 			size_t hi = lo; int64_t reads = 0;
 			while (hi < n_regions && (hi == lo || (reads + rn_[hi] <= 400000 && hi - lo < 20000))) reads += rn_[hi++];
 			double t2 = now_s();
-			uniq.assign(idx_.begin() + (long)at_idx, idx_.begin() + (long)(at_idx + (size_t)reads));
-			std::sort(uniq.begin(), uniq.end()); uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
-			local.resize((size_t)reads);
-			for (int64_t k = 0; k < reads; ++k) local[(size_t)k] = std::lower_bound(uniq.begin(), uniq.end(), idx_[at_idx + (size_t)k]) - uniq.begin();
-			idl_bam_reads *rd = nullptr;
-			const int fr = idl_bam_fetch(bam, uniq.size(), uniq.data(), IDL_BAM_SEQ, &rd);
-			if (fr != IDL_OK) { status = die("idl_bam_fetch", idl_strerror(fr)); break; }
-			idlh_rois *grp = idlh_rois_from_arrays(ref, (int64_t)rd->n, rd->start, rd->stop, rd->len, rd->mapq, rd->flag, rd->seq_off, rd->bases, rd->quals, (int64_t)(hi - lo),
-			                                       rc_.data() + lo, rs_.data() + lo, re_.data() + lo, rn_.data() + lo, local.data());
-			idl_bam_reads_free(rd);
+			idlh_rois *grp = nullptr;
+			if (host_pack) {
+				uniq.assign(idx_.begin() + (long)at_idx, idx_.begin() + (long)(at_idx + (size_t)reads));
+				std::sort(uniq.begin(), uniq.end()); uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+				local.resize((size_t)reads);
+				for (int64_t k = 0; k < reads; ++k) local[(size_t)k] = std::lower_bound(uniq.begin(), uniq.end(), idx_[at_idx + (size_t)k]) - uniq.begin();
+				idl_bam_reads *rd = nullptr;
+				const int fr = idl_bam_fetch(bam, uniq.size(), uniq.data(), IDL_BAM_SEQ, &rd);
+				if (fr != IDL_OK) { status = die("idl_bam_fetch", idl_strerror(fr)); break; }
+				grp = idlh_rois_from_arrays(ref, (int64_t)rd->n, rd->start, rd->stop, rd->len, rd->mapq, rd->flag, rd->seq_off, rd->bases, rd->quals, (int64_t)(hi - lo),
+				                            rc_.data() + lo, rs_.data() + lo, re_.data() + lo, rn_.data() + lo, local.data());
+				idl_bam_reads_free(rd);
+			} else {
+				// the VCF stage reads only the regions' coordinates and the reference of this group
+				grp = idlh_rois_from_arrays(ref, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (int64_t)(hi - lo),
+				                            rc_.data() + lo, rs_.data() + lo, re_.data() + lo, rn_.data() + lo, idx_.data() + at_idx);
+			}
 			t_fetch += now_s() - t2;
 			const idlh_roiset *rs = idlh_rois_view(grp);
 			if (inflight.size() >= lanes.size() && !drain()) { idlh_rois_free(grp); break; }
-			Lane &L = lanes[nb % lanes.size()];
 			t2 = now_s();
-			size_t need[4] = {(size_t)rs->n_rois, 0, 0, 0};
-			idlh_pack_size(rs, 0, rs->n_rois, &P, &need[1], &need[2], &need[3]);
-			bool grow = L.batch == nullptr;
-			for (int k = 0; k < 4; ++k) grow |= need[k] > L.cap[k];
-			if (grow) {
-				if (L.batch) idl_batch_free(ctx, L.batch);
-				for (int k = 0; k < 4; ++k) L.cap[k] = need[k] + need[k] / 4 + 64;
-				if (idl_batch_alloc(ctx, L.cap[0], L.cap[1], L.cap[2], L.cap[3], &L.batch) != IDL_OK) { status = die("idl_batch_alloc", "out of pinned memory"); idlh_rois_free(grp); break; }
-			}
-			if (idlh_pack(rs, 0, rs->n_rois, &P, L.batch) != 0) { status = die("idlh_pack", "the pinned batch is smaller than idlh_pack_size reported (internal error)"); idlh_rois_free(grp); break; }
 			uint64_t ticket = 0;
-			const int r = idl_submit(ctx, L.batch, &ticket);
-			if (r != IDL_OK) { status = die("idl_submit", std::string(idl_strerror(r)) + " " + idl_last_cuda_error(ctx)); idlh_rois_free(grp); break; }
+			if (host_pack) {
+				Lane &L = lanes[nb % lanes.size()];
+				size_t need[4] = {(size_t)rs->n_rois, 0, 0, 0};
+				idlh_pack_size(rs, 0, rs->n_rois, &P, &need[1], &need[2], &need[3]);
+				bool grow = L.batch == nullptr;
+				for (int k = 0; k < 4; ++k) grow |= need[k] > L.cap[k];
+				if (grow) {
+					if (L.batch) idl_batch_free(ctx, L.batch);
+					for (int k = 0; k < 4; ++k) L.cap[k] = need[k] + need[k] / 4 + 64;
+					if (idl_batch_alloc(ctx, L.cap[0], L.cap[1], L.cap[2], L.cap[3], &L.batch) != IDL_OK) { status = die("idl_batch_alloc", "out of pinned memory"); idlh_rois_free(grp); break; }
+				}
+				if (idlh_pack(rs, 0, rs->n_rois, &P, L.batch) != 0) { status = die("idlh_pack", "the pinned batch is smaller than idlh_pack_size reported (internal error)"); idlh_rois_free(grp); break; }
+				const int r = idl_submit(ctx, L.batch, &ticket);
+				if (r != IDL_OK) { status = die("idl_submit", std::string(idl_strerror(r)) + " " + idl_last_cuda_error(ctx)); idlh_rois_free(grp); break; }
+			} else {
+				const int r = idl_bam_submit(ctx, bam, hi - lo, rc_.data() + lo, rs_.data() + lo, re_.data() + lo, rn_.data() + lo, idx_.data() + at_idx, (uint32_t)lo, &ticket);
+				if (r != IDL_OK) { status = die("idl_bam_submit", std::string(idl_strerror(r)) + " " + idl_last_cuda_error(ctx)); idlh_rois_free(grp); break; }
+			}
 			inflight.push_back({grp, ticket});
 			t_pack += now_s() - t2;
 			at_idx += (size_t)reads; lo = hi; ++nb;
@@ -180,7 +207,7 @@ static int main_gpu_decode(const std::string &fa, const std::string &bam_path, i
 	}
 	if (timing && info)
 		fprintf(stderr, "indelope timing (gpu decode): read file %.3f s, fasta %.3f s, idl_bam_open %.3f s (h2d %.1f ms, inflate %.1f ms, parse %.1f ms; %.1f MB -> %.1f MB, "
-		        "%lld records, %u boundary fixups), idl_create %.3f s, idl_bam_sweep %.3f s, idl_bam_fetch %.3f s, pack+submit %.3f s, idl_wait %.3f s, vcf %.3f s, total %.3f s, "
+		        "%lld records, %u boundary fixups), idl_create %.3f s, idl_bam_sweep %.3f s, reference / fetch %.3f s, build+submit %.3f s, idl_wait %.3f s, vcf %.3f s, total %.3f s, "
 		        "batches %zu, regions %zu\n", t_read, t_fasta, t_open, info->ms_h2d, info->ms_inflate, info->ms_parse, info->file_bytes / 1e6, info->inflated_bytes / 1e6,
 		        (long long)info->n_records, info->boundary_fixups, t_create, t_sweep, t_fetch, t_pack, t_wait, t_vcf, now_s() - t_begin, nb, n_regions);
 	if (bam) idl_bam_close(bam);

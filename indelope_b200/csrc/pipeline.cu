@@ -16,6 +16,7 @@
 #include "ksw2.cuh"
 #include "assemble.cuh"
 #include "genotype.cuh"
+#include "bamdev.h"
 
 static_assert(sizeof(idl_region) == 48 && sizeof(idl_read) == 24, "batch records are part of the ABI");
 static_assert(sizeof(idl_region_result) == 16 && sizeof(idl_contig_result) == 24 && sizeof(idl_aln_result) == 72 && sizeof(idl_event_result) == 128,
@@ -513,6 +514,77 @@ int idl_submit(idl_ctx *ctx, idl_batch *b, uint64_t *ticket)
 	if (rc) return rc;
 	L.ticket = ctx->next_ticket++; L.state = 1;
 	*ticket = L.ticket;
+	return IDL_OK;
+}
+
+// the batch of <n_regions> regions built by the device from a resident BAM into lane L's buffers (bamdev.cu); sets the lane's sizes and summary
+static int build_from_bam(idl_ctx *ctx, Lane &L, idl_bam *bam, size_t n_regions, const int32_t *roi_chrom, const int32_t *roi_start, const int32_t *roi_end,
+                          const int32_t *roi_n_reads, const int64_t *read_idx, uint32_t ordinal_base, BamBatchTotals &T)
+{
+	size_t n_reads = 0;
+	for (size_t k = 0; k < n_regions; ++k) { if (roi_n_reads[k] < 0) return IDL_E_ARG; n_reads += (size_t)roi_n_reads[k]; }
+	if (n_reads >= (1ull << 31) || n_regions >= (1ull << 31)) return IDL_E_CAPACITY;
+	CK(L.region.ensure((n_regions + 1) * sizeof(idl_region))); CK(L.read.ensure((n_reads + 1) * sizeof(idl_read)));
+	int rc = bam_batch_records(bam, L.stream, &ctx->P, n_regions, roi_chrom, roi_start, roi_end, roi_n_reads, read_idx, n_reads, ordinal_base,
+	                           (idl_region*)L.region.p, (idl_read*)L.read.p, &T);
+	if (rc) return rc;
+	if (T.bad_index) return IDL_E_ARG;
+	if (T.n_seq_bases >= (1ull << 32) || T.n_ref_bases >= (1ull << 32)) return IDL_E_CAPACITY;
+	if ((int)T.max_region_reads + 2 > ctx->ns) return IDL_E_CAPACITY;
+	L.n_regions = n_regions; L.n_reads = n_reads; L.n_seq_bases = (size_t)T.n_seq_bases; L.n_ref_bases = (size_t)T.n_ref_bases;
+	CK(L.seq2.ensure(L.n_seq_bases / 4 + 16)); CK(L.seqn.ensure(L.n_seq_bases / 8 + 16)); CK(L.ref2.ensure(L.n_ref_bases / 4 + 16)); CK(L.refn.ensure(L.n_ref_bases / 8 + 16));
+	rc = bam_batch_bases(bam, L.stream, n_regions, n_reads, (idl_region*)L.region.p, (const idl_read*)L.read.p, &T, (uint32_t*)L.seq2.p, (uint32_t*)L.seqn.p,
+	                     (uint32_t*)L.ref2.p, (uint32_t*)L.refn.p);
+	if (rc) return rc;
+	L.max_trim = (int)std::max(1u, std::min(T.max_trim_len, (unsigned)ctx->P.max_read_len)); L.max_ref = std::max(16u, T.max_ref_len); L.n_small = T.n_small_regions;
+	return IDL_OK;
+}
+
+int idl_bam_submit(idl_ctx *ctx, idl_bam *bam, size_t n_regions, const int32_t *roi_chrom, const int32_t *roi_start, const int32_t *roi_end, const int32_t *roi_n_reads,
+                   const int64_t *read_idx, uint32_t ordinal_base, uint64_t *ticket)
+{
+	if (!ctx || !bam || !ticket || (n_regions && (!roi_chrom || !roi_start || !roi_end || !roi_n_reads))) return IDL_E_ARG;
+	if (bam_device_of(bam) != ctx->device) return IDL_E_ARG;
+	cudaSetDevice(ctx->device);
+	Lane *Lp = nullptr;
+	for (size_t k = 0; k < ctx->lanes.size(); ++k) { Lane &c = ctx->lanes[(ctx->next_ticket + k) % ctx->lanes.size()]; if (c.state == 0) { Lp = &c; break; } }
+	if (!Lp) return IDL_E_BUSY;
+	Lane &L = *Lp;
+	L.resident = false; L.payload = true; L.retries = 0;
+	CK(cudaEventRecord(L.ev[EV_START], L.stream));
+	BamBatchTotals T;
+	int rc = build_from_bam(ctx, L, bam, n_regions, roi_chrom, roi_start, roi_end, roi_n_reads, read_idx, ordinal_base, T);
+	if (rc) return rc;
+	CK(cudaEventRecord(L.ev[EV_H2D], L.stream));
+	rc = launch_chain(ctx, L);
+	if (rc) return rc;
+	L.ticket = ctx->next_ticket++; L.state = 1;
+	*ticket = L.ticket;
+	return IDL_OK;
+}
+
+int idl_bam_pack(idl_ctx *ctx, idl_bam *bam, size_t n_regions, const int32_t *roi_chrom, const int32_t *roi_start, const int32_t *roi_end, const int32_t *roi_n_reads,
+                 const int64_t *read_idx, uint32_t ordinal_base, idl_batch *b)
+{
+	if (!ctx || !bam || !b || (n_regions && (!roi_chrom || !roi_start || !roi_end || !roi_n_reads))) return IDL_E_ARG;
+	if (bam_device_of(bam) != ctx->device) return IDL_E_ARG;
+	cudaSetDevice(ctx->device);
+	Lane *Lp = nullptr;
+	for (Lane &c : ctx->lanes) if (c.state == 0) { Lp = &c; break; }
+	if (!Lp) return IDL_E_BUSY;
+	Lane &L = *Lp;
+	BamBatchTotals T;
+	int rc = build_from_bam(ctx, L, bam, n_regions, roi_chrom, roi_start, roi_end, roi_n_reads, read_idx, ordinal_base, T);
+	L.resident = false;
+	if (rc) return rc;
+	if (L.n_regions > b->cap_regions || L.n_reads > b->cap_reads || L.n_seq_bases > b->cap_seq_bases || L.n_ref_bases > b->cap_ref_bases) return IDL_E_CAPACITY;
+	CK(cudaMemcpyAsync(b->region, L.region.p, L.n_regions * sizeof(idl_region), cudaMemcpyDeviceToHost, L.stream));
+	CK(cudaMemcpyAsync(b->read, L.read.p, L.n_reads * sizeof(idl_read), cudaMemcpyDeviceToHost, L.stream));
+	CK(cudaMemcpyAsync(b->seq2, L.seq2.p, L.n_seq_bases / 4 + 16, cudaMemcpyDeviceToHost, L.stream)); CK(cudaMemcpyAsync(b->seqn, L.seqn.p, L.n_seq_bases / 8 + 16, cudaMemcpyDeviceToHost, L.stream));
+	CK(cudaMemcpyAsync(b->ref2, L.ref2.p, L.n_ref_bases / 4 + 16, cudaMemcpyDeviceToHost, L.stream)); CK(cudaMemcpyAsync(b->refn, L.refn.p, L.n_ref_bases / 8 + 16, cudaMemcpyDeviceToHost, L.stream));
+	CK(cudaStreamSynchronize(L.stream));
+	b->n_regions = L.n_regions; b->n_reads = L.n_reads; b->n_seq_bases = L.n_seq_bases; b->n_ref_bases = L.n_ref_bases;
+	b->max_trim_len = T.max_trim_len; b->max_ref_len = T.max_ref_len; b->max_region_reads = T.max_region_reads; b->n_small_regions = T.n_small_regions; b->summary_valid = 1;
 	return IDL_OK;
 }
 

@@ -47,7 +47,7 @@ def lib():
 
 EXPORTS = ("idl_default_params idl_create idl_destroy idl_batch_alloc idl_batch_free idl_submit idl_upload idl_run_resident idl_wait "
            "idl_release idl_strerror idl_last_cuda_error idl_device_count idl_ksw2_batch idl_sweep idl_sweep_free "
-           "idl_bam_open idl_bam_get_info idl_bam_close idl_bam_sweep idl_bam_fetch idl_bam_reads_free").split()
+           "idl_bam_open idl_bam_get_info idl_bam_close idl_bam_sweep idl_bam_fetch idl_bam_reads_free idl_bam_set_reference idl_bam_submit idl_bam_pack").split()
 
 
 class SweepIn(C.Structure):
@@ -168,12 +168,27 @@ class Bam:
         L.idl_bam_reads_free(out)
         return r
 
+    def set_reference(self, target, seq):
+        """the sequence of one target (ASCII bytes / uint8 array, as in the FASTA) for the batches built on the device"""
+        a = np.ascontiguousarray(seq, dtype=np.uint8)
+        L = lib()
+        L.idl_bam_set_reference.argtypes = [C.c_void_p, C.c_int32, u8p, C.c_int64]
+        rc = L.idl_bam_set_reference(self.h, target, a.ctypes.data_as(u8p), len(a))
+        if rc != 0:
+            raise IdlError("idl_bam_set_reference: %s" % L.idl_strerror(rc).decode())
+
     def close(self):
         if self.h:
             lib().idl_bam_close(self.h); self.h = None
 
     def __del__(self):
         self.close()
+
+
+def _roi_args(roi_chrom, roi_start, roi_end, roi_n_reads, read_idx):
+    a = [np.ascontiguousarray(x, dtype=t) for x, t in ((roi_chrom, np.int32), (roi_start, np.int32), (roi_end, np.int32), (roi_n_reads, np.int32), (read_idx, np.int64))]
+    i32 = C.POINTER(C.c_int32)
+    return a, (len(a[0]), a[0].ctypes.data_as(i32), a[1].ctypes.data_as(i32), a[2].ctypes.data_as(i32), a[3].ctypes.data_as(i32), a[4].ctypes.data_as(C.POINTER(C.c_int64)))
 
 
 class Context:
@@ -203,6 +218,24 @@ class Context:
         t = C.c_uint64()
         self._check(lib().idl_submit(self.h, batch, C.byref(t)), "idl_submit")
         return t.value
+
+    def bam_submit(self, bam, roi_chrom, roi_start, roi_end, roi_n_reads, read_idx, ordinal_base=0):
+        """idl_bam_submit: the batch of these regions is built on the device from the resident BAM and run; returns the ticket"""
+        L = lib()
+        i32 = C.POINTER(C.c_int32)
+        L.idl_bam_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, i32, i32, i32, i32, C.POINTER(C.c_int64), C.c_uint32, u64p]
+        keep, args = _roi_args(roi_chrom, roi_start, roi_end, roi_n_reads, read_idx)
+        t = C.c_uint64()
+        self._check(L.idl_bam_submit(self.h, bam.h, *args, ordinal_base, C.byref(t)), "idl_bam_submit")
+        return t.value
+
+    def bam_pack(self, bam, roi_chrom, roi_start, roi_end, roi_n_reads, read_idx, batch, ordinal_base=0):
+        """idl_bam_pack: the same batch copied into a host idl_batch (from batch_alloc)"""
+        L = lib()
+        i32 = C.POINTER(C.c_int32)
+        L.idl_bam_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, i32, i32, i32, i32, C.POINTER(C.c_int64), C.c_uint32, C.POINTER(Batch)]
+        keep, args = _roi_args(roi_chrom, roi_start, roi_end, roi_n_reads, read_idx)
+        self._check(L.idl_bam_pack(self.h, bam.h, *args, ordinal_base, batch), "idl_bam_pack")
 
     def upload(self, batch):
         self._check(lib().idl_upload(self.h, batch), "idl_upload")

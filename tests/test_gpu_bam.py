@@ -8,7 +8,10 @@ import zlib
 import numpy as np
 import pytest
 
-from indelope_b200 import cuda, host
+import ctypes as C
+
+from indelope_b200 import abi, cuda, host
+from oracle import pyoracle as orc
 import idl_testutil as util
 
 pytestmark = pytest.mark.gpu
@@ -193,3 +196,99 @@ def test_same_records_and_regions_as_the_host_reader(files):
         assert np.array_equal(sub["quals"][sub["seq_off"][j]:sub["seq_off"][j + 1]], allr["quals"][allr["seq_off"][i]:allr["seq_off"][i + 1]])
         assert np.array_equal(sub["cigar"][int(sub["cig_off"][j]):int(sub["cig_off"][j + 1])], allr["cigar"][int(allr["cig_off"][i]):int(allr["cig_off"][i + 1])])
     b.close()
+
+
+def _batch_bytes(b):
+    """the filled part of an idl_batch as bytes per array (+ the summary)"""
+    c = b.contents
+    out = dict(sizes=(c.n_regions, c.n_reads, c.n_seq_bases, c.n_ref_bases), summary=(c.summary_valid, c.max_trim_len, c.max_ref_len, c.max_region_reads, c.n_small_regions))
+    out["region"] = C.string_at(c.region, c.n_regions * C.sizeof(abi.Region)); out["read"] = C.string_at(c.read, c.n_reads * C.sizeof(abi.Read))
+    out["seq2"] = C.string_at(c.seq2, c.n_seq_bases // 4 + 16); out["seqn"] = C.string_at(c.seqn, c.n_seq_bases // 8 + 16)
+    out["ref2"] = C.string_at(c.ref2, c.n_ref_bases // 4 + 16); out["refn"] = C.string_at(c.refn, c.n_ref_bases // 8 + 16)
+    return out
+
+
+def _compare_device_and_host_pack(fa, bam, min_reads=5, expect_flags=None):
+    data = open(bam, "rb").read()
+    b = cuda.Bam(data)
+    full = host.Dataset.load(fa, bam, threads=2)
+    rois = full.sweep(min_reads=min_reads)
+    a = rois.arrays()
+    n = rois.n_rois
+    assert n > 0
+    for c in range(b.n_ref):
+        b.set_reference(c, a["chrom_seqs"][c])
+    params = abi.default_params(min_reads=min_reads, min_ctg_len=73, min_event_len=5)
+    ctx = cuda.Context(0, params)
+    nr, sb, rb = rois.pack_size(0, n, params)
+    hb = ctx.batch_alloc(n + 8, nr + 8, sb + 64, rb + 64); db = ctx.batch_alloc(n + 8, nr + 8, sb + 64, rb + 64)
+    rois.pack(0, n, params, hb)
+    ctx.bam_pack(b, a["roi_chrom"], a["roi_start"], a["roi_stop"], a["roi_n_reads"], a["read_idx"], db)
+    H, D = _batch_bytes(hb), _batch_bytes(db)
+    for k in ("sizes", "summary", "region", "read", "seq2", "seqn", "ref2", "refn"):
+        assert H[k] == D[k], k
+    if expect_flags is not None:
+        flags = [hb.contents.region[k].flags for k in range(n)]
+        assert expect_flags(flags), flags
+    # ... and through the calling chain: idl_bam_submit == idl_submit of the host batch == the oracle
+    w1, w2 = host.VcfWriter(), host.VcfWriter()
+    t = ctx.submit(hb); v1, _ = w1.records(rois, 0, params, ctx.wait(t)); ctx.release(t)
+    t = ctx.bam_submit(b, a["roi_chrom"], a["roi_start"], a["roi_stop"], a["roi_n_reads"], a["read_idx"]); v2, _ = w2.records(rois, 0, params, ctx.wait(t)); ctx.release(t)
+    assert v1 == v2
+    ctx.batch_free(hb); ctx.batch_free(db); ctx.close(); b.close()
+    return rois, v2
+
+
+def test_device_built_batch_equals_the_host_pack(files):
+    """idl_bam_pack / idl_bam_submit: quality trim, windows, records and the 2-bit pools built on the device == idlh_pack on the host reader's arrays,
+    byte for byte; the VCF through idl_bam_submit == the oracle's"""
+    ds, fa, bam = files
+    rois, vcf = _compare_device_and_host_pack(fa, bam)
+    _, ovcf, cnt = orc.call(rois.arrays(), dump_level=0, min_reads=5, min_ctg_len=73, min_event_len=5, use_ref_ksw2=orc.have_ref())
+    assert vcf == ovcf and cnt["variants"] >= 3
+
+
+def test_device_pack_of_odd_letters_trims_and_long_reads(tmp_path):
+    """hand-made files: lower-case, N and IUPAC letters in the reference window and IUPAC codes in reads (folded + IDL_RF_ALPHABET), reads whose
+    qualities trim to nothing / to one base / at both ends, an empty read, a read longer than max_read_len (IDL_RF_READ_TOO_LONG), low MAPQ"""
+    rng = random.Random(21)
+    L = 6000
+    seq = [rng.choice("ACGT") for _ in range(L)]
+    for i in range(1000, 1100):
+        seq[i] = seq[i].lower()
+    seq[1200] = "N"; seq[1201] = "n"; seq[1250] = "R"; seq[4100] = "y"
+    ref = "".join(seq)
+    fa = tmp_path / "r.fa"
+    fa.write_text(">c1\n" + "\n".join(ref[i:i + 60] for i in range(0, L, 60)) + "\n>c2\n" + "ACGT" * 50 + "\n")
+    recs = []
+    def reads_at(center, n, odd=None):
+        out = []
+        for k in range(n):
+            start = center - 100 + 3 * k
+            left = center - start                                        # every read of the cluster carries the insertion at `center`
+            s = ref[start:center].upper().replace("N", "A").replace("R", "A").replace("Y", "C") + "TTGCA" + ref[center:start + 140].upper().replace("Y", "C")
+            q = [30] * len(s)
+            cig = [("M", left), ("I", 5), ("M", 140 - left)]
+            mapq = 60
+            if odd == "letters" and k % 4 == 0:
+                s = s[:20] + "MRN" + s[23:]
+            if odd == "quals":
+                if k == 0: q = [2] * len(s)
+                if k == 1: q = [2] * 50 + [30] + [2] * (len(s) - 51)
+                if k == 2: q = [2] * 7 + [30] * (len(s) - 20) + [5] * 13
+                if k == 3: mapq = 3
+            out.append((start, util.bam_record(0, start, cig, s, qual=q, mapq=mapq, name=b"r%d_%d" % (center, k))))
+        if odd == "long":
+            s = "".join(rng.choice("ACGT") for _ in range(700))
+            out.append((center - 50, util.bam_record(0, center - 50, [("M", 300), ("I", 100), ("M", 300)], s, name=b"long")))
+        if odd == "quals":
+            out.append((center - 10, util.bam_record(0, center - 10, [], "", name=b"empty")))
+        return out
+    allr = reads_at(1150, 12, "letters") + reads_at(2500, 12, "quals") + reads_at(4000, 12, "long") + reads_at(5200, 10)
+    allr.sort(key=lambda t: t[0])
+    raw = util.bam_bytes([("c1", L), ("c2", 200)], [r for _, r in allr])
+    bam = tmp_path / "r.bam"
+    bam.write_bytes(util.bgzf_compress(raw, level=6))
+    def flags_ok(flags):
+        return any(f & 1 for f in flags) and any(f & 2 for f in flags) and any(f == 0 for f in flags)
+    _compare_device_and_host_pack(str(fa), str(bam), min_reads=5, expect_flags=flags_ok)

@@ -66,6 +66,11 @@ def main():
                     best = dt; out["gpu_decode_phases"] = r2.stderr.strip().split("\n")[-2:]
             if best is not None:
                 out["gpu_decode_cli_s"] = round(best, 3); out["gpu_decode_vcf_identical_to_oracle"] = (r2.stdout == whole.header() + ovcf)
+            # ... and with the batches packed on the host from fetched records instead of built on the device
+            r3 = subprocess.run([exe, "--gpu-decode", "--min-event-len", "5", "--min-reads", "5", fa, bam], capture_output=True, text=True,
+                                env=dict(os.environ, INDELOPE_TIMING="1", INDELOPE_HOST_PACK="1"))
+            if r3.returncode == 0:
+                out["gpu_decode_host_pack_phases"] = r3.stderr.strip().split("\n")[-1]; out["gpu_decode_host_pack_vcf_identical_to_oracle"] = (r3.stdout == whole.header() + ovcf)
             # the decoders alone, in process: host reader (inflate + parse on `threads` host threads) against idl_bam_open
             from indelope_b200 import cuda
             data = open(bam, "rb").read()

@@ -171,6 +171,11 @@ proc idl_bam_sweep*(bam: IdlBam, target: int32, min_event_support, min_read_cove
                     outp: ptr ptr IdlSweepOut): cint {.importc.}
 proc idl_bam_fetch*(bam: IdlBam, n: csize_t, idx: ptr int64, what: uint32, outp: ptr ptr IdlBamReads): cint {.importc.}
 proc idl_bam_reads_free*(r: ptr IdlBamReads) {.importc.}
+proc idl_bam_set_reference*(bam: IdlBam, target: int32, sequence: ptr uint8, len: int64): cint {.importc.}
+proc idl_bam_submit*(ctx: IdlCtx, bam: IdlBam, n_regions: csize_t, roi_chrom, roi_start, roi_end, roi_n_reads: ptr int32, read_idx: ptr int64,
+                     ordinal_base: uint32, ticket: ptr uint64): cint {.importc.}
+proc idl_bam_pack*(ctx: IdlCtx, bam: IdlBam, n_regions: csize_t, roi_chrom, roi_start, roi_end, roi_n_reads: ptr int32, read_idx: ptr int64,
+                   ordinal_base: uint32, b: ptr IdlBatch): cint {.importc.}
 {.pop.}
 
 when isMainModule:

@@ -324,7 +324,9 @@ typedef struct idl_bam_info {
 	int64_t n_records;               /* records with a target */
 	int64_t n_unplaced;              /* records of the unplaced tail (dropped) */
 	const int64_t *ref_first;        /* n_ref + 1 entries: records [ref_first[c], ref_first[c + 1]) belong to target c */
-	float ms_h2d, ms_inflate, ms_parse;   /* CUDA events on the call's stream */
+	float ms_h2d, ms_inflate, ms_parse;   /* CUDA events on the call's stream; the file goes up in chunks that are inflated as they arrive: ms_h2d is
+	                                         the set-up before the first chunk, ms_inflate the copies and the kernels together */
+	uint32_t n_chunks;
 } idl_bam_info;
 
 int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **bam, char *err, size_t errlen);

@@ -54,8 +54,8 @@ struct Member { unsigned long long in_off; unsigned long long out_off; uint32_t 
 
 // ---- stage 2 ----
 __global__ void __launch_bounds__(INF_WARPS * 32, INF_CTAS_PER_SM)
-bgzf_inflate_kernel(const uint8_t *comp, const Member *members, uint32_t n_members, uint8_t *out, unsigned long long *first_error, unsigned *next)
-{
+bgzf_inflate_kernel(const uint8_t *comp, const Member *members, uint32_t m_begin, uint32_t n_members, uint8_t *out, unsigned long long *first_error, unsigned *next)
+{   // members [m_begin, n_members) of the file: one launch per chunk of the file as its bytes arrive (idl_bam_open)
 	__shared__ Tables tables[INF_WARPS];
 	__shared__ uint32_t crc_tab[256], xp[32];
 	crc_init_tables((int)threadIdx.x, (int)blockDim.x, crc_tab, xp);
@@ -63,7 +63,7 @@ bgzf_inflate_kernel(const uint8_t *comp, const Member *members, uint32_t n_membe
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	for (;;) {
 		unsigned m = 0;
-		if (lane == 0) m = atomicAdd(next, 1u);
+		if (lane == 0) m = m_begin + atomicAdd(next, 1u);
 		m = __shfl_sync(0xffffffffu, m, 0);
 		if (m >= n_members) break;
 		const Member M = members[m];
@@ -580,20 +580,52 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 		cudaStream_t st = b->st;
 		for (auto &e : ev) BCK(cudaEventCreate(&e));
 		Member *d_members = nullptr; unsigned long long *d_err = nullptr; unsigned *d_next = nullptr;
-		BALLOC(b->d_comp, file_len + 512); BALLOC(b->d_out, total + 64); BALLOC(d_members, members.size() * sizeof(Member)); BALLOC(d_err, 64); BALLOC(d_next, 16);
+		BALLOC(b->d_comp, file_len + 512); BALLOC(b->d_out, total + 64); BALLOC(d_members, members.size() * sizeof(Member)); BALLOC(d_err, 64); BALLOC(d_next, 4 * 64);
 		// 2. H2D + inflate
 		tw[2] = now();
 		BCK(cudaEventRecord(ev[0], st));
-		BCK(cudaMemcpyAsync(b->d_comp, file, file_len, cudaMemcpyHostToDevice, st));
 		BCK(cudaMemsetAsync(b->d_comp + file_len, 0, 512, st));
 		BCK(cudaMemcpyAsync(d_members, members.data(), members.size() * sizeof(Member), cudaMemcpyHostToDevice, st));
-		BCK(cudaMemsetAsync(d_err, 0xff, 64, st)); BCK(cudaMemsetAsync(d_next, 0, 16, st)); BCK(cudaMemsetAsync(b->d_out + total, 0, 64, st));
+		BCK(cudaMemsetAsync(d_err, 0xff, 64, st)); BCK(cudaMemsetAsync(d_next, 0, 4 * 64, st)); BCK(cudaMemsetAsync(b->d_out + total, 0, 64, st));
 		BCK(cudaEventRecord(ev[1], st));
 		{
-			const unsigned ctas = (unsigned)std::min<size_t>((size_t)n_sm * INF_CTAS_PER_SM, (members.size() + INF_WARPS - 1) / INF_WARPS);
-			bgzf_inflate_kernel<<<ctas, INF_WARPS * 32, 0, st>>>(b->d_comp, d_members, (uint32_t)members.size(), b->d_out, d_err, d_next);
+			// The file goes up in chunks of whole members and every chunk's members are inflated as soon as they have arrived, on one of four
+			// streams: the copy of chunk k+1 (a staged copy when the caller's buffer is pageable) overlaps the kernels of chunks k, k-1, ...
+			// One member is a serial chain of ~9 ms whatever the chunk's size, so consecutive chunks' kernels have to share the SMs.
+			constexpr int NS = 4; constexpr size_t CHUNK = 32u << 20;
+			cudaStream_t ks[NS] = {}; cudaEvent_t ce[64] = {}, ke[NS] = {};
+			cudaError_t e_ = cudaSuccess;
+			for (int k = 0; k < NS && e_ == cudaSuccess; ++k) { e_ = cudaStreamCreateWithFlags(&ks[k], cudaStreamNonBlocking); if (e_ == cudaSuccess) e_ = cudaEventCreateWithFlags(&ke[k], cudaEventDisableTiming); }
+			if (e_ == cudaSuccess) e_ = cudaEventCreateWithFlags(&ce[0], cudaEventDisableTiming);
+			if (e_ == cudaSuccess) e_ = cudaEventRecord(ce[0], st);   // the member table, the cleared counters
+			size_t m0 = 0, byte0 = 0; int chunk = 0;
+			while (m0 < members.size() && e_ == cudaSuccess) {
+				size_t m1 = m0, byte1 = byte0;
+				while (m1 < members.size() && (m1 == m0 || members[m1].in_off + members[m1].in_len + 8 - byte0 <= CHUNK)) { byte1 = (size_t)(members[m1].in_off + members[m1].in_len + 8); ++m1; }
+				if (chunk >= 62) { m1 = members.size(); byte1 = file_len; }   // (a file of more than 2 GB: the rest as one chunk)
+				const int c = chunk + 1;
+				e_ = cudaMemcpyAsync(b->d_comp + byte0, file + byte0, byte1 - byte0, cudaMemcpyHostToDevice, st);
+				if (e_ == cudaSuccess) e_ = cudaEventCreateWithFlags(&ce[c], cudaEventDisableTiming);
+				if (e_ == cudaSuccess) e_ = cudaEventRecord(ce[c], st);
+				cudaStream_t k_st = ks[chunk % NS];
+				if (e_ == cudaSuccess) e_ = cudaStreamWaitEvent(k_st, ce[c], 0);
+				if (e_ == cudaSuccess && chunk < NS) e_ = cudaStreamWaitEvent(k_st, ce[0], 0);
+				if (e_ == cudaSuccess) {
+					const size_t nm = m1 - m0;
+					const unsigned ctas = (unsigned)std::min<size_t>((size_t)n_sm * INF_CTAS_PER_SM, (nm + INF_WARPS - 1) / INF_WARPS);
+					bgzf_inflate_kernel<<<ctas, INF_WARPS * 32, 0, k_st>>>(b->d_comp, d_members, (uint32_t)m0, (uint32_t)m1, b->d_out, d_err, d_next + c);
+					e_ = cudaGetLastError();
+				}
+				m0 = m1; byte0 = byte1; ++chunk;
+			}
+			// the call's stream continues when every chunk's kernel is done (the padding behind the file was cleared before the first of them started)
+			for (int k = 0; k < NS && e_ == cudaSuccess; ++k) { e_ = cudaEventRecord(ke[k], ks[k]); if (e_ == cudaSuccess) e_ = cudaStreamWaitEvent(st, ke[k], 0); }
+			const cudaError_t e_sync = cudaStreamSynchronize(st);
+			for (auto &e : ce) if (e) cudaEventDestroy(e);
+			for (int k = 0; k < NS; ++k) { if (ke[k]) cudaEventDestroy(ke[k]); if (ks[k]) cudaStreamDestroy(ks[k]); }
+			if (e_ != cudaSuccess || e_sync != cudaSuccess) { why = std::string("inflate: ") + cudaGetErrorString(e_ != cudaSuccess ? e_ : e_sync); rc = IDL_E_CUDA; goto done; }
+			b->info.n_chunks = (uint32_t)chunk;
 		}
-		BCK(cudaGetLastError());
 		BCK(cudaEventRecord(ev[2], st));
 		unsigned long long herr[8];
 		BCK(cudaMemcpyAsync(herr, d_err, 64, cudaMemcpyDeviceToHost, st));

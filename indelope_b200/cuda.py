@@ -94,7 +94,7 @@ class BamInfo(C.Structure):
     _fields_ = [("file_bytes", C.c_uint64), ("inflated_bytes", C.c_uint64), ("n_members", C.c_uint32), ("boundary_fixups", C.c_uint32), ("n_ref", C.c_int32),
                 ("ref_name", C.POINTER(C.c_char_p)), ("ref_len", C.POINTER(C.c_int64)), ("header_text", C.c_void_p), ("header_len", C.c_size_t),
                 ("n_records", C.c_int64), ("n_unplaced", C.c_int64), ("ref_first", C.POINTER(C.c_int64)), ("ms_h2d", C.c_float), ("ms_inflate", C.c_float),
-                ("ms_parse", C.c_float)]
+                ("ms_parse", C.c_float), ("n_chunks", C.c_uint32)]
 
 
 class BamReads(C.Structure):
@@ -132,7 +132,7 @@ class Bam:
         self.header = C.string_at(i.header_text, i.header_len).decode() if i.header_len else ""
         self.n_records, self.n_unplaced = int(i.n_records), int(i.n_unplaced)
         self.info = dict(file_bytes=int(i.file_bytes), inflated_bytes=int(i.inflated_bytes), n_members=int(i.n_members), boundary_fixups=int(i.boundary_fixups),
-                         ms_h2d=i.ms_h2d, ms_inflate=i.ms_inflate, ms_parse=i.ms_parse)
+                         ms_h2d=i.ms_h2d, ms_inflate=i.ms_inflate, ms_parse=i.ms_parse, n_chunks=int(i.n_chunks))
 
     def sweep(self, target, min_event_support=3, min_read_coverage=3, max_read_coverage=600, evidence=False):
         L = lib()

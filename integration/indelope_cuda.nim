@@ -121,6 +121,7 @@ type
     n_records*, n_unplaced*: int64
     ref_first*: ptr UncheckedArray[int64]  ## n_ref + 1: records of target c are [ref_first[c], ref_first[c + 1])
     ms_h2d*, ms_inflate*, ms_parse*: cfloat
+    n_chunks*: uint32
 
   IdlBamReads* {.bycopy.} = object         ## idl_bam_reads: what callsemble reads of a cached Record (src/indelope.nim:216-222)
     n*: csize_t

@@ -502,8 +502,10 @@ struct idl_bam {
 	int32_t *d_ref_len = nullptr;
 	const uint8_t **d_ref_seq = nullptr;       // per target: its sequence (ASCII) on the device, or null (idl_bam_set_reference)
 	std::vector<const uint8_t*> ref_seq;
-	// scratch of the batch builder (grown on demand, reused)
-	void *scratch[8] = {}; size_t scratch_cap[8] = {};
+	// scratch of the batch builder: four sets used in turn (grown on demand); a set is reused only after the kernels of the batch that used it
+	// last are done (`done`, recorded on that batch's stream behind its pack kernels): several batches are in flight on different lanes
+	struct ScratchSet { void *p[8] = {}; size_t cap[8] = {}; cudaEvent_t done = nullptr; bool used = false; };
+	ScratchSet sets[4]; unsigned next_set = 0;
 	std::vector<void*> owned;   // every cudaMalloc of this object
 	idl_bam_info info = {};
 	std::vector<std::string> names; std::vector<const char*> name_ptrs; std::vector<int64_t> ref_len, ref_first;
@@ -517,7 +519,7 @@ void idl_bam_close(idl_bam *b)
 	if (!b) return;
 	cudaSetDevice(b->device);
 	for (void *p : b->owned) cudaFree(p);
-	for (void *p : b->scratch) if (p) cudaFree(p);
+	for (auto &S : b->sets) { for (void *p : S.p) if (p) cudaFree(p); if (S.done) cudaEventDestroy(S.done); }
 	for (const uint8_t *p : b->ref_seq) if (p) cudaFree((void*)p);
 	if (b->st) cudaStreamDestroy(b->st);
 	delete b;
@@ -888,17 +890,17 @@ done:
 
 // ---- batch builder entry points (bamdev.h) ----
 namespace {
-template <class T> cudaError_t scratch_get(idl_bam *b, int slot, size_t count, T **out)
+template <class T> cudaError_t scratch_get(idl_bam::ScratchSet &S, int slot, size_t count, T **out)
 {
 	const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
-	if (b->scratch_cap[slot] < bytes) {
-		if (b->scratch[slot]) cudaFree(b->scratch[slot]);
-		b->scratch[slot] = nullptr; b->scratch_cap[slot] = 0;
-		const cudaError_t e = cudaMalloc(&b->scratch[slot], bytes + bytes / 4);
+	if (S.cap[slot] < bytes) {
+		if (S.p[slot]) cudaFree(S.p[slot]);
+		S.p[slot] = nullptr; S.cap[slot] = 0;
+		const cudaError_t e = cudaMalloc(&S.p[slot], bytes + bytes / 4);
 		if (e != cudaSuccess) return e;
-		b->scratch_cap[slot] = bytes + bytes / 4;
+		S.cap[slot] = bytes + bytes / 4;
 	}
-	*out = (T*)b->scratch[slot];
+	*out = (T*)S.p[slot];
 	return cudaSuccess;
 }
 // exclusive 64-bit scan of n uint32 values into out[0..n] (out[n] = total); tot = scratch for the tile totals
@@ -919,12 +921,18 @@ int bam_batch_records(idl_bam *b, cudaStream_t st, const idl_params *P, size_t n
 {
 #define QCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fprintf(stderr, "idl_bam batch: %s: %s\n", #call, cudaGetErrorString(e_)); return IDL_E_CUDA; } } while (0)
 	memset(T, 0, sizeof *T);
+	T->scratch_set = b->next_set++ % 4u;
+	idl_bam::ScratchSet &S = b->sets[T->scratch_set];
+	if (!S.done) QCK(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+	if (S.used) QCK(cudaEventSynchronize(S.done));   // the batch that used this set last has consumed it
+	S.used = true;
+	QCK(cudaEventRecord(S.done, st));               // (re-recorded behind the pack kernels in bam_batch_bases; this covers an early return)
 	// scratch: 0 roi arrays (4 x int32), 1 read_idx, 2 read_pad + slot_region, 3 ref_pad, 4 scans (n_reads + 1 + n_regions + 1 + tile totals), 5 roi_read_begin + counters
 	int32_t *d_roi; long long *d_idx; uint32_t *d_rp; uint32_t *d_refpad; unsigned long long *d_scan; unsigned long long *d_rb;
-	QCK(scratch_get(b, 0, 4 * n_regions, &d_roi)); QCK(scratch_get(b, 1, n_reads, &d_idx)); QCK(scratch_get(b, 2, 2 * n_reads + 2, &d_rp));
-	QCK(scratch_get(b, 3, n_regions + 1, &d_refpad));
+	QCK(scratch_get(S, 0, 4 * n_regions, &d_roi)); QCK(scratch_get(S, 1, n_reads, &d_idx)); QCK(scratch_get(S, 2, 2 * n_reads + 2, &d_rp));
+	QCK(scratch_get(S, 3, n_regions + 1, &d_refpad));
 	const size_t nt = (std::max(n_reads, n_regions) + 1 + SCAN_TILE - 1) / SCAN_TILE + 1;
-	QCK(scratch_get(b, 4, n_reads + 1 + n_regions + 1 + nt, &d_scan)); QCK(scratch_get(b, 5, n_regions + 1 + 8, &d_rb));
+	QCK(scratch_get(S, 4, n_reads + 1 + n_regions + 1 + nt, &d_scan)); QCK(scratch_get(S, 5, n_regions + 1 + 8, &d_rb));
 	std::vector<unsigned long long> rb(n_regions + 1, 0);
 	for (size_t k = 0; k < n_regions; ++k) { if (roi_n_reads[k] < 0) return IDL_E_ARG; rb[k + 1] = rb[k] + (unsigned long long)roi_n_reads[k]; }
 	if (rb[n_regions] != n_reads) return IDL_E_ARG;
@@ -961,14 +969,16 @@ int bam_batch_records(idl_bam *b, cudaStream_t st, const idl_params *P, size_t n
 int bam_batch_bases(idl_bam *b, cudaStream_t st, size_t n_regions, size_t n_reads, idl_region *d_region, const idl_read *d_read, const BamBatchTotals *T,
                     uint32_t *seq2, uint32_t *seqn, uint32_t *ref2, uint32_t *refn)
 {
-	const long long *d_idx = (const long long*)b->scratch[1];
-	const uint32_t *d_slot_region = (const uint32_t*)b->scratch[2] + n_reads + 1;
+	idl_bam::ScratchSet &S = b->sets[T->scratch_set & 3u];
+	const long long *d_idx = (const long long*)S.p[1];
+	const uint32_t *d_slot_region = (const uint32_t*)S.p[2] + n_reads + 1;
 	if (n_reads) bam_pack_reads_kernel<<<(unsigned)((n_reads * 32 + 255) / 256), 256, 0, st>>>(b->d_out, b->R, d_idx, n_reads, d_read, d_slot_region, d_region, seq2, seqn);
 	if (n_regions) bam_pack_ref_kernel<<<(unsigned)((n_regions * 32 + 255) / 256), 256, 0, st>>>(b->d_ref_seq, n_regions, d_region, ref2, refn);
 	QCK(cudaGetLastError());
 	// guard words behind the pools (the kernels read up to two words past a record)
 	QCK(cudaMemsetAsync(seq2 + T->n_seq_bases / 16, 0, 16, st)); QCK(cudaMemsetAsync(seqn + T->n_seq_bases / 32, 0, 16, st));
 	QCK(cudaMemsetAsync(ref2 + T->n_ref_bases / 16, 0, 16, st)); QCK(cudaMemsetAsync(refn + T->n_ref_bases / 32, 0, 16, st));
+	QCK(cudaEventRecord(S.done, st));
 	return IDL_OK;
 #undef QCK
 }

@@ -10,6 +10,7 @@ struct BamBatchTotals {            // what the device reports after the records 
 	unsigned long long n_seq_bases, n_ref_bases;   // multiples of 64
 	unsigned max_trim_len, max_ref_len, max_region_reads, n_small_regions;
 	unsigned bad_index;                            // a read index outside the BAM's records, or a region on a target without a reference
+	unsigned scratch_set;                          // which of the BAM's scratch sets phase 1 used (phase 2 reads the indices from it)
 };
 
 // phase 1: region and read records (quality trim, windows, pool offsets) for the regions given as host arrays; d_region / d_read must

@@ -387,43 +387,157 @@ void idlh_vcf_status_counts(const idlh_vcf *w, uint64_t out[8]) { for (int i = 0
 char *idlh_vcf_dedup(const char *records) { return idlh_vcf_dedup_n(records, strlen(records), nullptr); }
 
 // the same over a buffer of `n` bytes that need not be terminated (the gathered shards of a multi-GPU run: tens of megabytes per
-// genome).  In place: lines are compared where they lie and the kept ones are moved down over the dropped ones, so nothing is
-// allocated; returns the new length.
+// genome).  In place: lines are compared where they lie and the kept ones are moved down over the dropped ones, so nothing but an
+// index of the dropped lines is allocated; returns the new length.
+//
+// The dedup is a two-key state machine over the lines in order (a line is dropped when its CHROM, POS, REF, ALT equal those of one of
+// the last two KEPT lines, src/indelope.nim:604-608) -- sequential by definition.  It is run on all host threads exactly:
+//   1. the buffer is cut at line ends into one chunk per thread; every chunk runs the machine from the EMPTY state and notes its drops;
+//   2. the chunks are stitched in order: chunk c is run again from the TRUE state the previous chunk ends in, side by side with the
+//      empty-state run, until both machines hold the same two lines in the same order -- from there on they agree for ever, so the
+//      rest of the chunk's phase-1 decisions stand (usually after two kept lines);
+//   3. the dropped lines are squeezed out, run by run.
+namespace {
+struct DdKey { const char *chrom, *pos, *ref, *alt; size_t lc, lp, lr, la; const char *line; };
+inline bool dd_same(const DdKey &x, const DdKey &y)
+{
+	return x.lp == y.lp && x.lc == y.lc && x.lr == y.lr && x.la == y.la && !memcmp(x.pos, y.pos, x.lp) && !memcmp(x.chrom, y.chrom, x.lc) &&
+	       !memcmp(x.ref, y.ref, x.lr) && !memcmp(x.alt, y.alt, x.la);
+}
+struct DdState { DdKey k1{}, k2{}; bool h1 = false, h2 = false; };
+// next line of [p, end): returns false at the end; *line / *le its bounds (no terminator), *key filled when the line has the six leading fields
+inline bool dd_next(const char *&p, const char *end, const char *&line, const char *&le, DdKey &k, bool &keyed)
+{
+	for (;;) {
+		if (p >= end) return false;
+		const char *e = (const char*)memchr(p, '\n', (size_t)(end - p));
+		le = e ? e : end; line = p; p = e ? e + 1 : end;
+		if (le == line) continue;   // empty lines vanish
+		break;
+	}
+	const char *f[6]; int nf = 0; f[nf++] = line;
+	for (const char *q = line; q < le && nf < 6; ) { const char *t = (const char*)memchr(q, '\t', (size_t)(le - q)); if (!t) break; f[nf++] = t + 1; q = t + 1; }
+	keyed = nf == 6;
+	if (keyed) {
+		k.chrom = f[0]; k.lc = (size_t)(f[1] - 1 - f[0]); k.pos = f[1]; k.lp = (size_t)(f[2] - 1 - f[1]);
+		k.ref = f[3]; k.lr = (size_t)(f[4] - 1 - f[3]); k.alt = f[4]; k.la = (size_t)(f[5] - 1 - f[4]); k.line = line;
+	}
+	return true;
+}
+// one step of the machine: true = the line is kept
+inline bool dd_step(DdState &S, const DdKey &k, bool keyed)
+{
+	if (!keyed) return true;   // a line without the fields is passed through and leaves the state alone
+	if ((S.h1 && dd_same(k, S.k1)) || (S.h2 && dd_same(k, S.k2))) return false;
+	S.k2 = S.k1; S.h2 = S.h1; S.k1 = k; S.h1 = true;
+	return true;
+}
+inline bool dd_converged(const DdState &a, const DdState &b) { return a.h1 && a.h2 && b.h1 && b.h2 && a.k1.line == b.k1.line && a.k2.line == b.k2.line; }
+} // namespace
+
 size_t idlh_vcf_dedup_inplace(char *records, size_t n)
 {
-	struct Key { const char *chrom, *pos, *ref, *alt; size_t lc, lp, lr, la; };
-	auto same = [](const Key &x, const Key &y) {
-		return x.lp == y.lp && x.lc == y.lc && x.lr == y.lr && x.la == y.la && !memcmp(x.pos, y.pos, x.lp) && !memcmp(x.chrom, y.chrom, x.lc) &&
-		       !memcmp(x.ref, y.ref, x.lr) && !memcmp(x.alt, y.alt, x.la);
-	};
-	char *o = records;
-	size_t w = 0;
-	Key last1{}, last2{}; bool have1 = false, have2 = false;
-	const char *p = records, *end = records + n;
-	while (p < end) {
-		const char *e = (const char*)memchr(p, '\n', (size_t)(end - p));
-		const char *le = e ? e : end;
-		const char *line = p;
-		p = e ? e + 1 : end;
-		if (le == line) continue;
-		// CHROM POS ID REF ALT ...
-		const char *f[6]; int nf = 0; f[nf++] = line;
-		for (const char *q = line; q < le && nf < 6; ) { const char *t = (const char*)memchr(q, '\t', (size_t)(le - q)); if (!t) break; f[nf++] = t + 1; q = t + 1; }
-		Key k{};
-		if (nf == 6) {
-			k.chrom = f[0]; k.lc = (size_t)(f[1] - 1 - f[0]); k.pos = f[1]; k.lp = (size_t)(f[2] - 1 - f[1]);
-			k.ref = f[3]; k.lr = (size_t)(f[4] - 1 - f[3]); k.alt = f[4]; k.la = (size_t)(f[5] - 1 - f[4]);
-			if ((have1 && same(k, last1)) || (have2 && same(k, last2))) continue;
-		}
-		const size_t ll = (size_t)(le - line);
-		if (o + w != line) memmove(o + w, line, ll); // (the keys of the last two kept lines lie below o + w: never overwritten)
-		if (nf == 6) {
-			const ptrdiff_t sh = (o + w) - line;
-			k.chrom += sh; k.pos += sh; k.ref += sh; k.alt += sh;
-			last2 = last1; have2 = have1; last1 = k; have1 = true;
-		}
-		w += ll; o[w++] = '\n';
+	const char *end = records + n;
+	int nt = pack_threads();
+	if (n < (1u << 20)) nt = 1;
+	// chunk starts at line starts
+	std::vector<const char*> cut((size_t)nt + 1, end);
+	cut[0] = records;
+	for (int c = 1; c < nt; ++c) {
+		const char *q = records + n / (size_t)nt * (size_t)c;
+		if (q < cut[(size_t)c - 1]) q = cut[(size_t)c - 1];
+		const char *e = q < end ? (const char*)memchr(q, '\n', (size_t)(end - q)) : nullptr;
+		cut[(size_t)c] = e ? e + 1 : end;
 	}
+	struct Span { const char *b, *e; };            // a dropped line (with its newline) or an empty line
+	std::vector<std::vector<Span>> drops((size_t)nt);
+	std::vector<DdState> final_state((size_t)nt);
+	auto run_chunk = [&](int c) {
+		DdState S; const char *p = cut[(size_t)c], *ce = cut[(size_t)c + 1];
+		const char *line, *le; DdKey k{}; bool keyed;
+		const char *expect = p;
+		while (dd_next(p, ce, line, le, k, keyed)) {
+			if (line != expect) drops[(size_t)c].push_back({expect, line});          // empty lines in front of this one
+			if (!dd_step(S, k, keyed)) drops[(size_t)c].push_back({line, p});
+			expect = p;
+		}
+		if (expect != ce) drops[(size_t)c].push_back({expect, ce});
+		final_state[(size_t)c] = S;
+	};
+	if (nt > 1) {
+		std::vector<std::thread> th;
+		for (int c = 1; c < nt; ++c) th.emplace_back(run_chunk, c);
+		run_chunk(0);
+		for (auto &x : th) x.join();
+	} else run_chunk(0);
+	// 2. stitch
+	DdState T = final_state[0];
+	for (int c = 1; c < nt; ++c) {
+		DdState L;   // the empty-state machine of phase 1, replayed
+		const char *p = cut[(size_t)c], *ce = cut[(size_t)c + 1];
+		const char *line, *le; DdKey k{}; bool keyed;
+		std::vector<Span> head; const char *expect = p; bool conv = false; const char *conv_at = ce;
+		while (dd_next(p, ce, line, le, k, keyed)) {
+			if (line != expect) head.push_back({expect, line});
+			dd_step(L, k, keyed);
+			if (!dd_step(T, k, keyed)) head.push_back({line, p});
+			expect = p;
+			if (dd_converged(T, L)) { conv = true; conv_at = p; break; }
+		}
+		if (conv) {
+			// phase-1 drops from the convergence point on stand; the ones before it are replaced by the stitched ones
+			std::vector<Span> &d = drops[(size_t)c];
+			size_t i = 0; while (i < d.size() && d[i].b < conv_at) ++i;
+			head.insert(head.end(), d.begin() + (long)i, d.end());
+			d.swap(head);
+			T = final_state[(size_t)c];
+		} else {
+			if (expect != ce) head.push_back({expect, ce});
+			drops[(size_t)c].swap(head);   // the whole chunk was decided by the stitched run; T already holds its final state
+		}
+	}
+	// 3. squeeze the dropped spans out (they are in address order).  Sequentially that is one pass of memmove over everything behind the first
+	// drop -- as long as the whole parse.  With threads: every chunk's kept runs are copied to their final offsets in a scratch buffer (the
+	// offsets follow from the drops before the chunk), then copied back, both in parallel.
+	size_t n_drops = 0;
+	for (auto &d : drops) n_drops += d.size();
+	size_t w = 0;
+	if (n_drops == 0) w = n;
+	else if (nt == 1) {
+		const char *src = records;
+		auto take = [&](const char *b, const char *e) { if (e > b) { if (records + w != b) memmove(records + w, b, (size_t)(e - b)); w += (size_t)(e - b); } };
+		for (const Span &d : drops[0]) { take(src, d.b); src = d.e; }
+		take(src, end);
+	} else {
+		std::vector<size_t> dst((size_t)nt + 1, 0);   // final offset of each chunk's first kept byte
+		for (int c = 0; c < nt; ++c) {
+			size_t dropped = 0;
+			for (const Span &d : drops[(size_t)c]) dropped += (size_t)(d.e - d.b);
+			dst[(size_t)c + 1] = dst[(size_t)c] + (size_t)(cut[(size_t)c + 1] - cut[(size_t)c]) - dropped;
+		}
+		w = dst[(size_t)nt];
+		int first = 0;
+		while (first < nt && drops[(size_t)first].empty()) ++first;   // chunks in front of the first drop stay where they are
+		const size_t base = dst[(size_t)first];
+		static thread_local std::vector<char> scratch;
+		if (scratch.size() < w - base) scratch.resize(w - base + (w - base) / 8);
+		char *const sp = scratch.data();   // (the workers must not name the thread_local themselves: they would see their own, empty one)
+		auto squeeze = [&](int c) {
+			char *o = sp + (dst[(size_t)c] - base);
+			const char *src = cut[(size_t)c];
+			for (const Span &d : drops[(size_t)c]) { if (d.b > src) { memcpy(o, src, (size_t)(d.b - src)); o += d.b - src; } src = d.e; }
+			if (cut[(size_t)c + 1] > src) memcpy(o, src, (size_t)(cut[(size_t)c + 1] - src));
+		};
+		auto back = [&](int c) { memcpy(records + dst[(size_t)c], sp + (dst[(size_t)c] - base), dst[(size_t)c + 1] - dst[(size_t)c]); };
+		for (int pass = 0; pass < 2; ++pass) {
+			std::vector<std::thread> th;
+			for (int c = first + 1; c < nt; ++c) { if (pass == 0) th.emplace_back(squeeze, c); else th.emplace_back(back, c); }
+			if (pass == 0) squeeze(first); else back(first);
+			for (auto &x : th) x.join();
+		}
+	}
+	// a kept last line without a newline gets one, as the sequential version wrote it
+	if (w && records[w - 1] != '\n') records[w++] = '\n';
 	return w;
 }
 

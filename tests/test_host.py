@@ -200,3 +200,49 @@ def test_header_matches_oracle():
     a = rois.arrays()
     assert rois.header() == orc.vcf_header(a["chrom_names"], [len(s) for s in a["chrom_seqs"]])
     assert rois.header().startswith("##fileformat=VCFv4.2\n") and rois.header().endswith("\tFORMAT\tsample\n")
+
+
+def _dedup_reference(data):
+    """src/indelope.nim:604-608 over record lines, the plain sequential way: drop a line whose CHROM, POS, REF, ALT equal those of one of the last two kept"""
+    out, last = [], []
+    for line in data.split(b"\n"):
+        if not line:
+            continue
+        f = line.split(b"\t")
+        if len(f) >= 6:
+            key = (f[0], f[1], f[3], f[4])
+            if key in last[-2:]:
+                continue
+            last = (last + [key])[-2:]
+        out.append(line + b"\n")
+    return b"".join(out)
+
+
+def test_parallel_dedup_equals_the_sequential_machine():
+    """idlh_vcf_dedup_inplace cuts the buffer into one chunk per thread and stitches the chunks exactly: streams with few distinct keys (long
+    interactions across the cuts: ...Y Z Y Z...), empty lines, lines without the fields, a last line without newline, any thread count"""
+    import ctypes
+    rng = np.random.default_rng(11)
+    for trial in range(12):
+        nkeys = int(rng.choice([2, 3, 4, 6, 50, 5000]))
+        n = int(rng.choice([40_000, 60_000]))
+        ks = rng.integers(0, nkeys, n)
+        lines = []
+        for i, k in enumerate(ks):
+            r = rng.random()
+            if r < 0.01:
+                lines.append(b"")
+            elif r < 0.02:
+                lines.append(b"# a line without the fields %d" % i)
+            else:
+                lines.append(b"chr%d\t%d\t.\t%s\t%s\t30\tPASS\tX=%d;pad=%s" % (k % 3, 100 + k, b"A" * (1 + k % 2), b"AC" * (1 + k % 5), i, b"p" * int(rng.integers(0, 40))))
+        data = b"\n".join(lines) + (b"" if trial % 3 == 0 else b"\n")
+        assert len(data) > (1 << 20)
+        want = _dedup_reference(data)
+        for threads in (1, 2, 3, 8, 16):
+            host.set_threads(threads)
+            buf = ctypes.create_string_buffer(data, len(data) + 2)
+            kept = host.dedup_inplace(ctypes.addressof(buf), len(data))
+            assert buf.raw[:kept] == want, (trial, nkeys, threads)
+    host.set_threads(0)
+    assert host.dedup_records(b"") == b"" and host.dedup_records(b"\n\n") == b""

@@ -770,6 +770,9 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 		for (auto &s : b->names) b->name_ptrs.push_back(s.c_str());
 		b->info.ref_name = b->name_ptrs.data(); b->info.ref_len = b->ref_len.data(); b->info.ref_first = b->ref_first.data();
 		b->info.header_text = b->header.c_str(); b->info.header_len = b->header.size();
+		// the compressed bytes are not needed any more: the resident footprint is the inflated stream + ~60 bytes per record
+		for (auto it = b->owned.begin(); it != b->owned.end(); ++it) if (*it == (void*)b->d_comp) { b->owned.erase(it); break; }
+		cudaFree(b->d_comp); b->d_comp = nullptr;
 		tw[5] = now();
 		if (timing)
 			fprintf(stderr, "idl_bam_open: member index %.1f ms, context %.1f ms, stream + allocations %.1f ms, h2d + inflate + header %.1f ms, boundaries %.1f ms, fields + cigars %.1f ms\n",

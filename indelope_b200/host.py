@@ -57,6 +57,9 @@ def lib():
         L.idlh_load.restype = C.c_void_p
         L.idlh_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
         L.idlh_load_region.restype = C.c_void_p
+        L.idlh_load_fasta.restype = C.c_void_p
+        L.idlh_load_fasta.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+        L.idlh_dataset_set_targets.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), i64p, C.c_char_p, C.c_size_t]
         L.idlh_load_region.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.c_int64, C.c_char_p, C.c_size_t]
         L.idlh_write_fasta.argtypes = [C.c_void_p, C.c_char_p]
         L.idlh_write_bam.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
@@ -175,6 +178,34 @@ class Dataset:
         if not h:
             raise IOError(err.value.decode())
         return cls(_handle=h)
+
+    @classmethod
+    def load_fasta(cls, fasta):
+        """the reference sequences alone (the BAM is decoded on the device: cuda.Bam)"""
+        err = C.create_string_buffer(512)
+        h = lib().idlh_load_fasta(str(fasta).encode(), err, 512)
+        if not h:
+            raise IOError(err.value.decode())
+        return cls(_handle=h)
+
+    def set_targets(self, names, lengths):
+        """order the sequences as a BAM header lists its targets (same checks and messages as Dataset.load)"""
+        n = len(names)
+        arr = (C.c_char_p * n)(*[s.encode() for s in names])
+        lens = np.ascontiguousarray(lengths, dtype=np.int64)
+        err = C.create_string_buffer(512)
+        if lib().idlh_dataset_set_targets(self.h, n, arr, lens.ctypes.data_as(i64p), err, 512) != 0:
+            raise IOError(err.value.decode())
+        c = (C.c_int64 * 4)()
+        lib().idlh_dataset_counts(self.h, c)
+        self.n_reads, self.n_bases, self.n_events, self.n_chroms = list(c)
+
+    def sequences(self):
+        """(names, sequences as uint8 arrays): views of the dataset's memory -- keep the dataset alive"""
+        r = Rois(lib().idlh_sweep(self.h, 255, 1 << 30, 1 << 30), self)   # no regions: just the views
+        a = r.arrays()
+        self._seq_owner = r
+        return a["chrom_names"], a["chrom_seqs"]
 
     def write_fasta(self, path):
         """FASTA (60 columns) + path.fai"""

@@ -187,6 +187,34 @@ def test_cli_gpu_decode_gives_the_same_vcf(files):
     assert r.stdout == rois.header() + ovcf
 
 
+@pytest.mark.gpu
+def test_api_call_bam_equals_the_cli_and_the_oracle(files):
+    """api.call_bam: the in-process twin of `indelope --gpu-decode` (several small batches in flight)"""
+    from indelope_b200 import api
+    ds, fa, bam = files
+    rois = ds.sweep(min_reads=5)
+    _, ovcf, cnt = orc.call(rois.arrays(), dump_level=0, **CALL)
+    assert api.call_bam(fa, bam, max_reads=3000, **CALL) == rois.header() + ovcf
+
+
+def test_fasta_only_dataset_and_target_order(files, tmp_path):
+    """idlh_load_fasta + idlh_dataset_set_targets: what the device path keeps of the host reader -- the sequences, ordered as the BAM header lists them"""
+    ds, fa, bam = files
+    ref = host.Dataset.load_fasta(fa)
+    names, seqs = ref.sequences()
+    assert names == ["chrS1", "chrS2"] and [len(s) for s in seqs] == [120_000, 120_000]
+    second = bytes(seqs[1][:50])   # (the views die with the reordering)
+    ref.set_targets(["chrS2", "chrS1"], [120_000, 120_000])
+    n2, s2 = ref.sequences()
+    assert n2 == ["chrS2", "chrS1"] and bytes(s2[0][:50]) == second
+    with pytest.raises(IOError, match="not in the FASTA"):
+        host.Dataset.load_fasta(fa).set_targets(["chrX"], [10])
+    with pytest.raises(IOError, match="different length"):
+        host.Dataset.load_fasta(fa).set_targets(["chrS1"], [5])
+    with pytest.raises(IOError):
+        host.Dataset.load_fasta(str(tmp_path / "missing.fa"))
+
+
 def _parse_bai(path):
     """the index as the SAM specification lays it out (5.2), read with struct alone"""
     b = open(path, "rb").read()

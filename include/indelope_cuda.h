@@ -330,6 +330,19 @@ typedef struct idl_bam_info {
 } idl_bam_info;
 
 int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **bam, char *err, size_t errlen);
+
+/* The same for ONE TARGET of a file that does not fit in device memory as a whole: <members> is a run of whole BGZF members from the middle of the
+ * file that holds the target's records (the index <bam>.bai says where: libindelope_host's idlh_bai_target_span), the header comes from the caller.
+ * The record chain starts at first_record (an offset into the inflated bytes of the run: the low 16 bits of the virtual offset of the target's first
+ * record) and ends end_offset bytes into the member that starts end_member bytes into the run (end_member == len, end_offset == 0: at the end of the
+ * run) -- what lies in front of and behind them belongs to the neighbouring targets.  Everything else as after idl_bam_open; record indices count
+ * from the first record of the run. */
+typedef struct idl_bam_slice {
+	int32_t n_ref; const char *const *ref_name; const int64_t *ref_len;   /* the targets of the file's header */
+	uint64_t first_record;
+	uint64_t end_member, end_offset;
+} idl_bam_slice;
+int idl_bam_open_slice(int device, const uint8_t *members, size_t len, const idl_bam_slice *slice, idl_bam **bam, char *err, size_t errlen);
 const idl_bam_info *idl_bam_get_info(const idl_bam *bam);
 void idl_bam_close(idl_bam *bam);
 

@@ -128,6 +128,10 @@ const char *idlh_dataset_chrom_name(const idlh_dataset *d, int32_t chrom);
 /* the device reads the BAM (idl_bam_open of indelope_cuda.h); the host keeps the reference sequences and turns what idl_bam_sweep / idl_bam_fetch
  * return into the idlh_rois that idlh_pack and idlh_vcf_records take */
 idlh_dataset *idlh_load_fasta(const char *fasta_path, char *err, size_t errlen);
+/* where one target's records lie in the file, from <bam>.bai: the run of whole BGZF members [*file_begin, *file_end) and the start / end of the record
+ * chain inside it as idl_bam_open_slice takes them; 0 ok, 1 the index lists no record for the target, -1 error */
+int idlh_bai_target_span(const char *bam_path, int32_t target, uint64_t *file_begin, uint64_t *file_end, uint64_t *first_record, uint64_t *end_member,
+                         uint64_t *end_offset, char *err, size_t errlen);
 int idlh_dataset_set_targets(idlh_dataset *d, int32_t n_ref, const char *const *ref_name, const int64_t *ref_len, char *err, size_t errlen);
 idlh_rois *idlh_rois_from_arrays(const idlh_dataset *d, int64_t n_reads, const int32_t *start, const int32_t *stop, const int32_t *len, const uint8_t *mapq, const uint16_t *flag,
                                  const int64_t *seq_off, const uint8_t *bases, const uint8_t *quals, int64_t n_rois, const int32_t *roi_chrom, const int32_t *roi_start,

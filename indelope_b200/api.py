@@ -110,50 +110,77 @@ class Caller:
         self.ctx.close()
 
 
-def call_bam(fasta, bam, device=0, min_reads=3, min_ctg_len=73, min_event_len=4, max_reads=400_000, host_pack=False, timings=None, **kw):
+def call_bam(fasta, bam, device=0, min_reads=3, min_ctg_len=73, min_event_len=4, max_reads=400_000, by_target=False, timings=None, **kw):
     """`indelope --gpu-decode [options] <fasta> <bam>` in process: the VCF (header + records) with everything in front of callsemble on the
     device as well -- BGZF inflate and record parse (idl_bam_open), gen_roi per target (idl_bam_sweep, src/indelope.nim:515-545,601-602), the
-    batches built from the resident records (idl_bam_submit).  The host reads the two files and writes the VCF text."""
-    ref = host.Dataset.load_fasta(fasta)
-    data = open(bam, "rb").read()
-    b = cuda.Bam(data, device=device)
-    try:
-        ref.set_targets(b.ref_names, b.ref_len)
+    batches built from the resident records (idl_bam_submit).  The host reads the two files and writes the VCF text.
+    by_target: the file is not decoded as a whole but target by target, each from the run of BGZF members <bam>.bai points to
+    (idl_bam_open_slice) -- for files that do not fit in device memory; needs the index."""
+    if by_target:
+        st = host.Stream(fasta, bam)          # parses the BAM header and orders the FASTA's sequences after it; no record is read through it
+        tg = st.targets()
+        ta = tg.arrays()
+        names, seqs = ta["chrom_names"], ta["chrom_seqs"]
+        ref_len = [len(x) for x in seqs]
+        keep = (st, tg)
+    else:
+        ref = host.Dataset.load_fasta(fasta)
+        data = open(bam, "rb").read()
+        whole = cuda.Bam(data, device=device)
+        ref.set_targets(whole.ref_names, whole.ref_len)
         names, seqs = ref.sequences()
-        chrom, rs, re, nr, idx = [], [], [], [], []
-        for c, name in enumerate(b.ref_names):
+        keep = (ref,)
+    caller = Caller(device, min_reads=min_reads, min_ctg_len=min_ctg_len, min_event_len=min_event_len, **kw)
+    writer = host.VcfWriter()
+    empty = dict(start=[], stop=[], mapq=[], flag=[], len=[], seq_off=[], bases=[], quals=[])
+    out = [host.Rois(arrays=dict(empty, roi_chrom=[], roi_start=[], roi_stop=[], roi_read_begin=[], roi_n_reads=[], read_idx=[], chrom_names=names, chrom_seqs=seqs)).header()]
+    n_regions_done = 0
+    try:
+        for c, name in enumerate(names):
             if name == "hs37d5" or name.startswith("GL"):   # skippable targets, src/indelope.nim:41-42
                 continue
-            r = b.sweep(c, min_event_support=max(3, min_reads - 2), min_read_coverage=min_reads, max_read_coverage=600)
-            chrom.append(np.full(len(r["roi_start"]), c, np.int32)); rs.append(r["roi_start"]); re.append(r["roi_end"]); nr.append(r["roi_n_reads"]); idx.append(r["read_idx"])
-        cat = lambda xs, t: np.concatenate(xs).astype(t) if xs else np.zeros(0, t)
-        chrom, rs, re, nr, idx = cat(chrom, np.int32), cat(rs, np.int32), cat(re, np.int32), cat(nr, np.int32), cat(idx, np.int64)
-        begin = np.concatenate([[0], np.cumsum(nr)]).astype(np.int64)
-        empty = dict(start=[], stop=[], mapq=[], flag=[], len=[], seq_off=[], bases=[], quals=[])
-        rois = host.Rois(arrays=dict(empty, roi_chrom=chrom, roi_start=rs, roi_stop=re, roi_read_begin=begin[:-1], roi_n_reads=nr, read_idx=idx, chrom_names=names, chrom_seqs=seqs))
-        for c in sorted(set(chrom.tolist())):
-            b.set_reference(c, seqs[c])
-        caller = Caller(device, min_reads=min_reads, min_ctg_len=min_ctg_len, min_event_len=min_event_len, **kw)
-        try:
-            writer = host.VcfWriter()
-            out, inflight = [rois.header()], []
+            if by_target:
+                sp = host.bai_target_span(bam, c)
+                if sp is None:
+                    continue
+                with open(bam, "rb") as f:
+                    f.seek(sp["file_begin"]); run = f.read(sp["file_end"] - sp["file_begin"])
+                b = cuda.Bam(run, device=device, slice=dict(ref_names=names, ref_len=ref_len, first_record=sp["first_record"], end_member=sp["end_member"],
+                                                            end_offset=sp["end_offset"]))
+            else:
+                b = whole
+            try:
+                r = b.sweep(c, min_event_support=max(3, min_reads - 2), min_read_coverage=min_reads, max_read_coverage=600)
+                n = len(r["roi_start"])
+                if n == 0:
+                    continue
+                chrom = np.full(n, c, np.int32); rs, re, nr, idx = r["roi_start"], r["roi_end"], r["roi_n_reads"], r["read_idx"]
+                begin = np.concatenate([[0], np.cumsum(nr)]).astype(np.int64)
+                rois = host.Rois(arrays=dict(empty, roi_chrom=chrom, roi_start=rs, roi_stop=re, roi_read_begin=begin[:-1], roi_n_reads=nr, read_idx=idx, chrom_names=names, chrom_seqs=seqs))
+                b.set_reference(c, seqs[c])
+                inflight = []
 
-            def drain():
-                lo, t = inflight.pop(0)
-                res = caller.ctx.wait(t)
-                v, _ = writer.records(rois, lo, caller.params, res, 0)
-                if timings is not None:
-                    timings.append({k: getattr(res.contents, k) for k in ("ms_assemble", "ms_align", "ms_genotype", "ms_al", "n_regions", "n_events")})
-                caller.ctx.release(t); out.append(v)
-            for lo, hi in plan_batches(rois, 0, rois.n_rois, max_reads=max_reads):
-                if len(inflight) >= caller.params.n_streams:
+                def drain():
+                    lo, t = inflight.pop(0)
+                    res = caller.ctx.wait(t)
+                    v, _ = writer.records(rois, lo, caller.params, res, 0)
+                    if timings is not None:
+                        timings.append({k: getattr(res.contents, k) for k in ("ms_assemble", "ms_align", "ms_genotype", "ms_al", "n_regions", "n_events")})
+                    caller.ctx.release(t); out.append(v)
+                for lo, hi in plan_batches(rois, 0, n, max_reads=max_reads):
+                    if len(inflight) >= caller.params.n_streams:
+                        drain()
+                    inflight.append((lo, caller.ctx.bam_submit(b, chrom[lo:hi], rs[lo:hi], re[lo:hi], nr[lo:hi], idx[begin[lo]:begin[hi]], ordinal_base=n_regions_done + lo)))
+                while inflight:
                     drain()
-                inflight.append((lo, caller.ctx.bam_submit(b, chrom[lo:hi], rs[lo:hi], re[lo:hi], nr[lo:hi], idx[begin[lo]:begin[hi]], ordinal_base=lo)))
-            while inflight:
-                drain()
-            caller.status_counts = writer.status_counts()
-        finally:
-            caller.close()
+                n_regions_done += n
+            finally:
+                if by_target:
+                    b.close()
+        caller.status_counts = writer.status_counts()
     finally:
-        b.close()
+        caller.close()
+        if not by_target:
+            whole.close()
+    del keep
     return "".join(out)

@@ -527,7 +527,20 @@ void idl_bam_close(idl_bam *b)
 
 const idl_bam_info *idl_bam_get_info(const idl_bam *b) { return b ? &b->info : nullptr; }
 
+static int bam_open_impl(int device, const uint8_t *file, size_t file_len, const idl_bam_slice *slice, idl_bam **out, char *err, size_t errlen);
+
 int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out, char *err, size_t errlen)
+{
+	return bam_open_impl(device, file, file_len, nullptr, out, err, errlen);
+}
+
+int idl_bam_open_slice(int device, const uint8_t *members, size_t len, const idl_bam_slice *slice, idl_bam **out, char *err, size_t errlen)
+{
+	if (!slice || slice->n_ref < 0 || (slice->n_ref && (!slice->ref_name || !slice->ref_len))) return IDL_E_ARG;
+	return bam_open_impl(device, members, len, slice, out, err, errlen);
+}
+
+static int bam_open_impl(int device, const uint8_t *file, size_t file_len, const idl_bam_slice *slice, idl_bam **out, char *err, size_t errlen)
 {
 	if (!out || (!file && file_len)) return IDL_E_ARG;
 	*out = nullptr;
@@ -536,7 +549,7 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_err(err, errlen, "no CUDA device (idl_bam_open has no CPU path)"); return IDL_E_NO_DEVICE; }
 	if (device < 0 || device >= ndev) return IDL_E_ARG;
 	// 1. members
-	std::vector<Member> members; size_t total = 0;
+	std::vector<Member> members; std::vector<size_t> member_at; size_t total = 0;
 	for (size_t at = 0; at < file_len;) {
 		if (file_len - at < 18) { set_err(err, errlen, "truncated BGZF header"); return IDL_E_FORMAT; }
 		const uint8_t *h = file + at;
@@ -555,10 +568,10 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 		const uint32_t usize = h32(h + csize - 4);
 		if (usize > 65536) { set_err(err, errlen, "BGZF block larger than 64 KiB"); return IDL_E_FORMAT; }
 		Member M; M.in_off = at + 12 + xlen; M.in_len = (uint32_t)(csize - 12 - xlen - 8); M.out_off = total; M.out_len = usize; M.crc = h32(h + csize - 8); M.pad = 0;
-		members.push_back(M);
+		members.push_back(M); member_at.push_back(at);
 		total += usize; at += csize;
 	}
-	if (members.empty() || total < 12) { set_err(err, errlen, "not a BAM file"); return IDL_E_FORMAT; }
+	if (members.empty() || (!slice && total < 12)) { set_err(err, errlen, "not a BAM file"); return IDL_E_FORMAT; }
 	if (members.size() >= (1ull << 32)) return IDL_E_CAPACITY;
 	// IDL_BAM_TIMING=1: wall-clock phases of the call on stderr (context creation and allocations are not inside the CUDA events)
 	const bool timing = getenv("IDL_BAM_TIMING") != nullptr;
@@ -641,31 +654,51 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 			snprintf(msg, sizeof msg, "BGZF block %llu failed to inflate (corrupt data or CRC mismatch: %s)", herr[0] >> 8, inf_error_text((int)(herr[0] & 0xff)));
 			BFAIL(msg);
 		}
-		if (memcmp(head.data(), "BAM\1", 4) != 0) BFAIL("not a BAM file");
-		size_t at = 4;
-		const uint32_t l_text = h32(head.data() + at); at += 4;
-		auto need = [&](size_t upto) -> bool {   // make head[0..upto) available
-			if (upto > total) return false;
-			if (upto <= head.size()) return true;
-			const size_t old = head.size(); head.resize(std::min(total, std::max(upto, old * 2)));
-			return cudaMemcpy(head.data() + old, b->d_out + old, head.size() - old, cudaMemcpyDeviceToHost) == cudaSuccess;
-		};
-		if (!need(at + (size_t)l_text + 4)) BFAIL("truncated BAM header");
-		b->header.assign((const char*)head.data() + at, l_text); at += l_text;
-		const uint32_t n_ref = h32(head.data() + at); at += 4;
-		if (n_ref > (1u << 24)) BFAIL("truncated BAM reference list");
-		std::vector<int32_t> ref_len32;
-		for (uint32_t r = 0; r < n_ref; ++r) {
-			if (!need(at + 4)) BFAIL("truncated BAM reference list");
-			const uint32_t l_name = h32(head.data() + at); at += 4;
-			if (l_name == 0 || !need(at + (size_t)l_name + 4)) BFAIL("truncated BAM reference list");
-			b->names.emplace_back((const char*)head.data() + at, l_name - 1); at += l_name;
-			const uint32_t l_ref = h32(head.data() + at); at += 4;
-			b->ref_len.push_back((int64_t)l_ref); ref_len32.push_back((int32_t)std::min<uint32_t>(l_ref, INT_MAX));
+		uint32_t n_ref = 0; std::vector<int32_t> ref_len32; size_t begin = 0, rec_total = total;
+		if (!slice) {
+			if (memcmp(head.data(), "BAM\1", 4) != 0) BFAIL("not a BAM file");
+			size_t at = 4;
+			const uint32_t l_text = h32(head.data() + at); at += 4;
+			auto need = [&](size_t upto) -> bool {   // make head[0..upto) available
+				if (upto > total) return false;
+				if (upto <= head.size()) return true;
+				const size_t old = head.size(); head.resize(std::min(total, std::max(upto, old * 2)));
+				return cudaMemcpy(head.data() + old, b->d_out + old, head.size() - old, cudaMemcpyDeviceToHost) == cudaSuccess;
+			};
+			if (!need(at + (size_t)l_text + 4)) BFAIL("truncated BAM header");
+			b->header.assign((const char*)head.data() + at, l_text); at += l_text;
+			n_ref = h32(head.data() + at); at += 4;
+			if (n_ref > (1u << 24)) BFAIL("truncated BAM reference list");
+			for (uint32_t r = 0; r < n_ref; ++r) {
+				if (!need(at + 4)) BFAIL("truncated BAM reference list");
+				const uint32_t l_name = h32(head.data() + at); at += 4;
+				if (l_name == 0 || !need(at + (size_t)l_name + 4)) BFAIL("truncated BAM reference list");
+				b->names.emplace_back((const char*)head.data() + at, l_name - 1); at += l_name;
+				const uint32_t l_ref = h32(head.data() + at); at += 4;
+				b->ref_len.push_back((int64_t)l_ref); ref_len32.push_back((int32_t)std::min<uint32_t>(l_ref, INT_MAX));
+			}
+			begin = at;   // the first alignment record
+		} else {
+			// a run of members from the middle of a file (one target's records, found through the index): the header comes from the caller, the
+			// records start at first_record and end at end_offset bytes into the member that starts end_member bytes into the run
+			n_ref = (uint32_t)slice->n_ref;
+			for (uint32_t r = 0; r < n_ref; ++r) {
+				b->names.emplace_back(slice->ref_name[r]); b->ref_len.push_back(slice->ref_len[r]);
+				ref_len32.push_back((int32_t)std::min<int64_t>(std::max<int64_t>(slice->ref_len[r], 0), INT_MAX));
+			}
+			begin = (size_t)slice->first_record;
+			if (slice->end_member == file_len && slice->end_offset == 0) rec_total = total;
+			else {
+				const auto it = std::lower_bound(member_at.begin(), member_at.end(), (size_t)slice->end_member);
+				if (it == member_at.end() || *it != (size_t)slice->end_member) BFAIL("the slice's end does not lie on a BGZF member of the run");
+				const Member &M = members[(size_t)(it - member_at.begin())];
+				if (slice->end_offset > M.out_len) BFAIL("the slice's end lies outside its member");
+				rec_total = (size_t)M.out_off + (size_t)slice->end_offset;
+			}
+			if (begin > rec_total) BFAIL("the slice's first record lies behind its end");
 		}
-		const size_t begin = at;   // the first alignment record
 		// 3. record boundaries
-		const size_t span = total - begin;
+		const size_t span = rec_total - begin;
 		const uint32_t n_seg = (uint32_t)((span + SEG_BYTES - 1) / SEG_BYTES);
 		int32_t *&d_ref_len = b->d_ref_len; long long *d_first = nullptr, *d_exit = nullptr, *d_preset = nullptr; uint32_t *d_count = nullptr, *d_bad = nullptr, *d_which = nullptr;
 		unsigned long long *d_rec_base = nullptr;
@@ -678,7 +711,7 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 		if (n_seg) {
 			preset[0] = (long long)begin;
 			BCK(cudaMemcpyAsync(d_preset, preset.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
-			bam_seg_kernel<<<(n_seg * 32 + 255) / 256, 256, 0, st>>>(b->d_out, total, begin, n_seg, nullptr, 0, (int32_t)n_ref, d_ref_len, d_preset, d_first, d_exit, d_count, d_bad);
+			bam_seg_kernel<<<(n_seg * 32 + 255) / 256, 256, 0, st>>>(b->d_out, rec_total, begin, n_seg, nullptr, 0, (int32_t)n_ref, d_ref_len, d_preset, d_first, d_exit, d_count, d_bad);
 			BCK(cudaGetLastError());
 			auto fetch = [&]() -> cudaError_t {
 				cudaError_t e = cudaMemcpyAsync(first.data(), d_first, (size_t)n_seg * 8, cudaMemcpyDeviceToHost, st);
@@ -693,7 +726,7 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 			// `expect` is walked again from there (one small launch each; guesses are almost never wrong)
 			size_t expect = begin;
 			for (uint32_t k = 0; k < n_seg; ++k) {
-				const size_t s0 = begin + (size_t)k * SEG_BYTES, s1 = std::min(total, s0 + SEG_BYTES);
+				const size_t s0 = begin + (size_t)k * SEG_BYTES, s1 = std::min(rec_total, s0 + SEG_BYTES);
 				const long long want = expect < s1 ? (long long)expect : -1;   // -1: a record spans the whole segment
 				if (first[k] != want) {
 					++b->info.boundary_fixups;
@@ -701,7 +734,7 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 					const uint32_t which = k;
 					BCK(cudaMemcpyAsync(d_preset + k, &preset[k], 8, cudaMemcpyHostToDevice, st));
 					BCK(cudaMemcpyAsync(d_which, &which, 4, cudaMemcpyHostToDevice, st));
-					bam_seg_kernel<<<1, 32, 0, st>>>(b->d_out, total, begin, n_seg, d_which, 1, (int32_t)n_ref, d_ref_len, d_preset, d_first, d_exit, d_count, d_bad);
+					bam_seg_kernel<<<1, 32, 0, st>>>(b->d_out, rec_total, begin, n_seg, d_which, 1, (int32_t)n_ref, d_ref_len, d_preset, d_first, d_exit, d_count, d_bad);
 					BCK(cudaGetLastError());
 					BCK(cudaMemcpyAsync(&first[k], d_first + k, 8, cudaMemcpyDeviceToHost, st)); BCK(cudaMemcpyAsync(&exitv[k], d_exit + k, 8, cudaMemcpyDeviceToHost, st));
 					BCK(cudaMemcpyAsync(&count[k], d_count + k, 4, cudaMemcpyDeviceToHost, st)); BCK(cudaMemcpyAsync(&bad[k], d_bad + k, 4, cudaMemcpyDeviceToHost, st));
@@ -713,7 +746,7 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 				}
 				n_all += count[k];
 			}
-			if (expect != total) BFAIL("truncated BAM record");
+			if (expect != rec_total) BFAIL("truncated BAM record");
 		}
 		tw[4] = now();
 		if (n_all >= (1ull << 31)) { rc = IDL_E_CAPACITY; why = "more than 2^31 records"; goto done; }
@@ -732,7 +765,7 @@ int idl_bam_open(int device, const uint8_t *file, size_t file_len, idl_bam **out
 			BALLOC(d_ref_first, ((size_t)n_ref + 1) * 8); BALLOC(d_tot, nt * 8);
 			BCK(cudaMemsetAsync(d_err, 0xff, 64, st));
 			if (n_all) {
-				bam_offsets_kernel<<<(n_seg * 32 + 255) / 256, 256, 0, st>>>(b->d_out, total, begin, n_seg, d_first, d_rec_base, b->d_rec_off);
+				bam_offsets_kernel<<<(n_seg * 32 + 255) / 256, 256, 0, st>>>(b->d_out, rec_total, begin, n_seg, d_first, d_rec_base, b->d_rec_off);
 				bam_fields_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(b->d_out, b->d_rec_off, n_all, (int32_t)n_ref, b->R, d_err);
 				bam_order_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(b->R.ref_id, b->R.pos, n_all, d_err + 1, d_err + 2);
 			}
@@ -791,6 +824,15 @@ int idl_bam_sweep(idl_bam *b, int32_t target, int32_t min_event_support, int32_t
 	if (!b || !out || target < 0 || target >= b->info.n_ref) return IDL_E_ARG;
 	const size_t r0 = (size_t)b->ref_first[(size_t)target], r1 = (size_t)b->ref_first[(size_t)target + 1];
 	if (b->ref_len[(size_t)target] > INT_MAX) return IDL_E_CAPACITY;
+	if (r1 == r0 && !(flags & IDL_SWEEP_EVIDENCE)) {
+		// a target without records has no regions (a header with thousands of alt / decoy contigs): nothing to launch
+		idl_sweep_out *o = (idl_sweep_out*)calloc(1, sizeof *o);
+		if (!o) return IDL_E_NOMEM;
+		o->roi_start = (int32_t*)malloc(16); o->roi_end = (int32_t*)malloc(16); o->roi_read_begin = (int64_t*)malloc(16); o->roi_n_reads = (int32_t*)malloc(16);
+		o->read_idx = (int64_t*)malloc(16);
+		*out = o;
+		return IDL_OK;
+	}
 	idl_sweep_in in; memset(&in, 0, sizeof in);
 	in.chrom_len = (int32_t)b->ref_len[(size_t)target]; in.n_reads = r1 - r0;
 	in.start = b->R.pos + r0; in.stop = b->R.stop + r0; in.flag = b->R.flag + r0; in.cigar = b->d_cigar; in.cig_off = (const uint64_t*)(b->d_cig_off + r0);

@@ -359,6 +359,55 @@ int idlh_write_bam(const idlh_dataset *d, const char *path, int level)
 
 /* reference FASTA + coordinate-sorted BAM -> dataset.  Records without a reference id are dropped (a per-target query never
  * returns them); everything else, flags included, is kept for the sweep's `skippable` test (src/indelope.nim:40-47). */
+/* Where the records of one target lie in the BAM file, from <bam>.bai (SAM spec 5.2): the smallest chunk begin and the largest chunk end of the target's
+ * bins are the virtual offsets of its first record and of the byte behind its last one.  [*file_begin, *file_end) is the run of whole BGZF members that
+ * holds them, *first_record the offset of the first record inside the inflated bytes of that run, (*end_member, *end_offset) the end as idl_bam_open_slice
+ * takes it.  Returns 0, 1 when the index lists no record for the target, -1 on error. */
+int idlh_bai_target_span(const char *bam_path, int32_t target, uint64_t *file_begin, uint64_t *file_end, uint64_t *first_record, uint64_t *end_member,
+                         uint64_t *end_offset, char *err, size_t errlen)
+{
+	std::vector<uint8_t> bai; std::string why;
+	if (!read_file((std::string(bam_path) + ".bai").c_str(), bai, why)) { set_err(err, errlen, why + " (no index: write one with idlh_write_bam or samtools index)"); return -1; }
+	if (bai.size() < 8 || memcmp(bai.data(), "BAI\1", 4) != 0) { set_err(err, errlen, "not a BAI index"); return -1; }
+	size_t ia = 4;
+	auto rd32 = [&](uint32_t &x) -> bool { if (ia + 4 > bai.size()) return false; x = le32(bai.data() + ia); ia += 4; return true; };
+	auto rd64 = [&](uint64_t &x) -> bool { if (ia + 8 > bai.size()) return false; x = (uint64_t)le32(bai.data() + ia) | (uint64_t)le32(bai.data() + ia + 4) << 32; ia += 8; return true; };
+	uint32_t n_ref = 0;
+	if (!rd32(n_ref)) { set_err(err, errlen, "truncated index"); return -1; }
+	if (target < 0 || (uint32_t)target >= n_ref) { set_err(err, errlen, "the index has no such target"); return -1; }
+	uint64_t vmin = ~0ULL, vmax = 0;
+	for (uint32_t r = 0; r <= (uint32_t)target; ++r) {
+		uint32_t n_bin = 0;
+		if (!rd32(n_bin)) { set_err(err, errlen, "truncated index"); return -1; }
+		for (uint32_t b = 0; b < n_bin; ++b) {
+			uint32_t bin = 0, n_chunk = 0;
+			if (!rd32(bin) || !rd32(n_chunk)) { set_err(err, errlen, "truncated index"); return -1; }
+			for (uint32_t c = 0; c < n_chunk; ++c) {
+				uint64_t a = 0, z = 0;
+				if (!rd64(a) || !rd64(z)) { set_err(err, errlen, "truncated index"); return -1; }
+				if (r == (uint32_t)target && bin != 37450u) { vmin = std::min(vmin, a); vmax = std::max(vmax, z); }   // 37450: the metadata pseudo-bin of samtools
+			}
+		}
+		uint32_t n_intv = 0;
+		if (!rd32(n_intv)) { set_err(err, errlen, "truncated index"); return -1; }
+		ia += (size_t)n_intv * 8;
+	}
+	if (vmin == ~0ULL || vmax <= vmin) return 1;
+	*file_begin = vmin >> 16; *first_record = vmin & 0xffff;
+	const uint64_t ce = vmax >> 16, ue = vmax & 0xffff;
+	*end_member = ce - *file_begin; *end_offset = ue;
+	if (ue == 0) { *file_end = ce; return 0; }
+	// the member the records end in is part of the run: its size is in its own header
+	FILE *f = fopen(bam_path, "rb");
+	if (!f) { set_err(err, errlen, std::string("cannot open ") + bam_path); return -1; }
+	uint8_t h[18];
+	const bool ok = fseek(f, (long)ce, SEEK_SET) == 0 && fread(h, 1, 18, f) == 18 && h[0] == 0x1f && h[1] == 0x8b && h[12] == 'B' && h[13] == 'C';
+	fclose(f);
+	if (!ok) { set_err(err, errlen, "the index points between BGZF blocks"); return -1; }
+	*file_end = ce + (uint64_t)le16(h + 16) + 1;
+	return 0;
+}
+
 /* the reference sequences alone (the device reads the BAM: idl_bam_open) */
 idlh_dataset *idlh_load_fasta(const char *fasta_path, char *err, size_t errlen)
 {

@@ -47,7 +47,7 @@ def lib():
 
 EXPORTS = ("idl_default_params idl_create idl_destroy idl_batch_alloc idl_batch_free idl_submit idl_upload idl_run_resident idl_wait "
            "idl_release idl_strerror idl_last_cuda_error idl_device_count idl_ksw2_batch idl_sweep idl_sweep_free "
-           "idl_bam_open idl_bam_get_info idl_bam_close idl_bam_sweep idl_bam_fetch idl_bam_reads_free idl_bam_set_reference idl_bam_submit idl_bam_pack").split()
+           "idl_bam_open idl_bam_get_info idl_bam_close idl_bam_sweep idl_bam_fetch idl_bam_reads_free idl_bam_set_reference idl_bam_submit idl_bam_pack idl_bam_open_slice").split()
 
 
 class SweepIn(C.Structure):
@@ -106,11 +106,18 @@ class BamReads(C.Structure):
 BAM_SEQ, BAM_CIGAR = 1, 2
 
 
-class Bam:
-    """idl_bam_*: a BAM file inflated and parsed on the GPU.  `data` = the file's bytes."""
+class BamSlice(C.Structure):
+    _fields_ = [("n_ref", C.c_int32), ("ref_name", C.POINTER(C.c_char_p)), ("ref_len", C.POINTER(C.c_int64)), ("first_record", C.c_uint64), ("end_member", C.c_uint64),
+                ("end_offset", C.c_uint64)]
 
-    def __init__(self, data, device=0):
+
+class Bam:
+    """idl_bam_*: a BAM file inflated and parsed on the GPU.  `data` = the file's bytes, or -- with `slice` = dict(ref_names, ref_len,
+    first_record, end_member, end_offset) -- a run of whole BGZF members holding one target's records (idl_bam_open_slice; host.bai_target_span)."""
+
+    def __init__(self, data, device=0, slice=None):
         L = lib()
+        L.idl_bam_open_slice.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(BamSlice), C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
         L.idl_bam_open.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
         L.idl_bam_get_info.argtypes = [C.c_void_p]; L.idl_bam_get_info.restype = C.POINTER(BamInfo)
         L.idl_bam_close.argtypes = [C.c_void_p]
@@ -120,7 +127,14 @@ class Bam:
         L.idl_bam_reads_free.argtypes = [C.POINTER(BamReads)]
         self.h = C.c_void_p()
         err = C.create_string_buffer(512)
-        rc = L.idl_bam_open(device, data, len(data), C.byref(self.h), err, 512)
+        if slice is None:
+            rc = L.idl_bam_open(device, data, len(data), C.byref(self.h), err, 512)
+        else:
+            n = len(slice["ref_names"])
+            names = (C.c_char_p * n)(*[x.encode() for x in slice["ref_names"]])
+            lens = np.ascontiguousarray(slice["ref_len"], dtype=np.int64)
+            sl = BamSlice(n, names, lens.ctypes.data_as(C.POINTER(C.c_int64)), int(slice["first_record"]), int(slice["end_member"]), int(slice["end_offset"]))
+            rc = L.idl_bam_open_slice(device, data, len(data), C.byref(sl), C.byref(self.h), err, 512)
         if rc != 0:
             self.h = None
             raise IdlError("idl_bam_open: %s: %s" % (L.idl_strerror(rc).decode(), err.value.decode()))

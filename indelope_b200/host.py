@@ -370,6 +370,21 @@ class Rois:
             self.h = None
 
 
+def bai_target_span(bam, target):
+    """where one target's records lie in the file, from <bam>.bai: dict(file_begin, file_end, first_record, end_member, end_offset) or None when the index
+    lists no record for the target -- the arguments of cuda.Bam(bytes[file_begin:file_end], slice=...)"""
+    L = lib()
+    v = [C.c_uint64() for _ in range(5)]
+    err = C.create_string_buffer(512)
+    L.idlh_bai_target_span.argtypes = [C.c_char_p, C.c_int32] + [C.POINTER(C.c_uint64)] * 5 + [C.c_char_p, C.c_size_t]
+    rc = L.idlh_bai_target_span(str(bam).encode(), target, *[C.byref(x) for x in v], err, 512)
+    if rc < 0:
+        raise IOError(err.value.decode())
+    if rc == 1:
+        return None
+    return dict(zip(("file_begin", "file_end", "first_record", "end_member", "end_offset"), (int(x.value) for x in v)))
+
+
 def set_threads(n):
     """host threads of idlh_pack / idlh_pack_size (0 = $IDLH_THREADS, else every core up to 32)"""
     lib().idlh_set_threads(int(n))

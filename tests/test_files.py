@@ -195,6 +195,76 @@ def test_api_call_bam_equals_the_cli_and_the_oracle(files):
     rois = ds.sweep(min_reads=5)
     _, ovcf, cnt = orc.call(rois.arrays(), dump_level=0, **CALL)
     assert api.call_bam(fa, bam, max_reads=3000, **CALL) == rois.header() + ovcf
+    # target by target through the index: every target decoded from its own run of BGZF members (idl_bam_open_slice)
+    assert api.call_bam(fa, bam, max_reads=3000, by_target=True, **CALL) == rois.header() + ovcf
+
+
+@pytest.mark.gpu
+def test_one_target_from_its_slice_equals_the_whole_file(files):
+    """idl_bam_open_slice: records, per-target range and regions of target c decoded from the members the index points to == the same from the whole file"""
+    from indelope_b200 import cuda
+    ds, fa, bam = files
+    raw = open(bam, "rb").read()
+    whole = cuda.Bam(raw)
+    W = whole.fetch()
+    for c in range(whole.n_ref):
+        sp = host.bai_target_span(bam, c)
+        b = cuda.Bam(raw[sp["file_begin"]:sp["file_end"]], slice=dict(ref_names=whole.ref_names, ref_len=whole.ref_len, first_record=sp["first_record"],
+                                                                     end_member=sp["end_member"], end_offset=sp["end_offset"]))
+        lo, hi = b.ref_first[c], b.ref_first[c + 1]
+        wlo, whi = whole.ref_first[c], whole.ref_first[c + 1]
+        assert hi - lo == whi - wlo > 1000 and lo == 0 and b.n_records == hi   # the chain starts at the target's first record and ends behind its last
+        S = b.fetch()
+        for k in ("chrom", "start", "stop", "len", "mapq", "flag"):
+            assert np.array_equal(S[k][lo:hi], W[k][wlo:whi]), k
+        assert np.array_equal(S["bases"][S["seq_off"][lo]:S["seq_off"][hi]], W["bases"][W["seq_off"][wlo]:W["seq_off"][whi]])
+        assert np.array_equal(S["cigar"][int(S["cig_off"][lo]):int(S["cig_off"][hi])], W["cigar"][int(W["cig_off"][wlo]):int(W["cig_off"][whi])])
+        s1, s2 = b.sweep(c, min_read_coverage=5), whole.sweep(c, min_read_coverage=5)
+        for k in ("roi_start", "roi_end", "roi_n_reads"):
+            assert np.array_equal(s1[k], s2[k]), k
+        assert np.array_equal(s1["read_idx"] - lo, s2["read_idx"] - wlo)
+        b.close()
+    whole.close()
+    with pytest.raises(cuda.IdlError, match="truncated BAM record|malformed|first record|not coordinate sorted|follow records"):
+        sp = host.bai_target_span(bam, 1)
+        cuda.Bam(raw[sp["file_begin"]:sp["file_end"]], slice=dict(ref_names=["a", "b"], ref_len=[120_000, 120_000], first_record=sp["first_record"] + 3,
+                                                                 end_member=sp["end_member"], end_offset=sp["end_offset"]))
+
+
+def _records_of(data, at, end):
+    """(ref_id, pos) of the records in data[at:end] (an uncompressed BAM record stream)"""
+    out = []
+    while at < end:
+        bs, ref_id, pos = struct.unpack_from("<iii", data, at)
+        out.append((ref_id, pos)); at += 4 + bs
+    assert at == end
+    return out
+
+
+def test_target_span_from_the_index(files):
+    """idlh_bai_target_span: the run of BGZF members that holds one target's records and where its record chain starts and ends inside it -- checked by
+    inflating exactly that run with gzip and walking the records"""
+    ds, fa, bam = files
+    raw = open(bam, "rb").read()
+    whole = gzip.decompress(raw)
+    l_text, = struct.unpack_from("<i", whole, 4); at = 8 + l_text
+    n_ref, = struct.unpack_from("<i", whole, at); at += 4
+    for _ in range(n_ref):
+        l_name, = struct.unpack_from("<i", whole, at); at += 4 + l_name + 4
+    allrec = _records_of(whole, at, len(whole))
+    for c in range(2):
+        sp = host.bai_target_span(bam, c)
+        assert sp is not None and 0 <= sp["file_begin"] < sp["file_end"] <= len(raw)
+        run = raw[sp["file_begin"]:sp["file_end"]]
+        inflated = gzip.decompress(run)                                  # whole members: decompresses cleanly
+        # where the chain ends: the inflated size of the members in front of end_member + end_offset
+        end = len(gzip.decompress(run[:sp["end_member"]])) + sp["end_offset"] if sp["end_member"] else sp["end_offset"]
+        recs = _records_of(inflated, sp["first_record"], end)
+        assert recs == [r for r in allrec if r[0] == c] and len(recs) > 1000
+    with pytest.raises(IOError):
+        host.bai_target_span(bam, 7)
+    with pytest.raises(IOError):
+        host.bai_target_span(bam + ".nope", 0)
 
 
 def test_fasta_only_dataset_and_target_order(files, tmp_path):

@@ -248,6 +248,7 @@ int idl_release(idl_ctx *ctx, uint64_t ticket);
 const char *idl_strerror(int status);
 const char *idl_last_cuda_error(idl_ctx *ctx);
 int idl_device_count(void);
+int idl_device_memory(int device, size_t *free_bytes, size_t *total_bytes);   /* cudaMemGetInfo of the device (callers size their work by it) */
 
 /* ---- unit-level entry point: a batch of independent extension alignments through kernel 2 ------
  * Same contract as the reference's ksw_extz2_sse (src/ksw2/csrc/ksw2.h:54, flag = 0, m = 5 with the matrix of

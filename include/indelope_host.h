@@ -128,6 +128,8 @@ const char *idlh_dataset_chrom_name(const idlh_dataset *d, int32_t chrom);
 /* the device reads the BAM (idl_bam_open of indelope_cuda.h); the host keeps the reference sequences and turns what idl_bam_sweep / idl_bam_fetch
  * return into the idlh_rois that idlh_pack and idlh_vcf_records take */
 idlh_dataset *idlh_load_fasta(const char *fasta_path, char *err, size_t errlen);
+/* the FASTA's sequences in the order of the BAM header's targets; of the BAM only the header is read */
+idlh_dataset *idlh_load_targets(const char *fasta_path, const char *bam_path, char *err, size_t errlen);
 /* where one target's records lie in the file, from <bam>.bai: the run of whole BGZF members [*file_begin, *file_end) and the start / end of the record
  * chain inside it as idl_bam_open_slice takes them; 0 ok, 1 the index lists no record for the target, -1 error */
 int idlh_bai_target_span(const char *bam_path, int32_t target, uint64_t *file_begin, uint64_t *file_end, uint64_t *first_record, uint64_t *end_member,

@@ -408,6 +408,64 @@ int idlh_bai_target_span(const char *bam_path, int32_t target, uint64_t *file_be
 	return 0;
 }
 
+/* The FASTA's sequences ordered as the BAM header lists its targets, WITHOUT reading the BAM's records: only the first members of the file are read and
+ * inflated, as far as the header reaches (what `open(b, path)` + `b.hdr.targets` give the reference's main, src/indelope.nim:595-601).  For the path that
+ * decodes the records on the device target by target (idl_bam_open_slice).  Same checks and messages as idlh_load. */
+idlh_dataset *idlh_load_targets(const char *fasta_path, const char *bam_path, char *err, size_t errlen)
+{
+	idlh_dataset *D = new idlh_dataset();
+	memset(&D->P, 0, sizeof D->P);
+	std::string why;
+	auto fail = [&](const std::string &m) -> idlh_dataset* { set_err(err, errlen, m); delete D; return nullptr; };
+	if (!load_fasta(fasta_path, *D, why)) return fail(why);
+	FILE *f = fopen(bam_path, "rb");
+	if (!f) return fail(std::string("cannot open ") + bam_path);
+	std::vector<uint8_t> file, u; size_t cpos = 0; bool eof = false;
+	// inflate members from the front until `bytes` of the stream are there
+	auto need = [&](size_t bytes) -> bool {
+		while (u.size() < bytes) {
+			while (!eof && (file.size() - cpos < 18 || file.size() - cpos < (size_t)le16(file.data() + cpos + 16) + 1)) {
+				const size_t o = file.size(); file.resize(o + (1u << 20));
+				const size_t got = fread(file.data() + o, 1, 1u << 20, f);
+				file.resize(o + got);
+				if (got == 0) eof = true;
+			}
+			if (file.size() - cpos < 18) return false;
+			const uint8_t *h = file.data() + cpos;
+			if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4) || h[12] != 'B' || h[13] != 'C') return false;
+			const size_t csize = (size_t)le16(h + 16) + 1;
+			if (file.size() - cpos < csize || csize < 26) return false;
+			BgzfBlock b{cpos, csize, u.size(), le32(h + csize - 4)};
+			const size_t o = u.size(); u.resize(o + b.usize);
+			if (!bgzf_inflate_block(file, b, u.data() + o)) return false;
+			cpos += csize;
+		}
+		return true;
+	};
+	auto done = [&](idlh_dataset *r) { fclose(f); return r; };
+	if (!need(12) || memcmp(u.data(), "BAM\1", 4) != 0) return done(fail(std::string(bam_path) + ": not a BAM file"));
+	size_t at = 4;
+	const uint32_t l_text = le32(u.data() + at); at += 4;
+	if (!need(at + l_text + 4)) return done(fail("truncated BAM header"));
+	at += l_text;
+	const uint32_t n_ref = le32(u.data() + at); at += 4;
+	std::vector<std::string> names; std::vector<std::vector<uint8_t>> chroms;
+	for (uint32_t r = 0; r < n_ref; ++r) {
+		if (!need(at + 4)) return done(fail("truncated BAM reference list"));
+		const uint32_t l_name = le32(u.data() + at); at += 4;
+		if (l_name == 0 || !need(at + l_name + 4)) return done(fail("truncated BAM reference list"));
+		const std::string name((const char*)u.data() + at, l_name - 1); at += l_name;
+		const uint32_t l_ref = le32(u.data() + at); at += 4;
+		size_t k = 0;
+		while (k < D->names.size() && D->names[k] != name) ++k;
+		if (k == D->names.size()) return done(fail("BAM target " + name + " is not in the FASTA"));
+		if (D->chroms[k].size() != l_ref) return done(fail("BAM target " + name + " has a different length than the FASTA record"));
+		names.push_back(name); chroms.push_back(D->chroms[k]);
+	}
+	D->names.swap(names); D->chroms.swap(chroms);
+	return done(D);
+}
+
 /* the reference sequences alone (the device reads the BAM: idl_bam_open) */
 idlh_dataset *idlh_load_fasta(const char *fasta_path, char *err, size_t errlen)
 {

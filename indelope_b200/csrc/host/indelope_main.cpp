@@ -216,6 +216,99 @@ static int main_gpu_decode(const std::string &fa, const std::string &bam_path, i
 	return status;
 }
 
+// --gpu-decode for a file that does not fit in device memory as a whole (or with INDELOPE_BY_TARGET=1): target by target.  For every target the index
+// <bam>.bai says which run of BGZF members holds its records; that run is read, decoded on the device (idl_bam_open_slice), swept, called and dropped.
+// Regions keep gen_roi's order (targets in header order), so the dedup state carries over from target to target as in the reference's single loop.
+static int main_gpu_by_target(const std::string &fa, const std::string &bam_path, int min_reads, int min_ctg_len, int min_event_len, int device)
+{
+	char err[512] = {0};
+	const bool timing = getenv("INDELOPE_TIMING") != nullptr;
+	const double t_begin = now_s();
+	idl_params P;
+	idl_default_params(&P);
+	P.min_reads = min_reads; P.min_ctg_len = min_ctg_len; P.min_event_len = min_event_len;
+	idl_ctx *ctx = nullptr; int create_rc = IDL_OK;
+	std::thread creator([&]() { create_rc = idl_create(device, &P, &ctx); });
+	idlh_dataset *ref = idlh_load_targets(fa.c_str(), bam_path.c_str(), err, sizeof err);
+	creator.join();
+	if (!ref) { if (ctx) idl_destroy(ctx); return die("input", err); }
+	if (create_rc != IDL_OK) { idlh_dataset_free(ref); return die("libindelope_cuda", std::string(idl_strerror(create_rc)) + " (this program has no CPU path; it needs a CUDA device)"); }
+	idlh_rois *seqs = idlh_rois_from_arrays(ref, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+	const idlh_roiset *all = idlh_rois_view(seqs);
+	{ char *h = idlh_vcf_header(all); fputs(h, stdout); idlh_free(h); }   // echo header % [b.contig_header, "sample"], :599
+	std::vector<const char*> names((size_t)all->n_chroms); std::vector<int64_t> lens((size_t)all->n_chroms);
+	for (int32_t c = 0; c < all->n_chroms; ++c) { names[(size_t)c] = all->chrom_name[c]; lens[(size_t)c] = all->chrom_len[c]; }
+	FILE *f = fopen(bam_path.c_str(), "rb");
+	int status = f ? 0 : die("input", "cannot open " + bam_path);
+	idlh_vcf *writer = idlh_vcf_new();
+	double t_read = 0, t_open = 0, t_sweep = 0, t_call = 0; size_t n_regions = 0, n_targets = 0; uint64_t bytes = 0;
+	std::vector<uint8_t> run;
+	for (int32_t c = 0; c < all->n_chroms && !status; ++c) {
+		const std::string name = names[(size_t)c];
+		if (name == "hs37d5" || name.compare(0, 2, "GL") == 0) continue;   // skippable targets, :41-42
+		uint64_t fb = 0, fe = 0, first = 0, em = 0, eo = 0;
+		const int sr = idlh_bai_target_span(bam_path.c_str(), c, &fb, &fe, &first, &em, &eo, err, sizeof err);
+		if (sr < 0) { status = die("input", err); break; }
+		if (sr == 1) continue;   // no record on this target
+		double t1 = now_s();
+		run.resize((size_t)(fe - fb));
+		if (fseek(f, (long)fb, SEEK_SET) != 0 || fread(run.data(), 1, run.size(), f) != run.size()) { status = die("input", "cannot read " + bam_path); break; }
+		t_read += now_s() - t1; t1 = now_s(); bytes += run.size();
+		idl_bam_slice sl; memset(&sl, 0, sizeof sl);
+		sl.n_ref = all->n_chroms; sl.ref_name = names.data(); sl.ref_len = lens.data(); sl.first_record = first; sl.end_member = em; sl.end_offset = eo;
+		idl_bam *bam = nullptr; char berr[512] = {0};
+		const int orc = idl_bam_open_slice(device, run.data(), run.size(), &sl, &bam, berr, sizeof berr);
+		if (orc != IDL_OK) { status = die("input", bam_path + " (" + name + "): " + (berr[0] ? berr : idl_strerror(orc))); break; }
+		t_open += now_s() - t1; t1 = now_s();
+		idl_sweep_out *so = nullptr;
+		int r = idl_bam_sweep(bam, c, min_reads - 2 > 3 ? min_reads - 2 : 3, min_reads, 600, 0, &so);
+		if (r != IDL_OK) { status = die("idl_bam_sweep", idl_strerror(r)); idl_bam_close(bam); break; }
+		t_sweep += now_s() - t1; t1 = now_s();
+		++n_targets;
+		if (so->n_rois && idl_bam_set_reference(bam, c, all->chrom_seq[c], all->chrom_len[c]) != IDL_OK) status = die("idl_bam_set_reference", "could not place the reference on the device");
+		std::vector<int32_t> chrom(so->n_rois, c);
+		std::deque<Flight> inflight;
+		auto drain = [&]() -> bool {
+			const Flight fl = inflight.front(); inflight.pop_front();
+			const idl_results *res = nullptr;
+			const int w = idl_wait(ctx, fl.ticket, &res);
+			if (w != IDL_OK) { status = die("idl_wait", std::string(idl_strerror(w)) + " " + idl_last_cuda_error(ctx)); idlh_rois_free(fl.rois); return false; }
+			char *txt = idlh_vcf_records(writer, idlh_rois_view(fl.rois), 0, &P, res, 0, nullptr);
+			fputs(txt, stdout); idlh_free(txt);
+			idl_release(ctx, fl.ticket); idlh_rois_free(fl.rois);
+			return true;
+		};
+		size_t at_idx = 0;
+		for (size_t lo = 0; lo < so->n_rois && !status; ) {
+			size_t hi = lo; int64_t reads = 0;
+			while (hi < so->n_rois && (hi == lo || (reads + so->roi_n_reads[hi] <= 400000 && hi - lo < 20000))) reads += so->roi_n_reads[hi++];
+			idlh_rois *grp = idlh_rois_from_arrays(ref, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (int64_t)(hi - lo), chrom.data() + lo,
+			                                       so->roi_start + lo, so->roi_end + lo, so->roi_n_reads + lo, so->read_idx + at_idx);
+			if (inflight.size() >= (size_t)(P.n_streams > 0 ? P.n_streams : 1) && !drain()) { idlh_rois_free(grp); break; }
+			uint64_t ticket = 0;
+			r = idl_bam_submit(ctx, bam, hi - lo, chrom.data() + lo, so->roi_start + lo, so->roi_end + lo, so->roi_n_reads + lo, so->read_idx + at_idx, (uint32_t)(n_regions + lo), &ticket);
+			if (r != IDL_OK) { status = die("idl_bam_submit", std::string(idl_strerror(r)) + " " + idl_last_cuda_error(ctx)); idlh_rois_free(grp); break; }
+			inflight.push_back({grp, ticket});
+			at_idx += (size_t)reads; lo = hi;
+		}
+		while (!inflight.empty() && !status) if (!drain()) break;
+		while (!inflight.empty()) { idlh_rois_free(inflight.front().rois); inflight.pop_front(); }
+		n_regions += so->n_rois;
+		idl_sweep_free(so);
+		idl_bam_close(bam);
+		t_call += now_s() - t1;
+	}
+	if (f) fclose(f);
+	if (timing)
+		fprintf(stderr, "indelope timing (gpu decode, target by target): %zu targets with records, %.1f MB read in %.3f s, idl_bam_open_slice %.3f s, idl_bam_sweep %.3f s, "
+		        "build + call + vcf %.3f s, total %.3f s, regions %zu\n", n_targets, bytes / 1e6, t_read, t_open, t_sweep, t_call, now_s() - t_begin, n_regions);
+	idlh_vcf_free(writer);
+	idlh_rois_free(seqs);
+	idl_destroy(ctx);
+	idlh_dataset_free(ref);
+	return status;
+}
+
 int main(int argc, char **argv)
 {
 	int min_reads = 3, min_ctg_len = 73, min_event_len = 4, threads = 1, device = 0;
@@ -250,7 +343,18 @@ int main(int argc, char **argv)
 	char err[512] = {0};
 	const bool timing = getenv("INDELOPE_TIMING") != nullptr;
 	const double t_begin = now_s(); double t_sweep = 0, t_pack = 0, t_wait = 0, t_vcf = 0, t0;
-	if (gpu_sweep) return main_gpu_decode(pos[0], pos[1], min_reads, min_ctg_len, min_event_len, device);
+	if (gpu_sweep) {
+		// the whole file on the device when it fits (the file and ~5x its size: inflated stream + record arrays), else target by target through the index
+		bool by_target = getenv("INDELOPE_BY_TARGET") != nullptr;
+		if (!by_target) {
+			size_t free_b = 0, total_b = 0;
+			FILE *bf = fopen(pos[1].c_str(), "rb");
+			if (bf && idl_device_memory(device, &free_b, &total_b) == IDL_OK) { fseek(bf, 0, SEEK_END); const long n = ftell(bf); by_target = n > 0 && (size_t)n > free_b / 8; }
+			if (bf) fclose(bf);
+		}
+		return by_target ? main_gpu_by_target(pos[0], pos[1], min_reads, min_ctg_len, min_event_len, device)
+		                 : main_gpu_decode(pos[0], pos[1], min_reads, min_ctg_len, min_event_len, device);
+	}
 	// gen_roi(b, target, min_read_coverage=min_reads, min_event_support=max(3, min_reads-2)), src/indelope.nim:602; the BAM
 	// is swept front to back in bounded memory (idlh_stream_*), a group of regions at a time
 	idlh_stream *in = idlh_stream_open(pos[0].c_str(), pos[1].c_str(), threads, min_reads - 2 > 3 ? min_reads - 2 : 3, min_reads, 600, err, sizeof err);

@@ -162,6 +162,15 @@ int idl_device_count(void)
 	return n;
 }
 
+int idl_device_memory(int device, size_t *free_bytes, size_t *total_bytes)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return IDL_E_NO_DEVICE;
+	if (device < 0 || device >= n || !free_bytes || !total_bytes) return IDL_E_ARG;
+	if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(free_bytes, total_bytes) != cudaSuccess) return IDL_E_CUDA;
+	return IDL_OK;
+}
+
 int idl_create(int device, const idl_params *p, idl_ctx **out)
 {
 	if (!out || !p) return IDL_E_ARG;

@@ -185,6 +185,10 @@ def test_cli_gpu_decode_gives_the_same_vcf(files):
     rois = ds.sweep(min_reads=5)
     _, ovcf, cnt = orc.call(rois.arrays(), dump_level=0, **CALL)
     assert r.stdout == rois.header() + ovcf
+    # ... and target by target through the index (what the binary does by itself for a file that does not fit in device memory)
+    r = subprocess.run([exe, "--gpu-decode", "--min-event-len", "5", "--min-reads", "5", fa, bam], capture_output=True, text=True, env=dict(os.environ, INDELOPE_BY_TARGET="1"))
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == rois.header() + ovcf
 
 
 @pytest.mark.gpu
@@ -265,6 +269,27 @@ def test_target_span_from_the_index(files):
         host.bai_target_span(bam, 7)
     with pytest.raises(IOError):
         host.bai_target_span(bam + ".nope", 0)
+
+
+def test_targets_from_the_header_alone(files, tmp_path):
+    """idlh_load_targets: the FASTA's sequences in the BAM header's order; of the BAM only the header members are read"""
+    import ctypes as C
+    ds, fa, bam = files
+    L = host.lib()
+    L.idlh_load_targets.restype = C.c_void_p
+    L.idlh_load_targets.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+    err = C.create_string_buffer(512)
+    h = L.idlh_load_targets(fa.encode(), bam.encode(), err, 512)
+    assert h, err.value
+    d = host.Dataset(_handle=h)
+    names, seqs = d.sequences()
+    assert names == ["chrS1", "chrS2"] and d.n_reads == 0 and len(seqs[1]) == 120_000
+    cut = tmp_path / "head.bam"
+    cut.write_bytes(open(bam, "rb").read()[:70_000])          # the header survives a file cut off behind its first members
+    h2 = L.idlh_load_targets(fa.encode(), str(cut).encode(), err, 512)
+    assert h2
+    host.Dataset(_handle=h2)
+    assert not L.idlh_load_targets(fa.encode(), fa.encode(), err, 512) and b"not a BAM" in err.value
 
 
 def test_fasta_only_dataset_and_target_order(files, tmp_path):

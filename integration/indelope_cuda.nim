@@ -123,6 +123,12 @@ type
     ms_h2d*, ms_inflate*, ms_parse*: cfloat
     n_chunks*: uint32
 
+  IdlBamSlice* {.bycopy.} = object         ## idl_bam_slice: a run of BGZF members holding one target's records (found through the .bai)
+    n_ref*: int32
+    ref_name*: cstringArray
+    ref_len*: ptr UncheckedArray[int64]
+    first_record*, end_member*, end_offset*: uint64
+
   IdlBamReads* {.bycopy.} = object         ## idl_bam_reads: what callsemble reads of a cached Record (src/indelope.nim:216-222)
     n*: csize_t
     chrom*, start*, stop*, len*: ptr UncheckedArray[int32]
@@ -166,6 +172,8 @@ proc idl_sweep*(device: cint, inp: ptr IdlSweepIn, min_event_support, min_read_c
 proc idl_sweep_free*(o: ptr IdlSweepOut) {.importc.}
 # the BAM on the device: replaces hts-nim's open / querys / Record accessors for the sweep (src/indelope.nim:595, :527, :40-47, :430-452)
 proc idl_bam_open*(device: cint, file: ptr uint8, file_len: csize_t, bam: ptr IdlBam, err: cstring, errlen: csize_t): cint {.importc.}
+proc idl_bam_open_slice*(device: cint, members: ptr uint8, len: csize_t, slice: ptr IdlBamSlice, bam: ptr IdlBam, err: cstring, errlen: csize_t): cint {.importc.}
+proc idl_device_memory*(device: cint, free_bytes, total_bytes: ptr csize_t): cint {.importc.}
 proc idl_bam_get_info*(bam: IdlBam): ptr IdlBamInfo {.importc.}
 proc idl_bam_close*(bam: IdlBam) {.importc.}
 proc idl_bam_sweep*(bam: IdlBam, target: int32, min_event_support, min_read_coverage, max_read_coverage: int32, flags: uint32,

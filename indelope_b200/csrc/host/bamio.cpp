@@ -17,6 +17,7 @@
 #include <condition_variable>
 #include <deque>
 #include <mutex>
+#include <sys/stat.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -366,32 +367,46 @@ int idlh_write_bam(const idlh_dataset *d, const char *path, int level)
 int idlh_bai_target_span(const char *bam_path, int32_t target, uint64_t *file_begin, uint64_t *file_end, uint64_t *first_record, uint64_t *end_member,
                          uint64_t *end_offset, char *err, size_t errlen)
 {
-	std::vector<uint8_t> bai; std::string why;
-	if (!read_file((std::string(bam_path) + ".bai").c_str(), bai, why)) { set_err(err, errlen, why + " (no index: write one with idlh_write_bam or samtools index)"); return -1; }
-	if (bai.size() < 8 || memcmp(bai.data(), "BAI\1", 4) != 0) { set_err(err, errlen, "not a BAI index"); return -1; }
-	size_t ia = 4;
-	auto rd32 = [&](uint32_t &x) -> bool { if (ia + 4 > bai.size()) return false; x = le32(bai.data() + ia); ia += 4; return true; };
-	auto rd64 = [&](uint64_t &x) -> bool { if (ia + 8 > bai.size()) return false; x = (uint64_t)le32(bai.data() + ia) | (uint64_t)le32(bai.data() + ia + 4) << 32; ia += 8; return true; };
-	uint32_t n_ref = 0;
-	if (!rd32(n_ref)) { set_err(err, errlen, "truncated index"); return -1; }
-	if (target < 0 || (uint32_t)target >= n_ref) { set_err(err, errlen, "the index has no such target"); return -1; }
-	uint64_t vmin = ~0ULL, vmax = 0;
-	for (uint32_t r = 0; r <= (uint32_t)target; ++r) {
-		uint32_t n_bin = 0;
-		if (!rd32(n_bin)) { set_err(err, errlen, "truncated index"); return -1; }
-		for (uint32_t b = 0; b < n_bin; ++b) {
-			uint32_t bin = 0, n_chunk = 0;
-			if (!rd32(bin) || !rd32(n_chunk)) { set_err(err, errlen, "truncated index"); return -1; }
-			for (uint32_t c = 0; c < n_chunk; ++c) {
-				uint64_t a = 0, z = 0;
-				if (!rd64(a) || !rd64(z)) { set_err(err, errlen, "truncated index"); return -1; }
-				if (r == (uint32_t)target && bin != 37450u) { vmin = std::min(vmin, a); vmax = std::max(vmax, z); }   // 37450: the metadata pseudo-bin of samtools
+	// the spans of every target of the index read last (a header with thousands of targets asks for them one after the other)
+	static std::mutex mu; static std::string cached_path; static std::vector<std::pair<uint64_t, uint64_t>> spans;
+	std::lock_guard<std::mutex> lock(mu);
+	static long long cached_stamp = -1;
+	long long stamp = -1;
+	{ struct stat sb; if (stat((std::string(bam_path) + ".bai").c_str(), &sb) == 0) stamp = (long long)sb.st_mtime * 1000003LL + (long long)sb.st_size; }
+	if (cached_path != bam_path || stamp != cached_stamp) {
+		cached_stamp = stamp;
+		cached_path.clear(); spans.clear();
+		std::vector<uint8_t> bai; std::string why;
+		if (!read_file((std::string(bam_path) + ".bai").c_str(), bai, why)) { set_err(err, errlen, why + " (no index: write one with idlh_write_bam or samtools index)"); return -1; }
+		if (bai.size() < 8 || memcmp(bai.data(), "BAI\1", 4) != 0) { set_err(err, errlen, "not a BAI index"); return -1; }
+		size_t ia = 4;
+		auto rd32 = [&](uint32_t &x) -> bool { if (ia + 4 > bai.size()) return false; x = le32(bai.data() + ia); ia += 4; return true; };
+		auto rd64 = [&](uint64_t &x) -> bool { if (ia + 8 > bai.size()) return false; x = (uint64_t)le32(bai.data() + ia) | (uint64_t)le32(bai.data() + ia + 4) << 32; ia += 8; return true; };
+		uint32_t n_ref = 0;
+		if (!rd32(n_ref)) { set_err(err, errlen, "truncated index"); return -1; }
+		std::vector<std::pair<uint64_t, uint64_t>> sp;
+		for (uint32_t r = 0; r < n_ref; ++r) {
+			uint64_t lo = ~0ULL, hi = 0;
+			uint32_t n_bin = 0;
+			if (!rd32(n_bin)) { set_err(err, errlen, "truncated index"); return -1; }
+			for (uint32_t b = 0; b < n_bin; ++b) {
+				uint32_t bin = 0, n_chunk = 0;
+				if (!rd32(bin) || !rd32(n_chunk)) { set_err(err, errlen, "truncated index"); return -1; }
+				for (uint32_t c = 0; c < n_chunk; ++c) {
+					uint64_t a = 0, z = 0;
+					if (!rd64(a) || !rd64(z)) { set_err(err, errlen, "truncated index"); return -1; }
+					if (bin != 37450u) { lo = std::min(lo, a); hi = std::max(hi, z); }   // 37450: the metadata pseudo-bin of samtools
+				}
 			}
+			uint32_t n_intv = 0;
+			if (!rd32(n_intv) || ia + (size_t)n_intv * 8 > bai.size()) { set_err(err, errlen, "truncated index"); return -1; }
+			ia += (size_t)n_intv * 8;
+			sp.push_back({lo, hi});
 		}
-		uint32_t n_intv = 0;
-		if (!rd32(n_intv)) { set_err(err, errlen, "truncated index"); return -1; }
-		ia += (size_t)n_intv * 8;
+		spans.swap(sp); cached_path = bam_path;
 	}
+	if (target < 0 || (size_t)target >= spans.size()) { set_err(err, errlen, "the index has no such target"); return -1; }
+	const uint64_t vmin = spans[(size_t)target].first, vmax = spans[(size_t)target].second;
 	if (vmin == ~0ULL || vmax <= vmin) return 1;
 	*file_begin = vmin >> 16; *first_record = vmin & 0xffff;
 	const uint64_t ce = vmax >> 16, ue = vmax & 0xffff;

@@ -86,7 +86,6 @@ __device__ __forceinline__ uint32_t ld32u(const uint8_t *u, size_t o)
 	const uint32_t *w = (const uint32_t*)(u + (o & ~(size_t)3));
 	return __funnelshift_r(w[0], w[1], (unsigned)(o & 3) * 8);
 }
-__device__ __forceinline__ uint32_t ld16u(const uint8_t *u, size_t o) { return ld32u(u, o) & 0xffffu; }
 
 // necessary conditions of a BAM alignment record at offset o (SAM spec 4.2); true records always pass
 __device__ bool bam_plausible(const uint8_t *u, size_t total, size_t o, int32_t n_ref, const int32_t *ref_len, size_t *next)

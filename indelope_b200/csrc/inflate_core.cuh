@@ -251,15 +251,15 @@ IDL_INF_FN int inflate_member(int lane, Tables &T, const uint8_t *base, size_t i
 			for (;;) {
 				bits_refill(B);
 				const uint32_t e = decode_entry(B, T.lit_fast, LIT_BITS, A_LIT, T.lit_sym, T.lit_count);
-				const uint32_t kind = (e >> 8) & 3u;
-				if (kind == K_LIT) {
+				// (bit tests, not a switch on the kind: the compiler turned the switch into a jump table and an indirect branch per symbol)
+				if (!(e & 0x300u)) {
 					if (!e) return INF_E_SYMBOL;
 					if (op >= out_len) return INF_E_OUTPUT;
 					if (lane == 0) { out[op] = (uint8_t)(e >> 16); if (RING != 0) T.ring[op & (RING - 1)] = (uint8_t)(e >> 16); }
 					++op;
 					continue;
 				}
-				if (kind != K_BASE) { if (kind == K_END) break; return INF_E_SYMBOL; }
+				if (e & 0x200u) { if (e & 0x100u) return INF_E_SYMBOL; break; }   // K_BAD : K_END
 				const uint32_t len = (e >> 16) + bits_take(B, (int)((e >> 4) & 15u));
 				bits_refill(B);
 				const uint32_t d = decode_entry(B, T.dist_fast, DIST_BITS, A_DIST, T.dist_sym, T.dist_count);

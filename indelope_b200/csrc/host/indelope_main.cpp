@@ -238,22 +238,48 @@ static int main_gpu_by_target(const std::string &fa, const std::string &bam_path
 	{ char *h = idlh_vcf_header(all); fputs(h, stdout); idlh_free(h); }   // echo header % [b.contig_header, "sample"], :599
 	std::vector<const char*> names((size_t)all->n_chroms); std::vector<int64_t> lens((size_t)all->n_chroms);
 	for (int32_t c = 0; c < all->n_chroms; ++c) { names[(size_t)c] = all->chrom_name[c]; lens[(size_t)c] = all->chrom_len[c]; }
-	FILE *f = fopen(bam_path.c_str(), "rb");
-	int status = f ? 0 : die("input", "cannot open " + bam_path);
+	int status = 0;
 	idlh_vcf *writer = idlh_vcf_new();
 	double t_read = 0, t_open = 0, t_sweep = 0, t_call = 0; size_t n_regions = 0, n_targets = 0; uint64_t bytes = 0;
-	std::vector<uint8_t> run;
-	for (int32_t c = 0; c < all->n_chroms && !status; ++c) {
+	// the targets that have records, and a reader one target ahead: while the device decodes and calls target k, a thread reads the run of members of
+	// target k + 1 from the file
+	struct Run { int32_t c = -1; uint64_t first = 0, em = 0, eo = 0; std::vector<uint8_t> bytes; std::string error; double seconds = 0; };
+	std::vector<int32_t> todo;
+	for (int32_t c = 0; c < all->n_chroms; ++c) {
 		const std::string name = names[(size_t)c];
 		if (name == "hs37d5" || name.compare(0, 2, "GL") == 0) continue;   // skippable targets, :41-42
-		uint64_t fb = 0, fe = 0, first = 0, em = 0, eo = 0;
-		const int sr = idlh_bai_target_span(bam_path.c_str(), c, &fb, &fe, &first, &em, &eo, err, sizeof err);
-		if (sr < 0) { status = die("input", err); break; }
-		if (sr == 1) continue;   // no record on this target
+		todo.push_back(c);
+	}
+	auto load = [&](int32_t c, Run *R) {
+		const double t1 = now_s();
+		char e2[512] = {0};
+		uint64_t fb = 0, fe = 0;
+		R->c = c; R->bytes.clear(); R->error.clear();
+		const int sr = idlh_bai_target_span(bam_path.c_str(), c, &fb, &fe, &R->first, &R->em, &R->eo, e2, sizeof e2);
+		if (sr < 0) { R->error = e2; return; }
+		if (sr == 1) { R->c = -2; return; }   // no record on this target
+		FILE *f = fopen(bam_path.c_str(), "rb");
+		if (!f) { R->error = "cannot open " + bam_path; return; }
+		R->bytes.resize((size_t)(fe - fb));
+		if (fseek(f, (long)fb, SEEK_SET) != 0 || fread(R->bytes.data(), 1, R->bytes.size(), f) != R->bytes.size()) R->error = "cannot read " + bam_path;
+		fclose(f);
+		R->seconds = now_s() - t1;
+	};
+	Run runs[2]; std::thread reader;
+	if (!todo.empty()) reader = std::thread(load, todo[0], &runs[0]);
+	for (size_t ti = 0; ti < todo.size() && !status; ++ti) {
+		const int32_t c = todo[ti];
+		const std::string name = names[(size_t)c];
 		double t1 = now_s();
-		run.resize((size_t)(fe - fb));
-		if (fseek(f, (long)fb, SEEK_SET) != 0 || fread(run.data(), 1, run.size(), f) != run.size()) { status = die("input", "cannot read " + bam_path); break; }
-		t_read += now_s() - t1; t1 = now_s(); bytes += run.size();
+		reader.join();                                   // the run of this target
+		Run &R = runs[ti & 1];
+		if (ti + 1 < todo.size()) reader = std::thread(load, todo[ti + 1], &runs[(ti + 1) & 1]);
+		t_read += now_s() - t1;                          // (what the call waited for the reader)
+		if (!R.error.empty()) { status = die("input", R.error); break; }
+		if (R.c == -2) continue;
+		t1 = now_s(); bytes += R.bytes.size();
+		const std::vector<uint8_t> &run = R.bytes;
+		const uint64_t first = R.first, em = R.em, eo = R.eo;
 		idl_bam_slice sl; memset(&sl, 0, sizeof sl);
 		sl.n_ref = all->n_chroms; sl.ref_name = names.data(); sl.ref_len = lens.data(); sl.first_record = first; sl.end_member = em; sl.end_offset = eo;
 		idl_bam *bam = nullptr; char berr[512] = {0};
@@ -298,9 +324,9 @@ static int main_gpu_by_target(const std::string &fa, const std::string &bam_path
 		idl_bam_close(bam);
 		t_call += now_s() - t1;
 	}
-	if (f) fclose(f);
+	if (reader.joinable()) reader.join();
 	if (timing)
-		fprintf(stderr, "indelope timing (gpu decode, target by target): %zu targets with records, %.1f MB read in %.3f s, idl_bam_open_slice %.3f s, idl_bam_sweep %.3f s, "
+		fprintf(stderr, "indelope timing (gpu decode, target by target): %zu targets with records, %.1f MB read (a reader thread one target ahead; waited %.3f s for it), idl_bam_open_slice %.3f s, idl_bam_sweep %.3f s, "
 		        "build + call + vcf %.3f s, total %.3f s, regions %zu\n", n_targets, bytes / 1e6, t_read, t_open, t_sweep, t_call, now_s() - t_begin, n_regions);
 	idlh_vcf_free(writer);
 	idlh_rois_free(seqs);

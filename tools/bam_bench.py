@@ -33,13 +33,15 @@ def main():
             t0 = time.time(); full = host.Dataset.load(fa, bam, threads=th); out["host_load_s_%dthr" % th] = round(time.time() - t0, 3)
             del full
     cuda.Bam(data).close()
-    best = None
+    best, walls = None, []
     for _ in range(reps):
         t0 = time.time(); b = cuda.Bam(data); dt = time.time() - t0
-        if best is None or b.info["ms_inflate"] < best["ms_inflate"]:
+        walls.append(round(dt, 4))
+        if best is None or dt < best["wall_s"]:
             best = dict(b.info, wall_s=round(dt, 4), n_records=b.n_records)
         b.close()
-    out["idl_bam_open"] = best
+    out["idl_bam_open"] = best          # the repetition with the shortest wall time
+    out["wall_s_all_reps"] = walls
     out["copy_inflate_gbs_in"] = round(best["file_bytes"] / best["ms_inflate"] / 1e6, 2)
     out["copy_inflate_gbs_out"] = round(best["inflated_bytes"] / best["ms_inflate"] / 1e6, 2)
     out["parse_gbs"] = round(best["inflated_bytes"] / best["ms_parse"] / 1e6, 2)

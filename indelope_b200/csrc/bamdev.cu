@@ -505,7 +505,9 @@ struct idl_bam {
 	// last are done (`done`, recorded on that batch's stream behind its pack kernels): several batches are in flight on different lanes
 	struct ScratchSet { void *p[8] = {}; size_t cap[8] = {}; cudaEvent_t done = nullptr; bool used = false; };
 	ScratchSet sets[4]; unsigned next_set = 0;
-	std::vector<void*> owned;   // every cudaMalloc of this object
+	std::vector<void*> owned;   // every stream-ordered allocation of this object (cudaMallocAsync on `st` from the device's default pool, which keeps
+	                            // freed memory: a process that opens BAM after BAM -- one per target -- saw cudaMalloc / cudaFree of the gigabyte
+	                            // buffers take 0.3-0.7 s now and then)
 	idl_bam_info info = {};
 	std::vector<std::string> names; std::vector<const char*> name_ptrs; std::vector<int64_t> ref_len, ref_first;
 	std::string header;
@@ -517,7 +519,9 @@ void idl_bam_close(idl_bam *b)
 {
 	if (!b) return;
 	cudaSetDevice(b->device);
-	for (void *p : b->owned) cudaFree(p);
+	cudaDeviceSynchronize();   // nothing on any stream still reads the buffers
+	if (b->st) { for (void *p : b->owned) cudaFreeAsync(p, b->st); cudaStreamSynchronize(b->st); }
+	else for (void *p : b->owned) cudaFree(p);
 	for (auto &S : b->sets) { for (void *p : S.p) if (p) cudaFree(p); if (S.done) cudaEventDestroy(S.done); }
 	for (const uint8_t *p : b->ref_seq) if (p) cudaFree((void*)p);
 	if (b->st) cudaStreamDestroy(b->st);
@@ -585,13 +589,17 @@ static int bam_open_impl(int device, const uint8_t *file, size_t file_len, const
 	cudaEvent_t ev[4] = {};
 	std::string why;
 #define BCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { why = std::string(#call) + ": " + cudaGetErrorString(e_); rc = IDL_E_CUDA; goto done; } } while (0)
-#define BALLOC(ptr, bytes) do { void *p_ = nullptr; BCK(cudaMalloc(&p_, (bytes) ? (bytes) : 16)); b->owned.push_back(p_); ptr = (decltype(ptr))p_; } while (0)
+#define BALLOC(ptr, bytes) do { void *p_ = nullptr; BCK(cudaMallocAsync(&p_, (bytes) ? (bytes) : 16, b->st)); b->owned.push_back(p_); ptr = (decltype(ptr))p_; } while (0)
 #define BFAIL(msg) do { why = (msg); rc = IDL_E_FORMAT; goto done; } while (0)
 	{
 		int n_sm = 0;
 		BCK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
 		BCK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
 		cudaStream_t st = b->st;
+		{
+			cudaMemPool_t pool;   // freed buffers stay with the pool instead of going back to the driver
+			if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { unsigned long long thr = ~0ULL; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
+		}
 		for (auto &e : ev) BCK(cudaEventCreate(&e));
 		Member *d_members = nullptr; unsigned long long *d_err = nullptr; unsigned *d_next = nullptr;
 		BALLOC(b->d_comp, file_len + 512); BALLOC(b->d_out, total + 64); BALLOC(d_members, members.size() * sizeof(Member)); BALLOC(d_err, 64); BALLOC(d_next, 4 * 64);
@@ -804,7 +812,7 @@ static int bam_open_impl(int device, const uint8_t *file, size_t file_len, const
 		b->info.header_text = b->header.c_str(); b->info.header_len = b->header.size();
 		// the compressed bytes are not needed any more: the resident footprint is the inflated stream + ~60 bytes per record
 		for (auto it = b->owned.begin(); it != b->owned.end(); ++it) if (*it == (void*)b->d_comp) { b->owned.erase(it); break; }
-		cudaFree(b->d_comp); b->d_comp = nullptr;
+		cudaFreeAsync(b->d_comp, st); b->d_comp = nullptr;
 		tw[5] = now();
 		if (timing)
 			fprintf(stderr, "idl_bam_open: member index %.1f ms, context %.1f ms, stream + allocations %.1f ms, h2d + inflate + header %.1f ms, boundaries %.1f ms, fields + cigars %.1f ms\n",
